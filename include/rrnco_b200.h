@@ -1,0 +1,235 @@
+/*
+ * rrnco_b200.h -- C ABI of librrnco_b200.so: the B200-native (sm_100a) construction-rollout hot path of
+ * ai4co/real-routing-nco (RRNCO).
+ *
+ * The reference has NO FFI / plugin / operator registry: its boundary is the Python
+ * class API of rl4co-style envs and of RRNetDecoder / RRNetPolicy.  Each entry point below is therefore
+ * what a binding for ONE reference method would call; the reference interface it replaces is cited as
+ * file:line (paths relative to the upstream repo root).  `rrnco_b200/` (Python) mirrors the reference
+ * classes on top of this ABI via ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - extern "C", C99 types only; every pointer is a DEVICE pointer unless its name starts with `h_`.
+ *  - The library never allocates or frees caller-visible memory and keeps no global mutable state.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises.
+ *  - Return value: 0 = RRNCO_OK, negative = error (see rrnco_strerror).  Device-side conditions the
+ *    reference raises as Python exceptions (NaN logits, infeasible action) are OR-ed into a caller-owned
+ *    sticky `status` word (RRNCO_DEV_*), read back by the host once per rollout.
+ *  - "Reference layout": flat rollout index r = s * n_inst + b (repeat-major batchify,
+ *    rrnco/models/decoding.py:189, rrnco/models/decoder.py:203), int64 nodes/actions, bool/uint8 masks,
+ *    fp32 everything else -- exactly the td tensors of SURVEY.md App. B, passed by data_ptr().
+ *  - `data_rows`: instance data (demand, matrices, time windows ...) may be given un-replicated; rollout r
+ *    uses row r % data_rows.  The reference's batchified td has data_rows == R.
+ */
+#ifndef RRNCO_B200_H
+#define RRNCO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRNCO_ABI_VERSION 1
+
+/* status codes */
+#define RRNCO_OK 0
+#define RRNCO_ERR_BAD_ARG (-1)        /* null pointer / non-positive size / misaligned pointer */
+#define RRNCO_ERR_UNSUPPORTED (-2)    /* variant or size not supported by this build (e.g. N > RRNCO_MAX_NODES_FUSED) */
+#define RRNCO_ERR_CUDA (-3)           /* a CUDA runtime call failed (launch error) */
+
+/* bits of the device-side sticky status word */
+#define RRNCO_DEV_NAN_LOGITS 1u       /* "Logits contain NaNs"           rrnco/models/decoder.py:303-304 */
+#define RRNCO_DEV_INFEASIBLE 2u       /* "infeasible action selected"    rrnco/models/decoding.py:278-280 */
+#define RRNCO_DEV_NO_FEASIBLE 4u      /* fully-masked row (never happens upstream: depot always feasible) */
+
+#define RRNCO_ENV_ATSP 0
+#define RRNCO_ENV_RCVRP 1
+#define RRNCO_ENV_RCVRPTW 2
+
+#define RRNCO_DECODE_GREEDY 0         /* argmax, ties -> lowest index     rrnco/models/decoding.py:272-282 */
+#define RRNCO_DECODE_SAMPLING 1       /* Gumbel-max sample of softmax     rrnco/models/decoding.py:284-298 */
+#define RRNCO_DECODE_EVALUATE 2       /* actions given, log-probs out     rrnco/models/decoding.py:386-399 */
+
+#define RRNCO_EMBED_DIM 128           /* experiment/rrnet.yaml: embed_dim 128, 8 heads */
+#define RRNCO_NUM_HEADS 8
+#define RRNCO_MAX_NODES_FUSED 128     /* fused decode kernel: one key tile; larger N -> RRNCO_ERR_UNSUPPORTED */
+
+int rrnco_abi_version(void);
+const char* rrnco_strerror(int code);
+
+/* Precision of the in-kernel contractions of the fused decoder kernels (process-wide, set before use):
+ *   3 = 3xTF32 error-compensated tensor-core passes, fp32-faithful (default; the reference's CPU / fp32 path)
+ *   1 = one TF32 pass (analogue of the reference's `torch.autocast("cuda")` inference path, test.py:182-185) */
+int rrnco_set_precision(int32_t passes);
+
+/* ------------------------------------------------------------------------------------------------
+ * env.reset: per-instance min-max normalisation of the distance matrix
+ *   replaces RCVRPEnv._reset rrnco/envs/rcvrp/env.py:138-145 (same lines in atsp/env.py:113-120,
+ *   rmtvrp/env.py:271-280):  out = (d - min) / (max - min + 1e-6), min/max over the whole [N,N] matrix.
+ * ---------------------------------------------------------------------------------------------- */
+int rrnco_minmax_normalize(int64_t n_mat, int32_t n_nodes, const float* dist_in, float* dist_out,
+                           float* min_out, float* max_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Instance sub-sampling gather: out[b,i,j] = (float) M[idx[b,i], idx[b,j]]
+ *   replaces Real_World_Sampler.sample rrnco/envs/rcvrp/sampler.py:84-90 (+ the fp32 cast of
+ *   rrnco/envs/rcvrp/generator_lazy.py:300).  M is the float64 city matrix [L,L]
+ *   (data_generation/utilities/create_dataset.py:169-174); idx is int32 [batch, n].
+ *   If normalize != 0 the min-max normalisation of env.reset is fused (min_out / max_out filled);
+ *   min_out / max_out may be NULL when normalize == 0.
+ * ---------------------------------------------------------------------------------------------- */
+int rrnco_gather_submatrix(const double* city_matrix, int32_t city_len, const int32_t* idx, int64_t batch,
+                           int32_t n, float* out, int32_t normalize, float* min_out, float* max_out,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ATSPEnv._step  rrnco/envs/atsp/env.py:79-105   (reference layout, R rollouts)
+ *   mask_out = mask_in with action cleared; done = no node left; first_node latched when *step_i == 0
+ *   (step_i: DEVICE pointer to td["i"]; upstream reads it with a blocking .item(), atsp/env.py:82).
+ *   In/out pointers may alias.
+ * ---------------------------------------------------------------------------------------------- */
+int rrnco_atsp_step(int64_t R, int32_t n_nodes, const int64_t* action, const int64_t* step_i,
+                    const uint8_t* mask_in, const int64_t* first_in, uint8_t* mask_out, int64_t* first_out,
+                    int64_t* current_out, uint8_t* done_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RCVRPEnv._step + get_action_mask  rrnco/envs/rcvrp/env.py:90-122, 183-195
+ *   demand [data_rows, N-1] (customers only, already / capacity), capacity [data_rows_cap] broadcast by
+ *   r % cap_rows.  If action == NULL only the mask is recomputed from (visited_in, used_in, current_in)
+ *   (= the static get_action_mask).  visited is uint8 [R,N], mask bool [R,N].
+ * ---------------------------------------------------------------------------------------------- */
+int rrnco_rcvrp_step(int64_t R, int32_t n_nodes, int64_t data_rows, const int64_t* action,
+                     const float* demand, const float* capacity, int64_t cap_rows, const float* used_in,
+                     const uint8_t* visited_in, const int64_t* current_in, float* used_out,
+                     uint8_t* visited_out, int64_t* current_out, uint8_t* done_out, uint8_t* mask_out,
+                     void* stream);
+
+/* Instance data shared by the RCVRPTW step and the fused kernels (row = index % data_rows). Unused members NULL. */
+typedef struct rrnco_instance_data {
+  int64_t data_rows;
+  const float* distance;        /* [rows,N,N] normalised (env.reset output) */
+  const float* duration;        /* [rows,N,N] rcvrptw */
+  const float* demand;          /* rcvrp: [rows,N-1]; rcvrptw: demand_linehaul [rows,N] depot-padded */
+  const float* demand_backhaul; /* rcvrptw [rows,N] */
+  const float* time_windows;    /* rcvrptw [rows,N,2] */
+  const float* service_time;    /* rcvrptw [rows,N] */
+  const float* vehicle_capacity;/* [rows] */
+  const float* distance_limit;  /* rcvrptw [rows] */
+  const uint8_t* open_route;    /* rcvrptw [rows] */
+  const float* backhaul_class;  /* rcvrptw [rows] */
+  const float* min_distance;    /* [rows] for the de-normalised reward (may be NULL) */
+  const float* max_distance;    /* [rows] */
+} rrnco_instance_data_t;
+
+/* ------------------------------------------------------------------------------------------------
+ * RMTVRPEnv._step + get_action_mask  rrnco/envs/rmtvrp/env.py:155-215, 343-428  (all O/B/L/MB/TW branches)
+ *   data->demand is demand_linehaul [rows,N]; every rcvrptw member of `data` must be set.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rrnco_rmtvrp_state {
+  int64_t* current_node;        /* [R] */
+  float* current_time;          /* [R] */
+  float* current_route_length;  /* [R] */
+  float* used_capacity_linehaul;/* [R] */
+  float* used_capacity_backhaul;/* [R] */
+  uint8_t* visited;             /* [R,N] bool */
+} rrnco_rmtvrp_state_t;
+
+/* action == NULL -> mask only (static get_action_mask on state_in). state_in / state_out may alias. */
+int rrnco_rmtvrp_step(int64_t R, int32_t n_nodes, const rrnco_instance_data_t* data, const int64_t* action,
+                      const rrnco_rmtvrp_state_t* state_in, const rrnco_rmtvrp_state_t* state_out,
+                      uint8_t* done_out, uint8_t* mask_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * env._get_reward: negative tour length over the (normalised) matrix + de-normalised "real" value
+ *   ATSP    rrnco/envs/atsp/env.py:192-211     closed tour a_0..a_{T-1}->a_0              (prepend_depot 0)
+ *   RCVRP   rrnco/envs/rcvrp/env.py:197-219    depot, a_0..a_{T-1}, back to depot         (prepend_depot 1)
+ *   RCVRPTW rrnco/envs/rmtvrp/env.py:430-455   same, legs INTO the depot cost 0 if open_route[row]
+ *   real = norm * (max - min + 1e-6) + min   (min_d/max_d [data_rows]; pass NULL to skip `real_out`).
+ * ---------------------------------------------------------------------------------------------- */
+int rrnco_tour_reward(int64_t R, int32_t T, int32_t n_nodes, int64_t data_rows, const int64_t* actions,
+                      const float* distance, int32_t prepend_depot, const uint8_t* open_route,
+                      const float* min_d, const float* max_d, float* norm_out, float* real_out,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder weights + per-batch cache (RRNetDecoder.state_dict())
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rrnco_decoder_weights {
+  const float* ffn_w1;   /* pointer.ffn.lins.0.weight [4E, E]   rrnco/models/decoder.py:272-277 */
+  const float* ffn_b1;   /* pointer.ffn.lins.0.bias   [4E] */
+  const float* ffn_w2;   /* pointer.ffn.lins.1.weight [E, 4E] */
+  const float* ffn_b2;   /* pointer.ffn.lins.1.bias   [E] */
+  const float* ctx_state_w; /* [n_state, E]: transposed state columns of context_embedding.project_context.weight
+                               (rcvrp: 1 row; rcvrptw: 4 rows; atsp: NULL)  rrnco/models/env_embeddings/context.py:27-31 */
+  const float* ctx_placeholder_q; /* [E] = W_ctx . W_placeholder (atsp, only used when multistart == 0), else NULL */
+  float alpha;           /* distance-bias scale  rrnco/models/decoder.py:121,189-193 */
+  float beta;            /* duration-bias scale (rcvrptw) rrnco/models/decoder.py:97-98 */
+  float tanh_clipping;   /* 10.0  rrnco/models/policy.py:83 */
+  float temperature;     /* 1.0 */
+} rrnco_decoder_weights_t;
+
+typedef struct rrnco_decoder_cache {
+  /* all [n_inst, N, E] fp32, contiguous; K/V/Lk = project_node_embeddings(col_emb).chunk(3)
+     rrnco/models/decoder.py:214-232 */
+  const float* glimpse_key;
+  const float* glimpse_val;
+  const float* logit_key;
+  const float* ctx_node_proj;   /* row_emb . W_ctx[:, :E]^T  (atsp: first-node half W_ctx[:, :E]) */
+  const float* ctx_node_proj2;  /* atsp only: row_emb . W_ctx[:, E:2E]^T (current-node half), else NULL */
+} rrnco_decoder_cache_t;
+
+/* Fills K/V/Lk/ctx projections from the encoder output with the library's own GEMM kernel:
+ *   RRNetDecoder._precompute_cache rrnco/models/decoder.py:214-232 + the node half of EnvContext.forward
+ *   rrnco/models/env_embeddings/context.py:27-31.  w_node [3E,E], w_ctx [E, ctx_in] as in state_dict. */
+int rrnco_precompute_cache(int32_t env, int64_t n_inst, int32_t n_nodes, const float* row_emb,
+                           const float* col_emb, const float* w_node, const float* w_ctx, int32_t ctx_in,
+                           float* glimpse_key, float* glimpse_val, float* logit_key, float* ctx_node_proj,
+                           float* ctx_node_proj2, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * RRNetDecoder.forward  rrnco/models/decoder.py:151-206  (one decode step, logits only)
+ *   state in reference layout: current [R] int64, first [R] int64 (atsp, else NULL), mask bool [R,N],
+ *   ctx_state fp32 [R, n_state] (rcvrp: capacity-used; rcvrptw: avail_load, time, open, remaining_dist;
+ *   atsp: NULL).  logits_out fp32 [R,N] = log(exp(pointer_logits - bias) + 1e-6), rows in (s b) order.
+ *   use_placeholder != 0: atsp step 0 without multistart (TSPContext placeholder query).
+ * ---------------------------------------------------------------------------------------------- */
+int rrnco_decoder_logits(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts,
+                         const rrnco_decoder_weights_t* w, const rrnco_decoder_cache_t* cache,
+                         const rrnco_instance_data_t* data, const int64_t* current, const int64_t* first,
+                         const uint8_t* mask, const float* ctx_state, int32_t use_placeholder,
+                         float* logits_out, uint32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused construction rollout = RRNetPolicy.forward decode loop  rrnco/models/policy.py:203-243
+ *   (multistart pre-hook decoding.py:157-205, decoder.py:151-206, process_logits decoding.py:311-361,
+ *    greedy / sampling / evaluate decoding.py:272-298,386-399, env._step, _get_reward, get_log_likelihood)
+ *   One launch decodes all R = n_inst * n_starts rollouts to completion without host round-trips.
+ *
+ *   multistart != 0: rollout (b, s) is forced to start node (s % num_loc) + has_depot
+ *                    (rl4co select_start_nodes; rrnco/envs/rmtvrp/selectstartnodes.py:42-50); that action is
+ *                    written as actions[:,0] with log-prob 0.   multistart == 0 requires n_starts == 1.
+ *   forced_actions  (mode EVALUATE): int64 [R, forced_T] in reference layout, the decisions AFTER the forced
+ *                    start (policy.py:214-218 indexes actions[..., step]).
+ *   actions_out     int64 [R, t_cap]; unused tail filled with 0 (= depot, what upstream emits for finished
+ *                    rollouts).  t_cap must be >= the longest rollout; *max_steps_out (device int32) receives
+ *                    the longest length = the T upstream would have produced.
+ *   logprob_out     fp32 [R, t_cap] per-step log-probs (may be NULL); loglik_out fp32 [R] their sum.
+ *   norm_reward_out fp32 [R] = -(tour length on the normalised matrix); real_reward_out de-normalised
+ *                    (NULL if data->min_distance is NULL).  Padding legs 0->0 are accounted like upstream.
+ *   workspace       >= rrnco_rollout_workspace_bytes(...) bytes, 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts);
+
+int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts, int32_t multistart,
+                  int32_t decode_mode, uint64_t seed, const rrnco_decoder_weights_t* w,
+                  const rrnco_decoder_cache_t* cache, const rrnco_instance_data_t* data,
+                  const int64_t* forced_actions, int32_t forced_T, int32_t t_cap, int64_t* actions_out,
+                  float* logprob_out, float* loglik_out, float* norm_reward_out, float* real_reward_out,
+                  int32_t* max_steps_out, uint32_t* status, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRNCO_B200_H */

@@ -1,0 +1,20 @@
+"""rrnco_b200 -- B200-native (sm_100a) construction-rollout hot path of ai4co/real-routing-nco.
+
+Host-side mirror of the reference interface for this path (same class / method names, td schema and error
+texts) on top of the C-ABI library `librrnco_b200.so` (include/rrnco_b200.h):
+
+    from rrnco_b200 import ATSPEnv, RCVRPEnv, RMTVRPEnv            # rrnco.envs.{atsp,rcvrp,rmtvrp}
+    from rrnco_b200 import RRNetDecoder, RRNetPolicy              # rrnco.models
+    from rrnco_b200 import Real_World_Sampler                     # rrnco.envs.*.sampler
+
+No CPU fallback, no Triton / torch.compile: if the CUDA library is missing, calls raise.
+"""
+from ._lib import RRNCOError, set_precision  # noqa: F401
+from .envs import ATSPEnv, RCVRPEnv, RMTVRPEnv, get_env  # noqa: F401
+from .models import PrecomputedCache, RRNetDecoder, RRNetPolicy, fused_rollout  # noqa: F401
+from .sampler import Real_World_Sampler  # noqa: F401
+from .tdlite import TensorDictLite, batchify, unbatchify  # noqa: F401
+
+__all__ = ["ATSPEnv", "RCVRPEnv", "RMTVRPEnv", "get_env", "RRNetDecoder", "RRNetPolicy", "PrecomputedCache",
+           "fused_rollout", "Real_World_Sampler", "TensorDictLite", "batchify", "unbatchify", "set_precision",
+           "RRNCOError"]

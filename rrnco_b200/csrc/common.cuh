@@ -1,0 +1,97 @@
+// Shared device helpers for librrnco_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rrnco_b200.h"
+
+#define RRNCO_CHECK_ARG(cond) \
+  do {                        \
+    if (!(cond)) return RRNCO_ERR_BAD_ARG; \
+  } while (0)
+
+static inline int rrnco_launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? RRNCO_OK : RRNCO_ERR_CUDA;
+}
+
+namespace rrnco {
+
+constexpr int kE = RRNCO_EMBED_DIM;   // 128
+constexpr int kH = RRNCO_NUM_HEADS;   // 8
+constexpr int kDh = kE / kH;          // 16
+constexpr int kF = 4 * kE;            // 512 FFN hidden
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- cp.async (LDGSTS) 16-byte copies, L2-only caching for streamed operands -------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- 3xTF32 tensor-core MMA (fp32-faithful: a*b ~= ah*bh + al*bh + ah*bl) ----------------------
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = f2tf32(x);
+  lo = f2tf32(x - __uint_as_float(hi));
+}
+// D(16x8) += A(16x8, row) * B(8x8, col); fragment layouts per PTX ISA mma.m16n8k8.tf32.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// kPasses == 3: 3xTF32 (fp32-faithful); kPasses == 1: single TF32 pass (autocast-like fast mode)
+template <int kPasses>
+__device__ __forceinline__ void mma_x(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                      const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  if (kPasses == 3) {
+    mma_tf32(d, al, bh);
+    mma_tf32(d, ah, bl);
+  }
+  mma_tf32(d, ah, bh);
+}
+
+// ---- Philox-4x32-10 counter RNG (Gumbel-max sampling) -----------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// uniform in (0,1), 24 bits
+__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+}  // namespace rrnco

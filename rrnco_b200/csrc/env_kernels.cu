@@ -1,0 +1,408 @@
+// Environment kernels in REFERENCE LAYOUT (flat [R, ...] td tensors): reset normalisation, instance
+// gather, step + action mask for ATSP / RCVRP / RCVRPTW, tour reward.  All are HBM-bound byte / fp32
+// streaming kernels: one warp per rollout (a rollout's row of N nodes is 100-400 contiguous bytes),
+// lanes stride over nodes so that every global access of a warp is one contiguous segment; the
+// any-feasible reduction the depot rule needs is a ballot.  fp32 arithmetic uses explicit _rn
+// intrinsics in the reference's evaluation order so that masks are bit-exact (no FMA contraction).
+#include "common.cuh"
+
+namespace rrnco {
+
+constexpr int kWarpsPerBlock = 8;
+
+// ------------------------------------------------------------------------------------------------
+// reset: (d - min) / (max - min + 1e-6)      rrnco/envs/rcvrp/env.py:138-145
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_minmax(float& lo, float& hi, float* red /*[64]*/) {
+  lo = warp_min(lo);
+  hi = warp_max(hi);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    red[warp] = lo;
+    red[32 + warp] = hi;
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  lo = lane < nw ? red[lane] : INFINITY;
+  hi = lane < nw ? red[32 + lane] : -INFINITY;
+  lo = warp_min(lo);
+  hi = warp_max(hi);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) minmax_normalize_kernel(int n2, const float* __restrict__ in,
+                                                               float* __restrict__ out,
+                                                               float* __restrict__ mn, float* __restrict__ mx) {
+  __shared__ float red[64];
+  const float* src = in + (size_t)blockIdx.x * n2;
+  float* dst = out + (size_t)blockIdx.x * n2;
+  float lo = INFINITY, hi = -INFINITY;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    float v = src[i];
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+  block_minmax(lo, hi, red);
+  const float denom = __fadd_rn(__fsub_rn(hi, lo), 1e-6f);
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __fdiv_rn(__fsub_rn(src[i], lo), denom);
+  if (threadIdx.x == 0) {
+    mn[blockIdx.x] = lo;
+    mx[blockIdx.x] = hi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather: out[b,i,j] = (float) M[idx[b,i], idx[b,j]]      rrnco/envs/rcvrp/sampler.py:84-90
+// One CTA per instance; idx row staged in shared memory; the fp64 city matrix (8 MB) is L2 resident,
+// writes are fully coalesced.  Optional fused reset normalisation (second pass hits L1/L2).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_submatrix_kernel(const double* __restrict__ M, int L,
+                                                               const int32_t* __restrict__ idx, int n,
+                                                               float* __restrict__ out, int normalize,
+                                                               float* __restrict__ mn, float* __restrict__ mx) {
+  extern __shared__ int32_t sidx[];
+  __shared__ float red[64];
+  const size_t b = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sidx[i] = idx[b * n + i];
+  __syncthreads();
+  float* dst = out + b * (size_t)n * n;
+  float lo = INFINITY, hi = -INFINITY;
+  const int n2 = n * n;
+  for (int e = threadIdx.x; e < n2; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    const float v = (float)__ldg(M + (size_t)sidx[i] * L + sidx[j]);
+    dst[e] = v;
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+  if (!normalize) return;
+  block_minmax(lo, hi, red);  // contains __syncthreads: dst writes of this CTA are visible below
+  const float denom = __fadd_rn(__fsub_rn(hi, lo), 1e-6f);
+  for (int e = threadIdx.x; e < n2; e += blockDim.x) dst[e] = __fdiv_rn(__fsub_rn(dst[e], lo), denom);
+  if (threadIdx.x == 0) {
+    mn[b] = lo;
+    mx[b] = hi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ATSP step      rrnco/envs/atsp/env.py:79-105
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) atsp_step_kernel(
+    int64_t R, int N, const int64_t* __restrict__ action, const int64_t* __restrict__ step_i, const uint8_t* mask_in,
+    const int64_t* first_in, uint8_t* mask_out, int64_t* first_out, int64_t* cur_out, uint8_t* done_out) {
+  const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  const int a = (int)action[r];
+  bool any = false;
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    const int n = n0 + lane;
+    bool m = false;
+    if (n < N) {
+      m = mask_in[r * N + n] != 0 && n != a;
+      mask_out[r * N + n] = m;
+    }
+    any |= __any_sync(0xffffffffu, m);
+  }
+  if (lane == 0) {
+    first_out[r] = step_i[0] == 0 ? (int64_t)a : first_in[r];
+    cur_out[r] = a;
+    done_out[r] = !any;  // count_nonzero(available) <= 0
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RCVRP step + mask      rrnco/envs/rcvrp/env.py:90-122, 183-195
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) rcvrp_step_kernel(
+    int64_t R, int N, int64_t data_rows, const int64_t* __restrict__ action, const float* __restrict__ demand,
+    const float* __restrict__ capacity, int64_t cap_rows, const float* used_in, const uint8_t* visited_in,
+    const int64_t* current_in, float* used_out, uint8_t* visited_out, int64_t* current_out,
+    uint8_t* done_out, uint8_t* mask_out) {
+  const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  const float* dem = demand + (r % data_rows) * (int64_t)(N - 1);
+  const float cap = capacity[r % cap_rows];
+  float used = used_in[r];
+  int cur;
+  if (action != nullptr) {
+    cur = (int)action[r];
+    const int di = min(max(cur - 1, 0), N - 2);  // clamp(a - 1, 0, n_loc - 1)
+    used = __fmul_rn(__fadd_rn(used, dem[di]), cur != 0 ? 1.0f : 0.0f);
+  } else {
+    cur = (int)current_in[r];
+  }
+  int n_visited = 0;
+  bool any_free = false;
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    const int n = n0 + lane;
+    bool v = false, free_loc = false;
+    if (n < N) {
+      uint8_t vb = visited_in[r * N + n];
+      if (action != nullptr) {
+        if (n == cur) vb = 1;  // scatter(-1, cur, 1)
+        visited_out[r * N + n] = vb;
+      }
+      v = vb != 0;
+      if (n >= 1) {
+        const bool exceeds = __fadd_rn(dem[n - 1], used) > cap;
+        free_loc = !(v || exceeds);
+        mask_out[r * N + n] = free_loc;
+      }
+    }
+    n_visited += __popc(__ballot_sync(0xffffffffu, v));
+    any_free |= __any_sync(0xffffffffu, free_loc);
+  }
+  if (lane == 0) {
+    mask_out[r * N] = !(cur == 0 && any_free);
+    if (action != nullptr) {
+      used_out[r] = used;
+      current_out[r] = cur;
+      done_out[r] = n_visited == N;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RCVRPTW (RMTVRP) step + mask      rrnco/envs/rmtvrp/env.py:155-215, 343-428
+// ------------------------------------------------------------------------------------------------
+struct RmtvrpState {
+  int64_t* cur;
+  float *time, *route, *used_l, *used_b;
+  uint8_t* visited;
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) rmtvrp_step_kernel(
+    int64_t R, int N, rrnco_instance_data_t d, const int64_t* __restrict__ action, RmtvrpState in,
+    RmtvrpState out, uint8_t* done_out, uint8_t* mask_out) {
+  const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = r % d.data_rows;
+  const float* D = d.distance + row * (int64_t)N * N;
+  const float* U = d.duration + row * (int64_t)N * N;
+  const float* tw = d.time_windows + row * (int64_t)N * 2;
+  const float* svc = d.service_time + row * (int64_t)N;
+  const float* dl = d.demand + row * (int64_t)N;
+  const float* db = d.demand_backhaul + row * (int64_t)N;
+  const float cap = d.vehicle_capacity[row];
+  const float limit = d.distance_limit[row];
+  const float closed = d.open_route[row] ? 0.0f : 1.0f;  // "* ~open_route" (bool -> 0/1)
+  const float bclass = d.backhaul_class[row];
+
+  int cur = (int)in.cur[r];
+  float time = in.time[r], route = in.route[r], used_l = in.used_l[r], used_b = in.used_b[r];
+  if (action != nullptr) {
+    const int prev = cur;
+    cur = (int)action[r];
+    const float away = cur != 0 ? 1.0f : 0.0f;
+    const float dist = D[prev * N + cur], dur = U[prev * N + cur];
+    time = __fmul_rn(away, __fadd_rn(fmaxf(__fadd_rn(time, dur), tw[cur * 2]), svc[cur]));
+    route = __fmul_rn(away, __fadd_rn(route, dist));
+    used_l = __fmul_rn(away, __fadd_rn(used_l, dl[cur]));
+    used_b = __fmul_rn(away, __fadd_rn(used_b, db[cur]));
+  }
+  // pass 1: visited update, done, linehauls_missing
+  int n_visited = 0;
+  bool missing = false;
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    const int n = n0 + lane;
+    bool v = false, miss = false;
+    if (n < N) {
+      uint8_t vb = in.visited[r * N + n];
+      if (action != nullptr) {
+        if (n == cur) vb = 1;
+        out.visited[r * N + n] = vb;
+      }
+      v = vb != 0;
+      miss = !v && dl[n] > 0.0f;  // (demand_linehaul * ~visited).sum(-1) > 0 with non-negative demands
+    }
+    n_visited += __popc(__ballot_sync(0xffffffffu, v));
+    missing |= __any_sync(0xffffffffu, miss);
+  }
+  __syncwarp();  // out.visited (may alias in.visited) is re-read below by the same lanes only
+  const bool carrying_b = db[cur] > 0.0f;
+  const float late0 = tw[1];
+  bool any_cust = false;
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    const int n = n0 + lane;
+    bool can = false;
+    if (n < N) {
+      const bool v = (action != nullptr ? out.visited[r * N + n] : in.visited[r * N + n]) != 0;
+      const float dist_ij = D[cur * N + n], dist_j0 = D[n * N];
+      const float dur_ij = U[cur * N + n], dur_j0 = U[n * N];
+      const float early = tw[n * 2], late = tw[n * 2 + 1];
+      const float arrival = __fadd_rn(time, dur_ij);
+      const bool reach_c = arrival < late;
+      const bool reach_d =
+          __fmul_rn(__fadd_rn(__fadd_rn(fmaxf(arrival, early), svc[n]), dur_j0), closed) < late0;
+      const bool exc_lim = __fadd_rn(__fadd_rn(route, dist_ij), __fmul_rn(dist_j0, closed)) > limit;
+      const bool exc_l = __fadd_rn(dl[n], used_l) > cap;
+      const bool exc_b = __fadd_rn(db[n], used_b) > cap;
+      const bool ok1 = (missing && !exc_l && !carrying_b && dl[n] > 0.0f) || (!exc_b && db[n] > 0.0f);
+      const bool cannot_l = dl[n] > __fsub_rn(cap, used_b);
+      const bool ok2 = !exc_l && !exc_b && !cannot_l;
+      const bool ok = (bclass == 1.0f && ok1) || (bclass == 2.0f && ok2);
+      can = reach_c && reach_d && ok && !exc_lim && !v;
+      if (n >= 1) mask_out[r * N + n] = can;
+    }
+    any_cust |= __any_sync(0xffffffffu, can && n >= 1);
+  }
+  if (lane == 0) {
+    mask_out[r * N] = !(cur == 0 && any_cust);
+    if (action != nullptr) {
+      out.cur[r] = cur;
+      out.time[r] = time;
+      out.route[r] = route;
+      out.used_l[r] = used_l;
+      out.used_b[r] = used_b;
+      done_out[r] = n_visited == N;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tour reward      atsp/env.py:192-211, rcvrp/env.py:197-219, rmtvrp/env.py:430-455
+// warp per rollout, lanes over legs, fp64 accumulation (<= 0.5 ulp of the exact fp32-leg sum)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) tour_reward_kernel(
+    int64_t R, int T, int N, int64_t data_rows, const int64_t* __restrict__ actions,
+    const float* __restrict__ distance, int prepend_depot, const uint8_t* __restrict__ open_route,
+    const float* __restrict__ mn, const float* __restrict__ mx, float* norm_out, float* real_out) {
+  const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = r % data_rows;
+  const float* D = distance + row * (int64_t)N * N;
+  const int64_t* a = actions + r * (int64_t)T;
+  const bool open = open_route != nullptr && open_route[row] != 0;
+  const int legs = prepend_depot ? T + 1 : T;
+  double acc = 0.0;
+  for (int l = lane; l < legs; l += 32) {
+    int from, to;
+    if (prepend_depot) {  // go_from = [0, a...], go_to = roll(go_from, -1)
+      from = l == 0 ? 0 : (int)a[l - 1];
+      to = l == T ? 0 : (int)a[l];
+    } else {
+      from = (int)a[l];
+      to = (int)a[l + 1 == T ? 0 : l + 1];
+    }
+    float c = D[from * N + to];
+    if (open && to == 0) c = __fmul_rn(c, 0.0f);  // column 0 zeroed for open routes (rmtvrp/env.py:433)
+    acc += (double)c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const float neg = -(float)acc;
+    norm_out[r] = neg;
+    if (real_out != nullptr)
+      real_out[r] = __fadd_rn(__fmul_rn(neg, __fadd_rn(__fsub_rn(mx[row], mn[row]), 1e-6f)), mn[row]);
+  }
+}
+
+}  // namespace rrnco
+
+using namespace rrnco;
+
+static inline unsigned warp_grid(int64_t R) { return (unsigned)((R + kWarpsPerBlock - 1) / kWarpsPerBlock); }
+
+extern "C" {
+
+int rrnco_abi_version(void) { return RRNCO_ABI_VERSION; }
+
+const char* rrnco_strerror(int code) {
+  switch (code) {
+    case RRNCO_OK: return "ok";
+    case RRNCO_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size or misaligned buffer)";
+    case RRNCO_ERR_UNSUPPORTED: return "unsupported variant or size for this build";
+    case RRNCO_ERR_CUDA: return "CUDA launch failed";
+    default: return "unknown rrnco status";
+  }
+}
+
+int rrnco_minmax_normalize(int64_t n_mat, int32_t n_nodes, const float* dist_in, float* dist_out,
+                           float* min_out, float* max_out, void* stream) {
+  if (n_mat == 0) return RRNCO_OK;
+  RRNCO_CHECK_ARG(n_mat > 0 && n_nodes > 0 && dist_in && dist_out && min_out && max_out);
+  minmax_normalize_kernel<<<(unsigned)n_mat, 256, 0, (cudaStream_t)stream>>>(n_nodes * n_nodes, dist_in, dist_out,
+                                                                          min_out, max_out);
+  return rrnco_launch_status();
+}
+
+int rrnco_gather_submatrix(const double* city_matrix, int32_t city_len, const int32_t* idx, int64_t batch,
+                           int32_t n, float* out, int32_t normalize, float* min_out, float* max_out,
+                           void* stream) {
+  if (batch == 0) return RRNCO_OK;
+  RRNCO_CHECK_ARG(batch > 0 && n > 0 && city_len >= n && city_matrix && idx && out);
+  RRNCO_CHECK_ARG(!normalize || (min_out && max_out));
+  if ((size_t)n * sizeof(int32_t) > 48 * 1024) return RRNCO_ERR_UNSUPPORTED;
+  gather_submatrix_kernel<<<(unsigned)batch, 256, n * sizeof(int32_t), (cudaStream_t)stream>>>(
+      city_matrix, city_len, idx, n, out, normalize, min_out, max_out);
+  return rrnco_launch_status();
+}
+
+int rrnco_atsp_step(int64_t R, int32_t n_nodes, const int64_t* action, const int64_t* step_i, const uint8_t* mask_in,
+                    const int64_t* first_in, uint8_t* mask_out, int64_t* first_out, int64_t* current_out,
+                    uint8_t* done_out, void* stream) {
+  if (R == 0) return RRNCO_OK;
+  RRNCO_CHECK_ARG(R > 0 && n_nodes > 0 && action && step_i && mask_in && first_in && mask_out && first_out &&
+                  current_out && done_out);
+  atsp_step_kernel<<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      R, n_nodes, action, step_i, mask_in, first_in, mask_out, first_out, current_out, done_out);
+  return rrnco_launch_status();
+}
+
+int rrnco_rcvrp_step(int64_t R, int32_t n_nodes, int64_t data_rows, const int64_t* action, const float* demand,
+                     const float* capacity, int64_t cap_rows, const float* used_in, const uint8_t* visited_in,
+                     const int64_t* current_in, float* used_out, uint8_t* visited_out, int64_t* current_out,
+                     uint8_t* done_out, uint8_t* mask_out, void* stream) {
+  if (R == 0) return RRNCO_OK;
+  RRNCO_CHECK_ARG(R > 0 && n_nodes > 1 && data_rows > 0 && cap_rows > 0 && demand && capacity && used_in &&
+                  visited_in && mask_out);
+  RRNCO_CHECK_ARG(action ? (used_out && visited_out && current_out && done_out) : (current_in != nullptr));
+  rcvrp_step_kernel<<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      R, n_nodes, data_rows, action, demand, capacity, cap_rows, used_in, visited_in, current_in, used_out,
+      visited_out, current_out, done_out, mask_out);
+  return rrnco_launch_status();
+}
+
+int rrnco_rmtvrp_step(int64_t R, int32_t n_nodes, const rrnco_instance_data_t* data, const int64_t* action,
+                      const rrnco_rmtvrp_state_t* state_in, const rrnco_rmtvrp_state_t* state_out,
+                      uint8_t* done_out, uint8_t* mask_out, void* stream) {
+  if (R == 0) return RRNCO_OK;
+  RRNCO_CHECK_ARG(R > 0 && n_nodes > 1 && data && state_in && mask_out);
+  RRNCO_CHECK_ARG(data->data_rows > 0 && data->distance && data->duration && data->time_windows &&
+                  data->service_time && data->demand && data->demand_backhaul && data->vehicle_capacity &&
+                  data->distance_limit && data->open_route && data->backhaul_class);
+  RRNCO_CHECK_ARG(state_in->current_node && state_in->current_time && state_in->current_route_length &&
+                  state_in->used_capacity_linehaul && state_in->used_capacity_backhaul && state_in->visited);
+  RmtvrpState in{state_in->current_node, state_in->current_time, state_in->current_route_length,
+                 state_in->used_capacity_linehaul, state_in->used_capacity_backhaul, state_in->visited};
+  RmtvrpState out = in;
+  if (action) {
+    RRNCO_CHECK_ARG(state_out && done_out && state_out->current_node && state_out->current_time &&
+                    state_out->current_route_length && state_out->used_capacity_linehaul &&
+                    state_out->used_capacity_backhaul && state_out->visited);
+    out = RmtvrpState{state_out->current_node, state_out->current_time, state_out->current_route_length,
+                      state_out->used_capacity_linehaul, state_out->used_capacity_backhaul, state_out->visited};
+  }
+  rmtvrp_step_kernel<<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(R, n_nodes, *data, action, in,
+                                                                                 out, done_out, mask_out);
+  return rrnco_launch_status();
+}
+
+int rrnco_tour_reward(int64_t R, int32_t T, int32_t n_nodes, int64_t data_rows, const int64_t* actions,
+                      const float* distance, int32_t prepend_depot, const uint8_t* open_route, const float* min_d,
+                      const float* max_d, float* norm_out, float* real_out, void* stream) {
+  if (R == 0) return RRNCO_OK;
+  RRNCO_CHECK_ARG(R > 0 && T > 0 && n_nodes > 0 && data_rows > 0 && actions && distance && norm_out);
+  RRNCO_CHECK_ARG(real_out == nullptr || (min_d && max_d));
+  tour_reward_kernel<<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      R, T, n_nodes, data_rows, actions, distance, prepend_depot, open_route, min_d, max_d, norm_out, real_out);
+  return rrnco_launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,944 @@
+// Fused construction-rollout kernel (RRNetPolicy.forward decode loop, rrnco/models/policy.py:203-243).
+//
+// One CTA = one problem instance x one tile of up to 128 POMO starts, persistent over ALL decode steps:
+// rollout state (current node, visited bitset, load / time / route length, running tour length and
+// log-likelihood) never leaves shared memory, so HBM only sees the per-instance key cache, the matrix
+// rows the bias / mask need, and the int64 action stream that the reference API returns.
+//
+// Per step (all 128 rollouts of the tile together, weights shared => real GEMMs on the tensor pipe):
+//   A. action mask (env.get_action_mask) as 128-bit row bitsets; query q = ctx_node_proj[cur] + state.w
+//   B. K / V of the instance staged in shared memory with cp.async (zero-filled to a multiple of 8 keys)
+//   C. 8-head masked attention, flash-style in registers: S = Q_h K_h^T (mma), softmax (quad shuffles),
+//      P V_h (mma, accumulator layout re-used as the A operand through a key permutation), + q
+//   E. FFN 128 -> 512 -> 128 with residual; W1/W2 streamed from L2 through a 3-stage cp.async ring
+//   G. pointer logits g.Lk^T / sqrt(E), scale-adaptive bias log(exp(l - a.D[cur,:] - b.Dur[cur,:]) + 1e-6),
+//      10.tanh, mask, log-softmax, greedy argmax / Gumbel-max sample / forced action, state transition.
+// All contractions run as 3xTF32 (error-compensated split, fp32-faithful) or 1xTF32 (kPasses == 1, the
+// analogue of the reference's autocast inference path).
+#include "common.cuh"
+
+namespace rrnco {
+
+constexpr int kThreads = 256;
+constexpr int kRows = 128;   // rollouts per CTA tile
+constexpr int kLdA = 132;    // fp32 row stride of the activation tiles (bank-conflict-free fragments)
+constexpr int kLdB = 36;     // fp32 row stride of a streamed weight slice (32 k + 4 pad)
+constexpr int kSliceK = 32;
+constexpr int kStages = 3;
+constexpr int kStageFloats = kRows * kLdB;
+constexpr int kTileFloats = kRows * kLdA;
+constexpr int kNumSlices = 36;  // 4 chunks x (4 W1 + 4 W2) + 4 Lk
+constexpr int kMaxState = 4;
+
+struct RolloutParams {
+  int N, NT, S, n_tiles, n_state;
+  int64_t n_inst;
+  int multistart, mode, logits_only, use_placeholder, t_cap, forced_T, max_steps;
+  uint64_t seed;
+  rrnco_decoder_weights_t w;
+  rrnco_decoder_cache_t c;
+  rrnco_instance_data_t d;
+  const int64_t* in_cur;
+  const int64_t* in_first;
+  const uint8_t* in_mask;
+  const float* in_state;
+  float* logits_out;
+  const int64_t* forced;
+  int64_t* actions;
+  float* logprob;
+  double* ws_len;
+  double* ws_lp;
+  int32_t* ws_tile_steps;
+  int32_t* max_steps_out;
+  uint32_t* status;
+};
+
+struct Smem {
+  float A[kTileFloats];   // q -> glimpse -> glimpse'
+  float Hb[kTileFloats];  // K tile (attention) / FFN hidden chunk
+  float Bs[kTileFloats];  // V tile (attention) / 3-stage weight-slice ring
+  float b1[kF];
+  float b2[kE];
+  float wstate[kMaxState][kE];
+  float placeholder[kE];
+  // per-instance node data
+  float dem[kRows], demb[kRows], tw0[kRows], tw1[kRows], svc[kRows], dj0[kRows], uj0[kRows];
+  // per-rollout state
+  int cur[kRows], first[kRows], active[kRows], done[kRows];
+  float f[kMaxState][kRows];  // rcvrp: used | rcvrptw: time, route, used_l, used_b | logits_only: ctx state
+  uint32_t vis[kRows][4];
+  uint32_t mask[kRows][4];
+  double len[kRows];
+  double lp[kRows];
+};
+
+__device__ __forceinline__ bool bit_of(const uint32_t (&w)[4], int j, int e8) {
+  // column c = 8 j + e8 (e8 < 8): word j >> 2, bit 8 (j & 3) + e8
+  return (w[j >> 2] >> (8 * (j & 3) + e8)) & 1u;
+}
+
+// ---- env transition on the shared-memory state (one lane per row) -----------------------------------
+template <int kEnv>
+__device__ __forceinline__ void transition(Smem& sm, const RolloutParams& p, int row, int a, const float* D,
+                                           const float* U, float cap, float closed, bool count_leg) {
+  const int prev = sm.cur[row];
+  const int N = p.N;
+  if (kEnv == RRNCO_ENV_ATSP) {
+    if (count_leg) sm.len[row] += (double)D[prev * N + a];
+  } else if (kEnv == RRNCO_ENV_RCVRP) {
+    sm.len[row] += (double)D[prev * N + a];
+    const int di = min(max(a - 1, 0), N - 2) + 1;  // clamp(a-1, 0, n_loc-1), dem[] is depot-shifted
+    sm.f[0][row] = __fmul_rn(__fadd_rn(sm.f[0][row], sm.dem[di]), a != 0 ? 1.0f : 0.0f);
+  } else {
+    const float away = a != 0 ? 1.0f : 0.0f;
+    float leg = D[prev * N + a];
+    if (a == 0) leg = __fmul_rn(leg, closed);
+    sm.len[row] += (double)leg;
+    const float dist = D[prev * N + a], dur = U[prev * N + a];
+    sm.f[0][row] = __fmul_rn(away, __fadd_rn(fmaxf(__fadd_rn(sm.f[0][row], dur), sm.tw0[a]), sm.svc[a]));
+    sm.f[1][row] = __fmul_rn(away, __fadd_rn(sm.f[1][row], dist));
+    sm.f[2][row] = __fmul_rn(away, __fadd_rn(sm.f[2][row], sm.dem[a]));
+    sm.f[3][row] = __fmul_rn(away, __fadd_rn(sm.f[3][row], sm.demb[a]));
+  }
+  sm.vis[row][a >> 5] |= 1u << (a & 31);
+  sm.cur[row] = a;
+  const int cnt = __popc(sm.vis[row][0]) + __popc(sm.vis[row][1]) + __popc(sm.vis[row][2]) + __popc(sm.vis[row][3]);
+  sm.done[row] = cnt == N;
+}
+
+// ---- weight / logit-key slice stream ---------------------------------------------------------------
+__device__ __forceinline__ void issue_slice(int s, Smem& sm, const RolloutParams& p, const float* Lk, int tid) {
+  if (s < kNumSlices) {
+    float* dst = sm.Bs + (s % kStages) * kStageFloats;
+    const float* src;
+    int ld, nrows;
+    if (s < 32) {
+      const int c = s >> 3, ks = s & 3;
+      if (((s >> 2) & 1) == 0) {
+        src = p.w.ffn_w1 + (size_t)c * kRows * kE + ks * kSliceK;  // rows: hidden units of chunk c
+        ld = kE;
+      } else {
+        src = p.w.ffn_w2 + c * kRows + ks * kSliceK;  // rows: output dims, cols: hidden units of chunk c
+        ld = kF;
+      }
+      nrows = kRows;
+    } else {
+      src = Lk + (s - 32) * kSliceK;
+      ld = kE;
+      nrows = p.N;
+    }
+#pragma unroll
+    for (int i = 0; i < (kRows * 8) / kThreads; ++i) {
+      const int idx = tid + i * kThreads, row = idx >> 3, c4 = idx & 7;
+      cp_async16_zfill(dst + row * kLdB + c4 * 4, src + (size_t)(row < nrows ? row : 0) * ld + c4 * 4, row < nrows);
+    }
+  }
+  cp_async_commit();  // always commit (possibly empty) so that wait_group counting stays uniform
+}
+
+template <int kEnv, int kNTMax, int kPasses>
+__global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int N = p.N, NT = p.NT;
+  const int tile = blockIdx.x % p.n_tiles;
+  const int64_t b = blockIdx.x / p.n_tiles;
+  const int64_t drow = b % p.d.data_rows;
+  const float* D = p.d.distance + drow * (int64_t)N * N;
+  const float* U = kEnv == RRNCO_ENV_RCVRPTW ? p.d.duration + drow * (int64_t)N * N : nullptr;
+  const float* Kc = p.c.glimpse_key + b * (int64_t)N * kE;
+  const float* Vc = p.c.glimpse_val + b * (int64_t)N * kE;
+  const float* Lk = p.c.logit_key + b * (int64_t)N * kE;
+  const float* P1 = p.c.ctx_node_proj + b * (int64_t)N * kE;
+  const float* P2 = kEnv == RRNCO_ENV_ATSP ? p.c.ctx_node_proj2 + b * (int64_t)N * kE : nullptr;
+  const float cap = (kEnv == RRNCO_ENV_ATSP || p.logits_only) ? 0.f : p.d.vehicle_capacity[drow];
+  float closed = 1.f, limit = INFINITY, bclass = 1.f;
+  if (kEnv == RRNCO_ENV_RCVRPTW && !p.logits_only) {
+    closed = p.d.open_route[drow] ? 0.f : 1.f;
+    limit = p.d.distance_limit[drow];
+    bclass = p.d.backhaul_class[drow];
+  }
+
+  // ---------------- one-time staging ----------------
+  for (int i = tid; i < kF; i += kThreads) sm.b1[i] = p.w.ffn_b1[i];
+  if (tid < kE) {
+    sm.b2[tid] = p.w.ffn_b2[tid];
+    sm.placeholder[tid] = p.w.ctx_placeholder_q ? p.w.ctx_placeholder_q[tid] : 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxState; ++k) sm.wstate[k][tid] = k < p.n_state ? p.w.ctx_state_w[k * kE + tid] : 0.f;
+  }
+  if (tid < kRows && !p.logits_only) {
+    const int n = tid;
+    float dem = 0.f, demb = 0.f, tw0 = 0.f, tw1 = 0.f, svc = 0.f, dj0 = 0.f, uj0 = 0.f;
+    if (n < N) {
+      if (kEnv == RRNCO_ENV_RCVRP) dem = n >= 1 ? p.d.demand[drow * (N - 1) + n - 1] : 0.f;
+      if (kEnv == RRNCO_ENV_RCVRPTW) {
+        dem = p.d.demand[drow * N + n];
+        demb = p.d.demand_backhaul[drow * N + n];
+        tw0 = p.d.time_windows[(drow * N + n) * 2];
+        tw1 = p.d.time_windows[(drow * N + n) * 2 + 1];
+        svc = p.d.service_time[drow * N + n];
+        dj0 = D[n * N];
+        uj0 = U[n * N];
+      }
+    }
+    sm.dem[n] = dem; sm.demb[n] = demb; sm.tw0[n] = tw0; sm.tw1[n] = tw1; sm.svc[n] = svc;
+    sm.dj0[n] = dj0; sm.uj0[n] = uj0;
+  }
+  __syncthreads();
+
+  // ---------------- rollout state init ----------------
+  const int num_loc = kEnv == RRNCO_ENV_ATSP ? N : N - 1;
+  if (tid < kRows) {
+    const int row = tid;
+    const int s_real = tile * kRows + row;
+    const int active = s_real < p.S;
+    const int s = active ? s_real : tile * kRows;  // padded rows shadow the tile's first rollout
+    const int64_t r = (int64_t)s * p.n_inst + b;
+    sm.active[row] = active;
+    sm.len[row] = 0.0;
+    sm.lp[row] = 0.0;
+    sm.first[row] = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxState; ++k) sm.f[k][row] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sm.vis[row][k] = 0u; sm.mask[row][k] = 0u; }
+    sm.done[row] = 0;
+    sm.cur[row] = 0;
+    if (p.logits_only) {
+      sm.cur[row] = (int)p.in_cur[r];
+      if (kEnv == RRNCO_ENV_ATSP) sm.first[row] = (int)p.in_first[r];
+      for (int k = 0; k < p.n_state; ++k) sm.f[k][row] = p.in_state[r * p.n_state + k];
+      const uint8_t* m = p.in_mask + r * (int64_t)N;
+      for (int n = 0; n < N; ++n)
+        if (m[n]) sm.mask[row][n >> 5] |= 1u << (n & 31);
+    } else if (p.multistart) {
+      const int a0 = s % num_loc + (kEnv == RRNCO_ENV_ATSP ? 0 : 1);  // select_start_nodes
+      transition<kEnv>(sm, p, row, a0, D, U, cap, closed, /*count_leg=*/false);
+      sm.first[row] = a0;
+      if (active) {
+        p.actions[r * p.t_cap] = a0;
+        if (p.logprob) p.logprob[r * p.t_cap] = 0.f;
+      }
+    }
+  }
+  __syncthreads();
+
+  const int r0 = warp * 16 + g, r1 = r0 + 8;  // rows owned by this quad in the row-owner phases
+  const int wm = warp >> 1, wn = warp & 1;    // FFN warp grid 4 (M) x 2 (N): 32 x 64 warp tiles
+  int step = 0;
+  int t_out = p.multistart ? 1 : 0;
+  const int NPAD = NT * 8;
+
+  while (true) {
+    if (!p.logits_only) {
+      const int all_done = __syncthreads_and(tid < kRows ? (sm.done[tid] || !sm.active[tid]) : 1);
+      if (all_done || step >= p.max_steps) break;
+    }
+    // ---- B (issued first so that the copies overlap phase A): K -> Hb, V -> Bs -----------------
+    for (int idx = tid; idx < NPAD * 32; idx += kThreads) {
+      const int row = idx >> 5, c4 = idx & 31;
+      const bool ok = row < N;
+      const size_t off = (size_t)(ok ? row : 0) * kE + c4 * 4;
+      cp_async16_zfill(sm.Hb + row * kLdA + c4 * 4, Kc + off, ok);
+      cp_async16_zfill(sm.Bs + row * kLdA + c4 * 4, Vc + off, ok);
+    }
+    cp_async_commit();
+
+    // ---- A1: action mask bitsets (row-owner quads) ---------------------------------------------
+    if (!p.logits_only) {
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = rr ? r1 : r0;
+        const int cur = sm.cur[row];
+        uint32_t vis[4], bits[4] = {0u, 0u, 0u, 0u};
+        *reinterpret_cast<uint4*>(vis) = *reinterpret_cast<const uint4*>(sm.vis[row]);
+        float f0 = sm.f[0][row], f1 = sm.f[1][row], f2 = sm.f[2][row], f3 = sm.f[3][row];
+        bool missing = false, carrying_b = false;
+        if (kEnv == RRNCO_ENV_RCVRPTW) {
+          // linehauls_missing: any unvisited node with linehaul demand (lane-strided scan of 128 nodes)
+          for (int n = t; n < N; n += 4)
+            missing |= sm.dem[n] > 0.f && !((vis[n >> 5] >> (n & 31)) & 1u);
+          missing = __any_sync(0xfu << (lane & ~3), missing);
+          carrying_b = sm.demb[cur] > 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kNTMax; ++j) {
+          if (j < NT) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = 8 * j + 2 * t + e;
+              bool ok = false;
+              if (c < N) {
+                const bool v = bit_of(vis, j, 2 * t + e);
+                if (kEnv == RRNCO_ENV_ATSP) {
+                  ok = !v;
+                } else if (kEnv == RRNCO_ENV_RCVRP) {
+                  ok = c >= 1 && !v && !(__fadd_rn(sm.dem[c], f0) > cap);
+                } else if (c >= 1) {
+                  const float dist_ij = D[cur * N + c], dur_ij = U[cur * N + c];
+                  const float arrival = __fadd_rn(f0, dur_ij);
+                  const bool reach_c = arrival < sm.tw1[c];
+                  const bool reach_d =
+                      __fmul_rn(__fadd_rn(__fadd_rn(fmaxf(arrival, sm.tw0[c]), sm.svc[c]), sm.uj0[c]), closed) <
+                      sm.tw1[0];
+                  const bool exc_lim = __fadd_rn(__fadd_rn(f1, dist_ij), __fmul_rn(sm.dj0[c], closed)) > limit;
+                  const bool exc_l = __fadd_rn(sm.dem[c], f2) > cap;
+                  const bool exc_b = __fadd_rn(sm.demb[c], f3) > cap;
+                  const bool ok1 = (missing && !exc_l && !carrying_b && sm.dem[c] > 0.f) ||
+                                   (!exc_b && sm.demb[c] > 0.f);
+                  const bool cannot_l = sm.dem[c] > __fsub_rn(cap, f3);
+                  const bool ok2 = !exc_l && !exc_b && !cannot_l;
+                  const bool okc = (bclass == 1.0f && ok1) || (bclass == 2.0f && ok2);
+                  ok = reach_c && reach_d && okc && !exc_lim && !v;
+                }
+              }
+              if (ok) bits[j >> 2] |= 1u << (8 * (j & 3) + 2 * t + e);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          bits[k] |= __shfl_xor_sync(0xffffffffu, bits[k], 1);
+          bits[k] |= __shfl_xor_sync(0xffffffffu, bits[k], 2);
+        }
+        if (kEnv != RRNCO_ENV_ATSP) {
+          const bool any_cust = ((bits[0] & ~1u) | bits[1] | bits[2] | bits[3]) != 0u;
+          if (!(cur == 0 && any_cust)) bits[0] |= 1u;
+        }
+        if ((bits[0] | bits[1] | bits[2] | bits[3]) == 0u) {  // cannot happen upstream; keep the math finite
+          if (t == 0 && sm.active[row] && !sm.done[row]) atomicOr(p.status, RRNCO_DEV_NO_FEASIBLE);
+          bits[0] |= 1u;
+        }
+        sm.mask[row][t] = t == 0 ? bits[0] : t == 1 ? bits[1] : t == 2 ? bits[2] : bits[3];
+      }
+    }
+    // ---- A2: query rows q = ctx_node_proj[cur] (+ proj2[...]) + sum_k state_k * wstate[k] ------
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int row = warp * 16 + i;
+      const int cur = sm.cur[row];
+      float4 q;
+      if (kEnv == RRNCO_ENV_ATSP) {
+        if (p.use_placeholder && step == 0) {
+          q = *reinterpret_cast<const float4*>(&sm.placeholder[lane * 4]);
+        } else {
+          const float4 a4 = __ldg(reinterpret_cast<const float4*>(P1 + (size_t)sm.first[row] * kE) + lane);
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(P2 + (size_t)cur * kE) + lane);
+          q = make_float4(a4.x + c4.x, a4.y + c4.y, a4.z + c4.z, a4.w + c4.w);
+        }
+      } else {
+        q = __ldg(reinterpret_cast<const float4*>(P1 + (size_t)cur * kE) + lane);
+        float st[kMaxState];
+        if (p.logits_only) {
+#pragma unroll
+          for (int k = 0; k < kMaxState; ++k) st[k] = sm.f[k][row];
+        } else if (kEnv == RRNCO_ENV_RCVRP) {
+          st[0] = __fsub_rn(cap, sm.f[0][row]);
+          st[1] = st[2] = st[3] = 0.f;
+        } else {
+          const float used = sm.f[3][row] == 0.f ? sm.f[2][row] : sm.f[3][row];
+          st[0] = __fsub_rn(cap, used);
+          st[1] = sm.f[0][row];
+          st[2] = closed == 0.f ? 1.f : 0.f;
+          float rem = __fsub_rn(limit, sm.f[1][row]);  // nan_to_num(limit - route, posinf=10)
+          rem = rem == INFINITY ? 10.f : (rem != rem ? 0.f : (rem == -INFINITY ? -3.4028234663852886e38f : rem));
+          st[3] = rem;
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxState; ++k) {
+          if (k < p.n_state) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&sm.wstate[k][lane * 4]);
+            q.x = fmaf(st[k], w4.x, q.x); q.y = fmaf(st[k], w4.y, q.y);
+            q.z = fmaf(st[k], w4.z, q.z); q.w = fmaf(st[k], w4.w, q.w);
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(&sm.A[row * kLdA + lane * 4]) = q;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- C: attention, 16 rows x 8 heads per warp ----------------------------------------------
+    {
+      uint32_t m0[4], m1[4];
+      *reinterpret_cast<uint4*>(m0) = *reinterpret_cast<const uint4*>(sm.mask[r0]);
+      *reinterpret_cast<uint4*>(m1) = *reinterpret_cast<const uint4*>(sm.mask[r1]);
+      const float* sK = sm.Hb;
+      const float* sV = sm.Bs;
+#pragma unroll 1
+      for (int h = 0; h < kH; ++h) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const int k0 = h * kDh + ks * 8 + t;
+          split_tf32(sm.A[r0 * kLdA + k0], ah[ks][0], al[ks][0]);
+          split_tf32(sm.A[r1 * kLdA + k0], ah[ks][1], al[ks][1]);
+          split_tf32(sm.A[r0 * kLdA + k0 + 4], ah[ks][2], al[ks][2]);
+          split_tf32(sm.A[r1 * kLdA + k0 + 4], ah[ks][3], al[ks][3]);
+        }
+        float sc[kNTMax][4];
+#pragma unroll
+        for (int j = 0; j < kNTMax; ++j) {
+          sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+          if (j < NT) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const float* kp = sK + (8 * j + g) * kLdA + h * kDh + ks * 8 + t;
+              uint32_t bh[2], bl[2];
+              split_tf32(kp[0], bh[0], bl[0]);
+              split_tf32(kp[4], bh[1], bl[1]);
+              mma_x<kPasses>(sc[j], ah[ks], al[ks], bh, bl);
+            }
+          }
+        }
+        // masked softmax over the keys (scale 1/sqrt(16) is a power of two: exact)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kNTMax; ++j) {
+          if (j < NT) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              sc[j][e] = bit_of(m0, j, 2 * t + e) ? sc[j][e] * 0.25f : -INFINITY;
+              sc[j][2 + e] = bit_of(m1, j, 2 * t + e) ? sc[j][2 + e] * 0.25f : -INFINITY;
+              mx0 = fmaxf(mx0, sc[j][e]);
+              mx1 = fmaxf(mx1, sc[j][2 + e]);
+            }
+          }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kNTMax; ++j) {
+          if (j < NT) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              sc[j][e] = expf(sc[j][e] - mx0);
+              sc[j][2 + e] = expf(sc[j][2 + e] - mx1);
+              sum0 += sc[j][e];
+              sum1 += sc[j][2 + e];
+            }
+          }
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        // heads = P V_h: the accumulator tile j IS the A fragment of k-step j under the key permutation
+        // k = t -> key 8j + 2t, k = t + 4 -> key 8j + 2t + 1 (applied to the V rows below).
+        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int j = 0; j < kNTMax; ++j) {
+          if (j < NT) {
+            uint32_t ph[4], pl[4];
+            split_tf32(sc[j][0], ph[0], pl[0]);
+            split_tf32(sc[j][2], ph[1], pl[1]);
+            split_tf32(sc[j][1], ph[2], pl[2]);
+            split_tf32(sc[j][3], ph[3], pl[3]);
+#pragma unroll
+            for (int dd = 0; dd < 2; ++dd) {
+              const float* vp = sV + (8 * j + 2 * t) * kLdA + h * kDh + dd * 8 + g;
+              uint32_t bh[2], bl[2];
+              split_tf32(vp[0], bh[0], bl[0]);
+              split_tf32(vp[kLdA], bh[1], bl[1]);
+              mma_x<kPasses>(o[dd], ph, pl, bh, bl);
+            }
+          }
+        }
+        const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+#pragma unroll
+        for (int dd = 0; dd < 2; ++dd) {
+          const int col = h * kDh + dd * 8 + 2 * t;
+          float2* g0 = reinterpret_cast<float2*>(&sm.A[r0 * kLdA + col]);
+          float2* g1 = reinterpret_cast<float2*>(&sm.A[r1 * kLdA + col]);
+          float2 q0 = *g0, q1 = *g1;
+          q0.x += o[dd][0] * inv0; q0.y += o[dd][1] * inv0;
+          q1.x += o[dd][2] * inv1; q1.y += o[dd][3] * inv1;
+          *g0 = q0;  // glimpse = heads + q  (decoder.py:292-293), in place: these columns are only read
+          *g1 = q1;  // by head h of this warp, whose A fragments are already in registers
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();  // all warps done with the K / V tiles; glimpse complete in A
+
+    // ---- E: FFN  g' = W2 relu(W1 g + b1) + b2 + g ---------------------------------------------
+    issue_slice(0, sm, p, Lk, tid);
+    issue_slice(1, sm, p, Lk, tid);
+    int sl = 0;
+    float acc2[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) acc2[mt][nt][0] = acc2[mt][nt][1] = acc2[mt][nt][2] = acc2[mt][nt][3] = 0.f;
+
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float acc1[2][8][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc1[mt][nt][0] = acc1[mt][nt][1] = acc1[mt][nt][2] = acc1[mt][nt][3] = 0.f;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const float* Asrc = half == 0 ? sm.A : sm.Hb;
+#pragma unroll 1
+        for (int ks4 = 0; ks4 < 4; ++ks4, ++sl) {
+          cp_async_wait<1>();
+          __syncthreads();
+          issue_slice(sl + 2, sm, p, Lk, tid);
+          const float* sB = sm.Bs + (sl % kStages) * kStageFloats;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const float* ap = Asrc + (wm * 32 + mt * 16 + g) * kLdA + ks4 * kSliceK + kk * 8 + t;
+              split_tf32(ap[0], ah[mt][0], al[mt][0]);
+              split_tf32(ap[8 * kLdA], ah[mt][1], al[mt][1]);
+              split_tf32(ap[4], ah[mt][2], al[mt][2]);
+              split_tf32(ap[8 * kLdA + 4], ah[mt][3], al[mt][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+              const float* bp = sB + (wn * 64 + nt * 8 + g) * kLdB + kk * 8 + t;
+              uint32_t bh[2], bl[2];
+              split_tf32(bp[0], bh[0], bl[0]);
+              split_tf32(bp[4], bh[1], bl[1]);
+              if (half == 0) {
+                mma_x<kPasses>(acc1[0][nt], ah[0], al[0], bh, bl);
+                mma_x<kPasses>(acc1[1][nt], ah[1], al[1], bh, bl);
+              } else {
+                mma_x<kPasses>(acc2[0][nt], ah[0], al[0], bh, bl);
+                mma_x<kPasses>(acc2[1][nt], ah[1], al[1], bh, bl);
+              }
+            }
+          }
+        }
+        if (half == 0) {
+          // hidden chunk c: relu(acc1 + b1) -> Hb.  Every warp passed >= 1 barrier since it last read Hb
+          // (GEMM2 of chunk c-1 / the K tile), and the next slice barrier publishes these writes.
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+              const int col = wn * 64 + nt * 8 + 2 * t;
+              const int row = wm * 32 + mt * 16 + g;
+              const float bb0 = sm.b1[c * kRows + col], bb1 = sm.b1[c * kRows + col + 1];
+              *reinterpret_cast<float2*>(&sm.Hb[row * kLdA + col]) =
+                  make_float2(fmaxf(acc1[mt][nt][0] + bb0, 0.f), fmaxf(acc1[mt][nt][1] + bb1, 0.f));
+              *reinterpret_cast<float2*>(&sm.Hb[(row + 8) * kLdA + col]) =
+                  make_float2(fmaxf(acc1[mt][nt][2] + bb0, 0.f), fmaxf(acc1[mt][nt][3] + bb1, 0.f));
+            }
+        }
+      }
+    }
+    // residual epilogue: g' = acc2 + b2 + g, in place (each element is read and written by one thread)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = wn * 64 + nt * 8 + 2 * t;
+        const int row = wm * 32 + mt * 16 + g;
+        float2* g0 = reinterpret_cast<float2*>(&sm.A[row * kLdA + col]);
+        float2* g1 = reinterpret_cast<float2*>(&sm.A[(row + 8) * kLdA + col]);
+        float2 v0 = *g0, v1 = *g1;
+        v0.x += acc2[mt][nt][0] + sm.b2[col]; v0.y += acc2[mt][nt][1] + sm.b2[col + 1];
+        v1.x += acc2[mt][nt][2] + sm.b2[col]; v1.y += acc2[mt][nt][3] + sm.b2[col + 1];
+        *g0 = v0;
+        *g1 = v1;
+      }
+
+    // ---- G: pointer logits, row-owner layout (warp = 16 rows x all keys) ------------------------
+    float lg[kNTMax][4];
+#pragma unroll
+    for (int j = 0; j < kNTMax; ++j) lg[j][0] = lg[j][1] = lg[j][2] = lg[j][3] = 0.f;
+#pragma unroll 1
+    for (int ks4 = 0; ks4 < 4; ++ks4, ++sl) {
+      cp_async_wait<1>();
+      __syncthreads();  // first iteration also publishes the residual epilogue
+      issue_slice(sl + 2, sm, p, Lk, tid);
+      const float* sB = sm.Bs + (sl % kStages) * kStageFloats;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t ah[4], al[4];
+        const float* ap = sm.A + r0 * kLdA + ks4 * kSliceK + kk * 8 + t;
+        split_tf32(ap[0], ah[0], al[0]);
+        split_tf32(ap[8 * kLdA], ah[1], al[1]);
+        split_tf32(ap[4], ah[2], al[2]);
+        split_tf32(ap[8 * kLdA + 4], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < kNTMax; ++j) {
+          if (j < NT) {
+            const float* bp = sB + (8 * j + g) * kLdB + kk * 8 + t;
+            uint32_t bh[2], bl[2];
+            split_tf32(bp[0], bh[0], bl[0]);
+            split_tf32(bp[4], bh[1], bl[1]);
+            mma_x<kPasses>(lg[j], ah, al, bh, bl);
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: bias, clip, mask, log-softmax, selection, transition --------------------------
+    const float inv_sqrt_e = 0.08838834764831845f;  // 1 / sqrt(128)
+    const int cur0 = sm.cur[r0], cur1 = sm.cur[r1];
+    bool nan_seen = false;
+#pragma unroll
+    for (int j = 0; j < kNTMax; ++j) {
+      if (j < NT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 8 * j + 2 * t + (e & 1);
+          const int cur = e < 2 ? cur0 : cur1;
+          float l = lg[j][e] * inv_sqrt_e;
+          if (c < N) {
+            nan_seen |= l != l;
+            float bias = __fmul_rn(p.w.alpha, D[cur * N + c]);
+            if (kEnv == RRNCO_ENV_RCVRPTW) bias = __fadd_rn(bias, __fmul_rn(p.w.beta, U[cur * N + c]));
+            l = logf(__fadd_rn(expf(__fsub_rn(l, bias)), 1e-6f));  // decoder.py:198
+          }
+          lg[j][e] = l;
+        }
+      }
+    }
+    if (nan_seen) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
+
+    if (p.logits_only) {
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = rr ? r1 : r0;
+        const int s = tile * kRows + row;
+        if (s < p.S) {
+          float* dst = p.logits_out + ((int64_t)s * p.n_inst + b) * N;
+#pragma unroll
+          for (int j = 0; j < kNTMax; ++j)
+            if (j < NT) {
+              const int c = 8 * j + 2 * t;
+              if (c < N) dst[c] = lg[j][2 * rr];
+              if (c + 1 < N) dst[c + 1] = lg[j][2 * rr + 1];
+            }
+        }
+      }
+      break;
+    }
+
+    uint32_t m0[4], m1[4];
+    *reinterpret_cast<uint4*>(m0) = *reinterpret_cast<const uint4*>(sm.mask[r0]);
+    *reinterpret_cast<uint4*>(m1) = *reinterpret_cast<const uint4*>(sm.mask[r1]);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < kNTMax; ++j) {
+      if (j < NT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool ok = bit_of(e < 2 ? m0 : m1, j, 2 * t + (e & 1));
+          float l = lg[j][e];
+          if (p.w.tanh_clipping > 0.f) l = __fmul_rn(tanhf(l), p.w.tanh_clipping);  // decoding.py:342-343
+          l = ok ? __fdiv_rn(l, p.w.temperature) : -INFINITY;                       // decoding.py:348-351
+          lg[j][e] = l;
+          mx[e >> 1] = fmaxf(mx[e >> 1], l);
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 1));
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 2));
+    }
+    float se[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < kNTMax; ++j)
+      if (j < NT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) se[e >> 1] += expf(lg[j][e] - mx[e >> 1]);
+      }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      se[rr] += __shfl_xor_sync(0xffffffffu, se[rr], 1);
+      se[rr] += __shfl_xor_sync(0xffffffffu, se[rr], 2);
+      se[rr] = logf(se[rr]);
+    }
+    // log-probs (x - max) - log(sum) in the reference's order; selection on them
+    float best[2] = {-INFINITY, -INFINITY};
+    int besti[2] = {0x7fffffff, 0x7fffffff};
+    // reference-layout rollout ids (padded rows shadow the tile's first rollout)
+    const int64_t rg0 = (int64_t)(tile * kRows + (sm.active[r0] ? r0 : 0)) * p.n_inst + b;
+    const int64_t rg1 = (int64_t)(tile * kRows + (sm.active[r1] ? r1 : 0)) * p.n_inst + b;
+#pragma unroll
+    for (int j = 0; j < kNTMax; ++j) {
+      if (j < NT) {
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        if (p.mode == RRNCO_DECODE_SAMPLING)
+          rnd = philox4x32(make_uint4((uint32_t)rg0, (uint32_t)(rg0 >> 32), (uint32_t)step, (uint32_t)(j * 4 + t)),
+                           make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 8 * j + 2 * t + (e & 1);
+          const float lpv = __fsub_rn(__fsub_rn(lg[j][e], mx[e >> 1]), se[e >> 1]);
+          lg[j][e] = lpv;
+          float key = lpv;
+          if (p.mode == RRNCO_DECODE_SAMPLING) {
+            const uint32_t x = e == 0 ? rnd.x : e == 1 ? rnd.y : e == 2 ? rnd.z : rnd.w;
+            key = lpv + (-logf(-logf(u01(x))));  // Gumbel-max
+          }
+          if (key > best[e >> 1]) {  // strict: lowest index wins ties (ascending c within a lane)
+            best[e >> 1] = key;
+            besti[e >> 1] = c;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best[rr], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti[rr], o);
+        if (ov > best[rr] || (ov == best[rr] && oi < besti[rr])) {
+          best[rr] = ov;
+          besti[rr] = oi;
+        }
+      }
+    }
+    int act[2] = {besti[0] == 0x7fffffff ? 0 : besti[0], besti[1] == 0x7fffffff ? 0 : besti[1]};
+    if (p.mode == RRNCO_DECODE_EVALUATE) {
+      const bool have = step < p.forced_T;
+      act[0] = have && sm.active[r0] ? (int)p.forced[rg0 * p.forced_T + step] : act[0];
+      act[1] = have && sm.active[r1] ? (int)p.forced[rg1 * p.forced_T + step] : act[1];
+      act[0] = min(max(act[0], 0), N - 1);
+      act[1] = min(max(act[1], 0), N - 1);
+    }
+    // chosen log-prob: owner lane contributes, quad-sum
+    float chosen[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < kNTMax; ++j)
+      if (j < NT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (8 * j + 2 * t + (e & 1) == act[e >> 1]) chosen[e >> 1] = lg[j][e];
+      }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {  // only the owner lane matched: quad-sum broadcasts its value
+      chosen[rr] += __shfl_xor_sync(0xffffffffu, chosen[rr], 1);
+      chosen[rr] += __shfl_xor_sync(0xffffffffu, chosen[rr], 2);
+    }
+    // one lane per row applies the transition and emits the outputs
+    if (t < 2) {
+      const int rr = t;
+      const int row = rr ? r1 : r0;
+      const int a = act[rr];
+      const int64_t rg = rr ? rg1 : rg0;
+      const bool feasible = (sm.mask[row][a >> 5] >> (a & 31)) & 1u;
+      if (!feasible && sm.active[row]) atomicOr(p.status, RRNCO_DEV_INFEASIBLE);
+      const bool count_leg = kEnv != RRNCO_ENV_ATSP || t_out > 0;
+      transition<kEnv>(sm, p, row, a, D, U, cap, closed, count_leg);
+      if (kEnv == RRNCO_ENV_ATSP && t_out == 0) sm.first[row] = a;
+      sm.lp[row] += (double)chosen[rr];
+      if (sm.active[row] && t_out < p.t_cap) {
+        p.actions[rg * p.t_cap + t_out] = a;
+        if (p.logprob) p.logprob[rg * p.t_cap + t_out] = chosen[rr];
+      }
+    }
+    ++step;
+    ++t_out;
+  }
+
+  if (p.logits_only) return;
+  // ---------------- exit: close the tours, publish per-rollout sums ----------------
+  __syncthreads();
+  if (tid < kRows && sm.active[tid]) {
+    const int row = tid;
+    const int64_t r = (int64_t)(tile * kRows + row) * p.n_inst + b;
+    const int last = sm.cur[row];
+    float leg;
+    if (kEnv == RRNCO_ENV_ATSP) {
+      leg = D[last * N + sm.first[row]];
+    } else {
+      leg = D[last * N];  // back to the depot (go_to = roll(go_from, -1), rcvrp/env.py:203)
+      if (kEnv == RRNCO_ENV_RCVRPTW) leg = __fmul_rn(leg, closed);
+    }
+    p.ws_len[r] = sm.len[row] + (double)leg;
+    p.ws_lp[r] = sm.lp[row];
+  }
+  if (tid == 0) {
+    p.ws_tile_steps[blockIdx.x] = t_out;
+    atomicMax(p.max_steps_out, t_out);
+  }
+}
+
+// After the rollout: pad legs (0 -> 0) up to the global length, de-normalised reward, zero action tails.
+template <int kEnv>
+__global__ void __launch_bounds__(256) finalize_kernel(RolloutParams p, float* loglik, float* norm_out, float* real_out) {
+  const int64_t R = p.n_inst * (int64_t)p.S;
+  const int t_glob = *p.max_steps_out;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = r % p.n_inst;
+    const int s = (int)(r / p.n_inst);
+    const int64_t drow = b % p.d.data_rows;
+    const int t_own = p.ws_tile_steps[b * p.n_tiles + s / kRows];
+    double len = p.ws_len[r];
+    if (kEnv != RRNCO_ENV_ATSP && t_glob > t_own) {
+      float d00 = p.d.distance[drow * (int64_t)p.N * p.N];
+      if (kEnv == RRNCO_ENV_RCVRPTW && p.d.open_route[drow]) d00 = __fmul_rn(d00, 0.f);
+      len += (double)(t_glob - t_own) * (double)d00;
+    }
+    const float neg = -(float)len;
+    if (norm_out) norm_out[r] = neg;
+    if (real_out) {
+      const float mn = p.d.min_distance[drow], mx = p.d.max_distance[drow];
+      real_out[r] = __fadd_rn(__fmul_rn(neg, __fadd_rn(__fsub_rn(mx, mn), 1e-6f)), mn);
+    }
+    if (loglik) loglik[r] = (float)p.ws_lp[r];
+    for (int tt = t_own; tt < t_glob && tt < p.t_cap; ++tt) {
+      p.actions[r * p.t_cap + tt] = 0;
+      if (p.logprob) p.logprob[r * p.t_cap + tt] = 0.f;
+    }
+  }
+}
+
+}  // namespace rrnco
+
+using namespace rrnco;
+
+namespace {
+
+template <int kEnv, int kNTMax, int kPasses>
+int launch_rollout(const RolloutParams& p, cudaStream_t st) {
+  auto kern = rollout_kernel<kEnv, kNTMax, kPasses>;
+  static bool configured = false;  // idempotent attribute; benign if raced
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess)
+      return RRNCO_ERR_CUDA;
+    configured = true;
+  }
+  const int64_t grid = p.n_inst * p.n_tiles;
+  if (grid <= 0 || grid > 0x7fffffffLL) return RRNCO_ERR_UNSUPPORTED;
+  kern<<<(unsigned)grid, kThreads, sizeof(Smem), st>>>(p);
+  return rrnco_launch_status();
+}
+
+template <int kEnv>
+int dispatch_rollout(const RolloutParams& p, int passes, cudaStream_t st) {
+  if (p.NT <= 13) return passes == 1 ? launch_rollout<kEnv, 13, 1>(p, st) : launch_rollout<kEnv, 13, 3>(p, st);
+  return passes == 1 ? launch_rollout<kEnv, 16, 1>(p, st) : launch_rollout<kEnv, 16, 3>(p, st);
+}
+
+int dispatch_env(const RolloutParams& p, int env, int passes, cudaStream_t st) {
+  switch (env) {
+    case RRNCO_ENV_ATSP: return dispatch_rollout<RRNCO_ENV_ATSP>(p, passes, st);
+    case RRNCO_ENV_RCVRP: return dispatch_rollout<RRNCO_ENV_RCVRP>(p, passes, st);
+    case RRNCO_ENV_RCVRPTW: return dispatch_rollout<RRNCO_ENV_RCVRPTW>(p, passes, st);
+    default: return RRNCO_ERR_BAD_ARG;
+  }
+}
+
+inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+int check_common(int32_t env, int32_t N, int64_t n_inst, int32_t S, const rrnco_decoder_weights_t* w,
+                 const rrnco_decoder_cache_t* c, const rrnco_instance_data_t* d) {
+  RRNCO_CHECK_ARG(w && c && d && n_inst > 0 && S > 0 && N > 1);
+  RRNCO_CHECK_ARG(env >= 0 && env <= 2);
+  if (N > RRNCO_MAX_NODES_FUSED) return RRNCO_ERR_UNSUPPORTED;
+  RRNCO_CHECK_ARG(w->ffn_w1 && w->ffn_b1 && w->ffn_w2 && w->ffn_b2 && w->temperature > 0.f);
+  RRNCO_CHECK_ARG(c->glimpse_key && c->glimpse_val && c->logit_key && c->ctx_node_proj);
+  RRNCO_CHECK_ARG(aligned16(w->ffn_w1) && aligned16(w->ffn_w2) && aligned16(c->glimpse_key) &&
+                  aligned16(c->glimpse_val) && aligned16(c->logit_key) && aligned16(c->ctx_node_proj));
+  RRNCO_CHECK_ARG(d->data_rows > 0 && d->distance);
+  if (env == RRNCO_ENV_ATSP) RRNCO_CHECK_ARG(c->ctx_node_proj2 && aligned16(c->ctx_node_proj2));
+  if (env != RRNCO_ENV_ATSP) RRNCO_CHECK_ARG(w->ctx_state_w != nullptr);
+  if (env == RRNCO_ENV_RCVRPTW) RRNCO_CHECK_ARG(d->duration != nullptr);
+  return RRNCO_OK;
+}
+
+int g_passes = 3;  // set through rrnco_set_precision (process-wide default, read-only on the hot path)
+
+}  // namespace
+
+extern "C" {
+
+// precision of the in-kernel contractions: 3 = 3xTF32 (fp32-faithful, default), 1 = single TF32 pass
+int rrnco_set_precision(int32_t passes) {
+  if (passes != 1 && passes != 3) return RRNCO_ERR_BAD_ARG;
+  g_passes = passes;
+  return RRNCO_OK;
+}
+
+int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts) {
+  (void)env; (void)n_nodes;
+  if (n_inst <= 0 || n_starts <= 0) return 0;
+  const int64_t R = n_inst * n_starts;
+  const int64_t tiles = n_inst * ((n_starts + kRows - 1) / kRows);
+  return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL);
+}
+
+int rrnco_decoder_logits(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts,
+                         const rrnco_decoder_weights_t* w, const rrnco_decoder_cache_t* cache,
+                         const rrnco_instance_data_t* data, const int64_t* current, const int64_t* first,
+                         const uint8_t* mask, const float* ctx_state, int32_t use_placeholder, float* logits_out,
+                         uint32_t* status, void* stream) {
+  int rc = check_common(env, n_nodes, n_inst, n_starts, w, cache, data);
+  if (rc != RRNCO_OK) return rc;
+  RRNCO_CHECK_ARG(current && mask && logits_out && status);
+  RRNCO_CHECK_ARG(env == RRNCO_ENV_ATSP ? first != nullptr : ctx_state != nullptr);
+  RRNCO_CHECK_ARG(!use_placeholder || w->ctx_placeholder_q);
+  RolloutParams p{};
+  p.N = n_nodes; p.NT = (n_nodes + 7) / 8; p.S = n_starts; p.n_tiles = (n_starts + kRows - 1) / kRows;
+  p.n_state = env == RRNCO_ENV_ATSP ? 0 : env == RRNCO_ENV_RCVRP ? 1 : 4;
+  p.n_inst = n_inst; p.logits_only = 1; p.use_placeholder = use_placeholder; p.max_steps = 1;
+  p.w = *w; p.c = *cache; p.d = *data;
+  p.in_cur = current; p.in_first = first; p.in_mask = mask; p.in_state = ctx_state; p.logits_out = logits_out;
+  p.status = status;
+  return dispatch_env(p, env, g_passes, (cudaStream_t)stream);
+}
+
+int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts, int32_t multistart,
+                  int32_t decode_mode, uint64_t seed, const rrnco_decoder_weights_t* w,
+                  const rrnco_decoder_cache_t* cache, const rrnco_instance_data_t* data,
+                  const int64_t* forced_actions, int32_t forced_T, int32_t t_cap, int64_t* actions_out,
+                  float* logprob_out, float* loglik_out, float* norm_reward_out, float* real_reward_out,
+                  int32_t* max_steps_out, uint32_t* status, void* workspace, void* stream) {
+  int rc = check_common(env, n_nodes, n_inst, n_starts, w, cache, data);
+  if (rc != RRNCO_OK) return rc;
+  RRNCO_CHECK_ARG(actions_out && max_steps_out && status && workspace && aligned16(workspace) && t_cap > 0);
+  RRNCO_CHECK_ARG(decode_mode >= 0 && decode_mode <= 2);
+  RRNCO_CHECK_ARG(multistart || n_starts == 1);
+  RRNCO_CHECK_ARG(decode_mode != RRNCO_DECODE_EVALUATE || (forced_actions && forced_T > 0));
+  RRNCO_CHECK_ARG(real_reward_out == nullptr || (data->min_distance && data->max_distance));
+  if (env == RRNCO_ENV_RCVRP) RRNCO_CHECK_ARG(data->demand && data->vehicle_capacity);
+  if (env == RRNCO_ENV_RCVRPTW)
+    RRNCO_CHECK_ARG(data->demand && data->demand_backhaul && data->time_windows && data->service_time &&
+                    data->vehicle_capacity && data->distance_limit && data->open_route && data->backhaul_class);
+  if (env == RRNCO_ENV_ATSP && !multistart) RRNCO_CHECK_ARG(w->ctx_placeholder_q != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  RolloutParams p{};
+  p.N = n_nodes; p.NT = (n_nodes + 7) / 8; p.S = n_starts; p.n_tiles = (n_starts + kRows - 1) / kRows;
+  p.n_state = env == RRNCO_ENV_ATSP ? 0 : env == RRNCO_ENV_RCVRP ? 1 : 4;
+  p.n_inst = n_inst; p.multistart = multistart; p.mode = decode_mode; p.use_placeholder = !multistart;
+  p.t_cap = t_cap; p.forced_T = forced_T; p.max_steps = t_cap - (multistart ? 1 : 0); p.seed = seed;
+  p.w = *w; p.c = *cache; p.d = *data;
+  p.forced = forced_actions; p.actions = actions_out; p.logprob = logprob_out;
+  const int64_t R = n_inst * n_starts;
+  p.ws_len = reinterpret_cast<double*>(workspace);
+  p.ws_lp = p.ws_len + R;
+  p.ws_tile_steps = reinterpret_cast<int32_t*>(p.ws_lp + R);
+  p.max_steps_out = max_steps_out; p.status = status;
+  if (cudaMemsetAsync(max_steps_out, 0, sizeof(int32_t), st) != cudaSuccess) return RRNCO_ERR_CUDA;
+  rc = dispatch_env(p, env, g_passes, st);
+  if (rc != RRNCO_OK) return rc;
+  const unsigned fgrid = (unsigned)((R + 255) / 256 > 4096 ? 4096 : (R + 255) / 256);
+  switch (env) {
+    case RRNCO_ENV_ATSP: finalize_kernel<RRNCO_ENV_ATSP><<<fgrid, 256, 0, st>>>(p, loglik_out, norm_reward_out, real_reward_out); break;
+    case RRNCO_ENV_RCVRP: finalize_kernel<RRNCO_ENV_RCVRP><<<fgrid, 256, 0, st>>>(p, loglik_out, norm_reward_out, real_reward_out); break;
+    default: finalize_kernel<RRNCO_ENV_RCVRPTW><<<fgrid, 256, 0, st>>>(p, loglik_out, norm_reward_out, real_reward_out); break;
+  }
+  return rrnco_launch_status();
+}
+
+}  // extern "C"

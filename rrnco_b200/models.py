@@ -1,0 +1,335 @@
+"""Drop-in decoder / policy: the reference's `RRNetDecoder` and `RRNetPolicy` call surface with the per-step
+decoder and the whole decode loop running as fused sm_100a kernels (librrnco_b200).
+
+  RRNetDecoder  <- rrnco/models/decoder.py:46-232 (+ RRNet_PointerAttention :235-329); parameter names are
+                   identical, so reference checkpoints load with `load_state_dict`.
+  RRNetPolicy   <- rrnco/models/policy.py:19-255; `forward` returns the same out-dict.  The encoder stays the
+                   reference's PyTorch module (pass it as `encoder=`), as BASELINE.json's north star states.
+
+Unsupported reference options raise NotImplementedError (beam search, top-k / top-p, select_best,
+store_all_logp / return_entropy, mask_logits=False, dynamic embeddings): they are not on any BASELINE config.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib
+from ._lib import DECODE_ID, ENV_ID, DecoderCache, DecoderWeights, InstanceData, call, ptr, stream_ptr
+from .envs import _u8
+
+CTX_IN = {"atsp": 256, "rcvrp": 129, "rcvrptw": 132}
+N_STATE = {"atsp": 0, "rcvrp": 1, "rcvrptw": 4}
+
+
+@dataclass
+class PrecomputedCache:
+    """decoder.py:25-43, plus the node half of the context projection the fused kernels consume."""
+    node_embeddings: Tensor
+    graph_context: Union[Tensor, float]
+    glimpse_key: Tensor
+    glimpse_val: Tensor
+    logit_key: Tensor
+    ctx_node_proj: Optional[Tensor] = None
+    ctx_node_proj2: Optional[Tensor] = None
+
+    def struct(self) -> DecoderCache:
+        c = DecoderCache()
+        c.glimpse_key, c.glimpse_val, c.logit_key = ptr(self.glimpse_key), ptr(self.glimpse_val), ptr(self.logit_key)
+        c.ctx_node_proj, c.ctx_node_proj2 = ptr(self.ctx_node_proj), ptr(self.ctx_node_proj2)
+        return c
+
+
+class _Context(nn.Module):
+    """Parameter holder named like rl4co's EnvContext (project_context [+ W_placeholder for atsp])."""
+
+    def __init__(self, env_name, embed_dim):
+        super().__init__()
+        self.project_context = nn.Linear(CTX_IN[env_name], embed_dim, bias=False)
+        if env_name == "atsp":
+            self.W_placeholder = nn.Parameter(torch.Tensor(2 * embed_dim).uniform_(-1, 1))
+
+
+class _FFN(nn.Module):
+    def __init__(self, embed_dim):
+        super().__init__()
+        self.lins = nn.ModuleList([nn.Linear(embed_dim, 4 * embed_dim), nn.Linear(4 * embed_dim, embed_dim)])
+
+
+class _Pointer(nn.Module):
+    def __init__(self, embed_dim):
+        super().__init__()
+        self.project_out = nn.Linear(embed_dim, embed_dim, bias=False)  # unused upstream too (decoder.py:295)
+        self.ffn = _FFN(embed_dim)
+
+
+def instance_data_from_td(env_name: str, td, keep: list) -> InstanceData:
+    """InstanceData over a reset td; rows are indexed by instance (b % data_rows)."""
+    def put(t, dtype=torch.float32):
+        t = _u8(t) if dtype == torch.uint8 else t.to(dtype).contiguous()
+        keep.append(t)
+        return ptr(t)
+
+    d = InstanceData()
+    d.data_rows = td["distance_matrix"].shape[0]
+    d.distance = put(td["distance_matrix"])
+    if "min_distance" in td.keys():
+        d.min_distance, d.max_distance = put(td["min_distance"]), put(td["max_distance"])
+    if env_name == "rcvrp":
+        d.demand = put(td["demand"])
+        d.vehicle_capacity = put(td["vehicle_capacity"].reshape(-1))
+    elif env_name == "rcvrptw":
+        d.duration = put(td["duration_matrix"])
+        d.demand = put(td["demand_linehaul"])
+        d.demand_backhaul = put(td["demand_backhaul"])
+        d.time_windows = put(td["time_windows"])
+        d.service_time = put(td["service_time"])
+        d.vehicle_capacity = put(td["vehicle_capacity"].reshape(-1))
+        d.distance_limit = put(td["distance_limit"].reshape(-1))
+        d.open_route = put(td["open_route"].reshape(-1), torch.uint8)
+        d.backhaul_class = put(td["backhaul_class"].reshape(-1))
+    return d
+
+
+class RRNetDecoder(nn.Module):
+    def __init__(self, embed_dim: int = 128, num_heads: int = 8, env_name: str = "rcvrp", mask_inner: bool = True,
+                 out_bias_pointer_attn: bool = False, linear_bias: bool = False, use_graph_context: bool = True,
+                 check_nan: bool = True, **unused):
+        super().__init__()
+        env_name = getattr(env_name, "name", env_name)
+        if env_name not in ENV_ID:
+            raise ValueError(f"Unknown environment name '{env_name}'. Available: {list(ENV_ID)}")
+        if embed_dim != 128 or num_heads != 8:
+            raise NotImplementedError("the fused kernels are built for embed_dim 128, 8 heads (experiment/rrnet.yaml)")
+        if not mask_inner or out_bias_pointer_attn or linear_bias:
+            raise NotImplementedError("mask_inner=False / pointer or linear biases are not on the reference's configs")
+        self.env_name, self.embed_dim, self.num_heads = env_name, embed_dim, num_heads
+        self.check_nan = check_nan
+        if env_name == "rcvrptw":
+            self.beta = nn.Parameter(torch.tensor([1.0]))
+        self.context_embedding = _Context(env_name, embed_dim)
+        self.pointer = _Pointer(embed_dim)
+        self.project_node_embeddings = nn.Linear(embed_dim, 3 * embed_dim, bias=False)
+        self.project_fixed_context = nn.Linear(embed_dim, embed_dim, bias=False)  # unused: graph_context = 0
+        self.alpha = nn.Parameter(torch.tensor([1.0]))
+        self.is_dynamic_embedding = False
+        self._wcache = None
+
+    # -- weights handed to the kernels ---------------------------------------------------------------
+    def kernel_weights(self, temperature: float = 1.0, tanh_clipping: float = 10.0):
+        """(DecoderWeights struct, keep-alive list)."""
+        E = self.embed_dim
+        keep = []
+        w = DecoderWeights()
+
+        def put(t):
+            t = t.detach().to(torch.float32).contiguous()
+            keep.append(t)
+            return ptr(t)
+
+        lins = self.pointer.ffn.lins
+        w.ffn_w1, w.ffn_b1, w.ffn_w2, w.ffn_b2 = put(lins[0].weight), put(lins[0].bias), put(lins[1].weight), put(lins[1].bias)
+        wc = self.context_embedding.project_context.weight.detach().float()
+        if self.env_name != "atsp":
+            w.ctx_state_w = put(wc[:, E:].t())  # [n_state, E]
+        else:
+            w.ctx_placeholder_q = put(wc @ self.context_embedding.W_placeholder.detach().float())
+        beta = self.beta if self.env_name == "rcvrptw" else self.alpha
+        key = (self.alpha._version, beta._version, self.alpha.data_ptr())
+        if self._wcache is None or self._wcache[0] != key:  # one D2H read per parameter update, not per call
+            self._wcache = (key, torch.stack([self.alpha.detach().float().reshape(()),
+                                              beta.detach().float().reshape(())]).tolist())
+        w.alpha, w.beta = self._wcache[1]
+        w.tanh_clipping, w.temperature = float(tanh_clipping), float(temperature)
+        return w, keep
+
+    # -- reference API ---------------------------------------------------------------------------------
+    def _precompute_cache(self, embeddings: Tuple[Tensor, Tensor], num_starts: int = 0) -> PrecomputedCache:
+        row_emb, col_emb = embeddings
+        row_emb, col_emb = row_emb.float().contiguous(), col_emb.float().contiguous()
+        B, N, E = col_emb.shape
+        outs = [torch.empty_like(col_emb) for _ in range(4)]
+        p2 = torch.empty_like(col_emb) if self.env_name == "atsp" else None
+        wn = self.project_node_embeddings.weight.detach().float().contiguous()
+        wc = self.context_embedding.project_context.weight.detach().float().contiguous()
+        call("rrnco_precompute_cache", ENV_ID[self.env_name], B, N, ptr(row_emb), ptr(col_emb), ptr(wn), ptr(wc),
+             wc.shape[1], ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), ptr(p2), stream_ptr(col_emb.device))
+        return PrecomputedCache(node_embeddings=row_emb, graph_context=0, glimpse_key=outs[0], glimpse_val=outs[1],
+                                logit_key=outs[2], ctx_node_proj=outs[3], ctx_node_proj2=p2)
+
+    def pre_decoder_hook(self, td, env, embeddings, num_starts: int = 0):
+        return td, env, self._precompute_cache(embeddings, num_starts=num_starts)
+
+    def _ctx_state(self, td):
+        if self.env_name == "rcvrp":
+            return (td["vehicle_capacity"] - td["used_capacity"]).float()
+        used = torch.where(td["used_capacity_backhaul"] == 0, td["used_capacity_linehaul"], td["used_capacity_backhaul"])
+        rem = torch.nan_to_num(td["distance_limit"] - td["current_route_length"], posinf=10)
+        return torch.cat((td["vehicle_capacity"] - used, td["current_time"], td["open_route"].float(), rem), -1).float()
+
+    def forward(self, td, cached: PrecomputedCache, num_starts: int = 0) -> Tuple[Tensor, Tensor]:
+        """One decode step: (logits [R,N] fp32 after the distance/duration bias, mask [R,N] bool)."""
+        mask = td["action_mask"].contiguous()
+        R, N = mask.shape
+        S = num_starts if num_starts > 1 else 1
+        n_inst = R // S
+        if cached.glimpse_key.shape[0] != n_inst:
+            raise ValueError(f"cache holds {cached.glimpse_key.shape[0]} instances, td implies {n_inst}")
+        keep = []
+        w, keep_w = self.kernel_weights()
+        data = InstanceData()  # the logits kernel only needs the matrices (bias rows)
+        data.data_rows = td["distance_matrix"].shape[0]
+        dm = td["distance_matrix"].float().contiguous()
+        keep.append(dm)
+        data.distance = ptr(dm)
+        if self.env_name == "rcvrptw":
+            du = td["duration_matrix"].float().contiguous()
+            keep.append(du)
+            data.duration = ptr(du)
+        cur = td["current_node"].reshape(-1).contiguous()
+        first, state, placeholder = None, None, 0
+        if self.env_name == "atsp":
+            first = td["first_node"].reshape(-1).contiguous()
+            if S == 1:  # only reachable without multistart; upstream syncs here too (TSPContext .item())
+                placeholder = int(int(td["i"].reshape(-1)[0]) < 1)
+        else:
+            state = self._ctx_state(td).contiguous()
+        logits = torch.empty((R, N), dtype=torch.float32, device=mask.device)
+        status = torch.zeros(1, dtype=torch.int32, device=mask.device)
+        cs = cached.struct()
+        call("rrnco_decoder_logits", ENV_ID[self.env_name], N, n_inst, S, C.byref(w), C.byref(cs), C.byref(data),
+             ptr(cur), ptr(first), ptr(_u8(mask)), ptr(state), placeholder, ptr(logits), ptr(status),
+             stream_ptr(mask.device))
+        if self.check_nan:  # upstream asserts (and syncs) every step: decoder.py:303-304
+            _lib.raise_device_status(int(status.item()) & _lib.DEV_NAN_LOGITS)
+        return logits, mask
+
+
+class RRNetPolicy(nn.Module):
+    def __init__(self, encoder: nn.Module = None, decoder: nn.Module = None, embed_dim: int = 128,
+                 num_heads: int = 8, env_name: str = "rcvrp", temperature: float = 1.0, tanh_clipping: float = 10.0,
+                 mask_logits: bool = True, train_decode_type: str = "sampling", val_decode_type: str = "greedy",
+                 test_decode_type: str = "greedy", check_nan: bool = True, **unused_kwargs):
+        super().__init__()
+        env_name = getattr(env_name, "name", env_name)
+        if encoder is None:
+            raise ValueError("pass the reference's RRNetEncoder (or any module returning (row_emb, col_emb)) as "
+                             "`encoder=`: the encoder stays in the reference PyTorch path")
+        if not mask_logits:
+            raise NotImplementedError("mask_logits=False")
+        self.encoder = encoder
+        self.decoder = decoder if decoder is not None else RRNetDecoder(embed_dim, num_heads, env_name, check_nan=check_nan)
+        self.env_name = env_name
+        self.temperature, self.tanh_clipping, self.mask_logits = temperature, tanh_clipping, mask_logits
+        self.train_decode_type, self.val_decode_type, self.test_decode_type = (
+            train_decode_type, val_decode_type, test_decode_type)
+        self.seed = 1234
+        self._calls = 0
+
+    def forward(self, td, env=None, phase: str = "train", calc_reward: bool = True, return_actions: bool = True,
+                return_entropy: bool = False, return_hidden: bool = False, return_init_embeds: bool = False,
+                return_sum_log_likelihood: bool = True, actions=None, max_steps=1_000_000, **decoding_kwargs) -> dict:
+        if env is None or isinstance(env, str):
+            raise ValueError("pass an instantiated rrnco_b200 env")
+        if return_entropy or decoding_kwargs.get("store_all_logp"):
+            raise NotImplementedError("store_all_logp / return_entropy")
+        for k in ("top_k", "top_p"):
+            if decoding_kwargs.get(k):
+                raise NotImplementedError(k)
+        if decoding_kwargs.get("select_best"):
+            raise NotImplementedError("select_best")
+        if td.device.type != "cuda":
+            td = td.to(env.device)
+
+        row_emb, col_emb = self.encoder(td, phase=phase)  # policy.py:176
+
+        decode_type = decoding_kwargs.pop("decode_type", None)
+        if actions is not None:
+            decode_type = "evaluate"
+        elif decode_type is None:
+            decode_type = getattr(self, f"{phase}_decode_type")
+        if decode_type.replace("multistart_", "") not in DECODE_ID:
+            raise NotImplementedError(f"decode type '{decode_type}' (only greedy / sampling / evaluate [+ multistart_])")
+        num_starts = decoding_kwargs.pop("num_starts", None)
+        multistart = "multistart" in decode_type  # decoding.py:31-32
+        if num_starts is not None:  # decoding.py:117-118
+            multistart = num_starts > 1
+        if multistart and num_starts is None:
+            num_starts = env.get_num_starts(td)  # decoding.py:162-163
+        S = num_starts if multistart else 1
+        temperature = decoding_kwargs.pop("temperature", self.temperature)
+        tanh_clipping = decoding_kwargs.pop("tanh_clipping", self.tanh_clipping)
+
+        cache = self.decoder._precompute_cache((row_emb, col_emb), num_starts=S)
+        self._calls += 1
+        out = fused_rollout(self.decoder, cache, env, td, S, multistart, decode_type.replace("multistart_", ""),
+                            forced_actions=actions, seed=decoding_kwargs.pop("seed", self.seed + self._calls),
+                            temperature=temperature, tanh_clipping=tanh_clipping, calc_reward=calc_reward,
+                            per_step_logprobs=not return_sum_log_likelihood, check=self.decoder.check_nan)
+        outdict = {"reward": out["reward"],
+                   "log_likelihood": out["log_likelihood"] if return_sum_log_likelihood else out["logprobs"]}
+        if calc_reward and env.normalize:
+            outdict["normalized_reward"] = out["normalized_reward"]
+        if return_actions:
+            outdict["actions"] = out["actions"]
+        if return_hidden:
+            outdict["hidden"] = cache
+        return outdict
+
+
+def fused_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_starts: int, multistart: bool,
+                  kind: str, forced_actions=None, seed: int = 0, temperature: float = 1.0, tanh_clipping: float = 10.0,
+                  calc_reward: bool = True, per_step_logprobs: bool = False, check: bool = True,
+                  t_cap: Optional[int] = None) -> dict:
+    """policy.py:203-243 as ONE kernel launch (+ a finalize kernel).  `td` is the reset td ([n_inst] batch)."""
+    name = decoder.env_name
+    dev = cache.glimpse_key.device
+    n_inst, N, _ = cache.glimpse_key.shape
+    S = int(num_starts)
+    R = n_inst * S
+    if N > _lib.MAX_NODES_FUSED:
+        raise NotImplementedError(f"fused rollout supports N <= {_lib.MAX_NODES_FUSED} nodes (got {N})")
+    keep = []
+    w, keep_w = decoder.kernel_weights(temperature, tanh_clipping)
+    data = instance_data_from_td(name, td, keep)
+    if t_cap is None:
+        t_cap = N if name == "atsp" else 2 * N
+    forced, forced_T = None, 0
+    if kind == "evaluate":
+        fa = forced_actions.to(dev).contiguous()
+        if multistart:
+            pass  # the given decisions follow the forced start (policy.py:214-218)
+        forced, forced_T = fa, fa.shape[1]
+        t_cap = max(t_cap, forced_T + (1 if multistart else 0))
+    acts = torch.empty((R, t_cap), dtype=torch.int64, device=dev)
+    logp = torch.empty((R, t_cap), dtype=torch.float32, device=dev) if per_step_logprobs else None
+    ll = torch.empty(R, dtype=torch.float32, device=dev)
+    norm = torch.empty(R, dtype=torch.float32, device=dev)
+    has_minmax = "min_distance" in td.keys()
+    real = torch.empty(R, dtype=torch.float32, device=dev) if has_minmax else None
+    info = torch.zeros(2, dtype=torch.int32, device=dev)  # [max_steps, status]
+    ws_bytes = _lib.lib().rrnco_rollout_workspace_bytes(ENV_ID[name], N, n_inst, S)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cs = cache.struct()
+    call("rrnco_rollout", ENV_ID[name], N, n_inst, S, int(multistart), DECODE_ID[kind], int(seed) & (2**64 - 1),
+         C.byref(w), C.byref(cs), C.byref(data), ptr(forced), forced_T, t_cap, ptr(acts), ptr(logp), ptr(ll),
+         ptr(norm), ptr(real), ptr(info[0:1]), ptr(info[1:2]), ptr(ws), stream_ptr(dev))
+    T, status = info.tolist()  # the ONE host sync of the rollout (upstream: 3-5 per decode step)
+    if check:
+        _lib.raise_device_status(status)
+    out = {"actions": acts[:, :T], "log_likelihood": ll}
+    if per_step_logprobs:
+        out["logprobs"] = logp[:, :T]
+    if calc_reward:
+        if env.normalize and has_minmax:
+            out["reward"], out["normalized_reward"] = real, norm
+        else:
+            out["reward"] = norm
+    else:  # upstream returns the (all-zero) step reward of the last env.step
+        out["reward"] = torch.zeros(R, dtype=torch.float32 if name == "rcvrptw" else torch.bool, device=dev)
+    return out
