@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- RCVRP n=100 POMO rollout throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (fused construction rollout: decode loop + env step + reward) over one
+batch of BASELINE config[1]: RCVRP n=100, 1024 instances x 8 augmentations x 101 POMO starts, greedy.
+Instances are independent, so each rank owns its own 1024 instances (weak scaling, no data-path collective);
+the only collective is one all-gather of the best costs per step.
+
+Printed JSON line (rank 0): see the contract in the task statement; extra keys
+  roofline      dominant kernel (rollout_kernel) vs the measured HBM peak, algorithmic bytes per SURVEY.md 8(d)
+  cpu_baseline  the CPU oracle (= line-faithful restatement of the reference's eager rollout) on this box's cores
+  e2e           same metric through RRNetPolicy.forward with HOST (pinned) inputs, H2D/D2H inside the timing
+`--impl reference` times the reference's own CPU path (oracle port; rl4co cannot be installed offline).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_LOC, N_AUG, N_START = 100, 8, 101
+BYTES_PER_ROLLOUT_STEP = 737 + 404 + 512 + 12 + 1536   # env step + bias row + ctx gather + out + K/V/Lk / S
+FLOPS_PER_ROLLOUT_STEP = 373_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="instances per GPU per step")
+    ap.add_argument("--precision", type=int, default=3, choices=[1, 3], help="3 = 3xTF32 fp32-faithful (headline)")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="instances in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic workload: city-like asymmetric 1000-node matrix -> sub-sampled instances
+# --------------------------------------------------------------------------------------------------
+def make_city(city_id=0, length=1000):
+    rng = np.random.default_rng(1000 + city_id)
+    pts = rng.uniform(0.0, 3.0, size=(length, 2))
+    eu = np.linalg.norm(pts[:, None, :] - pts[None, :, :], axis=-1)
+    dist = eu * (1.2 + 0.4 * rng.uniform(size=(length, length)))
+    np.fill_diagonal(dist, 0.0)
+    return {"points": pts, "distance": dist}
+
+
+def host_instances(batch, seed):
+    """Raw instance batch on the HOST (what a DataLoader hands to env.reset): fp32, pinned."""
+    city = make_city(seed % 10)
+    rng = np.random.RandomState(seed)
+    idx = np.array([rng.choice(1000, N_LOC + 1, replace=False) for _ in range(batch)])
+    dm = torch.from_numpy(city["distance"][idx[:, :, None], idx[:, None, :]].astype(np.float32))
+    pts = torch.from_numpy(city["points"][idx].astype(np.float32))
+    g = torch.Generator().manual_seed(seed)
+    demand = torch.randint(1, 10, (batch, N_LOC), generator=g).float() / 50.0
+    return {"locs": pts[:, 1:].contiguous(), "depot": pts[:, :1].contiguous(), "demand": demand, "distance_matrix": dm}
+
+
+def stand_in_embeddings(n_inst, seed):
+    """Encoder output stand-in (the encoder stays the reference's PyTorch module and is not on this path):
+    unit-variance embeddings, as an instance-normalised encoder produces."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n_inst, N_LOC + 1, 128, generator=g), torch.randn(n_inst, N_LOC + 1, 128, generator=g)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows)
+        out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_max_mhz"] = float(rows[0][2])
+        out["power_w_max"] = max(float(r[3]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for i, n in enumerate(names) if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows)]
+        out["samples"] = len(rows)
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (line-faithful restatement of the reference's eager rollout) on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_rollout_rate(n_inst_sample, threads, seed=4242):
+    from oracle import envs as oenvs, model as omodel
+    from oracle.td import TD, batchify
+    torch.set_num_threads(threads)
+    raw = host_instances(n_inst_sample, seed)
+    env = oenvs.RCVRPEnv(N_LOC, check_solution=False)
+    p = omodel.init_decoder_params("rcvrp", seed=1234)
+    row, col = stand_in_embeddings(n_inst_sample * N_AUG, seed)
+    with torch.inference_mode():
+        t0 = time.perf_counter()
+        td = env.reset(TD(raw, batch_size=[n_inst_sample]))
+        td = batchify(td, N_AUG)  # StateAugmentation = batchify(td, 8) (distance matrices identical across augs)
+        out = omodel.policy_forward(p, env, td, row, col, decode_type="multistart_greedy", num_starts=N_START)
+        best = out["reward"].view(N_START, N_AUG, n_inst_sample).amax(0).amax(0)
+        dt = time.perf_counter() - t0
+    return n_inst_sample / dt, dt, float(-best.mean()), int(out["actions"].shape[1])
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rates = []
+    for i in range(args.warmup + args.steps):
+        rate, dt, cost, T = cpu_rollout_rate(args.cpu_sample, threads, seed=4242 + i)
+        if i >= args.warmup:
+            rates.append((rate, dt))
+    value = sum(args.cpu_sample for _ in rates) / sum(dt for _, dt in rates)
+    sample = f"{args.cpu_sample} instances x {N_AUG} aug x {N_START} starts per step (bounded sample of the 1024-instance batch)"
+    line = {
+        "impl": "reference", "metric": "RCVRP n100 POMO rollout instances/s", "value": value, "unit": "instances/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(dt for _, dt in rates) / len(rates), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "RCVRP n=100 POMO multi-start x8 aug greedy rollout (BASELINE config[1])",
+                   "num_starts": N_START, "n_aug": N_AUG, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "instances/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = CPU oracle port of the reference's eager rollout (rl4co/tensordict not installable offline)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import rrnco_b200 as rb
+    from rrnco_b200 import _lib
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    rb.set_precision(args.precision)
+    B, Bp = args.batch, args.batch * N_AUG
+    env = rb.RCVRPEnv(generator_params={"num_loc": N_LOC}, check_solution=False, device=dev)
+
+    # decoder weights: default-initialised RRNetDecoder, seed 1234 (experiment/rrnet.yaml:55)
+    torch.manual_seed(1234)
+    decoder = rb.RRNetDecoder(env_name="rcvrp").to(dev)
+
+    class HostEncoder(torch.nn.Module):
+        """Hands the (host, pinned) encoder output of the current batch to the policy."""
+        def __init__(self):
+            super().__init__()
+            self.row = self.col = None
+
+        def forward(self, td, phase=None):
+            return self.row.to(dev, non_blocking=True), self.col.to(dev, non_blocking=True)
+
+    enc = HostEncoder()
+    policy = rb.RRNetPolicy(encoder=enc, decoder=decoder, env_name="rcvrp").to(dev)
+
+    # two alternating batches so that consecutive steps never see the same inputs (and > L2: 1.7 GB of cache each)
+    n_sets = 2
+    host_sets, dev_sets = [], []
+    for i in range(n_sets):
+        raw = host_instances(B, seed=100 * (rank + 1) + i)
+        row, col = stand_in_embeddings(Bp, seed=200 * (rank + 1) + i)
+        raw = {k: v.pin_memory() for k, v in raw.items()}
+        host_sets.append((raw, row.pin_memory(), col.pin_memory()))
+        td = env.reset(rb.TensorDictLite({k: v.to(dev) for k, v in raw.items()}, batch_size=[B]))
+        td_aug = rb.batchify(td, N_AUG)
+        cache = decoder._precompute_cache((row.to(dev), col.to(dev)))
+        dev_sets.append((td_aug, cache))
+    torch.cuda.synchronize()
+
+    def step_resident(i):
+        td_aug, cache = dev_sets[i % n_sets]
+        out = rb.fused_rollout(decoder, cache, env, td_aug, N_START, True, "greedy", check=False)
+        best = rb.unbatchify(out["reward"], (N_AUG, N_START)).amax(-1).amax(-1)  # [B]  test.py:210-212
+        if dist_on:
+            gathered = torch.empty(world * B, dtype=best.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, best)
+        return out
+
+    def step_e2e(i):
+        raw, row, col = host_sets[i % n_sets]
+        enc.row, enc.col = row, col
+        td = env.reset(rb.TensorDictLite(raw, batch_size=[B]))       # H2D of the instance batch + normalise
+        td_aug = rb.batchify(td, N_AUG)                              # StateAugmentation (transforms.py:143)
+        out = policy(td_aug, env, phase="val", decode_type="multistart_greedy", num_starts=N_START)
+        best = rb.unbatchify(out["reward"], (N_AUG, N_START)).amax(-1).amax(-1)
+        return best.cpu()                                            # D2H of the result
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        last = None
+        for i in range(steps):
+            last = fn(warmup + i)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        if isinstance(last, torch.Tensor) and not last.is_cuda:
+            ms = max(ms, wall * 1e3)  # e2e ends with a host-visible result: the wall clock bounds it
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist_on:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, last
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.kernel_count
+    ms_step, out = timed(step_resident, args.steps, args.warmup)
+    launches = (_lib.kernel_count - launches0) // (args.steps + args.warmup) * args.steps
+    clocks = sampler.stop() if sampler else None
+    T = int(out["actions"].shape[1])
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- dominant kernel alone (rollout + finalize), CUDA events on the launching stream -------------
+    def kernel_only(i):
+        td_aug, cache = dev_sets[i % n_sets]
+        return rb.fused_rollout(decoder, cache, env, td_aug, N_START, True, "greedy", check=False)
+    ms_kernel, _ = timed(kernel_only, max(2, args.steps // 2), 1)
+
+    # ---- e2e: host inputs, H2D + reset + cache + rollout + reduction + D2H ----------------------------
+    ms_e2e, best = timed(step_e2e, max(2, args.steps // 2), 1)
+    raw, row, col = host_sets[0]
+    h2d = sum(v.numel() * v.element_size() for v in raw.values()) + 2 * row.numel() * row.element_size()
+    d2h = B * 4
+
+    if rank == 0:
+        hbm_peak, tf_peak, peak_src = peaks()
+        rollout_steps = Bp * N_START * T
+        alg_bytes = rollout_steps * BYTES_PER_ROLLOUT_STEP
+        achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+        tflops = rollout_steps * FLOPS_PER_ROLLOUT_STEP / (ms_kernel * 1e-3) / 1e12
+        line = {
+            "metric": "RCVRP n100 POMO rollout instances/s", "value": value, "unit": "instances/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tensor-core contractions)" if args.precision == 3 else "tf32",
+            "data": "synthetic (city-like asymmetric 1000-node matrices, integer demands 1-9 / 50; random-init "
+                    "decoder seed 1234; encoder output = unit-variance stand-in embeddings)",
+            "config": {"workload": "RCVRP n=100 POMO multi-start x8 aug greedy rollout, batch 1024 per GPU "
+                                   "(BASELINE config[1])",
+                       "instances_per_gpu": B, "n_aug": N_AUG, "num_starts": N_START, "decode_steps": T,
+                       "rollouts_per_gpu": Bp * N_START,
+                       "l2_policy": "two alternating input sets, 1.7 GB of key cache per set (>> 126 MB L2)"},
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                    "what": "RRNetPolicy.forward on pinned HOST inputs (instance td + encoder output): H2D, "
+                            "env.reset normalisation, x8 augmentation, cache GEMM, fused rollout, best-of reduction, D2H"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "rrnco::rollout_kernel<RCVRP>", "ms_per_launch": ms_kernel,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "tensor": {"achieved_tflops_algorithmic": tflops, "peak_bf16_tflops": tf_peak,
+                                    "frac": tflops / tf_peak,
+                                    "note": "fp32-faithful mode issues 3 TF32 passes per algorithmic FLOP"}},
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, dt, cost, Tc = cpu_rollout_rate(args.cpu_sample, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_sample} instances x {N_AUG} aug x {N_START} starts, "
+                                              f"{Tc} decode steps, {dt:.1f} s on {threads} threads"}
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,7 +69,9 @@ _SIGNATURES = {
 }
 
 _lib = None
-launch_count = 0  # number of library calls that enqueue kernels (bench.py reports it as gpu_launches)
+launch_count = 0  # library calls that enqueued work
+kernel_count = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
+_KERNELS_PER_CALL = {"rrnco_rollout": 2}  # rollout_kernel + finalize_kernel; every other entry point launches one
 
 
 def lib():
@@ -117,8 +119,9 @@ def stream_ptr(device=None):
 
 
 def call(name, *args):
-    global launch_count
+    global launch_count, kernel_count
     launch_count += 1
+    kernel_count += _KERNELS_PER_CALL.get(name, 1)
     check(getattr(lib(), name)(*args))
 
 

@@ -1,0 +1,412 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the C-ABI library.
+
+Bars (BASELINE.json north star):
+  * forced action sequences: masks / visited / tours bit-exact, load / time / reward <= 1e-6 relative;
+  * greedy rollouts from identical weights: per-instance costs within 1e-4 relative on >= 99.9 % of instances
+    (the fp32-vs-fp64 oracle disagreement is measured beside it as the noise floor);
+  * fp32 logits within 2e-5 absolute of the reference's (3xTF32 contractions).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import envs as oenvs, model as omodel, sampler as osampler, synth
+from oracle.td import TD, batchify as obatchify
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+dev = "cuda"
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import rrnco_b200
+    rrnco_b200.set_precision(3)
+    return rrnco_b200
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return {k: torch.from_numpy(z[k]) if z[k].shape != () else z[k].item() for k in z.files}
+
+
+def lite(rb, td, device=dev):
+    return rb.TensorDictLite({k: v.to(device) for k, v in td.items()}, batch_size=list(td.batch_size))
+
+
+def make_policy(rb, name, p, row, col):
+    class Enc(torch.nn.Module):
+        def forward(self, td, phase=None):
+            return row, col
+    pol = rb.RRNetPolicy(encoder=Enc(), env_name=name).to(dev)
+    pol.decoder.load_state_dict(p, strict=True)
+    return pol
+
+
+def rel(a, b):
+    return ((a - b).abs() / b.abs().clamp_min(1e-12)).max().item()
+
+
+# ----------------------------------------------------------------------------------------------------
+# env step / mask / reward on forced action sequences
+# ----------------------------------------------------------------------------------------------------
+ENV_FILES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "env_*.npz")))
+
+
+@pytest.mark.parametrize("fname", ENV_FILES)
+def test_env_forced_sequence_vs_reference_golden(rb, fname):
+    z = load(fname)
+    name = fname[4:-4].split("_")[0]
+    raw = TD({k[3:]: v for k, v in z.items() if k.startswith("in.")}, batch_size=[z["actions"].shape[0]])
+    n = raw["distance_matrix"].shape[-1] - (0 if name == "atsp" else 1)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=(name != "rcvrptw"))
+    td = env.reset(lite(rb, raw, "cpu"))  # host td: reset does the H2D
+    assert td["action_mask"].is_cuda
+    assert torch.equal(td["action_mask"].cpu(), z["reset.action_mask"])
+    assert torch.equal(td["distance_matrix"].cpu(), z["reset.distance_matrix"])
+    assert torch.equal(td["min_distance"].cpu(), z["reset.min_distance"])
+    assert torch.equal(td["max_distance"].cpu(), z["reset.max_distance"])
+    acts = z["actions"].to(dev)
+    for t in range(acts.shape[1]):
+        td.set("action", acts[:, t])
+        td = env.step(td)["next"]
+        for k in [k for k in z if k.startswith("step.")]:
+            got, want = td[k[5:]].cpu(), z[k][t]
+            assert got.shape == want.shape and got.dtype == want.dtype, (k, t)
+            assert torch.equal(got, want), (k, t)  # fp32 state too: same _rn operations in the same order
+    real, norm = env.get_reward(td, acts)
+    assert rel(real.cpu(), z["reward.real"]) < 1e-6 and rel(norm.cpu(), z["reward.norm"]) < 1e-6
+    if name == "rcvrptw":
+        assert torch.equal(td["distance_matrix"].cpu(), z["after_reward.distance_matrix"])
+
+
+@pytest.mark.parametrize("name,n,B", [("atsp", 100, 64), ("rcvrp", 100, 64), ("rcvrptw", 100, 64), ("rcvrp", 37, 33)])
+def test_env_random_transitions_vs_oracle(rb, name, n, B):
+    """>= 1e5 random forced transitions at n=100 in total: masks / visited bit-exact, scalars <= 1e-6 rel."""
+    g = torch.Generator().manual_seed(n + B)
+    raw = synth.make_instances(name, B, n, seed=n, integer_demand=False)
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    S = 8
+    otd = obatchify(oenv.reset(raw), S)
+    td = rb.batchify(env.reset(lite(rb, raw)), S)
+    actions, t = [], 0
+    while not otd["done"].all():
+        a = torch.multinomial(otd["action_mask"].float(), 1, generator=g).squeeze(1)
+        otd["action"] = a
+        otd = oenv.step(otd)["next"]
+        td.set("action", a.to(dev))
+        td = env.step(td)["next"]
+        actions.append(a)
+        assert torch.equal(td["action_mask"].cpu(), otd["action_mask"]), t
+        assert torch.equal(td["done"].cpu(), otd["done"]), t
+        if name != "atsp":
+            assert torch.equal(td["visited"].cpu(), otd["visited"]), t
+        for k in ("used_capacity", "current_time", "current_route_length", "used_capacity_linehaul"):
+            if k in otd:
+                assert torch.equal(td[k].cpu(), otd[k]), (k, t)
+        t += 1
+    acts = torch.stack(actions, 1)
+    real, norm = env.get_reward(td, acts.to(dev))
+    oreal, onorm = oenv.get_reward(otd, acts)
+    assert rel(real.cpu(), oreal) < 1e-6 and rel(norm.cpu(), onorm) < 1e-6
+    # static get_action_mask on the final state
+    assert torch.equal(type(env).get_action_mask(td).cpu(), otd["action_mask"]) if name != "atsp" else True
+
+
+def test_env_edge_cases(rb):
+    env = rb.RCVRPEnv(generator_params={"num_loc": 3}, check_solution=True)
+    # demand exactly filling the vehicle is feasible (strict >), one that overflows by an ulp is not
+    raw = TD({"locs": torch.rand(2, 3, 2), "depot": torch.rand(2, 2), "distance_matrix": torch.rand(2, 4, 4),
+              "demand": torch.tensor([[0.5, 0.5, 1.0], [0.5, 0.5000001, 0.25]])}, batch_size=[2])
+    td = env.reset(lite(rb, raw))
+    assert td["action_mask"].cpu().tolist() == [[False, True, True, True]] * 2
+    td.set("action", torch.tensor([1, 1], device=dev))
+    td = env.step(td)["next"]
+    assert td["action_mask"].cpu().tolist() == [[True, False, True, False], [True, False, False, True]]
+    assert td["current_node"].shape == (2, 1) and td["visited"].dtype == torch.uint8
+    # empty batch is a no-op
+    empty = TD({"locs": torch.rand(0, 3, 2), "depot": torch.rand(0, 2), "distance_matrix": torch.rand(0, 4, 4),
+                "demand": torch.rand(0, 3)}, batch_size=[0])
+    assert env.reset(lite(rb, empty))["action_mask"].shape == (0, 4)
+    # invalid tours are rejected with the reference's message
+    with pytest.raises(AssertionError, match="Invalid tour"):
+        env.get_reward(td, torch.tensor([[1, 1, 2, 0], [1, 2, 3, 0]], device=dev))
+
+
+# ----------------------------------------------------------------------------------------------------
+# gather + reset normalisation
+# ----------------------------------------------------------------------------------------------------
+def test_gather_matches_reference_sampler_golden(rb):
+    from rrnco_b200.sampler import CityOnDevice, gather_submatrix
+    z = np.load(os.path.join(GOLDEN, "sampler.npz"))
+    city = {k[5:]: z[k] for k in z.files if k.startswith("city.")}
+    c = CityOnDevice(city)
+    idx = torch.from_numpy(z["indices"])
+    assert np.array_equal(gather_submatrix(c.distance, idx).cpu().numpy(), z["c.distance_matrix"].astype(np.float32))
+    assert np.array_equal(gather_submatrix(c.duration, idx).cpu().numpy(), z["tw.duration_matrix"].astype(np.float32))
+    np.random.seed(4321)
+    s = rb.Real_World_Sampler(with_duration=True).sample(c, 5, 11)
+    assert np.array_equal(s["distance_matrix"].cpu().numpy(), z["tw.distance_matrix"].astype(np.float32))
+    assert np.array_equal(s["points"].cpu().numpy(), z["tw.points"].astype(np.float32))
+    with pytest.raises(ValueError):
+        rb.Real_World_Sampler().sample(c, 0, 3)
+    with pytest.raises(ValueError):
+        rb.Real_World_Sampler().sample(c, 2, 61)
+
+
+def test_gather_full_size_and_fused_normalise(rb):
+    from rrnco_b200.sampler import CityOnDevice, gather_submatrix
+    city = synth.make_city(3, 1000)
+    rng = np.random.RandomState(0)
+    idx = osampler.uniform_sample(256, 1000, 101, rng)
+    want = torch.from_numpy(osampler.gather_submatrix(city["distance"], idx).astype(np.float32))
+    c = CityOnDevice(city)
+    got = gather_submatrix(c.distance, torch.from_numpy(idx))
+    assert torch.equal(got.cpu(), want)
+    got_n, mn, mx = gather_submatrix(c.distance, torch.from_numpy(idx), normalize=True)
+    lo, hi = want.amin((1, 2), keepdim=True), want.amax((1, 2), keepdim=True)
+    assert torch.equal(got_n.cpu(), (want - lo) / (hi - lo + 1e-6))
+    assert torch.equal(mn.cpu(), lo.flatten()) and torch.equal(mx.cpu(), hi.flatten())
+    # idempotence property: gathering with the identity permutation returns the (cast) matrix itself
+    ident = torch.arange(1000).unsqueeze(0)
+    assert torch.equal(gather_submatrix(c.distance, ident)[0].cpu(), torch.from_numpy(city["distance"].astype(np.float32)))
+
+
+# ----------------------------------------------------------------------------------------------------
+# decoder logits / fused rollout vs the reference's golden outputs
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["atsp", "rcvrp", "rcvrptw"])
+def test_decoder_and_rollout_vs_reference_golden(rb, name):
+    z = load(f"policy_{name}.npz")
+    B = z["row_emb"].shape[0]
+    raw = TD({k[3:]: v for k, v in z.items() if k.startswith("in.")}, batch_size=[B])
+    p = {k[6:]: v for k, v in z.items() if k.startswith("param.")}
+    n = raw["distance_matrix"].shape[-1] - (0 if name == "atsp" else 1)
+    S = z["num_starts"]
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=(name != "rcvrptw"))
+    row, col = z["row_emb"].to(dev), z["col_emb"].to(dev)
+    pol = make_policy(rb, name, p, row, col)
+    assert env.get_num_starts(env.reset(lite(rb, raw))) == S
+
+    # RRNetDecoder.forward at the mid-rollout state, driven through env.step like upstream's loop
+    td = rb.batchify(env.reset(lite(rb, raw)), S)
+    for t in range(4):
+        td.set("action", z["greedy.actions"][:, t].to(dev))
+        td = env.step(td)["next"]
+    _, _, cache = pol.decoder.pre_decoder_hook(td, env, (row, col), S)
+    logits, mask = pol.decoder(td, cache, S)
+    assert torch.equal(mask.cpu(), z["mid.mask"])
+    assert logits.dtype == torch.float32 and logits.shape == z["mid.logits"].shape
+    assert (logits.cpu() - z["mid.logits"]).abs().max() < 2e-5
+
+    # RRNetPolicy.forward (fused rollout): tours identical, reward / log-likelihood within tolerance
+    out = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    assert torch.equal(out["actions"].cpu(), z["greedy.actions"])
+    assert out["actions"].dtype == torch.int64
+    assert rel(out["reward"].cpu(), z["greedy.reward"]) < 1e-6
+    assert rel(out["normalized_reward"].cpu(), z["greedy.normalized_reward"]) < 1e-6
+    assert (out["log_likelihood"].cpu() - z["greedy.log_likelihood"]).abs().max() < 1e-4
+    # rewards are consistent with env.get_reward on the emitted tours (independent kernel)
+    tdb = rb.batchify(env.reset(lite(rb, raw)), S)
+    real, norm = env.get_reward(tdb, out["actions"])
+    assert rel(real, out["reward"]) < 1e-6
+
+    # non-multistart evaluate (flat td, start action scored by the policy; atsp uses the placeholder context)
+    rowb, colb = rb.batchify(row, S), rb.batchify(col, S)
+    pol2 = make_policy(rb, name, p, rowb, colb)
+    td_flat = rb.batchify(env.reset(lite(rb, raw)), S)
+    out2 = pol2(td_flat, env, phase="val", actions=z["greedy.actions"].to(dev))
+    assert torch.equal(out2["actions"].cpu(), z["greedy.actions"])
+    assert (out2["log_likelihood"].cpu() - z["evaluate.log_likelihood"]).abs().max() < 1e-4
+    assert rel(out2["reward"].cpu(), z["evaluate.reward"]) < 1e-6
+
+
+@pytest.mark.parametrize("name,n,B", [("rcvrp", 100, 16), ("atsp", 100, 8), ("rcvrptw", 100, 8), ("rcvrp", 50, 8),
+                                       ("atsp", 128, 2), ("rcvrp", 7, 5)])
+def test_greedy_rollout_vs_oracle(rb, name, n, B):
+    raw = synth.make_instances(name, B, n, seed=n + B)
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    otd = oenv.reset(raw)
+    N = otd["action_mask"].shape[-1]
+    S = oenv.get_num_starts(otd)
+    row, col = synth.random_embeddings(B, N, seed=n)
+    p = omodel.init_decoder_params(name, seed=n)
+    oout = omodel.policy_forward(p, oenv, otd, row, col, decode_type="multistart_greedy", num_starts=S)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=(name != "rcvrptw"))
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    out = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    acts, want = out["actions"].cpu(), oout["actions"]
+    assert acts.shape == want.shape
+    same = (acts == want).all(1)
+    assert same.float().mean() >= 0.99, same.float().mean()
+    # identical tours must give (near-)identical reward and log-likelihood
+    assert rel(out["reward"].cpu()[same], oout["reward"][same]) < 1e-6
+    ll, oll = out["log_likelihood"].cpu()[same], oout["log_likelihood"][same]
+    assert ((ll - oll).abs() <= 1e-5 * oll.abs() + 5e-5).all()  # sum of ~T fp32 log-probs of magnitude ~1
+    best, obest = out["reward"].cpu().view(S, B).max(0)[0], oout["reward"].view(S, B).max(0)[0]
+    assert (((best - obest).abs() / obest.abs()) < 1e-4).float().mean() >= 0.999
+    # every emitted tour is feasible (reference's own validity oracle)
+    if name != "rcvrptw":
+        env.check_solution_validity(rb.batchify(env.reset(lite(rb, raw)), S), out["actions"])
+
+
+def test_evaluate_multistart_vs_oracle(rb):
+    name, n, B = "rcvrptw", 30, 6
+    raw = synth.make_instances(name, B, n, seed=9)
+    oenv = oenvs.make_env(name, n)
+    otd = oenv.reset(raw)
+    S = oenv.get_num_starts(otd)
+    row, col = synth.random_embeddings(B, n + 1, seed=2)
+    p = omodel.init_decoder_params(name, seed=4)
+    g = torch.Generator().manual_seed(0)
+    osamp = omodel.policy_forward(p, oenv, otd, row, col, decode_type="multistart_sampling", num_starts=S, generator=g)
+    forced = osamp["actions"][:, 1:]
+    oev = omodel.policy_forward(p, oenv, oenv.reset(raw), row, col, num_starts=S, actions=forced)
+    env = rb.get_env(name, generator_params={"num_loc": n})
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    out = pol(env.reset(lite(rb, raw)), env, phase="train", num_starts=S, actions=forced.to(dev),
+              return_sum_log_likelihood=False)
+    assert torch.equal(out["actions"].cpu(), osamp["actions"])
+    assert (out["log_likelihood"].cpu() - oev["logprobs"]).abs().max() < 1e-4
+    assert rel(out["reward"].cpu(), oev["reward"]) < 1e-6
+    # an infeasible forced action is reported with the reference's message
+    bad = forced.clone()
+    bad[:, 0] = osamp["actions"][:, 0]  # revisit the start node
+    with pytest.raises(AssertionError, match="infeasible action selected"):
+        pol(env.reset(lite(rb, raw)), env, phase="train", num_starts=S, actions=bad.to(dev))
+
+
+# ----------------------------------------------------------------------------------------------------
+# sampling: Gumbel-max with a counter RNG -- exact twin in numpy, plus a distribution test
+# ----------------------------------------------------------------------------------------------------
+def philox4x32(c0, c1, c2, c3, k0, k1):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3)]
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(M0) * c[0], np.uint64(M1) * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [(hi1 ^ c[1] ^ k0) & mask, lo1, (hi0 ^ c[3] ^ k1) & mask, lo0]
+        k0, k1 = (k0 + np.uint64(W0)) & mask, (k1 + np.uint64(W1)) & mask
+    return c
+
+
+def gumbel_twin(seed, n_inst, S, N):
+    """noise(step, [R,N]) reproducing the kernel's (rollout pair, step, column) -> Philox mapping."""
+    def noise(step_idx, shape):
+        step = step_idx - 1  # strategy has already stored the forced start
+        out = np.zeros((S, n_inst, N), dtype=np.float32)
+        for s in range(S):
+            row = s % 128
+            tile = s // 128
+            r0 = row if (row % 16) < 8 else row - 8
+            e_base = 0 if (row % 16) < 8 else 2
+            s0 = tile * 128 + r0
+            s0 = s0 if s0 < S else tile * 128
+            for b in range(n_inst):
+                rg0 = s0 * n_inst + b
+                cols = np.arange(N)
+                j, t, e = cols >> 3, (cols & 7) >> 1, e_base + (cols & 1)
+                x = philox4x32(np.full(N, rg0 & 0xFFFFFFFF), np.full(N, rg0 >> 32), np.full(N, step), j * 4 + t,
+                               seed & 0xFFFFFFFF, seed >> 32)
+                x = np.stack(x, 0)[e, np.arange(N)]
+                u = ((x >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+                out[s, b] = -np.log(-np.log(u))
+        return torch.from_numpy(out.reshape(S * n_inst, N))
+    return noise
+
+
+def test_sampling_matches_gumbel_twin_and_is_valid(rb):
+    name, n, B, seed = "rcvrp", 20, 3, 77
+    raw = synth.make_instances(name, B, n, seed=5)
+    oenv = oenvs.make_env(name, n)
+    otd = oenv.reset(raw)
+    S = oenv.get_num_starts(otd)
+    row, col = synth.random_embeddings(B, n + 1, seed=3)
+    p = omodel.init_decoder_params(name, seed=6)
+    oout = omodel.policy_forward(p, oenv, otd, row, col, decode_type="multistart_sampling", num_starts=S,
+                                 gumbel_noise=gumbel_twin(seed, B, S, n + 1))
+    env = rb.get_env(name, generator_params={"num_loc": n})
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    out = pol(env.reset(lite(rb, raw)), env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=seed)
+    T = min(out["actions"].shape[1], oout["actions"].shape[1])
+    same = (out["actions"].cpu()[:, :T] == oout["actions"][:, :T]).all(1)
+    assert same.float().mean() >= 0.97, same.float().mean()  # identical noise => identical sampled tours
+    ll, oll = out["log_likelihood"].cpu()[same], oout["log_likelihood"][same]
+    assert ((ll - oll).abs() <= 1e-5 * oll.abs() + 5e-5).all()
+    env.check_solution_validity(rb.batchify(env.reset(lite(rb, raw)), S), out["actions"])
+    out_b = pol(env.reset(lite(rb, raw)), env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=seed + 1)
+    assert not torch.equal(out_b["actions"][:, : T], out["actions"][:, : T])  # different seed, different tours
+
+
+def test_sampling_distribution_chi_square(rb):
+    """First sampled decision over many seeds follows softmax(logits) (chi-square, 5 sigma)."""
+    name, n, B = "atsp", 12, 1
+    raw = synth.make_instances(name, B, n, seed=1)
+    oenv = oenvs.make_env(name, n)
+    otd = oenv.reset(raw)
+    S = n
+    row, col = synth.random_embeddings(B, n, seed=8)
+    p = omodel.init_decoder_params(name, seed=8)
+    trace = []
+    omodel.policy_forward(p, oenv, otd, row, col, decode_type="multistart_greedy", num_starts=S, trace=trace)
+    probs = omodel.process_logits(trace[0]["logits"].clone(), trace[0]["mask"]).exp()[0]  # rollout s=0, b=0
+    env = rb.get_env(name, generator_params={"num_loc": n})
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    td0 = env.reset(lite(rb, raw))
+    counts = torch.zeros(n)
+    trials = 600
+    for sd in range(trials):
+        out = pol(td0, env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=1000 + sd)
+        counts[out["actions"][0, 1].item()] += 1
+    exp = probs * trials
+    keep = exp > 5
+    chi2 = (((counts - exp) ** 2) / exp.clamp_min(1e-9))[keep].sum().item()
+    dof = int(keep.sum()) - 1
+    assert chi2 < dof + 5 * (2 * dof) ** 0.5 + 5, (chi2, dof)
+
+
+# ----------------------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties
+# ----------------------------------------------------------------------------------------------------
+def test_full_size_rcvrp_rollout_properties(rb):
+    """RCVRP n=100, 128 instances x 8 aug x 101 starts: all tours valid, in-kernel reward == independent
+    tour-reward kernel, evaluate replay reproduces the log-likelihood, best-of-aug reduction."""
+    n, B, A = 100, 128, 8
+    raw = synth.make_instances("rcvrp", B, n, seed=11)
+    env = rb.RCVRPEnv(generator_params={"num_loc": n}, check_solution=False)
+    td = env.reset(lite(rb, raw))
+    td_aug = rb.batchify(td, A)
+    S = env.get_num_starts(td_aug)
+    assert S == 101
+    row, col = synth.random_embeddings(A * B, n + 1, seed=12)
+    p = omodel.init_decoder_params("rcvrp", seed=13)
+    pol = make_policy(rb, "rcvrp", p, row.to(dev), col.to(dev))
+    out = pol(td_aug, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    acts = out["actions"]
+    R = A * B * S
+    assert acts.shape[0] == R and out["reward"].shape == (R,)
+    # permutation property: every customer exactly once, zeros elsewhere
+    srt = acts.sort(1)[0]
+    assert (srt[:, -n:] == torch.arange(1, n + 1, device=dev)).all() and (srt[:, :-n] == 0).all()
+    # capacity property via the reference's running-load check on a slice (the loop is O(T) launches)
+    sl = slice(0, 20000)
+    tdb = rb.TensorDictLite({"demand": td_aug["demand"][torch.arange(R, device=dev)[sl] % (A * B)],
+                             "vehicle_capacity": torch.ones(20000, 1, device=dev)}, batch_size=[20000])
+    env.check_solution_validity(tdb, acts[sl])
+    # reward == independent tour-length kernel over un-replicated matrices (data_rows = A*B)
+    from rrnco_b200.envs import tour_reward
+    real, norm = tour_reward(acts, td_aug["distance_matrix"], True, None, td_aug["min_distance"], td_aug["max_distance"])
+    assert rel(norm, out["normalized_reward"]) < 1e-6 and rel(real, out["reward"]) < 1e-6
+    # evaluate replay of the greedy tours reproduces the log-likelihood
+    out2 = pol(td_aug, env, phase="val", num_starts=S, actions=acts[:, 1:])
+    assert (out2["log_likelihood"] - out["log_likelihood"]).abs().max() < 1e-5
+    assert torch.equal(out2["actions"], acts)
+    # augmentation copies share matrices and (here) differ only by embeddings: best-of reduction shape
+    best = rb.unbatchify(out["reward"], (A, S)).max(-1)[0].max(-1)[0]
+    assert best.shape == (B,)
