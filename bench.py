@@ -177,6 +177,7 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import rrnco_b200 as rb
     from rrnco_b200 import _lib
+    from rrnco_b200.sharding import gather_costs
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -223,8 +224,7 @@ def run_ours(args, rank, world, local_rank):
         out = rb.fused_rollout(decoder, cache, env, td_aug, N_START, True, "greedy", check=False)
         best = rb.unbatchify(out["reward"], (N_AUG, N_START)).amax(-1).amax(-1)  # [B]  test.py:210-212
         if dist_on:
-            gathered = torch.empty(world * B, dtype=best.dtype, device=dev)
-            dist.all_gather_into_tensor(gathered, best)
+            gather_costs(best, world * B)  # the path's only collective (NCCL all-gather of [B] fp32 per rank)
         return out
 
     def step_e2e(i):
