@@ -63,6 +63,11 @@ const char* rrnco_strerror(int code);
  *   1 = one TF32 pass (analogue of the reference's `torch.autocast("cuda")` inference path, test.py:182-185) */
 int rrnco_set_precision(int32_t passes);
 
+/* FFN engine of the fused rollout kernel (process-wide, set before use):
+ *   1 = tcgen05.mma kind::tf32, TMEM accumulators, TMA-streamed weights (default)
+ *   0 = mma.sync tensor-core path (also what rrnco_decoder_logits uses) */
+int rrnco_set_ffn_engine(int32_t engine);
+
 /* ------------------------------------------------------------------------------------------------
  * env.reset: per-instance min-max normalisation of the distance matrix
  *   replaces RCVRPEnv._reset rrnco/envs/rcvrp/env.py:138-145 (same lines in atsp/env.py:113-120,
@@ -104,6 +109,16 @@ int rrnco_rcvrp_step(int64_t R, int32_t n_nodes, int64_t data_rows, const int64_
                      const uint8_t* visited_in, const int64_t* current_in, float* used_out,
                      uint8_t* visited_out, int64_t* current_out, uint8_t* done_out, uint8_t* mask_out,
                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Residual FFN of RRNet_PointerAttention  rrnco/models/decoder.py:272-277,296  (rl4co MLP E -> 4E -> E, ReLU)
+ *   g_out = W2 relu(W1 g_in + b1) + b2 + g_in     g: [n_rows, E] fp32
+ *   tcgen05 (kind::tf32, 3xTF32 split, TMEM accumulators) form of the FFN phase of the fused kernel.
+ *   workspace >= rrnco_pointer_ffn_workspace_bytes() bytes (holds the hi/lo split of W1, W2).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t rrnco_pointer_ffn_workspace_bytes(void);
+int rrnco_pointer_ffn(int64_t n_rows, const float* g_in, const float* w1, const float* b1, const float* w2,
+                      const float* b2, float* g_out, void* workspace, void* stream);
 
 /* Instance data shared by the RCVRPTW step and the fused kernels (row = index % data_rows). Unused members NULL. */
 typedef struct rrnco_instance_data {

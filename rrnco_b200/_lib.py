@@ -48,6 +48,7 @@ _SIGNATURES = {
     "rrnco_abi_version": (C.c_int, []),
     "rrnco_strerror": (C.c_char_p, [C.c_int]),
     "rrnco_set_precision": (C.c_int, [C.c_int32]),
+    "rrnco_set_ffn_engine": (C.c_int, [C.c_int32]),
     "rrnco_minmax_normalize": (C.c_int, [C.c_int64, C.c_int32, _f, _f, _f, _f, _f]),
     "rrnco_gather_submatrix": (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, _f, C.c_int32, _f, _f, _f]),
     "rrnco_atsp_step": (C.c_int, [C.c_int64, C.c_int32, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
@@ -62,6 +63,8 @@ _SIGNATURES = {
     "rrnco_decoder_logits": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(DecoderWeights),
                                        C.POINTER(DecoderCache), C.POINTER(InstanceData), _f, _f, _f, _f, C.c_int32,
                                        _f, _f, _f]),
+    "rrnco_pointer_ffn_workspace_bytes": (C.c_int64, []),
+    "rrnco_pointer_ffn": (C.c_int, [C.c_int64, _f, _f, _f, _f, _f, _f, _f, _f]),
     "rrnco_rollout_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     "rrnco_rollout": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
                                 C.POINTER(DecoderWeights), C.POINTER(DecoderCache), C.POINTER(InstanceData), _f,
@@ -71,7 +74,7 @@ _SIGNATURES = {
 _lib = None
 launch_count = 0  # library calls that enqueued work
 kernel_count = 0  # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
-_KERNELS_PER_CALL = {"rrnco_rollout": 2}  # rollout_kernel + finalize_kernel; every other entry point launches one
+_KERNELS_PER_CALL = {"rrnco_rollout": 3, "rrnco_pointer_ffn": 2}  # rollout: weight pack + rollout + finalize  # rollout_kernel + finalize_kernel; every other entry point launches one
 
 
 def lib():
@@ -127,6 +130,11 @@ def call(name, *args):
 
 def set_precision(passes: int):
     check(lib().rrnco_set_precision(passes))
+
+
+def set_ffn_engine(engine: int):
+    """1 = tcgen05 FFN (default), 0 = mma.sync FFN in the fused rollout kernel."""
+    check(lib().rrnco_set_ffn_engine(engine))
 
 
 def raise_device_status(word: int):

@@ -16,10 +16,13 @@
 // All contractions run as 3xTF32 (error-compensated split, fp32-faithful) or 1xTF32 (kPasses == 1, the
 // analogue of the reference's autocast inference path).
 #include "common.cuh"
+#include "tc05.cuh"
+#include "ffn_pack.cuh"
 
 namespace rrnco {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;      // compute threads (8 warps)
+constexpr int kThreadsTc = 288;    // + 1 TMA producer warp in the tcgen05 variant
 constexpr int kRows = 128;   // rollouts per CTA tile
 constexpr int kLdA = 132;    // fp32 row stride of the activation tiles (bank-conflict-free fragments)
 constexpr int kLdB = 36;     // fp32 row stride of a streamed weight slice (32 k + 4 pad)
@@ -29,6 +32,17 @@ constexpr int kStageFloats = kRows * kLdB;
 constexpr int kTileFloats = kRows * kLdA;
 constexpr int kNumSlices = 36;  // 4 chunks x (4 W1 + 4 W2) + 4 Lk
 constexpr int kMaxState = 4;
+
+// per-phase cycle accumulator of CTA 0 (debug / profiling aid, read back with rrnco_debug_phase_cycles)
+__device__ long long g_phase_cycles[16];
+#define PHASE_STAMP(i)                                   \
+  do {                                                   \
+    if (blockIdx.x == 0 && tid == 0) {                   \
+      const long long now_ = clock64();                  \
+      g_phase_cycles[i] += now_ - phase_t0;              \
+      phase_t0 = now_;                                   \
+    }                                                    \
+  } while (0)
 
 struct RolloutParams {
   int N, NT, S, n_tiles, n_state;
@@ -51,6 +65,7 @@ struct RolloutParams {
   int32_t* ws_tile_steps;
   int32_t* max_steps_out;
   uint32_t* status;
+  const float* ffn_packed;  // tcgen05 variant: W1 / W2 packed hi | lo slices (ffn_pack.cuh)
 };
 
 struct Smem {
@@ -70,6 +85,13 @@ struct Smem {
   uint32_t mask[kRows][4];
   double len[kRows];
   double lp[kRows];
+  // tcgen05 FFN pipeline
+  uint64_t bar_full[kFStages];
+  uint64_t bar_empty[kFStages];
+  uint64_t bar_acc;
+  uint64_t bar_go;
+  uint32_t tmem_base;
+  volatile int exit_flag;
 };
 
 __device__ __forceinline__ bool bit_of(const uint32_t (&w)[4], int j, int e8) {
@@ -136,8 +158,29 @@ __device__ __forceinline__ void issue_slice(int s, Smem& sm, const RolloutParams
   cp_async_commit();  // always commit (possibly empty) so that wait_group counting stays uniform
 }
 
-template <int kEnv, int kNTMax, int kPasses>
-__global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParams p) {
+// CTA-wide barriers over the 256 compute threads (the producer warp of the tcgen05 variant never joins them)
+template <bool kTc>
+__device__ __forceinline__ void cta_sync() {
+  if (kTc) asm volatile("bar.sync 1, 256;\n" ::: "memory");
+  else __syncthreads();
+}
+template <bool kTc>
+__device__ __forceinline__ int cta_sync_and(int pred) {
+  if (!kTc) return __syncthreads_and(pred);
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "bar.red.and.pred p, 1, 256, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(r)
+      : "r"((uint32_t)pred)
+      : "memory");
+  return (int)r;
+}
+
+template <int kEnv, int kNTMax, int kPasses, bool kTc>
+__global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel(const RolloutParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -162,7 +205,20 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParam
   }
 
   // ---------------- one-time staging ----------------
-  for (int i = tid; i < kF; i += kThreads) sm.b1[i] = p.w.ffn_b1[i];
+  if (kTc) {
+    if (warp == 0) tc05::tmem_alloc(&sm.tmem_base, 512);
+    if (tid == 32) {
+      for (int i = 0; i < kFStages; ++i) {
+        tc05::mbar_init(&sm.bar_full[i], 1);
+        tc05::mbar_init(&sm.bar_empty[i], 1);
+      }
+      tc05::mbar_init(&sm.bar_acc, 1);
+      tc05::mbar_init(&sm.bar_go, 1);
+      tc05::fence_mbar_init();
+      sm.exit_flag = 0;
+    }
+  }
+  for (int i = tid; i < kF; i += kTc ? kThreadsTc : kThreads) sm.b1[i] = p.w.ffn_b1[i];
   if (tid < kE) {
     sm.b2[tid] = p.w.ffn_b2[tid];
     sm.placeholder[tid] = p.w.ctx_placeholder_q ? p.w.ctx_placeholder_q[tid] : 0.f;
@@ -226,6 +282,33 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParam
   }
   __syncthreads();
 
+  if (kTc) {
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    if (warp == 8) {
+      // ===== TMA producer warp: each decode step, streams the 64 packed weight slices through the ring =====
+      if (lane == 0) {
+        uint32_t go_phase = 0;
+        uint32_t sl = 0;
+        while (true) {
+          tc05::mbar_wait(&sm.bar_go, go_phase);
+          go_phase ^= 1u;
+          if (sm.exit_flag) break;
+          for (int s = 0; s < kFSlices; ++s, ++sl) {
+            const int st = sl & (kFStages - 1);
+            if (sl >= kFStages) tc05::mbar_wait(&sm.bar_empty[st], ((sl / kFStages) - 1) & 1);
+            tc05::mbar_arrive_expect_tx(&sm.bar_full[st], kFSliceBytes);
+            tc05::bulk_g2s(sm.Bs + st * kFSliceFloats, p.ffn_packed + (size_t)s * kFSliceFloats, kFSliceBytes,
+                           &sm.bar_full[st]);
+          }
+        }
+      }
+      return;
+    }
+  }
+  uint32_t tc_sl = 0, tc_acc_phase = 0;  // running slice counter / accumulator-barrier phase of the MMA warp
+  long long phase_t0 = clock64();
   const int r0 = warp * 16 + g, r1 = r0 + 8;  // rows owned by this quad in the row-owner phases
   const int wm = warp >> 1, wn = warp & 1;    // FFN warp grid 4 (M) x 2 (N): 32 x 64 warp tiles
   int step = 0;
@@ -234,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParam
 
   while (true) {
     if (!p.logits_only) {
-      const int all_done = __syncthreads_and(tid < kRows ? (sm.done[tid] || !sm.active[tid]) : 1);
+      const int all_done = cta_sync_and<kTc>(tid < kRows ? (sm.done[tid] || !sm.active[tid]) : 1);
       if (all_done || step >= p.max_steps) break;
     }
     // ---- B (issued first so that the copies overlap phase A): K -> Hb, V -> Bs -----------------
@@ -359,7 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParam
       *reinterpret_cast<float4*>(&sm.A[row * kLdA + lane * 4]) = q;
     }
     cp_async_wait<0>();
-    __syncthreads();
+    cta_sync<kTc>();
+    PHASE_STAMP(0);
 
     // ---- C: attention, 16 rows x 8 heads per warp ----------------------------------------------
     {
@@ -465,95 +549,236 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParam
         __syncwarp();
       }
     }
-    __syncthreads();  // all warps done with the K / V tiles; glimpse complete in A
+    if (kTc) tc05::fence_proxy_async();  // generic-proxy reads of the V tile precede the TMA writes into the same memory
+    cta_sync<kTc>();  // all warps done with the K / V tiles; glimpse complete in A
+    PHASE_STAMP(1);
 
     // ---- E: FFN  g' = W2 relu(W1 g + b1) + b2 + g ---------------------------------------------
-    issue_slice(0, sm, p, Lk, tid);
-    issue_slice(1, sm, p, Lk, tid);
     int sl = 0;
-    float acc2[2][8][4];
+    if (kTc) {
+      // tcgen05 path (see ffn_tc_kernel.cu for the standalone form): glimpse -> hi | lo K-major core-matrix
+      // tiles in shared memory (A region | Hb region), weights streamed by the TMA producer warp through the
+      // Bs region, accumulators and the hidden activations (A operand of GEMM2) in tensor memory.
+      if (tid == 0) tc05::mbar_arrive(&sm.bar_go);  // the ring (Bs) is free: producer starts this step's stream
+      float4 gres[16];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+      for (int i = 0; i < 16; ++i) {
+        const int idx = tid + i * kThreads, c4 = idx >> 7, row = idx & 127;
+        gres[i] = *reinterpret_cast<const float4*>(&sm.A[row * kLdA + c4 * 4]);
+      }
+      cta_sync<kTc>();  // every thread holds its part of the glimpse: A / Hb may now be re-laid out
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) acc2[mt][nt][0] = acc2[mt][nt][1] = acc2[mt][nt][2] = acc2[mt][nt][3] = 0.f;
+      for (int i = 0; i < 16; ++i) {
+        const int idx = tid + i * kThreads, c4 = idx >> 7, row = idx & 127;
+        uint32_t h[4], l[4];
+        split_tf32(gres[i].x, h[0], l[0]); split_tf32(gres[i].y, h[1], l[1]);
+        split_tf32(gres[i].z, h[2], l[2]); split_tf32(gres[i].w, h[3], l[3]);
+        const int dst = c4 * (kFRows * 4) + row * 4;
+        *reinterpret_cast<uint4*>(&sm.A[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(&sm.Hb[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      tc05::fence_proxy_async();
+      tc05::fence_before_sync();
+      cta_sync<kTc>();
+      tc05::fence_after_sync();
+      PHASE_STAMP(2);
 
+      const uint32_t tbase = sm.tmem_base;
+      const uint32_t t_hacc = tbase, t_ahi = tbase + 128, t_alo = tbase + 256, t_out = tbase + 384;
+      const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+      const int colhalf = warp >> 2;
+      const uint32_t idesc = tc05::make_idesc_tf32(128, 128);
+      const uint32_t g_hi_addr = tc05::smem_u32(sm.A), g_lo_addr = tc05::smem_u32(sm.Hb);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float acc1[2][8][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) acc1[mt][nt][0] = acc1[mt][nt][1] = acc1[mt][nt][2] = acc1[mt][nt][3] = 0.f;
+      for (int c = 0; c < 4; ++c) {
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        const float* Asrc = half == 0 ? sm.A : sm.Hb;
+        for (int half = 0; half < 2; ++half) {
+          if (warp == 0) {  // MMA issue: the whole warp waits for the slice, lane 0 issues
 #pragma unroll 1
-        for (int ks4 = 0; ks4 < 4; ++ks4, ++sl) {
-          cp_async_wait<1>();
-          __syncthreads();
-          issue_slice(sl + 2, sm, p, Lk, tid);
-          const float* sB = sm.Bs + (sl % kStages) * kStageFloats;
+            for (int ks = 0; ks < 8; ++ks, ++tc_sl) {
+              const int st = tc_sl & (kFStages - 1);
+              tc05::mbar_wait(&sm.bar_full[st], (tc_sl / kFStages) & 1);
+              tc05::fence_after_sync();
+              if (lane == 0) {
+                const uint32_t whi = tc05::smem_u32(sm.Bs + st * kFSliceFloats), wlo = whi + kFRows * kFSliceK * 4;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint32_t ah[2][4], al[2][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              const float* ap = Asrc + (wm * 32 + mt * 16 + g) * kLdA + ks4 * kSliceK + kk * 8 + t;
-              split_tf32(ap[0], ah[mt][0], al[mt][0]);
-              split_tf32(ap[8 * kLdA], ah[mt][1], al[mt][1]);
-              split_tf32(ap[4], ah[mt][2], al[mt][2]);
-              split_tf32(ap[8 * kLdA + 4], ah[mt][3], al[mt][3]);
+                for (int kk = 0; kk < 2; ++kk) {
+                  const uint64_t bh = tc05::make_desc(whi + kk * 2 * kLboTile, kLboTile, kSbo);
+                  const uint64_t bl = tc05::make_desc(wlo + kk * 2 * kLboTile, kLboTile, kSbo);
+                  if (half == 0) {
+                    const uint32_t first = (ks == 0 && kk == 0) ? 0u : 1u;
+                    const uint32_t koff = (ks * 4 + kk * 2) * kLboTile;
+                    const uint64_t ah = tc05::make_desc(g_hi_addr + koff, kLboTile, kSbo);
+                    if (kPasses == 3) {
+                      const uint64_t al = tc05::make_desc(g_lo_addr + koff, kLboTile, kSbo);
+                      tc05::mma_ss(t_hacc, al, bh, idesc, first);
+                      tc05::mma_ss(t_hacc, ah, bl, idesc, 1u);
+                      tc05::mma_ss(t_hacc, ah, bh, idesc, 1u);
+                    } else {
+                      tc05::mma_ss(t_hacc, ah, bh, idesc, first);
+                    }
+                  } else {
+                    const uint32_t kcol = ks * kFSliceK + kk * 8;
+                    const uint32_t acc = (c == 0 && ks == 0 && kk == 0) ? 0u : 1u;
+                    if (kPasses == 3) {
+                      tc05::mma_ts(t_out, t_alo + kcol, bh, idesc, acc);
+                      tc05::mma_ts(t_out, t_ahi + kcol, bl, idesc, 1u);
+                      tc05::mma_ts(t_out, t_ahi + kcol, bh, idesc, 1u);
+                    } else {
+                      tc05::mma_ts(t_out, t_ahi + kcol, bh, idesc, acc);
+                    }
+                  }
+                }
+                tc05::commit(&sm.bar_empty[st]);
+                if (ks == 7) tc05::commit(&sm.bar_acc);
+              }
+              __syncwarp();
             }
+          }
+          tc05::mbar_wait(&sm.bar_acc, tc_acc_phase);
+          tc_acc_phase ^= 1u;
+          tc05::fence_after_sync();
+          if (half == 0) {  // hidden chunk: + b1, relu, split -> A operand (hi | lo) of GEMM2 in tensor memory
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-              const float* bp = sB + (wn * 64 + nt * 8 + g) * kLdB + kk * 8 + t;
-              uint32_t bh[2], bl[2];
-              split_tf32(bp[0], bh[0], bl[0]);
-              split_tf32(bp[4], bh[1], bl[1]);
-              if (half == 0) {
-                mma_x<kPasses>(acc1[0][nt], ah[0], al[0], bh, bl);
-                mma_x<kPasses>(acc1[1][nt], ah[1], al[1], bh, bl);
-              } else {
-                mma_x<kPasses>(acc2[0][nt], ah[0], al[0], bh, bl);
-                mma_x<kPasses>(acc2[1][nt], ah[1], al[1], bh, bl);
+            for (int q = 0; q < 4; ++q) {
+              const int col0 = colhalf * 64 + q * 16;
+              uint32_t v[16], hi[16], lo[16];
+              tc05::tmem_ld16(t_hacc + lane_base + col0, v);
+              tc05::tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float hv = fmaxf(__uint_as_float(v[i]) + sm.b1[c * kFRows + col0 + i], 0.f);
+                split_tf32(hv, hi[i], lo[i]);
+              }
+              tc05::tmem_st16(t_ahi + lane_base + col0, hi);
+              tc05::tmem_st16(t_alo + lane_base + col0, lo);
+            }
+            tc05::tmem_wait_st();
+            tc05::fence_before_sync();
+            cta_sync<kTc>();
+          }
+        }
+      }
+      PHASE_STAMP(3);
+      // output epilogue (thread per row): acc + b2 -> A (row-major again); all MMAs that read the hi tile are done
+      {
+        const int row = (warp & 3) * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col0 = colhalf * 64 + q * 16;
+          uint32_t v[16];
+          tc05::tmem_ld16(t_out + lane_base + col0, v);
+          tc05::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(&sm.A[row * kLdA + col0 + i]) =
+                make_float4(__uint_as_float(v[i]) + sm.b2[col0 + i], __uint_as_float(v[i + 1]) + sm.b2[col0 + i + 1],
+                            __uint_as_float(v[i + 2]) + sm.b2[col0 + i + 2], __uint_as_float(v[i + 3]) + sm.b2[col0 + i + 3]);
+        }
+      }
+      tc05::fence_before_sync();
+      cta_sync<kTc>();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {  // + g (the residual, kept exact in registers)
+        const int idx = tid + i * kThreads, c4 = idx >> 7, row = idx & 127;
+        float4* dst = reinterpret_cast<float4*>(&sm.A[row * kLdA + c4 * 4]);
+        float4 o = *dst;
+        o.x += gres[i].x; o.y += gres[i].y; o.z += gres[i].z; o.w += gres[i].w;
+        *dst = o;
+      }
+      PHASE_STAMP(4);
+      sl = 32;  // the logits phase streams its 4 logit-key slices through the same ring memory
+      issue_slice(32, sm, p, Lk, tid);
+      issue_slice(33, sm, p, Lk, tid);
+    } else {
+      issue_slice(0, sm, p, Lk, tid);
+      issue_slice(1, sm, p, Lk, tid);
+      sl = 0;
+      float acc2[2][8][4];
+  #pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+  #pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc2[mt][nt][0] = acc2[mt][nt][1] = acc2[mt][nt][2] = acc2[mt][nt][3] = 0.f;
+
+  #pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float acc1[2][8][4];
+  #pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+  #pragma unroll
+          for (int nt = 0; nt < 8; ++nt) acc1[mt][nt][0] = acc1[mt][nt][1] = acc1[mt][nt][2] = acc1[mt][nt][3] = 0.f;
+  #pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const float* Asrc = half == 0 ? sm.A : sm.Hb;
+  #pragma unroll 1
+          for (int ks4 = 0; ks4 < 4; ++ks4, ++sl) {
+            cp_async_wait<1>();
+            cta_sync<kTc>();
+            issue_slice(sl + 2, sm, p, Lk, tid);
+            const float* sB = sm.Bs + (sl % kStages) * kStageFloats;
+  #pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              uint32_t ah[2][4], al[2][4];
+  #pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                const float* ap = Asrc + (wm * 32 + mt * 16 + g) * kLdA + ks4 * kSliceK + kk * 8 + t;
+                split_tf32(ap[0], ah[mt][0], al[mt][0]);
+                split_tf32(ap[8 * kLdA], ah[mt][1], al[mt][1]);
+                split_tf32(ap[4], ah[mt][2], al[mt][2]);
+                split_tf32(ap[8 * kLdA + 4], ah[mt][3], al[mt][3]);
+              }
+  #pragma unroll
+              for (int nt = 0; nt < 8; ++nt) {
+                const float* bp = sB + (wn * 64 + nt * 8 + g) * kLdB + kk * 8 + t;
+                uint32_t bh[2], bl[2];
+                split_tf32(bp[0], bh[0], bl[0]);
+                split_tf32(bp[4], bh[1], bl[1]);
+                if (half == 0) {
+                  mma_x<kPasses>(acc1[0][nt], ah[0], al[0], bh, bl);
+                  mma_x<kPasses>(acc1[1][nt], ah[1], al[1], bh, bl);
+                } else {
+                  mma_x<kPasses>(acc2[0][nt], ah[0], al[0], bh, bl);
+                  mma_x<kPasses>(acc2[1][nt], ah[1], al[1], bh, bl);
+                }
               }
             }
           }
-        }
-        if (half == 0) {
-          // hidden chunk c: relu(acc1 + b1) -> Hb.  Every warp passed >= 1 barrier since it last read Hb
-          // (GEMM2 of chunk c-1 / the K tile), and the next slice barrier publishes these writes.
-#pragma unroll
-          for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-              const int col = wn * 64 + nt * 8 + 2 * t;
-              const int row = wm * 32 + mt * 16 + g;
-              const float bb0 = sm.b1[c * kRows + col], bb1 = sm.b1[c * kRows + col + 1];
-              *reinterpret_cast<float2*>(&sm.Hb[row * kLdA + col]) =
-                  make_float2(fmaxf(acc1[mt][nt][0] + bb0, 0.f), fmaxf(acc1[mt][nt][1] + bb1, 0.f));
-              *reinterpret_cast<float2*>(&sm.Hb[(row + 8) * kLdA + col]) =
-                  make_float2(fmaxf(acc1[mt][nt][2] + bb0, 0.f), fmaxf(acc1[mt][nt][3] + bb1, 0.f));
-            }
+          if (half == 0) {
+            // hidden chunk c: relu(acc1 + b1) -> Hb.  Every warp passed >= 1 barrier since it last read Hb
+            // (GEMM2 of chunk c-1 / the K tile), and the next slice barrier publishes these writes.
+  #pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+  #pragma unroll
+              for (int nt = 0; nt < 8; ++nt) {
+                const int col = wn * 64 + nt * 8 + 2 * t;
+                const int row = wm * 32 + mt * 16 + g;
+                const float bb0 = sm.b1[c * kRows + col], bb1 = sm.b1[c * kRows + col + 1];
+                *reinterpret_cast<float2*>(&sm.Hb[row * kLdA + col]) =
+                    make_float2(fmaxf(acc1[mt][nt][0] + bb0, 0.f), fmaxf(acc1[mt][nt][1] + bb1, 0.f));
+                *reinterpret_cast<float2*>(&sm.Hb[(row + 8) * kLdA + col]) =
+                    make_float2(fmaxf(acc1[mt][nt][2] + bb0, 0.f), fmaxf(acc1[mt][nt][3] + bb1, 0.f));
+              }
+          }
         }
       }
+      // residual epilogue: g' = acc2 + b2 + g, in place (each element is read and written by one thread)
+  #pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+  #pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int col = wn * 64 + nt * 8 + 2 * t;
+          const int row = wm * 32 + mt * 16 + g;
+          float2* g0 = reinterpret_cast<float2*>(&sm.A[row * kLdA + col]);
+          float2* g1 = reinterpret_cast<float2*>(&sm.A[(row + 8) * kLdA + col]);
+          float2 v0 = *g0, v1 = *g1;
+          v0.x += acc2[mt][nt][0] + sm.b2[col]; v0.y += acc2[mt][nt][1] + sm.b2[col + 1];
+          v1.x += acc2[mt][nt][2] + sm.b2[col]; v1.y += acc2[mt][nt][3] + sm.b2[col + 1];
+          *g0 = v0;
+          *g1 = v1;
+        }
     }
-    // residual epilogue: g' = acc2 + b2 + g, in place (each element is read and written by one thread)
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = wn * 64 + nt * 8 + 2 * t;
-        const int row = wm * 32 + mt * 16 + g;
-        float2* g0 = reinterpret_cast<float2*>(&sm.A[row * kLdA + col]);
-        float2* g1 = reinterpret_cast<float2*>(&sm.A[(row + 8) * kLdA + col]);
-        float2 v0 = *g0, v1 = *g1;
-        v0.x += acc2[mt][nt][0] + sm.b2[col]; v0.y += acc2[mt][nt][1] + sm.b2[col + 1];
-        v1.x += acc2[mt][nt][2] + sm.b2[col]; v1.y += acc2[mt][nt][3] + sm.b2[col + 1];
-        *g0 = v0;
-        *g1 = v1;
-      }
 
+    if (!kTc) PHASE_STAMP(3);
     // ---- G: pointer logits, row-owner layout (warp = 16 rows x all keys) ------------------------
     float lg[kNTMax][4];
 #pragma unroll
@@ -561,7 +786,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParam
 #pragma unroll 1
     for (int ks4 = 0; ks4 < 4; ++ks4, ++sl) {
       cp_async_wait<1>();
-      __syncthreads();  // first iteration also publishes the residual epilogue
+      cta_sync<kTc>();  // first iteration also publishes the residual epilogue
       issue_slice(sl + 2, sm, p, Lk, tid);
       const float* sB = sm.Bs + (sl % kStages) * kStageFloats;
 #pragma unroll
@@ -585,6 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParam
       }
     }
     cp_async_wait<0>();
+    PHASE_STAMP(5);
 
     // ---- epilogue: bias, clip, mask, log-softmax, selection, transition --------------------------
     const float inv_sqrt_e = 0.08838834764831845f;  // 1 / sqrt(128)
@@ -748,11 +974,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParam
     }
     ++step;
     ++t_out;
+    PHASE_STAMP(6);
   }
 
   if (p.logits_only) return;
   // ---------------- exit: close the tours, publish per-rollout sums ----------------
-  __syncthreads();
+  cta_sync<kTc>();
   if (tid < kRows && sm.active[tid]) {
     const int row = tid;
     const int64_t r = (int64_t)(tile * kRows + row) * p.n_inst + b;
@@ -770,6 +997,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutParam
   if (tid == 0) {
     p.ws_tile_steps[blockIdx.x] = t_out;
     atomicMax(p.max_steps_out, t_out);
+  }
+  if (kTc) {
+    if (tid == 0) {
+      sm.exit_flag = 1;
+      tc05::mbar_arrive(&sm.bar_go);  // releases the producer warp
+    }
+    tc05::fence_before_sync();
+    cta_sync<kTc>();
+    if (warp == 0) tc05::tmem_dealloc(sm.tmem_base, 512);
   }
 }
 
@@ -803,15 +1039,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(RolloutParams p, float* l
   }
 }
 
-}  // namespace rrnco
-
-using namespace rrnco;
-
-namespace {
-
-template <int kEnv, int kNTMax, int kPasses>
+// The kernel template is instantiated in two translation units so that they compile in parallel:
+// this file (mma.sync FFN, also the logits-only mode) and rollout_kernel_tc.cu (RRNCO_BUILD_TC: tcgen05 FFN).
+template <int kEnv, int kNTMax, int kPasses, bool kTc>
 int launch_rollout(const RolloutParams& p, cudaStream_t st) {
-  auto kern = rollout_kernel<kEnv, kNTMax, kPasses>;
+  auto kern = rollout_kernel<kEnv, kNTMax, kPasses, kTc>;
   static bool configured = false;  // idempotent attribute; benign if raced
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess)
@@ -820,24 +1052,54 @@ int launch_rollout(const RolloutParams& p, cudaStream_t st) {
   }
   const int64_t grid = p.n_inst * p.n_tiles;
   if (grid <= 0 || grid > 0x7fffffffLL) return RRNCO_ERR_UNSUPPORTED;
-  kern<<<(unsigned)grid, kThreads, sizeof(Smem), st>>>(p);
+  kern<<<(unsigned)grid, kTc ? kThreadsTc : kThreads, sizeof(Smem), st>>>(p);
   return rrnco_launch_status();
 }
 
-template <int kEnv>
+template <int kEnv, bool kTc>
 int dispatch_rollout(const RolloutParams& p, int passes, cudaStream_t st) {
-  if (p.NT <= 13) return passes == 1 ? launch_rollout<kEnv, 13, 1>(p, st) : launch_rollout<kEnv, 13, 3>(p, st);
-  return passes == 1 ? launch_rollout<kEnv, 16, 1>(p, st) : launch_rollout<kEnv, 16, 3>(p, st);
+  if (p.NT <= 13)
+    return passes == 1 ? launch_rollout<kEnv, 13, 1, kTc>(p, st) : launch_rollout<kEnv, 13, 3, kTc>(p, st);
+  return passes == 1 ? launch_rollout<kEnv, 16, 1, kTc>(p, st) : launch_rollout<kEnv, 16, 3, kTc>(p, st);
 }
 
-int dispatch_env(const RolloutParams& p, int env, int passes, cudaStream_t st) {
+static int phase_cycles_local(long long* h_out, int reset) {
+  if (h_out && cudaMemcpyFromSymbol(h_out, g_phase_cycles, sizeof(long long) * 16) != cudaSuccess) return RRNCO_ERR_CUDA;
+  if (reset) {
+    long long z[16] = {0};
+    if (cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)) != cudaSuccess) return RRNCO_ERR_CUDA;
+  }
+  return RRNCO_OK;
+}
+
+#ifdef RRNCO_BUILD_TC
+int phase_cycles_tc(long long* h_out, int reset) { return phase_cycles_local(h_out, reset); }
+int dispatch_env_tc(const RolloutParams& p, int env, int passes, cudaStream_t st) {
   switch (env) {
-    case RRNCO_ENV_ATSP: return dispatch_rollout<RRNCO_ENV_ATSP>(p, passes, st);
-    case RRNCO_ENV_RCVRP: return dispatch_rollout<RRNCO_ENV_RCVRP>(p, passes, st);
-    case RRNCO_ENV_RCVRPTW: return dispatch_rollout<RRNCO_ENV_RCVRPTW>(p, passes, st);
+    case RRNCO_ENV_ATSP: return dispatch_rollout<RRNCO_ENV_ATSP, true>(p, passes, st);
+    case RRNCO_ENV_RCVRP: return dispatch_rollout<RRNCO_ENV_RCVRP, true>(p, passes, st);
+    case RRNCO_ENV_RCVRPTW: return dispatch_rollout<RRNCO_ENV_RCVRPTW, true>(p, passes, st);
     default: return RRNCO_ERR_BAD_ARG;
   }
 }
+}  // namespace rrnco
+#else
+int dispatch_env_tc(const RolloutParams& p, int env, int passes, cudaStream_t st);  // rollout_kernel_tc.cu
+int phase_cycles_tc(long long* h_out, int reset);
+
+int dispatch_env(const RolloutParams& p, int env, int passes, cudaStream_t st) {
+  switch (env) {
+    case RRNCO_ENV_ATSP: return dispatch_rollout<RRNCO_ENV_ATSP, false>(p, passes, st);
+    case RRNCO_ENV_RCVRP: return dispatch_rollout<RRNCO_ENV_RCVRP, false>(p, passes, st);
+    case RRNCO_ENV_RCVRPTW: return dispatch_rollout<RRNCO_ENV_RCVRPTW, false>(p, passes, st);
+    default: return RRNCO_ERR_BAD_ARG;
+  }
+}
+}  // namespace rrnco
+
+using namespace rrnco;
+
+namespace {
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
@@ -858,10 +1120,16 @@ int check_common(int32_t env, int32_t N, int64_t n_inst, int32_t S, const rrnco_
 }
 
 int g_passes = 3;  // set through rrnco_set_precision (process-wide default, read-only on the hot path)
+int g_engine = 1;  // FFN engine of the fused rollout: 1 = tcgen05 (TMEM accumulators), 0 = mma.sync
 
 }  // namespace
 
 extern "C" {
+
+// debug: per-phase cycle totals of CTA 0 since the last reset (host buffer of 16 int64); reset != 0 clears them
+int rrnco_debug_phase_cycles(long long* h_out, int reset) {
+  return g_engine == 1 ? phase_cycles_tc(h_out, reset) : phase_cycles_local(h_out, reset);
+}
 
 // precision of the in-kernel contractions: 3 = 3xTF32 (fp32-faithful, default), 1 = single TF32 pass
 int rrnco_set_precision(int32_t passes) {
@@ -870,12 +1138,20 @@ int rrnco_set_precision(int32_t passes) {
   return RRNCO_OK;
 }
 
+// FFN engine of the fused rollout kernel: 1 = tcgen05.mma + TMEM + TMA weight stream (default), 0 = mma.sync
+int rrnco_set_ffn_engine(int32_t engine) {
+  if (engine != 0 && engine != 1) return RRNCO_ERR_BAD_ARG;
+  g_engine = engine;
+  return RRNCO_OK;
+}
+
 int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts) {
   (void)env; (void)n_nodes;
   if (n_inst <= 0 || n_starts <= 0) return 0;
   const int64_t R = n_inst * n_starts;
   const int64_t tiles = n_inst * ((n_starts + kRows - 1) / kRows);
-  return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL);
+  return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL) +
+         kFfnPackedFloats * (int64_t)sizeof(float);
 }
 
 int rrnco_decoder_logits(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts,
@@ -928,9 +1204,18 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
   p.ws_len = reinterpret_cast<double*>(workspace);
   p.ws_lp = p.ws_len + R;
   p.ws_tile_steps = reinterpret_cast<int32_t*>(p.ws_lp + R);
+  const int64_t tiles = n_inst * p.n_tiles;
+  float* packed = reinterpret_cast<float*>(reinterpret_cast<char*>(p.ws_tile_steps) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL));
+  p.ffn_packed = packed;
   p.max_steps_out = max_steps_out; p.status = status;
   if (cudaMemsetAsync(max_steps_out, 0, sizeof(int32_t), st) != cudaSuccess) return RRNCO_ERR_CUDA;
-  rc = dispatch_env(p, env, g_passes, st);
+  if (g_engine == 1) {
+    rc = pack_ffn_weights(w->ffn_w1, w->ffn_w2, packed, st);
+    if (rc != RRNCO_OK) return rc;
+    rc = dispatch_env_tc(p, env, g_passes, st);
+  } else {
+    rc = dispatch_env(p, env, g_passes, st);
+  }
   if (rc != RRNCO_OK) return rc;
   const unsigned fgrid = (unsigned)((R + 255) / 256 > 4096 ? 4096 : (R + 255) / 256);
   switch (env) {
@@ -942,3 +1227,4 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
 }
 
 }  // extern "C"
+#endif  // RRNCO_BUILD_TC

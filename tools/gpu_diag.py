@@ -212,6 +212,17 @@ def diag_speed(name="rcvrp", B=256, n=100, A=1):
             torch.cuda.synchronize()
             dt = time.time() - t0
         T = out["actions"].shape[1]
+        import ctypes
+        buf = (ctypes.c_longlong * 16)()
+        L = rb._lib.lib()
+        L.rrnco_debug_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.rrnco_debug_phase_cycles(None, 1)
+        out = pol(td0, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+        torch.cuda.synchronize()
+        L.rrnco_debug_phase_cycles(buf, 0)
+        cyc = [c / max(T - 1, 1) for c in list(buf)[:7]]
+        names = ["mask+q+KVwait", "attention", "ffn:convert", "ffn:gemm+epi1", "ffn:out-epi", "logits gemm", "select+transition"]
+        print("   cycles/step (CTA 0): " + ", ".join(f"{n}={c:.0f}" for n, c in zip(names, cyc)) + f"  total={sum(cyc):.0f}")
         print(f"  passes={passes}: {dt*1e3:.1f} ms for {B} instances x {S} starts, T={T} -> {B/dt:.0f} inst/s; "
               f"per CTA-step {dt/ (B*T/148) *1e6:.1f} us")
     rb.set_precision(3)
@@ -219,10 +230,17 @@ def diag_speed(name="rcvrp", B=256, n=100, A=1):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), "abi", rb._lib.lib().rrnco_abi_version())
-    diag_env_golden()
-    diag_gather()
-    diag_policy_golden()
-    for name in ["rcvrp", "atsp", "rcvrptw"]:
-        diag_rollout_vs_oracle(name, 4, 20)
-    diag_rollout_vs_oracle("rcvrp", 4, 100)
-    diag_speed("rcvrp", 296, 100)
+    quick = len(sys.argv) > 1 and sys.argv[1] in ("quick", "speed")
+    if not quick:
+        diag_env_golden()
+        diag_gather()
+    speed_only = len(sys.argv) > 1 and sys.argv[1] == "speed"
+    for engine in (1, 0):
+        rb.set_ffn_engine(engine)
+        print(f"\n######## FFN engine {engine} ({'tcgen05' if engine else 'mma.sync'}) ########")
+        if not speed_only:
+            diag_policy_golden()
+            for name in ["rcvrp", "atsp", "rcvrptw"]:
+                diag_rollout_vs_oracle(name, 4, 20)
+            diag_rollout_vs_oracle("rcvrp", 4, 100)
+        diag_speed("rcvrp", 296, 100)
