@@ -15,6 +15,7 @@
 //      10.tanh, mask, log-softmax, greedy argmax / Gumbel-max sample / forced action, state transition.
 // All contractions run as 3xTF32 (error-compensated split, fp32-faithful) or 1xTF32 (kPasses == 1, the
 // analogue of the reference's autocast inference path).
+#include <cstdio>
 #include "common.cuh"
 #include "tc05.cuh"
 #include "ffn_pack.cuh"
@@ -68,6 +69,12 @@ struct RolloutParams {
   const float* ffn_packed;  // tcgen05 variant: W1 / W2 packed hi | lo slices (ffn_pack.cuh)
 };
 
+// Transcendentals of the softmax / bias / clip chain on the SFU (ex2 / lg2 / rcp .approx): absolute error
+// <~ 1e-6 on the ranges that occur here, i.e. below the 3xTF32 noise of the logits themselves (~3e-6).
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+__device__ __forceinline__ float flog(float x) { return __logf(x); }
+__device__ __forceinline__ float ftanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
 struct Smem {
   float A[kTileFloats];   // q -> glimpse -> glimpse'
   float Hb[kTileFloats];  // K tile (attention) / FFN hidden chunk
@@ -85,6 +92,10 @@ struct Smem {
   uint32_t mask[kRows][4];
   double len[kRows];
   double lp[kRows];
+  // thread-per-row select epilogue of the tcgen05 variant: the two column halves of a row exchange here
+  float xf[3][2][kRows];
+  int xi[2][kRows];
+  float xchosen[kRows];
   // tcgen05 FFN pipeline
   uint64_t bar_full[kFStages];
   uint64_t bar_empty[kFStages];
@@ -210,9 +221,9 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     if (tid == 32) {
       for (int i = 0; i < kFStages; ++i) {
         tc05::mbar_init(&sm.bar_full[i], 1);
-        tc05::mbar_init(&sm.bar_empty[i], 1);
+        tc05::mbar_init(&sm.bar_empty[i], kPasses);
       }
-      tc05::mbar_init(&sm.bar_acc, 1);
+      tc05::mbar_init(&sm.bar_acc, kPasses);
       tc05::mbar_init(&sm.bar_go, 1);
       tc05::fence_mbar_init();
       sm.exit_flag = 0;
@@ -307,13 +318,29 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       return;
     }
   }
-  uint32_t tc_sl = 0, tc_acc_phase = 0;  // running slice counter / accumulator-barrier phase of the MMA warp
+  uint32_t tc_sl = 0, tc_acc_phase = 0;  // running slice counter / accumulator-barrier phase of the MMA warps
+  if (kTc) {  // every MMA accumulates: zero the hidden-chunk and output accumulators once
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0u;
+    const uint32_t lb = (uint32_t)((warp & 3) * 32) << 16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      tc05::tmem_st16(sm.tmem_base + lb + (warp >> 2) * 64 + q * 16, z);
+      tc05::tmem_st16(sm.tmem_base + 384 + lb + (warp >> 2) * 64 + q * 16, z);
+    }
+    tc05::tmem_wait_st();
+    tc05::fence_before_sync();
+    cta_sync<kTc>();
+    tc05::fence_after_sync();
+  }
   long long phase_t0 = clock64();
   const int r0 = warp * 16 + g, r1 = r0 + 8;  // rows owned by this quad in the row-owner phases
   const int wm = warp >> 1, wn = warp & 1;    // FFN warp grid 4 (M) x 2 (N): 32 x 64 warp tiles
   int step = 0;
   int t_out = p.multistart ? 1 : 0;
   const int NPAD = NT * 8;
+  bool kv_prefetched = false;
 
   while (true) {
     if (!p.logits_only) {
@@ -321,14 +348,18 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       if (all_done || step >= p.max_steps) break;
     }
     // ---- B (issued first so that the copies overlap phase A): K -> Hb, V -> Bs -----------------
-    for (int idx = tid; idx < NPAD * 32; idx += kThreads) {
-      const int row = idx >> 5, c4 = idx & 31;
-      const bool ok = row < N;
-      const size_t off = (size_t)(ok ? row : 0) * kE + c4 * 4;
-      cp_async16_zfill(sm.Hb + row * kLdA + c4 * 4, Kc + off, ok);
-      cp_async16_zfill(sm.Bs + row * kLdA + c4 * 4, Vc + off, ok);
+    // (the tcgen05 variant prefetches them for step t+1 right after the logits MMAs of step t)
+    if (!kv_prefetched) {
+      for (int idx = tid; idx < NPAD * 32; idx += kThreads) {
+        const int row = idx >> 5, c4 = idx & 31;
+        const bool ok = row < N;
+        const size_t off = (size_t)(ok ? row : 0) * kE + c4 * 4;
+        cp_async16_zfill(sm.Hb + row * kLdA + c4 * 4, Kc + off, ok);
+        cp_async16_zfill(sm.Bs + row * kLdA + c4 * 4, Vc + off, ok);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
+    kv_prefetched = false;
 
     // ---- A1: action mask bitsets (row-owner quads) ---------------------------------------------
     if (!p.logits_only) {
@@ -502,8 +533,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           if (j < NT) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              sc[j][e] = expf(sc[j][e] - mx0);
-              sc[j][2 + e] = expf(sc[j][2 + e] - mx1);
+              sc[j][e] = fexp(sc[j][e] - mx0);
+              sc[j][2 + e] = fexp(sc[j][2 + e] - mx1);
               sum0 += sc[j][e];
               sum1 += sc[j][2 + e];
             }
@@ -582,9 +613,20 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       cta_sync<kTc>();
       tc05::fence_after_sync();
       PHASE_STAMP(2);
+      // logit keys of this instance -> registers now (L2 latency hidden behind the FFN); they are split into the
+      // hi | lo core-matrix tiles of the logits GEMM once the FFN has released the shared memory.
+      const int R16 = ((N + 15) >> 4) << 4;  // rows of the logit-key tile = N of the logits MMA (multiple of 16)
+      float4 lkr[kNTMax + 1];
+#pragma unroll
+      for (int i = 0; i < kNTMax + 1; ++i) {
+        const int item = tid + i * kThreads, rest = item >> 5;
+        const int c4 = (rest & 7) * 4 + ((item >> 3) & 3), row = (rest >> 3) * 8 + (item & 7);
+        lkr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < N) lkr[i] = __ldg(reinterpret_cast<const float4*>(Lk + (size_t)row * kE) + c4);
+      }
 
       const uint32_t tbase = sm.tmem_base;
-      const uint32_t t_hacc = tbase, t_ahi = tbase + 128, t_alo = tbase + 256, t_out = tbase + 384;
+      const uint32_t t_hacc = tbase, t_ahi = tbase + 128, t_alo = tbase + 256, t_oacc = tbase + 384;
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       const int colhalf = warp >> 2;
       const uint32_t idesc = tc05::make_idesc_tf32(128, 128);
@@ -593,40 +635,29 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       for (int c = 0; c < 4; ++c) {
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-          if (warp == 0) {  // MMA issue: the whole warp waits for the slice, lane 0 issues
+          if (warp < kPasses) {
+            // MMA issue: warp w issues pass w of every K step (3xTF32: 0 = lo*hi, 1 = hi*lo, 2 = hi*hi; 1xTF32: hi*hi).
+            // One thread sustains only ~1 tcgen05.mma per 160 cycles, the tensor pipe wants one per 64, hence
+            // several issuing warps; all passes accumulate into the same pre-zeroed TMEM tile.
+            const bool a_lo = kPasses == 3 && warp == 0, b_lo = kPasses == 3 && warp == 1;
 #pragma unroll 1
-            for (int ks = 0; ks < 8; ++ks, ++tc_sl) {
-              const int st = tc_sl & (kFStages - 1);
-              tc05::mbar_wait(&sm.bar_full[st], (tc_sl / kFStages) & 1);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t sg = tc_sl + ks;
+              const int st = sg & (kFStages - 1);
+              tc05::mbar_wait(&sm.bar_full[st], (sg / kFStages) & 1);
               tc05::fence_after_sync();
               if (lane == 0) {
                 const uint32_t whi = tc05::smem_u32(sm.Bs + st * kFSliceFloats), wlo = whi + kFRows * kFSliceK * 4;
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
-                  const uint64_t bh = tc05::make_desc(whi + kk * 2 * kLboTile, kLboTile, kSbo);
-                  const uint64_t bl = tc05::make_desc(wlo + kk * 2 * kLboTile, kLboTile, kSbo);
+                  const uint64_t bdesc = tc05::make_desc((b_lo ? wlo : whi) + kk * 2 * kLboTile, kLboTile, kSbo);
                   if (half == 0) {
-                    const uint32_t first = (ks == 0 && kk == 0) ? 0u : 1u;
                     const uint32_t koff = (ks * 4 + kk * 2) * kLboTile;
-                    const uint64_t ah = tc05::make_desc(g_hi_addr + koff, kLboTile, kSbo);
-                    if (kPasses == 3) {
-                      const uint64_t al = tc05::make_desc(g_lo_addr + koff, kLboTile, kSbo);
-                      tc05::mma_ss(t_hacc, al, bh, idesc, first);
-                      tc05::mma_ss(t_hacc, ah, bl, idesc, 1u);
-                      tc05::mma_ss(t_hacc, ah, bh, idesc, 1u);
-                    } else {
-                      tc05::mma_ss(t_hacc, ah, bh, idesc, first);
-                    }
+                    const uint64_t adesc = tc05::make_desc((a_lo ? g_lo_addr : g_hi_addr) + koff, kLboTile, kSbo);
+                    tc05::mma_ss(t_hacc, adesc, bdesc, idesc, 1u);
                   } else {
                     const uint32_t kcol = ks * kFSliceK + kk * 8;
-                    const uint32_t acc = (c == 0 && ks == 0 && kk == 0) ? 0u : 1u;
-                    if (kPasses == 3) {
-                      tc05::mma_ts(t_out, t_alo + kcol, bh, idesc, acc);
-                      tc05::mma_ts(t_out, t_ahi + kcol, bl, idesc, 1u);
-                      tc05::mma_ts(t_out, t_ahi + kcol, bh, idesc, 1u);
-                    } else {
-                      tc05::mma_ts(t_out, t_ahi + kcol, bh, idesc, acc);
-                    }
+                    tc05::mma_ts(t_oacc, (a_lo ? t_alo : t_ahi) + kcol, bdesc, idesc, 1u);
                   }
                 }
                 tc05::commit(&sm.bar_empty[st]);
@@ -635,6 +666,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
               __syncwarp();
             }
           }
+          tc_sl += 8;
           tc05::mbar_wait(&sm.bar_acc, tc_acc_phase);
           tc_acc_phase ^= 1u;
           tc05::fence_after_sync();
@@ -652,6 +684,9 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
               }
               tc05::tmem_st16(t_ahi + lane_base + col0, hi);
               tc05::tmem_st16(t_alo + lane_base + col0, lo);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = 0u;
+              tc05::tmem_st16(t_hacc + lane_base + col0, v);  // re-zero the chunk accumulator for the next GEMM1
             }
             tc05::tmem_wait_st();
             tc05::fence_before_sync();
@@ -660,36 +695,201 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         }
       }
       PHASE_STAMP(3);
-      // output epilogue (thread per row): acc + b2 -> A (row-major again); all MMAs that read the hi tile are done
+      // ---- output epilogue (thread per row): g' = acc + b2 + g  ->  split -> TMEM as the A operand of the logits GEMM
+      const uint32_t lkhi_addr = tc05::smem_u32(sm.Bs), lklo_addr = tc05::smem_u32(sm.Hb);
       {
         const int row = (warp & 3) * 32 + lane;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int col0 = colhalf * 64 + q * 16;
-          uint32_t v[16];
-          tc05::tmem_ld16(t_out + lane_base + col0, v);
+          uint32_t v[16], hi[16], lo[16];
+          tc05::tmem_ld16(t_oacc + lane_base + col0, v);
           tc05::tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(&sm.A[row * kLdA + col0 + i]) =
-                make_float4(__uint_as_float(v[i]) + sm.b2[col0 + i], __uint_as_float(v[i + 1]) + sm.b2[col0 + i + 1],
-                            __uint_as_float(v[i + 2]) + sm.b2[col0 + i + 2], __uint_as_float(v[i + 3]) + sm.b2[col0 + i + 3]);
+          for (int i = 0; i < 16; i += 4) {
+            const int off = ((col0 + i) >> 2) * (kFRows * 4) + row * 4;  // residual g = hi + lo (exact to 2^-22)
+            const float4 gh = *reinterpret_cast<const float4*>(&sm.A[off]);
+            const float4 gl = *reinterpret_cast<const float4*>(&sm.Hb[off]);
+            split_tf32(__uint_as_float(v[i]) + sm.b2[col0 + i] + (gh.x + gl.x), hi[i], lo[i]);
+            split_tf32(__uint_as_float(v[i + 1]) + sm.b2[col0 + i + 1] + (gh.y + gl.y), hi[i + 1], lo[i + 1]);
+            split_tf32(__uint_as_float(v[i + 2]) + sm.b2[col0 + i + 2] + (gh.z + gl.z), hi[i + 2], lo[i + 2]);
+            split_tf32(__uint_as_float(v[i + 3]) + sm.b2[col0 + i + 3] + (gh.w + gl.w), hi[i + 3], lo[i + 3]);
+          }
+          tc05::tmem_st16(t_ahi + lane_base + col0, hi);
+          tc05::tmem_st16(t_alo + lane_base + col0, lo);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+          tc05::tmem_st16(t_oacc + lane_base + col0, v);  // re-zero the output accumulator for the next decode step
+        }
+        tc05::tmem_wait_st();
+      }
+      // logit keys -> hi tile in the (now idle) weight ring; the lo tile overwrites g_lo after the barrier
+#pragma unroll
+      for (int i = 0; i < kNTMax + 1; ++i) {
+        const int item = tid + i * kThreads, rest = item >> 5;
+        const int c4 = (rest & 7) * 4 + ((item >> 3) & 3), row = (rest >> 3) * 8 + (item & 7);
+        if (row < R16) {
+          uint32_t h[4], l[4];
+          split_tf32(lkr[i].x, h[0], l[0]); split_tf32(lkr[i].y, h[1], l[1]);
+          split_tf32(lkr[i].z, h[2], l[2]); split_tf32(lkr[i].w, h[3], l[3]);
+          *reinterpret_cast<uint4*>(&sm.Bs[c4 * (R16 * 4) + row * 4]) = make_uint4(h[0], h[1], h[2], h[3]);
+          lkr[i] = make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
         }
       }
       tc05::fence_before_sync();
-      cta_sync<kTc>();
+      cta_sync<kTc>();  // every thread has read its residual from g_hi / g_lo
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {  // + g (the residual, kept exact in registers)
-        const int idx = tid + i * kThreads, c4 = idx >> 7, row = idx & 127;
-        float4* dst = reinterpret_cast<float4*>(&sm.A[row * kLdA + c4 * 4]);
-        float4 o = *dst;
-        o.x += gres[i].x; o.y += gres[i].y; o.z += gres[i].z; o.w += gres[i].w;
-        *dst = o;
+      for (int i = 0; i < kNTMax + 1; ++i) {
+        const int item = tid + i * kThreads, rest = item >> 5;
+        const int c4 = (rest & 7) * 4 + ((item >> 3) & 3), row = (rest >> 3) * 8 + (item & 7);
+        if (row < R16) *reinterpret_cast<float4*>(&sm.Hb[c4 * (R16 * 4) + row * 4]) = lkr[i];
       }
+      tc05::fence_proxy_async();
+      tc05::fence_before_sync();
+      cta_sync<kTc>();
+      tc05::fence_after_sync();
       PHASE_STAMP(4);
-      sl = 32;  // the logits phase streams its 4 logit-key slices through the same ring memory
-      issue_slice(32, sm, p, Lk, tid);
-      issue_slice(33, sm, p, Lk, tid);
+
+      // ---- G: pointer logits on tcgen05: D[128 x R16] = g'(hi|lo, TMEM) . Lk(hi|lo, smem)^T, 16 K steps ----
+      if (warp < kPasses) {
+        const bool a_lo = kPasses == 3 && warp == 0, b_lo = kPasses == 3 && warp == 1;
+        if (lane == 0) {
+          const uint32_t idesc_l = tc05::make_idesc_tf32(128, R16);
+          const uint32_t lbo_l = (uint32_t)R16 * 16u;
+#pragma unroll 4
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint64_t bdesc = tc05::make_desc((b_lo ? lklo_addr : lkhi_addr) + ks * 2 * lbo_l, lbo_l, kSbo);
+            tc05::mma_ts(t_hacc, (a_lo ? t_alo : t_ahi) + ks * 8, bdesc, idesc_l, 1u);
+          }
+          tc05::commit(&sm.bar_acc);
+        }
+        __syncwarp();
+      }
+      tc05::mbar_wait(&sm.bar_acc, tc_acc_phase);
+      tc_acc_phase ^= 1u;
+      tc05::fence_after_sync();
+      // K / V of the next decode step: both tiles' memory is idle from here to the next attention phase
+      for (int idx = tid; idx < NPAD * 32; idx += kThreads) {
+        const int row = idx >> 5, c4 = idx & 31;
+        const bool ok = row < N;
+        const size_t off = (size_t)(ok ? row : 0) * kE + c4 * 4;
+        cp_async16_zfill(sm.Hb + row * kLdA + c4 * 4, Kc + off, ok);
+        cp_async16_zfill(sm.Bs + row * kLdA + c4 * 4, Vc + off, ok);
+      }
+      cp_async_commit();
+      kv_prefetched = true;
+      PHASE_STAMP(5);
+
+      // ---- select epilogue, thread per row: two threads (column halves) own one rollout ----
+      {
+        const int row = (warp & 3) * 32 + lane;
+        const int cbeg = colhalf * 64;
+        const int cur = sm.cur[row];
+        const int64_t rg = (int64_t)(tile * kRows + (sm.active[row] ? row : 0)) * p.n_inst + b;
+        uint32_t mrow[4];
+        *reinterpret_cast<uint4*>(mrow) = *reinterpret_cast<const uint4*>(sm.mask[row]);
+        const float inv_sqrt_e = 0.08838834764831845f;
+        float lv[64];
+        float mxl = -INFINITY;
+        bool nan_seen = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col0 = cbeg + q * 16;
+          uint32_t v[16];
+          if (col0 < R16) {  // warp-uniform
+            tc05::tmem_ld16(t_hacc + lane_base + col0, v);
+            tc05::tmem_wait_ld();
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = col0 + i;
+            float l = -INFINITY;
+            if (c < N) {
+              l = __uint_as_float(v[i]) * inv_sqrt_e;
+              nan_seen |= l != l;
+              float bias = __fmul_rn(p.w.alpha, D[cur * N + c]);
+              if (kEnv == RRNCO_ENV_RCVRPTW) bias = __fadd_rn(bias, __fmul_rn(p.w.beta, U[cur * N + c]));
+              l = flog(__fadd_rn(fexp(__fsub_rn(l, bias)), 1e-6f));  // decoder.py:198
+              if (p.w.tanh_clipping > 0.f) l = __fmul_rn(ftanh(l), p.w.tanh_clipping);
+              const bool ok = (mrow[c >> 5] >> (c & 31)) & 1u;
+              l = ok ? __fdiv_rn(l, p.w.temperature) : -INFINITY;
+            }
+            lv[q * 16 + i] = l;
+            mxl = fmaxf(mxl, l);
+          }
+          if (col0 < R16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+            tc05::tmem_st16(t_hacc + lane_base + col0, v);  // leave the accumulator zeroed for the next GEMM1
+          }
+        }
+        tc05::tmem_wait_st();
+        if (nan_seen) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
+        sm.xf[0][colhalf][row] = mxl;
+        tc05::fence_before_sync();
+        cta_sync<kTc>();
+        const float mx = fmaxf(sm.xf[0][0][row], sm.xf[0][1][row]);
+        float sel = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) sel += fexp(lv[i] - mx);
+        sm.xf[1][colhalf][row] = sel;
+        cta_sync<kTc>();
+        const float se = flog(sm.xf[1][0][row] + sm.xf[1][1][row]);
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+        const uint2 key2 = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+#pragma unroll
+        for (int i4 = 0; i4 < 64; i4 += 4) {
+          uint4 rnd = make_uint4(0, 0, 0, 0);
+          if (p.mode == RRNCO_DECODE_SAMPLING)
+            rnd = philox4x32(make_uint4((uint32_t)rg, (uint32_t)(rg >> 32), (uint32_t)step, (uint32_t)((cbeg + i4) >> 2)), key2);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lpv = __fsub_rn(__fsub_rn(lv[i4 + e], mx), se);  // log-softmax in the reference's order
+            lv[i4 + e] = lpv;
+            float key = lpv;
+            if (p.mode == RRNCO_DECODE_SAMPLING) {
+              const uint32_t x = e == 0 ? rnd.x : e == 1 ? rnd.y : e == 2 ? rnd.z : rnd.w;
+              key = lpv + (-logf(-logf(u01(x))));
+            }
+            if (key > best) {
+              best = key;
+              besti = cbeg + i4 + e;
+            }
+          }
+        }
+        sm.xf[2][colhalf][row] = best;
+        sm.xi[colhalf][row] = besti;
+        cta_sync<kTc>();
+        int act = (sm.xf[2][1][row] > sm.xf[2][0][row]) ? sm.xi[1][row] : sm.xi[0][row];  // ties -> lower index
+        if (act == 0x7fffffff) act = sm.xi[1][row] == 0x7fffffff ? 0 : sm.xi[1][row];
+        if (p.mode == RRNCO_DECODE_EVALUATE) {
+          if (step < p.forced_T) act = (int)p.forced[rg * p.forced_T + step];
+          act = min(max(act, 0), N - 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (cbeg + i == act) sm.xchosen[row] = lv[i];
+        cta_sync<kTc>();
+        if (colhalf == 0) {
+          const float chosen = sm.xchosen[row];
+          const bool feasible = (mrow[act >> 5] >> (act & 31)) & 1u;
+          if (!feasible && sm.active[row]) atomicOr(p.status, RRNCO_DEV_INFEASIBLE);
+          const bool count_leg = kEnv != RRNCO_ENV_ATSP || t_out > 0;
+          transition<kEnv>(sm, p, row, act, D, U, cap, closed, count_leg);
+          if (kEnv == RRNCO_ENV_ATSP && t_out == 0) sm.first[row] = act;
+          sm.lp[row] += (double)chosen;
+          if (sm.active[row] && t_out < p.t_cap) {
+            p.actions[rg * p.t_cap + t_out] = act;
+            if (p.logprob) p.logprob[rg * p.t_cap + t_out] = chosen;
+          }
+#ifdef RRNCO_DEBUG_PRINT
+          if (blockIdx.x == 0 && row < 2 && step < 3)
+            printf("dbg row %d step %d t_out %d act %d rg %lld t_cap %d active %d chosen %f ptr %p\n", row, step, t_out, act,
+                   (long long)rg, p.t_cap, sm.active[row], chosen, (void*)p.actions);
+#endif
+        }
+      }
     } else {
       issue_slice(0, sm, p, Lk, tid);
       issue_slice(1, sm, p, Lk, tid);
@@ -778,198 +978,205 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         }
     }
 
-    if (!kTc) PHASE_STAMP(3);
-    // ---- G: pointer logits, row-owner layout (warp = 16 rows x all keys) ------------------------
-    float lg[kNTMax][4];
-#pragma unroll
-    for (int j = 0; j < kNTMax; ++j) lg[j][0] = lg[j][1] = lg[j][2] = lg[j][3] = 0.f;
-#pragma unroll 1
-    for (int ks4 = 0; ks4 < 4; ++ks4, ++sl) {
-      cp_async_wait<1>();
-      cta_sync<kTc>();  // first iteration also publishes the residual epilogue
-      issue_slice(sl + 2, sm, p, Lk, tid);
-      const float* sB = sm.Bs + (sl % kStages) * kStageFloats;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t ah[4], al[4];
-        const float* ap = sm.A + r0 * kLdA + ks4 * kSliceK + kk * 8 + t;
-        split_tf32(ap[0], ah[0], al[0]);
-        split_tf32(ap[8 * kLdA], ah[1], al[1]);
-        split_tf32(ap[4], ah[2], al[2]);
-        split_tf32(ap[8 * kLdA + 4], ah[3], al[3]);
-#pragma unroll
-        for (int j = 0; j < kNTMax; ++j) {
-          if (j < NT) {
-            const float* bp = sB + (8 * j + g) * kLdB + kk * 8 + t;
-            uint32_t bh[2], bl[2];
-            split_tf32(bp[0], bh[0], bl[0]);
-            split_tf32(bp[4], bh[1], bl[1]);
-            mma_x<kPasses>(lg[j], ah, al, bh, bl);
-          }
-        }
-      }
-    }
-    cp_async_wait<0>();
-    PHASE_STAMP(5);
-
-    // ---- epilogue: bias, clip, mask, log-softmax, selection, transition --------------------------
-    const float inv_sqrt_e = 0.08838834764831845f;  // 1 / sqrt(128)
-    const int cur0 = sm.cur[r0], cur1 = sm.cur[r1];
-    bool nan_seen = false;
-#pragma unroll
-    for (int j = 0; j < kNTMax; ++j) {
-      if (j < NT) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 8 * j + 2 * t + (e & 1);
-          const int cur = e < 2 ? cur0 : cur1;
-          float l = lg[j][e] * inv_sqrt_e;
-          if (c < N) {
-            nan_seen |= l != l;
-            float bias = __fmul_rn(p.w.alpha, D[cur * N + c]);
-            if (kEnv == RRNCO_ENV_RCVRPTW) bias = __fadd_rn(bias, __fmul_rn(p.w.beta, U[cur * N + c]));
-            l = logf(__fadd_rn(expf(__fsub_rn(l, bias)), 1e-6f));  // decoder.py:198
-          }
-          lg[j][e] = l;
-        }
-      }
-    }
-    if (nan_seen) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
-
-    if (p.logits_only) {
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int row = rr ? r1 : r0;
-        const int s = tile * kRows + row;
-        if (s < p.S) {
-          float* dst = p.logits_out + ((int64_t)s * p.n_inst + b) * N;
-#pragma unroll
-          for (int j = 0; j < kNTMax; ++j)
+    if (!kTc) {
+      PHASE_STAMP(3);
+      // ---- G: pointer logits, row-owner layout (warp = 16 rows x all keys) ------------------------
+      float lg[kNTMax][4];
+  #pragma unroll
+      for (int j = 0; j < kNTMax; ++j) lg[j][0] = lg[j][1] = lg[j][2] = lg[j][3] = 0.f;
+  #pragma unroll 1
+      for (int ks4 = 0; ks4 < 4; ++ks4, ++sl) {
+        cp_async_wait<1>();
+        cta_sync<kTc>();  // first iteration also publishes the residual epilogue
+        issue_slice(sl + 2, sm, p, Lk, tid);
+        const float* sB = sm.Bs + (sl % kStages) * kStageFloats;
+  #pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t ah[4], al[4];
+          const float* ap = sm.A + r0 * kLdA + ks4 * kSliceK + kk * 8 + t;
+          split_tf32(ap[0], ah[0], al[0]);
+          split_tf32(ap[8 * kLdA], ah[1], al[1]);
+          split_tf32(ap[4], ah[2], al[2]);
+          split_tf32(ap[8 * kLdA + 4], ah[3], al[3]);
+  #pragma unroll
+          for (int j = 0; j < kNTMax; ++j) {
             if (j < NT) {
-              const int c = 8 * j + 2 * t;
-              if (c < N) dst[c] = lg[j][2 * rr];
-              if (c + 1 < N) dst[c + 1] = lg[j][2 * rr + 1];
+              const float* bp = sB + (8 * j + g) * kLdB + kk * 8 + t;
+              uint32_t bh[2], bl[2];
+              split_tf32(bp[0], bh[0], bl[0]);
+              split_tf32(bp[4], bh[1], bl[1]);
+              mma_x<kPasses>(lg[j], ah, al, bh, bl);
             }
+          }
         }
       }
-      break;
-    }
+      cp_async_wait<0>();
+      PHASE_STAMP(5);
 
-    uint32_t m0[4], m1[4];
-    *reinterpret_cast<uint4*>(m0) = *reinterpret_cast<const uint4*>(sm.mask[r0]);
-    *reinterpret_cast<uint4*>(m1) = *reinterpret_cast<const uint4*>(sm.mask[r1]);
-    float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int j = 0; j < kNTMax; ++j) {
-      if (j < NT) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const bool ok = bit_of(e < 2 ? m0 : m1, j, 2 * t + (e & 1));
-          float l = lg[j][e];
-          if (p.w.tanh_clipping > 0.f) l = __fmul_rn(tanhf(l), p.w.tanh_clipping);  // decoding.py:342-343
-          l = ok ? __fdiv_rn(l, p.w.temperature) : -INFINITY;                       // decoding.py:348-351
-          lg[j][e] = l;
-          mx[e >> 1] = fmaxf(mx[e >> 1], l);
+      // ---- epilogue: bias, clip, mask, log-softmax, selection, transition --------------------------
+      const float inv_sqrt_e = 0.08838834764831845f;  // 1 / sqrt(128)
+      const int cur0 = sm.cur[r0], cur1 = sm.cur[r1];
+      bool nan_seen = false;
+  #pragma unroll
+      for (int j = 0; j < kNTMax; ++j) {
+        if (j < NT) {
+  #pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 8 * j + 2 * t + (e & 1);
+            const int cur = e < 2 ? cur0 : cur1;
+            float l = lg[j][e] * inv_sqrt_e;
+            if (c < N) {
+              nan_seen |= l != l;
+              float bias = __fmul_rn(p.w.alpha, D[cur * N + c]);
+              if (kEnv == RRNCO_ENV_RCVRPTW) bias = __fadd_rn(bias, __fmul_rn(p.w.beta, U[cur * N + c]));
+              l = flog(__fadd_rn(fexp(__fsub_rn(l, bias)), 1e-6f));  // decoder.py:198
+            }
+            lg[j][e] = l;
+          }
         }
       }
-    }
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 1));
-      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 2));
-    }
-    float se[2] = {0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < kNTMax; ++j)
-      if (j < NT) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) se[e >> 1] += expf(lg[j][e] - mx[e >> 1]);
+      if (nan_seen) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
+
+      if (p.logits_only) {
+  #pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int row = rr ? r1 : r0;
+          const int s = tile * kRows + row;
+          if (s < p.S) {
+            float* dst = p.logits_out + ((int64_t)s * p.n_inst + b) * N;
+  #pragma unroll
+            for (int j = 0; j < kNTMax; ++j)
+              if (j < NT) {
+                const int c = 8 * j + 2 * t;
+                if (c < N) dst[c] = lg[j][2 * rr];
+                if (c + 1 < N) dst[c + 1] = lg[j][2 * rr + 1];
+              }
+          }
+        }
+        break;
       }
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      se[rr] += __shfl_xor_sync(0xffffffffu, se[rr], 1);
-      se[rr] += __shfl_xor_sync(0xffffffffu, se[rr], 2);
-      se[rr] = logf(se[rr]);
-    }
-    // log-probs (x - max) - log(sum) in the reference's order; selection on them
-    float best[2] = {-INFINITY, -INFINITY};
-    int besti[2] = {0x7fffffff, 0x7fffffff};
-    // reference-layout rollout ids (padded rows shadow the tile's first rollout)
-    const int64_t rg0 = (int64_t)(tile * kRows + (sm.active[r0] ? r0 : 0)) * p.n_inst + b;
-    const int64_t rg1 = (int64_t)(tile * kRows + (sm.active[r1] ? r1 : 0)) * p.n_inst + b;
-#pragma unroll
-    for (int j = 0; j < kNTMax; ++j) {
-      if (j < NT) {
-        uint4 rnd = make_uint4(0, 0, 0, 0);
-        if (p.mode == RRNCO_DECODE_SAMPLING)
-          rnd = philox4x32(make_uint4((uint32_t)rg0, (uint32_t)(rg0 >> 32), (uint32_t)step, (uint32_t)(j * 4 + t)),
-                           make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 8 * j + 2 * t + (e & 1);
-          const float lpv = __fsub_rn(__fsub_rn(lg[j][e], mx[e >> 1]), se[e >> 1]);
-          lg[j][e] = lpv;
-          float key = lpv;
+
+      uint32_t m0[4], m1[4];
+      *reinterpret_cast<uint4*>(m0) = *reinterpret_cast<const uint4*>(sm.mask[r0]);
+      *reinterpret_cast<uint4*>(m1) = *reinterpret_cast<const uint4*>(sm.mask[r1]);
+      float mx[2] = {-INFINITY, -INFINITY};
+  #pragma unroll
+      for (int j = 0; j < kNTMax; ++j) {
+        if (j < NT) {
+  #pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool ok = bit_of(e < 2 ? m0 : m1, j, 2 * t + (e & 1));
+            float l = lg[j][e];
+            if (p.w.tanh_clipping > 0.f) l = __fmul_rn(ftanh(l), p.w.tanh_clipping);  // decoding.py:342-343
+            l = ok ? __fdiv_rn(l, p.w.temperature) : -INFINITY;                       // decoding.py:348-351
+            lg[j][e] = l;
+            mx[e >> 1] = fmaxf(mx[e >> 1], l);
+          }
+        }
+      }
+  #pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 1));
+        mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 2));
+      }
+      float se[2] = {0.f, 0.f};
+  #pragma unroll
+      for (int j = 0; j < kNTMax; ++j)
+        if (j < NT) {
+  #pragma unroll
+          for (int e = 0; e < 4; ++e) se[e >> 1] += fexp(lg[j][e] - mx[e >> 1]);
+        }
+  #pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        se[rr] += __shfl_xor_sync(0xffffffffu, se[rr], 1);
+        se[rr] += __shfl_xor_sync(0xffffffffu, se[rr], 2);
+        se[rr] = flog(se[rr]);
+      }
+      // log-probs (x - max) - log(sum) in the reference's order; selection on them
+      float best[2] = {-INFINITY, -INFINITY};
+      int besti[2] = {0x7fffffff, 0x7fffffff};
+      // reference-layout rollout ids (padded rows shadow the tile's first rollout)
+      const int64_t rg0 = (int64_t)(tile * kRows + (sm.active[r0] ? r0 : 0)) * p.n_inst + b;
+      const int64_t rg1 = (int64_t)(tile * kRows + (sm.active[r1] ? r1 : 0)) * p.n_inst + b;
+  #pragma unroll
+      for (int j = 0; j < kNTMax; ++j) {
+        if (j < NT) {
+          // Gumbel noise of (rollout r, step, column c) = Philox(key = seed; ctr = (r, step, c >> 2))[c & 3]
+          uint4 rnd0 = make_uint4(0, 0, 0, 0), rnd1 = rnd0;
           if (p.mode == RRNCO_DECODE_SAMPLING) {
-            const uint32_t x = e == 0 ? rnd.x : e == 1 ? rnd.y : e == 2 ? rnd.z : rnd.w;
-            key = lpv + (-logf(-logf(u01(x))));  // Gumbel-max
+            const uint2 key2 = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+            rnd0 = philox4x32(make_uint4((uint32_t)rg0, (uint32_t)(rg0 >> 32), (uint32_t)step, (uint32_t)(2 * j + (t >> 1))), key2);
+            rnd1 = philox4x32(make_uint4((uint32_t)rg1, (uint32_t)(rg1 >> 32), (uint32_t)step, (uint32_t)(2 * j + (t >> 1))), key2);
           }
-          if (key > best[e >> 1]) {  // strict: lowest index wins ties (ascending c within a lane)
-            best[e >> 1] = key;
-            besti[e >> 1] = c;
+  #pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 8 * j + 2 * t + (e & 1);
+            const float lpv = __fsub_rn(__fsub_rn(lg[j][e], mx[e >> 1]), se[e >> 1]);
+            lg[j][e] = lpv;
+            float key = lpv;
+            if (p.mode == RRNCO_DECODE_SAMPLING) {
+              const uint4 rnd = e < 2 ? rnd0 : rnd1;
+              const int comp = 2 * (t & 1) + (e & 1);
+              const uint32_t x = comp == 0 ? rnd.x : comp == 1 ? rnd.y : comp == 2 ? rnd.z : rnd.w;
+              key = lpv + (-logf(-logf(u01(x))));  // Gumbel-max
+            }
+            if (key > best[e >> 1]) {  // strict: lowest index wins ties (ascending c within a lane)
+              best[e >> 1] = key;
+              besti[e >> 1] = c;
+            }
           }
         }
       }
-    }
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-#pragma unroll
-      for (int o = 1; o <= 2; o <<= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best[rr], o);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti[rr], o);
-        if (ov > best[rr] || (ov == best[rr] && oi < besti[rr])) {
-          best[rr] = ov;
-          besti[rr] = oi;
+  #pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+  #pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best[rr], o);
+          const int oi = __shfl_xor_sync(0xffffffffu, besti[rr], o);
+          if (ov > best[rr] || (ov == best[rr] && oi < besti[rr])) {
+            best[rr] = ov;
+            besti[rr] = oi;
+          }
         }
       }
-    }
-    int act[2] = {besti[0] == 0x7fffffff ? 0 : besti[0], besti[1] == 0x7fffffff ? 0 : besti[1]};
-    if (p.mode == RRNCO_DECODE_EVALUATE) {
-      const bool have = step < p.forced_T;
-      act[0] = have && sm.active[r0] ? (int)p.forced[rg0 * p.forced_T + step] : act[0];
-      act[1] = have && sm.active[r1] ? (int)p.forced[rg1 * p.forced_T + step] : act[1];
-      act[0] = min(max(act[0], 0), N - 1);
-      act[1] = min(max(act[1], 0), N - 1);
-    }
-    // chosen log-prob: owner lane contributes, quad-sum
-    float chosen[2] = {0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < kNTMax; ++j)
-      if (j < NT) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (8 * j + 2 * t + (e & 1) == act[e >> 1]) chosen[e >> 1] = lg[j][e];
+      int act[2] = {besti[0] == 0x7fffffff ? 0 : besti[0], besti[1] == 0x7fffffff ? 0 : besti[1]};
+      if (p.mode == RRNCO_DECODE_EVALUATE) {
+        const bool have = step < p.forced_T;
+        act[0] = have && sm.active[r0] ? (int)p.forced[rg0 * p.forced_T + step] : act[0];
+        act[1] = have && sm.active[r1] ? (int)p.forced[rg1 * p.forced_T + step] : act[1];
+        act[0] = min(max(act[0], 0), N - 1);
+        act[1] = min(max(act[1], 0), N - 1);
       }
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {  // only the owner lane matched: quad-sum broadcasts its value
-      chosen[rr] += __shfl_xor_sync(0xffffffffu, chosen[rr], 1);
-      chosen[rr] += __shfl_xor_sync(0xffffffffu, chosen[rr], 2);
-    }
-    // one lane per row applies the transition and emits the outputs
-    if (t < 2) {
-      const int rr = t;
-      const int row = rr ? r1 : r0;
-      const int a = act[rr];
-      const int64_t rg = rr ? rg1 : rg0;
-      const bool feasible = (sm.mask[row][a >> 5] >> (a & 31)) & 1u;
-      if (!feasible && sm.active[row]) atomicOr(p.status, RRNCO_DEV_INFEASIBLE);
-      const bool count_leg = kEnv != RRNCO_ENV_ATSP || t_out > 0;
-      transition<kEnv>(sm, p, row, a, D, U, cap, closed, count_leg);
-      if (kEnv == RRNCO_ENV_ATSP && t_out == 0) sm.first[row] = a;
-      sm.lp[row] += (double)chosen[rr];
-      if (sm.active[row] && t_out < p.t_cap) {
-        p.actions[rg * p.t_cap + t_out] = a;
-        if (p.logprob) p.logprob[rg * p.t_cap + t_out] = chosen[rr];
+      // chosen log-prob: owner lane contributes, quad-sum
+      float chosen[2] = {0.f, 0.f};
+  #pragma unroll
+      for (int j = 0; j < kNTMax; ++j)
+        if (j < NT) {
+  #pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (8 * j + 2 * t + (e & 1) == act[e >> 1]) chosen[e >> 1] = lg[j][e];
+        }
+  #pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {  // only the owner lane matched: quad-sum broadcasts its value
+        chosen[rr] += __shfl_xor_sync(0xffffffffu, chosen[rr], 1);
+        chosen[rr] += __shfl_xor_sync(0xffffffffu, chosen[rr], 2);
+      }
+      // one lane per row applies the transition and emits the outputs
+      if (t < 2) {
+        const int rr = t;
+        const int row = rr ? r1 : r0;
+        const int a = act[rr];
+        const int64_t rg = rr ? rg1 : rg0;
+        const bool feasible = (sm.mask[row][a >> 5] >> (a & 31)) & 1u;
+        if (!feasible && sm.active[row]) atomicOr(p.status, RRNCO_DEV_INFEASIBLE);
+        const bool count_leg = kEnv != RRNCO_ENV_ATSP || t_out > 0;
+        transition<kEnv>(sm, p, row, a, D, U, cap, closed, count_leg);
+        if (kEnv == RRNCO_ENV_ATSP && t_out == 0) sm.first[row] = a;
+        sm.lp[row] += (double)chosen[rr];
+        if (sm.active[row] && t_out < p.t_cap) {
+          p.actions[rg * p.t_cap + t_out] = a;
+          if (p.logprob) p.logprob[rg * p.t_cap + t_out] = chosen[rr];
+        }
       }
     }
     ++step;
@@ -977,6 +1184,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     PHASE_STAMP(6);
   }
 
+  cp_async_wait<0>();  // a prefetch of the tcgen05 variant may still be in flight
   if (p.logits_only) return;
   // ---------------- exit: close the tours, publish per-rollout sums ----------------
   cta_sync<kTc>();
