@@ -221,9 +221,9 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     if (tid == 32) {
       for (int i = 0; i < kFStages; ++i) {
         tc05::mbar_init(&sm.bar_full[i], 1);
-        tc05::mbar_init(&sm.bar_empty[i], kPasses);
+        tc05::mbar_init(&sm.bar_empty[i], 2 * kPasses);
       }
-      tc05::mbar_init(&sm.bar_acc, kPasses);
+      tc05::mbar_init(&sm.bar_acc, 2 * kPasses);
       tc05::mbar_init(&sm.bar_go, 1);
       tc05::fence_mbar_init();
       sm.exit_flag = 0;
@@ -635,11 +635,13 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       for (int c = 0; c < 4; ++c) {
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-          if (warp < kPasses) {
-            // MMA issue: warp w issues pass w of every K step (3xTF32: 0 = lo*hi, 1 = hi*lo, 2 = hi*hi; 1xTF32: hi*hi).
-            // One thread sustains only ~1 tcgen05.mma per 160 cycles, the tensor pipe wants one per 64, hence
-            // several issuing warps; all passes accumulate into the same pre-zeroed TMEM tile.
-            const bool a_lo = kPasses == 3 && warp == 0, b_lo = kPasses == 3 && warp == 1;
+          if (warp < 2 * kPasses) {
+            // MMA issue: one thread sustains only ~1 tcgen05.mma per 160 cycles while the tensor pipe wants one per
+            // 64, so 2 x kPasses warps issue: warp w -> K step (w & 1) of every slice, pass w >> 1
+            // (3xTF32: 0 = lo*hi, 1 = hi*lo, 2 = hi*hi; 1xTF32: hi*hi).  All of them accumulate into the same
+            // pre-zeroed TMEM tile, so no issue order between the warps is needed.
+            const int pass = warp >> 1, kk = warp & 1;
+            const bool a_lo = kPasses == 3 && pass == 0, b_lo = kPasses == 3 && pass == 1;
 #pragma unroll 1
             for (int ks = 0; ks < 8; ++ks) {
               const uint32_t sg = tc_sl + ks;
@@ -648,17 +650,14 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
               tc05::fence_after_sync();
               if (lane == 0) {
                 const uint32_t whi = tc05::smem_u32(sm.Bs + st * kFSliceFloats), wlo = whi + kFRows * kFSliceK * 4;
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                  const uint64_t bdesc = tc05::make_desc((b_lo ? wlo : whi) + kk * 2 * kLboTile, kLboTile, kSbo);
-                  if (half == 0) {
-                    const uint32_t koff = (ks * 4 + kk * 2) * kLboTile;
-                    const uint64_t adesc = tc05::make_desc((a_lo ? g_lo_addr : g_hi_addr) + koff, kLboTile, kSbo);
-                    tc05::mma_ss(t_hacc, adesc, bdesc, idesc, 1u);
-                  } else {
-                    const uint32_t kcol = ks * kFSliceK + kk * 8;
-                    tc05::mma_ts(t_oacc, (a_lo ? t_alo : t_ahi) + kcol, bdesc, idesc, 1u);
-                  }
+                const uint64_t bdesc = tc05::make_desc((b_lo ? wlo : whi) + kk * 2 * kLboTile, kLboTile, kSbo);
+                if (half == 0) {
+                  const uint32_t koff = (ks * 4 + kk * 2) * kLboTile;
+                  const uint64_t adesc = tc05::make_desc((a_lo ? g_lo_addr : g_hi_addr) + koff, kLboTile, kSbo);
+                  tc05::mma_ss(t_hacc, adesc, bdesc, idesc, 1u);
+                } else {
+                  const uint32_t kcol = ks * kFSliceK + kk * 8;
+                  tc05::mma_ts(t_oacc, (a_lo ? t_alo : t_ahi) + kcol, bdesc, idesc, 1u);
                 }
                 tc05::commit(&sm.bar_empty[st]);
                 if (ks == 7) tc05::commit(&sm.bar_acc);
@@ -751,13 +750,14 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       PHASE_STAMP(4);
 
       // ---- G: pointer logits on tcgen05: D[128 x R16] = g'(hi|lo, TMEM) . Lk(hi|lo, smem)^T, 16 K steps ----
-      if (warp < kPasses) {
-        const bool a_lo = kPasses == 3 && warp == 0, b_lo = kPasses == 3 && warp == 1;
+      if (warp < 2 * kPasses) {
+        const int pass = warp >> 1, kpar = warp & 1;
+        const bool a_lo = kPasses == 3 && pass == 0, b_lo = kPasses == 3 && pass == 1;
         if (lane == 0) {
           const uint32_t idesc_l = tc05::make_idesc_tf32(128, R16);
           const uint32_t lbo_l = (uint32_t)R16 * 16u;
 #pragma unroll 4
-          for (int ks = 0; ks < 16; ++ks) {
+          for (int ks = kpar; ks < 16; ks += 2) {
             const uint64_t bdesc = tc05::make_desc((b_lo ? lklo_addr : lkhi_addr) + ks * 2 * lbo_l, lbo_l, kSbo);
             tc05::mma_ts(t_hacc, (a_lo ? t_alo : t_ahi) + ks * 8, bdesc, idesc_l, 1u);
           }
