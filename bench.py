@@ -278,6 +278,55 @@ def run_ours(args, rank, world, local_rank):
         return rb.fused_rollout(decoder, cache, env, td_aug, N_START, True, "greedy", check=False)
     ms_kernel, _ = timed(kernel_only, max(2, args.steps // 2), 1)
 
+    # ---- standalone env-step and gather kernels (the "env-step HBM GB/s" half of the metric) ---------------
+    def env_step_probe():
+        # reference layout: td batchified over the POMO starts (R rollouts), one RCVRPEnv._step + get_action_mask
+        td_aug, _ = dev_sets[0]
+        R_probe = Bp * 16  # 131 072 rollouts: 97 MB of state+demand per step (> L2 together with the outputs)
+        tdb = rb.batchify(rb.TensorDictLite({k: td_aug[k] for k in ("demand", "used_capacity", "vehicle_capacity",
+                                                                     "visited", "current_node")}, batch_size=[Bp]), 16)
+        g = torch.Generator(device=dev).manual_seed(0)
+        tdb.set("action", torch.randint(1, N_LOC + 1, (R_probe,), device=dev, generator=g))
+        for _ in range(3):
+            type(env)._kernel(tdb, tdb["action"])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            type(env)._kernel(tdb, tdb["action"])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        nbytes = R_probe * (7 * (N_LOC + 1) + 30)  # RCVRP 7N+30 B per rollout-step
+        return {"kernel": "rrnco::rcvrp_step_kernel (RCVRPEnv._step + get_action_mask)", "rollouts": R_probe,
+                "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes, "achieved": nbytes / (ms * 1e-3) / 1e9,
+                "unit": "GB/s", "note": "includes the torch.empty allocations of the 5 output tensors"}
+
+    def gather_probe():
+        from rrnco_b200.sampler import CityOnDevice, gather_submatrix
+        city = CityOnDevice(make_city(3), dev)
+        rng = np.random.RandomState(1)
+        idx = torch.from_numpy(np.array([rng.choice(1000, N_LOC + 1, replace=False) for _ in range(4096)])).to(dev)
+        for _ in range(3):
+            gather_submatrix(city.distance, idx, normalize=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            gather_submatrix(city.distance, idx, normalize=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        nbytes = 4096 * 12 * (N_LOC + 1) ** 2  # 8 B fp64 gathered + 4 B fp32 written per element
+        return {"kernel": "rrnco::gather_submatrix_kernel (+ fused reset normalisation)", "instances": 4096,
+                "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes, "achieved": nbytes / (ms * 1e-3) / 1e9,
+                "unit": "GB/s"}
+
+    env_probe = env_step_probe() if rank == 0 else None
+    gat_probe = gather_probe() if rank == 0 else None
+
     # ---- e2e: host inputs, H2D + reset + cache + rollout + reduction + D2H ----------------------------
     ms_e2e, best = timed(step_e2e, max(2, args.steps // 2), 1)
     raw, row, col = host_sets[0]
@@ -316,6 +365,11 @@ def run_ours(args, rank, world, local_rank):
                                     "frac": tflops / tf_peak,
                                     "note": "fp32-faithful mode issues 3 TF32 passes per algorithmic FLOP"}},
         }
+        for probe in (env_probe, gat_probe):
+            probe["peak"] = hbm_peak
+            probe["frac"] = probe["achieved"] / hbm_peak
+        line["env_step"] = env_probe
+        line["gather"] = gat_probe
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rate, dt, cost, Tc = cpu_rollout_rate(args.cpu_sample, threads)

@@ -216,6 +216,27 @@ int rrnco_decoder_logits(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n
                          const uint8_t* mask, const float* ctx_state, int32_t use_placeholder,
                          float* logits_out, uint32_t* status, void* stream);
 
+/* Key-streaming variant of rrnco_decoder_logits for ANY number of nodes (e.g. the n=1000 generalisation
+ * configs): online-softmax attention over streamed keys, the tcgen05 pointer FFN, streamed logit keys.
+ * Same arguments plus a workspace of >= rrnco_decoder_logits_large_workspace_bytes(n_inst * n_starts) bytes. */
+int64_t rrnco_decoder_logits_large_workspace_bytes(int64_t n_rollouts);
+int rrnco_decoder_logits_large(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts,
+                               const rrnco_decoder_weights_t* w, const rrnco_decoder_cache_t* cache,
+                               const rrnco_instance_data_t* data, const int64_t* current, const int64_t* first,
+                               const uint8_t* mask, const float* ctx_state, int32_t use_placeholder,
+                               float* logits_out, uint32_t* status, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DecodingStrategy.step  rrnco/models/decoding.py:219-298 with process_logits :311-361 (top-k / top-p off)
+ *   logits fp32 [R,N] (decoder output), mask bool [R,N]  ->  action int64 [R], log-prob of the action fp32 [R]
+ *   greedy: argmax of the log-softmax, lowest index on ties; sampling: Gumbel-max with noise
+ *   Philox(seed; (r, step, n >> 2))[n & 3]; evaluate: forced_action [R].
+ * ---------------------------------------------------------------------------------------------- */
+int rrnco_select_action(int64_t n_rollouts, int32_t n_nodes, const float* logits, const uint8_t* mask,
+                        int32_t decode_mode, float tanh_clipping, float temperature, uint64_t seed, int32_t step,
+                        const int64_t* forced_action, int64_t* action_out, float* logprob_out, uint32_t* status,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused construction rollout = RRNetPolicy.forward decode loop  rrnco/models/policy.py:203-243
  *   (multistart pre-hook decoding.py:157-205, decoder.py:151-206, process_logits decoding.py:311-361,

@@ -202,9 +202,16 @@ class RRNetDecoder(nn.Module):
         logits = torch.empty((R, N), dtype=torch.float32, device=mask.device)
         status = torch.zeros(1, dtype=torch.int32, device=mask.device)
         cs = cached.struct()
-        call("rrnco_decoder_logits", ENV_ID[self.env_name], N, n_inst, S, C.byref(w), C.byref(cs), C.byref(data),
-             ptr(cur), ptr(first), ptr(_u8(mask)), ptr(state), placeholder, ptr(logits), ptr(status),
-             stream_ptr(mask.device))
+        if N <= _lib.MAX_NODES_FUSED:
+            call("rrnco_decoder_logits", ENV_ID[self.env_name], N, n_inst, S, C.byref(w), C.byref(cs), C.byref(data),
+                 ptr(cur), ptr(first), ptr(_u8(mask)), ptr(state), placeholder, ptr(logits), ptr(status),
+                 stream_ptr(mask.device))
+        else:  # key-streaming kernels: any N
+            ws = torch.empty(_lib.lib().rrnco_decoder_logits_large_workspace_bytes(R), dtype=torch.uint8,
+                             device=mask.device)
+            call("rrnco_decoder_logits_large", ENV_ID[self.env_name], N, n_inst, S, C.byref(w), C.byref(cs),
+                 C.byref(data), ptr(cur), ptr(first), ptr(_u8(mask)), ptr(state), placeholder, ptr(logits),
+                 ptr(status), ptr(ws), stream_ptr(mask.device))
         if self.check_nan:  # upstream asserts (and syncs) every step: decoder.py:303-304
             _lib.raise_device_status(int(status.item()) & _lib.DEV_NAN_LOGITS)
         return logits, mask
@@ -267,7 +274,8 @@ class RRNetPolicy(nn.Module):
 
         cache = self.decoder._precompute_cache((row_emb, col_emb), num_starts=S)
         self._calls += 1
-        out = fused_rollout(self.decoder, cache, env, td, S, multistart, decode_type.replace("multistart_", ""),
+        rollout_fn = fused_rollout if cache.glimpse_key.shape[1] <= _lib.MAX_NODES_FUSED else stepwise_rollout
+        out = rollout_fn(self.decoder, cache, env, td, S, multistart, decode_type.replace("multistart_", ""),
                             forced_actions=actions, seed=decoding_kwargs.pop("seed", self.seed + self._calls),
                             temperature=temperature, tanh_clipping=tanh_clipping, calc_reward=calc_reward,
                             per_step_logprobs=not return_sum_log_likelihood, check=self.decoder.check_nan)
@@ -331,5 +339,94 @@ def fused_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_s
         else:
             out["reward"] = norm
     else:  # upstream returns the (all-zero) step reward of the last env.step
+        out["reward"] = torch.zeros(R, dtype=torch.float32 if name == "rcvrptw" else torch.bool, device=dev)
+    return out
+
+
+def select_action(logits, mask, kind: str = "greedy", tanh_clipping: float = 10.0, temperature: float = 1.0,
+                  seed: int = 0, step: int = 0, forced_action=None, status=None):
+    """DecodingStrategy.step (decoding.py:219-298): (action int64 [R], log-prob fp32 [R]) in one kernel."""
+    logits, mask = logits.contiguous(), mask.contiguous()
+    R, N = logits.shape
+    action = torch.empty(R, dtype=torch.int64, device=logits.device)
+    logp = torch.empty(R, dtype=torch.float32, device=logits.device)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=logits.device)
+    forced = None if forced_action is None else forced_action.contiguous()
+    call("rrnco_select_action", R, N, ptr(logits), ptr(_u8(mask)), DECODE_ID[kind], float(tanh_clipping),
+         float(temperature), int(seed) & (2**64 - 1), int(step), ptr(forced), ptr(action), ptr(logp), ptr(status),
+         stream_ptr(logits.device))
+    return action, logp, status
+
+
+_ROLLOUT_STATE_KEYS = {
+    "atsp": ("first_node", "current_node", "i", "action_mask"),
+    "rcvrp": ("current_node", "used_capacity", "vehicle_capacity", "visited", "action_mask"),
+    "rcvrptw": ("current_node", "current_time", "current_route_length", "used_capacity_linehaul",
+                "used_capacity_backhaul", "visited", "action_mask", "vehicle_capacity", "open_route", "distance_limit",
+                "backhaul_class"),
+}
+
+
+def stepwise_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_starts: int, multistart: bool,
+                     kind: str, forced_actions=None, seed: int = 0, temperature: float = 1.0, tanh_clipping: float = 10.0,
+                     calc_reward: bool = True, per_step_logprobs: bool = False, check: bool = True, t_cap=None) -> dict:
+    """policy.py:203-243 as a per-step kernel pipeline for ANY number of nodes (decoder_logits_large ->
+    select_action -> env step), used when N exceeds the fused kernel's 128-key tile.  Only the rollout STATE is
+    replicated over the POMO starts; matrices / demands / time windows stay one copy per instance (the kernels
+    index row r % data_rows), so the n=1000 configs never materialise upstream's S-fold `batchify` of [N,N] data."""
+    from .tdlite import TensorDictLite, batchify
+    from .envs import tour_reward
+    name = decoder.env_name
+    n_inst, N, _ = cache.glimpse_key.shape
+    S = int(num_starts)
+    R = n_inst * S
+    dev = cache.glimpse_key.device
+    roll = {k: (batchify(td[k], S) if k in _ROLLOUT_STATE_KEYS[name] else td[k]) for k in td.keys() if k != "done"}
+    roll = TensorDictLite(roll, batch_size=[R])
+    actions, logps = [], []
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if multistart:
+        a0 = env.select_start_nodes(td, S)
+        roll.set("action", a0)
+        roll = env.step(roll)["next"]
+        actions.append(a0)
+        logps.append(torch.zeros(R, dtype=torch.float32, device=dev))
+        done = roll["done"]
+    else:
+        done = torch.zeros(R, dtype=torch.bool, device=dev)
+    step = 0
+    max_steps = 2 * N + 2
+    while step < max_steps:
+        if name == "atsp":  # fixed length: no host sync needed
+            if len(actions) >= N:
+                break
+        elif bool(done.all()):  # upstream syncs here every step too (policy.py:212)
+            break
+        logits, mask = decoder(roll, cache, S)
+        forced = forced_actions[:, step].to(dev) if kind == "evaluate" else None
+        a, lp, status = select_action(logits, mask, kind, tanh_clipping, temperature, seed, step, forced, status)
+        roll.set("action", a)
+        roll = env.step(roll)["next"]
+        done = roll["done"]
+        actions.append(a)
+        logps.append(lp)
+        step += 1
+    if check:
+        _lib.raise_device_status(int(status.item()))
+    acts = torch.stack(actions, 1)
+    lps = torch.stack(logps, 1)
+    out = {"actions": acts, "log_likelihood": lps.double().sum(1).float(), "logprobs": lps}
+    has_minmax = "min_distance" in td.keys()
+    if calc_reward:
+        open_route = td["open_route"] if name == "rcvrptw" else None
+        real, norm = tour_reward(acts, td["distance_matrix"], name != "atsp", open_route,
+                                 td["min_distance"] if has_minmax and env.normalize else None,
+                                 td["max_distance"] if has_minmax and env.normalize else None)
+        if env.normalize and has_minmax:
+            out["reward"], out["normalized_reward"] = real, norm
+        else:
+            out["reward"] = norm
+    else:
         out["reward"] = torch.zeros(R, dtype=torch.float32 if name == "rcvrptw" else torch.bool, device=dev)
     return out

@@ -285,6 +285,53 @@ def test_pointer_ffn_tcgen05(rb):
         assert (out.double() - ref).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("name,n,B,S", [("atsp", 150, 2, None), ("rcvrp", 140, 2, None), ("rcvrptw", 130, 2, 40),
+                                         ("atsp", 1000, 1, 100)])
+def test_large_n_stepwise_rollout_vs_oracle(rb, name, n, B, S):
+    """N > 128 (incl. BASELINE's ATSP n=1000 generalisation case, 100 starts like test.py:129-130): key-streaming
+    decoder + select + env-step kernels, matrices never replicated over the starts."""
+    raw = synth.make_instances(name, B, n, seed=n)
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    otd = oenv.reset(raw)
+    N = otd["action_mask"].shape[-1]
+    S = oenv.get_num_starts(otd) if S is None else S
+    row, col = synth.random_embeddings(B, N, seed=n + 1)
+    p = omodel.init_decoder_params(name, seed=n + 2)
+    with torch.inference_mode():
+        oout = omodel.policy_forward(p, oenv, otd, row, col, decode_type="multistart_greedy", num_starts=S)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    out = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    acts, want = out["actions"].cpu(), oout["actions"]
+    T = max(acts.shape[1], want.shape[1])
+    acts = torch.nn.functional.pad(acts, (0, T - acts.shape[1]))
+    want = torch.nn.functional.pad(want, (0, T - want.shape[1]))
+    same = (acts == want).all(1)
+    assert same.float().mean() >= 0.97, same.float().mean()
+    assert rel(out["reward"].cpu()[same], oout["reward"][same]) < 1e-6
+    best, obest = out["reward"].cpu().view(S, B).max(0)[0], oout["reward"].view(S, B).max(0)[0]
+    assert ((best - obest).abs() / obest.abs() < 1e-4).all()
+    if name == "atsp":  # every tour is a permutation
+        assert (out["actions"].sort(1)[0] == torch.arange(N, device=dev)).all()
+
+
+def test_select_action_matches_process_logits(rb):
+    """rrnco_select_action == decoding.py process_logits + greedy / evaluate on random logits and masks."""
+    g = torch.Generator().manual_seed(3)
+    R, N = 257, 333
+    logits = torch.randn(R, N, generator=g) * 3
+    mask = torch.rand(R, N, generator=g) < 0.4
+    mask[:, 0] = True
+    logp = omodel.process_logits(logits.clone(), mask)
+    a, lp, _ = rb.select_action(logits.to(dev), mask.to(dev), "greedy")
+    assert torch.equal(a.cpu(), logp.argmax(-1))
+    assert (lp.cpu() - logp.gather(1, a.cpu()[:, None]).squeeze(1)).abs().max() < 1e-5
+    forced = torch.multinomial(mask.float(), 1, generator=g).squeeze(1)
+    a2, lp2, _ = rb.select_action(logits.to(dev), mask.to(dev), "evaluate", forced_action=forced.to(dev))
+    assert torch.equal(a2.cpu(), forced)
+    assert (lp2.cpu() - logp.gather(1, forced[:, None]).squeeze(1)).abs().max() < 1e-5
+
+
 def test_evaluate_multistart_vs_oracle(rb):
     name, n, B = "rcvrptw", 30, 6
     raw = synth.make_instances(name, B, n, seed=9)
