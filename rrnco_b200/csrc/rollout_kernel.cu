@@ -765,6 +765,26 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         }
         __syncwarp();
       }
+      // bias rows of this rollout (alpha . D[cur,:] + beta . Dur[cur,:]) -> registers while the logits MMAs run.
+      // Column groups of 16 are dealt round-robin to the two threads of a row (balanced for N not a multiple of 32).
+      float lv[64];
+      {
+        const int row_s = (warp & 3) * 32 + lane;
+        const int cur_s = sm.cur[row_s];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = (2 * q + colhalf) * 16 + i;
+            float bias = 0.f;
+            if (c < N) {
+              bias = __fmul_rn(p.w.alpha, D[cur_s * N + c]);
+              if (kEnv == RRNCO_ENV_RCVRPTW) bias = __fadd_rn(bias, __fmul_rn(p.w.beta, U[cur_s * N + c]));
+            }
+            lv[q * 16 + i] = bias;
+          }
+        }
+      }
       tc05::mbar_wait(&sm.bar_acc, tc_acc_phase);
       tc_acc_phase ^= 1u;
       tc05::fence_after_sync();
@@ -783,18 +803,16 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       // ---- select epilogue, thread per row: two threads (column halves) own one rollout ----
       {
         const int row = (warp & 3) * 32 + lane;
-        const int cbeg = colhalf * 64;
-        const int cur = sm.cur[row];
         const int64_t rg = (int64_t)(tile * kRows + (sm.active[row] ? row : 0)) * p.n_inst + b;
         uint32_t mrow[4];
         *reinterpret_cast<uint4*>(mrow) = *reinterpret_cast<const uint4*>(sm.mask[row]);
         const float inv_sqrt_e = 0.08838834764831845f;
-        float lv[64];
+        const bool unit_temp = p.w.temperature == 1.0f;
         float mxl = -INFINITY;
         bool nan_seen = false;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int col0 = cbeg + q * 16;
+          const int col0 = (2 * q + colhalf) * 16;
           uint32_t v[16];
           if (col0 < R16) {  // warp-uniform
             tc05::tmem_ld16(t_hacc + lane_base + col0, v);
@@ -807,12 +825,10 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             if (c < N) {
               l = __uint_as_float(v[i]) * inv_sqrt_e;
               nan_seen |= l != l;
-              float bias = __fmul_rn(p.w.alpha, D[cur * N + c]);
-              if (kEnv == RRNCO_ENV_RCVRPTW) bias = __fadd_rn(bias, __fmul_rn(p.w.beta, U[cur * N + c]));
-              l = flog(__fadd_rn(fexp(__fsub_rn(l, bias)), 1e-6f));  // decoder.py:198
+              l = flog(__fadd_rn(fexp(__fsub_rn(l, lv[q * 16 + i])), 1e-6f));  // decoder.py:198
               if (p.w.tanh_clipping > 0.f) l = __fmul_rn(ftanh(l), p.w.tanh_clipping);
               const bool ok = (mrow[c >> 5] >> (c & 31)) & 1u;
-              l = ok ? __fdiv_rn(l, p.w.temperature) : -INFINITY;
+              l = ok ? (unit_temp ? l : __fdiv_rn(l, p.w.temperature)) : -INFINITY;
             }
             lv[q * 16 + i] = l;
             mxl = fmaxf(mxl, l);
@@ -842,7 +858,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         for (int i4 = 0; i4 < 64; i4 += 4) {
           uint4 rnd = make_uint4(0, 0, 0, 0);
           if (p.mode == RRNCO_DECODE_SAMPLING)
-            rnd = philox4x32(make_uint4((uint32_t)rg, (uint32_t)(rg >> 32), (uint32_t)step, (uint32_t)((cbeg + i4) >> 2)), key2);
+            rnd = philox4x32(make_uint4((uint32_t)rg, (uint32_t)(rg >> 32), (uint32_t)step,
+                                        (uint32_t)(((2 * (i4 >> 4) + colhalf) * 16 + (i4 & 15)) >> 2)), key2);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float lpv = __fsub_rn(__fsub_rn(lv[i4 + e], mx), se);  // log-softmax in the reference's order
@@ -854,14 +871,15 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             }
             if (key > best) {
               best = key;
-              besti = cbeg + i4 + e;
+              besti = (2 * (i4 >> 4) + colhalf) * 16 + (i4 & 15) + e;
             }
           }
         }
         sm.xf[2][colhalf][row] = best;
         sm.xi[colhalf][row] = besti;
         cta_sync<kTc>();
-        int act = (sm.xf[2][1][row] > sm.xf[2][0][row]) ? sm.xi[1][row] : sm.xi[0][row];  // ties -> lower index
+        int act = sm.xi[0][row];  // larger key wins, ties -> lower index
+        if (sm.xf[2][1][row] > sm.xf[2][0][row] || (sm.xf[2][1][row] == sm.xf[2][0][row] && sm.xi[1][row] < act)) act = sm.xi[1][row];
         if (act == 0x7fffffff) act = sm.xi[1][row] == 0x7fffffff ? 0 : sm.xi[1][row];
         if (p.mode == RRNCO_DECODE_EVALUATE) {
           if (step < p.forced_T) act = (int)p.forced[rg * p.forced_T + step];
@@ -869,7 +887,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         }
 #pragma unroll
         for (int i = 0; i < 64; ++i)
-          if (cbeg + i == act) sm.xchosen[row] = lv[i];
+          if ((2 * (i >> 4) + colhalf) * 16 + (i & 15) == act) sm.xchosen[row] = lv[i];
         cta_sync<kTc>();
         if (colhalf == 0) {
           const float chosen = sm.xchosen[row];
