@@ -276,32 +276,45 @@ def run_ours(args, rank, world, local_rank):
     def kernel_only(i):
         td_aug, cache = dev_sets[i % n_sets]
         return rb.fused_rollout(decoder, cache, env, td_aug, N_START, True, "greedy", check=False)
-    ms_kernel, _ = timed(kernel_only, max(2, args.steps // 2), 1)
+    ms_kernel, _ = timed(kernel_only, args.steps, 2)
 
     # ---- standalone env-step and gather kernels (the "env-step HBM GB/s" half of the metric) ---------------
     def env_step_probe():
-        # reference layout: td batchified over the POMO starts (R rollouts), one RCVRPEnv._step + get_action_mask
+        # reference layout, the C2 rollout count: R = 8192 x 101 rollouts, one RCVRPEnv._step + get_action_mask
+        # through the C ABI with pre-allocated outputs (610 MB of algorithmic traffic per launch, >> L2)
+        from rrnco_b200._lib import call, ptr, stream_ptr
         td_aug, _ = dev_sets[0]
-        R_probe = Bp * 16  # 131 072 rollouts: 97 MB of state+demand per step (> L2 together with the outputs)
-        tdb = rb.batchify(rb.TensorDictLite({k: td_aug[k] for k in ("demand", "used_capacity", "vehicle_capacity",
-                                                                     "visited", "current_node")}, batch_size=[Bp]), 16)
+        R_probe = Bp * N_START
+        N = N_LOC + 1
         g = torch.Generator(device=dev).manual_seed(0)
-        tdb.set("action", torch.randint(1, N_LOC + 1, (R_probe,), device=dev, generator=g))
+        demand = rb.batchify(td_aug["demand"], N_START).contiguous()           # [R, N-1] as upstream's batchify
+        cap = torch.ones(R_probe, device=dev)
+        used = torch.rand(R_probe, device=dev, generator=g) * 0.5
+        visited = (torch.rand(R_probe, N, device=dev, generator=g) < 0.3).to(torch.uint8)
+        action = torch.randint(1, N, (R_probe,), device=dev, generator=g)
+        used_o, vis_o = torch.empty_like(used), torch.empty_like(visited)
+        cur_o = torch.empty(R_probe, dtype=torch.int64, device=dev)
+        done_o = torch.empty(R_probe, dtype=torch.bool, device=dev)
+        mask_o = torch.empty(R_probe, N, dtype=torch.bool, device=dev)
+
+        def launch():
+            call("rrnco_rcvrp_step", R_probe, N, R_probe, ptr(action), ptr(demand), ptr(cap), R_probe, ptr(used),
+                 ptr(visited), None, ptr(used_o), ptr(vis_o), ptr(cur_o), ptr(done_o), ptr(mask_o), stream_ptr(dev))
         for _ in range(3):
-            type(env)._kernel(tdb, tdb["action"])
+            launch()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
+        reps = 10
         e0.record()
         for _ in range(reps):
-            type(env)._kernel(tdb, tdb["action"])
+            launch()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        nbytes = R_probe * (7 * (N_LOC + 1) + 30)  # RCVRP 7N+30 B per rollout-step
-        return {"kernel": "rrnco::rcvrp_step_kernel (RCVRPEnv._step + get_action_mask)", "rollouts": R_probe,
-                "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes, "achieved": nbytes / (ms * 1e-3) / 1e9,
-                "unit": "GB/s", "note": "includes the torch.empty allocations of the 5 output tensors"}
+        nbytes = R_probe * (7 * N + 30)  # RCVRP 7N+30 B per rollout-step
+        return {"kernel": "rrnco::rcvrp_step_kernel (RCVRPEnv._step + get_action_mask, reference layout)",
+                "rollouts": R_probe, "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
+                "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s"}
 
     def gather_probe():
         from rrnco_b200.sampler import CityOnDevice, gather_submatrix
@@ -328,7 +341,7 @@ def run_ours(args, rank, world, local_rank):
     gat_probe = gather_probe() if rank == 0 else None
 
     # ---- e2e: host inputs, H2D + reset + cache + rollout + reduction + D2H ----------------------------
-    ms_e2e, best = timed(step_e2e, max(2, args.steps // 2), 1)
+    ms_e2e, best = timed(step_e2e, args.steps, 2)
     raw, row, col = host_sets[0]
     h2d = sum(v.numel() * v.element_size() for v in raw.values()) + 2 * row.numel() * row.element_size()
     d2h = B * 4

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librrnco_b200.so")
 SOURCES = ["env_kernels.cu", "rollout_kernel.cu", "rollout_kernel_tc.cu", "cache_kernel.cu", "ffn_tc_kernel.cu", "step_kernels.cu"]
-NVCC_FLAGS = (["-DRRNCO_DEBUG_PRINT"] if os.environ.get("RRNCO_DEBUG_PRINT") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = (["-DRRNCO_DEBUG_PRINT"] if os.environ.get("RRNCO_DEBUG_PRINT") else []) + (["-DRRNCO_SPLIT_LO_RAW"] if os.environ.get("RRNCO_SPLIT_LO_RAW") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 

@@ -56,7 +56,11 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ uint32_t f2tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = f2tf32(x);
+#ifdef RRNCO_SPLIT_LO_RAW
+  lo = __float_as_uint(x - __uint_as_float(hi));  // experiment: let the tensor core truncate the low part
+#else
   lo = f2tf32(x - __uint_as_float(hi));
+#endif
 }
 // D(16x8) += A(16x8, row) * B(8x8, col); fragment layouts per PTX ISA mma.m16n8k8.tf32.
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {

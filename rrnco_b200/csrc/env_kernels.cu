@@ -165,6 +165,73 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rcvrp_step_kernel(
   }
 }
 
+// Vectorised variant for the un-aliased, fully replicated reference layout (data_rows == R, cap_rows == R or 1):
+// a CTA owns 32 consecutive rollouts, whose visited / mask rows (32 N bytes) and demand rows (32 (N-1) floats) are
+// contiguous and 16-byte aligned as a block, so every global access is a coalesced 128-bit vector; rows are
+// processed from shared memory (one warp per 8 rollouts) and written back the same way.
+constexpr int kGroup = 32;
+__global__ void __launch_bounds__(128) rcvrp_step_vec_kernel(
+    int64_t R, int N, const int64_t* __restrict__ action, const float* __restrict__ demand,
+    const float* __restrict__ capacity, int64_t cap_rows, const float* __restrict__ used_in,
+    const uint8_t* __restrict__ visited_in, float* __restrict__ used_out, uint8_t* __restrict__ visited_out,
+    int64_t* __restrict__ current_out, uint8_t* __restrict__ done_out, uint8_t* __restrict__ mask_out) {
+  extern __shared__ __align__(16) unsigned char sraw[];
+  const int nb = kGroup * N;                       // bytes of one visited / mask block (multiple of 16)
+  uint8_t* s_vis = sraw;                           // [32][N]  (updated in place)
+  uint8_t* s_msk = sraw + nb;                      // [32][N]
+  float* s_dem = reinterpret_cast<float*>(sraw + 2 * nb);  // [32][N-1]
+  const int64_t r0 = (int64_t)blockIdx.x * kGroup;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const uint4* gv = reinterpret_cast<const uint4*>(visited_in + r0 * N);
+    for (int i = tid; i < nb / 16; i += 128) reinterpret_cast<uint4*>(s_vis)[i] = __ldg(gv + i);
+    const uint4* gd = reinterpret_cast<const uint4*>(demand + r0 * (N - 1));
+    for (int i = tid; i < kGroup * (N - 1) / 4; i += 128) reinterpret_cast<uint4*>(s_dem)[i] = __ldg(gd + i);
+  }
+  __syncthreads();
+  for (int k = 0; k < kGroup / 4; ++k) {
+    const int lr = warp * (kGroup / 4) + k;
+    const int64_t r = r0 + lr;
+    const int cur = (int)action[r];
+    const float cap = capacity[r % cap_rows];
+    const float* dem = s_dem + lr * (N - 1);
+    const int di = min(max(cur - 1, 0), N - 2);
+    const float used = __fmul_rn(__fadd_rn(used_in[r], dem[di]), cur != 0 ? 1.0f : 0.0f);
+    uint8_t* vis = s_vis + lr * N;
+    uint8_t* msk = s_msk + lr * N;
+    int n_visited = 0;
+    bool any_free = false;
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      const int n = n0 + lane;
+      bool v = false, free_loc = false;
+      if (n < N) {
+        uint8_t vb = vis[n];
+        if (n == cur) { vb = 1; vis[n] = 1; }
+        v = vb != 0;
+        if (n >= 1) {
+          free_loc = !(v || __fadd_rn(dem[n - 1], used) > cap);
+          msk[n] = free_loc;
+        }
+      }
+      n_visited += __popc(__ballot_sync(0xffffffffu, v));
+      any_free |= __any_sync(0xffffffffu, free_loc);
+    }
+    if (lane == 0) {
+      msk[0] = !(cur == 0 && any_free);
+      used_out[r] = used;
+      current_out[r] = cur;
+      done_out[r] = n_visited == N;
+    }
+  }
+  __syncthreads();
+  uint4* ov = reinterpret_cast<uint4*>(visited_out + r0 * N);
+  uint4* om = reinterpret_cast<uint4*>(mask_out + r0 * N);
+  for (int i = tid; i < nb / 16; i += 128) {
+    ov[i] = reinterpret_cast<const uint4*>(s_vis)[i];
+    om[i] = reinterpret_cast<const uint4*>(s_msk)[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // RCVRPTW (RMTVRP) step + mask      rrnco/envs/rmtvrp/env.py:155-215, 343-428
 // ------------------------------------------------------------------------------------------------
@@ -363,9 +430,27 @@ int rrnco_rcvrp_step(int64_t R, int32_t n_nodes, int64_t data_rows, const int64_
   RRNCO_CHECK_ARG(R > 0 && n_nodes > 1 && data_rows > 0 && cap_rows > 0 && demand && capacity && used_in &&
                   visited_in && mask_out);
   RRNCO_CHECK_ARG(action ? (used_out && visited_out && current_out && done_out) : (current_in != nullptr));
-  rcvrp_step_kernel<<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      R, n_nodes, data_rows, action, demand, capacity, cap_rows, used_in, visited_in, current_in, used_out,
-      visited_out, current_out, done_out, mask_out);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  const size_t smem = 2 * (size_t)kGroup * n_nodes + (size_t)kGroup * (n_nodes - 1) * sizeof(float);
+  const bool vec_ok = action != nullptr && data_rows == R && (cap_rows == 1 || cap_rows == R) && R >= kGroup &&
+                      smem <= 48 * 1024 && al16(demand) &&
+                      al16(visited_in) && al16(visited_out) && al16(mask_out) && visited_in != visited_out;
+  const int64_t R_vec = vec_ok ? (R / kGroup) * kGroup : 0;
+  if (R_vec > 0) {
+    rcvrp_step_vec_kernel<<<(unsigned)(R_vec / kGroup), 128, smem, (cudaStream_t)stream>>>(
+        R_vec, n_nodes, action, demand, capacity, cap_rows, used_in, visited_in, used_out, visited_out, current_out,
+        done_out, mask_out);
+    int rc = rrnco_launch_status();
+    if (rc != RRNCO_OK) return rc;
+  }
+  if (R_vec < R) {  // tail (or the general data_rows / mask-only / aliased case): one warp per rollout
+    const int64_t off = R_vec, Rt = R - R_vec;
+    rcvrp_step_kernel<<<warp_grid(Rt), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        Rt, n_nodes, data_rows, action ? action + off : nullptr, vec_ok ? demand + off * (n_nodes - 1) : demand,
+        (vec_ok && cap_rows == R) ? capacity + off : capacity, (vec_ok && cap_rows == R) ? Rt : cap_rows, used_in + off, visited_in + off * n_nodes, current_in ? current_in + off : nullptr,
+        used_out ? used_out + off : nullptr, visited_out ? visited_out + off * n_nodes : nullptr,
+        current_out ? current_out + off : nullptr, done_out ? done_out + off : nullptr, mask_out + off * n_nodes);
+  }
   return rrnco_launch_status();
 }
 
