@@ -257,6 +257,22 @@ def test_greedy_rollout_vs_oracle(rb, name, n, B):
         env.check_solution_validity(rb.batchify(env.reset(lite(rb, raw)), S), out["actions"])
 
 
+def test_more_starts_than_one_tile(rb):
+    """num_starts > 128 spans two CTA tiles per instance (start nodes wrap around, as upstream's modulo does)."""
+    name, n, B, S = "rcvrp", 40, 3, 150
+    raw = synth.make_instances(name, B, n, seed=8)
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    row, col = synth.random_embeddings(B, n + 1, seed=9)
+    p = omodel.init_decoder_params(name, seed=10)
+    oout = omodel.policy_forward(p, oenv, oenv.reset(raw), row, col, decode_type="multistart_greedy", num_starts=S)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    out = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    assert out["actions"].shape == oout["actions"].shape
+    assert (out["actions"].cpu() == oout["actions"]).all(1).float().mean() >= 0.99
+    assert rel(out["reward"].cpu(), oout["reward"]) < 1e-4
+
+
 @pytest.mark.parametrize("engine", [0, 1])
 def test_ffn_engines_agree(rb, engine):
     """Both FFN engines of the fused kernel (mma.sync / tcgen05) reproduce the oracle's tours."""
