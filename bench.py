@@ -371,7 +371,10 @@ def run_ours(args, rank, world, local_rank):
                     "what": "RRNetPolicy.forward on pinned HOST inputs (instance td + encoder output): H2D, "
                             "env.reset normalisation, x8 augmentation, cache GEMM, fused rollout, best-of reduction, D2H"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch, ncu --set full
+                         # (profiles/r1_ncu_rollout_full_size.csv); only valid for the default 1024-instance batch
+                         "traffic": 3.00e9 if B == 1024 else None, "peak_source": peak_src,
                          "kernel": "rrnco::rollout_kernel<RCVRP>", "ms_per_launch": ms_kernel,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "tensor": {"achieved_tflops_algorithmic": tflops, "peak_bf16_tflops": tf_peak,
