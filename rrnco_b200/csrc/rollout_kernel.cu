@@ -71,9 +71,33 @@ struct RolloutParams {
 
 // Transcendentals of the softmax / bias / clip chain on the SFU (ex2 / lg2 / rcp .approx): absolute error
 // <~ 1e-6 on the ranges that occur here, i.e. below the 3xTF32 noise of the logits themselves (~3e-6).
-__device__ __forceinline__ float fexp(float x) { return __expf(x); }
-__device__ __forceinline__ float flog(float x) { return __logf(x); }
-__device__ __forceinline__ float ftanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+// The .ftz forms skip the denormal pre/post-scaling sequences of __expf / __logf (never needed here: the arguments
+// of lg2 are >= 1e-6, and a denormal exp underflows to 0 against sums that are >= 1).
+__device__ __forceinline__ float ex2a(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2a(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpa(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fexp(float x) { return ex2a(x * 1.4426950408889634f); }
+__device__ __forceinline__ float flog(float x) { return lg2a(x) * 0.6931471805599453f; }
+__device__ __forceinline__ float ftanh(float x) { return fmaf(-2.0f, rcpa(ex2a(x * 2.8853900817779268f) + 1.0f), 1.0f); }
+
+// Gumbel noise of four consecutive columns (canonical mapping, see the select epilogue).  Deliberately not inlined:
+// sixteen inlined copies of Philox + 8 accurate logarithms were 80 KB of code that the greedy path had to jump over.
+static __device__ __noinline__ float4 gumbel4(uint4 ctr, uint2 key) {
+  const uint4 r = philox4x32(ctr, key);
+  return make_float4(-logf(-logf(u01(r.x))), -logf(-logf(u01(r.y))), -logf(-logf(u01(r.z))), -logf(-logf(u01(r.w))));
+}
 
 struct Smem {
   float A[kTileFloats];   // q -> glimpse -> glimpse'
@@ -666,7 +690,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             }
           }
           tc_sl += 8;
-          tc05::mbar_wait(&sm.bar_acc, tc_acc_phase);
+          tc05::mbar_wait(&sm.bar_acc, tc_acc_phase, 64);
           tc_acc_phase ^= 1u;
           tc05::fence_after_sync();
           if (half == 0) {  // hidden chunk: + b1, relu, split -> A operand (hi | lo) of GEMM2 in tensor memory
@@ -785,7 +809,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           }
         }
       }
-      tc05::mbar_wait(&sm.bar_acc, tc_acc_phase);
+      tc05::mbar_wait(&sm.bar_acc, tc_acc_phase, 64);
       tc_acc_phase ^= 1u;
       tc05::fence_after_sync();
       // K / V of the next decode step: both tiles' memory is idle from here to the next attention phase
@@ -801,35 +825,37 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       PHASE_STAMP(5);
 
       // ---- select epilogue, thread per row: two threads (column halves) own one rollout ----
+      // Straight-line and branch-free per element: the step loop's code is larger than the 32 KB L1.5 instruction
+      // cache, so every taken branch costs a fetch from L2 (stall_no_inst dominated the first version of this phase).
       {
         const int row = (warp & 3) * 32 + lane;
         const int64_t rg = (int64_t)(tile * kRows + (sm.active[row] ? row : 0)) * p.n_inst + b;
         uint32_t mrow[4];
         *reinterpret_cast<uint4*>(mrow) = *reinterpret_cast<const uint4*>(sm.mask[row]);
         const float inv_sqrt_e = 0.08838834764831845f;
-        const bool unit_temp = p.w.temperature == 1.0f;
+        const float clip = p.w.tanh_clipping;
+        const int hsh = 16 * colhalf;  // this thread's columns: 32 q + hsh + i
         float mxl = -INFINITY;
         bool nan_seen = false;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int col0 = (2 * q + colhalf) * 16;
+          const int col0 = 32 * q + hsh;
           uint32_t v[16];
           if (col0 < R16) {  // warp-uniform
             tc05::tmem_ld16(t_hacc + lane_base + col0, v);
             tc05::tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
           }
+          const uint32_t mq = mrow[q] >> hsh;  // mask bits of columns >= N are never set
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int c = col0 + i;
-            float l = -INFINITY;
-            if (c < N) {
-              l = __uint_as_float(v[i]) * inv_sqrt_e;
-              nan_seen |= l != l;
-              l = flog(__fadd_rn(fexp(__fsub_rn(l, lv[q * 16 + i])), 1e-6f));  // decoder.py:198
-              if (p.w.tanh_clipping > 0.f) l = __fmul_rn(ftanh(l), p.w.tanh_clipping);
-              const bool ok = (mrow[c >> 5] >> (c & 31)) & 1u;
-              l = ok ? (unit_temp ? l : __fdiv_rn(l, p.w.temperature)) : -INFINITY;
-            }
+            float l = __uint_as_float(v[i]) * inv_sqrt_e;
+            nan_seen |= l != l;
+            l = flog(__fadd_rn(fexp(__fsub_rn(l, lv[q * 16 + i])), 1e-6f));  // decoder.py:198
+            if (clip > 0.f) l = __fmul_rn(ftanh(l), clip);
+            l = ((mq >> i) & 1u) ? l : -INFINITY;
             lv[q * 16 + i] = l;
             mxl = fmaxf(mxl, l);
           }
@@ -839,7 +865,16 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             tc05::tmem_st16(t_hacc + lane_base + col0, v);  // leave the accumulator zeroed for the next GEMM1
           }
         }
+        if (p.w.temperature != 1.0f) {
+          mxl = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            lv[i] = __fdiv_rn(lv[i], p.w.temperature);
+            mxl = fmaxf(mxl, lv[i]);
+          }
+        }
         tc05::tmem_wait_st();
+        PHASE_STAMP(7);
         if (nan_seen) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
         sm.xf[0][colhalf][row] = mxl;
         tc05::fence_before_sync();
@@ -850,47 +885,60 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         for (int i = 0; i < 64; ++i) sel += fexp(lv[i] - mx);
         sm.xf[1][colhalf][row] = sel;
         cta_sync<kTc>();
+        PHASE_STAMP(8);
         const float se = flog(sm.xf[1][0][row] + sm.xf[1][1][row]);
-        float best = -INFINITY;
-        int besti = 0x7fffffff;
-        const uint2 key2 = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        // log-softmax in the reference's order; argmax of log p (greedy / evaluate) or of log p + Gumbel noise
+        float best = -INFINITY, bestlp = -INFINITY;
+        int besti = -1;  // local column 32 q + i, hsh is added below
+        if (p.mode == RRNCO_DECODE_SAMPLING) {
+          const uint2 key2 = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
 #pragma unroll
-        for (int i4 = 0; i4 < 64; i4 += 4) {
-          uint4 rnd = make_uint4(0, 0, 0, 0);
-          if (p.mode == RRNCO_DECODE_SAMPLING)
-            rnd = philox4x32(make_uint4((uint32_t)rg, (uint32_t)(rg >> 32), (uint32_t)step,
-                                        (uint32_t)(((2 * (i4 >> 4) + colhalf) * 16 + (i4 & 15)) >> 2)), key2);
+          for (int i4 = 0; i4 < 64; i4 += 4) {
+            const float4 gn = gumbel4(make_uint4((uint32_t)rg, (uint32_t)(rg >> 32), (uint32_t)step,
+                                                 (uint32_t)((32 * (i4 >> 4) + hsh + (i4 & 15)) >> 2)), key2);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float lpv = __fsub_rn(__fsub_rn(lv[i4 + e], mx), se);  // log-softmax in the reference's order
-            lv[i4 + e] = lpv;
-            float key = lpv;
-            if (p.mode == RRNCO_DECODE_SAMPLING) {
-              const uint32_t x = e == 0 ? rnd.x : e == 1 ? rnd.y : e == 2 ? rnd.z : rnd.w;
-              key = lpv + (-logf(-logf(u01(x))));
-            }
-            if (key > best) {
-              best = key;
-              besti = (2 * (i4 >> 4) + colhalf) * 16 + (i4 & 15) + e;
+            for (int e = 0; e < 4; ++e) {
+              const float lpv = __fsub_rn(__fsub_rn(lv[i4 + e], mx), se);
+              const float key = lpv + (e == 0 ? gn.x : e == 1 ? gn.y : e == 2 ? gn.z : gn.w);
+              const bool better = key > best;
+              best = better ? key : best;
+              bestlp = better ? lpv : bestlp;
+              besti = better ? 32 * (i4 >> 4) + (i4 & 15) + e : besti;
             }
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float lpv = __fsub_rn(__fsub_rn(lv[i], mx), se);
+            lv[i] = lpv;
+            const bool better = lpv > best;
+            best = better ? lpv : best;
+            besti = better ? 32 * (i >> 4) + (i & 15) : besti;
+          }
+          bestlp = best;
         }
         sm.xf[2][colhalf][row] = best;
-        sm.xi[colhalf][row] = besti;
+        sm.xf[0][colhalf][row] = bestlp;  // xf[0] (row maxima) was last read before the previous barrier
+        sm.xi[colhalf][row] = besti < 0 ? 0x7fffffff : besti + hsh;
         cta_sync<kTc>();
+        PHASE_STAMP(9);
         int act = sm.xi[0][row];  // larger key wins, ties -> lower index
-        if (sm.xf[2][1][row] > sm.xf[2][0][row] || (sm.xf[2][1][row] == sm.xf[2][0][row] && sm.xi[1][row] < act)) act = sm.xi[1][row];
-        if (act == 0x7fffffff) act = sm.xi[1][row] == 0x7fffffff ? 0 : sm.xi[1][row];
+        int win = 0;
+        if (sm.xf[2][1][row] > sm.xf[2][0][row] || (sm.xf[2][1][row] == sm.xf[2][0][row] && sm.xi[1][row] < act)) win = 1;
+        act = sm.xi[win][row];
+        float chosen = sm.xf[0][win][row];
+        if (act == 0x7fffffff) act = 0;
         if (p.mode == RRNCO_DECODE_EVALUATE) {
           if (step < p.forced_T) act = (int)p.forced[rg * p.forced_T + step];
           act = min(max(act, 0), N - 1);
-        }
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if ((2 * (i >> 4) + colhalf) * 16 + (i & 15) == act) sm.xchosen[row] = lv[i];
-        cta_sync<kTc>();
+          for (int i = 0; i < 64; ++i)
+            if (32 * (i >> 4) + hsh + (i & 15) == act) sm.xchosen[row] = lv[i];
+          cta_sync<kTc>();
+          chosen = sm.xchosen[row];
+        }
+        PHASE_STAMP(10);
         if (colhalf == 0) {
-          const float chosen = sm.xchosen[row];
           const bool feasible = (mrow[act >> 5] >> (act & 31)) & 1u;
           if (!feasible && sm.active[row]) atomicOr(p.status, RRNCO_DEV_INFEASIBLE);
           const bool count_leg = kEnv != RRNCO_ENV_ATSP || t_out > 0;

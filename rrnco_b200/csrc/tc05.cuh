@@ -16,12 +16,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Wait for the phase with the given parity.  `backoff_ns` > 0 parks the warp between polls (used by the warps that
+// idle through the tensor-core phases, so that they do not compete for issue slots with the MMA-issuing warps).
+// A lost arrival must fail loudly, never hang the GPU: after ~2^26 polls the kernel traps.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns = 0) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t ok;
-  const long long t0 = clock64();
-  do {
-    if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s: a lost arrival must fail loudly, never hang the GPU
+  uint32_t ok, polls = 0;
+  while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -29,9 +30,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(addr), "r"(parity)
         : "memory");
-  } while (!ok);
+    if (ok) break;
+    if (backoff_ns) __nanosleep(backoff_ns);
+    if (++polls > (1u << 26)) __trap();
+  }
 }
-
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t tx_bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(tx_bytes) : "memory");
 }
