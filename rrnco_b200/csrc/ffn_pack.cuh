@@ -1,23 +1,65 @@
-// Packed FFN weight stream shared by the standalone tcgen05 FFN kernel and the fused rollout kernel.
-//   slice s in [0, 64): chunk c = s >> 4 (128 hidden units), half = (s >> 3) & 1 (0: W1 rows of the chunk,
-//   1: W2 columns of the chunk), ks = s & 7 (16 k values).  Each slice is one contiguous 16 KB block
-//   [hi | lo][16-byte K chunk c4 (4)][row (128)][4 floats]  ==  the shared-memory core-matrix layout (tc05.cuh),
-//   so a single cp.async.bulk moves it and two UMMA descriptors (hi, lo) address it.
+// Packed FFN weight stream shared by the standalone tcgen05 FFN kernel and the fused rollout kernel, and the
+// two-term fp16 operand split ("f16s") both of them compute in.
+//
+// f16s split of an fp32 value x, pre-scaled by a power of two S:  x' = S x,  hi = x' rounded to 11 significant
+// bits,  lo = x' - hi  (exact in fp32, |lo| <= 2^-12 |x'|);  both parts are stored as fp16.
+//   activations (A operand): S = kAScale;   weights / logit keys (B operand): S = kWScale / kLkScale
+//   S_a S_w a w ~= A_hi B_hi + A_lo B_hi + A_hi B_lo        (dropped term a_lo w_lo <= 2^-24 |a w|)
+// i.e. three kind::f16 tcgen05 MMAs (K = 16 each, twice the TF32 rate) into ONE fp32 accumulator give the same
+// fp32-faithful product as 3xTF32 at half the tensor time and half the operand bytes (the weight stream, 512 KB per
+// decode step, is what bounds the FFN: one SM ingests ~27 B/clk through TMA).  The scales keep the lo parts in the
+// normal fp16 range for every value that matters (|a| >= 2^-6, |w| >= 2^-10; smaller ones carry an absolute error
+// <= 2^-25 / S) and are undone exactly in the epilogues.  |S x| >= 65520 (|a| >= 4094, |w| >= 255) overflows fp16
+// and surfaces as non-finite logits (RRNCO_DEV_NAN_LOGITS), never silently.
+//
+// Stream layout: 16 slices in the order the tensor pipe consumes them.  job j = s >> 1 in
+//   G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) G2(3)      (G1(c): W1 rows of hidden chunk c, G2(c): W2 columns of c)
+// so that epilogue 1 of chunk c overlaps GEMM1 of chunk c+1; s & 1 selects 64 k values.  Each slice is one
+// contiguous 32 KB block [B_hi | B_lo][16-byte K chunk (8)][row (128)][8 halves] == the shared-memory core-matrix
+// layout (tc05.cuh), so one cp.async.bulk moves it and UMMA descriptors address its four K steps.  Large slices
+// matter: a bulk copy costs ~250 cycles of fixed overhead plus ~1 cycle per 66 bytes, and the tensor pipe needs a
+// K step (two variants, 8 KB) every ~290 cycles.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace rrnco {
 constexpr int kFRows = 128;
-constexpr int kFSliceK = 16;
-constexpr int kFStages = 4;
-constexpr int kFSlices = 64;
-constexpr int kFSliceFloats = 2 * kFRows * kFSliceK;  // hi | lo
-constexpr uint32_t kFSliceBytes = kFSliceFloats * 4;  // 16 KB
-constexpr uint32_t kLboTile = kFRows * 16;            // bytes between the 16-byte K chunks of a 128-row tile
-constexpr uint32_t kSbo = 128;                        // bytes between 8-row groups
-constexpr int64_t kFfnPackedFloats = (int64_t)kFSlices * kFSliceFloats;  // 1 MB
+constexpr int kFSliceK = 64;                                     // k values per slice
+constexpr int kFKSteps = kFSliceK / 16;                          // kind::f16 MMAs (K = 16) per slice and split term
+constexpr int kFSlicesPerJob = kFRows / kFSliceK;                // a job = one 128 x 128 x 128 GEMM
+constexpr int kFStages = 4;                                      // ring stages (128 KB in flight)
+constexpr int kFSlices = 8 * kFSlicesPerJob;
+constexpr int kFVariantHalves = kFRows * kFSliceK;               // B_hi or B_lo: 16 KB
+constexpr int kFSliceHalves = 2 * kFVariantHalves;
+constexpr uint32_t kFSliceBytes = kFSliceHalves * 2;             // 32 KB
+constexpr uint32_t kLboTile = kFRows * 16;                       // bytes between the 16-byte K chunks of a 128-row tile
+constexpr uint32_t kSbo = 128;                                   // bytes between 8-row groups
+constexpr int64_t kFfnPackedBytes = (int64_t)kFSlices * kFSliceBytes;  // 512 KB
+constexpr float kWScale = 256.0f;                                // weights; |w| < 255 representable
+constexpr float kLkScale = 16.0f;                                // logit keys; |Lk| < 4094 representable
+constexpr float kAScale = 16.0f;                                 // activations; |a| < 4094 representable
 
-// launches the packing kernel on `st` (defined in ffn_tc_kernel.cu)
-int pack_ffn_weights(const float* w1, const float* w2, float* packed, cudaStream_t st);
+// chunk / half of job j (see above)
+__host__ __device__ constexpr int ffn_job_chunk(int j) { return j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 0 : j == 3 ? 2 : j == 4 ? 1 : j == 5 ? 3 : j == 6 ? 2 : 3; }
+__host__ __device__ constexpr int ffn_job_half(int j) { return j == 0 ? 0 : j == 1 ? 0 : j == 2 ? 1 : j == 3 ? 0 : j == 4 ? 1 : j == 5 ? 0 : j == 6 ? 1 : 1; }
+
+#ifdef __CUDACC__
+// hi part as an fp32 value with 11 significant bits (integer round-to-nearest, ties away; same bit trick as f2tf32)
+__device__ __forceinline__ float f16s_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// pair (x0, x1), pre-scaled by `scale` -> packed hi / lo fp16 words (low half = x0)
+__device__ __forceinline__ void f16s_split2(float x0, float x1, float scale, uint32_t& hi, uint32_t& lo) {
+  x0 *= scale;
+  x1 *= scale;
+  const float h0 = f16s_hi(x0), h1 = f16s_hi(x1);
+  const __half2 hh = __floats2half2_rn(h0, h1);
+  const __half2 ll = __floats2half2_rn(x0 - h0, x1 - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+#endif
+
+// launches the packing kernel on `st` (defined in ffn_tc_kernel.cu); `packed` holds kFfnPackedBytes
+int pack_ffn_weights(const float* w1, const float* w2, void* packed, cudaStream_t st);
 }  // namespace rrnco

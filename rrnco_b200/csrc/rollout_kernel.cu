@@ -23,7 +23,7 @@
 namespace rrnco {
 
 constexpr int kThreads = 256;      // compute threads (8 warps)
-constexpr int kThreadsTc = 288;    // + 1 TMA producer warp in the tcgen05 variant
+constexpr int kThreadsTc = 384;    // tcgen05 variant: + warp 8 (TMA producer) + warps 9-11 (MMA issue, one per split term)
 constexpr int kRows = 128;   // rollouts per CTA tile
 constexpr int kLdA = 132;    // fp32 row stride of the activation tiles (bank-conflict-free fragments)
 constexpr int kLdB = 36;     // fp32 row stride of a streamed weight slice (32 k + 4 pad)
@@ -66,7 +66,7 @@ struct RolloutParams {
   int32_t* ws_tile_steps;
   int32_t* max_steps_out;
   uint32_t* status;
-  const float* ffn_packed;  // tcgen05 variant: W1 / W2 packed hi | lo slices (ffn_pack.cuh)
+  const unsigned char* ffn_packed;  // tcgen05 variant: W1 / W2 packed fp16 hi | lo slices (ffn_pack.cuh)
 };
 
 // Transcendentals of the softmax / bias / clip chain on the SFU (ex2 / lg2 / rcp .approx): absolute error
@@ -123,8 +123,13 @@ struct Smem {
   // tcgen05 FFN pipeline
   uint64_t bar_full[kFStages];
   uint64_t bar_empty[kFStages];
-  uint64_t bar_acc;
-  uint64_t bar_go;
+  uint64_t bar_go;      // compute -> producer: the ring memory is free, stream this step's weights (or exit)
+  uint64_t bar_gready;  // compute -> issuers: glimpse tiles (A operand of GEMM1) written (256 arrivals; also the exit signal)
+  uint64_t bar_h[2];    // issuers -> compute: GEMM1 into hidden accumulator b complete
+  uint64_t bar_epi;     // compute -> issuers: epilogue 1 done (A operand of GEMM2 in TMEM, accumulator re-zeroed)
+  uint64_t bar_g2;      // issuers -> compute: GEMM2 of a chunk complete (its A operand may be overwritten)
+  uint64_t bar_lk;      // compute -> issuers: g' (TMEM) and the logit-key tiles written
+  uint64_t bar_acc;     // issuers -> compute: logits complete
   uint32_t tmem_base;
   volatile int exit_flag;
 };
@@ -245,10 +250,16 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     if (tid == 32) {
       for (int i = 0; i < kFStages; ++i) {
         tc05::mbar_init(&sm.bar_full[i], 1);
-        tc05::mbar_init(&sm.bar_empty[i], 2 * kPasses);
+        tc05::mbar_init(&sm.bar_empty[i], kPasses);
       }
-      tc05::mbar_init(&sm.bar_acc, 2 * kPasses);
       tc05::mbar_init(&sm.bar_go, 1);
+      tc05::mbar_init(&sm.bar_gready, kThreads);
+      tc05::mbar_init(&sm.bar_h[0], kPasses);
+      tc05::mbar_init(&sm.bar_h[1], kPasses);
+      tc05::mbar_init(&sm.bar_epi, kThreads);
+      tc05::mbar_init(&sm.bar_g2, kPasses);
+      tc05::mbar_init(&sm.bar_lk, kThreads);
+      tc05::mbar_init(&sm.bar_acc, kPasses);
       tc05::fence_mbar_init();
       sm.exit_flag = 0;
     }
@@ -322,10 +333,12 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     __syncthreads();
     tc05::fence_after_sync();
     if (warp == 8) {
-      // ===== TMA producer warp: each decode step, streams the 64 packed weight slices through the ring =====
+      // ===== TMA producer warp: each decode step, streams the 16 packed 32 KB weight slices through the ring
+      // (Hb | Bs regions, idle between the attention of this step and the K / V prefetch for the next) =====
       if (lane == 0) {
         uint32_t go_phase = 0;
         uint32_t sl = 0;
+        unsigned char* ring = reinterpret_cast<unsigned char*>(sm.Hb);
         while (true) {
           tc05::mbar_wait(&sm.bar_go, go_phase);
           go_phase ^= 1u;
@@ -334,16 +347,83 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             const int st = sl & (kFStages - 1);
             if (sl >= kFStages) tc05::mbar_wait(&sm.bar_empty[st], ((sl / kFStages) - 1) & 1);
             tc05::mbar_arrive_expect_tx(&sm.bar_full[st], kFSliceBytes);
-            tc05::bulk_g2s(sm.Bs + st * kFSliceFloats, p.ffn_packed + (size_t)s * kFSliceFloats, kFSliceBytes,
+            tc05::bulk_g2s(ring + (size_t)st * kFSliceBytes, p.ffn_packed + (size_t)s * kFSliceBytes, kFSliceBytes,
                            &sm.bar_full[st]);
           }
         }
       }
       return;
     }
+    if (warp >= 9) {
+      // ===== MMA issue warps: warp 9 + term issues one term of the two-term fp16 split (ffn_pack.cuh) for every K step
+      // (0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo; single-pass mode: term 0 only).  A single thread sustains only ~1
+      // tcgen05.mma per 160 cycles, the tensor pipe retires one per ~97.  All terms accumulate into the same pre-zeroed
+      // TMEM tile, so no issue order between the warps is needed.  Tensor-pipe order per decode step:
+      //   G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) G2(3) logits
+      // GEMM1 alternates between two accumulators, so epilogue 1 of chunk c runs under GEMM1 of chunk c + 1. =====
+      const int term = warp - 9;
+      if (lane == 0 && term < kPasses) {
+        const uint32_t tb = sm.tmem_base;
+        const uint32_t t_hacc0 = tb, t_oacc = tb + 256, t_a = tb + (term == 1 ? 448 : 384);
+        const uint32_t idesc = tc05::make_idesc_f16(128, 128);
+        const uint32_t a_addr = tc05::smem_u32(sm.A) + (term == 1 ? kRows * kE * 2 : 0);  // G_hi | G_lo
+        const uint32_t ring_addr = tc05::smem_u32(sm.Hb);
+        const uint32_t b_var = term == 2 ? kFVariantHalves * 2 : 0;
+        const int R16i = ((N + 15) >> 4) << 4;
+        const uint32_t idesc_l = tc05::make_idesc_f16(128, R16i);
+        const uint32_t lbo_l = (uint32_t)R16i * 16u;
+        const uint32_t lk_addr = ring_addr + (term == 2 ? (uint32_t)R16i * kE * 2 : 0);  // Lk_hi | Lk_lo
+        uint32_t step_par = 0, epi_phase = 0, sl = 0;
+        while (true) {
+          tc05::mbar_wait(&sm.bar_gready, step_par);
+          if (sm.exit_flag) break;
+          tc05::fence_after_sync();
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j) {
+            const int c = ffn_job_chunk(j), half = ffn_job_half(j);
+            if (half == 1) {  // A operand of GEMM2(c) written (and, one job later, accumulator c & 1 re-zeroed)
+              tc05::mbar_wait(&sm.bar_epi, epi_phase);
+              epi_phase ^= 1u;
+              tc05::fence_after_sync();
+            }
+#pragma unroll 1
+            for (int sj = 0; sj < kFSlicesPerJob; ++sj, ++sl) {
+              const int st = sl & (kFStages - 1);
+              tc05::mbar_wait(&sm.bar_full[st], (sl / kFStages) & 1);
+              tc05::fence_after_sync();
+              const uint32_t b_addr = ring_addr + st * kFSliceBytes + b_var;
+#pragma unroll
+              for (int kk = 0; kk < kFKSteps; ++kk) {
+                const int ks = sj * kFKSteps + kk;  // K step (16 values) of the job
+                const uint64_t bdesc = tc05::make_desc(b_addr + kk * 2 * kLboTile, kLboTile, kSbo);
+                if (half == 0) {
+                  const uint64_t adesc = tc05::make_desc(a_addr + ks * 2 * kLboTile, kLboTile, kSbo);
+                  tc05::mma_ss_f16(t_hacc0 + (c & 1) * 128, adesc, bdesc, idesc, 1u);
+                } else {
+                  tc05::mma_ts_f16(t_oacc, t_a + ks * 8, bdesc, idesc, 1u);
+                }
+              }
+              tc05::commit(&sm.bar_empty[st]);
+            }
+            tc05::commit(half == 0 ? &sm.bar_h[c & 1] : &sm.bar_g2);
+          }
+          // pointer logits: D[128 x R16] = g'(hi | lo, TMEM) . Lk(hi | lo, shared memory)^T, 8 K steps
+          tc05::mbar_wait(&sm.bar_lk, step_par);
+          tc05::fence_after_sync();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t bdesc = tc05::make_desc(lk_addr + ks * 2 * lbo_l, lbo_l, kSbo);
+            tc05::mma_ts_f16(t_hacc0, t_a + ks * 8, bdesc, idesc_l, 1u);
+          }
+          tc05::commit(&sm.bar_acc);
+          step_par ^= 1u;
+        }
+      }
+      return;
+    }
   }
-  uint32_t tc_sl = 0, tc_acc_phase = 0;  // running slice counter / accumulator-barrier phase of the MMA warps
-  if (kTc) {  // every MMA accumulates: zero the hidden-chunk and output accumulators once
+  uint32_t tc_step_par = 0;  // parity of the once-per-step barriers (bar_acc)
+  if (kTc) {  // every MMA accumulates: zero the two hidden-chunk accumulators and the output accumulator once
     uint32_t z[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) z[i] = 0u;
@@ -351,7 +431,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       tc05::tmem_st16(sm.tmem_base + lb + (warp >> 2) * 64 + q * 16, z);
-      tc05::tmem_st16(sm.tmem_base + 384 + lb + (warp >> 2) * 64 + q * 16, z);
+      tc05::tmem_st16(sm.tmem_base + 128 + lb + (warp >> 2) * 64 + q * 16, z);
+      tc05::tmem_st16(sm.tmem_base + 256 + lb + (warp >> 2) * 64 + q * 16, z);
     }
     tc05::tmem_wait_st();
     tc05::fence_before_sync();
@@ -611,184 +692,147 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     // ---- E: FFN  g' = W2 relu(W1 g + b1) + b2 + g ---------------------------------------------
     int sl = 0;
     if (kTc) {
-      // tcgen05 path (see ffn_tc_kernel.cu for the standalone form): glimpse -> hi | lo K-major core-matrix
-      // tiles in shared memory (A region | Hb region), weights streamed by the TMA producer warp through the
-      // Bs region, accumulators and the hidden activations (A operand of GEMM2) in tensor memory.
-      if (tid == 0) tc05::mbar_arrive(&sm.bar_go);  // the ring (Bs) is free: producer starts this step's stream
-      float4 gres[16];
+      // tcgen05 path (see ffn_tc_kernel.cu for the standalone form): glimpse -> fp16 hi | lo K-major core-matrix
+      // tiles in the A region, weights streamed by the TMA producer warp through the Hb | Bs regions, accumulators and
+      // the hidden activations (A operand of GEMM2) in tensor memory, MMAs issued by warps 9-11.  The compute warps
+      // only run the epilogues.
+      if (tid == 0) tc05::mbar_arrive(&sm.bar_go);  // K / V tiles are dead: the producer starts this step's stream
+      uint16_t* g_hi = reinterpret_cast<uint16_t*>(sm.A);  // [16-byte K chunk (16)][row (128)][8 halves]
+      uint16_t* g_lo = g_hi + kRows * kE;
+      {
+        float4 gres[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int idx = tid + i * kThreads, c4 = idx >> 7, row = idx & 127;
-        gres[i] = *reinterpret_cast<const float4*>(&sm.A[row * kLdA + c4 * 4]);
-      }
-      cta_sync<kTc>();  // every thread holds its part of the glimpse: A / Hb may now be re-laid out
+        for (int i = 0; i < 8; ++i) {
+          const int idx = tid + i * kThreads, row = idx & 127, c8 = idx >> 7;
+          gres[2 * i] = *reinterpret_cast<const float4*>(&sm.A[row * kLdA + c8 * 8]);
+          gres[2 * i + 1] = *reinterpret_cast<const float4*>(&sm.A[row * kLdA + c8 * 8 + 4]);
+        }
+        cta_sync<kTc>();  // every thread holds its part of the glimpse: the A region may now be re-laid out
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int idx = tid + i * kThreads, c4 = idx >> 7, row = idx & 127;
-        uint32_t h[4], l[4];
-        split_tf32(gres[i].x, h[0], l[0]); split_tf32(gres[i].y, h[1], l[1]);
-        split_tf32(gres[i].z, h[2], l[2]); split_tf32(gres[i].w, h[3], l[3]);
-        const int dst = c4 * (kFRows * 4) + row * 4;
-        *reinterpret_cast<uint4*>(&sm.A[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(&sm.Hb[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int i = 0; i < 8; ++i) {
+          const int idx = tid + i * kThreads, row = idx & 127, c8 = idx >> 7;
+          const float4 v0 = gres[2 * i], v1 = gres[2 * i + 1];
+          uint32_t h[4], l[4];
+          f16s_split2(v0.x, v0.y, kAScale, h[0], l[0]); f16s_split2(v0.z, v0.w, kAScale, h[1], l[1]);
+          f16s_split2(v1.x, v1.y, kAScale, h[2], l[2]); f16s_split2(v1.z, v1.w, kAScale, h[3], l[3]);
+          const int dst = c8 * (kRows * 8) + row * 8;
+          *reinterpret_cast<uint4*>(&g_hi[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(&g_lo[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
       }
       tc05::fence_proxy_async();
       tc05::fence_before_sync();
-      cta_sync<kTc>();
-      tc05::fence_after_sync();
+      tc05::mbar_arrive(&sm.bar_gready);
+      cta_sync<kTc>();  // the output epilogue below reads residual values other threads wrote
       PHASE_STAMP(2);
       // logit keys of this instance -> registers now (L2 latency hidden behind the FFN); they are split into the
-      // hi | lo core-matrix tiles of the logits GEMM once the FFN has released the shared memory.
+      // fp16 hi | lo core-matrix tiles of the logits GEMM once the FFN has released the ring memory.
       const int R16 = ((N + 15) >> 4) << 4;  // rows of the logit-key tile = N of the logits MMA (multiple of 16)
-      float4 lkr[kNTMax + 1];
+      float4 lkr[16];
 #pragma unroll
-      for (int i = 0; i < kNTMax + 1; ++i) {
-        const int item = tid + i * kThreads, rest = item >> 5;
-        const int c4 = (rest & 7) * 4 + ((item >> 3) & 3), row = (rest >> 3) * 8 + (item & 7);
-        lkr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < N) lkr[i] = __ldg(reinterpret_cast<const float4*>(Lk + (size_t)row * kE) + c4);
+      for (int i = 0; i < 8; ++i) {
+        const int idx = tid + i * kThreads, row = idx & 127, c8 = idx >> 7;
+        lkr[2 * i] = lkr[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < N) {
+          lkr[2 * i] = __ldg(reinterpret_cast<const float4*>(Lk + (size_t)row * kE) + c8 * 2);
+          lkr[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(Lk + (size_t)row * kE) + c8 * 2 + 1);
+        }
       }
 
       const uint32_t tbase = sm.tmem_base;
-      const uint32_t t_hacc = tbase, t_ahi = tbase + 128, t_alo = tbase + 256, t_oacc = tbase + 384;
+      const uint32_t t_hacc = tbase, t_oacc = tbase + 256, t_hhi = tbase + 384, t_hlo = tbase + 448;
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       const int colhalf = warp >> 2;
-      const uint32_t idesc = tc05::make_idesc_tf32(128, 128);
-      const uint32_t g_hi_addr = tc05::smem_u32(sm.A), g_lo_addr = tc05::smem_u32(sm.Hb);
+      constexpr float kUnscaleW = 1.0f / (kAScale * kWScale), kUnscaleL = 1.0f / (kAScale * kLkScale);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          if (warp < 2 * kPasses) {
-            // MMA issue: one thread sustains only ~1 tcgen05.mma per 160 cycles while the tensor pipe wants one per
-            // 64, so 2 x kPasses warps issue: warp w -> K step (w & 1) of every slice, pass w >> 1
-            // (3xTF32: 0 = lo*hi, 1 = hi*lo, 2 = hi*hi; 1xTF32: hi*hi).  All of them accumulate into the same
-            // pre-zeroed TMEM tile, so no issue order between the warps is needed.
-            const int pass = warp >> 1, kk = warp & 1;
-            const bool a_lo = kPasses == 3 && pass == 0, b_lo = kPasses == 3 && pass == 1;
-#pragma unroll 1
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint32_t sg = tc_sl + ks;
-              const int st = sg & (kFStages - 1);
-              tc05::mbar_wait(&sm.bar_full[st], (sg / kFStages) & 1);
-              tc05::fence_after_sync();
-              if (lane == 0) {
-                const uint32_t whi = tc05::smem_u32(sm.Bs + st * kFSliceFloats), wlo = whi + kFRows * kFSliceK * 4;
-                const uint64_t bdesc = tc05::make_desc((b_lo ? wlo : whi) + kk * 2 * kLboTile, kLboTile, kSbo);
-                if (half == 0) {
-                  const uint32_t koff = (ks * 4 + kk * 2) * kLboTile;
-                  const uint64_t adesc = tc05::make_desc((a_lo ? g_lo_addr : g_hi_addr) + koff, kLboTile, kSbo);
-                  tc05::mma_ss(t_hacc, adesc, bdesc, idesc, 1u);
-                } else {
-                  const uint32_t kcol = ks * kFSliceK + kk * 8;
-                  tc05::mma_ts(t_oacc, (a_lo ? t_alo : t_ahi) + kcol, bdesc, idesc, 1u);
-                }
-                tc05::commit(&sm.bar_empty[st]);
-                if (ks == 7) tc05::commit(&sm.bar_acc);
-              }
-              __syncwarp();
-            }
+        // hidden chunk c: + b1, relu, split -> A operand (hi | lo, fp16) of GEMM2 in tensor memory
+        tc05::mbar_wait(&sm.bar_h[c & 1], (c >> 1) & 1, 32);
+        if (c > 0) tc05::mbar_wait(&sm.bar_g2, (c - 1) & 1, 32);  // GEMM2(c - 1) has consumed the previous A operand
+        tc05::fence_after_sync();
+        const uint32_t t_h = t_hacc + (c & 1) * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col0 = colhalf * 64 + q * 16;
+          uint32_t v[16], hi[8], lo[8];
+          tc05::tmem_ld16(t_h + lane_base + col0, v);
+          tc05::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float h0 = fmaxf(fmaf(__uint_as_float(v[i]), kUnscaleW, sm.b1[c * kFRows + col0 + i]), 0.f);
+            const float h1 = fmaxf(fmaf(__uint_as_float(v[i + 1]), kUnscaleW, sm.b1[c * kFRows + col0 + i + 1]), 0.f);
+            f16s_split2(h0, h1, kAScale, hi[i >> 1], lo[i >> 1]);
           }
-          tc_sl += 8;
-          tc05::mbar_wait(&sm.bar_acc, tc_acc_phase, 64);
-          tc_acc_phase ^= 1u;
-          tc05::fence_after_sync();
-          if (half == 0) {  // hidden chunk: + b1, relu, split -> A operand (hi | lo) of GEMM2 in tensor memory
+          tc05::tmem_st8(t_hhi + lane_base + (col0 >> 1), hi);
+          tc05::tmem_st8(t_hlo + lane_base + (col0 >> 1), lo);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int col0 = colhalf * 64 + q * 16;
-              uint32_t v[16], hi[16], lo[16];
-              tc05::tmem_ld16(t_hacc + lane_base + col0, v);
-              tc05::tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float hv = fmaxf(__uint_as_float(v[i]) + sm.b1[c * kFRows + col0 + i], 0.f);
-                split_tf32(hv, hi[i], lo[i]);
-              }
-              tc05::tmem_st16(t_ahi + lane_base + col0, hi);
-              tc05::tmem_st16(t_alo + lane_base + col0, lo);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = 0u;
-              tc05::tmem_st16(t_hacc + lane_base + col0, v);  // re-zero the chunk accumulator for the next GEMM1
-            }
-            tc05::tmem_wait_st();
-            tc05::fence_before_sync();
-            cta_sync<kTc>();
-          }
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+          tc05::tmem_st16(t_h + lane_base + col0, v);  // re-zero the chunk accumulator for GEMM1(c + 2) / the logits
         }
+        tc05::tmem_wait_st();
+        tc05::fence_before_sync();
+        tc05::mbar_arrive(&sm.bar_epi);
       }
+      tc05::mbar_wait(&sm.bar_g2, 1, 32);  // GEMM2(3): FFN output complete, ring memory idle
+      tc05::fence_after_sync();
       PHASE_STAMP(3);
       // ---- output epilogue (thread per row): g' = acc + b2 + g  ->  split -> TMEM as the A operand of the logits GEMM
-      const uint32_t lkhi_addr = tc05::smem_u32(sm.Bs), lklo_addr = tc05::smem_u32(sm.Hb);
       {
         const int row = (warp & 3) * 32 + lane;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int col0 = colhalf * 64 + q * 16;
-          uint32_t v[16], hi[16], lo[16];
+          uint32_t v[16], hi[8], lo[8];
           tc05::tmem_ld16(t_oacc + lane_base + col0, v);
           tc05::tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const int off = ((col0 + i) >> 2) * (kFRows * 4) + row * 4;  // residual g = hi + lo (exact to 2^-22)
-            const float4 gh = *reinterpret_cast<const float4*>(&sm.A[off]);
-            const float4 gl = *reinterpret_cast<const float4*>(&sm.Hb[off]);
-            split_tf32(__uint_as_float(v[i]) + sm.b2[col0 + i] + (gh.x + gl.x), hi[i], lo[i]);
-            split_tf32(__uint_as_float(v[i + 1]) + sm.b2[col0 + i + 1] + (gh.y + gl.y), hi[i + 1], lo[i + 1]);
-            split_tf32(__uint_as_float(v[i + 2]) + sm.b2[col0 + i + 2] + (gh.z + gl.z), hi[i + 2], lo[i + 2]);
-            split_tf32(__uint_as_float(v[i + 3]) + sm.b2[col0 + i + 3] + (gh.w + gl.w), hi[i + 3], lo[i + 3]);
+          for (int i = 0; i < 16; i += 8) {
+            const int off = ((col0 + i) >> 3) * (kRows * 8) + row * 8;  // residual g = (hi + lo) / kAScale, exact to 2^-24
+            const uint4 gh = *reinterpret_cast<const uint4*>(&g_hi[off]);
+            const uint4 gl = *reinterpret_cast<const uint4*>(&g_lo[off]);
+            const uint32_t ghw[4] = {gh.x, gh.y, gh.z, gh.w}, glw[4] = {gl.x, gl.y, gl.z, gl.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&ghw[e]));
+              const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&glw[e]));
+              const float o0 = fmaf(__uint_as_float(v[i + 2 * e]), kUnscaleW, sm.b2[col0 + i + 2 * e]) +
+                               (fh.x + fl.x) * (1.0f / kAScale);
+              const float o1 = fmaf(__uint_as_float(v[i + 2 * e + 1]), kUnscaleW, sm.b2[col0 + i + 2 * e + 1]) +
+                               (fh.y + fl.y) * (1.0f / kAScale);
+              f16s_split2(o0, o1, kAScale, hi[(i >> 1) + e], lo[(i >> 1) + e]);
+            }
           }
-          tc05::tmem_st16(t_ahi + lane_base + col0, hi);
-          tc05::tmem_st16(t_alo + lane_base + col0, lo);
+          tc05::tmem_st8(t_hhi + lane_base + (col0 >> 1), hi);
+          tc05::tmem_st8(t_hlo + lane_base + (col0 >> 1), lo);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0u;
           tc05::tmem_st16(t_oacc + lane_base + col0, v);  // re-zero the output accumulator for the next decode step
         }
-        tc05::tmem_wait_st();
       }
-      // logit keys -> hi tile in the (now idle) weight ring; the lo tile overwrites g_lo after the barrier
+      // logit keys -> fp16 hi | lo tiles [16-byte K chunk (16)][row (R16)][8 halves] at the start of the idle ring
+      {
+        uint16_t* lk_hi = reinterpret_cast<uint16_t*>(sm.Hb);
+        uint16_t* lk_lo = lk_hi + R16 * kE;
 #pragma unroll
-      for (int i = 0; i < kNTMax + 1; ++i) {
-        const int item = tid + i * kThreads, rest = item >> 5;
-        const int c4 = (rest & 7) * 4 + ((item >> 3) & 3), row = (rest >> 3) * 8 + (item & 7);
-        if (row < R16) {
-          uint32_t h[4], l[4];
-          split_tf32(lkr[i].x, h[0], l[0]); split_tf32(lkr[i].y, h[1], l[1]);
-          split_tf32(lkr[i].z, h[2], l[2]); split_tf32(lkr[i].w, h[3], l[3]);
-          *reinterpret_cast<uint4*>(&sm.Bs[c4 * (R16 * 4) + row * 4]) = make_uint4(h[0], h[1], h[2], h[3]);
-          lkr[i] = make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+        for (int i = 0; i < 8; ++i) {
+          const int idx = tid + i * kThreads, row = idx & 127, c8 = idx >> 7;
+          if (row < R16) {
+            const float4 v0 = lkr[2 * i], v1 = lkr[2 * i + 1];
+            uint32_t h[4], l[4];
+            f16s_split2(v0.x, v0.y, kLkScale, h[0], l[0]); f16s_split2(v0.z, v0.w, kLkScale, h[1], l[1]);
+            f16s_split2(v1.x, v1.y, kLkScale, h[2], l[2]); f16s_split2(v1.z, v1.w, kLkScale, h[3], l[3]);
+            const int dst = c8 * (R16 * 8) + row * 8;
+            *reinterpret_cast<uint4*>(&lk_hi[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(&lk_lo[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
       }
-      tc05::fence_before_sync();
-      cta_sync<kTc>();  // every thread has read its residual from g_hi / g_lo
-#pragma unroll
-      for (int i = 0; i < kNTMax + 1; ++i) {
-        const int item = tid + i * kThreads, rest = item >> 5;
-        const int c4 = (rest & 7) * 4 + ((item >> 3) & 3), row = (rest >> 3) * 8 + (item & 7);
-        if (row < R16) *reinterpret_cast<float4*>(&sm.Hb[c4 * (R16 * 4) + row * 4]) = lkr[i];
-      }
+      tc05::tmem_wait_st();
       tc05::fence_proxy_async();
       tc05::fence_before_sync();
-      cta_sync<kTc>();
-      tc05::fence_after_sync();
+      tc05::mbar_arrive(&sm.bar_lk);
       PHASE_STAMP(4);
 
-      // ---- G: pointer logits on tcgen05: D[128 x R16] = g'(hi|lo, TMEM) . Lk(hi|lo, smem)^T, 16 K steps ----
-      if (warp < 2 * kPasses) {
-        const int pass = warp >> 1, kpar = warp & 1;
-        const bool a_lo = kPasses == 3 && pass == 0, b_lo = kPasses == 3 && pass == 1;
-        if (lane == 0) {
-          const uint32_t idesc_l = tc05::make_idesc_tf32(128, R16);
-          const uint32_t lbo_l = (uint32_t)R16 * 16u;
-#pragma unroll 4
-          for (int ks = kpar; ks < 16; ks += 2) {
-            const uint64_t bdesc = tc05::make_desc((b_lo ? lklo_addr : lkhi_addr) + ks * 2 * lbo_l, lbo_l, kSbo);
-            tc05::mma_ts(t_hacc, (a_lo ? t_alo : t_ahi) + ks * 8, bdesc, idesc_l, 1u);
-          }
-          tc05::commit(&sm.bar_acc);
-        }
-        __syncwarp();
-      }
       // bias rows of this rollout (alpha . D[cur,:] + beta . Dur[cur,:]) -> registers while the logits MMAs run.
       // Column groups of 16 are dealt round-robin to the two threads of a row (balanced for N not a multiple of 32).
       float lv[64];
@@ -809,8 +853,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           }
         }
       }
-      tc05::mbar_wait(&sm.bar_acc, tc_acc_phase, 64);
-      tc_acc_phase ^= 1u;
+      tc05::mbar_wait(&sm.bar_acc, tc_step_par, 32);
+      tc_step_par ^= 1u;
       tc05::fence_after_sync();
       // K / V of the next decode step: both tiles' memory is idle from here to the next attention phase
       for (int idx = tid; idx < NPAD * 32; idx += kThreads) {
@@ -832,7 +876,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         const int64_t rg = (int64_t)(tile * kRows + (sm.active[row] ? row : 0)) * p.n_inst + b;
         uint32_t mrow[4];
         *reinterpret_cast<uint4*>(mrow) = *reinterpret_cast<const uint4*>(sm.mask[row]);
-        const float inv_sqrt_e = 0.08838834764831845f;
+        const float inv_sqrt_e = 0.08838834764831845f * kUnscaleL;  // 1 / sqrt(128), and the operand scales undone
         const float clip = p.w.tanh_clipping;
         const int hsh = 16 * colhalf;  // this thread's columns: 32 q + hsh + i
         float mxl = -INFINITY;
@@ -852,7 +896,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float l = __uint_as_float(v[i]) * inv_sqrt_e;
-            nan_seen |= l != l;
+            nan_seen |= !(fabsf(l) <= 3.0e38f);  // NaN, or an fp16 operand overflow (ffn_pack.cuh)
             l = flog(__fadd_rn(fexp(__fsub_rn(l, lv[q * 16 + i])), 1e-6f));  // decoder.py:198
             if (clip > 0.f) l = __fmul_rn(ftanh(l), clip);
             l = ((mq >> i) & 1u) ? l : -INFINITY;
@@ -1279,6 +1323,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     }
     tc05::fence_before_sync();
     cta_sync<kTc>();
+    tc05::mbar_arrive(&sm.bar_gready);  // releases the MMA-issue warps (they see exit_flag)
     if (warp == 0) tc05::tmem_dealloc(sm.tmem_base, 512);
   }
 }
@@ -1425,7 +1470,7 @@ int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_in
   const int64_t R = n_inst * n_starts;
   const int64_t tiles = n_inst * ((n_starts + kRows - 1) / kRows);
   return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL) +
-         kFfnPackedFloats * (int64_t)sizeof(float);
+         kFfnPackedBytes;
 }
 
 int rrnco_decoder_logits(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts,
@@ -1479,7 +1524,7 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
   p.ws_lp = p.ws_len + R;
   p.ws_tile_steps = reinterpret_cast<int32_t*>(p.ws_lp + R);
   const int64_t tiles = n_inst * p.n_tiles;
-  float* packed = reinterpret_cast<float*>(reinterpret_cast<char*>(p.ws_tile_steps) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL));
+  unsigned char* packed = reinterpret_cast<unsigned char*>(p.ws_tile_steps) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL);
   p.ffn_packed = packed;
   p.max_steps_out = max_steps_out; p.status = status;
   if (cudaMemsetAsync(max_steps_out, 0, sizeof(int32_t), st) != cudaSuccess) return RRNCO_ERR_CUDA;
