@@ -40,6 +40,9 @@ constexpr int64_t kFfnPackedBytes = (int64_t)kFSlices * kFSliceBytes;  // 512 KB
 constexpr float kWScale = 256.0f;                                // weights; |w| < 255 representable
 constexpr float kLkScale = 16.0f;                                // logit keys; |Lk| < 4094 representable
 constexpr float kAScale = 16.0f;                                 // activations; |a| < 4094 representable
+constexpr float kKvScale = 16.0f;                                // attention keys / values; |x| < 4094 representable
+constexpr uint32_t kKvSlotBytes = 131072;                        // packed K | V tiles of one instance (per-SM workspace slot)
+constexpr int kKvSlots = 256;                                    // >= %nsmid
 
 // chunk / half of job j (see above)
 __host__ __device__ constexpr int ffn_job_chunk(int j) { return j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 0 : j == 3 ? 2 : j == 4 ? 1 : j == 5 ? 3 : j == 6 ? 2 : 3; }

@@ -67,6 +67,7 @@ struct RolloutParams {
   int32_t* max_steps_out;
   uint32_t* status;
   const unsigned char* ffn_packed;  // tcgen05 variant: W1 / W2 packed fp16 hi | lo slices (ffn_pack.cuh)
+  unsigned char* kv_pack;           // tcgen05 variant: kKvSlots per-SM slots of packed fp16 K | V tiles (kKvSlotBytes each)
 };
 
 // Transcendentals of the softmax / bias / clip chain on the SFU (ex2 / lg2 / rcp .approx): absolute error
@@ -120,11 +121,18 @@ struct Smem {
   float xf[3][2][kRows];
   int xi[2][kRows];
   float xchosen[kRows];
+  float xsum[kH][kRows];  // tcgen05 attention: softmax denominators (written and read by the same thread)
   // tcgen05 FFN pipeline
   uint64_t bar_full[kFStages];
   uint64_t bar_empty[kFStages];
-  uint64_t bar_go;      // compute -> producer: the ring memory is free, stream this step's weights (or exit)
-  uint64_t bar_gready;  // compute -> issuers: glimpse tiles (A operand of GEMM1) written (256 arrivals; also the exit signal)
+  uint64_t bar_go;      // compute -> producer: K / V tiles are dead, stream this step's weights (256 arrivals; or exit)
+  uint64_t bar_kvgo;    // compute -> producer: the ring memory is free, load the packed K / V tiles of the next step
+  uint64_t bar_kv;      // TMA -> issuers: packed K / V tiles landed
+  uint64_t bar_q;       // compute -> issuers: query tiles written (256 arrivals; also the exit signal)
+  uint64_t bar_s[kH];   // issuers -> compute: scores of head h in TMEM
+  uint64_t bar_p[kH];   // compute -> issuers: probabilities of head h written in place (128 arrivals)
+  uint64_t bar_o[kH];   // issuers -> compute: P V of head h complete
+  uint64_t bar_gready;  // compute -> issuers: glimpse tiles (A operand of GEMM1) written (256 arrivals)
   uint64_t bar_h[2];    // issuers -> compute: GEMM1 into hidden accumulator b complete
   uint64_t bar_epi;     // compute -> issuers: epilogue 1 done (A operand of GEMM2 in TMEM, accumulator re-zeroed)
   uint64_t bar_g2;      // issuers -> compute: GEMM2 of a chunk complete (its A operand may be overwritten)
@@ -252,7 +260,15 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         tc05::mbar_init(&sm.bar_full[i], 1);
         tc05::mbar_init(&sm.bar_empty[i], kPasses);
       }
-      tc05::mbar_init(&sm.bar_go, 1);
+      tc05::mbar_init(&sm.bar_go, kThreads);
+      tc05::mbar_init(&sm.bar_kvgo, 1);
+      tc05::mbar_init(&sm.bar_kv, 1);
+      tc05::mbar_init(&sm.bar_q, kThreads);
+      for (int i = 0; i < kH; ++i) {
+        tc05::mbar_init(&sm.bar_s[i], 1);
+        tc05::mbar_init(&sm.bar_p[i], kThreads / 2);
+        tc05::mbar_init(&sm.bar_o[i], kPasses);
+      }
       tc05::mbar_init(&sm.bar_gready, kThreads);
       tc05::mbar_init(&sm.bar_h[0], kPasses);
       tc05::mbar_init(&sm.bar_h[1], kPasses);
@@ -329,23 +345,74 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
   __syncthreads();
 
   if (kTc) {
+    // ---- one-time: K / V of this instance -> fp16 hi | lo tiles in the shared-memory layouts of the attention MMAs,
+    // parked in this SM's workspace slot (L2-resident; exactly one CTA lives on an SM at a time) and re-loaded by TMA
+    // every decode step, because the FFN weight ring needs the same shared memory in between.
+    //   K: [hi | lo][16-byte K chunk c8 (16)][key (R16)][8 halves]            B operand of Q K^T, head h = chunks 2h, 2h+1
+    //   V: [hi | lo][head (8)][key chunk (R16 / 8)][dim (16)][8 halves]       B operand (V_h^T, K-major) of P V
+    const int R16p = ((N + 15) >> 4) << 4;
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid >= (uint32_t)kKvSlots) __trap();
+    unsigned char* slot = p.kv_pack + (size_t)smid * kKvSlotBytes;
+    if (tid < kThreads) {
+      uint4* k_hi = reinterpret_cast<uint4*>(slot);
+      uint4* v_hi = reinterpret_cast<uint4*>(slot + kKvSlotBytes / 2);
+      const int var16 = R16p * 16;  // uint4 elements per variant
+      for (int idx = tid; idx < R16p * 16; idx += kThreads) {
+        const int r = idx >> 4, c8 = idx & 15;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (r < N) {
+          v0 = __ldg(reinterpret_cast<const float4*>(Kc + (size_t)r * kE) + c8 * 2);
+          v1 = __ldg(reinterpret_cast<const float4*>(Kc + (size_t)r * kE) + c8 * 2 + 1);
+        }
+        uint32_t h[4], l[4];
+        f16s_split2(v0.x, v0.y, kKvScale, h[0], l[0]); f16s_split2(v0.z, v0.w, kKvScale, h[1], l[1]);
+        f16s_split2(v1.x, v1.y, kKvScale, h[2], l[2]); f16s_split2(v1.z, v1.w, kKvScale, h[3], l[3]);
+        k_hi[c8 * R16p + r] = make_uint4(h[0], h[1], h[2], h[3]);
+        k_hi[var16 + c8 * R16p + r] = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      const int nkc = R16p >> 3;
+      for (int idx = tid; idx < R16p * 16; idx += kThreads) {
+        const int d = idx & 15, kc = (idx >> 4) % nkc, hh = (idx >> 4) / nkc;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int key = kc * 8 + j;
+          x[j] = key < N ? __ldg(Vc + (size_t)key * kE + hh * kDh + d) : 0.f;
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f16s_split2(x[2 * j], x[2 * j + 1], kKvScale, h[j], l[j]);
+        v_hi[(hh * nkc + kc) * 16 + d] = make_uint4(h[0], h[1], h[2], h[3]);
+        v_hi[var16 + (hh * nkc + kc) * 16 + d] = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      tc05::fence_proxy_async_all();
+    }
     tc05::fence_before_sync();
     __syncthreads();
     tc05::fence_after_sync();
+    if (tid == 0) tc05::mbar_arrive(&sm.bar_kvgo);
     if (warp == 8) {
-      // ===== TMA producer warp: each decode step, streams the 16 packed 32 KB weight slices through the ring
-      // (Hb | Bs regions, idle between the attention of this step and the K / V prefetch for the next) =====
+      // ===== TMA producer warp.  Per decode step: the packed K / V tiles (as soon as the previous step's logits have
+      // released the Hb | Bs regions), then -- once the attention is done with them -- the 16 packed 32 KB FFN weight
+      // slices through the same memory used as a 4-stage ring =====
       if (lane == 0) {
         uint32_t go_phase = 0;
         uint32_t sl = 0;
         unsigned char* ring = reinterpret_cast<unsigned char*>(sm.Hb);
+        const uint32_t kv_bytes = (uint32_t)R16p * 512u;  // hi | lo tiles of K (same for V)
         while (true) {
-          tc05::mbar_wait(&sm.bar_go, go_phase);
+          tc05::mbar_wait(&sm.bar_kvgo, go_phase, 64);
+          tc05::mbar_arrive_expect_tx(&sm.bar_kv, 2 * kv_bytes);
+          tc05::bulk_g2s(ring, slot, kv_bytes, &sm.bar_kv);
+          tc05::bulk_g2s(ring + kKvSlotBytes / 2, slot + kKvSlotBytes / 2, kv_bytes, &sm.bar_kv);
+          tc05::mbar_wait(&sm.bar_go, go_phase, 64);
           go_phase ^= 1u;
           if (sm.exit_flag) break;
           for (int s = 0; s < kFSlices; ++s, ++sl) {
             const int st = sl & (kFStages - 1);
-            if (sl >= kFStages) tc05::mbar_wait(&sm.bar_empty[st], ((sl / kFStages) - 1) & 1);
+            if (sl >= kFStages) tc05::mbar_wait(&sm.bar_empty[st], ((sl / kFStages) - 1) & 1, 64);
             tc05::mbar_arrive_expect_tx(&sm.bar_full[st], kFSliceBytes);
             tc05::bulk_g2s(ring + (size_t)st * kFSliceBytes, p.ffn_packed + (size_t)s * kFSliceBytes, kFSliceBytes,
                            &sm.bar_full[st]);
@@ -355,41 +422,77 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       return;
     }
     if (warp >= 9) {
-      // ===== MMA issue warps: warp 9 + term issues one term of the two-term fp16 split (ffn_pack.cuh) for every K step
-      // (0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo; single-pass mode: term 0 only).  A single thread sustains only ~1
-      // tcgen05.mma per 160 cycles, the tensor pipe retires one per ~97.  All terms accumulate into the same pre-zeroed
-      // TMEM tile, so no issue order between the warps is needed.  Tensor-pipe order per decode step:
-      //   G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) G2(3) logits
-      // GEMM1 alternates between two accumulators, so epilogue 1 of chunk c runs under GEMM1 of chunk c + 1. =====
+      // ===== MMA issue warps 9-11.  A single thread sustains only ~1 tcgen05.mma per 122 cycles whatever its size
+      // (several lanes of one warp overlap to ~1 per 67), so the issue work is spread:
+      //  attention: warp 9 + i owns score buffer i and the heads at sequence positions k = i, i + 3, i + 6 (sequence
+      //    0 4 1 5 2 6 3 7: the two compute-warp groups take alternate positions).  Q K^T: three ordered MMAs from lane 0
+      //    (the first overwrites); P V: R16 / 16 K steps per split term, one lane per term, into the pre-zeroed O tile.
+      //  FFN / logits: warp 9 + term issues one term of the two-term fp16 split (ffn_pack.cuh) for every K step
+      //    (0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo; single-pass mode: term 0 only), all into pre-zeroed TMEM tiles.
+      //    Tensor-pipe order  G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) G2(3) logits: GEMM1 alternates between two
+      //    accumulators, so epilogue 1 of chunk c runs under GEMM1 of chunk c + 1. =====
       const int term = warp - 9;
-      if (lane == 0 && term < kPasses) {
-        const uint32_t tb = sm.tmem_base;
-        const uint32_t t_hacc0 = tb, t_oacc = tb + 256, t_a = tb + (term == 1 ? 448 : 384);
-        const uint32_t idesc = tc05::make_idesc_f16(128, 128);
-        const uint32_t a_addr = tc05::smem_u32(sm.A) + (term == 1 ? kRows * kE * 2 : 0);  // G_hi | G_lo
-        const uint32_t ring_addr = tc05::smem_u32(sm.Hb);
-        const uint32_t b_var = term == 2 ? kFVariantHalves * 2 : 0;
-        const int R16i = ((N + 15) >> 4) << 4;
-        const uint32_t idesc_l = tc05::make_idesc_f16(128, R16i);
-        const uint32_t lbo_l = (uint32_t)R16i * 16u;
-        const uint32_t lk_addr = ring_addr + (term == 2 ? (uint32_t)R16i * kE * 2 : 0);  // Lk_hi | Lk_lo
-        uint32_t step_par = 0, epi_phase = 0, sl = 0;
-        while (true) {
-          tc05::mbar_wait(&sm.bar_gready, step_par);
-          if (sm.exit_flag) break;
+      const uint32_t tb = sm.tmem_base;
+      const uint32_t t_hacc0 = tb, t_oacc = tb + 256, t_a = tb + (term == 1 ? 448 : 384);
+      const uint32_t idesc = tc05::make_idesc_f16(128, 128);
+      const uint32_t q_addr = tc05::smem_u32(sm.A);                                      // Q_hi | Q_lo, then G_hi | G_lo
+      const uint32_t a_addr = q_addr + (term == 1 ? kRows * kE * 2 : 0);
+      const uint32_t ring_addr = tc05::smem_u32(sm.Hb);
+      const uint32_t b_var = term == 2 ? kFVariantHalves * 2 : 0;
+      const int R16i = R16p;
+      const uint32_t idesc_l = tc05::make_idesc_f16(128, R16i);
+      const uint32_t idesc_pv = tc05::make_idesc_f16(128, 16);
+      const uint32_t lbo_l = (uint32_t)R16i * 16u;
+      const uint32_t kv_var = (uint32_t)R16i * 256u;  // bytes of one hi / lo variant of the K (or V) tiles
+      const uint32_t lk_addr = ring_addr + (term == 2 ? kv_var : 0);  // Lk_hi | Lk_lo
+      uint32_t step_par = 0, epi_phase = 0, sl = 0;
+      while (true) {
+        tc05::mbar_wait(&sm.bar_q, step_par, 32);
+        if (sm.exit_flag) break;
+        tc05::mbar_wait(&sm.bar_kv, step_par, 32);
+        tc05::fence_after_sync();
+#pragma unroll 1
+        for (int k = term; k < kH; k += 3) {
+          const int h = (k & 1) * 4 + (k >> 1);
+          const uint32_t t_s = tb + term * 128;
+          if (lane == 0) {
+            const uint32_t qh = q_addr + 2 * h * kLboTile, kh = ring_addr + 2 * h * lbo_l;
+            const uint64_t q_hi = tc05::make_desc(qh, kLboTile, kSbo), k_hi = tc05::make_desc(kh, lbo_l, kSbo);
+            tc05::mma_ss_f16(t_s, q_hi, k_hi, idesc_l, 0u);
+            if (kPasses == 3) {
+              tc05::mma_ss_f16(t_s, tc05::make_desc(qh + kRows * kE * 2, kLboTile, kSbo), k_hi, idesc_l, 1u);
+              tc05::mma_ss_f16(t_s, q_hi, tc05::make_desc(kh + kv_var, lbo_l, kSbo), idesc_l, 1u);
+            }
+            tc05::commit(&sm.bar_s[h]);
+          }
+          __syncwarp();
+          tc05::mbar_wait(&sm.bar_p[h], step_par, 32);
+          tc05::fence_after_sync();
+          if (lane < kPasses) {
+            // V_h^T tile: 16 dims x keys, K-major: 256 B between 16-byte key chunks, 128 B between 8-dim groups
+            const uint32_t vh = ring_addr + kKvSlotBytes / 2 + (lane == 2 ? kv_var : 0) + h * (R16i * 32);
+            const uint32_t ph = t_s + (lane == 1 ? 8 : 0);  // P_hi at columns 16 j, P_lo at 16 j + 8
+            for (int j = 0; j < (R16i >> 4); ++j)
+              tc05::mma_ts_f16(tb + 384 + 16 * h, ph + 16 * j, tc05::make_desc(vh + j * 512, 256, kSbo), idesc_pv, 1u);
+            tc05::commit(&sm.bar_o[h]);
+          }
+          __syncwarp();
+        }
+        if (lane == 0 && term < kPasses) {
+          tc05::mbar_wait(&sm.bar_gready, step_par, 32);
           tc05::fence_after_sync();
 #pragma unroll 1
           for (int j = 0; j < 8; ++j) {
             const int c = ffn_job_chunk(j), half = ffn_job_half(j);
             if (half == 1) {  // A operand of GEMM2(c) written (and, one job later, accumulator c & 1 re-zeroed)
-              tc05::mbar_wait(&sm.bar_epi, epi_phase);
+              tc05::mbar_wait(&sm.bar_epi, epi_phase, 32);
               epi_phase ^= 1u;
               tc05::fence_after_sync();
             }
 #pragma unroll 1
             for (int sj = 0; sj < kFSlicesPerJob; ++sj, ++sl) {
               const int st = sl & (kFStages - 1);
-              tc05::mbar_wait(&sm.bar_full[st], (sl / kFStages) & 1);
+              tc05::mbar_wait(&sm.bar_full[st], (sl / kFStages) & 1, 32);
               tc05::fence_after_sync();
               const uint32_t b_addr = ring_addr + st * kFSliceBytes + b_var;
 #pragma unroll
@@ -408,7 +511,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             tc05::commit(half == 0 ? &sm.bar_h[c & 1] : &sm.bar_g2);
           }
           // pointer logits: D[128 x R16] = g'(hi | lo, TMEM) . Lk(hi | lo, shared memory)^T, 8 K steps
-          tc05::mbar_wait(&sm.bar_lk, step_par);
+          tc05::mbar_wait(&sm.bar_lk, step_par, 32);
           tc05::fence_after_sync();
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
@@ -416,8 +519,9 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             tc05::mma_ts_f16(t_hacc0, t_a + ks * 8, bdesc, idesc_l, 1u);
           }
           tc05::commit(&sm.bar_acc);
-          step_par ^= 1u;
         }
+        __syncwarp();
+        step_par ^= 1u;
       }
       return;
     }
@@ -433,6 +537,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       tc05::tmem_st16(sm.tmem_base + lb + (warp >> 2) * 64 + q * 16, z);
       tc05::tmem_st16(sm.tmem_base + 128 + lb + (warp >> 2) * 64 + q * 16, z);
       tc05::tmem_st16(sm.tmem_base + 256 + lb + (warp >> 2) * 64 + q * 16, z);
+      tc05::tmem_st16(sm.tmem_base + 384 + lb + (warp >> 2) * 64 + q * 16, z);  // O tile of the attention
     }
     tc05::tmem_wait_st();
     tc05::fence_before_sync();
@@ -454,7 +559,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     }
     // ---- B (issued first so that the copies overlap phase A): K -> Hb, V -> Bs -----------------
     // (the tcgen05 variant prefetches them for step t+1 right after the logits MMAs of step t)
-    if (!kv_prefetched) {
+    if (!kTc && !kv_prefetched) {
       for (int idx = tid; idx < NPAD * 32; idx += kThreads) {
         const int row = idx >> 5, c4 = idx & 31;
         const bool ok = row < N;
@@ -534,197 +639,357 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         sm.mask[row][t] = t == 0 ? bits[0] : t == 1 ? bits[1] : t == 2 ? bits[2] : bits[3];
       }
     }
-    // ---- A2: query rows q = ctx_node_proj[cur] (+ proj2[...]) + sum_k state_k * wstate[k] ------
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int row = warp * 16 + i;
-      const int cur = sm.cur[row];
-      float4 q;
-      if (kEnv == RRNCO_ENV_ATSP) {
-        if (p.use_placeholder && step == 0) {
-          q = *reinterpret_cast<const float4*>(&sm.placeholder[lane * 4]);
-        } else {
-          const float4 a4 = __ldg(reinterpret_cast<const float4*>(P1 + (size_t)sm.first[row] * kE) + lane);
-          const float4 c4 = __ldg(reinterpret_cast<const float4*>(P2 + (size_t)cur * kE) + lane);
-          q = make_float4(a4.x + c4.x, a4.y + c4.y, a4.z + c4.z, a4.w + c4.w);
-        }
-      } else {
-        q = __ldg(reinterpret_cast<const float4*>(P1 + (size_t)cur * kE) + lane);
-        float st[kMaxState];
-        if (p.logits_only) {
-#pragma unroll
-          for (int k = 0; k < kMaxState; ++k) st[k] = sm.f[k][row];
-        } else if (kEnv == RRNCO_ENV_RCVRP) {
-          st[0] = __fsub_rn(cap, sm.f[0][row]);
-          st[1] = st[2] = st[3] = 0.f;
-        } else {
-          const float used = sm.f[3][row] == 0.f ? sm.f[2][row] : sm.f[3][row];
-          st[0] = __fsub_rn(cap, used);
-          st[1] = sm.f[0][row];
-          st[2] = closed == 0.f ? 1.f : 0.f;
-          float rem = __fsub_rn(limit, sm.f[1][row]);  // nan_to_num(limit - route, posinf=10)
-          rem = rem == INFINITY ? 10.f : (rem != rem ? 0.f : (rem == -INFINITY ? -3.4028234663852886e38f : rem));
-          st[3] = rem;
-        }
-#pragma unroll
-        for (int k = 0; k < kMaxState; ++k) {
-          if (k < p.n_state) {
-            const float4 w4 = *reinterpret_cast<const float4*>(&sm.wstate[k][lane * 4]);
-            q.x = fmaf(st[k], w4.x, q.x); q.y = fmaf(st[k], w4.y, q.y);
-            q.z = fmaf(st[k], w4.z, q.z); q.w = fmaf(st[k], w4.w, q.w);
-          }
-        }
-      }
-      *reinterpret_cast<float4*>(&sm.A[row * kLdA + lane * 4]) = q;
-    }
-    cp_async_wait<0>();
-    cta_sync<kTc>();
-    PHASE_STAMP(0);
-
-    // ---- C: attention, 16 rows x 8 heads per warp ----------------------------------------------
-    {
-      uint32_t m0[4], m1[4];
-      *reinterpret_cast<uint4*>(m0) = *reinterpret_cast<const uint4*>(sm.mask[r0]);
-      *reinterpret_cast<uint4*>(m1) = *reinterpret_cast<const uint4*>(sm.mask[r1]);
-      const float* sK = sm.Hb;
-      const float* sV = sm.Bs;
-#pragma unroll 1
-      for (int h = 0; h < kH; ++h) {
-        uint32_t ah[2][4], al[2][4];
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const int k0 = h * kDh + ks * 8 + t;
-          split_tf32(sm.A[r0 * kLdA + k0], ah[ks][0], al[ks][0]);
-          split_tf32(sm.A[r1 * kLdA + k0], ah[ks][1], al[ks][1]);
-          split_tf32(sm.A[r0 * kLdA + k0 + 4], ah[ks][2], al[ks][2]);
-          split_tf32(sm.A[r1 * kLdA + k0 + 4], ah[ks][3], al[ks][3]);
-        }
-        float sc[kNTMax][4];
-#pragma unroll
-        for (int j = 0; j < kNTMax; ++j) {
-          sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-          if (j < NT) {
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const float* kp = sK + (8 * j + g) * kLdA + h * kDh + ks * 8 + t;
-              uint32_t bh[2], bl[2];
-              split_tf32(kp[0], bh[0], bl[0]);
-              split_tf32(kp[4], bh[1], bl[1]);
-              mma_x<kPasses>(sc[j], ah[ks], al[ks], bh, bl);
-            }
-          }
-        }
-        // masked softmax over the keys (scale 1/sqrt(16) is a power of two: exact)
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < kNTMax; ++j) {
-          if (j < NT) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              sc[j][e] = bit_of(m0, j, 2 * t + e) ? sc[j][e] * 0.25f : -INFINITY;
-              sc[j][2 + e] = bit_of(m1, j, 2 * t + e) ? sc[j][2 + e] * 0.25f : -INFINITY;
-              mx0 = fmaxf(mx0, sc[j][e]);
-              mx1 = fmaxf(mx1, sc[j][2 + e]);
-            }
-          }
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < kNTMax; ++j) {
-          if (j < NT) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              sc[j][e] = fexp(sc[j][e] - mx0);
-              sc[j][2 + e] = fexp(sc[j][2 + e] - mx1);
-              sum0 += sc[j][e];
-              sum1 += sc[j][2 + e];
-            }
-          }
-        }
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-        // heads = P V_h: the accumulator tile j IS the A fragment of k-step j under the key permutation
-        // k = t -> key 8j + 2t, k = t + 4 -> key 8j + 2t + 1 (applied to the V rows below).
-        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-        for (int j = 0; j < kNTMax; ++j) {
-          if (j < NT) {
-            uint32_t ph[4], pl[4];
-            split_tf32(sc[j][0], ph[0], pl[0]);
-            split_tf32(sc[j][2], ph[1], pl[1]);
-            split_tf32(sc[j][1], ph[2], pl[2]);
-            split_tf32(sc[j][3], ph[3], pl[3]);
-#pragma unroll
-            for (int dd = 0; dd < 2; ++dd) {
-              const float* vp = sV + (8 * j + 2 * t) * kLdA + h * kDh + dd * 8 + g;
-              uint32_t bh[2], bl[2];
-              split_tf32(vp[0], bh[0], bl[0]);
-              split_tf32(vp[kLdA], bh[1], bl[1]);
-              mma_x<kPasses>(o[dd], ph, pl, bh, bl);
-            }
-          }
-        }
-        const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-#pragma unroll
-        for (int dd = 0; dd < 2; ++dd) {
-          const int col = h * kDh + dd * 8 + 2 * t;
-          float2* g0 = reinterpret_cast<float2*>(&sm.A[r0 * kLdA + col]);
-          float2* g1 = reinterpret_cast<float2*>(&sm.A[r1 * kLdA + col]);
-          float2 q0 = *g0, q1 = *g1;
-          q0.x += o[dd][0] * inv0; q0.y += o[dd][1] * inv0;
-          q1.x += o[dd][2] * inv1; q1.y += o[dd][3] * inv1;
-          *g0 = q0;  // glimpse = heads + q  (decoder.py:292-293), in place: these columns are only read
-          *g1 = q1;  // by head h of this warp, whose A fragments are already in registers
-        }
-        __syncwarp();
-      }
-    }
-    if (kTc) tc05::fence_proxy_async();  // generic-proxy reads of the V tile precede the TMA writes into the same memory
-    cta_sync<kTc>();  // all warps done with the K / V tiles; glimpse complete in A
-    PHASE_STAMP(1);
-
-    // ---- E: FFN  g' = W2 relu(W1 g + b1) + b2 + g ---------------------------------------------
-    int sl = 0;
     if (kTc) {
-      // tcgen05 path (see ffn_tc_kernel.cu for the standalone form): glimpse -> fp16 hi | lo K-major core-matrix
-      // tiles in the A region, weights streamed by the TMA producer warp through the Hb | Bs regions, accumulators and
-      // the hidden activations (A operand of GEMM2) in tensor memory, MMAs issued by warps 9-11.  The compute warps
-      // only run the epilogues.
-      if (tid == 0) tc05::mbar_arrive(&sm.bar_go);  // K / V tiles are dead: the producer starts this step's stream
-      uint16_t* g_hi = reinterpret_cast<uint16_t*>(sm.A);  // [16-byte K chunk (16)][row (128)][8 halves]
-      uint16_t* g_lo = g_hi + kRows * kE;
+      // ---- A2 (tcgen05): query rows -> fp16 hi | lo core-matrix tiles (A operand of Q K^T) in the A region.
+      // lane = (row of the warp's 16, 64-wide half of the embedding): conflict-free 16-byte tile stores.
       {
-        float4 gres[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = tid + i * kThreads, row = idx & 127, c8 = idx >> 7;
-          gres[2 * i] = *reinterpret_cast<const float4*>(&sm.A[row * kLdA + c8 * 8]);
-          gres[2 * i + 1] = *reinterpret_cast<const float4*>(&sm.A[row * kLdA + c8 * 8 + 4]);
+        uint16_t* q_hi = reinterpret_cast<uint16_t*>(sm.A);
+        uint16_t* q_lo = q_hi + kRows * kE;
+        const int row = warp * 16 + (lane & 15), dh = lane >> 4;
+        const int cur = sm.cur[row];
+        float st[kMaxState] = {0.f, 0.f, 0.f, 0.f};
+        const float* src1;
+        const float* src2 = nullptr;
+        if (kEnv == RRNCO_ENV_ATSP) {
+          if (p.use_placeholder && step == 0) {
+            src1 = sm.placeholder;
+          } else {
+            src1 = P1 + (size_t)sm.first[row] * kE;
+            src2 = P2 + (size_t)cur * kE;
+          }
+        } else {
+          src1 = P1 + (size_t)cur * kE;
+          if (kEnv == RRNCO_ENV_RCVRP) {
+            st[0] = __fsub_rn(cap, sm.f[0][row]);
+          } else {
+            const float used = sm.f[3][row] == 0.f ? sm.f[2][row] : sm.f[3][row];
+            st[0] = __fsub_rn(cap, used);
+            st[1] = sm.f[0][row];
+            st[2] = closed == 0.f ? 1.f : 0.f;
+            float rem = __fsub_rn(limit, sm.f[1][row]);  // nan_to_num(limit - route, posinf=10)
+            rem = rem == INFINITY ? 10.f : (rem != rem ? 0.f : (rem == -INFINITY ? -3.4028234663852886e38f : rem));
+            st[3] = rem;
+          }
         }
-        cta_sync<kTc>();  // every thread holds its part of the glimpse: the A region may now be re-laid out
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = tid + i * kThreads, row = idx & 127, c8 = idx >> 7;
-          const float4 v0 = gres[2 * i], v1 = gres[2 * i + 1];
+        for (int cc = 0; cc < 8; ++cc) {
+          const int c8 = dh * 8 + cc;
+          float4 v0 = *reinterpret_cast<const float4*>(src1 + c8 * 8), v1 = *reinterpret_cast<const float4*>(src1 + c8 * 8 + 4);
+          if (kEnv == RRNCO_ENV_ATSP) {
+            if (src2) {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(src2 + c8 * 8));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(src2 + c8 * 8 + 4));
+              v0 = make_float4(v0.x + w0.x, v0.y + w0.y, v0.z + w0.z, v0.w + w0.w);
+              v1 = make_float4(v1.x + w1.x, v1.y + w1.y, v1.z + w1.z, v1.w + w1.w);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kMaxState; ++k) {
+              if (k < p.n_state) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&sm.wstate[k][c8 * 8]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&sm.wstate[k][c8 * 8 + 4]);
+                v0.x = fmaf(st[k], w0.x, v0.x); v0.y = fmaf(st[k], w0.y, v0.y);
+                v0.z = fmaf(st[k], w0.z, v0.z); v0.w = fmaf(st[k], w0.w, v0.w);
+                v1.x = fmaf(st[k], w1.x, v1.x); v1.y = fmaf(st[k], w1.y, v1.y);
+                v1.z = fmaf(st[k], w1.z, v1.z); v1.w = fmaf(st[k], w1.w, v1.w);
+              }
+            }
+          }
           uint32_t h[4], l[4];
           f16s_split2(v0.x, v0.y, kAScale, h[0], l[0]); f16s_split2(v0.z, v0.w, kAScale, h[1], l[1]);
           f16s_split2(v1.x, v1.y, kAScale, h[2], l[2]); f16s_split2(v1.z, v1.w, kAScale, h[3], l[3]);
           const int dst = c8 * (kRows * 8) + row * 8;
-          *reinterpret_cast<uint4*>(&g_hi[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(&g_lo[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
+          *reinterpret_cast<uint4*>(&q_hi[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(&q_lo[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
         }
       }
       tc05::fence_proxy_async();
       tc05::fence_before_sync();
-      tc05::mbar_arrive(&sm.bar_gready);
-      cta_sync<kTc>();  // the output epilogue below reads residual values other threads wrote
-      PHASE_STAMP(2);
+      tc05::mbar_arrive(&sm.bar_q);
+      cta_sync<kTc>();  // action-mask bitsets visible to the row-owner threads
+      PHASE_STAMP(0);
+
+      // ---- C (tcgen05): attention.  Scores of head h arrive in a TMEM buffer (lane = rollout); the thread that owns
+      // (rollout, head group) runs the masked softmax on its row and writes the unnormalised probabilities back IN
+      // PLACE as the fp16 hi | lo A operand of P V (columns 16 j .. 16 j + 7 | 16 j + 8 .. 16 j + 15 of key block j).
+      // Warps 0-3 take heads 0-3, warps 4-7 heads 4-7, so a thread later normalises exactly the columns it summed.
+      {
+        const int row = (warp & 3) * 32 + lane, grp = warp >> 2;
+        const uint32_t tb = sm.tmem_base, lane_b = (uint32_t)((warp & 3) * 32) << 16;
+        const int R16a = ((N + 15) >> 4) << 4;
+        // s = q . k / 4; the operands carry kAScale kKvScale.  exp(s - m) = ex2(c1 v - c1 vmax); + 4 = log2(kAScale)
+        const float c1 = 0.25f * 1.4426950408889634f / (kAScale * kKvScale);
+        const int nblk = (R16a + 31) >> 5;  // 32-column blocks; columns past R16 hold stale data that the mask zeroes
+        // Rolled loops on purpose: the decode-step body is far larger than the instruction cache, and every unrolled
+        // copy of this code is fetched from L2 once per step (stall_no_inst was > 50 % of this phase when unrolled).
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int h = 4 * grp + j, k = 2 * j + grp;
+          const uint32_t t_s = tb + (uint32_t)(k % 3) * 128u + lane_b;
+          tc05::mbar_wait(&sm.bar_s[h], tc_step_par, 20);
+          tc05::fence_after_sync();
+          PHASE_STAMP(11);
+          // pass 1: row maximum over the feasible keys (four independent partial maxima)
+          float vm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+          for (int gb = 0; gb < nblk; ++gb) {
+            uint32_t v[2][16];
+            tc05::tmem_ld16(t_s + gb * 32, v[0]);
+            tc05::tmem_ld16(t_s + gb * 32 + 16, v[1]);
+            const uint32_t mw = sm.mask[row][gb];
+            tc05::tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              vm[i & 3] = fmaxf(vm[i & 3], ((mw >> i) & 1u) ? __uint_as_float(v[i >> 4][i & 15]) : -INFINITY);
+          }
+          const float off = fmaf(-c1, fmaxf(fmaxf(vm[0], vm[1]), fmaxf(vm[2], vm[3])), 4.0f);
+          PHASE_STAMP(12);
+          // pass 2: p = exp(s - max) (x kAScale), row sum, fp16 hi | lo split written back in place
+          float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll 1
+          for (int gb = 0; gb < nblk; ++gb) {
+            uint32_t v[2][16];
+            tc05::tmem_ld16(t_s + gb * 32, v[0]);
+            tc05::tmem_ld16(t_s + gb * 32 + 16, v[1]);
+            const uint32_t mw = sm.mask[row][gb];
+            tc05::tmem_wait_ld();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              uint32_t w[16];  // [hi (8 words) | lo (8 words)] of key block 2 gb + u
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                const float e0 = ex2a(fmaf(c1, __uint_as_float(v[u][i]), off));
+                const float e1 = ex2a(fmaf(c1, __uint_as_float(v[u][i + 1]), off));
+                const float p0 = ((mw >> (16 * u + i)) & 1u) ? e0 : 0.f;
+                const float p1 = ((mw >> (16 * u + i + 1)) & 1u) ? e1 : 0.f;
+                sum0 += p0;
+                sum1 += p1;
+                f16s_split2(p0, p1, 1.0f, w[i >> 1], w[8 + (i >> 1)]);
+              }
+              tc05::tmem_st16(t_s + gb * 32 + u * 16, w);
+            }
+          }
+          sm.xsum[h][row] = sum0 + sum1;
+          tc05::tmem_wait_st();
+          tc05::fence_before_sync();
+          tc05::mbar_arrive(&sm.bar_p[h]);
+          PHASE_STAMP(13);
+        }
+        // every P V complete (all eight: the score buffers are zeroed and the K / V memory handed over below)
+#pragma unroll 1
+        for (int h = 0; h < kH; ++h) tc05::mbar_wait(&sm.bar_o[h], tc_step_par, 20);
+        tc05::fence_after_sync();
+        PHASE_STAMP(14);
+        // glimpse = heads / sum + q (decoder.py:292-293) -> fp16 hi | lo tiles of the FFN, in place over the query tiles
+        uint16_t* g_hi = reinterpret_cast<uint16_t*>(sm.A);
+        uint16_t* g_lo = g_hi + kRows * kE;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int h = 4 * grp + j;
+          uint32_t o[16];
+          tc05::tmem_ld16(tb + 384 + 16 * h + lane_b, o);
+          const float inv = __fdividef(1.0f, kKvScale * sm.xsum[h][row]);
+          tc05::tmem_wait_ld();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int offq = (2 * h + cc) * (kRows * 8) + row * 8;
+            const uint4 qh = *reinterpret_cast<const uint4*>(&g_hi[offq]);
+            const uint4 ql = *reinterpret_cast<const uint4*>(&g_lo[offq]);
+            const uint32_t qhw[4] = {qh.x, qh.y, qh.z, qh.w}, qlw[4] = {ql.x, ql.y, ql.z, ql.w};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&qhw[e]));
+              const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&qlw[e]));
+              const float g0 = fmaf(__uint_as_float(o[cc * 8 + 2 * e]), inv, (fh.x + fl.x) * (1.0f / kAScale));
+              const float g1 = fmaf(__uint_as_float(o[cc * 8 + 2 * e + 1]), inv, (fh.y + fl.y) * (1.0f / kAScale));
+              f16s_split2(g0, g1, kAScale, hi[e], lo[e]);
+            }
+            *reinterpret_cast<uint4*>(&g_hi[offq]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(&g_lo[offq]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        {  // the three score buffers become the (pre-zeroed) accumulators of the FFN
+          uint32_t z[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+          for (int q = 0; q < 12; ++q) tc05::tmem_st16(tb + lane_b + (q >> 2) * 128 + grp * 64 + (q & 3) * 16, z);
+          tc05::tmem_wait_st();
+        }
+      }
+      tc05::fence_proxy_async();
+      tc05::fence_before_sync();
+      tc05::mbar_arrive(&sm.bar_go);      // K / V tiles are dead: the producer starts this step's weight stream
+      tc05::mbar_arrive(&sm.bar_gready);  // glimpse tiles written: GEMM1 may start
+      PHASE_STAMP(1);
+    } else {
+      // ---- A2: query rows q = ctx_node_proj[cur] (+ proj2[...]) + sum_k state_k * wstate[k] ------
+  #pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int row = warp * 16 + i;
+        const int cur = sm.cur[row];
+        float4 q;
+        if (kEnv == RRNCO_ENV_ATSP) {
+          if (p.use_placeholder && step == 0) {
+            q = *reinterpret_cast<const float4*>(&sm.placeholder[lane * 4]);
+          } else {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(P1 + (size_t)sm.first[row] * kE) + lane);
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(P2 + (size_t)cur * kE) + lane);
+            q = make_float4(a4.x + c4.x, a4.y + c4.y, a4.z + c4.z, a4.w + c4.w);
+          }
+        } else {
+          q = __ldg(reinterpret_cast<const float4*>(P1 + (size_t)cur * kE) + lane);
+          float st[kMaxState];
+          if (p.logits_only) {
+  #pragma unroll
+            for (int k = 0; k < kMaxState; ++k) st[k] = sm.f[k][row];
+          } else if (kEnv == RRNCO_ENV_RCVRP) {
+            st[0] = __fsub_rn(cap, sm.f[0][row]);
+            st[1] = st[2] = st[3] = 0.f;
+          } else {
+            const float used = sm.f[3][row] == 0.f ? sm.f[2][row] : sm.f[3][row];
+            st[0] = __fsub_rn(cap, used);
+            st[1] = sm.f[0][row];
+            st[2] = closed == 0.f ? 1.f : 0.f;
+            float rem = __fsub_rn(limit, sm.f[1][row]);  // nan_to_num(limit - route, posinf=10)
+            rem = rem == INFINITY ? 10.f : (rem != rem ? 0.f : (rem == -INFINITY ? -3.4028234663852886e38f : rem));
+            st[3] = rem;
+          }
+  #pragma unroll
+          for (int k = 0; k < kMaxState; ++k) {
+            if (k < p.n_state) {
+              const float4 w4 = *reinterpret_cast<const float4*>(&sm.wstate[k][lane * 4]);
+              q.x = fmaf(st[k], w4.x, q.x); q.y = fmaf(st[k], w4.y, q.y);
+              q.z = fmaf(st[k], w4.z, q.z); q.w = fmaf(st[k], w4.w, q.w);
+            }
+          }
+        }
+        *reinterpret_cast<float4*>(&sm.A[row * kLdA + lane * 4]) = q;
+      }
+      cp_async_wait<0>();
+      cta_sync<kTc>();
+      PHASE_STAMP(0);
+
+      // ---- C: attention, 16 rows x 8 heads per warp ----------------------------------------------
+      {
+        uint32_t m0[4], m1[4];
+        *reinterpret_cast<uint4*>(m0) = *reinterpret_cast<const uint4*>(sm.mask[r0]);
+        *reinterpret_cast<uint4*>(m1) = *reinterpret_cast<const uint4*>(sm.mask[r1]);
+        const float* sK = sm.Hb;
+        const float* sV = sm.Bs;
+  #pragma unroll 1
+        for (int h = 0; h < kH; ++h) {
+          uint32_t ah[2][4], al[2][4];
+  #pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const int k0 = h * kDh + ks * 8 + t;
+            split_tf32(sm.A[r0 * kLdA + k0], ah[ks][0], al[ks][0]);
+            split_tf32(sm.A[r1 * kLdA + k0], ah[ks][1], al[ks][1]);
+            split_tf32(sm.A[r0 * kLdA + k0 + 4], ah[ks][2], al[ks][2]);
+            split_tf32(sm.A[r1 * kLdA + k0 + 4], ah[ks][3], al[ks][3]);
+          }
+          float sc[kNTMax][4];
+  #pragma unroll
+          for (int j = 0; j < kNTMax; ++j) {
+            sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+            if (j < NT) {
+  #pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const float* kp = sK + (8 * j + g) * kLdA + h * kDh + ks * 8 + t;
+                uint32_t bh[2], bl[2];
+                split_tf32(kp[0], bh[0], bl[0]);
+                split_tf32(kp[4], bh[1], bl[1]);
+                mma_x<kPasses>(sc[j], ah[ks], al[ks], bh, bl);
+              }
+            }
+          }
+          // masked softmax over the keys (scale 1/sqrt(16) is a power of two: exact)
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+  #pragma unroll
+          for (int j = 0; j < kNTMax; ++j) {
+            if (j < NT) {
+  #pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                sc[j][e] = bit_of(m0, j, 2 * t + e) ? sc[j][e] * 0.25f : -INFINITY;
+                sc[j][2 + e] = bit_of(m1, j, 2 * t + e) ? sc[j][2 + e] * 0.25f : -INFINITY;
+                mx0 = fmaxf(mx0, sc[j][e]);
+                mx1 = fmaxf(mx1, sc[j][2 + e]);
+              }
+            }
+          }
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+          float sum0 = 0.f, sum1 = 0.f;
+  #pragma unroll
+          for (int j = 0; j < kNTMax; ++j) {
+            if (j < NT) {
+  #pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                sc[j][e] = fexp(sc[j][e] - mx0);
+                sc[j][2 + e] = fexp(sc[j][2 + e] - mx1);
+                sum0 += sc[j][e];
+                sum1 += sc[j][2 + e];
+              }
+            }
+          }
+          sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+          sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+          sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+          sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+          // heads = P V_h: the accumulator tile j IS the A fragment of k-step j under the key permutation
+          // k = t -> key 8j + 2t, k = t + 4 -> key 8j + 2t + 1 (applied to the V rows below).
+          float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  #pragma unroll
+          for (int j = 0; j < kNTMax; ++j) {
+            if (j < NT) {
+              uint32_t ph[4], pl[4];
+              split_tf32(sc[j][0], ph[0], pl[0]);
+              split_tf32(sc[j][2], ph[1], pl[1]);
+              split_tf32(sc[j][1], ph[2], pl[2]);
+              split_tf32(sc[j][3], ph[3], pl[3]);
+  #pragma unroll
+              for (int dd = 0; dd < 2; ++dd) {
+                const float* vp = sV + (8 * j + 2 * t) * kLdA + h * kDh + dd * 8 + g;
+                uint32_t bh[2], bl[2];
+                split_tf32(vp[0], bh[0], bl[0]);
+                split_tf32(vp[kLdA], bh[1], bl[1]);
+                mma_x<kPasses>(o[dd], ph, pl, bh, bl);
+              }
+            }
+          }
+          const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  #pragma unroll
+          for (int dd = 0; dd < 2; ++dd) {
+            const int col = h * kDh + dd * 8 + 2 * t;
+            float2* g0 = reinterpret_cast<float2*>(&sm.A[r0 * kLdA + col]);
+            float2* g1 = reinterpret_cast<float2*>(&sm.A[r1 * kLdA + col]);
+            float2 q0 = *g0, q1 = *g1;
+            q0.x += o[dd][0] * inv0; q0.y += o[dd][1] * inv0;
+            q1.x += o[dd][2] * inv1; q1.y += o[dd][3] * inv1;
+            *g0 = q0;  // glimpse = heads + q  (decoder.py:292-293), in place: these columns are only read
+            *g1 = q1;  // by head h of this warp, whose A fragments are already in registers
+          }
+          __syncwarp();
+        }
+      }
+      if (kTc) tc05::fence_proxy_async();  // generic-proxy reads of the V tile precede the TMA writes into the same memory
+      cta_sync<kTc>();  // all warps done with the K / V tiles; glimpse complete in A
+      PHASE_STAMP(1);
+
+    }
+
+    // ---- E: FFN  g' = W2 relu(W1 g + b1) + b2 + g ---------------------------------------------
+    int sl = 0;
+    if (kTc) {
+      // tcgen05 path (see ffn_tc_kernel.cu for the standalone form): glimpse = fp16 hi | lo K-major core-matrix
+      // tiles in the A region, weights streamed by the TMA producer warp through the Hb | Bs regions, accumulators and
+      // the hidden activations (A operand of GEMM2) in tensor memory, MMAs issued by warps 9-11.  The compute warps
+      // only run the epilogues.
+      uint16_t* g_hi = reinterpret_cast<uint16_t*>(sm.A);  // [16-byte K chunk (16)][row (128)][8 halves], written by
+      uint16_t* g_lo = g_hi + kRows * kE;                   // the attention epilogue (each thread re-reads its own part)
       // logit keys of this instance -> registers now (L2 latency hidden behind the FFN); they are split into the
       // fp16 hi | lo core-matrix tiles of the logits GEMM once the FFN has released the ring memory.
       const int R16 = ((N + 15) >> 4) << 4;  // rows of the logit-key tile = N of the logits MMA (multiple of 16)
@@ -765,9 +1030,11 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           }
           tc05::tmem_st8(t_hhi + lane_base + (col0 >> 1), hi);
           tc05::tmem_st8(t_hlo + lane_base + (col0 >> 1), lo);
+          if (c < 3) {  // re-zero the chunk accumulator for GEMM1(c + 2) / the logits (c == 2)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;
-          tc05::tmem_st16(t_h + lane_base + col0, v);  // re-zero the chunk accumulator for GEMM1(c + 2) / the logits
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+            tc05::tmem_st16(t_h + lane_base + col0, v);
+          }
         }
         tc05::tmem_wait_st();
         tc05::fence_before_sync();
@@ -804,9 +1071,6 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           }
           tc05::tmem_st8(t_hhi + lane_base + (col0 >> 1), hi);
           tc05::tmem_st8(t_hlo + lane_base + (col0 >> 1), lo);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;
-          tc05::tmem_st16(t_oacc + lane_base + col0, v);  // re-zero the output accumulator for the next decode step
         }
       }
       // logit keys -> fp16 hi | lo tiles [16-byte K chunk (16)][row (R16)][8 halves] at the start of the idle ring
@@ -856,16 +1120,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       tc05::mbar_wait(&sm.bar_acc, tc_step_par, 32);
       tc_step_par ^= 1u;
       tc05::fence_after_sync();
-      // K / V of the next decode step: both tiles' memory is idle from here to the next attention phase
-      for (int idx = tid; idx < NPAD * 32; idx += kThreads) {
-        const int row = idx >> 5, c4 = idx & 31;
-        const bool ok = row < N;
-        const size_t off = (size_t)(ok ? row : 0) * kE + c4 * 4;
-        cp_async16_zfill(sm.Hb + row * kLdA + c4 * 4, Kc + off, ok);
-        cp_async16_zfill(sm.Bs + row * kLdA + c4 * 4, Vc + off, ok);
-      }
-      cp_async_commit();
-      kv_prefetched = true;
+      // the logit-key tiles are dead: the producer may load the packed K / V tiles of the next decode step
+      if (tid == 0) tc05::mbar_arrive(&sm.bar_kvgo);
       PHASE_STAMP(5);
 
       // ---- select epilogue, thread per row: two threads (column halves) own one rollout ----
@@ -903,11 +1159,9 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             lv[q * 16 + i] = l;
             mxl = fmaxf(mxl, l);
           }
-          if (col0 < R16) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0u;
-            tc05::tmem_st16(t_hacc + lane_base + col0, v);  // leave the accumulator zeroed for the next GEMM1
-          }
+          for (int i = 0; i < 16; ++i) v[i] = 0u;  // the O tile of the next step's attention accumulates: zero it
+          tc05::tmem_st16(tbase + 384 + lane_base + colhalf * 64 + q * 16, v);
         }
         if (p.w.temperature != 1.0f) {
           mxl = -INFINITY;
@@ -1319,11 +1573,12 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
   if (kTc) {
     if (tid == 0) {
       sm.exit_flag = 1;
-      tc05::mbar_arrive(&sm.bar_go);  // releases the producer warp
+      tc05::mbar_wait(&sm.bar_kv, tc_step_par);  // the K / V load for the step that will not happen must have landed
     }
     tc05::fence_before_sync();
     cta_sync<kTc>();
-    tc05::mbar_arrive(&sm.bar_gready);  // releases the MMA-issue warps (they see exit_flag)
+    tc05::mbar_arrive(&sm.bar_go);  // releases the producer warp and the MMA-issue warps (they see exit_flag)
+    tc05::mbar_arrive(&sm.bar_q);
     if (warp == 0) tc05::tmem_dealloc(sm.tmem_base, 512);
   }
 }
@@ -1470,7 +1725,7 @@ int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_in
   const int64_t R = n_inst * n_starts;
   const int64_t tiles = n_inst * ((n_starts + kRows - 1) / kRows);
   return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL) +
-         kFfnPackedBytes;
+         kFfnPackedBytes + (int64_t)kKvSlots * kKvSlotBytes;
 }
 
 int rrnco_decoder_logits(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts,
@@ -1526,6 +1781,7 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
   const int64_t tiles = n_inst * p.n_tiles;
   unsigned char* packed = reinterpret_cast<unsigned char*>(p.ws_tile_steps) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL);
   p.ffn_packed = packed;
+  p.kv_pack = packed + kFfnPackedBytes;  // 16-byte aligned: every part above is a multiple of 16 bytes
   p.max_steps_out = max_steps_out; p.status = status;
   if (cudaMemsetAsync(max_steps_out, 0, sizeof(int32_t), st) != cudaSuccess) return RRNCO_ERR_CUDA;
   if (g_engine == 1) {
