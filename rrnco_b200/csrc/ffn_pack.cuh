@@ -41,7 +41,8 @@ constexpr float kWScale = 256.0f;                                // weights; |w|
 constexpr float kLkScale = 16.0f;                                // logit keys; |Lk| < 4094 representable
 constexpr float kAScale = 16.0f;                                 // activations; |a| < 4094 representable
 constexpr float kKvScale = 16.0f;                                // attention keys / values; |x| < 4094 representable
-constexpr uint32_t kKvSlotBytes = 131072;                        // packed K | V tiles of one instance (per-SM workspace slot)
+constexpr uint32_t kKvOffV = 65536, kKvOffLk = 131072;           // byte offsets of the V and logit-key tiles in a slot
+constexpr uint32_t kKvSlotBytes = 196608;                        // packed K | V | Lk tiles of one instance (per-SM workspace slot)
 constexpr int kKvSlots = 256;                                    // >= %nsmid
 
 // chunk / half of job j (see above)

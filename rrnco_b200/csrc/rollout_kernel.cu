@@ -136,7 +136,9 @@ struct Smem {
   uint64_t bar_h[2];    // issuers -> compute: GEMM1 into hidden accumulator b complete
   uint64_t bar_epi;     // compute -> issuers: epilogue 1 done (A operand of GEMM2 in TMEM, accumulator re-zeroed)
   uint64_t bar_g2;      // issuers -> compute: GEMM2 of a chunk complete (its A operand may be overwritten)
-  uint64_t bar_lk;      // compute -> issuers: g' (TMEM) and the logit-key tiles written
+  uint64_t bar_lk;      // compute -> issuers: g' (A operand of the logits GEMM) written to TMEM
+  uint64_t bar_lkgo;    // compute -> producer: FFN complete, the ring memory may take the packed logit-key tiles
+  uint64_t bar_lkfull;  // TMA -> issuers: packed logit-key tiles landed
   uint64_t bar_acc;     // issuers -> compute: logits complete
   uint32_t tmem_base;
   volatile int exit_flag;
@@ -275,6 +277,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       tc05::mbar_init(&sm.bar_epi, kThreads);
       tc05::mbar_init(&sm.bar_g2, kPasses);
       tc05::mbar_init(&sm.bar_lk, kThreads);
+      tc05::mbar_init(&sm.bar_lkgo, 1);
+      tc05::mbar_init(&sm.bar_lkfull, 1);
       tc05::mbar_init(&sm.bar_acc, kPasses);
       tc05::fence_mbar_init();
       sm.exit_flag = 0;
@@ -356,21 +360,26 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     if (smid >= (uint32_t)kKvSlots) __trap();
     unsigned char* slot = p.kv_pack + (size_t)smid * kKvSlotBytes;
     if (tid < kThreads) {
-      uint4* k_hi = reinterpret_cast<uint4*>(slot);
-      uint4* v_hi = reinterpret_cast<uint4*>(slot + kKvSlotBytes / 2);
+      uint4* v_hi = reinterpret_cast<uint4*>(slot + kKvOffV);
       const int var16 = R16p * 16;  // uint4 elements per variant
-      for (int idx = tid; idx < R16p * 16; idx += kThreads) {
-        const int r = idx >> 4, c8 = idx & 15;
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (r < N) {
-          v0 = __ldg(reinterpret_cast<const float4*>(Kc + (size_t)r * kE) + c8 * 2);
-          v1 = __ldg(reinterpret_cast<const float4*>(Kc + (size_t)r * kE) + c8 * 2 + 1);
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {  // glimpse keys, then logit keys: same row-major -> chunk-major repack
+        const float* src = which ? Lk : Kc;
+        const float scale = which ? kLkScale : kKvScale;
+        uint4* k_hi = reinterpret_cast<uint4*>(slot + (which ? kKvOffLk : 0));
+        for (int idx = tid; idx < R16p * 16; idx += kThreads) {
+          const int r = idx >> 4, c8 = idx & 15;
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+          if (r < N) {
+            v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * kE) + c8 * 2);
+            v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * kE) + c8 * 2 + 1);
+          }
+          uint32_t h[4], l[4];
+          f16s_split2(v0.x, v0.y, scale, h[0], l[0]); f16s_split2(v0.z, v0.w, scale, h[1], l[1]);
+          f16s_split2(v1.x, v1.y, scale, h[2], l[2]); f16s_split2(v1.z, v1.w, scale, h[3], l[3]);
+          k_hi[c8 * R16p + r] = make_uint4(h[0], h[1], h[2], h[3]);
+          k_hi[var16 + c8 * R16p + r] = make_uint4(l[0], l[1], l[2], l[3]);
         }
-        uint32_t h[4], l[4];
-        f16s_split2(v0.x, v0.y, kKvScale, h[0], l[0]); f16s_split2(v0.z, v0.w, kKvScale, h[1], l[1]);
-        f16s_split2(v1.x, v1.y, kKvScale, h[2], l[2]); f16s_split2(v1.z, v1.w, kKvScale, h[3], l[3]);
-        k_hi[c8 * R16p + r] = make_uint4(h[0], h[1], h[2], h[3]);
-        k_hi[var16 + c8 * R16p + r] = make_uint4(l[0], l[1], l[2], l[3]);
       }
       const int nkc = R16p >> 3;
       for (int idx = tid; idx < R16p * 16; idx += kThreads) {
@@ -406,7 +415,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           tc05::mbar_wait(&sm.bar_kvgo, go_phase, 64);
           tc05::mbar_arrive_expect_tx(&sm.bar_kv, 2 * kv_bytes);
           tc05::bulk_g2s(ring, slot, kv_bytes, &sm.bar_kv);
-          tc05::bulk_g2s(ring + kKvSlotBytes / 2, slot + kKvSlotBytes / 2, kv_bytes, &sm.bar_kv);
+          tc05::bulk_g2s(ring + kKvOffV, slot + kKvOffV, kv_bytes, &sm.bar_kv);
           tc05::mbar_wait(&sm.bar_go, go_phase, 64);
           go_phase ^= 1u;
           if (sm.exit_flag) break;
@@ -417,6 +426,9 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             tc05::bulk_g2s(ring + (size_t)st * kFSliceBytes, p.ffn_packed + (size_t)s * kFSliceBytes, kFSliceBytes,
                            &sm.bar_full[st]);
           }
+          tc05::mbar_wait(&sm.bar_lkgo, go_phase ^ 1u, 64);  // every weight slice consumed: logit keys -> ring start
+          tc05::mbar_arrive_expect_tx(&sm.bar_lkfull, kv_bytes);
+          tc05::bulk_g2s(ring, slot + kKvOffLk, kv_bytes, &sm.bar_lkfull);
         }
       }
       return;
@@ -470,7 +482,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           tc05::fence_after_sync();
           if (lane < kPasses) {
             // V_h^T tile: 16 dims x keys, K-major: 256 B between 16-byte key chunks, 128 B between 8-dim groups
-            const uint32_t vh = ring_addr + kKvSlotBytes / 2 + (lane == 2 ? kv_var : 0) + h * (R16i * 32);
+            const uint32_t vh = ring_addr + kKvOffV + (lane == 2 ? kv_var : 0) + h * (R16i * 32);
             const uint32_t ph = t_s + (lane == 1 ? 8 : 0);  // P_hi at columns 16 j, P_lo at 16 j + 8
             for (int j = 0; j < (R16i >> 4); ++j)
               tc05::mma_ts_f16(tb + 384 + 16 * h, ph + 16 * j, tc05::make_desc(vh + j * 512, 256, kSbo), idesc_pv, 1u);
@@ -512,6 +524,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           }
           // pointer logits: D[128 x R16] = g'(hi | lo, TMEM) . Lk(hi | lo, shared memory)^T, 8 K steps
           tc05::mbar_wait(&sm.bar_lk, step_par, 32);
+          tc05::mbar_wait(&sm.bar_lkfull, step_par, 32);
           tc05::fence_after_sync();
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
@@ -990,20 +1003,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       // only run the epilogues.
       uint16_t* g_hi = reinterpret_cast<uint16_t*>(sm.A);  // [16-byte K chunk (16)][row (128)][8 halves], written by
       uint16_t* g_lo = g_hi + kRows * kE;                   // the attention epilogue (each thread re-reads its own part)
-      // logit keys of this instance -> registers now (L2 latency hidden behind the FFN); they are split into the
-      // fp16 hi | lo core-matrix tiles of the logits GEMM once the FFN has released the ring memory.
       const int R16 = ((N + 15) >> 4) << 4;  // rows of the logit-key tile = N of the logits MMA (multiple of 16)
-      float4 lkr[16];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = tid + i * kThreads, row = idx & 127, c8 = idx >> 7;
-        lkr[2 * i] = lkr[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < N) {
-          lkr[2 * i] = __ldg(reinterpret_cast<const float4*>(Lk + (size_t)row * kE) + c8 * 2);
-          lkr[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(Lk + (size_t)row * kE) + c8 * 2 + 1);
-        }
-      }
-
       const uint32_t tbase = sm.tmem_base;
       const uint32_t t_hacc = tbase, t_oacc = tbase + 256, t_hhi = tbase + 384, t_hlo = tbase + 448;
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -1042,6 +1042,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       }
       tc05::mbar_wait(&sm.bar_g2, 1, 32);  // GEMM2(3): FFN output complete, ring memory idle
       tc05::fence_after_sync();
+      if (tid == 0) tc05::mbar_arrive(&sm.bar_lkgo);  // the producer loads the packed logit keys under the epilogue below
       PHASE_STAMP(3);
       // ---- output epilogue (thread per row): g' = acc + b2 + g  ->  split -> TMEM as the A operand of the logits GEMM
       {
@@ -1073,168 +1074,180 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           tc05::tmem_st8(t_hlo + lane_base + (col0 >> 1), lo);
         }
       }
-      // logit keys -> fp16 hi | lo tiles [16-byte K chunk (16)][row (R16)][8 halves] at the start of the idle ring
-      {
-        uint16_t* lk_hi = reinterpret_cast<uint16_t*>(sm.Hb);
-        uint16_t* lk_lo = lk_hi + R16 * kE;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = tid + i * kThreads, row = idx & 127, c8 = idx >> 7;
-          if (row < R16) {
-            const float4 v0 = lkr[2 * i], v1 = lkr[2 * i + 1];
-            uint32_t h[4], l[4];
-            f16s_split2(v0.x, v0.y, kLkScale, h[0], l[0]); f16s_split2(v0.z, v0.w, kLkScale, h[1], l[1]);
-            f16s_split2(v1.x, v1.y, kLkScale, h[2], l[2]); f16s_split2(v1.z, v1.w, kLkScale, h[3], l[3]);
-            const int dst = c8 * (R16 * 8) + row * 8;
-            *reinterpret_cast<uint4*>(&lk_hi[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(&lk_lo[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
-          }
-        }
-      }
       tc05::tmem_wait_st();
-      tc05::fence_proxy_async();
       tc05::fence_before_sync();
       tc05::mbar_arrive(&sm.bar_lk);
       PHASE_STAMP(4);
 
-      // bias rows of this rollout (alpha . D[cur,:] + beta . Dur[cur,:]) -> registers while the logits MMAs run.
-      // Column groups of 16 are dealt round-robin to the two threads of a row (balanced for N not a multiple of 32).
-      float lv[64];
+      // bias rows of the rollouts (alpha . D[cur,:] + beta . Dur[cur,:]) -> fp32 tile in the Bs region (idle: the weight
+      // ring is drained, the logit keys sit in Hb) while the logits MMAs run: coalesced, one warp per 16 rollouts.
       {
-        const int row_s = (warp & 3) * 32 + lane;
-        const int cur_s = sm.cur[row_s];
+        float* btile = sm.Bs;
+#pragma unroll 2
+        for (int i = 0; i < 16; ++i) {
+          const int row_s = warp * 16 + i;
+          const int cur_s = sm.cur[row_s];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = (2 * q + colhalf) * 16 + i;
+          for (int cq = 0; cq < 4; ++cq) {
+            const int c = cq * 32 + lane;
             float bias = 0.f;
             if (c < N) {
               bias = __fmul_rn(p.w.alpha, D[cur_s * N + c]);
               if (kEnv == RRNCO_ENV_RCVRPTW) bias = __fadd_rn(bias, __fmul_rn(p.w.beta, U[cur_s * N + c]));
             }
-            lv[q * 16 + i] = bias;
+            btile[row_s * kLdA + c] = bias;
           }
         }
       }
+      cta_sync<kTc>();
       tc05::mbar_wait(&sm.bar_acc, tc_step_par, 32);
       tc_step_par ^= 1u;
       tc05::fence_after_sync();
-      // the logit-key tiles are dead: the producer may load the packed K / V tiles of the next decode step
-      if (tid == 0) tc05::mbar_arrive(&sm.bar_kvgo);
       PHASE_STAMP(5);
 
-      // ---- select epilogue, thread per row: two threads (column halves) own one rollout ----
-      // Straight-line and branch-free per element: the step loop's code is larger than the 32 KB L1.5 instruction
-      // cache, so every taken branch costs a fetch from L2 (stall_no_inst dominated the first version of this phase).
+      // ---- select epilogue, thread per row: two threads own one rollout, 16-column groups dealt round-robin ----
+      // Three rolled passes over the logits, which stay in TMEM (pass A rewrites them in place): the decode-step body is
+      // several times the instruction cache, so code size costs more than the extra TMEM round trips.
       {
         const int row = (warp & 3) * 32 + lane;
         const int64_t rg = (int64_t)(tile * kRows + (sm.active[row] ? row : 0)) * p.n_inst + b;
-        uint32_t mrow[4];
-        *reinterpret_cast<uint4*>(mrow) = *reinterpret_cast<const uint4*>(sm.mask[row]);
         const float inv_sqrt_e = 0.08838834764831845f * kUnscaleL;  // 1 / sqrt(128), and the operand scales undone
         const float clip = p.w.tanh_clipping;
         const int hsh = 16 * colhalf;  // this thread's columns: 32 q + hsh + i
+        const uint32_t t_l = t_hacc + lane_base + hsh;
+        const int nq = (R16 - hsh + 31) >> 5;  // 16-column groups of this thread (warp-uniform)
+        const float* brow = sm.Bs + row * kLdA + hsh;
+        // pass A: bias, clip, mask (decoder.py:198-204) -> TMEM, running maximum
         float mxl = -INFINITY;
         bool nan_seen = false;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int col0 = 32 * q + hsh;
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
           uint32_t v[16];
-          if (col0 < R16) {  // warp-uniform
-            tc05::tmem_ld16(t_hacc + lane_base + col0, v);
-            tc05::tmem_wait_ld();
+          tc05::tmem_ld16(t_l + 32 * q, v);
+          float bv[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bv[i]) = *reinterpret_cast<const float4*>(brow + 32 * q + i);
+          const uint32_t mq = sm.mask[row][q] >> hsh;  // mask bits of columns >= N are never set
+          tc05::tmem_wait_ld();
+          if (clip > 0.f) {
+            // clip * tanh(log u), u = exp(l - bias) + 1e-6 (decoder.py:198-201), as clip * (1 - 2 / (u^2 + 1)):
+            // two SFU operations per element instead of four (this pass is SFU-bound)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float l = __uint_as_float(v[i]) * inv_sqrt_e;
+              nan_seen |= !(fabsf(l) <= 3.0e38f);  // NaN, or an fp16 operand overflow (ffn_pack.cuh)
+              const float u = __fadd_rn(fexp(__fsub_rn(l, bv[i])), 1e-6f);
+              const float th = fmaf(-2.0f, rcpa(fmaf(u, u, 1.0f)), 1.0f);
+              v[i] = __float_as_uint(((mq >> i) & 1u) ? __fmul_rn(th, clip) : -INFINITY);
+            }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0u;
+            for (int i = 0; i < 16; ++i) {
+              float l = __uint_as_float(v[i]) * inv_sqrt_e;
+              nan_seen |= !(fabsf(l) <= 3.0e38f);
+              l = flog(__fadd_rn(fexp(__fsub_rn(l, bv[i])), 1e-6f));
+              v[i] = __float_as_uint(((mq >> i) & 1u) ? l : -INFINITY);
+            }
           }
-          const uint32_t mq = mrow[q] >> hsh;  // mask bits of columns >= N are never set
+          if (p.w.temperature != 1.0f) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float l = __uint_as_float(v[i]) * inv_sqrt_e;
-            nan_seen |= !(fabsf(l) <= 3.0e38f);  // NaN, or an fp16 operand overflow (ffn_pack.cuh)
-            l = flog(__fadd_rn(fexp(__fsub_rn(l, lv[q * 16 + i])), 1e-6f));  // decoder.py:198
-            if (clip > 0.f) l = __fmul_rn(ftanh(l), clip);
-            l = ((mq >> i) & 1u) ? l : -INFINITY;
-            lv[q * 16 + i] = l;
-            mxl = fmaxf(mxl, l);
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__fdiv_rn(__uint_as_float(v[i]), p.w.temperature));
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;  // the O tile of the next step's attention accumulates: zero it
-          tc05::tmem_st16(tbase + 384 + lane_base + colhalf * 64 + q * 16, v);
+          for (int i = 0; i < 16; ++i) mxl = fmaxf(mxl, __uint_as_float(v[i]));
+          tc05::tmem_st16(t_l + 32 * q, v);
         }
-        if (p.w.temperature != 1.0f) {
-          mxl = -INFINITY;
+        {  // the O tile of the next step's attention accumulates: zero it
+          uint32_t z[16];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            lv[i] = __fdiv_rn(lv[i], p.w.temperature);
-            mxl = fmaxf(mxl, lv[i]);
-          }
+          for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tc05::tmem_st16(tbase + 384 + lane_base + colhalf * 64 + q * 16, z);
         }
         tc05::tmem_wait_st();
         PHASE_STAMP(7);
         if (nan_seen) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
         sm.xf[0][colhalf][row] = mxl;
-        tc05::fence_before_sync();
         cta_sync<kTc>();
+        // bias tile and logit-key tiles are dead: the producer may load the packed K / V tiles of the next decode step
+        if (tid == 0) tc05::mbar_arrive(&sm.bar_kvgo);
         const float mx = fmaxf(sm.xf[0][0][row], sm.xf[0][1][row]);
+        // pass B: softmax denominator
         float sel = 0.f;
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
+          uint32_t v[16];
+          tc05::tmem_ld16(t_l + 32 * q, v);
+          tc05::tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 64; ++i) sel += fexp(lv[i] - mx);
+          for (int i = 0; i < 16; ++i) sel += fexp(__uint_as_float(v[i]) - mx);
+        }
         sm.xf[1][colhalf][row] = sel;
         cta_sync<kTc>();
         PHASE_STAMP(8);
         const float se = flog(sm.xf[1][0][row] + sm.xf[1][1][row]);
-        // log-softmax in the reference's order; argmax of log p (greedy / evaluate) or of log p + Gumbel noise
+        // pass C: log-softmax in the reference's order; argmax of log p (greedy) or of log p + Gumbel noise (sampling);
+        // evaluate: log p of the forced action
+        int forced = -1;
+        if (p.mode == RRNCO_DECODE_EVALUATE) {
+          forced = step < p.forced_T ? (int)p.forced[rg * p.forced_T + step] : 0;
+          forced = min(max(forced, 0), N - 1);
+        }
         float best = -INFINITY, bestlp = -INFINITY;
-        int besti = -1;  // local column 32 q + i, hsh is added below
-        if (p.mode == RRNCO_DECODE_SAMPLING) {
-          const uint2 key2 = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        int besti = 0x7fffffff;
+        const uint2 key2 = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
+          uint32_t v[16];
+          tc05::tmem_ld16(t_l + 32 * q, v);
+          tc05::tmem_wait_ld();
+          const int cbase = 32 * q + hsh;
+          if (p.mode == RRNCO_DECODE_SAMPLING) {
+#pragma unroll 1
+            for (int i4 = 0; i4 < 16; i4 += 4) {
+              const float4 gn = gumbel4(make_uint4((uint32_t)rg, (uint32_t)(rg >> 32), (uint32_t)step, (uint32_t)((cbase + i4) >> 2)), key2);
+              const float gv[4] = {gn.x, gn.y, gn.z, gn.w};
 #pragma unroll
-          for (int i4 = 0; i4 < 64; i4 += 4) {
-            const float4 gn = gumbel4(make_uint4((uint32_t)rg, (uint32_t)(rg >> 32), (uint32_t)step,
-                                                 (uint32_t)((32 * (i4 >> 4) + hsh + (i4 & 15)) >> 2)), key2);
+              for (int e = 0; e < 4; ++e) {
+                // v[] is indexed dynamically here only through the unrolled selects below
+                const uint32_t raw = i4 == 0 ? v[e] : i4 == 4 ? v[4 + e] : i4 == 8 ? v[8 + e] : v[12 + e];
+                const float lpv = __fsub_rn(__fsub_rn(__uint_as_float(raw), mx), se);
+                const float key = lpv + gv[e];
+                const bool better = key > best;
+                best = better ? key : best;
+                bestlp = better ? lpv : bestlp;
+                besti = better ? cbase + i4 + e : besti;
+              }
+            }
+          } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float lpv = __fsub_rn(__fsub_rn(lv[i4 + e], mx), se);
-              const float key = lpv + (e == 0 ? gn.x : e == 1 ? gn.y : e == 2 ? gn.z : gn.w);
-              const bool better = key > best;
-              best = better ? key : best;
-              bestlp = better ? lpv : bestlp;
-              besti = better ? 32 * (i4 >> 4) + (i4 & 15) + e : besti;
+            for (int i = 0; i < 16; ++i) {
+              const float lpv = __fsub_rn(__fsub_rn(__uint_as_float(v[i]), mx), se);
+              const bool better = lpv > best;
+              best = better ? lpv : best;
+              besti = better ? cbase + i : besti;
+              if (cbase + i == forced) bestlp = lpv;
             }
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float lpv = __fsub_rn(__fsub_rn(lv[i], mx), se);
-            lv[i] = lpv;
-            const bool better = lpv > best;
-            best = better ? lpv : best;
-            besti = better ? 32 * (i >> 4) + (i & 15) : besti;
-          }
-          bestlp = best;
         }
+        if (p.mode == RRNCO_DECODE_GREEDY) bestlp = best;
         sm.xf[2][colhalf][row] = best;
         sm.xf[0][colhalf][row] = bestlp;  // xf[0] (row maxima) was last read before the previous barrier
-        sm.xi[colhalf][row] = besti < 0 ? 0x7fffffff : besti + hsh;
+        sm.xi[colhalf][row] = besti;
         cta_sync<kTc>();
         PHASE_STAMP(9);
         int act = sm.xi[0][row];  // larger key wins, ties -> lower index
         int win = 0;
         if (sm.xf[2][1][row] > sm.xf[2][0][row] || (sm.xf[2][1][row] == sm.xf[2][0][row] && sm.xi[1][row] < act)) win = 1;
         act = sm.xi[win][row];
-        float chosen = sm.xf[0][win][row];
         if (act == 0x7fffffff) act = 0;
         if (p.mode == RRNCO_DECODE_EVALUATE) {
-          if (step < p.forced_T) act = (int)p.forced[rg * p.forced_T + step];
-          act = min(max(act, 0), N - 1);
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (32 * (i >> 4) + hsh + (i & 15) == act) sm.xchosen[row] = lv[i];
-          cta_sync<kTc>();
-          chosen = sm.xchosen[row];
+          act = forced;
+          win = (act >> 4) & 1;  // the half that owns the forced column recorded its log p
         }
+        const float chosen = sm.xf[0][win][row];
+        uint32_t mrow[4];
+        *reinterpret_cast<uint4*>(mrow) = *reinterpret_cast<const uint4*>(sm.mask[row]);
         PHASE_STAMP(10);
         if (colhalf == 0) {
           const bool feasible = (mrow[act >> 5] >> (act & 31)) & 1u;
