@@ -94,15 +94,57 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        """NVML from a Python thread (pynvml, ~20 Hz): no process start-up or driver re-initialisation inside the timed
+        region, which an `nvidia-smi -lms` child costs.  Falls back to that child if NVML cannot be loaded."""
+        self.rows, self.p, self.thread, self.stop_flag = [], None, None, False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML handle through the PCI bus id
+            bus = torch.cuda.get_device_properties(gpu_index)
+            h = None
+            try:
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{bus.pci_domain_id:08x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0")
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                          pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.05)
+            import threading
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.p = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                           "-i", str(gpu_index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.p = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.rows:
+                return out
+            sm = sorted(r[0] for r in self.rows)
+            bits = 0
+            for r in self.rows:
+                bits |= r[2]
+            # nvml.h: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "power_w_max": max(r[1] for r in self.rows),
+                        "reasons": [n for b, n in names.items() if bits & b], "samples": len(self.rows), "source": "nvml"})
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -122,6 +164,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         out["reasons"] = [n for i, n in enumerate(names) if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows)]
         out["samples"] = len(rows)
+        out["source"] = "nvidia-smi"
         return out
 
 
@@ -250,12 +293,18 @@ def run_ours(args, rank, world, local_rank):
         t0 = time.perf_counter()
         e0.record()
         last = None
+        marks = []
         for i in range(steps):
             last = fn(warmup + i)
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
         ms = max(e0.elapsed_time(e1), 0.0)
+        if rank == 0:  # per-step device times (diagnostic only, stderr)
+            ts = [e0.elapsed_time(m) for m in marks]
+            print(f"[bench] {fn.__name__}: per-step ms " + " ".join(f"{b - a:.1f}" for a, b in zip([0.0] + ts[:-1], ts)), file=sys.stderr)
         if isinstance(last, torch.Tensor) and not last.is_cuda:
             ms = max(ms, wall * 1e3)  # e2e ends with a host-visible result: the wall clock bounds it
         t = torch.tensor([ms], dtype=torch.float64, device=dev)

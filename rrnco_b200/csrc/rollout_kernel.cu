@@ -36,6 +36,7 @@ constexpr int kMaxState = 4;
 
 // per-phase cycle accumulator of CTA 0 (debug / profiling aid, read back with rrnco_debug_phase_cycles)
 __device__ long long g_phase_cycles[16];
+#ifdef RRNCO_PHASE_STAMPS
 #define PHASE_STAMP(i)                                   \
   do {                                                   \
     if (blockIdx.x == 0 && tid == 0) {                   \
@@ -44,6 +45,9 @@ __device__ long long g_phase_cycles[16];
       phase_t0 = now_;                                   \
     }                                                    \
   } while (0)
+#else  // each stamp is a global read-modify-write on the critical warp: compiled out of the product build
+#define PHASE_STAMP(i) do { } while (0)
+#endif
 
 struct RolloutParams {
   int N, NT, S, n_tiles, n_state;
@@ -121,6 +125,7 @@ struct Smem {
   float xf[3][2][kRows];
   int xi[2][kRows];
   float xchosen[kRows];
+  uint32_t lhmask[4];     // rcvrptw: nodes with linehaul demand (bitset)
   float xsum[kH][kRows];  // tcgen05 attention: softmax denominators (written and read by the same thread)
   // tcgen05 FFN pipeline
   uint64_t bar_full[kFStages];
@@ -308,6 +313,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     }
     sm.dem[n] = dem; sm.demb[n] = demb; sm.tw0[n] = tw0; sm.tw1[n] = tw1; sm.svc[n] = svc;
     sm.dj0[n] = dj0; sm.uj0[n] = uj0;
+    const uint32_t lh = __ballot_sync(0xffffffffu, kEnv == RRNCO_ENV_RCVRPTW && dem > 0.f);
+    if (lane == 0) sm.lhmask[warp] = lh;
   }
   __syncthreads();
 
@@ -584,8 +591,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     }
     kv_prefetched = false;
 
-    // ---- A1: action mask bitsets (row-owner quads) ---------------------------------------------
-    if (!p.logits_only) {
+    // ---- A1: action mask bitsets (row-owner quads; the tcgen05 variant computes them in its phase A below) ----
+    if (!kTc && !p.logits_only) {
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int row = rr ? r1 : r0;
@@ -653,14 +660,16 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       }
     }
     if (kTc) {
-      // ---- A2 (tcgen05): query rows -> fp16 hi | lo core-matrix tiles (A operand of Q K^T) in the A region.
-      // lane = (row of the warp's 16, 64-wide half of the embedding): conflict-free 16-byte tile stores.
+      // ---- A (tcgen05): lane = (rollout of the warp's 16, 64-wide half of the columns): the action-mask words of
+      // that half, then the query rows -> fp16 hi | lo core-matrix tiles (A operand of Q K^T) in the A region with
+      // conflict-free 16-byte tile stores.  The query source rows are requested first: their L2 latency hides under the mask.
       {
         uint16_t* q_hi = reinterpret_cast<uint16_t*>(sm.A);
         uint16_t* q_lo = q_hi + kRows * kE;
         const int row = warp * 16 + (lane & 15), dh = lane >> 4;
         const int cur = sm.cur[row];
         float st[kMaxState] = {0.f, 0.f, 0.f, 0.f};
+        const float f0 = sm.f[0][row], f1 = sm.f[1][row], f2 = sm.f[2][row], f3 = sm.f[3][row];
         const float* src1;
         const float* src2 = nullptr;
         if (kEnv == RRNCO_ENV_ATSP) {
@@ -673,29 +682,92 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         } else {
           src1 = P1 + (size_t)cur * kE;
           if (kEnv == RRNCO_ENV_RCVRP) {
-            st[0] = __fsub_rn(cap, sm.f[0][row]);
+            st[0] = __fsub_rn(cap, f0);
           } else {
-            const float used = sm.f[3][row] == 0.f ? sm.f[2][row] : sm.f[3][row];
+            const float used = f3 == 0.f ? f2 : f3;
             st[0] = __fsub_rn(cap, used);
-            st[1] = sm.f[0][row];
+            st[1] = f0;
             st[2] = closed == 0.f ? 1.f : 0.f;
-            float rem = __fsub_rn(limit, sm.f[1][row]);  // nan_to_num(limit - route, posinf=10)
+            float rem = __fsub_rn(limit, f1);  // nan_to_num(limit - route, posinf=10)
             rem = rem == INFINITY ? 10.f : (rem != rem ? 0.f : (rem == -INFINITY ? -3.4028234663852886e38f : rem));
             st[3] = rem;
           }
         }
+        float4 pq[16];
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+          pq[cc] = *reinterpret_cast<const float4*>(src1 + dh * 64 + cc * 4);
+          if (kEnv == RRNCO_ENV_ATSP && src2) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(src2 + dh * 64 + cc * 4));
+            pq[cc] = make_float4(pq[cc].x + w.x, pq[cc].y + w.y, pq[cc].z + w.z, pq[cc].w + w.w);
+          }
+        }
+        // action mask (rcvrp/env.py:183-195, rmtvrp/env.py:343-428, atsp/env.py:107-111): words 2 dh, 2 dh + 1
+        uint32_t bits2[2];
+        {
+          const uint2 visw = *reinterpret_cast<const uint2*>(&sm.vis[row][2 * dh]);
+          bool missing = false, carrying_b = false;
+          if (kEnv == RRNCO_ENV_RCVRPTW) {
+            uint32_t m = (sm.lhmask[2 * dh] & ~visw.x) | (sm.lhmask[2 * dh + 1] & ~visw.y);
+            m |= __shfl_xor_sync(0xffffffffu, m, 16);
+            missing = m != 0u;  // linehauls_missing
+            carrying_b = sm.demb[cur] > 0.f;
+          }
+#pragma unroll 1
+          for (int k = 0; k < 2; ++k) {
+            const int c0 = 64 * dh + 32 * k;
+            const uint32_t valid = N >= c0 + 32 ? 0xffffffffu : (N > c0 ? (1u << (N - c0)) - 1u : 0u);
+            uint32_t ok = ~(k ? visw.y : visw.x) & valid;
+            if (kEnv == RRNCO_ENV_RCVRP) {
+              uint32_t bad = 0u;
+#pragma unroll 8
+              for (int i = 0; i < 32; ++i) bad |= (__fadd_rn(sm.dem[c0 + i], f0) > cap ? 1u : 0u) << i;
+              ok &= ~bad;
+            } else if (kEnv == RRNCO_ENV_RCVRPTW) {
+              uint32_t good = 0u;
+#pragma unroll 2
+              for (int i = 0; i < 32; ++i) {
+                const int c = c0 + i;
+                if (c < N) {
+                  const float dist_ij = D[cur * N + c], dur_ij = U[cur * N + c];
+                  const float arrival = __fadd_rn(f0, dur_ij);
+                  const bool reach_c = arrival < sm.tw1[c];
+                  const bool reach_d =
+                      __fmul_rn(__fadd_rn(__fadd_rn(fmaxf(arrival, sm.tw0[c]), sm.svc[c]), sm.uj0[c]), closed) < sm.tw1[0];
+                  const bool exc_lim = __fadd_rn(__fadd_rn(f1, dist_ij), __fmul_rn(sm.dj0[c], closed)) > limit;
+                  const bool exc_l = __fadd_rn(sm.dem[c], f2) > cap;
+                  const bool exc_b = __fadd_rn(sm.demb[c], f3) > cap;
+                  const bool ok1 = (missing && !exc_l && !carrying_b && sm.dem[c] > 0.f) || (!exc_b && sm.demb[c] > 0.f);
+                  const bool cannot_l = sm.dem[c] > __fsub_rn(cap, f3);
+                  const bool ok2 = !exc_l && !exc_b && !cannot_l;
+                  const bool okc = (bclass == 1.0f && ok1) || (bclass == 2.0f && ok2);
+                  good |= (reach_c && reach_d && okc && !exc_lim ? 1u : 0u) << i;
+                }
+              }
+              ok &= good;
+            }
+            if (kEnv != RRNCO_ENV_ATSP && c0 == 0) ok &= ~1u;  // the depot bit is decided below
+            bits2[k] = ok;
+          }
+          if (kEnv != RRNCO_ENV_ATSP) {
+            uint32_t any_cust = bits2[0] | bits2[1];
+            any_cust |= __shfl_xor_sync(0xffffffffu, any_cust, 16);
+            if (dh == 0 && !(cur == 0 && any_cust != 0u)) bits2[0] |= 1u;
+          }
+          uint32_t tot = bits2[0] | bits2[1];
+          tot |= __shfl_xor_sync(0xffffffffu, tot, 16);
+          if (tot == 0u && dh == 0) {  // cannot happen upstream; keep the math finite
+            if (sm.active[row] && !sm.done[row]) atomicOr(p.status, RRNCO_DEV_NO_FEASIBLE);
+            bits2[0] |= 1u;
+          }
+          *reinterpret_cast<uint2*>(&sm.mask[row][2 * dh]) = make_uint2(bits2[0], bits2[1]);
+        }
+        PHASE_STAMP(15);
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
           const int c8 = dh * 8 + cc;
-          float4 v0 = *reinterpret_cast<const float4*>(src1 + c8 * 8), v1 = *reinterpret_cast<const float4*>(src1 + c8 * 8 + 4);
-          if (kEnv == RRNCO_ENV_ATSP) {
-            if (src2) {
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(src2 + c8 * 8));
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(src2 + c8 * 8 + 4));
-              v0 = make_float4(v0.x + w0.x, v0.y + w0.y, v0.z + w0.z, v0.w + w0.w);
-              v1 = make_float4(v1.x + w1.x, v1.y + w1.y, v1.z + w1.z, v1.w + w1.w);
-            }
-          } else {
+          float4 v0 = pq[2 * cc], v1 = pq[2 * cc + 1];
+          if (kEnv != RRNCO_ENV_ATSP) {
 #pragma unroll
             for (int k = 0; k < kMaxState; ++k) {
               if (k < p.n_state) {

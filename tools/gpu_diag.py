@@ -220,10 +220,10 @@ def diag_speed(name="rcvrp", B=256, n=100, A=1):
         out = pol(td0, env, phase="val", decode_type="multistart_greedy", num_starts=S)
         torch.cuda.synchronize()
         L.rrnco_debug_phase_cycles(buf, 0)
-        cyc = [c / max(T - 1, 1) for c in list(buf)[:15]]
-        names = ["mask+q+KVwait", "attention", "ffn:convert", "ffn:gemm+epi1", "ffn:out-epi", "logits gemm", "transition+tail",
+        cyc = [c / max(T - 1, 1) for c in list(buf)[:16]]
+        names = ["q+sync", "attention", "ffn:convert", "ffn:gemm+epi1", "ffn:out-epi", "logits gemm", "transition+tail",
                  "sel:tmem+bias+clip", "sel:softmax-sum", "sel:argmax", "sel:chosen",
-                 "att:wait-scores", "att:max-pass", "att:exp-pass", "att:wait-PV"]
+                 "att:wait-scores", "att:max-pass", "att:exp-pass", "att:wait-PV", "top+mask"]
         print("   cycles/step (CTA 0): " + ", ".join(f"{n}={c:.0f}" for n, c in zip(names, cyc)) + f"  total={sum(cyc):.0f}")
         print(f"  passes={passes}: {dt*1e3:.1f} ms for {B} instances x {S} starts, T={T} -> {B/dt:.0f} inst/s; "
               f"per CTA-step {dt/ (B*T/148) *1e6:.1f} us")
