@@ -23,6 +23,7 @@
 namespace rrnco {
 
 constexpr int kThreads = 256;      // compute threads (8 warps)
+constexpr int kPvLanes = 1;         // lanes per split term issuing the P V MMAs of a head (K steps dealt round-robin)
 constexpr int kThreadsTc = 384;    // tcgen05 variant: + warp 8 (TMA producer) + warps 9-11 (MMA issue, one per split term)
 constexpr int kRows = 128;   // rollouts per CTA tile
 constexpr int kLdA = 132;    // fp32 row stride of the activation tiles (bank-conflict-free fragments)
@@ -47,6 +48,22 @@ __device__ long long g_phase_cycles[16];
   } while (0)
 #else  // each stamp is a global read-modify-write on the critical warp: compiled out of the product build
 #define PHASE_STAMP(i) do { } while (0)
+#endif
+
+#ifdef RRNCO_PHASE_STAMPS
+// event timeline of CTA 0 at decode step kTlStep (development aid): (tag, clock64) pairs
+__device__ long long g_tl[512];
+__device__ int g_tl_n;
+constexpr int kTlStep = 6;
+#define TL(stepvar, tag)                                           \
+  do {                                                             \
+    if (blockIdx.x == 0 && (stepvar) == kTlStep) {                 \
+      const int i_ = atomicAdd(&g_tl_n, 1);                        \
+      if (i_ < 256) { g_tl[2 * i_] = (tag); g_tl[2 * i_ + 1] = clock64(); } \
+    }                                                              \
+  } while (0)
+#else
+#define TL(stepvar, tag) do { } while (0)
 #endif
 
 struct RolloutParams {
@@ -134,6 +151,7 @@ struct Smem {
   uint64_t bar_kvgo;    // compute -> producer: the ring memory is free, load the packed K / V tiles of the next step
   uint64_t bar_kv;      // TMA -> issuers: packed K / V tiles landed
   uint64_t bar_q;       // compute -> issuers: query tiles written (256 arrivals; also the exit signal)
+  uint64_t bar_qkdone;  // issuers -> producer: every Q K^T of the step complete, the K tiles are dead (8 commits)
   uint64_t bar_s[kH];   // issuers -> compute: scores of head h in TMEM
   uint64_t bar_p[kH];   // compute -> issuers: probabilities of head h written in place (128 arrivals)
   uint64_t bar_o[kH];   // issuers -> compute: P V of head h complete
@@ -142,7 +160,6 @@ struct Smem {
   uint64_t bar_epi;     // compute -> issuers: epilogue 1 done (A operand of GEMM2 in TMEM, accumulator re-zeroed)
   uint64_t bar_g2;      // issuers -> compute: GEMM2 of a chunk complete (its A operand may be overwritten)
   uint64_t bar_lk;      // compute -> issuers: g' (A operand of the logits GEMM) written to TMEM
-  uint64_t bar_lkgo;    // compute -> producer: FFN complete, the ring memory may take the packed logit-key tiles
   uint64_t bar_lkfull;  // TMA -> issuers: packed logit-key tiles landed
   uint64_t bar_acc;     // issuers -> compute: logits complete
   uint32_t tmem_base;
@@ -259,6 +276,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     bclass = p.d.backhaul_class[drow];
   }
 
+  if (tid == 0) TL(kTlStep, 200);  // kernel start
   // ---------------- one-time staging ----------------
   if (kTc) {
     if (warp == 0) tc05::tmem_alloc(&sm.tmem_base, 512);
@@ -271,10 +289,11 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       tc05::mbar_init(&sm.bar_kvgo, 1);
       tc05::mbar_init(&sm.bar_kv, 1);
       tc05::mbar_init(&sm.bar_q, kThreads);
+      tc05::mbar_init(&sm.bar_qkdone, kH);
       for (int i = 0; i < kH; ++i) {
         tc05::mbar_init(&sm.bar_s[i], 1);
         tc05::mbar_init(&sm.bar_p[i], kThreads / 2);
-        tc05::mbar_init(&sm.bar_o[i], kPasses);
+        tc05::mbar_init(&sm.bar_o[i], kPvLanes * kPasses);
       }
       tc05::mbar_init(&sm.bar_gready, kThreads);
       tc05::mbar_init(&sm.bar_h[0], kPasses);
@@ -282,7 +301,6 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       tc05::mbar_init(&sm.bar_epi, kThreads);
       tc05::mbar_init(&sm.bar_g2, kPasses);
       tc05::mbar_init(&sm.bar_lk, kThreads);
-      tc05::mbar_init(&sm.bar_lkgo, 1);
       tc05::mbar_init(&sm.bar_lkfull, 1);
       tc05::mbar_init(&sm.bar_acc, kPasses);
       tc05::fence_mbar_init();
@@ -318,6 +336,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
   }
   __syncthreads();
 
+  if (tid == 0) TL(kTlStep, 201);  // staging done
   // ---------------- rollout state init ----------------
   const int num_loc = kEnv == RRNCO_ENV_ATSP ? N : N - 1;
   if (tid < kRows) {
@@ -361,6 +380,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     // every decode step, because the FFN weight ring needs the same shared memory in between.
     //   K: [hi | lo][16-byte K chunk c8 (16)][key (R16)][8 halves]            B operand of Q K^T, head h = chunks 2h, 2h+1
     //   V: [hi | lo][head (8)][key chunk (R16 / 8)][dim (16)][8 halves]       B operand (V_h^T, K-major) of P V
+    if (tid == 0) TL(kTlStep, 202);  // state init done
     const int R16p = ((N + 15) >> 4) << 4;
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -409,6 +429,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     __syncthreads();
     tc05::fence_after_sync();
     if (tid == 0) tc05::mbar_arrive(&sm.bar_kvgo);
+    if (tid == 0) TL(kTlStep, 203);  // K / V / Lk packed
     if (warp == 8) {
       // ===== TMA producer warp.  Per decode step: the packed K / V tiles (as soon as the previous step's logits have
       // released the Hb | Bs regions), then -- once the attention is done with them -- the 16 packed 32 KB FFN weight
@@ -423,17 +444,23 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           tc05::mbar_arrive_expect_tx(&sm.bar_kv, 2 * kv_bytes);
           tc05::bulk_g2s(ring, slot, kv_bytes, &sm.bar_kv);
           tc05::bulk_g2s(ring + kKvOffV, slot + kKvOffV, kv_bytes, &sm.bar_kv);
-          tc05::mbar_wait(&sm.bar_go, go_phase, 64);
-          go_phase ^= 1u;
+          // Weight slices 0 and 1 land in ring stages that overlap only the K tiles: they start as soon as the last
+          // Q K^T has completed, i.e. under the softmax / P V of the last heads.  The rest waits for the V tiles to die.
+          tc05::mbar_wait(&sm.bar_qkdone, go_phase, 64);
           if (sm.exit_flag) break;
+#pragma unroll 1
           for (int s = 0; s < kFSlices; ++s, ++sl) {
+            if (s == 2) tc05::mbar_wait(&sm.bar_go, go_phase, 64);
             const int st = sl & (kFStages - 1);
-            if (sl >= kFStages) tc05::mbar_wait(&sm.bar_empty[st], ((sl / kFStages) - 1) & 1, 64);
+            if (sl >= kFStages) tc05::mbar_wait(&sm.bar_empty[st], ((sl / kFStages) - 1) & 1);
             tc05::mbar_arrive_expect_tx(&sm.bar_full[st], kFSliceBytes);
             tc05::bulk_g2s(ring + (size_t)st * kFSliceBytes, p.ffn_packed + (size_t)s * kFSliceBytes, kFSliceBytes,
                            &sm.bar_full[st]);
           }
-          tc05::mbar_wait(&sm.bar_lkgo, go_phase ^ 1u, 64);  // every weight slice consumed: logit keys -> ring start
+          go_phase ^= 1u;
+          // logit keys -> ring start (stages 0 and 1) as soon as the weight slices 12 and 13 held there are consumed
+          tc05::mbar_wait(&sm.bar_empty[(sl - 4) & (kFStages - 1)], (((sl - 4) / kFStages)) & 1);
+          tc05::mbar_wait(&sm.bar_empty[(sl - 3) & (kFStages - 1)], (((sl - 3) / kFStages)) & 1);
           tc05::mbar_arrive_expect_tx(&sm.bar_lkfull, kv_bytes);
           tc05::bulk_g2s(ring, slot + kKvOffLk, kv_bytes, &sm.bar_lkfull);
         }
@@ -465,9 +492,12 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       const uint32_t kv_var = (uint32_t)R16i * 256u;  // bytes of one hi / lo variant of the K (or V) tiles
       const uint32_t lk_addr = ring_addr + (term == 2 ? kv_var : 0);  // Lk_hi | Lk_lo
       uint32_t step_par = 0, epi_phase = 0, sl = 0;
+      int istep = -1;
       while (true) {
         tc05::mbar_wait(&sm.bar_q, step_par, 32);
         if (sm.exit_flag) break;
+        ++istep;
+        if (lane == 0) TL(istep, 100 + term);  // Q ready seen
         tc05::mbar_wait(&sm.bar_kv, step_par, 32);
         tc05::fence_after_sync();
 #pragma unroll 1
@@ -483,23 +513,30 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
               tc05::mma_ss_f16(t_s, q_hi, tc05::make_desc(kh + kv_var, lbo_l, kSbo), idesc_l, 1u);
             }
             tc05::commit(&sm.bar_s[h]);
+            tc05::commit(&sm.bar_qkdone);
+            TL(istep, 110 + h);  // QK(h) issued
           }
           __syncwarp();
           tc05::mbar_wait(&sm.bar_p[h], step_par, 32);
           tc05::fence_after_sync();
-          if (lane < kPasses) {
+          if (lane == 0) TL(istep, 120 + h);  // P(h) seen
+          if (lane < kPvLanes * kPasses) {
+            // lane = (split term, K-step residue): issue latency, not tensor time, bounds these small MMAs
+            const int pterm = lane % kPasses, jres = lane / kPasses;
             // V_h^T tile: 16 dims x keys, K-major: 256 B between 16-byte key chunks, 128 B between 8-dim groups
-            const uint32_t vh = ring_addr + kKvOffV + (lane == 2 ? kv_var : 0) + h * (R16i * 32);
-            const uint32_t ph = t_s + (lane == 1 ? 8 : 0);  // P_hi at columns 16 j, P_lo at 16 j + 8
-            for (int j = 0; j < (R16i >> 4); ++j)
+            const uint32_t vh = ring_addr + kKvOffV + (pterm == 2 ? kv_var : 0) + h * (R16i * 32);
+            const uint32_t ph = t_s + (pterm == 1 ? 8 : 0);  // P_hi at columns 16 j, P_lo at 16 j + 8
+            for (int j = jres; j < (R16i >> 4); j += kPvLanes)
               tc05::mma_ts_f16(tb + 384 + 16 * h, ph + 16 * j, tc05::make_desc(vh + j * 512, 256, kSbo), idesc_pv, 1u);
             tc05::commit(&sm.bar_o[h]);
+            if (lane == 0) TL(istep, 130 + h);  // PV(h) issued
           }
           __syncwarp();
         }
         if (lane == 0 && term < kPasses) {
           tc05::mbar_wait(&sm.bar_gready, step_par, 32);
           tc05::fence_after_sync();
+          TL(istep, 140 + term);  // glimpse seen
 #pragma unroll 1
           for (int j = 0; j < 8; ++j) {
             const int c = ffn_job_chunk(j), half = ffn_job_half(j);
@@ -511,7 +548,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
 #pragma unroll 1
             for (int sj = 0; sj < kFSlicesPerJob; ++sj, ++sl) {
               const int st = sl & (kFStages - 1);
-              tc05::mbar_wait(&sm.bar_full[st], (sl / kFStages) & 1, 32);
+              tc05::mbar_wait(&sm.bar_full[st], (sl / kFStages) & 1);
               tc05::fence_after_sync();
               const uint32_t b_addr = ring_addr + st * kFSliceBytes + b_var;
 #pragma unroll
@@ -528,6 +565,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
               tc05::commit(&sm.bar_empty[st]);
             }
             tc05::commit(half == 0 ? &sm.bar_h[c & 1] : &sm.bar_g2);
+            if (term == 0) TL(istep, 150 + j);  // FFN job j issued
           }
           // pointer logits: D[128 x R16] = g'(hi | lo, TMEM) . Lk(hi | lo, shared memory)^T, 8 K steps
           tc05::mbar_wait(&sm.bar_lk, step_par, 32);
@@ -539,6 +577,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             tc05::mma_ts_f16(t_hacc0, t_a + ks * 8, bdesc, idesc_l, 1u);
           }
           tc05::commit(&sm.bar_acc);
+          if (term == 0) TL(istep, 160);  // logits issued
         }
         __syncwarp();
         step_par ^= 1u;
@@ -564,6 +603,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     cta_sync<kTc>();
     tc05::fence_after_sync();
   }
+  if (tid == 0) TL(kTlStep, 204);  // TMEM zeroed, entering the step loop
   long long phase_t0 = clock64();
   const int r0 = warp * 16 + g, r1 = r0 + 8;  // rows owned by this quad in the row-owner phases
   const int wm = warp >> 1, wn = warp & 1;    // FFN warp grid 4 (M) x 2 (N): 32 x 64 warp tiles
@@ -660,6 +700,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       }
     }
     if (kTc) {
+      if (tid == 0) TL(step, 1);  // step start (after the all-done vote)
       // ---- A (tcgen05): lane = (rollout of the warp's 16, 64-wide half of the columns): the action-mask words of
       // that half, then the query rows -> fp16 hi | lo core-matrix tiles (A operand of Q K^T) in the A region with
       // conflict-free 16-byte tile stores.  The query source rows are requested first: their L2 latency hides under the mask.
@@ -693,17 +734,9 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             st[3] = rem;
           }
         }
-        float4 pq[16];
-#pragma unroll
-        for (int cc = 0; cc < 16; ++cc) {
-          pq[cc] = *reinterpret_cast<const float4*>(src1 + dh * 64 + cc * 4);
-          if (kEnv == RRNCO_ENV_ATSP && src2) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(src2 + dh * 64 + cc * 4));
-            pq[cc] = make_float4(pq[cc].x + w.x, pq[cc].y + w.y, pq[cc].z + w.z, pq[cc].w + w.w);
-          }
-        }
         // action mask (rcvrp/env.py:183-195, rmtvrp/env.py:343-428, atsp/env.py:107-111): words 2 dh, 2 dh + 1
         uint32_t bits2[2];
+        float4 pq[16];
         {
           const uint2 visw = *reinterpret_cast<const uint2*>(&sm.vis[row][2 * dh]);
           bool missing = false, carrying_b = false;
@@ -712,6 +745,16 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
             m |= __shfl_xor_sync(0xffffffffu, m, 16);
             missing = m != 0u;  // linehauls_missing
             carrying_b = sm.demb[cur] > 0.f;
+          }
+            // query source rows: requested after every shared-memory read above has been consumed, so that the mask loop
+            // below does not wait on their scoreboard
+  #pragma unroll
+          for (int cc = 0; cc < 16; ++cc) {
+            pq[cc] = *reinterpret_cast<const float4*>(src1 + dh * 64 + cc * 4);
+            if (kEnv == RRNCO_ENV_ATSP && src2) {
+              const float4 w = __ldg(reinterpret_cast<const float4*>(src2 + dh * 64 + cc * 4));
+              pq[cc] = make_float4(pq[cc].x + w.x, pq[cc].y + w.y, pq[cc].z + w.z, pq[cc].w + w.w);
+            }
           }
 #pragma unroll 1
           for (int k = 0; k < 2; ++k) {
@@ -791,6 +834,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       tc05::fence_proxy_async();
       tc05::fence_before_sync();
       tc05::mbar_arrive(&sm.bar_q);
+      if (tid == 0) TL(step, 2);  // mask + query done
       cta_sync<kTc>();  // action-mask bitsets visible to the row-owner threads
       PHASE_STAMP(0);
 
@@ -811,8 +855,10 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         for (int j = 0; j < 4; ++j) {
           const int h = 4 * grp + j, k = 2 * j + grp;
           const uint32_t t_s = tb + (uint32_t)(k % 3) * 128u + lane_b;
+          if ((tid & 127) == 0) TL(step, 10 + h);  // group waits for scores h
           tc05::mbar_wait(&sm.bar_s[h], tc_step_par, 20);
           tc05::fence_after_sync();
+          if ((tid & 127) == 0) TL(step, 20 + h);  // scores h seen
           PHASE_STAMP(11);
           // pass 1: row maximum over the feasible keys (four independent partial maxima)
           float vm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -858,12 +904,14 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           tc05::tmem_wait_st();
           tc05::fence_before_sync();
           tc05::mbar_arrive(&sm.bar_p[h]);
+          if ((tid & 127) == 0) TL(step, 30 + h);  // P(h) written
           PHASE_STAMP(13);
         }
         // every P V complete (all eight: the score buffers are zeroed and the K / V memory handed over below)
 #pragma unroll 1
         for (int h = 0; h < kH; ++h) tc05::mbar_wait(&sm.bar_o[h], tc_step_par, 20);
         tc05::fence_after_sync();
+        if ((tid & 127) == 0) TL(step, 40 + grp);  // all PV seen
         PHASE_STAMP(14);
         // glimpse = heads / sum + q (decoder.py:292-293) -> fp16 hi | lo tiles of the FFN, in place over the query tiles
         uint16_t* g_hi = reinterpret_cast<uint16_t*>(sm.A);
@@ -907,6 +955,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       tc05::fence_before_sync();
       tc05::mbar_arrive(&sm.bar_go);      // K / V tiles are dead: the producer starts this step's weight stream
       tc05::mbar_arrive(&sm.bar_gready);  // glimpse tiles written: GEMM1 may start
+      if ((tid & 127) == 0) TL(step, 42 + (warp >> 2));  // glimpse written
       PHASE_STAMP(1);
     } else {
       // ---- A2: query rows q = ctx_node_proj[cur] (+ proj2[...]) + sum_k state_k * wstate[k] ------
@@ -1085,6 +1134,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       for (int c = 0; c < 4; ++c) {
         // hidden chunk c: + b1, relu, split -> A operand (hi | lo, fp16) of GEMM2 in tensor memory
         tc05::mbar_wait(&sm.bar_h[c & 1], (c >> 1) & 1, 32);
+        if (tid == 0) TL(step, 50 + c);  // hidden chunk c seen
         if (c > 0) tc05::mbar_wait(&sm.bar_g2, (c - 1) & 1, 32);  // GEMM2(c - 1) has consumed the previous A operand
         tc05::fence_after_sync();
         const uint32_t t_h = t_hacc + (c & 1) * 128;
@@ -1111,10 +1161,11 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         tc05::tmem_wait_st();
         tc05::fence_before_sync();
         tc05::mbar_arrive(&sm.bar_epi);
+        if (tid == 0) TL(step, 54 + c);  // epilogue 1 of chunk c done
       }
       tc05::mbar_wait(&sm.bar_g2, 1, 32);  // GEMM2(3): FFN output complete, ring memory idle
       tc05::fence_after_sync();
-      if (tid == 0) tc05::mbar_arrive(&sm.bar_lkgo);  // the producer loads the packed logit keys under the epilogue below
+      if (tid == 0) TL(step, 58);  // FFN output seen
       PHASE_STAMP(3);
       // ---- output epilogue (thread per row): g' = acc + b2 + g  ->  split -> TMEM as the A operand of the logits GEMM
       {
@@ -1149,13 +1200,14 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       tc05::tmem_wait_st();
       tc05::fence_before_sync();
       tc05::mbar_arrive(&sm.bar_lk);
+      if (tid == 0) TL(step, 59);  // g' written
       PHASE_STAMP(4);
 
       // bias rows of the rollouts (alpha . D[cur,:] + beta . Dur[cur,:]) -> fp32 tile in the Bs region (idle: the weight
       // ring is drained, the logit keys sit in Hb) while the logits MMAs run: coalesced, one warp per 16 rollouts.
       {
         float* btile = sm.Bs;
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < 16; ++i) {
           const int row_s = warp * 16 + i;
           const int cur_s = sm.cur[row_s];
@@ -1175,6 +1227,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       tc05::mbar_wait(&sm.bar_acc, tc_step_par, 32);
       tc_step_par ^= 1u;
       tc05::fence_after_sync();
+      if (tid == 0) TL(step, 60);  // logits seen
       PHASE_STAMP(5);
 
       // ---- select epilogue, thread per row: two threads own one rollout, 16-column groups dealt round-robin ----
@@ -1307,6 +1360,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         sm.xf[0][colhalf][row] = bestlp;  // xf[0] (row maxima) was last read before the previous barrier
         sm.xi[colhalf][row] = besti;
         cta_sync<kTc>();
+        if (tid == 0) TL(step, 63);  // select passes done
         PHASE_STAMP(9);
         int act = sm.xi[0][row];  // larger key wins, ties -> lower index
         int win = 0;
@@ -1662,8 +1716,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     }
     tc05::fence_before_sync();
     cta_sync<kTc>();
-    tc05::mbar_arrive(&sm.bar_go);  // releases the producer warp and the MMA-issue warps (they see exit_flag)
-    tc05::mbar_arrive(&sm.bar_q);
+    if (tid < kH) tc05::mbar_arrive(&sm.bar_qkdone);  // releases the producer warp ...
+    tc05::mbar_arrive(&sm.bar_q);                     // ... and the MMA-issue warps (both see exit_flag)
     if (warp == 0) tc05::tmem_dealloc(sm.tmem_base, 512);
   }
 }
@@ -1733,6 +1787,20 @@ static int phase_cycles_local(long long* h_out, int reset) {
 
 #ifdef RRNCO_BUILD_TC
 int phase_cycles_tc(long long* h_out, int reset) { return phase_cycles_local(h_out, reset); }
+// development aid: (tag, clock) event pairs of CTA 0 at decode step kTlStep (RRNCO_PHASE_STAMPS builds only)
+int timeline_tc(long long* h_out, int* n_out) {
+#ifdef RRNCO_PHASE_STAMPS
+  int zero = 0;
+  if (cudaMemcpyFromSymbol(h_out, g_tl, sizeof(long long) * 512) != cudaSuccess) return RRNCO_ERR_CUDA;
+  if (cudaMemcpyFromSymbol(n_out, g_tl_n, sizeof(int)) != cudaSuccess) return RRNCO_ERR_CUDA;
+  if (cudaMemcpyToSymbol(g_tl_n, &zero, sizeof(int)) != cudaSuccess) return RRNCO_ERR_CUDA;
+  return RRNCO_OK;
+#else
+  (void)h_out;
+  *n_out = 0;
+  return RRNCO_ERR_UNSUPPORTED;
+#endif
+}
 int dispatch_env_tc(const RolloutParams& p, int env, int passes, cudaStream_t st) {
   switch (env) {
     case RRNCO_ENV_ATSP: return dispatch_rollout<RRNCO_ENV_ATSP, true>(p, passes, st);
@@ -1745,6 +1813,7 @@ int dispatch_env_tc(const RolloutParams& p, int env, int passes, cudaStream_t st
 #else
 int dispatch_env_tc(const RolloutParams& p, int env, int passes, cudaStream_t st);  // rollout_kernel_tc.cu
 int phase_cycles_tc(long long* h_out, int reset);
+int timeline_tc(long long* h_out, int* n_out);
 
 int dispatch_env(const RolloutParams& p, int env, int passes, cudaStream_t st) {
   switch (env) {
@@ -1789,6 +1858,9 @@ extern "C" {
 int rrnco_debug_phase_cycles(long long* h_out, int reset) {
   return g_engine == 1 ? phase_cycles_tc(h_out, reset) : phase_cycles_local(h_out, reset);
 }
+
+// debug: event timeline of the tcgen05 variant (512 int64 = 256 (tag, clock) pairs); development builds only
+int rrnco_debug_timeline(long long* h_out, int* n_out) { return timeline_tc(h_out, n_out); }
 
 // precision of the in-kernel contractions: 3 = 3xTF32 (fp32-faithful, default), 1 = single TF32 pass
 int rrnco_set_precision(int32_t passes) {
