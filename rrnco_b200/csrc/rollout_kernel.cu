@@ -860,30 +860,27 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           tc05::fence_after_sync();
           if ((tid & 127) == 0) TL(step, 20 + h);  // scores h seen
           PHASE_STAMP(11);
-          // pass 1: row maximum over the feasible keys (four independent partial maxima)
+          // pass 1: row maximum over the feasible keys (four independent partial maxima).  A TMEM load costs ~230
+          // cycles round trip: 64 columns per wait (columns past R16 hold stale data that the mask ignores).
           float vm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
-          for (int gb = 0; gb < nblk; ++gb) {
-            uint32_t v[2][16];
-            tc05::tmem_ld16(t_s + gb * 32, v[0]);
-            tc05::tmem_ld16(t_s + gb * 32 + 16, v[1]);
-            const uint32_t mw = sm.mask[row][gb];
+          for (int gb = 0; gb < nblk; gb += 2) {
+            uint32_t v[4][16];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tc05::tmem_ld16(t_s + gb * 32 + u * 16, v[u]);
+            const uint2 mw2 = *reinterpret_cast<const uint2*>(&sm.mask[row][gb]);
             tc05::tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              vm[i & 3] = fmaxf(vm[i & 3], ((mw >> i) & 1u) ? __uint_as_float(v[i >> 4][i & 15]) : -INFINITY);
+            for (int i = 0; i < 64; ++i)
+              vm[i & 3] = fmaxf(vm[i & 3], (((i < 32 ? mw2.x : mw2.y) >> (i & 31)) & 1u) ? __uint_as_float(v[i >> 4][i & 15]) : -INFINITY);
           }
           const float off = fmaf(-c1, fmaxf(fmaxf(vm[0], vm[1]), fmaxf(vm[2], vm[3])), 4.0f);
           PHASE_STAMP(12);
-          // pass 2: p = exp(s - max) (x kAScale), row sum, fp16 hi | lo split written back in place
+          // pass 2: p = exp(s - max) (x kAScale), row sum, fp16 hi | lo split written back in place.  Software
+          // pipelined over 32-column blocks: the load of block gb + 1 is in flight while block gb is processed.
           float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll 1
-          for (int gb = 0; gb < nblk; ++gb) {
-            uint32_t v[2][16];
-            tc05::tmem_ld16(t_s + gb * 32, v[0]);
-            tc05::tmem_ld16(t_s + gb * 32 + 16, v[1]);
+          auto exp_block = [&](const uint32_t (&v)[2][16], int gb) {
             const uint32_t mw = sm.mask[row][gb];
-            tc05::tmem_wait_ld();
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               uint32_t w[16];  // [hi (8 words) | lo (8 words)] of key block 2 gb + u
@@ -898,6 +895,26 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
                 f16s_split2(p0, p1, 1.0f, w[i >> 1], w[8 + (i >> 1)]);
               }
               tc05::tmem_st16(t_s + gb * 32 + u * 16, w);
+            }
+          };
+          uint32_t va[2][16], vb[2][16];
+          tc05::tmem_ld16(t_s, va[0]);
+          tc05::tmem_ld16(t_s + 16, va[1]);
+#pragma unroll 1
+          for (int gb = 0; gb < nblk; gb += 2) {
+            tc05::tmem_wait_ld();
+            if (gb + 1 < nblk) {
+              tc05::tmem_ld16(t_s + (gb + 1) * 32, vb[0]);
+              tc05::tmem_ld16(t_s + (gb + 1) * 32 + 16, vb[1]);
+            }
+            exp_block(va, gb);
+            if (gb + 1 < nblk) {
+              tc05::tmem_wait_ld();
+              if (gb + 2 < nblk) {
+                tc05::tmem_ld16(t_s + (gb + 2) * 32, va[0]);
+                tc05::tmem_ld16(t_s + (gb + 2) * 32 + 16, va[1]);
+              }
+              exp_block(vb, gb + 1);
             }
           }
           sm.xsum[h][row] = sum0 + sum1;
