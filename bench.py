@@ -423,7 +423,7 @@ def run_ours(args, rank, world, local_rank):
                          "frac": achieved / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch, ncu --set full
                          # (profiles/r1_ncu_rollout_full_size.csv); only valid for the default 1024-instance batch
-                         "traffic": 3.00e9 if B == 1024 else None, "peak_source": peak_src,
+                         "traffic": 3.26e9 if B == 1024 else None, "peak_source": peak_src,
                          "kernel": "rrnco::rollout_kernel<RCVRP>", "ms_per_launch": ms_kernel,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "tensor": {"achieved_tflops_algorithmic": tflops, "peak_bf16_tflops": tf_peak,

@@ -226,7 +226,10 @@ def test_decoder_and_rollout_vs_reference_golden(rb, name):
 
 
 @pytest.mark.parametrize("name,n,B", [("rcvrp", 100, 16), ("atsp", 100, 8), ("rcvrptw", 100, 8), ("rcvrp", 50, 8),
-                                       ("atsp", 128, 2), ("rcvrp", 7, 5)])
+                                       ("atsp", 128, 2), ("rcvrp", 7, 5),
+                                       # key-tile boundaries of the tcgen05 engine: N = 16, 34, 112 (last size of the
+                                       # 13-tile variant), 120 (16-tile variant with time windows)
+                                       ("rcvrp", 15, 4), ("atsp", 34, 3), ("rcvrp", 111, 2), ("rcvrptw", 119, 2)])
 def test_greedy_rollout_vs_oracle(rb, name, n, B):
     raw = synth.make_instances(name, B, n, seed=n + B)
     oenv = oenvs.make_env(name, n, check_solution=False)
@@ -255,6 +258,23 @@ def test_greedy_rollout_vs_oracle(rb, name, n, B):
     # every emitted tour is feasible (reference's own validity oracle)
     if name != "rcvrptw":
         env.check_solution_validity(rb.batchify(env.reset(lite(rb, raw)), S), out["actions"])
+
+
+def test_fp16_operand_overflow_is_loud(rb):
+    """The tcgen05 engine computes on fp16 hi | lo operand pairs (|activation| < 4094): an overflow must surface as the
+    reference's "Logits contain NaNs" assertion (decoder.py:303-304), never as silently wrong tours."""
+    name, n, B = "rcvrp", 20, 2
+    raw = synth.make_instances(name, B, n, seed=3)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    td = env.reset(lite(rb, raw))
+    N = td["action_mask"].shape[-1]
+    row, col = synth.random_embeddings(B, N, seed=4)
+    p = omodel.init_decoder_params(name, seed=5)
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    with torch.no_grad():
+        pol.decoder.pointer.ffn.lins[0].weight.mul_(1.0e5)  # hidden activations ~1e5 >> fp16 range
+    with pytest.raises(AssertionError, match="Logits contain NaNs"):
+        pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=env.get_num_starts(td))
 
 
 def test_more_starts_than_one_tile(rb):
