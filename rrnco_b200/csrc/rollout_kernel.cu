@@ -1147,6 +1147,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
       const int colhalf = warp >> 2;
       constexpr float kUnscaleW = 1.0f / (kAScale * kWScale), kUnscaleL = 1.0f / (kAScale * kLkScale);
+      float nonfinite = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         // hidden chunk c: + b1, relu, split -> A operand (hi | lo, fp16) of GEMM2 in tensor memory
@@ -1165,6 +1166,8 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           for (int i = 0; i < 16; i += 2) {
             const float h0 = fmaxf(fmaf(__uint_as_float(v[i]), kUnscaleW, sm.b1[c * kFRows + col0 + i]), 0.f);
             const float h1 = fmaxf(fmaf(__uint_as_float(v[i + 1]), kUnscaleW, sm.b1[c * kFRows + col0 + i + 1]), 0.f);
+            // the ReLU would swallow a NaN (fp16 operand overflow upstream of here, ffn_pack.cuh): x * 0 keeps it
+            nonfinite = fmaf(__uint_as_float(v[i]), 0.0f, fmaf(__uint_as_float(v[i + 1]), 0.0f, nonfinite));
             f16s_split2(h0, h1, kAScale, hi[i >> 1], lo[i >> 1]);
           }
           tc05::tmem_st8(t_hhi + lane_base + (col0 >> 1), hi);
@@ -1180,6 +1183,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
         tc05::mbar_arrive(&sm.bar_epi);
         if (tid == 0) TL(step, 54 + c);  // epilogue 1 of chunk c done
       }
+      if (nonfinite != 0.f) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);  // NaN != 0
       tc05::mbar_wait(&sm.bar_g2, 1, 32);  // GEMM2(3): FFN output complete, ring memory idle
       tc05::fence_after_sync();
       if (tid == 0) TL(step, 58);  // FFN output seen
