@@ -59,12 +59,13 @@ int rrnco_abi_version(void);
 const char* rrnco_strerror(int code);
 
 /* Precision of the in-kernel contractions of the fused decoder kernels (process-wide, set before use):
- *   3 = 3xTF32 error-compensated tensor-core passes, fp32-faithful (default; the reference's CPU / fp32 path)
- *   1 = one TF32 pass (analogue of the reference's `torch.autocast("cuda")` inference path, test.py:182-185) */
+ *   3 = error-compensated tensor-core contractions, fp32-faithful (default; the reference's CPU / fp32 path):
+ *       three-term fp16 operand split on tcgen05 (engine 1) / 3xTF32 on mma.sync (engine 0)
+ *   1 = one reduced-precision pass (analogue of the reference's `torch.autocast("cuda")` inference path, test.py:182-185) */
 int rrnco_set_precision(int32_t passes);
 
 /* FFN engine of the fused rollout kernel (process-wide, set before use):
- *   1 = tcgen05.mma kind::tf32, TMEM accumulators, TMA-streamed weights (default)
+ *   1 = tcgen05.mma kind::f16 for attention, FFN and logits, TMEM accumulators, TMA-streamed operands (default)
  *   0 = mma.sync tensor-core path (also what rrnco_decoder_logits uses) */
 int rrnco_set_ffn_engine(int32_t engine);
 
@@ -113,7 +114,7 @@ int rrnco_rcvrp_step(int64_t R, int32_t n_nodes, int64_t data_rows, const int64_
 /* ------------------------------------------------------------------------------------------------
  * Residual FFN of RRNet_PointerAttention  rrnco/models/decoder.py:272-277,296  (rl4co MLP E -> 4E -> E, ReLU)
  *   g_out = W2 relu(W1 g_in + b1) + b2 + g_in     g: [n_rows, E] fp32
- *   tcgen05 (kind::tf32, 3xTF32 split, TMEM accumulators) form of the FFN phase of the fused kernel.
+ *   tcgen05 (kind::f16, three-term fp16 operand split, TMEM accumulators) form of the FFN phase of the fused kernel.
  *   workspace >= rrnco_pointer_ffn_workspace_bytes() bytes (holds the hi/lo split of W1, W2).
  * ---------------------------------------------------------------------------------------------- */
 int64_t rrnco_pointer_ffn_workspace_bytes(void);
@@ -254,7 +255,10 @@ int rrnco_select_action(int64_t n_rollouts, int32_t n_nodes, const float* logits
  *   logprob_out     fp32 [R, t_cap] per-step log-probs (may be NULL); loglik_out fp32 [R] their sum.
  *   norm_reward_out fp32 [R] = -(tour length on the normalised matrix); real_reward_out de-normalised
  *                    (NULL if data->min_distance is NULL).  Padding legs 0->0 are accounted like upstream.
- *   workspace       >= rrnco_rollout_workspace_bytes(...) bytes, 16-byte aligned.
+ *   workspace       >= rrnco_rollout_workspace_bytes(...) bytes, 16-byte aligned: fp64 accumulators (16 B per rollout),
+ *                    tile step counts, the packed FFN weights (512 KB) and 256 per-SM slots of 192 KB holding the fp16
+ *                    tiles of the resident instance's keys / values / logit keys.  Scratch only: nothing in it
+ *                    survives the call, but two concurrent rollouts (different streams) need two workspaces.
  * ---------------------------------------------------------------------------------------------- */
 int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts);
 

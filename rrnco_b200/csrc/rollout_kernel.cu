@@ -7,14 +7,19 @@
 //
 // Per step (all 128 rollouts of the tile together, weights shared => real GEMMs on the tensor pipe):
 //   A. action mask (env.get_action_mask) as 128-bit row bitsets; query q = ctx_node_proj[cur] + state.w
-//   B. K / V of the instance staged in shared memory with cp.async (zero-filled to a multiple of 8 keys)
-//   C. 8-head masked attention, flash-style in registers: S = Q_h K_h^T (mma), softmax (quad shuffles),
-//      P V_h (mma, accumulator layout re-used as the A operand through a key permutation), + q
-//   E. FFN 128 -> 512 -> 128 with residual; W1/W2 streamed from L2 through a 3-stage cp.async ring
+//   C. 8-head masked attention: S = Q_h K_h^T, masked softmax, P V_h, + q
+//   E. FFN 128 -> 512 -> 128 with residual
 //   G. pointer logits g.Lk^T / sqrt(E), scale-adaptive bias log(exp(l - a.D[cur,:] - b.Dur[cur,:]) + 1e-6),
 //      10.tanh, mask, log-softmax, greedy argmax / Gumbel-max sample / forced action, state transition.
-// All contractions run as 3xTF32 (error-compensated split, fp32-faithful) or 1xTF32 (kPasses == 1, the
-// analogue of the reference's autocast inference path).
+//
+// Two engines (template parameter kTc, rrnco_set_ffn_engine):
+//   kTc = true  (default): every contraction on tcgen05.mma kind::f16 with the two-term fp16 operand split of
+//       ffn_pack.cuh (three MMAs per K step = fp32-faithful; kPasses == 1 keeps only hi*hi), accumulators and the A
+//       operands of the second GEMMs in tensor memory, K / V / logit keys pre-packed per CTA and TMA-loaded each step,
+//       FFN weights TMA-streamed through a 4-stage ring; warps 0-7 run the element-wise passes thread-per-rollout,
+//       warp 8 is the TMA producer, warps 9-11 issue the MMAs.  See DESIGN.md section 4.2 for the memory maps.
+//   kTc = false: the first working version, everything on mma.sync.m16n8k8 3xTF32 with flash-style attention in
+//       registers and a cp.async weight ring; also serves the logits-only mode (rrnco_decoder_logits).
 #include <cstdio>
 #include "common.cuh"
 #include "tc05.cuh"
