@@ -4,6 +4,7 @@
 // lanes stride over nodes so that every global access of a warp is one contiguous segment; the
 // any-feasible reduction the depot rule needs is a ballot.  fp32 arithmetic uses explicit _rn
 // intrinsics in the reference's evaluation order so that masks are bit-exact (no FMA contraction).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace rrnco {
@@ -165,71 +166,100 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rcvrp_step_kernel(
   }
 }
 
-// Vectorised variant for the un-aliased, fully replicated reference layout (data_rows == R, cap_rows == R or 1):
-// a CTA owns 32 consecutive rollouts, whose visited / mask rows (32 N bytes) and demand rows (32 (N-1) floats) are
-// contiguous and 16-byte aligned as a block, so every global access is a coalesced 128-bit vector; rows are
-// processed from shared memory (one warp per 8 rollouts) and written back the same way.
+// Staged variant for the un-aliased, fully replicated reference layout (data_rows == R, cap_rows == R or 1):
+// blocks of 32 consecutive rollouts, whose visited / mask rows (32 N bytes) and demand rows (32 (N-1) floats) are
+// contiguous and 16-byte aligned as a block, so every global access is a coalesced 128-bit vector; rows are processed
+// from shared memory and written back the same way.
 constexpr int kGroup = 32;
-__global__ void __launch_bounds__(128) rcvrp_step_vec_kernel(
-    int64_t R, int N, const int64_t* __restrict__ action, const float* __restrict__ demand,
+// Persistent, warp-autonomous pipeline.  ncu of the first staged version (one warp per rollout over the staged bytes,
+// lanes = nodes, load -> barrier -> compute -> barrier -> store per CTA) showed 85 % issue-slot utilisation at 31 % DRAM
+// utilisation: the reference's bool [R, N] rows are byte-granular and unaligned, so the per-node work was scalar byte
+// traffic plus two ballots per 32 nodes.  Here a warp owns blocks of 32 consecutive rollouts (contiguous in every
+// array): cp.async stages block k+1 into the second half of the warp's private buffer while the 32 lanes each walk one
+// rollout of block k (no cross-lane operations, ~8 instructions per node for 32 rollouts at once, 128-bit demand
+// loads), then the warp writes the visited / mask blocks back as 128-bit vectors.  No CTA-wide barrier.
+constexpr int kStepWarps = 6;  // 6 warps x (2 x 16.0 KB staged visited | demand + 3.2 KB mask) (N = 101) = 212 KB: one CTA per SM
+__global__ void __launch_bounds__(kStepWarps * 32, 1) rcvrp_step_vec_kernel(
+    int64_t n_groups, int N, const int64_t* __restrict__ action, const float* __restrict__ demand,
     const float* __restrict__ capacity, int64_t cap_rows, const float* __restrict__ used_in,
     const uint8_t* __restrict__ visited_in, float* __restrict__ used_out, uint8_t* __restrict__ visited_out,
     int64_t* __restrict__ current_out, uint8_t* __restrict__ done_out, uint8_t* __restrict__ mask_out) {
   extern __shared__ __align__(16) unsigned char sraw[];
-  const int nb = kGroup * N;                       // bytes of one visited / mask block (multiple of 16)
-  uint8_t* s_vis = sraw;                           // [32][N]  (updated in place)
-  uint8_t* s_msk = sraw + nb;                      // [32][N]
-  float* s_dem = reinterpret_cast<float*>(sraw + 2 * nb);  // [32][N-1]
-  const int64_t r0 = (int64_t)blockIdx.x * kGroup;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  {
-    const uint4* gv = reinterpret_cast<const uint4*>(visited_in + r0 * N);
-    for (int i = tid; i < nb / 16; i += 128) reinterpret_cast<uint4*>(s_vis)[i] = __ldg(gv + i);
-    const uint4* gd = reinterpret_cast<const uint4*>(demand + r0 * (N - 1));
-    for (int i = tid; i < kGroup * (N - 1) / 4; i += 128) reinterpret_cast<uint4*>(s_dem)[i] = __ldg(gd + i);
-  }
-  __syncthreads();
-  for (int k = 0; k < kGroup / 4; ++k) {
-    const int lr = warp * (kGroup / 4) + k;
-    const int64_t r = r0 + lr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = kGroup * N;                                  // bytes of one visited / mask block (multiple of 16)
+  const int nd = kGroup * (N - 1) * (int)sizeof(float);       // bytes of one demand block (multiple of 16)
+  const int buf_bytes = nb + nd;                               // one staged buffer: [visited | demand]
+  unsigned char* wbase = sraw + (size_t)warp * (2 * buf_bytes + nb);  // this warp: two staged buffers + one mask block
+  unsigned char* s_mask = wbase + 2 * buf_bytes;
+  const int64_t stride = (int64_t)gridDim.x * kStepWarps;
+  int64_t gi = (int64_t)blockIdx.x * kStepWarps + warp;
+  auto stage = [&](int64_t g, int b) {
+    unsigned char* s = wbase + b * buf_bytes;
+    const unsigned char* gv = visited_in + g * nb;
+    for (int i = lane; i < nb / 16; i += 32) cp_async16(s + i * 16, gv + i * 16);
+    const unsigned char* gd = reinterpret_cast<const unsigned char*>(demand) + g * nd;
+    for (int i = lane; i < nd / 16; i += 32) cp_async16(s + nb + i * 16, gd + i * 16);
+  };
+  if (gi < n_groups) stage(gi, 0);
+  cp_async_commit();
+  for (int b = 0; gi < n_groups; gi += stride, b ^= 1) {
+    if (gi + stride < n_groups) stage(gi + stride, b ^ 1);
+    cp_async_commit();
+    const int64_t r = gi * kGroup + lane;
     const int cur = (int)action[r];
     const float cap = capacity[r % cap_rows];
-    const float* dem = s_dem + lr * (N - 1);
-    const int di = min(max(cur - 1, 0), N - 2);
-    const float used = __fmul_rn(__fadd_rn(used_in[r], dem[di]), cur != 0 ? 1.0f : 0.0f);
-    uint8_t* vis = s_vis + lr * N;
-    uint8_t* msk = s_msk + lr * N;
-    int n_visited = 0;
-    bool any_free = false;
-    for (int n0 = 0; n0 < N; n0 += 32) {
-      const int n = n0 + lane;
-      bool v = false, free_loc = false;
-      if (n < N) {
-        uint8_t vb = vis[n];
-        if (n == cur) { vb = 1; vis[n] = 1; }
-        v = vb != 0;
-        if (n >= 1) {
-          free_loc = !(v || __fadd_rn(dem[n - 1], used) > cap);
+    const float used0 = used_in[r];
+    cp_async_wait<1>();
+    __syncwarp();
+    unsigned char* s = wbase + b * buf_bytes;
+    {
+      uint8_t* vis = s + lane * N;
+      uint8_t* msk = s_mask + lane * N;
+      const float* dem = reinterpret_cast<const float*>(s + nb) + lane * (N - 1);
+      const int di = min(max(cur - 1, 0), N - 2);
+      const float used = __fmul_rn(__fadd_rn(used0, dem[di]), cur != 0 ? 1.0f : 0.0f);
+      vis[cur] = 1;
+      int n_visited = vis[0];
+      bool any_free = false;
+      // demand rows are 16-byte aligned whenever (N - 1) % 4 == 0 (e.g. N = 101): 128-bit shared loads, conflict-free at
+      // a lane stride of (N - 1) floats; the byte rows of visited / mask stay scalar
+      const int n4 = ((N - 1) & 3) == 0 ? (N - 1) >> 2 : 0;
+#pragma unroll 2
+      for (int j4 = 0; j4 < n4; ++j4) {
+        const float4 d4 = reinterpret_cast<const float4*>(dem)[j4];
+        const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int n = 4 * j4 + e + 1;
+          const bool v = vis[n] != 0;
+          const bool free_loc = !(v || __fadd_rn(dd[e], used) > cap);
           msk[n] = free_loc;
+          n_visited += v;
+          any_free |= free_loc;
         }
       }
-      n_visited += __popc(__ballot_sync(0xffffffffu, v));
-      any_free |= __any_sync(0xffffffffu, free_loc);
-    }
-    if (lane == 0) {
+      for (int n = 4 * n4 + 1; n < N; ++n) {
+        const bool v = vis[n] != 0;
+        const bool free_loc = !(v || __fadd_rn(dem[n - 1], used) > cap);
+        msk[n] = free_loc;
+        n_visited += v;
+        any_free |= free_loc;
+      }
       msk[0] = !(cur == 0 && any_free);
       used_out[r] = used;
       current_out[r] = cur;
       done_out[r] = n_visited == N;
     }
+    __syncwarp();
+    uint4* ov = reinterpret_cast<uint4*>(visited_out + gi * nb);
+    uint4* om = reinterpret_cast<uint4*>(mask_out + gi * nb);
+    for (int i = lane; i < nb / 16; i += 32) {
+      ov[i] = reinterpret_cast<const uint4*>(s)[i];
+      om[i] = reinterpret_cast<const uint4*>(s_mask)[i];
+    }
+    __syncwarp();  // the buffer is re-staged two iterations from now, after this warp's own reads
   }
-  __syncthreads();
-  uint4* ov = reinterpret_cast<uint4*>(visited_out + r0 * N);
-  uint4* om = reinterpret_cast<uint4*>(mask_out + r0 * N);
-  for (int i = tid; i < nb / 16; i += 128) {
-    ov[i] = reinterpret_cast<const uint4*>(s_vis)[i];
-    om[i] = reinterpret_cast<const uint4*>(s_msk)[i];
-  }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -431,14 +461,27 @@ int rrnco_rcvrp_step(int64_t R, int32_t n_nodes, int64_t data_rows, const int64_
                   visited_in && mask_out);
   RRNCO_CHECK_ARG(action ? (used_out && visited_out && current_out && done_out) : (current_in != nullptr));
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  const size_t smem = 2 * (size_t)kGroup * n_nodes + (size_t)kGroup * (n_nodes - 1) * sizeof(float);
+  // staged persistent kernel: each warp double-buffers blocks of kGroup rollouts in shared memory
+  const size_t nbk = (size_t)kGroup * n_nodes, buf = nbk + (size_t)kGroup * (n_nodes - 1) * sizeof(float);
+  const size_t smem = (size_t)kStepWarps * (2 * buf + nbk);
   const bool vec_ok = action != nullptr && data_rows == R && (cap_rows == 1 || cap_rows == R) && R >= kGroup &&
-                      smem <= 48 * 1024 && al16(demand) &&
-                      al16(visited_in) && al16(visited_out) && al16(mask_out) && visited_in != visited_out;
+                      smem <= 220 * 1024 && al16(demand) && al16(visited_in) && al16(visited_out) && al16(mask_out) &&
+                      visited_in != visited_out;
   const int64_t R_vec = vec_ok ? (R / kGroup) * kGroup : 0;
   if (R_vec > 0) {
-    rcvrp_step_vec_kernel<<<(unsigned)(R_vec / kGroup), 128, smem, (cudaStream_t)stream>>>(
-        R_vec, n_nodes, action, demand, capacity, cap_rows, used_in, visited_in, used_out, visited_out, current_out,
+    static int n_sm = 0;  // idempotent; benign if raced
+    if (n_sm == 0) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return RRNCO_ERR_CUDA;
+      if (cudaFuncSetAttribute(rcvrp_step_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+        return RRNCO_ERR_CUDA;
+    }
+    const int64_t n_groups = R_vec / kGroup;
+    const int64_t want = (n_groups + kStepWarps - 1) / kStepWarps;
+    const unsigned grid = (unsigned)(want < n_sm ? want : n_sm);
+    rcvrp_step_vec_kernel<<<grid, kStepWarps * 32, smem, (cudaStream_t)stream>>>(
+        n_groups, n_nodes, action, demand, capacity, cap_rows, used_in, visited_in, used_out, visited_out, current_out,
         done_out, mask_out);
     int rc = rrnco_launch_status();
     if (rc != RRNCO_OK) return rc;
