@@ -227,9 +227,19 @@ def run_ours(args, rank, world, local_rank):
     dist_on = world > 1
     if dist_on:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when the first communicator is created; stdout carries exactly one
+        # JSON line, so the file descriptor points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     rb.set_precision(args.precision)
     B, Bp = args.batch, args.batch * N_AUG
     env = rb.RCVRPEnv(generator_params={"num_loc": N_LOC}, check_solution=False, device=dev)
