@@ -62,7 +62,7 @@ __device__ int g_tl_n;
 constexpr int kTlStep = 6;
 #define TL(stepvar, tag)                                           \
   do {                                                             \
-    if (blockIdx.x == 0 && (stepvar) == kTlStep) {                 \
+    if (blockIdx.x == 0 && ((stepvar) == kTlStep || (stepvar) == kTlStep + 1)) { \
       const int i_ = atomicAdd(&g_tl_n, 1);                        \
       if (i_ < 256) { g_tl[2 * i_] = (tag); g_tl[2 * i_ + 1] = clock64(); } \
     }                                                              \
@@ -811,6 +811,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           *reinterpret_cast<uint2*>(&sm.mask[row][2 * dh]) = make_uint2(bits2[0], bits2[1]);
         }
         PHASE_STAMP(15);
+        if (tid == 0) TL(step, 3);  // mask words written
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
           const int c8 = dh * 8 + cc;
@@ -1407,6 +1408,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           const bool count_leg = kEnv != RRNCO_ENV_ATSP || t_out > 0;
           transition<kEnv>(sm, p, row, act, D, U, cap, closed, count_leg);
           if (kEnv == RRNCO_ENV_ATSP && t_out == 0) sm.first[row] = act;
+          if (tid == 0) TL(step, 64);  // transition done
           sm.lp[row] += (double)chosen;
           if (sm.active[row] && t_out < p.t_cap) {
             p.actions[rg * p.t_cap + t_out] = act;

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 import rrnco_b200 as rb  # noqa: E402
 from bench import host_instances, stand_in_embeddings, N_LOC, N_START  # noqa: E402
 
-NAMES = {1: "step start", 2: "mask+query done", 200: "kernel start", 201: "staging done", 202: "state init done",
+NAMES = {1: "step start", 2: "mask+query done", 3: "mask words written", 64: "transition done", 200: "kernel start", 201: "staging done", 202: "state init done",
          203: "K/V/Lk packed", 204: "entering step loop"}
 for h in range(8):
     NAMES.update({10 + h: f"grp waits scores h{h}", 20 + h: f"grp sees scores h{h}", 30 + h: f"grp wrote P h{h}",
