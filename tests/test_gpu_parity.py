@@ -117,6 +117,27 @@ def test_env_random_transitions_vs_oracle(rb, name, n, B):
     assert torch.equal(type(env).get_action_mask(td).cpu(), otd["action_mask"]) if name != "atsp" else True
 
 
+def test_rcvrp_env_step_persistent_pipeline_many_blocks(rb):
+    """40 400 rollouts = 1262 blocks of 32 (+ a tail of 16): every warp of the persistent staged env-step kernel runs its
+    double-buffered loop more than once; a few random forced transitions, everything bit-exact vs the oracle."""
+    name, n, B, S = "rcvrp", 100, 404, 100
+    g = torch.Generator().manual_seed(7)
+    raw = synth.make_instances(name, B, n, seed=11, integer_demand=False)
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    otd = obatchify(oenv.reset(raw), S)
+    td = rb.batchify(env.reset(lite(rb, raw)), S)
+    assert td["visited"].shape[0] == 40400
+    for t in range(4):
+        a = torch.multinomial(otd["action_mask"].float(), 1, generator=g).squeeze(1)
+        otd["action"] = a
+        otd = oenv.step(otd)["next"]
+        td.set("action", a.to(dev))
+        td = env.step(td)["next"]
+        for k in ("action_mask", "done", "visited", "used_capacity", "current_node"):
+            assert torch.equal(td[k].cpu(), otd[k]), (k, t)
+
+
 def test_env_edge_cases(rb):
     env = rb.RCVRPEnv(generator_params={"num_loc": 3}, check_solution=True)
     # demand exactly filling the vehicle is feasible (strict >), one that overflows by an ulp is not
