@@ -282,13 +282,27 @@ def run_ours(args, rank, world, local_rank):
             gather_costs(best, world * B)  # the path's only collective (NCCL all-gather of [B] fp32 per rank)
         return out
 
-    def step_e2e(i):
+    # e2e: every step copies its own batch from pinned host memory; the copy of step i+1 is issued on the copy stream
+    # before step i's kernels (rrnco_b200.HostPrefetcher), so in steady state it overlaps the rollout of step i
+    prefetch = rb.HostPrefetcher(dev)
+    tickets = {}
+
+    def host_batch(i):
         raw, row, col = host_sets[i % n_sets]
-        enc.row, enc.col = row, col
-        td = env.reset(rb.TensorDictLite(raw, batch_size=[B]))       # H2D of the instance batch + normalise
+        return {**raw, "__row_emb": row, "__col_emb": col}
+
+    def step_e2e(i):
+        if i not in tickets:
+            tickets[i] = prefetch.submit(host_batch(i))              # first call only
+        tickets[i + 1] = prefetch.submit(host_batch(i + 1))          # H2D of the next step's batch
+        ticket = tickets.pop(i)
+        d = prefetch.acquire(ticket)
+        enc.row, enc.col = d["__row_emb"], d["__col_emb"]
+        td = env.reset(rb.TensorDictLite({k: v for k, v in d.items() if not k.startswith("__")}, batch_size=[B]))
         td_aug = rb.batchify(td, N_AUG)                              # StateAugmentation (transforms.py:143)
         out = policy(td_aug, env, phase="val", decode_type="multistart_greedy", num_starts=N_START)
         best = rb.unbatchify(out["reward"], (N_AUG, N_START)).amax(-1).amax(-1)
+        prefetch.release(ticket)
         return best.cpu()                                            # D2H of the result
 
     def barrier():
@@ -377,6 +391,83 @@ def run_ours(args, rank, world, local_rank):
                 "rollouts": R_probe, "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
                 "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s"}
 
+    def time_launch(launch, reps=10, warm=3):
+        for _ in range(warm):
+            launch()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            launch()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def atsp_step_probe():
+        # ATSPEnv._step in the reference layout at the same rollout count (bool mask rows r/w + int64 scalars)
+        from rrnco_b200._lib import call, ptr, stream_ptr
+        R_probe, N = Bp * N_START, N_LOC
+        g = torch.Generator(device=dev).manual_seed(1)
+        mask_in = torch.rand(R_probe, N, device=dev, generator=g) < 0.7
+        action = torch.randint(0, N, (R_probe,), device=dev, generator=g)
+        step_i = torch.full((R_probe,), 5, dtype=torch.int64, device=dev)
+        first_in = torch.randint(0, N, (R_probe,), device=dev, generator=g)
+        mask_o = torch.empty_like(mask_in)
+        first_o, cur_o = torch.empty_like(first_in), torch.empty_like(first_in)
+        done_o = torch.empty(R_probe, dtype=torch.bool, device=dev)
+        ms = time_launch(lambda: call("rrnco_atsp_step", R_probe, N, ptr(action), ptr(step_i), ptr(mask_in),
+                                      ptr(first_in), ptr(mask_o), ptr(first_o), ptr(cur_o), ptr(done_o),
+                                      stream_ptr(dev)))
+        nbytes = R_probe * (2 * N + 50)  # ATSP 2N+50 B per rollout-step
+        return {"kernel": "rrnco::atsp_step_kernel (ATSPEnv._step, reference layout)", "rollouts": R_probe,
+                "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
+                "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s"}
+
+    def rcvrptw_step_probe():
+        # RMTVRPEnv._step + get_action_mask at the C3 size: 1024 instances x 100 starts; instance data stays
+        # un-replicated (data_rows = 1024, 84 MB: the matrix rows / columns are served by L2), the rollout state is
+        # in the reference layout.  Bytes are SURVEY.md 8(d)'s algorithmic count (39N+100 per rollout-step), so this
+        # figure is NOT bounded by the HBM peak.
+        import ctypes as C
+        from rrnco_b200._lib import call, ptr, stream_ptr
+        from rrnco_b200.envs import RMTVRPEnv
+        Bt, St, N = B, 100, N_LOC + 1
+        g = torch.Generator(device=dev).manual_seed(2)
+        env_tw = RMTVRPEnv(generator_params={"num_loc": N_LOC}, check_solution=False, device=dev)
+        dm = torch.rand(Bt, N, N, device=dev, generator=g)
+        td0 = rb.TensorDictLite({
+            "locs": torch.rand(Bt, N, 2, device=dev, generator=g), "distance_matrix": dm,
+            "duration_matrix": dm * (0.5 + torch.rand(Bt, N, N, device=dev, generator=g)),
+            "demand_linehaul": torch.rand(Bt, N_LOC, device=dev, generator=g) * 0.2,
+            "time_windows": torch.stack([torch.rand(Bt, N, device=dev, generator=g), 4 + torch.rand(Bt, N, device=dev, generator=g)], -1),
+            "service_time": torch.rand(Bt, N, device=dev, generator=g) * 0.05}, batch_size=[Bt])
+        td0 = env_tw.reset(td0)
+        td_r = rb.batchify(td0, St)
+        R_probe = Bt * St
+        keep = []
+        data = RMTVRPEnv.instance_data(td0, keep)
+        visited = torch.rand(R_probe, N, device=dev, generator=g) < 0.3
+        td_r.update({"visited": visited, "current_node": torch.randint(1, N, (R_probe,), device=dev, generator=g),
+                     "current_time": torch.rand(R_probe, 1, device=dev, generator=g),
+                     "used_capacity_linehaul": torch.rand(R_probe, 1, device=dev, generator=g) * 0.5})
+        s_in = RMTVRPEnv._state(td_r, keep)
+        out = {k: torch.empty_like(td_r[k].reshape(-1) if k != "visited" else td_r[k]) for k in
+               ("current_node", "current_time", "current_route_length", "used_capacity_linehaul",
+                "used_capacity_backhaul", "visited")}
+        s_out = type(s_in)()
+        for k, v in out.items():
+            setattr(s_out, k, ptr(v))
+        action = torch.randint(1, N, (R_probe,), device=dev, generator=g)
+        done_o = torch.empty(R_probe, dtype=torch.bool, device=dev)
+        mask_o = torch.empty(R_probe, N, dtype=torch.bool, device=dev)
+        ms = time_launch(lambda: call("rrnco_rmtvrp_step", R_probe, N, C.byref(data), ptr(action), C.byref(s_in),
+                                      C.byref(s_out), ptr(done_o), ptr(mask_o), stream_ptr(dev)))
+        nbytes = R_probe * (39 * N + 100)  # RCVRPTW 39N+100 B per rollout-step
+        return {"kernel": "rrnco::rmtvrp_step_kernel (RMTVRPEnv._step + get_action_mask; instance data un-replicated, "
+                          "L2-served: algorithmic bytes, not HBM-bounded)", "rollouts": R_probe,
+                "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
+                "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s"}
+
     def gather_probe():
         from rrnco_b200.sampler import CityOnDevice, gather_submatrix
         city = CityOnDevice(make_city(3), dev)
@@ -400,6 +491,8 @@ def run_ours(args, rank, world, local_rank):
 
     env_probe = env_step_probe() if rank == 0 else None
     gat_probe = gather_probe() if rank == 0 else None
+    atsp_probe = atsp_step_probe() if rank == 0 else None
+    tw_probe = rcvrptw_step_probe() if rank == 0 else None
 
     # ---- e2e: host inputs, H2D + reset + cache + rollout + reduction + D2H ----------------------------
     ms_e2e, best = timed(step_e2e, args.steps, 2)
@@ -429,8 +522,10 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
-                    "what": "RRNetPolicy.forward on pinned HOST inputs (instance td + encoder output): H2D, "
-                            "env.reset normalisation, x8 augmentation, cache GEMM, fused rollout, best-of reduction, D2H"},
+                    "what": "RRNetPolicy.forward on pinned HOST inputs (instance td + encoder output): H2D "
+                            "(every step, on the copy stream, double-buffered: the copy of batch i+1 overlaps the rollout "
+                            "of batch i), env.reset normalisation, x8 augmentation, cache GEMM, fused rollout, best-of "
+                            "reduction, D2H"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch, ncu --set full
@@ -440,12 +535,14 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "tensor": {"achieved_tflops_algorithmic": tflops, "peak_bf16_tflops": tf_peak,
                                     "frac": tflops / tf_peak,
-                                    "note": "fp32-faithful mode issues 3 TF32 passes per algorithmic FLOP"}},
+                                    "note": "fp32-faithful mode issues 3 fp16 tensor passes (hi*hi, lo*hi, hi*lo) per algorithmic FLOP"}},
         }
-        for probe in (env_probe, gat_probe):
+        for probe in (env_probe, gat_probe, atsp_probe, tw_probe):
             probe["peak"] = hbm_peak
             probe["frac"] = probe["achieved"] / hbm_peak
         line["env_step"] = env_probe
+        line["env_step_atsp"] = atsp_probe
+        line["env_step_rcvrptw"] = tw_probe
         line["gather"] = gat_probe
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

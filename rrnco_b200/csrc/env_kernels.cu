@@ -178,9 +178,15 @@ constexpr int kGroup = 32;
 // array): cp.async stages block k+1 into the second half of the warp's private buffer while the 32 lanes each walk one
 // rollout of block k (no cross-lane operations, ~8 instructions per node for 32 rollouts at once, 128-bit demand
 // loads), then the warp writes the visited / mask blocks back as 128-bit vectors.  No CTA-wide barrier.
-constexpr int kStepStages = 2;  // staged [visited | demand] buffers per warp (prefetch distance kStepStages - 1 blocks);
-                                // measured at N = 101: 2 stages x 6 warps 62 % of HBM peak, 3 stages x 4 warps 47 %, 2 x 5 53 %
-constexpr int kStepWarps = 6;  // 6 warps x (2 x 16.0 KB staged visited | demand + 3.2 KB mask) (N = 101) = 212 KB: one CTA per SM
+// Inside a block every lane walks its own rollout in chunks of 20 nodes held in registers: the visited bytes and the
+// five demand float4 of chunk c+1 are loaded before the mask bytes of chunk c are stored.  (The first version
+// interleaved one LDS.U8 / STS.U8 pair per node: the mask stores may alias the visited loads as far as the compiler
+// can tell, so every node paid a full shared-memory round trip, ~5 k cycles per block and warp; cuobjdump -sass.)
+// The per-rollout scalars (action, capacity, used) of block k+1 are fetched while block k is walked.
+constexpr int kStepStagesDefault = 2;  // staged [visited | demand] buffers per warp (prefetch distance stages - 1 blocks)
+constexpr int kStepWarpsDefault = 6;   // 6 warps x (2 x 16.0 KB staged visited | demand + 3.2 KB mask) (N = 101) = 212 KB: one CTA per SM
+constexpr int kChunkQ = 5;             // float4 of demand per register chunk (20 nodes)
+template <int kStepStages, int kStepWarps>
 __global__ void __launch_bounds__(kStepWarps * 32, 1) rcvrp_step_vec_kernel(
     int64_t n_groups, int N, const int64_t* __restrict__ action, const float* __restrict__ demand,
     const float* __restrict__ capacity, int64_t cap_rows, const float* __restrict__ used_in,
@@ -207,13 +213,26 @@ __global__ void __launch_bounds__(kStepWarps * 32, 1) rcvrp_step_vec_kernel(
     if (gi + k * stride < n_groups) stage(gi + k * stride, k);
     cp_async_commit();
   }
+  int cur_n = 0;
+  float cap_n = 0.0f, used_n = 0.0f;
+  if (gi < n_groups) {
+    const int64_t r0 = gi * kGroup + lane;
+    cur_n = (int)action[r0];
+    cap_n = capacity[r0 % cap_rows];
+    used_n = used_in[r0];
+  }
   for (int b = 0; gi < n_groups; gi += stride, b = (b + 1) % kStepStages) {
     if (gi + (kStepStages - 1) * stride < n_groups) stage(gi + (kStepStages - 1) * stride, (b + kStepStages - 1) % kStepStages);
     cp_async_commit();
     const int64_t r = gi * kGroup + lane;
-    const int cur = (int)action[r];
-    const float cap = capacity[r % cap_rows];
-    const float used0 = used_in[r];
+    const int cur = cur_n;
+    const float cap = cap_n, used0 = used_n;
+    if (gi + stride < n_groups) {  // next block's scalars: their latency hides under this block's walk
+      const int64_t rn = (gi + stride) * kGroup + lane;
+      cur_n = (int)action[rn];
+      cap_n = capacity[rn % cap_rows];
+      used_n = used_in[rn];
+    }
     cp_async_wait<kStepStages - 1>();
     __syncwarp();
     unsigned char* s = wbase + b * buf_bytes;
@@ -229,21 +248,38 @@ __global__ void __launch_bounds__(kStepWarps * 32, 1) rcvrp_step_vec_kernel(
       // demand rows are 16-byte aligned whenever (N - 1) % 4 == 0 (e.g. N = 101): 128-bit shared loads, conflict-free at
       // a lane stride of (N - 1) floats; the byte rows of visited / mask stay scalar
       const int n4 = ((N - 1) & 3) == 0 ? (N - 1) >> 2 : 0;
-#pragma unroll 5
-      for (int j4 = 0; j4 < n4; ++j4) {
-        const float4 d4 = reinterpret_cast<const float4*>(dem)[j4];
-        const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+      const int n_chunks = n4 / kChunkQ;
+      const float4* dem4 = reinterpret_cast<const float4*>(dem);
+      float4 dq[kChunkQ];
+      uint32_t vq[4 * kChunkQ];
+      auto load_chunk = [&](int c) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int n = 4 * j4 + e + 1;
-          const bool v = vis[n] != 0;
+        for (int q = 0; q < kChunkQ; ++q) dq[q] = dem4[c * kChunkQ + q];
+#pragma unroll
+        for (int e = 0; e < 4 * kChunkQ; ++e) vq[e] = vis[c * 4 * kChunkQ + 1 + e];
+      };
+      if (n_chunks > 0) load_chunk(0);
+      for (int c = 0; c < n_chunks; ++c) {
+        float dd[4 * kChunkQ];
+        uint32_t vv[4 * kChunkQ];
+#pragma unroll
+        for (int q = 0; q < kChunkQ; ++q) {
+          dd[4 * q] = dq[q].x, dd[4 * q + 1] = dq[q].y, dd[4 * q + 2] = dq[q].z, dd[4 * q + 3] = dq[q].w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4 * kChunkQ; ++e) vv[e] = vq[e];
+        if (c + 1 < n_chunks) load_chunk(c + 1);  // in flight before this chunk's mask stores
+        uint8_t* mc = msk + c * 4 * kChunkQ + 1;
+#pragma unroll
+        for (int e = 0; e < 4 * kChunkQ; ++e) {
+          const bool v = vv[e] != 0;
           const bool free_loc = !(v || __fadd_rn(dd[e], used) > cap);
-          msk[n] = free_loc;
+          mc[e] = free_loc;
           n_visited += v;
           any_free |= free_loc;
         }
       }
-      for (int n = 4 * n4 + 1; n < N; ++n) {
+      for (int n = 4 * kChunkQ * n_chunks + 1; n < N; ++n) {
         const bool v = vis[n] != 0;
         const bool free_loc = !(v || __fadd_rn(dem[n - 1], used) > cap);
         msk[n] = free_loc;
@@ -262,7 +298,7 @@ __global__ void __launch_bounds__(kStepWarps * 32, 1) rcvrp_step_vec_kernel(
       ov[i] = reinterpret_cast<const uint4*>(s)[i];
       om[i] = reinterpret_cast<const uint4*>(s_mask)[i];
     }
-    __syncwarp();  // the buffer is re-staged two iterations from now, after this warp's own reads
+    __syncwarp();  // the buffer is re-staged kStepStages - 1 iterations from now, after this warp's own reads
   }
   cp_async_wait<0>();
 }
@@ -466,9 +502,25 @@ int rrnco_rcvrp_step(int64_t R, int32_t n_nodes, int64_t data_rows, const int64_
                   visited_in && mask_out);
   RRNCO_CHECK_ARG(action ? (used_out && visited_out && current_out && done_out) : (current_in != nullptr));
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  // staged persistent kernel: each warp double-buffers blocks of kGroup rollouts in shared memory
+  // staged persistent kernel: each warp pipelines blocks of kGroup rollouts through shared memory
+  struct VecCfg {
+    int stages, warps;
+    decltype(&rcvrp_step_vec_kernel<2, 6>) fn;
+  };
+  static const VecCfg cfgs[] = {{2, 6, rcvrp_step_vec_kernel<2, 6>}, {3, 4, rcvrp_step_vec_kernel<3, 4>},
+                                {4, 3, rcvrp_step_vec_kernel<4, 3>}, {2, 5, rcvrp_step_vec_kernel<2, 5>},
+                                {3, 3, rcvrp_step_vec_kernel<3, 3>}, {2, 4, rcvrp_step_vec_kernel<2, 4>}};
+  static int cfg_i = -1;  // idempotent; benign if raced
+  if (cfg_i < 0) {
+    int pick = 0;  // development knob: RRNCO_STEP_CFG="<stages>x<warps>" selects another instantiation
+    if (const char* e = std::getenv("RRNCO_STEP_CFG"))
+      for (int i = 0; i < (int)(sizeof(cfgs) / sizeof(cfgs[0])); ++i)
+        if (e[0] - '0' == cfgs[i].stages && e[1] == 'x' && e[2] - '0' == cfgs[i].warps) pick = i;
+    cfg_i = pick;
+  }
+  const VecCfg& cfg = cfgs[cfg_i];
   const size_t nbk = (size_t)kGroup * n_nodes, buf = nbk + (size_t)kGroup * (n_nodes - 1) * sizeof(float);
-  const size_t smem = (size_t)kStepWarps * (kStepStages * buf + nbk);
+  const size_t smem = (size_t)cfg.warps * (cfg.stages * buf + nbk);
   const bool vec_ok = action != nullptr && data_rows == R && (cap_rows == 1 || cap_rows == R) && R >= kGroup &&
                       smem <= 220 * 1024 && al16(demand) && al16(visited_in) && al16(visited_out) && al16(mask_out) &&
                       visited_in != visited_out;
@@ -476,16 +528,17 @@ int rrnco_rcvrp_step(int64_t R, int32_t n_nodes, int64_t data_rows, const int64_
   if (R_vec > 0) {
     static int n_sm = 0;  // idempotent; benign if raced
     if (n_sm == 0) {
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      int dev = 0, sms = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return RRNCO_ERR_CUDA;
-      if (cudaFuncSetAttribute(rcvrp_step_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+      if (cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
         return RRNCO_ERR_CUDA;
+      n_sm = sms;
     }
     const int64_t n_groups = R_vec / kGroup;
-    const int64_t want = (n_groups + kStepWarps - 1) / kStepWarps;
+    const int64_t want = (n_groups + cfg.warps - 1) / cfg.warps;
     const unsigned grid = (unsigned)(want < n_sm ? want : n_sm);
-    rcvrp_step_vec_kernel<<<grid, kStepWarps * 32, smem, (cudaStream_t)stream>>>(
+    cfg.fn<<<grid, cfg.warps * 32, smem, (cudaStream_t)stream>>>(
         n_groups, n_nodes, action, demand, capacity, cap_rows, used_in, visited_in, used_out, visited_out, current_out,
         done_out, mask_out);
     int rc = rrnco_launch_status();

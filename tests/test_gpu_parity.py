@@ -83,7 +83,8 @@ def test_env_forced_sequence_vs_reference_golden(rb, fname):
         assert torch.equal(td["distance_matrix"].cpu(), z["after_reward.distance_matrix"])
 
 
-@pytest.mark.parametrize("name,n,B", [("atsp", 100, 64), ("rcvrp", 100, 64), ("rcvrptw", 100, 64), ("rcvrp", 37, 33)])
+@pytest.mark.parametrize("name,n,B", [("atsp", 100, 64), ("rcvrp", 100, 64), ("rcvrptw", 100, 64), ("rcvrp", 37, 33),
+                                        ("rcvrp", 28, 40), ("rcvrp", 40, 36), ("rcvrp", 4, 32)])
 def test_env_random_transitions_vs_oracle(rb, name, n, B):
     """>= 1e5 random forced transitions at n=100 in total: masks / visited bit-exact, scalars <= 1e-6 rel."""
     g = torch.Generator().manual_seed(n + B)
@@ -136,6 +137,27 @@ def test_rcvrp_env_step_persistent_pipeline_many_blocks(rb):
         td = env.step(td)["next"]
         for k in ("action_mask", "done", "visited", "used_capacity", "current_node"):
             assert torch.equal(td[k].cpu(), otd[k]), (k, t)
+
+
+def test_host_prefetcher_round_trip(rb):
+    """Double-buffered pinned-host -> HBM staging: three batches through two slots, contents intact, slot reuse ordered."""
+    pf = rb.HostPrefetcher(dev)
+    batches = [{"a": torch.randn(1 << 20).pin_memory(), "b": torch.randint(0, 255, (4097, 3), dtype=torch.uint8).pin_memory()}
+               for _ in range(3)]
+    t0 = pf.submit(batches[0])
+    t1 = pf.submit(batches[1])
+    d0 = pf.acquire(t0)
+    s0 = d0["a"].double().sum()
+    assert torch.equal(d0["b"].cpu(), batches[0]["b"])
+    pf.release(t0)
+    t2 = pf.submit(batches[2])  # reuses slot 0 after its release event
+    assert t2 == t0
+    assert torch.equal(pf.acquire(t1)["a"].cpu(), batches[1]["a"])
+    pf.release(t1)
+    assert torch.equal(pf.acquire(t2)["a"].cpu(), batches[2]["a"])
+    assert abs(s0.item() - batches[0]["a"].double().sum().item()) < 1e-6
+    with pytest.raises(RuntimeError, match="pinned"):
+        pf.submit({"a": torch.zeros(4), "b": batches[0]["b"]})
 
 
 def test_env_edge_cases(rb):
