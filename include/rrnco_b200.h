@@ -89,6 +89,14 @@ int rrnco_gather_submatrix(const double* city_matrix, int32_t city_len, const in
                            int32_t n, float* out, int32_t normalize, float* min_out, float* max_out,
                            void* stream);
 
+/* Same gather from an fp32 copy of the city matrix (the cast of generator_lazy.py:300 commutes with the gather, so the
+ * results are bit-identical): 8 instead of 4 elements per 32-byte L2 sector.  rrnco_city_matrix_to_f32 makes the copy,
+ * once per city (n_elems = L*L; also usable for `points`). */
+int rrnco_gather_submatrix_f32(const float* city_matrix_f32, int32_t city_len, const int32_t* idx, int64_t batch,
+                               int32_t n, float* out, int32_t normalize, float* min_out, float* max_out,
+                               void* stream);
+int rrnco_city_matrix_to_f32(const double* city_matrix, int64_t n_elems, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * ATSPEnv._step  rrnco/envs/atsp/env.py:79-105   (reference layout, R rollouts)
  *   mask_out = mask_in with action cleared; done = no node left; first_node latched when *step_i == 0

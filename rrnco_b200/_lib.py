@@ -51,6 +51,8 @@ _SIGNATURES = {
     "rrnco_set_ffn_engine": (C.c_int, [C.c_int32]),
     "rrnco_minmax_normalize": (C.c_int, [C.c_int64, C.c_int32, _f, _f, _f, _f, _f]),
     "rrnco_gather_submatrix": (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, _f, C.c_int32, _f, _f, _f]),
+    "rrnco_gather_submatrix_f32": (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, _f, C.c_int32, _f, _f, _f]),
+    "rrnco_city_matrix_to_f32": (C.c_int, [_f, C.c_int64, _f, _f]),
     "rrnco_atsp_step": (C.c_int, [C.c_int64, C.c_int32, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
     "rrnco_rcvrp_step": (C.c_int, [C.c_int64, C.c_int32, C.c_int64, _f, _f, _f, C.c_int64, _f, _f, _f, _f, _f,
                                    _f, _f, _f, _f]),

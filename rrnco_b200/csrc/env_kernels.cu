@@ -54,10 +54,16 @@ __global__ void __launch_bounds__(256) minmax_normalize_kernel(int n2, const flo
 
 // ------------------------------------------------------------------------------------------------
 // gather: out[b,i,j] = (float) M[idx[b,i], idx[b,j]]      rrnco/envs/rcvrp/sampler.py:84-90
-// One CTA per instance; idx row staged in shared memory; the fp64 city matrix (8 MB) is L2 resident,
-// writes are fully coalesced.  Optional fused reset normalisation (second pass hits L1/L2).
+// One CTA per instance; idx row staged in shared memory; the city matrix (fp64 8 MB, or its fp32 copy 4 MB made once
+// per city by rrnco_city_matrix_to_f32) is L2 resident, writes are fully coalesced.  Optional fused reset normalisation
+// (second pass hits L1/L2).  The kernel is bound by L2 -> SM sector traffic: n of the L columns of a row are wanted, so
+// nearly every element costs its own 32-byte sector (ncu: profiles/r1_ncu_gather.csv); the fp32 copy packs 8 elements
+// per sector instead of 4 (~70 instead of ~83 distinct sectors per row at n = 101, L = 1000).  Measured alternatives
+// that were slower: a warp per row with the tile kept in shared memory between the two passes (fewer resident CTAs,
+// fewer loads in flight: 0.25 ms vs 0.22 ms for 4096 instances).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gather_submatrix_kernel(const double* __restrict__ M, int L,
+template <typename T>
+__global__ void __launch_bounds__(256) gather_submatrix_kernel(const T* __restrict__ M, int L,
                                                                const int32_t* __restrict__ idx, int n,
                                                                float* __restrict__ out, int normalize,
                                                                float* __restrict__ mn, float* __restrict__ mx) {
@@ -86,6 +92,11 @@ __global__ void __launch_bounds__(256) gather_submatrix_kernel(const double* __r
   }
 }
 
+__global__ void __launch_bounds__(256) city_to_f32_kernel(int64_t n, const double* __restrict__ in, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (float)in[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // ATSP step      rrnco/envs/atsp/env.py:79-105
 // ------------------------------------------------------------------------------------------------
@@ -111,6 +122,67 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) atsp_step_kernel(
     cur_out[r] = a;
     done_out[r] = !any;  // count_nonzero(available) <= 0
   }
+}
+
+// Staged variant (un-aliased buffers): a warp owns blocks of 32 consecutive rollouts, whose mask rows (32 N bytes) are
+// contiguous and 16-byte aligned as a block.  cp.async keeps kStages - 1 blocks per warp in flight; each lane clears its
+// rollout's action byte in the staged copy and ORs its row (aligned words + edge bytes) for `done`; the block goes back
+// as 128-bit vectors.  Same warp-autonomous persistent pipeline as rcvrp_step_vec_kernel below, no CTA barrier.
+template <int kStages, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) atsp_step_vec_kernel(
+    int64_t n_groups, int N, const int64_t* __restrict__ action, const int64_t* __restrict__ step_i,
+    const uint8_t* __restrict__ mask_in, const int64_t* __restrict__ first_in, uint8_t* __restrict__ mask_out,
+    int64_t* __restrict__ first_out, int64_t* __restrict__ cur_out, uint8_t* __restrict__ done_out) {
+  extern __shared__ __align__(16) unsigned char sraw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = 32 * N;  // bytes of one mask block (multiple of 16)
+  unsigned char* wbase = sraw + (size_t)warp * kStages * nb;
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+  int64_t gi = (int64_t)blockIdx.x * kWarps + warp;
+  const bool first_step = step_i[0] == 0;
+  auto stage = [&](int64_t g, int b) {
+    unsigned char* s = wbase + b * nb;
+    const unsigned char* gm = mask_in + g * nb;
+    for (int i = lane; i < nb / 16; i += 32) cp_async16(s + i * 16, gm + i * 16);
+  };
+#pragma unroll
+  for (int k = 0; k < kStages - 1; ++k) {
+    if (gi + k * stride < n_groups) stage(gi + k * stride, k);
+    cp_async_commit();
+  }
+  int64_t a_n = 0, f_n = 0;
+  if (gi < n_groups) {
+    a_n = action[gi * 32 + lane];
+    if (!first_step) f_n = first_in[gi * 32 + lane];
+  }
+  for (int b = 0; gi < n_groups; gi += stride, b = (b + 1) % kStages) {
+    if (gi + (kStages - 1) * stride < n_groups) stage(gi + (kStages - 1) * stride, (b + kStages - 1) % kStages);
+    cp_async_commit();
+    const int64_t r = gi * 32 + lane;
+    const int64_t a = a_n, f = f_n;
+    if (gi + stride < n_groups) {  // next block's scalars: their latency hides under this block
+      a_n = action[(gi + stride) * 32 + lane];
+      if (!first_step) f_n = first_in[(gi + stride) * 32 + lane];
+    }
+    cp_async_wait<kStages - 1>();
+    __syncwarp();
+    unsigned char* s = wbase + b * nb;
+    const int o = lane * N, end = o + N;
+    s[o + (int)a] = 0;
+    const int a0 = min((o + 3) & ~3, end), a1 = max(end & ~3, a0);
+    uint32_t any = 0;
+    for (int q = o; q < a0; ++q) any |= s[q];
+    for (int q = a0; q < a1; q += 4) any |= *reinterpret_cast<const uint32_t*>(s + q);
+    for (int q = a1; q < end; ++q) any |= s[q];
+    first_out[r] = first_step ? a : f;
+    cur_out[r] = a;
+    done_out[r] = any == 0;  // count_nonzero(available) <= 0
+    __syncwarp();
+    uint4* om = reinterpret_cast<uint4*>(mask_out + gi * nb);
+    for (int i = lane; i < nb / 16; i += 32) om[i] = reinterpret_cast<const uint4*>(s)[i];
+    __syncwarp();  // the buffer is re-staged kStages - 1 iterations from now, after this warp's own reads
+  }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -312,19 +384,44 @@ struct RmtvrpState {
   uint8_t* visited;
 };
 
+// kShared: the CTA's warps are rollouts (starts) of ONE instance row (R = data_rows x starts, rollout r = s * data_rows +
+// row): the per-instance rows (time windows, service, demands) and column 0 of both matrices - 101 strided 32-byte
+// sectors each when read per rollout - are staged once per CTA in shared memory and shared by its warps.
+template <bool kShared>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmtvrp_step_kernel(
     int64_t R, int N, rrnco_instance_data_t d, const int64_t* __restrict__ action, RmtvrpState in,
     RmtvrpState out, uint8_t* done_out, uint8_t* mask_out) {
-  const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (r >= R) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t row = r % d.data_rows;
+  extern __shared__ __align__(16) float s_inst[];  // kShared: [col0 D | col0 Dur | tw (2N) | svc | dl | db]
+  int64_t r, row;
+  if (kShared) {
+    row = blockIdx.x % d.data_rows;
+    const int64_t s = (blockIdx.x / d.data_rows) * kWarpsPerBlock + (threadIdx.x >> 5);
+    r = s * d.data_rows + row;
+  } else {
+    r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    row = r % d.data_rows;
+  }
   const float* D = d.distance + row * (int64_t)N * N;
   const float* U = d.duration + row * (int64_t)N * N;
   const float* tw = d.time_windows + row * (int64_t)N * 2;
   const float* svc = d.service_time + row * (int64_t)N;
   const float* dl = d.demand + row * (int64_t)N;
   const float* db = d.demand_backhaul + row * (int64_t)N;
+  if (kShared) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      s_inst[n] = D[(int64_t)n * N];
+      s_inst[N + n] = U[(int64_t)n * N];
+      s_inst[2 * N + 2 * n] = tw[2 * n];
+      s_inst[2 * N + 2 * n + 1] = tw[2 * n + 1];
+      s_inst[4 * N + n] = svc[n];
+      s_inst[5 * N + n] = dl[n];
+      s_inst[6 * N + n] = db[n];
+    }
+    __syncthreads();
+    tw = s_inst + 2 * N, svc = s_inst + 4 * N, dl = s_inst + 5 * N, db = s_inst + 6 * N;
+  }
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
   const float cap = d.vehicle_capacity[row];
   const float limit = d.distance_limit[row];
   const float closed = d.open_route[row] ? 0.0f : 1.0f;  // "* ~open_route" (bool -> 0/1)
@@ -369,8 +466,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmtvrp_step_kernel(
     bool can = false;
     if (n < N) {
       const bool v = (action != nullptr ? out.visited[r * N + n] : in.visited[r * N + n]) != 0;
-      const float dist_ij = D[cur * N + n], dist_j0 = D[n * N];
-      const float dur_ij = U[cur * N + n], dur_j0 = U[n * N];
+      const float dist_ij = D[cur * N + n], dist_j0 = kShared ? s_inst[n] : D[n * N];
+      const float dur_ij = U[cur * N + n], dur_j0 = kShared ? s_inst[N + n] : U[n * N];
       const float early = tw[n * 2], late = tw[n * 2 + 1];
       const float arrival = __fadd_rn(time, dur_ij);
       const bool reach_c = arrival < late;
@@ -447,6 +544,18 @@ using namespace rrnco;
 
 static inline unsigned warp_grid(int64_t R) { return (unsigned)((R + kWarpsPerBlock - 1) / kWarpsPerBlock); }
 
+template <typename T>
+static int gather_launch(const T* city_matrix, int32_t city_len, const int32_t* idx, int64_t batch, int32_t n, float* out,
+                         int32_t normalize, float* min_out, float* max_out, void* stream) {
+  if (batch == 0) return RRNCO_OK;
+  RRNCO_CHECK_ARG(batch > 0 && n > 0 && city_len >= n && city_matrix && idx && out);
+  RRNCO_CHECK_ARG(!normalize || (min_out && max_out));
+  if ((size_t)n * sizeof(int32_t) > 48 * 1024) return RRNCO_ERR_UNSUPPORTED;
+  gather_submatrix_kernel<T><<<(unsigned)batch, 256, n * sizeof(int32_t), (cudaStream_t)stream>>>(
+      city_matrix, city_len, idx, n, out, normalize, min_out, max_out);
+  return rrnco_launch_status();
+}
+
 extern "C" {
 
 int rrnco_abi_version(void) { return RRNCO_ABI_VERSION; }
@@ -473,12 +582,20 @@ int rrnco_minmax_normalize(int64_t n_mat, int32_t n_nodes, const float* dist_in,
 int rrnco_gather_submatrix(const double* city_matrix, int32_t city_len, const int32_t* idx, int64_t batch,
                            int32_t n, float* out, int32_t normalize, float* min_out, float* max_out,
                            void* stream) {
-  if (batch == 0) return RRNCO_OK;
-  RRNCO_CHECK_ARG(batch > 0 && n > 0 && city_len >= n && city_matrix && idx && out);
-  RRNCO_CHECK_ARG(!normalize || (min_out && max_out));
-  if ((size_t)n * sizeof(int32_t) > 48 * 1024) return RRNCO_ERR_UNSUPPORTED;
-  gather_submatrix_kernel<<<(unsigned)batch, 256, n * sizeof(int32_t), (cudaStream_t)stream>>>(
-      city_matrix, city_len, idx, n, out, normalize, min_out, max_out);
+  return gather_launch(city_matrix, city_len, idx, batch, n, out, normalize, min_out, max_out, stream);
+}
+
+int rrnco_gather_submatrix_f32(const float* city_matrix_f32, int32_t city_len, const int32_t* idx, int64_t batch,
+                               int32_t n, float* out, int32_t normalize, float* min_out, float* max_out,
+                               void* stream) {
+  return gather_launch(city_matrix_f32, city_len, idx, batch, n, out, normalize, min_out, max_out, stream);
+}
+
+int rrnco_city_matrix_to_f32(const double* city_matrix, int64_t n_elems, float* out, void* stream) {
+  if (n_elems == 0) return RRNCO_OK;
+  RRNCO_CHECK_ARG(n_elems > 0 && city_matrix && out);
+  const int64_t blocks = (n_elems + 255) / 256;
+  city_to_f32_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, (cudaStream_t)stream>>>(n_elems, city_matrix, out);
   return rrnco_launch_status();
 }
 
@@ -488,8 +605,45 @@ int rrnco_atsp_step(int64_t R, int32_t n_nodes, const int64_t* action, const int
   if (R == 0) return RRNCO_OK;
   RRNCO_CHECK_ARG(R > 0 && n_nodes > 0 && action && step_i && mask_in && first_in && mask_out && first_out &&
                   current_out && done_out);
-  atsp_step_kernel<<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      R, n_nodes, action, step_i, mask_in, first_in, mask_out, first_out, current_out, done_out);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  struct VecCfg {
+    int stages, warps;
+    decltype(&atsp_step_vec_kernel<4, 16>) fn;
+  };
+  // deepest pipeline whose per-CTA staging (warps x stages x 32 N bytes) fits; one CTA per SM
+  static const VecCfg cfgs[] = {{4, 16, atsp_step_vec_kernel<4, 16>}, {2, 16, atsp_step_vec_kernel<2, 16>},
+                                {2, 8, atsp_step_vec_kernel<2, 8>}, {2, 4, atsp_step_vec_kernel<2, 4>},
+                                {2, 2, atsp_step_vec_kernel<2, 2>}};
+  const VecCfg* cfg = nullptr;
+  for (const VecCfg& c : cfgs)
+    if (!cfg && (size_t)c.warps * c.stages * 32 * n_nodes <= 200 * 1024) cfg = &c;
+  const bool vec_ok = cfg && R >= 32 && mask_in != mask_out && al16(mask_in) && al16(mask_out);
+  const int64_t R_vec = vec_ok ? (R / 32) * 32 : 0;
+  if (R_vec > 0) {
+    static int n_sm = 0;  // idempotent; benign if raced
+    if (n_sm == 0) {
+      int dev = 0, sms = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return RRNCO_ERR_CUDA;
+      for (const VecCfg& c : cfgs)
+        if (cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+          return RRNCO_ERR_CUDA;
+      n_sm = sms;
+    }
+    const int64_t n_groups = R_vec / 32;
+    const int64_t want = (n_groups + cfg->warps - 1) / cfg->warps;
+    const unsigned grid = (unsigned)(want < n_sm ? want : n_sm);
+    cfg->fn<<<grid, cfg->warps * 32, (size_t)cfg->warps * cfg->stages * 32 * n_nodes, (cudaStream_t)stream>>>(
+        n_groups, n_nodes, action, step_i, mask_in, first_in, mask_out, first_out, current_out, done_out);
+    int rc = rrnco_launch_status();
+    if (rc != RRNCO_OK) return rc;
+  }
+  if (R_vec < R) {  // tail, or aliased / unaligned buffers: one warp per rollout
+    const int64_t off = R_vec, Rt = R - R_vec;
+    atsp_step_kernel<<<warp_grid(Rt), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        Rt, n_nodes, action + off, step_i, mask_in + off * n_nodes, first_in + off, mask_out + off * n_nodes,
+        first_out + off, current_out + off, done_out + off);
+  }
   return rrnco_launch_status();
 }
 
@@ -575,8 +729,17 @@ int rrnco_rmtvrp_step(int64_t R, int32_t n_nodes, const rrnco_instance_data_t* d
     out = RmtvrpState{state_out->current_node, state_out->current_time, state_out->current_route_length,
                       state_out->used_capacity_linehaul, state_out->used_capacity_backhaul, state_out->visited};
   }
-  rmtvrp_step_kernel<<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(R, n_nodes, *data, action, in,
-                                                                                 out, done_out, mask_out);
+  const size_t smem = (size_t)7 * n_nodes * sizeof(float);
+  if (R % data->data_rows == 0 && R / data->data_rows >= 2 && smem <= 48 * 1024) {
+    // several rollouts per instance row: CTAs of kWarpsPerBlock starts of one row share its staged per-instance data
+    const int64_t starts = R / data->data_rows;
+    const int64_t groups = (starts + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    rmtvrp_step_kernel<true><<<(unsigned)(data->data_rows * groups), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+        R, n_nodes, *data, action, in, out, done_out, mask_out);
+  } else {
+    rmtvrp_step_kernel<false><<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(R, n_nodes, *data, action,
+                                                                                          in, out, done_out, mask_out);
+  }
   return rrnco_launch_status();
 }
 

@@ -23,10 +23,22 @@ class CityOnDevice:
         if "duration" in data:
             self.duration = torch.as_tensor(np.asarray(data["duration"]), dtype=torch.float64).to(device).contiguous()
         self.max_distance = float(np.asarray(data["distance"]).max())
+        # fp32 copies for the gather (made once per city; the fp32 cast commutes with the gather: same bits)
+        self.distance_f32 = city_matrix_to_f32(self.distance)
+        self.duration_f32 = city_matrix_to_f32(self.duration) if self.duration is not None else None
+
+
+def city_matrix_to_f32(matrix: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(matrix.shape, dtype=torch.float32, device=matrix.device)
+    call("rrnco_city_matrix_to_f32", ptr(matrix), matrix.numel(), ptr(out), stream_ptr(matrix.device))
+    return out
 
 
 def gather_submatrix(matrix: torch.Tensor, idx: torch.Tensor, normalize: bool = False):
-    """out[b,i,j] = float32(matrix[idx[b,i], idx[b,j]]); with normalize also returns (min, max) per instance."""
+    """out[b,i,j] = float32(matrix[idx[b,i], idx[b,j]]); with normalize also returns (min, max) per instance.
+    `matrix` is the fp64 city matrix or its fp32 copy (CityOnDevice.distance_f32): identical results."""
+    if matrix.dtype not in (torch.float64, torch.float32) or not matrix.is_contiguous():
+        raise TypeError("gather_submatrix: contiguous float64 / float32 city matrix expected")
     idx = idx.to(device=matrix.device, dtype=torch.int32).contiguous()
     B, n = idx.shape
     out = torch.empty((B, n, n), dtype=torch.float32, device=matrix.device)
@@ -34,7 +46,7 @@ def gather_submatrix(matrix: torch.Tensor, idx: torch.Tensor, normalize: bool = 
     if normalize:
         mn = torch.empty(B, dtype=torch.float32, device=matrix.device)
         mx = torch.empty_like(mn)
-    call("rrnco_gather_submatrix", ptr(matrix), matrix.shape[0], ptr(idx), B, n, ptr(out), int(normalize), ptr(mn),
+    call("rrnco_gather_submatrix" if matrix.dtype == torch.float64 else "rrnco_gather_submatrix_f32", ptr(matrix), matrix.shape[0], ptr(idx), B, n, ptr(out), int(normalize), ptr(mn),
          ptr(mx), stream_ptr(matrix.device))
     return (out, mn, mx) if normalize else out
 
@@ -63,7 +75,7 @@ class Real_World_Sampler:
             raise NotImplementedError(f"loc_dist='{loc_dist}': only 'uniform' is on the training configs")
         indices = self.uniform_sample(batch, city.length, num_sample)
         idx = torch.from_numpy(indices.astype(np.int32)).to(city.distance.device, non_blocking=True)
-        out = {"points": city.points[idx.long()].float(), "distance_matrix": gather_submatrix(city.distance, idx)}
+        out = {"points": city.points[idx.long()].float(), "distance_matrix": gather_submatrix(city.distance_f32, idx)}
         if self.with_duration:
-            out["duration_matrix"] = gather_submatrix(city.duration, idx)
+            out["duration_matrix"] = gather_submatrix(city.duration_f32, idx)
         return out

@@ -84,7 +84,8 @@ def test_env_forced_sequence_vs_reference_golden(rb, fname):
 
 
 @pytest.mark.parametrize("name,n,B", [("atsp", 100, 64), ("rcvrp", 100, 64), ("rcvrptw", 100, 64), ("rcvrp", 37, 33),
-                                        ("rcvrp", 28, 40), ("rcvrp", 40, 36), ("rcvrp", 4, 32)])
+                                        ("rcvrp", 28, 40), ("rcvrp", 40, 36), ("rcvrp", 4, 32), ("atsp", 37, 33),
+                                        ("atsp", 3, 32), ("rcvrptw", 30, 20)])
 def test_env_random_transitions_vs_oracle(rb, name, n, B):
     """>= 1e5 random forced transitions at n=100 in total: masks / visited bit-exact, scalars <= 1e-6 rel."""
     g = torch.Generator().manual_seed(n + B)
@@ -191,6 +192,8 @@ def test_gather_matches_reference_sampler_golden(rb):
     idx = torch.from_numpy(z["indices"])
     assert np.array_equal(gather_submatrix(c.distance, idx).cpu().numpy(), z["c.distance_matrix"].astype(np.float32))
     assert np.array_equal(gather_submatrix(c.duration, idx).cpu().numpy(), z["tw.duration_matrix"].astype(np.float32))
+    # the fp32 copy of the city matrix (what Real_World_Sampler gathers from) gives the same bits
+    assert np.array_equal(gather_submatrix(c.distance_f32, idx).cpu().numpy(), z["c.distance_matrix"].astype(np.float32))
     np.random.seed(4321)
     s = rb.Real_World_Sampler(with_duration=True).sample(c, 5, 11)
     assert np.array_equal(s["distance_matrix"].cpu().numpy(), z["tw.distance_matrix"].astype(np.float32))
@@ -214,6 +217,14 @@ def test_gather_full_size_and_fused_normalise(rb):
     lo, hi = want.amin((1, 2), keepdim=True), want.amax((1, 2), keepdim=True)
     assert torch.equal(got_n.cpu(), (want - lo) / (hi - lo + 1e-6))
     assert torch.equal(mn.cpu(), lo.flatten()) and torch.equal(mx.cpu(), hi.flatten())
+    for src in (c.distance, c.distance_f32):  # fp64 / fp32 source, shared-memory tile (n = 101) and re-read path (n = 300)
+        for n in (101, 300):
+            idx_n = osampler.uniform_sample(8, 1000, n, np.random.RandomState(n))
+            w = torch.from_numpy(osampler.gather_submatrix(city["distance"], idx_n).astype(np.float32))
+            g_n, mn_n, mx_n = gather_submatrix(src, torch.from_numpy(idx_n), normalize=True)
+            lo_n, hi_n = w.amin((1, 2), keepdim=True), w.amax((1, 2), keepdim=True)
+            assert torch.equal(gather_submatrix(src, torch.from_numpy(idx_n)).cpu(), w)
+            assert torch.equal(g_n.cpu(), (w - lo_n) / (hi_n - lo_n + 1e-6)) and torch.equal(mn_n.cpu(), lo_n.flatten())
     # idempotence property: gathering with the identity permutation returns the (cast) matrix itself
     ident = torch.arange(1000).unsqueeze(0)
     assert torch.equal(gather_submatrix(c.distance, ident)[0].cpu(), torch.from_numpy(city["distance"].astype(np.float32)))
