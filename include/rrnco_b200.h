@@ -69,6 +69,11 @@ int rrnco_set_precision(int32_t passes);
  *   0 = mma.sync tensor-core path (also what rrnco_decoder_logits uses) */
 int rrnco_set_ffn_engine(int32_t engine);
 
+/* Key sharing of the any-N per-step decoder (rrnco_decoder_logits_large; process-wide, set before use):
+ *   1 = one CTA per (instance, group of starts): key / value / logit-key rows staged once per CTA in shared memory (default)
+ *   0 = one warp per rollout streaming its own copy of the rows from L2 (first version; kept as the bit-exact cross-check) */
+int rrnco_set_step_tiling(int32_t on);
+
 /* ------------------------------------------------------------------------------------------------
  * env.reset: per-instance min-max normalisation of the distance matrix
  *   replaces RCVRPEnv._reset rrnco/envs/rcvrp/env.py:138-145 (same lines in atsp/env.py:113-120,

@@ -9,7 +9,7 @@ texts) on top of the C-ABI library `librrnco_b200.so` (include/rrnco_b200.h):
 
 No CPU fallback, no Triton / torch.compile: if the CUDA library is missing, calls raise.
 """
-from ._lib import RRNCOError, set_ffn_engine, set_precision  # noqa: F401
+from ._lib import RRNCOError, set_ffn_engine, set_precision, set_step_tiling  # noqa: F401
 from .envs import ATSPEnv, RCVRPEnv, RMTVRPEnv, get_env  # noqa: F401
 from .models import (PrecomputedCache, RRNetDecoder, RRNetPolicy, fused_rollout, select_action,  # noqa: F401
                      stepwise_rollout)
@@ -18,5 +18,5 @@ from .sampler import Real_World_Sampler  # noqa: F401
 from .tdlite import TensorDictLite, batchify, unbatchify  # noqa: F401
 
 __all__ = ["ATSPEnv", "RCVRPEnv", "RMTVRPEnv", "get_env", "RRNetDecoder", "RRNetPolicy", "PrecomputedCache",
-           "fused_rollout", "stepwise_rollout", "select_action", "Real_World_Sampler", "TensorDictLite", "batchify", "unbatchify", "set_precision", "set_ffn_engine",
+           "fused_rollout", "stepwise_rollout", "select_action", "Real_World_Sampler", "TensorDictLite", "batchify", "unbatchify", "set_precision", "set_ffn_engine", "set_step_tiling",
            "RRNCOError", "HostPrefetcher"]

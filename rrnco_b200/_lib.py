@@ -49,6 +49,7 @@ _SIGNATURES = {
     "rrnco_strerror": (C.c_char_p, [C.c_int]),
     "rrnco_set_precision": (C.c_int, [C.c_int32]),
     "rrnco_set_ffn_engine": (C.c_int, [C.c_int32]),
+    "rrnco_set_step_tiling": (C.c_int, [C.c_int32]),
     "rrnco_minmax_normalize": (C.c_int, [C.c_int64, C.c_int32, _f, _f, _f, _f, _f]),
     "rrnco_gather_submatrix": (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, _f, C.c_int32, _f, _f, _f]),
     "rrnco_gather_submatrix_f32": (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, _f, C.c_int32, _f, _f, _f]),
@@ -138,6 +139,11 @@ def call(name, *args):
 
 def set_precision(passes: int):
     check(lib().rrnco_set_precision(passes))
+
+
+def set_step_tiling(on: bool):
+    """Any-N per-step decoder: shared-memory key tiles per (instance, start group) (default) or per-rollout streaming."""
+    check(lib().rrnco_set_step_tiling(int(bool(on))))
 
 
 def set_ffn_engine(engine: int):

@@ -32,16 +32,9 @@ struct StepArgs {
   uint32_t* status;
 };
 
-__global__ void __launch_bounds__(kStepWarps * 32) attention_stream_kernel(const StepArgs a) {
-  const int64_t r = (int64_t)blockIdx.x * kStepWarps + (threadIdx.x >> 5);
-  if (r >= a.R) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t b = r % a.n_inst;
+// query: node half of the context projection (precomputed) + state scalars . state weights; lane l gets dims 4l..4l+3
+__device__ __forceinline__ float4 step_query(const StepArgs& a, int64_t r, int64_t b, int cur, int lane) {
   const int N = a.N;
-  const float4* Kb = reinterpret_cast<const float4*>(a.K + b * (int64_t)N * kE);
-  const float4* Vb = reinterpret_cast<const float4*>(a.V + b * (int64_t)N * kE);
-  const int cur = (int)a.cur[r];
-  // query: node half of the context projection (precomputed) + state scalars . state weights
   float4 q;
   if (a.env == RRNCO_ENV_ATSP) {
     if (a.use_placeholder) {
@@ -59,6 +52,38 @@ __global__ void __launch_bounds__(kStepWarps * 32) attention_stream_kernel(const
       q.x = fmaf(st, w4.x, q.x); q.y = fmaf(st, w4.y, q.y); q.z = fmaf(st, w4.z, q.z); q.w = fmaf(st, w4.w, q.w);
     }
   }
+  return q;
+}
+
+// one key of the online softmax of a head, for the lane that owns dims 4l..4l+3 (explicit fma / rn ops: the streaming and
+// the tiled kernel must round identically)
+__device__ __forceinline__ void attn_key(const float4& q, const float4& k4, const float4& v4, float& m, float& l, float4& acc) {
+  float s = fmaf(q.w, k4.w, fmaf(q.z, k4.z, fmaf(q.y, k4.y, __fmul_rn(q.x, k4.x))));
+  s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
+  s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 2));
+  s = __fmul_rn(s, 0.25f);  // 1 / sqrt(head dim 16)
+  const float mn = fmaxf(m, s);
+  const float corr = sfexp(__fsub_rn(m, mn)), p = sfexp(__fsub_rn(s, mn));
+  l = fmaf(l, corr, p);
+  acc.x = fmaf(acc.x, corr, __fmul_rn(p, v4.x)); acc.y = fmaf(acc.y, corr, __fmul_rn(p, v4.y));
+  acc.z = fmaf(acc.z, corr, __fmul_rn(p, v4.z)); acc.w = fmaf(acc.w, corr, __fmul_rn(p, v4.w));
+  m = mn;
+}
+__device__ __forceinline__ float4 attn_finish(const float4& q, const float4& acc, float l) {
+  const float inv = l > 0.f ? __frcp_rn(l) : 0.f;
+  return make_float4(fmaf(acc.x, inv, q.x), fmaf(acc.y, inv, q.y), fmaf(acc.z, inv, q.z), fmaf(acc.w, inv, q.w));
+}
+
+__global__ void __launch_bounds__(kStepWarps * 32) attention_stream_kernel(const StepArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * kStepWarps + (threadIdx.x >> 5);
+  if (r >= a.R) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = r % a.n_inst;
+  const int N = a.N;
+  const float4* Kb = reinterpret_cast<const float4*>(a.K + b * (int64_t)N * kE);
+  const float4* Vb = reinterpret_cast<const float4*>(a.V + b * (int64_t)N * kE);
+  const int cur = (int)a.cur[r];
+  const float4 q = step_query(a, r, b, cur, lane);
   // lane l owns dims 4l..4l+3 of head l >> 2; online softmax state is replicated over the 4 lanes of a head
   float m = -INFINITY, l = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -70,24 +95,68 @@ __global__ void __launch_bounds__(kStepWarps * 32) attention_stream_kernel(const
       const int j = __ffs(feas) - 1;
       feas &= feas - 1;
       const int n = n0 + j;
-      const float4 k4 = __ldg(Kb + (size_t)n * 32 + lane);
-      float s = q.x * k4.x + q.y * k4.y + q.z * k4.z + q.w * k4.w;
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s *= 0.25f;  // 1 / sqrt(head dim 16)
-      const float mn = fmaxf(m, s);
-      const float corr = sfexp(m - mn), p = sfexp(s - mn);
-      const float4 v4 = __ldg(Vb + (size_t)n * 32 + lane);
-      l = l * corr + p;
-      acc.x = acc.x * corr + p * v4.x; acc.y = acc.y * corr + p * v4.y;
-      acc.z = acc.z * corr + p * v4.z; acc.w = acc.w * corr + p * v4.w;
-      m = mn;
+      attn_key(q, __ldg(Kb + (size_t)n * 32 + lane), __ldg(Vb + (size_t)n * 32 + lane), m, l, acc);
     }
   }
-  const float inv = l > 0.f ? 1.0f / l : 0.f;
   if (l <= 0.f && lane == 0) atomicOr(a.status, RRNCO_DEV_NO_FEASIBLE);
-  float4 g4 = make_float4(acc.x * inv + q.x, acc.y * inv + q.y, acc.z * inv + q.z, acc.w * inv + q.w);
-  reinterpret_cast<float4*>(a.G + r * (int64_t)kE)[lane] = g4;  // glimpse = heads + q (decoder.py:292-293)
+  reinterpret_cast<float4*>(a.G + r * (int64_t)kE)[lane] = attn_finish(q, acc, l);  // glimpse = heads + q (decoder.py:292-293)
+}
+
+// Tiled variant of attention_stream_kernel: one CTA = one instance x blockDim / 32 consecutive starts (one warp per rollout, same
+// lane -> dims mapping and the same key order, so the glimpses are bit-identical).  Key / value rows are staged once per
+// CTA in double-buffered shared-memory tiles of 32 keys (cp.async) and shared by the CTA's rollouts; each warp walks
+// its own feasible keys of the tile.
+constexpr int kAtGMax = 16, kAtKeys = 32;  // up to 16 warps per CTA, 64 KB of tiles: 3 CTAs per SM
+__global__ void __launch_bounds__(kAtGMax * 32) attention_tile_kernel(const StepArgs a, int n_starts) {
+  extern __shared__ __align__(16) float asm_[];  // [2][K tile | V tile], each kAtKeys x kE
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = blockIdx.x % a.n_inst;
+  const int s = (int)(blockIdx.x / a.n_inst) * (int)(blockDim.x >> 5) + w;
+  const bool live = s < n_starts;
+  const int64_t r = live ? (int64_t)s * a.n_inst + b : 0;
+  const int N = a.N;
+  const float* Kb = a.K + b * (int64_t)N * kE;
+  const float* Vb = a.V + b * (int64_t)N * kE;
+  auto stage = [&](int t, int buf) {
+    float* dk = asm_ + buf * 2 * kAtKeys * kE;
+    float* dv = dk + kAtKeys * kE;
+    const int n0 = t * kAtKeys;
+    for (int i = threadIdx.x; i < kAtKeys * (kE / 4); i += blockDim.x) {
+      const int k = i / (kE / 4);
+      const bool ok = n0 + k < N;
+      const size_t src = (size_t)min(n0 + k, N - 1) * kE + (i % (kE / 4)) * 4;
+      cp_async16_zfill(dk + i * 4, Kb + src, ok);
+      cp_async16_zfill(dv + i * 4, Vb + src, ok);
+    }
+  };
+  const int n_tiles = (N + kAtKeys - 1) / kAtKeys;
+  stage(0, 0);
+  cp_async_commit();
+  const int cur = (int)a.cur[r];
+  const float4 q = step_query(a, r, b, cur, lane);
+  float m = -INFINITY, l = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint8_t* mrow = a.mask + r * (int64_t)N;
+  for (int t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) stage(t + 1, (t + 1) & 1);
+    cp_async_commit();
+    const int nn = t * kAtKeys + lane;
+    uint32_t feas = __ballot_sync(0xffffffffu, live && nn < N && mrow[nn] != 0);
+    cp_async_wait<1>();
+    __syncthreads();
+    const float4* Kt = reinterpret_cast<const float4*>(asm_ + (t & 1) * 2 * kAtKeys * kE);
+    const float4* Vt = Kt + kAtKeys * (kE / 4);
+    while (feas) {
+      const int j = __ffs(feas) - 1;
+      feas &= feas - 1;
+      attn_key(q, Kt[j * 32 + lane], Vt[j * 32 + lane], m, l, acc);
+    }
+    __syncthreads();  // every warp is done with buffer t & 1 before it is re-staged
+  }
+  cp_async_wait<0>();
+  if (!live) return;
+  if (l <= 0.f && lane == 0) atomicOr(a.status, RRNCO_DEV_NO_FEASIBLE);
+  reinterpret_cast<float4*>(a.G + r * (int64_t)kE)[lane] = attn_finish(q, acc, l);  // glimpse = heads + q (decoder.py:292-293)
 }
 
 __global__ void __launch_bounds__(kStepWarps * 32) logits_stream_kernel(const StepArgs a) {
@@ -123,6 +192,96 @@ __global__ void __launch_bounds__(kStepWarps * 32) logits_stream_kernel(const St
       a.logits[r * (int64_t)N + n] = lg;
     }
   }
+  if (__any_sync(0xffffffffu, nan_seen) && lane == 0) atomicOr(a.status, RRNCO_DEV_NAN_LOGITS);
+}
+
+// Tiled variant of logits_stream_kernel: one CTA = one instance x kLtG consecutive starts.  The logit-key rows are staged
+// once per CTA through a double-buffered shared-memory tile of 32 keys (cp.async, rows padded to 132 floats so that the
+// lane = key float4 reads are conflict-free) and shared by the CTA's rollouts, instead of every rollout streaming all
+// N x 512 B from L2 with 16-byte accesses at a 512-byte lane stride (ncu launch list, ATSP n=1000: 800 us of a 1.2 ms
+// decode step).  A warp owns 4 rollouts, lane = key; g' rows sit in shared memory and are read as broadcasts.  The
+// accumulation order per (rollout, key) is the same as in logits_stream_kernel, so the logits are bit-identical.
+constexpr int kLtWarps = 8, kLtPerWarp = 4, kLtG = kLtWarps * kLtPerWarp, kLtKeys = 32, kLtStride = kE + 4;
+__global__ void __launch_bounds__(kLtWarps * 32) logits_tile_kernel(const StepArgs a, int n_starts) {
+  extern __shared__ __align__(16) float lsm[];
+  float* sg = lsm;                                  // [kLtG][kE]
+  float* tiles = lsm + kLtG * kE;                   // [2][kLtKeys][kLtStride]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = blockIdx.x % a.n_inst;
+  const int s0 = (int)(blockIdx.x / a.n_inst) * kLtG;
+  const int n_here = min(kLtG, n_starts - s0);
+  const int N = a.N;
+  const int64_t drow = b % a.data_rows;
+  for (int i = threadIdx.x; i < kLtG * (kE / 4); i += blockDim.x) {
+    const int j = i / (kE / 4), c = i % (kE / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < n_here) v = reinterpret_cast<const float4*>(a.G + ((int64_t)(s0 + j) * a.n_inst + b) * kE)[c];
+    reinterpret_cast<float4*>(sg + j * kE)[c] = v;
+  }
+  const float* Lkb = a.Lk + b * (int64_t)N * kE;
+  auto stage = [&](int t, int buf) {
+    float* dst = tiles + buf * kLtKeys * kLtStride;
+    const int n0 = t * kLtKeys;
+    for (int i = threadIdx.x; i < kLtKeys * (kE / 4); i += blockDim.x) {
+      const int k = i / (kE / 4), c = i % (kE / 4);
+      cp_async16_zfill(dst + k * kLtStride + c * 4, Lkb + (size_t)min(n0 + k, N - 1) * kE + c * 4, n0 + k < N);
+    }
+  };
+  // blockIdx.y = chunk of key tiles (more CTAs than (instance, start group) pairs when those are few)
+  const int tiles_all = (N + kLtKeys - 1) / kLtKeys;
+  const int per_chunk = (tiles_all + gridDim.y - 1) / gridDim.y;
+  const int t_begin = blockIdx.y * per_chunk, t_end = min(tiles_all, t_begin + per_chunk);
+  if (t_begin >= t_end) return;
+  stage(t_begin, 0);
+  cp_async_commit();
+  int64_t rr[kLtPerWarp];
+  const float* Drow[kLtPerWarp];
+  const float* Urow[kLtPerWarp];
+#pragma unroll
+  for (int j = 0; j < kLtPerWarp; ++j) {
+    const int sj = s0 + w * kLtPerWarp + j;
+    rr[j] = sj < n_starts ? (int64_t)sj * a.n_inst + b : -1;
+    const int cur = rr[j] >= 0 ? (int)a.cur[rr[j]] : 0;
+    Drow[j] = a.dist + (drow * N + cur) * (int64_t)N;
+    Urow[j] = a.env == RRNCO_ENV_RCVRPTW ? a.dur + (drow * N + cur) * (int64_t)N : nullptr;
+  }
+  bool nan_seen = false;
+  for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
+    if (t + 1 < t_end) stage(t + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();  // tile t (and, at the first one, the g' rows) visible to every warp
+    const float4* krow = reinterpret_cast<const float4*>(tiles + buf * kLtKeys * kLtStride + lane * kLtStride);
+    float acc[kLtPerWarp];
+#pragma unroll
+    for (int j = 0; j < kLtPerWarp; ++j) acc[j] = 0.f;
+#pragma unroll 8
+    for (int d4 = 0; d4 < kE / 4; ++d4) {
+      const float4 k4 = krow[d4];
+#pragma unroll
+      for (int j = 0; j < kLtPerWarp; ++j) {
+        const float4 g4 = reinterpret_cast<const float4*>(sg + (w * kLtPerWarp + j) * kE)[d4];
+        acc[j] = fmaf(g4.x, k4.x, acc[j]); acc[j] = fmaf(g4.y, k4.y, acc[j]);
+        acc[j] = fmaf(g4.z, k4.z, acc[j]); acc[j] = fmaf(g4.w, k4.w, acc[j]);
+      }
+    }
+    const int n = t * kLtKeys + lane;
+    if (n < N) {
+#pragma unroll
+      for (int j = 0; j < kLtPerWarp; ++j) {
+        if (rr[j] < 0) continue;
+        float lg = acc[j] * 0.08838834764831845f;  // 1 / sqrt(128)
+        nan_seen |= lg != lg;
+        float bias = __fmul_rn(a.alpha, Drow[j][n]);
+        if (Urow[j]) bias = __fadd_rn(bias, __fmul_rn(a.beta, Urow[j][n]));
+        lg = __logf(__fadd_rn(sfexp(__fsub_rn(lg, bias)), 1e-6f));  // decoder.py:198
+        a.logits[rr[j] * (int64_t)N + n] = lg;
+      }
+    }
+    __syncthreads();  // every warp is done with this buffer before it is re-staged (the next iteration stages t + 2)
+  }
+  cp_async_wait<0>();
   if (__any_sync(0xffffffffu, nan_seen) && lane == 0) atomicOr(a.status, RRNCO_DEV_NAN_LOGITS);
 }
 
@@ -184,7 +343,14 @@ __global__ void __launch_bounds__(kStepWarps * 32) select_action_kernel(int64_t 
 
 using namespace rrnco;
 
+static int g_step_tiling = 1;  // rrnco_set_step_tiling (process-wide, read-only on the hot path)
+
 extern "C" {
+
+int rrnco_set_step_tiling(int32_t on) {
+  g_step_tiling = on != 0;
+  return RRNCO_OK;
+}
 
 int64_t rrnco_decoder_logits_large_workspace_bytes(int64_t n_rollouts) {
   if (n_rollouts <= 0) return 0;
@@ -220,13 +386,44 @@ int rrnco_decoder_logits_large(int32_t env, int32_t n_nodes, int64_t n_inst, int
   a.logits = logits_out; a.status = status;
   const unsigned grid = (unsigned)((a.R + kStepWarps - 1) / kStepWarps);
   a.G = g0;
-  attention_stream_kernel<<<grid, kStepWarps * 32, 0, st>>>(a);
+  if (g_step_tiling && n_starts >= 4) {  // rollouts of one instance share the staged key / value tiles
+    const size_t smem = (size_t)4 * kAtKeys * kE * sizeof(float);
+    static bool attr_set = false;  // idempotent; benign if raced
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(attention_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return RRNCO_ERR_CUDA;
+      attr_set = true;
+    }
+    // warps per CTA: the starts split evenly over the fewest groups of <= kAtGMax (100 starts -> 7 x 15).  Measured on
+    // BASELINE's ATSP n=1000 case: 16 warps 303 us per step, 20 warps (5 groups, one wave) 342 us - the CTA barriers
+    // per key tile cost more with wider CTAs than the second partial wave does.
+    const int64_t groups = (n_starts + kAtGMax - 1) / kAtGMax;
+    const int warps = (int)((n_starts + groups - 1) / groups);
+    attention_tile_kernel<<<(unsigned)(n_inst * groups), warps * 32, smem, st>>>(a, n_starts);
+  } else {
+    attention_stream_kernel<<<grid, kStepWarps * 32, 0, st>>>(a);
+  }
   int rc = rrnco_launch_status();
   if (rc != RRNCO_OK) return rc;
   rc = rrnco_pointer_ffn(a.R, g0, w->ffn_w1, w->ffn_b1, w->ffn_w2, w->ffn_b2, g1, ffn_ws, stream);
   if (rc != RRNCO_OK) return rc;
   a.G = g1;
-  logits_stream_kernel<<<grid, kStepWarps * 32, 0, st>>>(a);
+  if (g_step_tiling && n_starts >= kLtPerWarp) {  // rollouts of one instance share the staged logit keys
+    const size_t smem = (size_t)(kLtG * kE + 2 * kLtKeys * kLtStride) * sizeof(float);
+    static bool attr_set = false;  // idempotent; benign if raced
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(logits_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return RRNCO_ERR_CUDA;
+      attr_set = true;
+    }
+    const int64_t groups = (n_starts + kLtG - 1) / kLtG;
+    const int64_t tiles_all = (n_nodes + kLtKeys - 1) / kLtKeys;
+    int64_t chunks = 4 * 148 / (n_inst * groups);  // fill, but do not exceed, one wave of 4 CTAs per SM when CTAs are few
+    chunks = chunks < 1 ? 1 : chunks > tiles_all ? tiles_all : chunks;
+    logits_tile_kernel<<<dim3((unsigned)(n_inst * groups), (unsigned)chunks), kLtWarps * 32, smem, st>>>(a, n_starts);
+  } else {
+    logits_stream_kernel<<<grid, kStepWarps * 32, 0, st>>>(a);
+  }
   return rrnco_launch_status();
 }
 

@@ -405,6 +405,37 @@ def test_large_n_stepwise_rollout_vs_oracle(rb, name, n, B, S):
         assert (out["actions"].sort(1)[0] == torch.arange(N, device=dev)).all()
 
 
+@pytest.mark.parametrize("name,n,S", [("atsp", 200, 37), ("rcvrptw", 150, 20), ("rcvrp", 133, 5)])
+def test_large_n_tiled_decoder_matches_the_streaming_one(rb, name, n, S):
+    """rrnco_decoder_logits_large: shared-memory key tiles per (instance, start group) vs one warp streaming per rollout,
+    on a mid-rollout state with ragged groups.  Both use the same accumulation order; the tcgen05 FFN between the two
+    stages is reproducible to the last ulp only (several MMA-issuing threads), hence a 2e-6 bar instead of bit equality."""
+    B = 3
+    raw = synth.make_instances(name, B, n, seed=n)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    td = env.reset(lite(rb, raw))
+    N = td["action_mask"].shape[-1]
+    row, col = synth.random_embeddings(B, N, seed=n + 1)
+    pol = make_policy(rb, name, omodel.init_decoder_params(name, seed=n + 2), row.to(dev), col.to(dev))
+    cache = pol.decoder._precompute_cache((row.to(dev), col.to(dev)))
+    from rrnco_b200.models import _ROLLOUT_STATE_KEYS
+    roll = rb.TensorDictLite({k: (rb.batchify(td[k], S) if k in _ROLLOUT_STATE_KEYS[name] else td[k])
+                              for k in td.keys() if k != "done"}, batch_size=[B * S])
+    g = torch.Generator().manual_seed(n)
+    for _ in range(7):  # a few random feasible transitions so that masks / current nodes differ between the starts
+        a = torch.multinomial(roll["action_mask"].float().cpu(), 1, generator=g).squeeze(1).to(dev)
+        roll.set("action", a)
+        roll = env.step(roll)["next"]
+    try:
+        rb.set_step_tiling(True)
+        tiled, _ = pol.decoder(roll, cache, S)
+        rb.set_step_tiling(False)
+        streamed, _ = pol.decoder(roll, cache, S)
+    finally:
+        rb.set_step_tiling(True)
+    assert torch.isfinite(tiled).all() and (tiled - streamed).abs().max().item() < 2e-6
+
+
 def test_select_action_matches_process_logits(rb):
     """rrnco_select_action == decoding.py process_logits + greedy / evaluate on random logits and masks."""
     g = torch.Generator().manual_seed(3)
