@@ -13,10 +13,11 @@ from ._lib import RRNCOError, set_ffn_engine, set_precision, set_step_tiling  # 
 from .envs import ATSPEnv, RCVRPEnv, RMTVRPEnv, get_env  # noqa: F401
 from .models import (PrecomputedCache, RRNetDecoder, RRNetPolicy, fused_rollout, select_action,  # noqa: F401
                      stepwise_rollout)
+from .dataio import iter_batches, load_city_npz, load_npz_to_tensordict, prepare_test_td  # noqa: F401
 from .hostio import HostPrefetcher  # noqa: F401
 from .sampler import Real_World_Sampler  # noqa: F401
 from .tdlite import TensorDictLite, batchify, unbatchify  # noqa: F401
 
 __all__ = ["ATSPEnv", "RCVRPEnv", "RMTVRPEnv", "get_env", "RRNetDecoder", "RRNetPolicy", "PrecomputedCache",
            "fused_rollout", "stepwise_rollout", "select_action", "Real_World_Sampler", "TensorDictLite", "batchify", "unbatchify", "set_precision", "set_ffn_engine", "set_step_tiling",
-           "RRNCOError", "HostPrefetcher"]
+           "RRNCOError", "HostPrefetcher", "load_city_npz", "load_npz_to_tensordict", "prepare_test_td", "iter_batches"]

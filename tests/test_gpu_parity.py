@@ -161,6 +161,41 @@ def test_host_prefetcher_round_trip(rb):
         pf.submit({"a": torch.zeros(4), "b": batches[0]["b"]})
 
 
+def test_npz_test_set_through_prefetcher_matches_direct_path(rb, tmp_path):
+    """test.py:152-212 data path: test-set .npz -> pinned host -> HostPrefetcher -> reset -> x8 aug -> policy; same tours
+    and costs as feeding the tensors directly."""
+    B, n, S = 6, 20, 21
+    raw = synth.make_instances("rcvrp", B, n, seed=5)
+    data = {k: raw[k].numpy() for k in ("depot", "locs", "distance_matrix")}
+    data["demand"] = (raw["demand"] * 30).numpy()
+    data["capacity"] = np.full(B, 30, np.float32)
+    np.savez(tmp_path / "rcvrp20.npz", **data)
+    td_host = rb.prepare_test_td(rb.load_npz_to_tensordict(str(tmp_path / "rcvrp20.npz"), pin=True), "rcvrp")
+    env = rb.get_env("rcvrp", generator_params={"num_loc": n}, check_solution=False)
+    row, col = synth.random_embeddings(8 * B, n + 1, seed=6)
+    p = omodel.init_decoder_params("rcvrp", seed=7)
+    pf = rb.HostPrefetcher(dev)
+    costs, acts = [], []
+    for i, batch in enumerate(rb.iter_batches(td_host, 4)):
+        b = batch.batch_size[0]
+        d = pf.acquire(pf.submit({k: batch[k].contiguous().pin_memory() for k in batch.keys()}))
+        td = rb.batchify(env.reset(rb.TensorDictLite(dict(d), batch_size=[b])), 8)
+        sel = torch.cat([torch.arange(4 * i, 4 * i + b) + a * B for a in range(8)])
+        pol = make_policy(rb, "rcvrp", p, row[sel].to(dev), col[sel].to(dev))
+        out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+        costs.append(rb.unbatchify(out["reward"], (8, S)).amax(-1).amax(-1).cpu())
+        acts.append(out["actions"].cpu())
+    raw2 = TD({**{k: raw[k] for k in ("depot", "locs", "distance_matrix")}, "demand": torch.from_numpy(data["demand"]) / 30},
+              batch_size=[B])
+    td = rb.batchify(env.reset(lite(rb, raw2)), 8)
+    pol = make_policy(rb, "rcvrp", p, row.to(dev), col.to(dev))
+    out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    want = rb.unbatchify(out["reward"], (8, S)).amax(-1).amax(-1).cpu()
+    got = torch.cat(costs)
+    # identical inputs -> identical tours up to last-ulp near-ties of the tensor-pipe accumulation order (DESIGN 4.2)
+    assert ((got - want).abs() <= 1e-6 * want.abs()).float().mean() >= 5 / 6
+
+
 def test_env_edge_cases(rb):
     env = rb.RCVRPEnv(generator_params={"num_loc": 3}, check_solution=True)
     # demand exactly filling the vehicle is feasible (strict >), one that overflows by an ulp is not
