@@ -387,7 +387,10 @@ struct RmtvrpState {
 // kShared: the CTA's warps are rollouts (starts) of ONE instance row (R = data_rows x starts, rollout r = s * data_rows +
 // row): the per-instance rows (time windows, service, demands) and column 0 of both matrices - 101 strided 32-byte
 // sectors each when read per rollout - are staged once per CTA in shared memory and shared by its warps.
-template <bool kShared>
+// kIters > 0 (N <= 32 kIters): the node loops are unrolled and every global load of the rollout (visited bytes, the two
+// matrix rows of the new node) is issued before the first use, so one memory round trip covers them all; the visited
+// bytes stay in registers between the two passes (ncu of the rolled version: long_scoreboard was the top stall).
+template <bool kShared, int kIters>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmtvrp_step_kernel(
     int64_t R, int N, rrnco_instance_data_t d, const int64_t* __restrict__ action, RmtvrpState in,
     RmtvrpState out, uint8_t* done_out, uint8_t* mask_out) {
@@ -428,10 +431,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmtvrp_step_kernel(
   const float bclass = d.backhaul_class[row];
 
   int cur = (int)in.cur[r];
+  const int prev = cur;
+  if (action != nullptr) cur = (int)action[r];
   float time = in.time[r], route = in.route[r], used_l = in.used_l[r], used_b = in.used_b[r];
+  // rollout-private loads of the unrolled form, all in flight together
+  uint8_t vreg[kIters > 0 ? kIters : 1];
+  float dreg[kIters > 0 ? kIters : 1], ureg[kIters > 0 ? kIters : 1];
+  if (kIters > 0) {
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int n = it * 32 + lane;
+      vreg[it] = 0, dreg[it] = 0.f, ureg[it] = 0.f;
+      if (n < N) {
+        vreg[it] = in.visited[r * N + n];
+        dreg[it] = D[cur * N + n];
+        ureg[it] = U[cur * N + n];
+      }
+    }
+  }
   if (action != nullptr) {
-    const int prev = cur;
-    cur = (int)action[r];
     const float away = cur != 0 ? 1.0f : 0.0f;
     const float dist = D[prev * N + cur], dur = U[prev * N + cur];
     time = __fmul_rn(away, __fadd_rn(fmaxf(__fadd_rn(time, dur), tw[cur * 2]), svc[cur]));
@@ -442,11 +460,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmtvrp_step_kernel(
   // pass 1: visited update, done, linehauls_missing
   int n_visited = 0;
   bool missing = false;
-  for (int n0 = 0; n0 < N; n0 += 32) {
-    const int n = n0 + lane;
+  auto pass1 = [&](int n, uint8_t vb) -> uint8_t {
     bool v = false, miss = false;
     if (n < N) {
-      uint8_t vb = in.visited[r * N + n];
       if (action != nullptr) {
         if (n == cur) vb = 1;
         out.visited[r * N + n] = vb;
@@ -456,18 +472,26 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmtvrp_step_kernel(
     }
     n_visited += __popc(__ballot_sync(0xffffffffu, v));
     missing |= __any_sync(0xffffffffu, miss);
+    return vb;
+  };
+  if (kIters > 0) {
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) vreg[it] = pass1(it * 32 + lane, vreg[it]);
+  } else {
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      const int n = n0 + lane;
+      pass1(n, n < N ? in.visited[r * N + n] : (uint8_t)0);
+    }
+    __syncwarp();  // out.visited (may alias in.visited) is re-read below by the same lanes only
   }
-  __syncwarp();  // out.visited (may alias in.visited) is re-read below by the same lanes only
   const bool carrying_b = db[cur] > 0.0f;
   const float late0 = tw[1];
   bool any_cust = false;
-  for (int n0 = 0; n0 < N; n0 += 32) {
-    const int n = n0 + lane;
+  auto pass2 = [&](int n, bool v, float dist_ij, float dur_ij) {
     bool can = false;
     if (n < N) {
-      const bool v = (action != nullptr ? out.visited[r * N + n] : in.visited[r * N + n]) != 0;
-      const float dist_ij = D[cur * N + n], dist_j0 = kShared ? s_inst[n] : D[n * N];
-      const float dur_ij = U[cur * N + n], dur_j0 = kShared ? s_inst[N + n] : U[n * N];
+      const float dist_j0 = kShared ? s_inst[n] : D[n * N];
+      const float dur_j0 = kShared ? s_inst[N + n] : U[n * N];
       const float early = tw[n * 2], late = tw[n * 2 + 1];
       const float arrival = __fadd_rn(time, dur_ij);
       const bool reach_c = arrival < late;
@@ -484,6 +508,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rmtvrp_step_kernel(
       if (n >= 1) mask_out[r * N + n] = can;
     }
     any_cust |= __any_sync(0xffffffffu, can && n >= 1);
+  };
+  if (kIters > 0) {
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) pass2(it * 32 + lane, vreg[it] != 0, dreg[it], ureg[it]);
+  } else {
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      const int n = n0 + lane;
+      const bool inb = n < N;
+      const bool v = inb && (action != nullptr ? out.visited[r * N + n] : in.visited[r * N + n]) != 0;
+      pass2(n, v, inb ? D[cur * N + n] : 0.f, inb ? U[cur * N + n] : 0.f);
+    }
   }
   if (lane == 0) {
     mask_out[r * N] = !(cur == 0 && any_cust);
@@ -730,15 +765,18 @@ int rrnco_rmtvrp_step(int64_t R, int32_t n_nodes, const rrnco_instance_data_t* d
                       state_out->used_capacity_linehaul, state_out->used_capacity_backhaul, state_out->visited};
   }
   const size_t smem = (size_t)7 * n_nodes * sizeof(float);
+  const bool unrolled = n_nodes <= 128;
   if (R % data->data_rows == 0 && R / data->data_rows >= 2 && smem <= 48 * 1024) {
     // several rollouts per instance row: CTAs of kWarpsPerBlock starts of one row share its staged per-instance data
     const int64_t starts = R / data->data_rows;
     const int64_t groups = (starts + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    rmtvrp_step_kernel<true><<<(unsigned)(data->data_rows * groups), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+    auto fn = unrolled ? rmtvrp_step_kernel<true, 4> : rmtvrp_step_kernel<true, 0>;
+    fn<<<(unsigned)(data->data_rows * groups), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
         R, n_nodes, *data, action, in, out, done_out, mask_out);
   } else {
-    rmtvrp_step_kernel<false><<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(R, n_nodes, *data, action,
-                                                                                          in, out, done_out, mask_out);
+    auto fn = unrolled ? rmtvrp_step_kernel<false, 4> : rmtvrp_step_kernel<false, 0>;
+    fn<<<warp_grid(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(R, n_nodes, *data, action, in, out, done_out,
+                                                                     mask_out);
   }
   return rrnco_launch_status();
 }
