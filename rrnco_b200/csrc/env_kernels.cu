@@ -62,7 +62,12 @@ __global__ void __launch_bounds__(256) minmax_normalize_kernel(int n2, const flo
 // that were slower: a warp per row with the tile kept in shared memory between the two passes (fewer resident CTAs,
 // fewer loads in flight: 0.25 ms vs 0.22 ms for 4096 instances).
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+// kPer > 0 (normalize, n^2 <= 256 kPer): the thread's gathered values stay in registers between the min/max reduction and
+// the single, normalised write - no first write and no re-read of the output - and all its loads are in flight at once.
+// kPer == 0: chunks of 4 loads issued before their 4 stores (the first version had one load in flight per thread:
+// long_scoreboard 18.9 per issue at 90 % occupancy, profiles/r1_ncu_env_kernels_v3.txt).  (i, j) advance incrementally:
+// one integer division per thread instead of one per element.
+template <typename T, int kPer>
 __global__ void __launch_bounds__(256) gather_submatrix_kernel(const T* __restrict__ M, int L,
                                                                const int32_t* __restrict__ idx, int n,
                                                                float* __restrict__ out, int normalize,
@@ -70,22 +75,66 @@ __global__ void __launch_bounds__(256) gather_submatrix_kernel(const T* __restri
   extern __shared__ int32_t sidx[];
   __shared__ float red[64];
   const size_t b = blockIdx.x;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sidx[i] = idx[b * n + i];
+  for (int i = threadIdx.x; i < n; i += 256) sidx[i] = idx[b * n + i];
   __syncthreads();
   float* dst = out + b * (size_t)n * n;
   float lo = INFINITY, hi = -INFINITY;
   const int n2 = n * n;
-  for (int e = threadIdx.x; e < n2; e += blockDim.x) {
-    const int i = e / n, j = e - i * n;
-    const float v = (float)__ldg(M + (size_t)sidx[i] * L + sidx[j]);
-    dst[e] = v;
-    lo = fminf(lo, v);
-    hi = fmaxf(hi, v);
+  const int q = 256 / n, rem = 256 - q * n;
+  int i = threadIdx.x / n, j = threadIdx.x - i * n;
+  auto advance = [&]() {
+    j += rem;
+    i += q;
+    if (j >= n) {
+      j -= n;
+      ++i;
+    }
+  };
+  if (kPer > 0) {
+    float v[kPer > 0 ? kPer : 1];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      v[u] = 0.f;
+      if (threadIdx.x + u * 256 < n2) v[u] = (float)__ldg(M + (size_t)sidx[i] * L + sidx[j]);
+      advance();
+    }
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+      if (threadIdx.x + u * 256 < n2) {
+        lo = fminf(lo, v[u]);
+        hi = fmaxf(hi, v[u]);
+      }
+    block_minmax(lo, hi, red);
+    const float denom = __fadd_rn(__fsub_rn(hi, lo), 1e-6f);
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+      if (threadIdx.x + u * 256 < n2) dst[threadIdx.x + u * 256] = __fdiv_rn(__fsub_rn(v[u], lo), denom);
+    if (threadIdx.x == 0) {
+      mn[b] = lo;
+      mx[b] = hi;
+    }
+    return;
+  }
+  for (int e0 = threadIdx.x; e0 < n2; e0 += 4 * 256) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u] = 0.f;
+      if (e0 + u * 256 < n2) v[u] = (float)__ldg(M + (size_t)sidx[i] * L + sidx[j]);
+      advance();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (e0 + u * 256 < n2) {
+        dst[e0 + u * 256] = v[u];
+        lo = fminf(lo, v[u]);
+        hi = fmaxf(hi, v[u]);
+      }
   }
   if (!normalize) return;
   block_minmax(lo, hi, red);  // contains __syncthreads: dst writes of this CTA are visible below
   const float denom = __fadd_rn(__fsub_rn(hi, lo), 1e-6f);
-  for (int e = threadIdx.x; e < n2; e += blockDim.x) dst[e] = __fdiv_rn(__fsub_rn(dst[e], lo), denom);
+  for (int e = threadIdx.x; e < n2; e += 256) dst[e] = __fdiv_rn(__fsub_rn(dst[e], lo), denom);
   if (threadIdx.x == 0) {
     mn[b] = lo;
     mx[b] = hi;
@@ -586,8 +635,13 @@ static int gather_launch(const T* city_matrix, int32_t city_len, const int32_t* 
   RRNCO_CHECK_ARG(batch > 0 && n > 0 && city_len >= n && city_matrix && idx && out);
   RRNCO_CHECK_ARG(!normalize || (min_out && max_out));
   if ((size_t)n * sizeof(int32_t) > 48 * 1024) return RRNCO_ERR_UNSUPPORTED;
-  gather_submatrix_kernel<T><<<(unsigned)batch, 256, n * sizeof(int32_t), (cudaStream_t)stream>>>(
-      city_matrix, city_len, idx, n, out, normalize, min_out, max_out);
+  constexpr int kPer = 40;  // values per thread kept in registers: n <= 101
+  if (normalize && (int64_t)n * n <= (int64_t)kPer * 256)
+    gather_submatrix_kernel<T, kPer><<<(unsigned)batch, 256, n * sizeof(int32_t), (cudaStream_t)stream>>>(
+        city_matrix, city_len, idx, n, out, normalize, min_out, max_out);
+  else
+    gather_submatrix_kernel<T, 0><<<(unsigned)batch, 256, n * sizeof(int32_t), (cudaStream_t)stream>>>(
+        city_matrix, city_len, idx, n, out, normalize, min_out, max_out);
   return rrnco_launch_status();
 }
 
