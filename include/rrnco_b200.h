@@ -70,9 +70,11 @@ int rrnco_set_precision(int32_t passes);
 int rrnco_set_ffn_engine(int32_t engine);
 
 /* Key sharing of the any-N per-step decoder (rrnco_decoder_logits_large; process-wide, set before use):
- *   1 = one CTA per (instance, group of starts): key / value / logit-key rows staged once per CTA in shared memory (default)
- *   0 = one warp per rollout streaming its own copy of the rows from L2 (first version; kept as the bit-exact cross-check) */
-int rrnco_set_step_tiling(int32_t on);
+ *   1 = one CTA per (instance, group of starts): key / value / logit-key rows staged once per CTA in shared memory; the
+ *       pointer logits (starts x keys contraction) on mma.sync 3xTF32 tensor-core tiles (default)
+ *   2 = same tiling, logits as FFMA dot products in the accumulation order of mode 0
+ *   0 = one warp per rollout streaming its own copy of the rows from L2 (first version; kept as the cross-check) */
+int rrnco_set_step_tiling(int32_t mode);
 
 /* ------------------------------------------------------------------------------------------------
  * env.reset: per-instance min-max normalisation of the distance matrix

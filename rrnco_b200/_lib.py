@@ -141,9 +141,10 @@ def set_precision(passes: int):
     check(lib().rrnco_set_precision(passes))
 
 
-def set_step_tiling(on: bool):
-    """Any-N per-step decoder: shared-memory key tiles per (instance, start group) (default) or per-rollout streaming."""
-    check(lib().rrnco_set_step_tiling(int(bool(on))))
+def set_step_tiling(mode):
+    """Any-N per-step decoder: 1 / True = shared-memory key tiles per (instance, start group) with tensor-core logits
+    (default), 2 = same tiling with FFMA logits, 0 / False = per-rollout streaming."""
+    check(lib().rrnco_set_step_tiling(int(mode)))
 
 
 def set_ffn_engine(engine: int):

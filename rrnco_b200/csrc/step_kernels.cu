@@ -285,6 +285,109 @@ __global__ void __launch_bounds__(kLtWarps * 32) logits_tile_kernel(const StepAr
   if (__any_sync(0xffffffffu, nan_seen) && lane == 0) atomicOr(a.status, RRNCO_DEV_NAN_LOGITS);
 }
 
+// Tensor-core form of logits_tile_kernel: the logits of one instance are the dense contraction
+// [starts x 128] . [128 x keys] that the POMO starts share, so it runs on mma.sync m16n8k8 with the 3xTF32 split
+// (fp32-faithful, same helpers as the cache GEMM) instead of 128 FFMAs per (rollout, key).  One CTA = one instance x 32
+// starts x a chunk of key tiles; 8 warps = 2 (rollout halves) x 4 (16-key slices of a 64-key tile).  The warp's A
+// fragments (its 16 g' rows, hi | lo) are split once and stay in registers for every key tile; B fragments are split on
+// the fly from the cp.async-staged, 132-float-padded key tile (conflict-free: bank = 4 g + t).
+constexpr int kMmG = 32, kMmKeys = 64, kMmLd = kE + 4;
+__global__ void __launch_bounds__(256) logits_mma_kernel(const StepArgs a, int n_starts) {
+  extern __shared__ __align__(16) float msm[];
+  float* sg = msm;                       // [kMmG][kMmLd]
+  float* tiles = msm + kMmG * kMmLd;     // [2][kMmKeys][kMmLd]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int64_t b = blockIdx.x % a.n_inst;
+  const int s0 = (int)(blockIdx.x / a.n_inst) * kMmG;
+  const int N = a.N;
+  const int64_t drow = b % a.data_rows;
+  const int tiles_all = (N + kMmKeys - 1) / kMmKeys;
+  const int per_chunk = (tiles_all + gridDim.y - 1) / gridDim.y;
+  const int t_begin = blockIdx.y * per_chunk, t_end = min(tiles_all, t_begin + per_chunk);
+  if (t_begin >= t_end) return;
+  for (int i = threadIdx.x; i < kMmG * (kE / 4); i += blockDim.x) {
+    const int j = i / (kE / 4), c = i % (kE / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s0 + j < n_starts) v = reinterpret_cast<const float4*>(a.G + ((int64_t)(s0 + j) * a.n_inst + b) * kE)[c];
+    *reinterpret_cast<float4*>(sg + j * kMmLd + c * 4) = v;
+  }
+  const float* Lkb = a.Lk + b * (int64_t)N * kE;
+  auto stage = [&](int tt, int buf) {
+    float* dst = tiles + buf * kMmKeys * kMmLd;
+    const int n0 = tt * kMmKeys;
+    for (int i = threadIdx.x; i < kMmKeys * (kE / 4); i += blockDim.x) {
+      const int k = i / (kE / 4), c = i % (kE / 4);
+      cp_async16_zfill(dst + k * kMmLd + c * 4, Lkb + (size_t)min(n0 + k, N - 1) * kE + c * 4, n0 + k < N);
+    }
+  };
+  stage(t_begin, 0);
+  cp_async_commit();
+  // the two rollout rows this lane owns in the accumulator fragments: wm * 16 + g and + 8
+  int64_t rr[2];
+  const float* Drow[2];
+  const float* Urow[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int sj = s0 + wm * 16 + g + 8 * h;
+    rr[h] = sj < n_starts ? (int64_t)sj * a.n_inst + b : -1;
+    const int cur = rr[h] >= 0 ? (int)a.cur[rr[h]] : 0;
+    Drow[h] = a.dist + (drow * N + cur) * (int64_t)N;
+    Urow[h] = a.env == RRNCO_ENV_RCVRPTW ? a.dur + (drow * N + cur) * (int64_t)N : nullptr;
+  }
+  __syncthreads();  // g' rows visible
+  uint32_t ah[16][4], al[16][4];
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) {
+    const float* ap = sg + (wm * 16 + g) * kMmLd + ks * 8 + t;
+    split_tf32(ap[0], ah[ks][0], al[ks][0]);
+    split_tf32(ap[8 * kMmLd], ah[ks][1], al[ks][1]);
+    split_tf32(ap[4], ah[ks][2], al[ks][2]);
+    split_tf32(ap[8 * kMmLd + 4], ah[ks][3], al[ks][3]);
+  }
+  bool nan_seen = false;
+  for (int tt = t_begin; tt < t_end; ++tt) {
+    const int buf = (tt - t_begin) & 1;
+    if (tt + 1 < t_end) stage(tt + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* tile = tiles + buf * kMmKeys * kMmLd;
+    float acc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float* bp = tile + (wn * 16 + nt * 8 + g) * kMmLd + ks * 8 + t;
+        uint32_t bh[2], bl[2];
+        split_tf32(bp[0], bh[0], bl[0]);
+        split_tf32(bp[4], bh[1], bl[1]);
+        mma_x<3>(acc[nt], ah[ks], al[ks], bh, bl);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = tt * kMmKeys + wn * 16 + nt * 8 + 2 * t + e;
+          if (n >= N || rr[h] < 0) continue;
+          float lg = acc[nt][2 * h + e] * 0.08838834764831845f;  // 1 / sqrt(128)
+          nan_seen |= lg != lg;
+          float bias = __fmul_rn(a.alpha, Drow[h][n]);
+          if (Urow[h]) bias = __fadd_rn(bias, __fmul_rn(a.beta, Urow[h][n]));
+          lg = __logf(__fadd_rn(sfexp(__fsub_rn(lg, bias)), 1e-6f));  // decoder.py:198
+          a.logits[rr[h] * (int64_t)N + n] = lg;
+        }
+    __syncthreads();  // every warp is done with this buffer before it is re-staged
+  }
+  cp_async_wait<0>();
+  if (__any_sync(0xffffffffu, nan_seen) && lane == 0) atomicOr(a.status, RRNCO_DEV_NAN_LOGITS);
+}
+
 // DecodingStrategy.step: process_logits (tanh clip, mask, temperature, log-softmax) + greedy / Gumbel-max / forced
 __global__ void __launch_bounds__(kStepWarps * 32) select_action_kernel(int64_t R, int N, const float* __restrict__ logits,
                                                                        const uint8_t* __restrict__ mask, int mode,
@@ -347,8 +450,9 @@ static int g_step_tiling = 1;  // rrnco_set_step_tiling (process-wide, read-only
 
 extern "C" {
 
-int rrnco_set_step_tiling(int32_t on) {
-  g_step_tiling = on != 0;
+int rrnco_set_step_tiling(int32_t mode) {
+  if (mode < 0 || mode > 2) return RRNCO_ERR_BAD_ARG;
+  g_step_tiling = mode;
   return RRNCO_OK;
 }
 
@@ -394,11 +498,11 @@ int rrnco_decoder_logits_large(int32_t env, int32_t n_nodes, int64_t n_inst, int
         return RRNCO_ERR_CUDA;
       attr_set = true;
     }
-    // warps per CTA: the starts split evenly over the fewest groups of <= kAtGMax (100 starts -> 7 x 15).  Measured on
-    // BASELINE's ATSP n=1000 case: 16 warps 303 us per step, 20 warps (5 groups, one wave) 342 us - the CTA barriers
-    // per key tile cost more with wider CTAs than the second partial wave does.
+    // 16 warps per CTA, the last group of an instance ragged.  Measured on BASELINE's ATSP n=1000 case (100 starts): 7
+    // groups of 16 (the last one 4 warps) 303 us per step; 7 even groups of 15 warps 330-345 us; 5 groups of 20 warps
+    // (one wave) 342 us - the CTA barriers per key tile cost more with wider / more uniform CTAs than the partial wave.
     const int64_t groups = (n_starts + kAtGMax - 1) / kAtGMax;
-    const int warps = (int)((n_starts + groups - 1) / groups);
+    const int warps = n_starts < kAtGMax ? n_starts : kAtGMax;
     attention_tile_kernel<<<(unsigned)(n_inst * groups), warps * 32, smem, st>>>(a, n_starts);
   } else {
     attention_stream_kernel<<<grid, kStepWarps * 32, 0, st>>>(a);
@@ -408,7 +512,21 @@ int rrnco_decoder_logits_large(int32_t env, int32_t n_nodes, int64_t n_inst, int
   rc = rrnco_pointer_ffn(a.R, g0, w->ffn_w1, w->ffn_b1, w->ffn_w2, w->ffn_b2, g1, ffn_ws, stream);
   if (rc != RRNCO_OK) return rc;
   a.G = g1;
-  if (g_step_tiling && n_starts >= kLtPerWarp) {  // rollouts of one instance share the staged logit keys
+  if (g_step_tiling == 1 && n_starts >= 8) {  // the starts of one instance share the staged logit keys: tensor-core tiles
+    const size_t smem = (size_t)(kMmG * kMmLd + 2 * kMmKeys * kMmLd) * sizeof(float);
+    static bool attr_set = false;  // idempotent; benign if raced
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return RRNCO_ERR_CUDA;
+      attr_set = true;
+    }
+    const int64_t groups = (n_starts + kMmG - 1) / kMmG;
+    const int64_t tiles_all = (n_nodes + kMmKeys - 1) / kMmKeys;
+    // 174 registers: one CTA per SM; aim at >= 6 waves so that the last, partial one costs little
+    int64_t chunks = (6 * 148 + n_inst * groups - 1) / (n_inst * groups);
+    chunks = chunks < 1 ? 1 : chunks > tiles_all ? tiles_all : chunks;
+    logits_mma_kernel<<<dim3((unsigned)(n_inst * groups), (unsigned)chunks), 256, smem, st>>>(a, n_starts);
+  } else if (g_step_tiling && n_starts >= kLtPerWarp) {  // FFMA form of the same tiling (rrnco_set_step_tiling(2))
     const size_t smem = (size_t)(kLtG * kE + 2 * kLtKeys * kLtStride) * sizeof(float);
     static bool attr_set = false;  // idempotent; benign if raced
     if (!attr_set) {

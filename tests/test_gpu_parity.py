@@ -462,13 +462,17 @@ def test_large_n_tiled_decoder_matches_the_streaming_one(rb, name, n, S):
         roll.set("action", a)
         roll = env.step(roll)["next"]
     try:
-        rb.set_step_tiling(True)
+        rb.set_step_tiling(1)
+        tiled_mma, _ = pol.decoder(roll, cache, S)
+        rb.set_step_tiling(2)
         tiled, _ = pol.decoder(roll, cache, S)
-        rb.set_step_tiling(False)
+        rb.set_step_tiling(0)
         streamed, _ = pol.decoder(roll, cache, S)
     finally:
-        rb.set_step_tiling(True)
+        rb.set_step_tiling(1)
     assert torch.isfinite(tiled).all() and (tiled - streamed).abs().max().item() < 2e-6
+    # 3xTF32 tensor-core logits: fp32-faithful, not the same rounding (bar of the logits elsewhere in this file: 2e-5)
+    assert torch.isfinite(tiled_mma).all() and (tiled_mma - streamed).abs().max().item() < 1e-5
 
 
 def test_select_action_matches_process_logits(rb):
