@@ -18,6 +18,7 @@ Printed JSON line (rank 0): see the contract in the task statement; extra keys
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -312,8 +313,15 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
+        last = None
         for i in range(warmup):
-            fn(i)
+            # keep the previous result alive while the next step runs, exactly as the timed loop does: otherwise the
+            # second output set (867 MB of int64 actions) is first needed - and cudaMalloc'ed, ~100 ms - inside the
+            # second timed step (seen as a 90-105 ms outlier there in three of six round-1 runs)
+            last = fn(i)
+        # no generation-2 pass of Python's cyclic collector inside the timed region either
+        gc.collect()
+        gc.disable()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -327,6 +335,7 @@ def run_ours(args, rank, world, local_rank):
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
+        gc.enable()
         ms = max(e0.elapsed_time(e1), 0.0)
         if rank == 0:  # per-step device times (diagnostic only, stderr)
             ts = [e0.elapsed_time(m) for m in marks]
