@@ -17,6 +17,7 @@ ENV_ID = {"atsp": 0, "rcvrp": 1, "rcvrptw": 2}
 DECODE_ID = {"greedy": 0, "sampling": 1, "evaluate": 2}
 DEV_NAN_LOGITS, DEV_INFEASIBLE, DEV_NO_FEASIBLE = 1, 2, 4
 MAX_NODES_FUSED = 128
+MIN_STARTS_TILED = 8   # RRNetDecoder.forward: starts per instance from which the any-N tile kernels serve every N
 
 _f = C.c_void_p  # every device pointer travels as void*
 

@@ -202,7 +202,9 @@ class RRNetDecoder(nn.Module):
         logits = torch.empty((R, N), dtype=torch.float32, device=mask.device)
         status = torch.zeros(1, dtype=torch.int32, device=mask.device)
         cs = cached.struct()
-        if N <= _lib.MAX_NODES_FUSED:
+        # per-step kernels: with >= 8 starts per instance the key-sharing tile kernels (any N) are also the faster ones at
+        # N <= 128 (RCVRP n=100 x8 aug x101 starts, per-step loop: 904 vs 661 instances/s, tools/per_step_probe.py)
+        if N <= _lib.MAX_NODES_FUSED and S < _lib.MIN_STARTS_TILED:
             call("rrnco_decoder_logits", ENV_ID[self.env_name], N, n_inst, S, C.byref(w), C.byref(cs), C.byref(data),
                  ptr(cur), ptr(first), ptr(_u8(mask)), ptr(state), placeholder, ptr(logits), ptr(status),
                  stream_ptr(mask.device))

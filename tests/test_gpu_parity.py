@@ -475,6 +475,36 @@ def test_large_n_tiled_decoder_matches_the_streaming_one(rb, name, n, S):
     assert torch.isfinite(tiled_mma).all() and (tiled_mma - streamed).abs().max().item() < 1e-5
 
 
+def test_per_step_decoder_entry_points_agree_below_128_nodes(rb):
+    """RRNetDecoder.forward at N <= 128: `rrnco_decoder_logits` (the N <= 128 per-step kernel) and the any-N tile kernels
+    (`rrnco_decoder_logits_large`, the default from 8 starts per instance) give the same logits (bar 2e-5)."""
+    from rrnco_b200 import _lib
+    from rrnco_b200.models import _ROLLOUT_STATE_KEYS
+    name, n, B, S = "rcvrptw", 50, 5, 19
+    raw = synth.make_instances(name, B, n, seed=3)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    td = env.reset(lite(rb, raw))
+    N = td["action_mask"].shape[-1]
+    row, col = synth.random_embeddings(B, N, seed=4)
+    pol = make_policy(rb, name, omodel.init_decoder_params(name, seed=5), row.to(dev), col.to(dev))
+    cache = pol.decoder._precompute_cache((row.to(dev), col.to(dev)))
+    roll = rb.TensorDictLite({k: (rb.batchify(td[k], S) if k in _ROLLOUT_STATE_KEYS[name] else td[k])
+                              for k in td.keys() if k != "done"}, batch_size=[B * S])
+    g = torch.Generator().manual_seed(1)
+    for _ in range(5):
+        a = torch.multinomial(roll["action_mask"].float().cpu(), 1, generator=g).squeeze(1).to(dev)
+        roll.set("action", a)
+        roll = env.step(roll)["next"]
+    keep = _lib.MIN_STARTS_TILED
+    try:
+        tiled, _ = pol.decoder(roll, cache, S)
+        _lib.MIN_STARTS_TILED = 1 << 30
+        small, _ = pol.decoder(roll, cache, S)
+    finally:
+        _lib.MIN_STARTS_TILED = keep
+    assert torch.isfinite(tiled).all() and (tiled - small).abs().max().item() < 2e-5
+
+
 def test_select_action_matches_process_logits(rb):
     """rrnco_select_action == decoding.py process_logits + greedy / evaluate on random logits and masks."""
     g = torch.Generator().manual_seed(3)
