@@ -17,7 +17,10 @@ from .dataio import iter_batches, load_city_npz, load_npz_to_tensordict, prepare
 from .hostio import HostPrefetcher  # noqa: F401
 from .sampler import Real_World_Sampler  # noqa: F401
 from .tdlite import TensorDictLite, batchify, unbatchify  # noqa: F401
+from .training import (batched_logprobs, collect_decode_inputs, pomo_shared_baseline_loss,  # noqa: F401
+                       replay_log_likelihood)
 
 __all__ = ["ATSPEnv", "RCVRPEnv", "RMTVRPEnv", "get_env", "RRNetDecoder", "RRNetPolicy", "PrecomputedCache",
            "fused_rollout", "stepwise_rollout", "select_action", "Real_World_Sampler", "TensorDictLite", "batchify", "unbatchify", "set_precision", "set_ffn_engine", "set_step_tiling",
-           "RRNCOError", "HostPrefetcher", "load_city_npz", "load_npz_to_tensordict", "prepare_test_td", "iter_batches"]
+           "RRNCOError", "HostPrefetcher", "load_city_npz", "load_npz_to_tensordict", "prepare_test_td", "iter_batches", "replay_log_likelihood", "batched_logprobs", "collect_decode_inputs",
+           "pomo_shared_baseline_loss"]

@@ -1,0 +1,138 @@
+"""Training hand-off: gradients for REINFORCE from rollouts sampled by the fused kernel.
+
+The fused rollout kernel is forward-only.  Upstream's training step (`rrnco/models/rl.py:99-130`) needs
+`log_likelihood` with a graph to the decoder parameters and the encoder output.  Here the two are separated:
+
+  1. actions are sampled by `RRNetPolicy.forward(..., phase="train")` on the fused kernel (no graph);
+  2. `replay_log_likelihood` re-evaluates log pi(a_t | s_t) for those actions with autograd:
+     a) the env is replayed on the CUDA step kernels (no graph) to collect the decoder inputs of every step - current /
+        first node, state scalars, action mask (`collect_decode_inputs`);
+     b) because the actions are known, ALL decode steps are evaluated at once as dense batched torch ops
+        (`batched_logprobs`: context projection, 8-head masked attention, FFN + residual, pointer logits, scale-adaptive
+        bias, tanh clip, mask, log-softmax; decoder.py:151-206,281-326, decoding.py:311-361) instead of upstream's T
+        sequential small-kernel steps; autograd gives the gradients (cuBLAS / ATen: library code, like the encoder).
+  3. `pomo_shared_baseline_loss` = rl4co REINFORCE with the shared (POMO) baseline [rl4co-recalled], rl.py:119-128.
+
+`batched_logprobs` is device-agnostic torch and is checked against the oracle's per-step decoder on the CPU; the
+replay-vs-kernel agreement (log-likelihood of the fused kernel's evaluate mode) is checked on the GPU.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .tdlite import TensorDictLite, batchify
+
+
+def collect_decode_inputs(decoder, env, td, actions: torch.Tensor, num_starts: int) -> dict:
+    """Replays `actions` [R, T] (R = num_starts * n_inst, multistart order) through the env's CUDA step kernels and
+    records, for every decoder call (steps 1..T-1; step 0 is the forced POMO start, decoding.py:186-192), what the
+    decoder saw: current_node [T-1, R], first_node (atsp), ctx_state [T-1, R, k], action_mask [T-1, R, N]."""
+    from .models import _ROLLOUT_STATE_KEYS
+    name = decoder.env_name
+    S = int(num_starts)
+    if S < 2:
+        raise NotImplementedError("training replay is multistart (POMO) only, as rl.py:119 asserts")
+    R, T = actions.shape
+    roll = TensorDictLite({k: (batchify(td[k], S) if k in _ROLLOUT_STATE_KEYS[name] else td[k])
+                           for k in td.keys() if k != "done"}, batch_size=[R])
+    roll.set("action", actions[:, 0].contiguous())
+    roll = env.step(roll)["next"]
+    cur, first, state, mask = [], [], [], []
+    for t in range(1, T):
+        cur.append(roll["current_node"].reshape(-1).clone())
+        mask.append(roll["action_mask"].clone())
+        if name == "atsp":
+            first.append(roll["first_node"].reshape(-1).clone())
+        else:
+            state.append(decoder._ctx_state(roll).clone())
+        roll.set("action", actions[:, t].contiguous())
+        roll = env.step(roll)["next"]
+    out = {"current_node": torch.stack(cur), "action_mask": torch.stack(mask)}
+    if name == "atsp":
+        out["first_node"] = torch.stack(first)
+    else:
+        out["ctx_state"] = torch.stack(state)
+    return out
+
+
+def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict, actions: torch.Tensor,
+                     num_starts: int, temperature: float = 1.0, tanh_clipping: float = 10.0,
+                     step_chunk: int = 32) -> torch.Tensor:
+    """log pi(a_t | s_t) for t = 1..T-1, [R, T-1], differentiable w.r.t. the decoder parameters, row_emb and col_emb.
+    Rollout r = s * n_inst + b (upstream's batchify order); instance data is never replicated over the starts."""
+    name, E, H = decoder.env_name, decoder.embed_dim, decoder.num_heads
+    n_inst, N, _ = col_emb.shape
+    S = int(num_starts)
+    R = S * n_inst
+    Tm = inputs["current_node"].shape[0]
+    k, v, lk = F.linear(col_emb, decoder.project_node_embeddings.weight).chunk(3, dim=-1)  # decoder.py:214-232
+    W = decoder.context_embedding.project_context.weight
+
+    def heads(x):  # [n_inst, L, E] -> [n_inst, H, L, E / H]
+        return x.unflatten(-1, (H, -1)).transpose(1, 2)
+
+    kh, vh = heads(k), heads(v)
+    inst = torch.arange(n_inst, device=col_emb.device)
+    w1, b1 = decoder.pointer.ffn.lins[0].weight, decoder.pointer.ffn.lins[0].bias
+    w2, b2 = decoder.pointer.ffn.lins[1].weight, decoder.pointer.ffn.lins[1].bias
+    out = []
+    for t0 in range(0, Tm, step_chunk):
+        t1 = min(Tm, t0 + step_chunk)
+        L = (t1 - t0) * S
+
+        def per_inst(x):  # [Tc, R, ...] with r = s * n_inst + b  ->  [n_inst, Tc * S, ...]
+            return x.unflatten(1, (S, n_inst)).movedim(2, 0).flatten(1, 2)
+
+        cur = per_inst(inputs["current_node"][t0:t1])                      # [n_inst, L]
+        mask = per_inst(inputs["action_mask"][t0:t1]).bool()               # [n_inst, L, N]
+        act = per_inst(actions[:, 1 + t0:1 + t1].t().contiguous())         # [n_inst, L]
+        emb_cur = row_emb[inst[:, None], cur]                              # [n_inst, L, E]
+        if name == "atsp":  # rl4co TSPContext: [first, current] (multistart: never the placeholder)
+            first = per_inst(inputs["first_node"][t0:t1])
+            ctx = torch.cat([row_emb[inst[:, None], first], emb_cur], -1)
+        else:               # context.py:18-31: [current-node embedding, state scalars]
+            ctx = torch.cat([emb_cur, per_inst(inputs["ctx_state"][t0:t1]).to(emb_cur.dtype)], -1)
+        q = F.linear(ctx, W)                                               # [n_inst, L, E]
+        h = F.scaled_dot_product_attention(heads(q), kh, vh, attn_mask=mask.unsqueeze(1))  # decoder.py:281-293
+        g = h.transpose(1, 2).flatten(-2) + q
+        g = F.linear(F.relu(F.linear(g, w1, b1)), w2, b2) + g              # decoder.py:296
+        logits = torch.bmm(g, lk.transpose(1, 2)) / math.sqrt(E)           # [n_inst, L, N]
+        bias = decoder.alpha * distance[inst[:, None], cur]                # decoder.py:183-198
+        if name == "rcvrptw":
+            bias = bias + decoder.beta * duration[inst[:, None], cur]
+        logits = torch.log(torch.exp(logits - bias) + 1e-6)
+        if tanh_clipping > 0:                                              # decoding.py:311-361
+            logits = torch.tanh(logits) * tanh_clipping
+        logits = logits.masked_fill(~mask, float("-inf")) / temperature
+        logp = F.log_softmax(logits, dim=-1).gather(-1, act.unsqueeze(-1)).squeeze(-1)   # [n_inst, L]
+        out.append(logp.unflatten(1, (t1 - t0, S)).permute(2, 0, 1).reshape(R, t1 - t0))  # back to r = s * n_inst + b
+    return torch.cat(out, 1)
+
+
+def replay_log_likelihood(policy, td, env, actions: torch.Tensor, num_starts: int, phase: str = "train",
+                          embeddings=None, temperature=None, tanh_clipping=None, step_chunk: int = 32):
+    """log_likelihood [R] of `actions` with a graph to the decoder parameters and the encoder (policy.py:240-243 for the
+    Evaluate strategy, decoding.py:386-399).  `td` is the reset td of the batch the actions were sampled on."""
+    row_emb, col_emb = embeddings if embeddings is not None else policy.encoder(td, phase=phase)
+    with torch.no_grad():
+        inputs = collect_decode_inputs(policy.decoder, env, td, actions, num_starts)
+    dur = td["duration_matrix"].float() if policy.decoder.env_name == "rcvrptw" else None
+    logp = batched_logprobs(policy.decoder, row_emb.float(), col_emb.float(), td["distance_matrix"].float(), dur, inputs,
+                            actions, num_starts, policy.temperature if temperature is None else temperature,
+                            policy.tanh_clipping if tanh_clipping is None else tanh_clipping, step_chunk)
+    if not bool((logp > -1000).all()):
+        raise AssertionError("Logprobs should not be -inf, check sampling procedure!")
+    return logp.sum(1)
+
+
+def pomo_shared_baseline_loss(reward: torch.Tensor, log_likelihood: torch.Tensor, num_starts: int) -> torch.Tensor:
+    """REINFORCE with the shared baseline over the starts of an instance (rl.py:112-128 + rl4co REINFORCE.calculate_loss
+    with baseline "shared" [rl4co-recalled]): advantage = reward - mean_s reward; loss = -(advantage * log pi).mean()."""
+    S = int(num_starts)
+    r = reward.unflatten(0, (S, -1))          # [S, n_inst] (r = s * n_inst + b)
+    ll = log_likelihood.unflatten(0, (S, -1))
+    advantage = r - r.mean(0, keepdim=True)
+    return -(advantage.detach() * ll).mean()

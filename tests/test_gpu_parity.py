@@ -475,6 +475,31 @@ def test_large_n_tiled_decoder_matches_the_streaming_one(rb, name, n, S):
     assert torch.isfinite(tiled_mma).all() and (tiled_mma - streamed).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("name,n,B", [("rcvrp", 50, 6), ("rcvrptw", 30, 4), ("atsp", 40, 3)])
+def test_training_handoff_replay_matches_fused_kernel_loglik(rb, name, n, B):
+    """rl.py:99-130 hand-off: actions sampled by the fused kernel; the differentiable batched replay (env replayed on the
+    CUDA step kernels, all decode steps as dense torch ops) reproduces the kernel's log-likelihoods and yields finite,
+    non-zero gradients for the decoder parameters and the encoder output."""
+    raw = synth.make_instances(name, B, n, seed=n)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    td = env.reset(lite(rb, raw))
+    N = td["action_mask"].shape[-1]
+    S = env.get_num_starts(td)
+    row, col = synth.random_embeddings(B, N, seed=n + 1)
+    row, col = row.to(dev).requires_grad_(True), col.to(dev).requires_grad_(True)
+    pol = make_policy(rb, name, omodel.init_decoder_params(name, seed=n + 2), row, col)
+    with torch.no_grad():
+        out = pol(td, env, phase="train", decode_type="multistart_sampling", num_starts=S)
+    ll = rb.replay_log_likelihood(pol, td, env, out["actions"], S, embeddings=(row, col))
+    assert ll.shape == out["log_likelihood"].shape and ll.requires_grad
+    assert (ll - out["log_likelihood"]).abs().max().item() < 2e-3, (ll - out["log_likelihood"]).abs().max()
+    loss = rb.pomo_shared_baseline_loss(out["reward"], ll, S)
+    loss.backward()
+    for gname, gten in (("W1", pol.decoder.pointer.ffn.lins[0].weight.grad), ("Wnode", pol.decoder.project_node_embeddings.weight.grad),
+                        ("alpha", pol.decoder.alpha.grad), ("row", row.grad), ("col", col.grad)):
+        assert gten is not None and torch.isfinite(gten).all() and gten.abs().max() > 0, gname
+
+
 def test_per_step_decoder_entry_points_agree_below_128_nodes(rb):
     """RRNetDecoder.forward at N <= 128: `rrnco_decoder_logits` (the N <= 128 per-step kernel) and the any-N tile kernels
     (`rrnco_decoder_logits_large`, the default from 8 starts per instance) give the same logits (bar 2e-5)."""
