@@ -1,0 +1,55 @@
+"""Training hand-off at a C5-like per-GPU shape (RCVRP n=100, 512 instances x 101 starts, sampling, no augmentation):
+fused sampling rollout + differentiable batched replay + backward (rrnco_b200/training.py).
+   python tools/train_step_probe.py [instances]"""
+import os, sys, time
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import rrnco_b200 as rb  # noqa: E402
+from oracle import synth, model as omodel  # noqa: E402  (input generator + default-initialised weights only)
+
+dev = torch.device("cuda", 0)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+n, S = 100, 101
+raw = synth.make_instances("rcvrp", B, n, seed=1)
+env = rb.get_env("rcvrp", generator_params={"num_loc": n}, check_solution=False)
+td = env.reset(rb.TensorDictLite({k: v.to(dev) for k, v in raw.items()}, batch_size=[B]))
+row, col = synth.random_embeddings(B, n + 1, seed=2)
+row, col = row.to(dev).requires_grad_(True), col.to(dev).requires_grad_(True)
+
+
+class Enc(torch.nn.Module):
+    def forward(self, td, phase=None):
+        return row, col
+
+
+pol = rb.RRNetPolicy(encoder=Enc(), env_name="rcvrp").to(dev)
+pol.decoder.load_state_dict(omodel.init_decoder_params("rcvrp", seed=1234))
+
+
+def sync_time():
+    torch.cuda.synchronize()
+    return time.perf_counter()
+
+
+for it in range(3):
+    torch.cuda.reset_peak_memory_stats()
+    t0 = sync_time()
+    with torch.no_grad():
+        out = pol(td, env, phase="train", decode_type="multistart_sampling", num_starts=S)
+    t1 = sync_time()
+    with torch.no_grad():
+        inputs = rb.collect_decode_inputs(pol.decoder, env, td, out["actions"], S)
+    t2 = sync_time()
+    logp = rb.batched_logprobs(pol.decoder, row, col, td["distance_matrix"].float(), None, inputs, out["actions"], S)
+    ll = logp.sum(1)
+    loss = rb.pomo_shared_baseline_loss(out["reward"], ll, S)
+    t3 = sync_time()
+    loss.backward()
+    t4 = sync_time()
+    err = (ll - out["log_likelihood"]).abs().max().item()
+    print(f"iter {it}: B={B} S={S} T={out['actions'].shape[1]}  sample (fused kernel) {1e3*(t1-t0):7.1f} ms | env replay "
+          f"{1e3*(t2-t1):7.1f} | batched logprobs fwd {1e3*(t3-t2):7.1f} | bwd {1e3*(t4-t3):7.1f} | total {1e3*(t4-t0):7.1f} ms "
+          f"= {B/(t4-t0):7.1f} instances/s | max |ll - kernel ll| {err:.1e} | peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB")
+    pol.zero_grad(set_to_none=True)
+    row.grad = col.grad = None
