@@ -60,9 +60,15 @@ def collect_decode_inputs(decoder, env, td, actions: torch.Tensor, num_starts: i
 
 def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict, actions: torch.Tensor,
                      num_starts: int, temperature: float = 1.0, tanh_clipping: float = 10.0,
-                     step_chunk: int = 32) -> torch.Tensor:
+                     step_chunk: int = 32, autocast_dtype=None) -> torch.Tensor:
     """log pi(a_t | s_t) for t = 1..T-1, [R, T-1], differentiable w.r.t. the decoder parameters, row_emb and col_emb.
-    Rollout r = s * n_inst + b (upstream's batchify order); instance data is never replicated over the starts."""
+    Rollout r = s * n_inst + b (upstream's batchify order); instance data is never replicated over the starts.
+    `autocast_dtype` (e.g. torch.bfloat16): run the contractions under torch.autocast, as upstream's trainer does
+    (`configs/trainer/default.yaml:8` precision "16-mixed"); default fp32."""
+    if autocast_dtype is not None:
+        with torch.autocast(col_emb.device.type, dtype=autocast_dtype):
+            return batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs, actions, num_starts,
+                                    temperature, tanh_clipping, step_chunk, None)
     name, E, H = decoder.env_name, decoder.embed_dim, decoder.num_heads
     n_inst, N, _ = col_emb.shape
     S = int(num_starts)
@@ -99,7 +105,7 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
         h = F.scaled_dot_product_attention(heads(q), kh, vh, attn_mask=mask.unsqueeze(1))  # decoder.py:281-293
         g = h.transpose(1, 2).flatten(-2) + q
         g = F.linear(F.relu(F.linear(g, w1, b1)), w2, b2) + g              # decoder.py:296
-        logits = torch.bmm(g, lk.transpose(1, 2)) / math.sqrt(E)           # [n_inst, L, N]
+        logits = torch.bmm(g, lk.transpose(1, 2)).float() / math.sqrt(E)   # [n_inst, L, N]
         bias = decoder.alpha * distance[inst[:, None], cur]                # decoder.py:183-198
         if name == "rcvrptw":
             bias = bias + decoder.beta * duration[inst[:, None], cur]
@@ -113,7 +119,8 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
 
 
 def replay_log_likelihood(policy, td, env, actions: torch.Tensor, num_starts: int, phase: str = "train",
-                          embeddings=None, temperature=None, tanh_clipping=None, step_chunk: int = 32):
+                          embeddings=None, temperature=None, tanh_clipping=None, step_chunk: int = 32,
+                          autocast_dtype=None):
     """log_likelihood [R] of `actions` with a graph to the decoder parameters and the encoder (policy.py:240-243 for the
     Evaluate strategy, decoding.py:386-399).  `td` is the reset td of the batch the actions were sampled on."""
     row_emb, col_emb = embeddings if embeddings is not None else policy.encoder(td, phase=phase)
@@ -122,7 +129,7 @@ def replay_log_likelihood(policy, td, env, actions: torch.Tensor, num_starts: in
     dur = td["duration_matrix"].float() if policy.decoder.env_name == "rcvrptw" else None
     logp = batched_logprobs(policy.decoder, row_emb.float(), col_emb.float(), td["distance_matrix"].float(), dur, inputs,
                             actions, num_starts, policy.temperature if temperature is None else temperature,
-                            policy.tanh_clipping if tanh_clipping is None else tanh_clipping, step_chunk)
+                            policy.tanh_clipping if tanh_clipping is None else tanh_clipping, step_chunk, autocast_dtype)
     if not bool((logp > -1000).all()):
         raise AssertionError("Logprobs should not be -inf, check sampling procedure!")
     return logp.sum(1)

@@ -32,7 +32,8 @@ def sync_time():
     return time.perf_counter()
 
 
-for it in range(3):
+for it in range(5):
+    ac = torch.bfloat16 if it >= 3 else None
     torch.cuda.reset_peak_memory_stats()
     t0 = sync_time()
     with torch.no_grad():
@@ -41,14 +42,15 @@ for it in range(3):
     with torch.no_grad():
         inputs = rb.collect_decode_inputs(pol.decoder, env, td, out["actions"], S)
     t2 = sync_time()
-    logp = rb.batched_logprobs(pol.decoder, row, col, td["distance_matrix"].float(), None, inputs, out["actions"], S)
+    logp = rb.batched_logprobs(pol.decoder, row, col, td["distance_matrix"].float(), None, inputs, out["actions"], S,
+                              autocast_dtype=ac)
     ll = logp.sum(1)
     loss = rb.pomo_shared_baseline_loss(out["reward"], ll, S)
     t3 = sync_time()
     loss.backward()
     t4 = sync_time()
     err = (ll - out["log_likelihood"]).abs().max().item()
-    print(f"iter {it}: B={B} S={S} T={out['actions'].shape[1]}  sample (fused kernel) {1e3*(t1-t0):7.1f} ms | env replay "
+    print(f"iter {it} ({'bf16 autocast' if ac else 'fp32'}): B={B} S={S} T={out['actions'].shape[1]}  sample (fused kernel) {1e3*(t1-t0):7.1f} ms | env replay "
           f"{1e3*(t2-t1):7.1f} | batched logprobs fwd {1e3*(t3-t2):7.1f} | bwd {1e3*(t4-t3):7.1f} | total {1e3*(t4-t0):7.1f} ms "
           f"= {B/(t4-t0):7.1f} instances/s | max |ll - kernel ll| {err:.1e} | peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB")
     pol.zero_grad(set_to_none=True)
