@@ -140,6 +140,52 @@ def test_rcvrp_env_step_persistent_pipeline_many_blocks(rb):
             assert torch.equal(td[k].cpu(), otd[k]), (k, t)
 
 
+def test_env_step_pipelines_wrap_their_stage_rings(rb):
+    """Staged env-step kernels at sizes where every warp runs its cp.async ring several times around (ATSP: 4 stages x 16
+    warps x 148 CTAs; RCVRP: 2 stages x 6 warps): checked against the step rule written in plain torch ops
+    (atsp/env.py:79-105, rcvrp/env.py:90-122,183-195), bit-exact."""
+    from rrnco_b200._lib import call, ptr, stream_ptr
+    g = torch.Generator(device=dev).manual_seed(3)
+    # ATSP: 12 001 blocks of 32 rollouts (> 4 x 2368) + a tail of 7
+    R, N = 32 * 12001 + 7, 100
+    mask_in = torch.rand(R, N, device=dev, generator=g) < 0.6
+    action = torch.randint(0, N, (R,), device=dev, generator=g)
+    first_in = torch.randint(0, N, (R,), device=dev, generator=g)
+    for step_val in (0, 5):
+        step_i = torch.full((1,), step_val, dtype=torch.int64, device=dev)
+        mask_o = torch.empty_like(mask_in)
+        first_o, cur_o = torch.empty_like(first_in), torch.empty_like(first_in)
+        done_o = torch.empty(R, dtype=torch.bool, device=dev)
+        call("rrnco_atsp_step", R, N, ptr(action), ptr(step_i), ptr(mask_in), ptr(first_in), ptr(mask_o), ptr(first_o),
+             ptr(cur_o), ptr(done_o), stream_ptr(dev))
+        want = mask_in.clone()
+        want[torch.arange(R, device=dev), action] = False
+        assert torch.equal(mask_o, want) and torch.equal(cur_o, action)
+        assert torch.equal(done_o, ~want.any(1)) and torch.equal(first_o, action if step_val == 0 else first_in)
+    # RCVRP: 4001 blocks (> 3 x 888) + a tail of 5, N - 1 a multiple of 20 (chunks only) and not (chunk + tail)
+    for N in (101, 29):
+        R = 32 * 4001 + 5
+        demand = torch.rand(R, N - 1, device=dev, generator=g) * 0.3
+        cap = torch.ones(R, device=dev)
+        used = torch.rand(R, device=dev, generator=g) * 0.8
+        visited = (torch.rand(R, N, device=dev, generator=g) < 0.4).to(torch.uint8)
+        action = torch.randint(0, N, (R,), device=dev, generator=g)
+        used_o, vis_o = torch.empty_like(used), torch.empty_like(visited)
+        cur_o = torch.empty(R, dtype=torch.int64, device=dev)
+        done_o = torch.empty(R, dtype=torch.bool, device=dev)
+        mask_o = torch.empty(R, N, dtype=torch.bool, device=dev)
+        call("rrnco_rcvrp_step", R, N, R, ptr(action), ptr(demand), ptr(cap), R, ptr(used), ptr(visited), None, ptr(used_o),
+             ptr(vis_o), ptr(cur_o), ptr(done_o), ptr(mask_o), stream_ptr(dev))
+        sel = torch.gather(demand, 1, (action - 1).clamp(0, N - 2)[:, None]).squeeze(1)
+        w_used = (used + sel) * (action != 0).float()
+        w_vis = visited.clone()
+        w_vis[torch.arange(R, device=dev), action] = 1
+        free = ~(w_vis[:, 1:].bool() | (demand + w_used[:, None] > cap[:, None]))
+        w_mask = torch.cat([~((action == 0) & free.any(1))[:, None], free], 1)
+        assert torch.equal(used_o, w_used) and torch.equal(vis_o, w_vis) and torch.equal(cur_o, action)
+        assert torch.equal(mask_o, w_mask) and torch.equal(done_o, w_vis.sum(1) == N)
+
+
 def test_host_prefetcher_round_trip(rb):
     """Double-buffered pinned-host -> HBM staging: three batches through two slots, contents intact, slot reuse ordered."""
     pf = rb.HostPrefetcher(dev)
