@@ -239,6 +239,7 @@ class RRNetPolicy(nn.Module):
             train_decode_type, val_decode_type, test_decode_type)
         self.seed = 1234
         self._calls = 0
+        self.train_replay_autocast = None  # e.g. torch.bfloat16: autocast of the differentiable replay in phase "train"
 
     def forward(self, td, env=None, phase: str = "train", calc_reward: bool = True, return_actions: bool = True,
                 return_entropy: bool = False, return_hidden: bool = False, return_init_embeds: bool = False,
@@ -283,6 +284,20 @@ class RRNetPolicy(nn.Module):
                             per_step_logprobs=not return_sum_log_likelihood, check=self.decoder.check_nan)
         outdict = {"reward": out["reward"],
                    "log_likelihood": out["log_likelihood"] if return_sum_log_likelihood else out["logprobs"]}
+        if phase == "train" and torch.is_grad_enabled() and multistart and actions is None:
+            # rl.py:119-128 differentiates out["log_likelihood"]: the kernel's value carries no graph, so the sampled
+            # actions are re-evaluated by the differentiable batched replay (training.py), same encoder output
+            from .training import batched_logprobs, collect_decode_inputs
+            with torch.no_grad():
+                inputs = collect_decode_inputs(self.decoder, env, td, out["actions"], S)
+            logp = batched_logprobs(self.decoder, row_emb.float(), col_emb.float(), td["distance_matrix"].float(),
+                                    td["duration_matrix"].float() if self.env_name == "rcvrptw" else None, inputs,
+                                    out["actions"], S, temperature, tanh_clipping,
+                                    autocast_dtype=self.train_replay_autocast)
+            if not bool((logp > -1000).all()):
+                raise AssertionError("Logprobs should not be -inf, check sampling procedure!")
+            outdict["log_likelihood"] = logp.sum(1) if return_sum_log_likelihood else torch.cat(
+                [torch.zeros_like(logp[:, :1]), logp], 1)
         if calc_reward and env.normalize:
             outdict["normalized_reward"] = out["normalized_reward"]
         if return_actions:

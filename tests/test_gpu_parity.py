@@ -539,7 +539,13 @@ def test_training_handoff_replay_matches_fused_kernel_loglik(rb, name, n, B):
     ll = rb.replay_log_likelihood(pol, td, env, out["actions"], S, embeddings=(row, col))
     assert ll.shape == out["log_likelihood"].shape and ll.requires_grad
     assert (ll - out["log_likelihood"]).abs().max().item() < 2e-3, (ll - out["log_likelihood"]).abs().max()
-    loss = rb.pomo_shared_baseline_loss(out["reward"], ll, S)
+    # the drop-in form: phase "train" with grad enabled returns the differentiable log-likelihood itself (rl.py:119-128)
+    out_t = pol(td, env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=77)
+    with torch.no_grad():
+        out_k = pol(td, env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=77)
+    assert out_t["log_likelihood"].requires_grad and torch.equal(out_t["actions"], out_k["actions"])
+    assert (out_t["log_likelihood"] - out_k["log_likelihood"]).abs().max().item() < 2e-3
+    loss = rb.pomo_shared_baseline_loss(out["reward"], ll, S) + rb.pomo_shared_baseline_loss(out_t["reward"], out_t["log_likelihood"], S)
     loss.backward()
     for gname, gten in (("W1", pol.decoder.pointer.ffn.lins[0].weight.grad), ("Wnode", pol.decoder.project_node_embeddings.weight.grad),
                         ("alpha", pol.decoder.alpha.grad), ("row", row.grad), ("col", col.grad)):
@@ -662,14 +668,16 @@ def test_sampling_matches_gumbel_twin_and_is_valid(rb):
                                  gumbel_noise=gumbel_twin(seed, B, S, n + 1))
     env = rb.get_env(name, generator_params={"num_loc": n})
     pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
-    out = pol(env.reset(lite(rb, raw)), env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=seed)
+    with torch.no_grad():  # the kernel's own log-likelihood (with grad enabled phase "train" returns the replayed one)
+        out = pol(env.reset(lite(rb, raw)), env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=seed)
     T = min(out["actions"].shape[1], oout["actions"].shape[1])
     same = (out["actions"].cpu()[:, :T] == oout["actions"][:, :T]).all(1)
     assert same.float().mean() >= 0.97, same.float().mean()  # identical noise => identical sampled tours
     ll, oll = out["log_likelihood"].cpu()[same], oout["log_likelihood"][same]
     assert ((ll - oll).abs() <= 1e-5 * oll.abs() + 5e-5).all()
     env.check_solution_validity(rb.batchify(env.reset(lite(rb, raw)), S), out["actions"])
-    out_b = pol(env.reset(lite(rb, raw)), env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=seed + 1)
+    with torch.no_grad():
+        out_b = pol(env.reset(lite(rb, raw)), env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=seed + 1)
     assert not torch.equal(out_b["actions"][:, : T], out["actions"][:, : T])  # different seed, different tours
 
 
@@ -690,9 +698,10 @@ def test_sampling_distribution_chi_square(rb):
     td0 = env.reset(lite(rb, raw))
     counts = torch.zeros(n)
     trials = 600
-    for sd in range(trials):
-        out = pol(td0, env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=1000 + sd)
-        counts[out["actions"][0, 1].item()] += 1
+    with torch.no_grad():
+        for sd in range(trials):
+            out = pol(td0, env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=1000 + sd)
+            counts[out["actions"][0, 1].item()] += 1
     exp = probs * trials
     keep = exp > 5
     chi2 = (((counts - exp) ** 2) / exp.clamp_min(1e-9))[keep].sum().item()
