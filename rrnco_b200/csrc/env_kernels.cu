@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) atsp_step_vec_kernel(
     __syncwarp();
     unsigned char* s = wbase + b * nb;
     const int o = lane * N, end = o + N;
-    s[o + (int)a] = 0;
+    if ((uint64_t)a < (uint64_t)N) s[o + (int)a] = 0;  // an out-of-range action must not touch a neighbour's row
     const int a0 = min((o + 3) & ~3, end), a1 = max(end & ~3, a0);
     uint32_t any = 0;
     for (int q = o; q < a0; ++q) any |= s[q];
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kStepWarps * 32, 1) rcvrp_step_vec_kernel(
       const float* dem = reinterpret_cast<const float*>(s + nb) + lane * (N - 1);
       const int di = min(max(cur - 1, 0), N - 2);
       const float used = __fmul_rn(__fadd_rn(used0, dem[di]), cur != 0 ? 1.0f : 0.0f);
-      vis[cur] = 1;
+      if ((unsigned)cur < (unsigned)N) vis[cur] = 1;  // an out-of-range action must not touch a neighbour's row
       int n_visited = vis[0];
       bool any_free = false;
       // demand rows are 16-byte aligned whenever (N - 1) % 4 == 0 (e.g. N = 101): 128-bit shared loads, conflict-free at
