@@ -28,8 +28,7 @@
 namespace rrnco {
 
 constexpr int kThreads = 256;      // compute threads (8 warps)
-constexpr int kPvLanes = 1;         // lanes per split term issuing the P V MMAs of a head (K steps dealt round-robin)
-constexpr int kThreadsTc = 384;    // tcgen05 variant: + warp 8 (TMA producer) + warps 9-11 (MMA issue, one per split term)
+constexpr int kThreadsTc = 320;    // tcgen05 variant: + warp 8 (TMA producer) + warp 9 (MMA issue: one elected thread)
 constexpr int kRows = 128;   // rollouts per CTA tile
 constexpr int kLdA = 132;    // fp32 row stride of the activation tiles (bank-conflict-free fragments)
 constexpr int kLdB = 36;     // fp32 row stride of a streamed weight slice (32 k + 4 pad)
@@ -288,7 +287,7 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     if (tid == 32) {
       for (int i = 0; i < kFStages; ++i) {
         tc05::mbar_init(&sm.bar_full[i], 1);
-        tc05::mbar_init(&sm.bar_empty[i], kPasses);
+        tc05::mbar_init(&sm.bar_empty[i], 1);
       }
       tc05::mbar_init(&sm.bar_go, kThreads);
       tc05::mbar_init(&sm.bar_kvgo, 1);
@@ -298,16 +297,16 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       for (int i = 0; i < kH; ++i) {
         tc05::mbar_init(&sm.bar_s[i], 1);
         tc05::mbar_init(&sm.bar_p[i], kThreads / 2);
-        tc05::mbar_init(&sm.bar_o[i], kPvLanes * kPasses);
+        tc05::mbar_init(&sm.bar_o[i], 1);
       }
       tc05::mbar_init(&sm.bar_gready, kThreads);
-      tc05::mbar_init(&sm.bar_h[0], kPasses);
-      tc05::mbar_init(&sm.bar_h[1], kPasses);
+      tc05::mbar_init(&sm.bar_h[0], 1);
+      tc05::mbar_init(&sm.bar_h[1], 1);
       tc05::mbar_init(&sm.bar_epi, kThreads);
-      tc05::mbar_init(&sm.bar_g2, kPasses);
+      tc05::mbar_init(&sm.bar_g2, 1);
       tc05::mbar_init(&sm.bar_lk, kThreads);
       tc05::mbar_init(&sm.bar_lkfull, 1);
-      tc05::mbar_init(&sm.bar_acc, kPasses);
+      tc05::mbar_init(&sm.bar_acc, 1);
       tc05::fence_mbar_init();
       sm.exit_flag = 0;
     }
@@ -435,11 +434,13 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
     tc05::fence_after_sync();
     if (tid == 0) tc05::mbar_arrive(&sm.bar_kvgo);
     if (tid == 0) TL(kTlStep, 203);  // K / V / Lk packed
-    if (warp == 8) {
+    // warp index as a value the compiler knows to be warp-uniform (threadIdx.x >> 5 is not, to its analysis)
+    const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
+    if (uwarp == 8) {
       // ===== TMA producer warp.  Per decode step: the packed K / V tiles (as soon as the previous step's logits have
       // released the Hb | Bs regions), then -- once the attention is done with them -- the 16 packed 32 KB FFN weight
-      // slices through the same memory used as a 4-stage ring =====
-      if (lane == 0) {
+      // slices through the same memory used as a 4-stage ring.  One elected thread (tc05::elect_one) =====
+      if (tc05::elect_one()) {
         uint32_t go_phase = 0;
         uint32_t sl = 0;
         unsigned char* ring = reinterpret_cast<unsigned char*>(sm.Hb);
@@ -472,76 +473,83 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
       }
       return;
     }
-    if (warp >= 9) {
-      // ===== MMA issue warps 9-11.  A single thread sustains only ~1 tcgen05.mma per 122 cycles whatever its size
-      // (several lanes of one warp overlap to ~1 per 67), so the issue work is spread:
-      //  attention: warp 9 + i owns score buffer i and the heads at sequence positions k = i, i + 3, i + 6 (sequence
-      //    0 4 1 5 2 6 3 7: the two compute-warp groups take alternate positions).  Q K^T: three ordered MMAs from lane 0
-      //    (the first overwrites); P V: R16 / 16 K steps per split term, one lane per term, into the pre-zeroed O tile.
-      //  FFN / logits: warp 9 + term issues one term of the two-term fp16 split (ffn_pack.cuh) for every K step
-      //    (0: A_hi B_hi, 1: A_lo B_hi, 2: A_hi B_lo; single-pass mode: term 0 only), all into pre-zeroed TMEM tiles.
-      //    Tensor-pipe order  G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) G2(3) logits: GEMM1 alternates between two
-      //    accumulators, so epilogue 1 of chunk c runs under GEMM1 of chunk c + 1. =====
-      const int term = warp - 9;
-      const uint32_t tb = sm.tmem_base;
-      const uint32_t t_hacc0 = tb, t_oacc = tb + 256, t_a = tb + (term == 1 ? 448 : 384);
-      const uint32_t idesc = tc05::make_idesc_f16(128, 128);
-      const uint32_t q_addr = tc05::smem_u32(sm.A);                                      // Q_hi | Q_lo, then G_hi | G_lo
-      const uint32_t a_addr = q_addr + (term == 1 ? kRows * kE * 2 : 0);
-      const uint32_t ring_addr = tc05::smem_u32(sm.Hb);
-      const uint32_t b_var = term == 2 ? kFVariantHalves * 2 : 0;
-      const int R16i = R16p;
-      const uint32_t idesc_l = tc05::make_idesc_f16(128, R16i);
-      const uint32_t idesc_pv = tc05::make_idesc_f16(128, 16);
-      const uint32_t lbo_l = (uint32_t)R16i * 16u;
-      const uint32_t kv_var = (uint32_t)R16i * 256u;  // bytes of one hi / lo variant of the K (or V) tiles
-      const uint32_t lk_addr = ring_addr + (term == 2 ? kv_var : 0);  // Lk_hi | Lk_lo
-      uint32_t step_par = 0, epi_phase = 0, sl = 0;
-      int istep = -1;
-      while (true) {
-        tc05::mbar_wait(&sm.bar_q, step_par, 32);
-        if (sm.exit_flag) break;
-        ++istep;
-        if (lane == 0) TL(istep, 100 + term);  // Q ready seen
-        tc05::mbar_wait(&sm.bar_kv, step_par, 32);
-        tc05::fence_after_sync();
-#pragma unroll 1
-        for (int k = term; k < kH; k += 3) {
+    if (uwarp == 9) {
+      // ===== MMA issue warp: ONE elected thread issues every tcgen05.mma of the CTA, in a fixed program order.  The
+      // tensor pipe executes MMAs in issue order, so the accumulation order into every TMEM accumulator is fixed and the
+      // rollout is bitwise reproducible run to run.  (Issue costs ~10 cycles per MMA from waterfall-free code, against
+      // 21 / 67 / 75 / 107 cycles of tensor time for TS N=16 / TS N=112 / TS N=128 / SS N=128: one thread is enough.)
+      //  attention: heads in the sequence 0 4 1 5 2 6 3 7 (the two compute-warp groups take alternate positions), score
+      //    buffer k % 3.  Q K^T of positions 0-2 at once; then per position k: wait for P(k), issue P V(k) (R16 / 16 K
+      //    steps x split terms into the pre-zeroed O tile) and, behind it on the in-order pipe, Q K^T(k + 3) into the
+      //    score buffer P V(k) has just finished reading.
+      //  FFN / logits: per K step the split terms (A_hi B_hi, A_lo B_hi, A_hi B_lo; single-pass mode: the first only), all
+      //    into pre-zeroed TMEM tiles.  Tensor-pipe order  G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) G2(3) logits: GEMM1
+      //    alternates between two accumulators, so epilogue 1 of chunk c runs under GEMM1 of chunk c + 1. =====
+      if (tc05::elect_one()) {
+        const uint32_t tb = sm.tmem_base;
+        const uint32_t t_hacc0 = tb, t_oacc = tb + 256, t_ahi = tb + 384, t_alo = tb + 448;
+        const uint32_t idesc = tc05::make_idesc_f16(128, 128);
+        const uint32_t q_addr = tc05::smem_u32(sm.A);                // Q_hi | Q_lo, then G_hi | G_lo
+        const uint32_t a_lo_off = kRows * kE * 2;
+        const uint32_t ring_addr = tc05::smem_u32(sm.Hb);
+        const uint32_t b_lo_off = kFVariantHalves * 2;
+        const int R16i = R16p;
+        const uint32_t idesc_l = tc05::make_idesc_f16(128, R16i);
+        const uint32_t idesc_pv = tc05::make_idesc_f16(128, 16);
+        const uint32_t lbo_l = (uint32_t)R16i * 16u;
+        const uint32_t kv_var = (uint32_t)R16i * 256u;  // bytes of one hi / lo variant of the K (or V) tiles
+        uint32_t step_par = 0, epi_phase = 0, sl = 0;
+        int istep = -1;
+        auto issue_qk = [&](int k) {
           const int h = (k & 1) * 4 + (k >> 1);
-          const uint32_t t_s = tb + term * 128;
-          if (lane == 0) {
-            const uint32_t qh = q_addr + 2 * h * kLboTile, kh = ring_addr + 2 * h * lbo_l;
-            const uint64_t q_hi = tc05::make_desc(qh, kLboTile, kSbo), k_hi = tc05::make_desc(kh, lbo_l, kSbo);
-            tc05::mma_ss_f16(t_s, q_hi, k_hi, idesc_l, 0u);
-            if (kPasses == 3) {
-              tc05::mma_ss_f16(t_s, tc05::make_desc(qh + kRows * kE * 2, kLboTile, kSbo), k_hi, idesc_l, 1u);
-              tc05::mma_ss_f16(t_s, q_hi, tc05::make_desc(kh + kv_var, lbo_l, kSbo), idesc_l, 1u);
-            }
-            tc05::commit(&sm.bar_s[h]);
-            tc05::commit(&sm.bar_qkdone);
-            TL(istep, 110 + h);  // QK(h) issued
+          const uint32_t t_s = tb + (uint32_t)(k % 3) * 128u;
+          const uint32_t qh = q_addr + 2 * h * kLboTile, kh = ring_addr + 2 * h * lbo_l;
+          const uint64_t q_hi = tc05::make_desc(qh, kLboTile, kSbo), k_hi = tc05::make_desc(kh, lbo_l, kSbo);
+          tc05::mma_ss_f16(t_s, q_hi, k_hi, idesc_l, 0u);
+          if (kPasses == 3) {
+            tc05::mma_ss_f16(t_s, tc05::make_desc(qh + a_lo_off, kLboTile, kSbo), k_hi, idesc_l, 1u);
+            tc05::mma_ss_f16(t_s, q_hi, tc05::make_desc(kh + kv_var, lbo_l, kSbo), idesc_l, 1u);
           }
-          __syncwarp();
-          tc05::mbar_wait(&sm.bar_p[h], step_par, 32);
+          tc05::commit(&sm.bar_s[h]);
+          tc05::commit(&sm.bar_qkdone);
+          TL(istep, 110 + h);  // QK(h) issued
+        };
+        while (true) {
+          tc05::mbar_wait(&sm.bar_q, step_par, 32);
+          if (sm.exit_flag) break;
+          ++istep;
+          TL(istep, 100);  // Q ready seen
+          tc05::mbar_wait(&sm.bar_kv, step_par, 32);
           tc05::fence_after_sync();
-          if (lane == 0) TL(istep, 120 + h);  // P(h) seen
-          if (lane < kPvLanes * kPasses) {
-            // lane = (split term, K-step residue): issue latency, not tensor time, bounds these small MMAs
-            const int pterm = lane % kPasses, jres = lane / kPasses;
-            // V_h^T tile: 16 dims x keys, K-major: 256 B between 16-byte key chunks, 128 B between 8-dim groups
-            const uint32_t vh = ring_addr + kKvOffV + (pterm == 2 ? kv_var : 0) + h * (R16i * 32);
-            const uint32_t ph = t_s + (pterm == 1 ? 8 : 0);  // P_hi at columns 16 j, P_lo at 16 j + 8
-            for (int j = jres; j < (R16i >> 4); j += kPvLanes)
-              tc05::mma_ts_f16(tb + 384 + 16 * h, ph + 16 * j, tc05::make_desc(vh + j * 512, 256, kSbo), idesc_pv, 1u);
+          issue_qk(0);
+          issue_qk(1);
+          issue_qk(2);
+#pragma unroll 1
+          for (int k = 0; k < kH; ++k) {
+            const int h = (k & 1) * 4 + (k >> 1);
+            const uint32_t t_s = tb + (uint32_t)(k % 3) * 128u;
+            tc05::mbar_wait(&sm.bar_p[h], step_par, 32);
+            tc05::fence_after_sync();
+            TL(istep, 120 + h);  // P(h) seen
+            // V_h^T tile: 16 dims x keys, K-major: 256 B between 16-byte key chunks, 128 B between 8-dim groups;
+            // P_hi at columns 16 j, P_lo at 16 j + 8 of the score buffer
+            const uint32_t vh = ring_addr + kKvOffV + h * (R16i * 32);
+#pragma unroll 1
+            for (int j = 0; j < (R16i >> 4); ++j) {
+              const uint64_t v_hi = tc05::make_desc(vh + j * 512, 256, kSbo);
+              tc05::mma_ts_f16(tb + 384 + 16 * h, t_s + 16 * j, v_hi, idesc_pv, 1u);
+              if (kPasses == 3) {
+                tc05::mma_ts_f16(tb + 384 + 16 * h, t_s + 16 * j + 8, v_hi, idesc_pv, 1u);
+                tc05::mma_ts_f16(tb + 384 + 16 * h, t_s + 16 * j, tc05::make_desc(vh + kv_var + j * 512, 256, kSbo), idesc_pv, 1u);
+              }
+            }
             tc05::commit(&sm.bar_o[h]);
-            if (lane == 0) TL(istep, 130 + h);  // PV(h) issued
+            TL(istep, 130 + h);  // PV(h) issued
+            if (k + 3 < kH) issue_qk(k + 3);
           }
-          __syncwarp();
-        }
-        if (lane == 0 && term < kPasses) {
           tc05::mbar_wait(&sm.bar_gready, step_par, 32);
           tc05::fence_after_sync();
-          TL(istep, 140 + term);  // glimpse seen
+          TL(istep, 140);  // glimpse seen
 #pragma unroll 1
           for (int j = 0; j < 8; ++j) {
             const int c = ffn_job_chunk(j), half = ffn_job_half(j);
@@ -555,22 +563,32 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
               const int st = sl & (kFStages - 1);
               tc05::mbar_wait(&sm.bar_full[st], (sl / kFStages) & 1);
               tc05::fence_after_sync();
-              const uint32_t b_addr = ring_addr + st * kFSliceBytes + b_var;
+              const uint32_t b_addr = ring_addr + st * kFSliceBytes;
 #pragma unroll
               for (int kk = 0; kk < kFKSteps; ++kk) {
                 const int ks = sj * kFKSteps + kk;  // K step (16 values) of the job
-                const uint64_t bdesc = tc05::make_desc(b_addr + kk * 2 * kLboTile, kLboTile, kSbo);
+                const uint64_t b_hi = tc05::make_desc(b_addr + kk * 2 * kLboTile, kLboTile, kSbo);
+                const uint64_t b_lo = tc05::make_desc(b_addr + b_lo_off + kk * 2 * kLboTile, kLboTile, kSbo);
                 if (half == 0) {
-                  const uint64_t adesc = tc05::make_desc(a_addr + ks * 2 * kLboTile, kLboTile, kSbo);
-                  tc05::mma_ss_f16(t_hacc0 + (c & 1) * 128, adesc, bdesc, idesc, 1u);
+                  const uint32_t t_h = t_hacc0 + (c & 1) * 128;
+                  const uint64_t a_hi = tc05::make_desc(q_addr + ks * 2 * kLboTile, kLboTile, kSbo);
+                  tc05::mma_ss_f16(t_h, a_hi, b_hi, idesc, 1u);
+                  if (kPasses == 3) {
+                    tc05::mma_ss_f16(t_h, tc05::make_desc(q_addr + a_lo_off + ks * 2 * kLboTile, kLboTile, kSbo), b_hi, idesc, 1u);
+                    tc05::mma_ss_f16(t_h, a_hi, b_lo, idesc, 1u);
+                  }
                 } else {
-                  tc05::mma_ts_f16(t_oacc, t_a + ks * 8, bdesc, idesc, 1u);
+                  tc05::mma_ts_f16(t_oacc, t_ahi + ks * 8, b_hi, idesc, 1u);
+                  if (kPasses == 3) {
+                    tc05::mma_ts_f16(t_oacc, t_alo + ks * 8, b_hi, idesc, 1u);
+                    tc05::mma_ts_f16(t_oacc, t_ahi + ks * 8, b_lo, idesc, 1u);
+                  }
                 }
               }
               tc05::commit(&sm.bar_empty[st]);
             }
             tc05::commit(half == 0 ? &sm.bar_h[c & 1] : &sm.bar_g2);
-            if (term == 0) TL(istep, 150 + j);  // FFN job j issued
+            TL(istep, 150 + j);  // FFN job j issued
           }
           // pointer logits: D[128 x R16] = g'(hi | lo, TMEM) . Lk(hi | lo, shared memory)^T, 8 K steps
           tc05::mbar_wait(&sm.bar_lk, step_par, 32);
@@ -578,14 +596,17 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
           tc05::fence_after_sync();
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t bdesc = tc05::make_desc(lk_addr + ks * 2 * lbo_l, lbo_l, kSbo);
-            tc05::mma_ts_f16(t_hacc0, t_a + ks * 8, bdesc, idesc_l, 1u);
+            const uint64_t l_hi = tc05::make_desc(ring_addr + ks * 2 * lbo_l, lbo_l, kSbo);
+            tc05::mma_ts_f16(t_hacc0, t_ahi + ks * 8, l_hi, idesc_l, 1u);
+            if (kPasses == 3) {
+              tc05::mma_ts_f16(t_hacc0, t_alo + ks * 8, l_hi, idesc_l, 1u);
+              tc05::mma_ts_f16(t_hacc0, t_ahi + ks * 8, tc05::make_desc(ring_addr + kv_var + ks * 2 * lbo_l, lbo_l, kSbo), idesc_l, 1u);
+            }
           }
           tc05::commit(&sm.bar_acc);
-          if (term == 0) TL(istep, 160);  // logits issued
+          TL(istep, 160);  // logits issued
+          step_par ^= 1u;
         }
-        __syncwarp();
-        step_par ^= 1u;
       }
       return;
     }

@@ -11,6 +11,20 @@ namespace tc05 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One thread of the (converged) warp, chosen by the hardware.  Unlike `lane == 0`, the compiler knows that exactly one
+// thread runs the guarded region, so every operand of the single-thread instructions in it (tcgen05.mma / commit,
+// cp.async.bulk: uniform-register operands in SASS) is trivially warp-uniform.  With `lane == 0` ptxas wraps EACH of
+// them in an ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall" loop: ~120 cycles per tcgen05.mma instead of ~10.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
