@@ -10,7 +10,10 @@
  *
  * Conventions
  *  - extern "C", C99 types only; every pointer is a DEVICE pointer unless its name starts with `h_`.
- *  - The library never allocates or frees caller-visible memory and keeps no global mutable state.
+ *  - The library never allocates or frees caller-visible memory.  Its only process-wide state are the three
+ *    development knobs below (rrnco_set_precision / rrnco_set_ffn_engine / rrnco_set_step_tiling: defaults are the
+ *    product configuration, set them before the first launch and never concurrently with one) and per-device
+ *    launch-configuration caches (shared-memory attributes, SM count), which are idempotent.
  *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises.
  *  - Return value: 0 = RRNCO_OK, negative = error (see rrnco_strerror).  Device-side conditions the
  *    reference raises as Python exceptions (NaN logits, infeasible action) are OR-ed into a caller-owned
@@ -42,6 +45,8 @@ extern "C" {
 #define RRNCO_DEV_NAN_LOGITS 1u       /* "Logits contain NaNs"           rrnco/models/decoder.py:303-304 */
 #define RRNCO_DEV_INFEASIBLE 2u       /* "infeasible action selected"    rrnco/models/decoding.py:278-280 */
 #define RRNCO_DEV_NO_FEASIBLE 4u      /* fully-masked row (never happens upstream: depot always feasible) */
+#define RRNCO_DEV_TRUNCATED 8u        /* rollout cut at t_cap with unfinished tours ("Exceeded maximum number of steps",
+                                         rrnco/models/policy.py:222-226: upstream logs an error and breaks) */
 
 #define RRNCO_ENV_ATSP 0
 #define RRNCO_ENV_RCVRP 1
@@ -57,6 +62,11 @@ extern "C" {
 
 int rrnco_abi_version(void);
 const char* rrnco_strerror(int code);
+
+/* Host twin of the device mapping from a 32-bit Philox word to a uniform in the OPEN interval (0, 1) used by the
+ * Gumbel-max sampler (rrnco/models/decoding.py:284-298 samples with torch.multinomial; see rrnco_rollout):
+ * u = ((x >> 9) + 0.5) / 2^23, exact in fp32, never 0 or 1 -- so -log(-log(u)) is always finite. */
+float rrnco_u01(uint32_t x);
 
 /* Precision of the in-kernel contractions of the fused decoder kernels (process-wide, set before use):
  *   3 = error-compensated tensor-core contractions, fp32-faithful (default; the reference's CPU / fp32 path):

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "librrnco_b200.so")
 
 ENV_ID = {"atsp": 0, "rcvrp": 1, "rcvrptw": 2}
 DECODE_ID = {"greedy": 0, "sampling": 1, "evaluate": 2}
-DEV_NAN_LOGITS, DEV_INFEASIBLE, DEV_NO_FEASIBLE = 1, 2, 4
+DEV_NAN_LOGITS, DEV_INFEASIBLE, DEV_NO_FEASIBLE, DEV_TRUNCATED = 1, 2, 4, 8
 MAX_NODES_FUSED = 128
 MIN_STARTS_TILED = 8   # RRNetDecoder.forward: starts per instance from which the any-N tile kernels serve every N
 
@@ -48,6 +48,7 @@ class RmtvrpState(C.Structure):
 _SIGNATURES = {
     "rrnco_abi_version": (C.c_int, []),
     "rrnco_strerror": (C.c_char_p, [C.c_int]),
+    "rrnco_u01": (C.c_float, [C.c_uint32]),
     "rrnco_set_precision": (C.c_int, [C.c_int32]),
     "rrnco_set_ffn_engine": (C.c_int, [C.c_int32]),
     "rrnco_set_step_tiling": (C.c_int, [C.c_int32]),
@@ -155,6 +156,10 @@ def set_ffn_engine(engine: int):
 
 def raise_device_status(word: int):
     """Surface the sticky device status with the reference's exception texts."""
+    if word & DEV_TRUNCATED:  # rrnco/models/policy.py:222-226 logs an error and breaks; so does this
+        import logging
+        logging.getLogger("rrnco_b200").error("Exceeded maximum number of steps during decoding: rollouts that had "
+                                              "not finished were cut and scored as they stood")
     if word & DEV_NAN_LOGITS:
         raise AssertionError("Logits contain NaNs")  # rrnco/models/decoder.py:303-304
     if word & DEV_INFEASIBLE:

@@ -100,11 +100,12 @@ extern "C" int rrnco_precompute_cache(int32_t env, int64_t n_inst, int32_t n_nod
   int n_jobs = 4;
   if (env == RRNCO_ENV_ATSP) jobs.job[n_jobs++] = {row_emb, w_ctx, ctx_in, kE, ctx_node_proj2};
   const size_t smem = 2 * 128 * kGLd * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(gemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  static PerDeviceOnce once;
+  if (once.first()) {
+    if (cudaFuncSetAttribute(gemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      once.undo();
       return RRNCO_ERR_CUDA;
-    configured = true;
+    }
   }
   dim3 grid((unsigned)((jobs.M + 127) / 128), n_jobs);
   gemm128_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(jobs);

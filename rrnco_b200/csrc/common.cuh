@@ -94,7 +94,44 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-// uniform in (0,1), 24 bits
-__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform in the OPEN interval (0,1), 23 bits: (k + 0.5) / 2^23 for k < 2^23 is exact in fp32 (24 significant bits),
+// so the largest value is 1 - 2^-24 < 1 and -log(-log(u)) stays finite.  (A 24-bit k would round 16777215.5 up to
+// 2^24 and return exactly 1.0 -> +inf Gumbel noise once per 2^24 draws.)
+__host__ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
+
+// ---- per-device launch configuration ----------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a DEVICE, not to the process: launchers
+// remember them per device ordinal (a process may hold tensors on several GPUs).  Races are benign (idempotent).
+struct PerDeviceOnce {
+  unsigned long long done[4] = {0, 0, 0, 0};  // one bit per device ordinal (< 256)
+  // true exactly when the current device has not been configured yet through this object (sets the bit)
+  bool first(int* dev_out = nullptr) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    if (dev_out) *dev_out = dev;
+    const unsigned long long bit = 1ull << (dev & 63);
+    unsigned long long& w = done[(dev >> 6) & 3];
+    if (w & bit) return false;
+    w |= bit;
+    return true;
+  }
+  void undo() {  // configuration failed: try again on the next call
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    done[(dev >> 6) & 3] &= ~(1ull << (dev & 63));
+  }
+};
+inline int device_sm_count() {
+  static int cache[256] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int& c = cache[dev & 255];
+  if (c == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    c = sms;
+  }
+  return c;
+}
 
 }  // namespace rrnco

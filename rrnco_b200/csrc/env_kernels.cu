@@ -648,6 +648,7 @@ static int gather_launch(const T* city_matrix, int32_t city_len, const int32_t* 
 extern "C" {
 
 int rrnco_abi_version(void) { return RRNCO_ABI_VERSION; }
+float rrnco_u01(uint32_t x) { return rrnco::u01(x); }
 
 const char* rrnco_strerror(int code) {
   switch (code) {
@@ -709,15 +710,15 @@ int rrnco_atsp_step(int64_t R, int32_t n_nodes, const int64_t* action, const int
   const bool vec_ok = cfg && R >= 32 && mask_in != mask_out && al16(mask_in) && al16(mask_out);
   const int64_t R_vec = vec_ok ? (R / 32) * 32 : 0;
   if (R_vec > 0) {
-    static int n_sm = 0;  // idempotent; benign if raced
-    if (n_sm == 0) {
-      int dev = 0, sms = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-        return RRNCO_ERR_CUDA;
+    static PerDeviceOnce once;  // per device ordinal; idempotent, benign if raced
+    const int n_sm = device_sm_count();
+    if (n_sm <= 0) return RRNCO_ERR_CUDA;
+    if (once.first()) {
       for (const VecCfg& c : cfgs)
-        if (cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+          once.undo();
           return RRNCO_ERR_CUDA;
-      n_sm = sms;
+        }
     }
     const int64_t n_groups = R_vec / 32;
     const int64_t want = (n_groups + cfg->warps - 1) / cfg->warps;
@@ -769,14 +770,14 @@ int rrnco_rcvrp_step(int64_t R, int32_t n_nodes, int64_t data_rows, const int64_
                       visited_in != visited_out;
   const int64_t R_vec = vec_ok ? (R / kGroup) * kGroup : 0;
   if (R_vec > 0) {
-    static int n_sm = 0;  // idempotent; benign if raced
-    if (n_sm == 0) {
-      int dev = 0, sms = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    static PerDeviceOnce once;  // per device ordinal; idempotent, benign if raced
+    const int n_sm = device_sm_count();
+    if (n_sm <= 0) return RRNCO_ERR_CUDA;
+    if (once.first()) {
+      if (cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+        once.undo();
         return RRNCO_ERR_CUDA;
-      if (cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
-        return RRNCO_ERR_CUDA;
-      n_sm = sms;
+      }
     }
     const int64_t n_groups = R_vec / kGroup;
     const int64_t want = (n_groups + cfg.warps - 1) / cfg.warps;

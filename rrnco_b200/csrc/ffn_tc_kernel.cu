@@ -273,12 +273,13 @@ int rrnco_pointer_ffn(int64_t n_rows, const float* g_in, const float* w1, const 
   cudaStream_t st = (cudaStream_t)stream;
   int rc = pack_ffn_weights(w1, w2, workspace, st);
   if (rc != RRNCO_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     if (cudaFuncSetAttribute(pointer_ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FfnSmem)) !=
-        cudaSuccess)
+        cudaSuccess) {
+      once.undo();
       return RRNCO_ERR_CUDA;
-    configured = true;
+    }
   }
   pointer_ffn_tc_kernel<<<(unsigned)((n_rows + kFRows - 1) / kFRows), kFThreads, sizeof(FfnSmem), st>>>(
       n_rows, g_in, reinterpret_cast<const uint16_t*>(workspace), b1, b2, g_out);

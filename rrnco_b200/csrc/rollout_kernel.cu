@@ -641,7 +641,11 @@ __global__ void __launch_bounds__(kTc ? kThreadsTc : kThreads, 1) rollout_kernel
   while (true) {
     if (!p.logits_only) {
       const int all_done = cta_sync_and<kTc>(tid < kRows ? (sm.done[tid] || !sm.active[tid]) : 1);
-      if (all_done || step >= p.max_steps) break;
+      if (all_done) break;
+      if (step >= p.max_steps) {  // policy.py:222-226: cut, but never silently
+        if (tid == 0) atomicOr(p.status, RRNCO_DEV_TRUNCATED);
+        break;
+      }
     }
     // ---- B (issued first so that the copies overlap phase A): K -> Hb, V -> Bs -----------------
     // (the tcgen05 variant prefetches them for step t+1 right after the logits MMAs of step t)
@@ -1806,11 +1810,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(RolloutParams p, float* l
 template <int kEnv, int kNTMax, int kPasses, bool kTc>
 int launch_rollout(const RolloutParams& p, cudaStream_t st) {
   auto kern = rollout_kernel<kEnv, kNTMax, kPasses, kTc>;
-  static bool configured = false;  // idempotent attribute; benign if raced
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess)
+  static PerDeviceOnce once;  // per device ordinal; idempotent attribute, benign if raced
+  if (once.first()) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
+      once.undo();
       return RRNCO_ERR_CUDA;
-    configured = true;
+    }
   }
   const int64_t grid = p.n_inst * p.n_tiles;
   if (grid <= 0 || grid > 0x7fffffffLL) return RRNCO_ERR_UNSUPPORTED;

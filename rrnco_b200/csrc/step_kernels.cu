@@ -492,11 +492,12 @@ int rrnco_decoder_logits_large(int32_t env, int32_t n_nodes, int64_t n_inst, int
   a.G = g0;
   if (g_step_tiling && n_starts >= 4) {  // rollouts of one instance share the staged key / value tiles
     const size_t smem = (size_t)4 * kAtKeys * kE * sizeof(float);
-    static bool attr_set = false;  // idempotent; benign if raced
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(attention_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    static PerDeviceOnce once;  // per device ordinal; idempotent, benign if raced
+    if (once.first()) {
+      if (cudaFuncSetAttribute(attention_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        once.undo();
         return RRNCO_ERR_CUDA;
-      attr_set = true;
+      }
     }
     // 16 warps per CTA, the last group of an instance ragged.  Measured on BASELINE's ATSP n=1000 case (100 starts): 7
     // groups of 16 (the last one 4 warps) 303 us per step; 7 even groups of 15 warps 330-345 us; 5 groups of 20 warps
@@ -514,11 +515,12 @@ int rrnco_decoder_logits_large(int32_t env, int32_t n_nodes, int64_t n_inst, int
   a.G = g1;
   if (g_step_tiling == 1 && n_starts >= 8) {  // the starts of one instance share the staged logit keys: tensor-core tiles
     const size_t smem = (size_t)(kMmG * kMmLd + 2 * kMmKeys * kMmLd) * sizeof(float);
-    static bool attr_set = false;  // idempotent; benign if raced
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    static PerDeviceOnce once;  // per device ordinal; idempotent, benign if raced
+    if (once.first()) {
+      if (cudaFuncSetAttribute(logits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        once.undo();
         return RRNCO_ERR_CUDA;
-      attr_set = true;
+      }
     }
     const int64_t groups = (n_starts + kMmG - 1) / kMmG;
     const int64_t tiles_all = (n_nodes + kMmKeys - 1) / kMmKeys;
@@ -528,11 +530,12 @@ int rrnco_decoder_logits_large(int32_t env, int32_t n_nodes, int64_t n_inst, int
     logits_mma_kernel<<<dim3((unsigned)(n_inst * groups), (unsigned)chunks), 256, smem, st>>>(a, n_starts);
   } else if (g_step_tiling && n_starts >= kLtPerWarp) {  // FFMA form of the same tiling (rrnco_set_step_tiling(2))
     const size_t smem = (size_t)(kLtG * kE + 2 * kLtKeys * kLtStride) * sizeof(float);
-    static bool attr_set = false;  // idempotent; benign if raced
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(logits_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    static PerDeviceOnce once;  // per device ordinal; idempotent, benign if raced
+    if (once.first()) {
+      if (cudaFuncSetAttribute(logits_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        once.undo();
         return RRNCO_ERR_CUDA;
-      attr_set = true;
+      }
     }
     const int64_t groups = (n_starts + kLtG - 1) / kLtG;
     const int64_t tiles_all = (n_nodes + kLtKeys - 1) / kLtKeys;

@@ -364,12 +364,13 @@ class RMTVRPEnv(_EnvBase):
         return RMTVRPEnv._kernel(td, None)
 
     def _get_reward(self, td, actions):
+        # upstream zeroes column 0 of its throw-away batchified copy for open routes (rmtvrp/env.py:433).  Here td may be
+        # the un-replicated reset td that later rollouts read again, so the matrix is NOT touched: the kernel multiplies
+        # the legs into the depot by 0 for open-route rows, which gives the same sum.
         cm = td["distance_matrix"]
-        # upstream zeroes column 0 in place for open routes (rmtvrp/env.py:433); keep the visible side effect
-        cm[:, :, 0] = cm[:, :, 0] * ~td["open_route"]
         if self.normalize:
-            return tour_reward(actions, cm, True, None, td["min_distance"], td["max_distance"])
-        return tour_reward(actions, cm, True)[1]
+            return tour_reward(actions, cm, True, td["open_route"], td["min_distance"], td["max_distance"])
+        return tour_reward(actions, cm, True, td["open_route"])[1]
 
     @staticmethod
     def check_solution_validity(td, actions):

@@ -11,6 +11,8 @@ store_all_logp / return_entropy, mask_logits=False, dynamic embeddings): they ar
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import Optional, Tuple, Union
@@ -237,9 +239,21 @@ class RRNetPolicy(nn.Module):
         self.temperature, self.tanh_clipping, self.mask_logits = temperature, tanh_clipping, mask_logits
         self.train_decode_type, self.val_decode_type, self.test_decode_type = (
             train_decode_type, val_decode_type, test_decode_type)
-        self.seed = 1234
+        self.seed = None  # sampling seed base; None = derived from torch.initial_seed() and the distributed rank
         self._calls = 0
         self.train_replay_autocast = None  # e.g. torch.bfloat16: autocast of the differentiable replay in phase "train"
+
+    def _seed_base(self) -> int:
+        """Philox key of the Gumbel-max sampler when the caller passes no `seed=`: follows torch / Lightning seeding
+        (`seed_everything` sets torch.initial_seed()) and differs per DDP rank, so ranks draw independent noise."""
+        if self.seed is not None:
+            return int(self.seed)
+        rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank()
+        else:
+            rank = int(os.environ.get("RANK", 0))
+        return (torch.initial_seed() + 0x9E3779B97F4A7C15 * (rank + 1)) & (2**64 - 1)
 
     def forward(self, td, env=None, phase: str = "train", calc_reward: bool = True, return_actions: bool = True,
                 return_entropy: bool = False, return_hidden: bool = False, return_init_embeds: bool = False,
@@ -279,7 +293,7 @@ class RRNetPolicy(nn.Module):
         self._calls += 1
         rollout_fn = fused_rollout if cache.glimpse_key.shape[1] <= _lib.MAX_NODES_FUSED else stepwise_rollout
         out = rollout_fn(self.decoder, cache, env, td, S, multistart, decode_type.replace("multistart_", ""),
-                            forced_actions=actions, seed=decoding_kwargs.pop("seed", self.seed + self._calls),
+                            forced_actions=actions, seed=decoding_kwargs.pop("seed", self._seed_base() + self._calls),
                             temperature=temperature, tanh_clipping=tanh_clipping, calc_reward=calc_reward,
                             per_step_logprobs=not return_sum_log_likelihood, check=self.decoder.check_nan)
         outdict = {"reward": out["reward"],
@@ -307,6 +321,20 @@ class RRNetPolicy(nn.Module):
         return outdict
 
 
+_WS_CACHE = {}
+
+
+def _workspace(dev, nbytes: int):
+    """Scratch for rrnco_rollout, kept per (device, stream) across calls (grown when a larger batch arrives): kernels on
+    one stream are ordered, so consecutive rollouts can share it."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WS_CACHE[key] = ws
+    return ws
+
+
 def fused_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_starts: int, multistart: bool,
                   kind: str, forced_actions=None, seed: int = 0, temperature: float = 1.0, tanh_clipping: float = 10.0,
                   calc_reward: bool = True, per_step_logprobs: bool = False, check: bool = True,
@@ -319,6 +347,11 @@ def fused_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_s
     R = n_inst * S
     if N > _lib.MAX_NODES_FUSED:
         raise NotImplementedError(f"fused rollout supports N <= {_lib.MAX_NODES_FUSED} nodes (got {N})")
+    num_loc = getattr(getattr(env, "generator", None), "num_loc", None)
+    if multistart and num_loc is not None and num_loc != (N if name == "atsp" else N - 1):
+        # select_start_nodes is `arange(S) % generator.num_loc` upstream; the kernel derives it from the instance size
+        raise ValueError(f"env.generator.num_loc = {num_loc} does not match the instance size ({N} nodes): the fused "
+                         "kernel's start-node rule would differ from env.select_start_nodes")
     keep = []
     w, keep_w = decoder.kernel_weights(temperature, tanh_clipping)
     data = instance_data_from_td(name, td, keep)
@@ -339,7 +372,7 @@ def fused_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_s
     real = torch.empty(R, dtype=torch.float32, device=dev) if has_minmax else None
     info = torch.zeros(2, dtype=torch.int32, device=dev)  # [max_steps, status]
     ws_bytes = _lib.lib().rrnco_rollout_workspace_bytes(ENV_ID[name], N, n_inst, S)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = _workspace(dev, ws_bytes)
     cs = cache.struct()
     call("rrnco_rollout", ENV_ID[name], N, n_inst, S, int(multistart), DECODE_ID[kind], int(seed) & (2**64 - 1),
          C.byref(w), C.byref(cs), C.byref(data), ptr(forced), forced_T, t_cap, ptr(acts), ptr(logp), ptr(ll),

@@ -42,6 +42,19 @@ def test_abi_version_and_strerror(lib_path):
     assert h.rrnco_rollout_workspace_bytes(1, 101, 4, 101) >= 2 * 4 * 101 * 8
 
 
+def test_gumbel_uniform_is_in_the_open_interval(lib_path):
+    """rrnco_u01 (host twin of the device mapping): never 0 or 1, so -log(-log(u)) is finite for every Philox word."""
+    from rrnco_b200 import _lib
+    h = _lib.lib()
+    one = np.float32(1.0)
+    for x in (0, 1, 0x1FF, 0x200, 0x7FFFFFFF, 0xFFFFFE00, 0xFFFFFFFF):
+        u = np.float32(h.rrnco_u01(x))
+        assert np.float32(0.0) < u < one, (hex(x), u)
+        assert np.isfinite(-np.log(-np.log(u)))
+    assert np.float32(h.rrnco_u01(0xFFFFFFFF)) == np.float32(1.0 - 2.0 ** -24)
+    assert np.float32(h.rrnco_u01(0)) == np.float32(2.0 ** -24)
+
+
 def test_bad_arguments_rejected_without_gpu(lib_path):
     from rrnco_b200 import _lib
     h = _lib.lib()

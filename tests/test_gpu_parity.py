@@ -238,8 +238,9 @@ def test_npz_test_set_through_prefetcher_matches_direct_path(rb, tmp_path):
     out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
     want = rb.unbatchify(out["reward"], (8, S)).amax(-1).amax(-1).cpu()
     got = torch.cat(costs)
-    # identical inputs -> identical tours up to last-ulp near-ties of the tensor-pipe accumulation order
-    assert ((got - want).abs() <= 1e-6 * want.abs()).float().mean() >= 5 / 6
+    # identical inputs -> identical costs: one thread issues every MMA in a fixed order, so the rollout is bitwise
+    # reproducible whatever the batch composition
+    assert torch.equal(got, want)
 
 
 def test_env_edge_cases(rb):
@@ -651,7 +652,7 @@ def gumbel_twin(seed, n_inst, S, N):
         c = np.tile(np.arange(N), R)
         x = philox4x32(r & 0xFFFFFFFF, r >> 32, np.full(R * N, step), c >> 2, seed & 0xFFFFFFFF, seed >> 32)
         x = np.stack(x, 0)[c & 3, np.arange(R * N)]
-        u = ((x >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+        u = ((x >> np.uint64(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)  # rrnco_u01
         return torch.from_numpy((-np.log(-np.log(u))).astype(np.float32).reshape(R, N))
     return noise
 
@@ -710,6 +711,155 @@ def test_sampling_distribution_chi_square(rb):
 
 
 # ----------------------------------------------------------------------------------------------------
+# the 99.9 % bar at a size where it means something: 1024 instances per env at n = 100 (configs C1-C3 sizes)
+# ----------------------------------------------------------------------------------------------------
+def _chunked_oracle(p, oenv, raw, row, col, S, chunk, dtype=torch.float32):
+    """Greedy multistart oracle rollout in chunks (upstream's batchify replicates every [N,N] matrix S times:
+    128 instances x 100 starts x 101^2 fp32 = 0.5 GB per matrix and chunk)."""
+    best, acts = [], []
+    B = raw.batch_size[0]
+    pp = omodel.cast_params(p, dtype) if dtype != torch.float32 else p
+    with torch.inference_mode():
+        for i in range(0, B, chunk):
+            b = min(chunk, B - i)
+            sub = TD({k: v[i:i + chunk] for k, v in raw.items()}, batch_size=[b])
+            o = omodel.policy_forward(pp, oenv, oenv.reset(sub), row[i:i + chunk].to(dtype), col[i:i + chunk].to(dtype),
+                                      decode_type="multistart_greedy", num_starts=S)
+            best.append(o["reward"].float().view(S, b).max(0)[0].clone())
+            acts.append(o["actions"].view(S, b, -1).clone())
+    return torch.cat(best), acts
+
+
+def _same_tours(a, b):
+    T = max(a.shape[-1], b.shape[-1])
+    return (torch.nn.functional.pad(a, (0, T - a.shape[-1])) == torch.nn.functional.pad(b, (0, T - b.shape[-1]))).all(-1)
+
+
+@pytest.mark.parametrize("name", ["rcvrp", "atsp", "rcvrptw"])
+def test_greedy_cost_parity_on_1024_instances(rb, name, capsys):
+    """North-star bar: greedy rollouts from identical random-init weights give per-instance costs within 1e-4 relative
+    on >= 99.9 % of instances -- asserted on 1024 instances (at most ONE may miss), n = 100, POMO multistart
+    (decoding.py:272-298, test.py:210-212 reduction).  The fp32-oracle-vs-fp64-oracle disagreement on the first 128
+    instances is the noise floor of the discontinuous argmax and is printed beside it; the same inputs are run twice
+    and must give bitwise identical outputs (fixed MMA issue order)."""
+    B, n, chunk, B64 = 1024, 100, 128, 128
+    raw = synth.make_instances(name, B, n, seed=2025)
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    S = oenv.get_num_starts(oenv.reset(TD({k: v[:2] for k, v in raw.items()}, batch_size=[2])))
+    N = n if name == "atsp" else n + 1
+    row, col = synth.random_embeddings(B, N, seed=77)
+    p = omodel.init_decoder_params(name, seed=1234)
+    obest, oacts = _chunked_oracle(p, oenv, raw, row, col, S, chunk)
+    raw64 = TD({k: v[:B64] for k, v in raw.items()}, batch_size=[B64])
+    o64best, o64acts = _chunked_oracle(p, oenv, raw64, row[:B64], col[:B64], S, chunk, torch.float64)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    outs = []
+    for _ in range(2):
+        out = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+        outs.append({k: out[k].cpu() for k in ("actions", "reward", "log_likelihood")})
+    # run-to-run determinism: bitwise
+    for k in ("actions", "reward", "log_likelihood"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    best = outs[0]["reward"].view(S, B).max(0)[0]
+    relc = (best - obest).abs() / obest.abs()
+    frac = (relc < 1e-4).float().mean().item()
+    ga = outs[0]["actions"].view(S, B, -1)
+    same = torch.cat([_same_tours(ga[:, i * chunk:(i + 1) * chunk], oa) for i, oa in enumerate(oacts)], 1)
+    floor_c = ((obest[:B64] - o64best).abs() / o64best.abs() < 1e-4).float().mean().item()
+    floor_t = _same_tours(oacts[0], o64acts[0]).float().mean().item()
+    with capsys.disabled():
+        print(f"\n[parity-1024] {name}: instances within 1e-4: {frac:.5f} (max rel {relc.max():.2e}); rollouts with "
+              f"identical tours {same.float().mean():.5f}; noise floor (fp32 vs fp64 oracle, {B64} instances): "
+              f"instances {floor_c:.5f}, tours {floor_t:.5f}; run-to-run bitwise identical")
+    assert frac >= 0.999, frac
+    assert same.float().mean() >= 0.999, same.float().mean()
+
+
+def test_sampling_twin_rcvrptw_n100(rb):
+    """Config C3's decode mode at C3's shape: RCVRPTW n=100, multistart sampling (decoding.py:284-298), against the oracle
+    driven by the NumPy twin of the kernel's Philox / Gumbel stream; also bitwise run-to-run."""
+    name, n, B, seed = "rcvrptw", 100, 8, 4242
+    raw = synth.make_instances(name, B, n, seed=31)
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    otd = oenv.reset(raw)
+    S = oenv.get_num_starts(otd)
+    assert S == 100
+    row, col = synth.random_embeddings(B, n + 1, seed=32)
+    p = omodel.init_decoder_params(name, seed=33)
+    with torch.inference_mode():
+        oout = omodel.policy_forward(p, oenv, otd, row, col, decode_type="multistart_sampling", num_starts=S,
+                                     gumbel_noise=gumbel_twin(seed, B, S, n + 1))
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    with torch.no_grad():
+        out = pol(env.reset(lite(rb, raw)), env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=seed)
+        out_b = pol(env.reset(lite(rb, raw)), env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=seed)
+    assert torch.equal(out["actions"], out_b["actions"]) and torch.equal(out["log_likelihood"], out_b["log_likelihood"])
+    same = _same_tours(out["actions"].cpu(), oout["actions"])
+    assert same.float().mean() >= 0.97, same.float().mean()  # identical noise => identical sampled tours
+    ll, oll = out["log_likelihood"].cpu()[same], oout["log_likelihood"][same]
+    assert ((ll - oll).abs() <= 1e-5 * oll.abs() + 1e-4).all()
+    assert rel(out["reward"].cpu()[same], oout["reward"][same]) < 1e-6
+    # every customer exactly once
+    srt = out["actions"].sort(1)[0]
+    assert (srt[:, -n:] == torch.arange(1, n + 1, device=dev)).all() and (srt[:, :-n] == 0).all()
+
+
+def test_c4_shape_atsp_n1000_batch4_vs_oracle(rb):
+    """Config C4's shape with more than one instance: ATSP n=1000, 4 instances x 100 starts (test.py:129-130)."""
+    name, n, B, S = "atsp", 1000, 4, 100
+    raw = synth.make_instances(name, B, n, seed=1000)
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    row, col = synth.random_embeddings(B, n, seed=1001)
+    p = omodel.init_decoder_params(name, seed=1002)
+    with torch.inference_mode():
+        oout = omodel.policy_forward(p, oenv, oenv.reset(raw), row, col, decode_type="multistart_greedy", num_starts=S)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    out = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    same = _same_tours(out["actions"].cpu(), oout["actions"])
+    assert same.float().mean() >= 0.97, same.float().mean()
+    assert rel(out["reward"].cpu()[same], oout["reward"][same]) < 1e-6
+    best, obest = out["reward"].cpu().view(S, B).max(0)[0], oout["reward"].view(S, B).max(0)[0]
+    assert ((best - obest).abs() / obest.abs() < 1e-4).all()
+    assert (out["actions"].sort(1)[0] == torch.arange(n, device=dev)).all()
+
+
+def test_truncated_rollout_is_reported_and_open_route_reward_does_not_mutate(rb, caplog):
+    """A rollout cut at t_cap with unfinished tours sets RRNCO_DEV_TRUNCATED and is logged like policy.py:222-226;
+    RMTVRPEnv.get_reward leaves the reset td's matrix alone for open routes (upstream mutates a throw-away copy)."""
+    import logging
+    name, n, B = "rcvrptw", 20, 3
+    raw = synth.make_instances(name, B, n, seed=9)
+    raw["open_route"] = torch.tensor([[True], [False], [True]])
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    td = env.reset(lite(rb, raw))
+    S = env.get_num_starts(td)
+    row, col = synth.random_embeddings(B, n + 1, seed=10)
+    p = omodel.init_decoder_params(name, seed=11)
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    cache = pol.decoder._precompute_cache((row.to(dev), col.to(dev)))
+    with caplog.at_level(logging.ERROR, logger="rrnco_b200"):
+        out = rb.fused_rollout(pol.decoder, cache, env, td, S, True, "greedy", t_cap=6)
+    assert out["actions"].shape[1] == 6
+    assert any("Exceeded maximum number of steps" in r.message for r in caplog.records)
+    caplog.clear()
+    before = td["distance_matrix"].clone()
+    with caplog.at_level(logging.ERROR, logger="rrnco_b200"):
+        full = rb.fused_rollout(pol.decoder, cache, env, td, S, True, "greedy")
+    assert not caplog.records
+    real, norm = env.get_reward(rb.batchify(td, S), full["actions"])
+    assert torch.equal(td["distance_matrix"], before)
+    assert rel(real, full["reward"]) < 1e-6
+    # oracle (= upstream's in-place zeroing on its own copy) agrees
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    otd = obatchify(oenv.reset(raw), S)
+    oreal, _ = oenv.get_reward(otd, full["actions"].cpu())
+    assert rel(real.cpu(), oreal) < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties
 # ----------------------------------------------------------------------------------------------------
 def test_full_size_rcvrp_rollout_properties(rb):
@@ -743,8 +893,8 @@ def test_full_size_rcvrp_rollout_properties(rb):
     assert rel(norm, out["normalized_reward"]) < 1e-6 and rel(real, out["reward"]) < 1e-6
     # evaluate replay of the greedy tours reproduces the log-likelihood
     out2 = pol(td_aug, env, phase="val", num_starts=S, actions=acts[:, 1:])
-    # (the three MMA-issuing warps accumulate in a run-dependent order: last-ulp differences between runs)
-    assert (out2["log_likelihood"] - out["log_likelihood"]).abs().max() < 1e-4
+    # (same MMAs in the same order on both calls; only the select epilogue differs: forced column vs argmax)
+    assert (out2["log_likelihood"] - out["log_likelihood"]).abs().max() < 1e-5
     assert torch.equal(out2["actions"], acts)
     # augmentation copies share matrices and (here) differ only by embeddings: best-of reduction shape
     best = rb.unbatchify(out["reward"], (A, S)).max(-1)[0].max(-1)[0]
