@@ -364,10 +364,14 @@ class RMTVRPEnv(_EnvBase):
         return RMTVRPEnv._kernel(td, None)
 
     def _get_reward(self, td, actions):
-        # upstream zeroes column 0 of its throw-away batchified copy for open routes (rmtvrp/env.py:433).  Here td may be
-        # the un-replicated reset td that later rollouts read again, so the matrix is NOT touched: the kernel multiplies
-        # the legs into the depot by 0 for open-route rows, which gives the same sum.
+        # upstream zeroes column 0 in place for open routes (rmtvrp/env.py:433) -- on the batchified td it was handed, a
+        # copy that lives for this call.  The same visible side effect is kept for a td in that layout (one matrix per
+        # rollout).  An un-replicated reset td (data_rows < R: rollout r reads row r % data_rows) is read again by later
+        # rollouts / decoder calls, so it is NOT touched: the kernel multiplies the legs into the depot by 0 for
+        # open-route rows, which gives the same sum.
         cm = td["distance_matrix"]
+        if cm.shape[0] == actions.shape[0]:
+            cm[:, :, 0] = cm[:, :, 0] * ~td["open_route"]
         if self.normalize:
             return tour_reward(actions, cm, True, td["open_route"], td["min_distance"], td["max_distance"])
         return tour_reward(actions, cm, True, td["open_route"])[1]

@@ -849,9 +849,11 @@ def test_truncated_rollout_is_reported_and_open_route_reward_does_not_mutate(rb,
     with caplog.at_level(logging.ERROR, logger="rrnco_b200"):
         full = rb.fused_rollout(pol.decoder, cache, env, td, S, True, "greedy")
     assert not caplog.records
-    real, norm = env.get_reward(rb.batchify(td, S), full["actions"])
+    real, norm = env.get_reward(td, full["actions"])  # un-replicated td: rollout r reads row r % B
     assert torch.equal(td["distance_matrix"], before)
     assert rel(real, full["reward"]) < 1e-6
+    real_b, _ = env.get_reward(rb.batchify(td, S), full["actions"])  # upstream's layout (its own copy is zeroed)
+    assert torch.equal(td["distance_matrix"], before) and torch.equal(real_b, real)
     # oracle (= upstream's in-place zeroing on its own copy) agrees
     oenv = oenvs.make_env(name, n, check_solution=False)
     otd = obatchify(oenv.reset(raw), S)
