@@ -24,12 +24,12 @@
 #include "common.cuh"
 #include "tc05.cuh"
 #include "ffn_pack.cuh"
+#include "rollout_common.cuh"
 
 namespace rrnco {
 
 constexpr int kThreads = 256;      // compute threads (8 warps)
 constexpr int kThreadsTc = 320;    // tcgen05 variant: + warp 8 (TMA producer) + warp 9 (MMA issue: one elected thread)
-constexpr int kRows = 128;   // rollouts per CTA tile
 constexpr int kLdA = 132;    // fp32 row stride of the activation tiles (bank-conflict-free fragments)
 constexpr int kLdB = 36;     // fp32 row stride of a streamed weight slice (32 k + 4 pad)
 constexpr int kSliceK = 32;
@@ -37,7 +37,6 @@ constexpr int kStages = 3;
 constexpr int kStageFloats = kRows * kLdB;
 constexpr int kTileFloats = kRows * kLdA;
 constexpr int kNumSlices = 36;  // 4 chunks x (4 W1 + 4 W2) + 4 Lk
-constexpr int kMaxState = 4;
 
 // per-phase cycle accumulator of CTA 0 (debug / profiling aid, read back with rrnco_debug_phase_cycles)
 __device__ long long g_phase_cycles[16];
@@ -69,61 +68,6 @@ constexpr int kTlStep = 6;
 #else
 #define TL(stepvar, tag) do { } while (0)
 #endif
-
-struct RolloutParams {
-  int N, NT, S, n_tiles, n_state;
-  int64_t n_inst;
-  int multistart, mode, logits_only, use_placeholder, t_cap, forced_T, max_steps;
-  uint64_t seed;
-  rrnco_decoder_weights_t w;
-  rrnco_decoder_cache_t c;
-  rrnco_instance_data_t d;
-  const int64_t* in_cur;
-  const int64_t* in_first;
-  const uint8_t* in_mask;
-  const float* in_state;
-  float* logits_out;
-  const int64_t* forced;
-  int64_t* actions;
-  float* logprob;
-  double* ws_len;
-  double* ws_lp;
-  int32_t* ws_tile_steps;
-  int32_t* max_steps_out;
-  uint32_t* status;
-  const unsigned char* ffn_packed;  // tcgen05 variant: W1 / W2 packed fp16 hi | lo slices (ffn_pack.cuh)
-  unsigned char* kv_pack;           // tcgen05 variant: kKvSlots per-SM slots of packed fp16 K | V tiles (kKvSlotBytes each)
-};
-
-// Transcendentals of the softmax / bias / clip chain on the SFU (ex2 / lg2 / rcp .approx): absolute error
-// <~ 1e-6 on the ranges that occur here, i.e. below the 3xTF32 noise of the logits themselves (~3e-6).
-// The .ftz forms skip the denormal pre/post-scaling sequences of __expf / __logf (never needed here: the arguments
-// of lg2 are >= 1e-6, and a denormal exp underflows to 0 against sums that are >= 1).
-__device__ __forceinline__ float ex2a(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lg2a(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcpa(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fexp(float x) { return ex2a(x * 1.4426950408889634f); }
-__device__ __forceinline__ float flog(float x) { return lg2a(x) * 0.6931471805599453f; }
-__device__ __forceinline__ float ftanh(float x) { return fmaf(-2.0f, rcpa(ex2a(x * 2.8853900817779268f) + 1.0f), 1.0f); }
-
-// Gumbel noise of four consecutive columns (canonical mapping, see the select epilogue).  Deliberately not inlined:
-// sixteen inlined copies of Philox + 8 accurate logarithms were 80 KB of code that the greedy path had to jump over.
-static __device__ __noinline__ float4 gumbel4(uint4 ctr, uint2 key) {
-  const uint4 r = philox4x32(ctr, key);
-  return make_float4(-logf(-logf(u01(r.x))), -logf(-logf(u01(r.y))), -logf(-logf(u01(r.z))), -logf(-logf(u01(r.w))));
-}
 
 struct Smem {
   float A[kTileFloats];   // q -> glimpse -> glimpse'
@@ -1866,6 +1810,10 @@ int dispatch_env_tc(const RolloutParams& p, int env, int passes, cudaStream_t st
 }  // namespace rrnco
 #else
 int dispatch_env_tc(const RolloutParams& p, int env, int passes, cudaStream_t st);  // rollout_kernel_tc.cu
+int dispatch_env_lean(const RolloutParams& p, int env, int passes, cudaStream_t st);  // rollout_lean.cu
+int pack_ffn_lean(const float* w1, const float* w2, void* packed, cudaStream_t st);
+int64_t lean_kv_bytes(int32_t n_nodes, int64_t n_tiles_total);
+constexpr int kLeanMaxNodes = 112;  // two score buffers + two P V slots in 256 TMEM columns
 int phase_cycles_tc(long long* h_out, int reset);
 int timeline_tc(long long* h_out, int* n_out);
 
@@ -1902,7 +1850,8 @@ int check_common(int32_t env, int32_t N, int64_t n_inst, int32_t S, const rrnco_
 }
 
 int g_passes = 3;  // set through rrnco_set_precision (process-wide default, read-only on the hot path)
-int g_engine = 1;  // FFN engine of the fused rollout: 1 = tcgen05 (TMEM accumulators), 0 = mma.sync
+int g_engine = 2;  // engine of the fused rollout: 2 = tcgen05, two lean CTAs per SM (N <= 112; else 1), 1 = tcgen05, one CTA
+                   // per SM, 0 = mma.sync
 
 }  // namespace
 
@@ -1910,7 +1859,7 @@ extern "C" {
 
 // debug: per-phase cycle totals of CTA 0 since the last reset (host buffer of 16 int64); reset != 0 clears them
 int rrnco_debug_phase_cycles(long long* h_out, int reset) {
-  return g_engine == 1 ? phase_cycles_tc(h_out, reset) : phase_cycles_local(h_out, reset);
+  return g_engine >= 1 ? phase_cycles_tc(h_out, reset) : phase_cycles_local(h_out, reset);
 }
 
 // debug: event timeline of the tcgen05 variant (512 int64 = 256 (tag, clock) pairs); development builds only
@@ -1925,18 +1874,20 @@ int rrnco_set_precision(int32_t passes) {
 
 // FFN engine of the fused rollout kernel: 1 = tcgen05.mma + TMEM + TMA weight stream (default), 0 = mma.sync
 int rrnco_set_ffn_engine(int32_t engine) {
-  if (engine != 0 && engine != 1) return RRNCO_ERR_BAD_ARG;
+  if (engine < 0 || engine > 2) return RRNCO_ERR_BAD_ARG;
   g_engine = engine;
   return RRNCO_OK;
 }
 
 int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts) {
-  (void)env; (void)n_nodes;
+  (void)env;
   if (n_inst <= 0 || n_starts <= 0) return 0;
   const int64_t R = n_inst * n_starts;
   const int64_t tiles = n_inst * ((n_starts + kRows - 1) / kRows);
-  return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL) +
-         kFfnPackedBytes + (int64_t)kKvSlots * kKvSlotBytes;
+  // packed K / V / logit-key tiles: one region per CTA (lean engine) or one slot per SM (one-CTA engine)
+  int64_t kv = (int64_t)kKvSlots * kKvSlotBytes;
+  if (n_nodes <= kLeanMaxNodes && lean_kv_bytes(n_nodes, tiles) > kv) kv = lean_kv_bytes(n_nodes, tiles);
+  return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL) + kFfnPackedBytes + kv;
 }
 
 int rrnco_decoder_logits(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts,
@@ -1995,7 +1946,11 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
   p.kv_pack = packed + kFfnPackedBytes;  // 16-byte aligned: every part above is a multiple of 16 bytes
   p.max_steps_out = max_steps_out; p.status = status;
   if (cudaMemsetAsync(max_steps_out, 0, sizeof(int32_t), st) != cudaSuccess) return RRNCO_ERR_CUDA;
-  if (g_engine == 1) {
+  if (g_engine == 2 && n_nodes <= kLeanMaxNodes) {
+    rc = pack_ffn_lean(w->ffn_w1, w->ffn_w2, packed, st);
+    if (rc != RRNCO_OK) return rc;
+    rc = dispatch_env_lean(p, env, g_passes, st);
+  } else if (g_engine >= 1) {
     rc = pack_ffn_weights(w->ffn_w1, w->ffn_w2, packed, st);
     if (rc != RRNCO_OK) return rc;
     rc = dispatch_env_tc(p, env, g_passes, st);
