@@ -780,22 +780,31 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
     // the logits MMAs run: coalesced, one warp per 16 rollouts
     {
       float* btile = reinterpret_cast<float*>(sm.A);
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int row_s = warp * 16 + i;
-        const int cur_s = sm.cur[row_s];
+      // 8 rollouts at a time: up to 32 (64 with durations) independent L2 loads in flight per lane before the first store
+#pragma unroll 1
+      for (int i0 = 0; i0 < 16; i0 += 8) {
+        float bias[8][4];
 #pragma unroll
-        for (int cq = 0; cq < 4; ++cq) {
-          const int c = cq * 32 + lane;
-          if (c < R16) {
-            float bias = 0.f;
+        for (int i = 0; i < 8; ++i) {
+          const int cur_s = sm.cur[warp * 16 + i0 + i];
+#pragma unroll
+          for (int cq = 0; cq < 4; ++cq) {
+            const int c = cq * 32 + lane;
+            float bv = 0.f;
             if (c < N) {
-              bias = __fmul_rn(p.w.alpha, D[cur_s * N + c]);
-              if (kEnv == RRNCO_ENV_RCVRPTW) bias = __fadd_rn(bias, __fmul_rn(p.w.beta, U[cur_s * N + c]));
+              bv = __fmul_rn(p.w.alpha, D[cur_s * N + c]);
+              if (kEnv == RRNCO_ENV_RCVRPTW) bv = __fadd_rn(bv, __fmul_rn(p.w.beta, U[cur_s * N + c]));
             }
-            btile[row_s * kLBiasLd + c] = bias;
+            bias[i][cq] = bv;
           }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int cq = 0; cq < 4; ++cq) {
+            const int c = cq * 32 + lane;
+            if (c < R16) btile[(warp * 16 + i0 + i) * kLBiasLd + c] = bias[i][cq];
+          }
       }
     }
     lean_sync();
