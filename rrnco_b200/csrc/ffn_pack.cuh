@@ -2,7 +2,7 @@
 // two-term fp16 operand split ("f16s") both of them compute in.
 //
 // f16s split of an fp32 value x, pre-scaled by a power of two S:  x' = S x,  hi = x' rounded to 11 significant
-// bits,  lo = x' - hi  (exact in fp32, |lo| <= 2^-12 |x'|);  both parts are stored as fp16.
+// bits (= fp16(x')),  lo = x' - hi  (exact in fp32, |lo| <= 2^-12 |x'|);  both parts are stored as fp16.
 //   activations (A operand): S = kAScale;   weights / logit keys (B operand): S = kWScale / kLkScale
 //   S_a S_w a w ~= A_hi B_hi + A_lo B_hi + A_hi B_lo        (dropped term a_lo w_lo <= 2^-24 |a w|)
 // i.e. three kind::f16 tcgen05 MMAs (K = 16 each, twice the TF32 rate) into ONE fp32 accumulator give the same
@@ -50,15 +50,14 @@ __host__ __device__ constexpr int ffn_job_chunk(int j) { return j == 0 ? 0 : j =
 __host__ __device__ constexpr int ffn_job_half(int j) { return j == 0 ? 0 : j == 1 ? 0 : j == 2 ? 1 : j == 3 ? 0 : j == 4 ? 1 : j == 5 ? 0 : j == 6 ? 1 : 1; }
 
 #ifdef __CUDACC__
-// hi part as an fp32 value with 11 significant bits (integer round-to-nearest, ties away; same bit trick as f2tf32)
-__device__ __forceinline__ float f16s_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
-// pair (x0, x1), pre-scaled by `scale` -> packed hi / lo fp16 words (low half = x0)
+// pair (x0, x1), pre-scaled by `scale` -> packed hi / lo fp16 words (low half = x0): hi = fp16(x) (round to nearest, 11
+// significant bits; one F2FP per pair), lo = fp16(x - hi) with the subtraction exact in fp32.  6 instructions per pair.
 __device__ __forceinline__ void f16s_split2(float x0, float x1, float scale, uint32_t& hi, uint32_t& lo) {
   x0 *= scale;
   x1 *= scale;
-  const float h0 = f16s_hi(x0), h1 = f16s_hi(x1);
-  const __half2 hh = __floats2half2_rn(h0, h1);
-  const __half2 ll = __floats2half2_rn(x0 - h0, x1 - h1);
+  const __half2 hh = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&hh);
   lo = *reinterpret_cast<const uint32_t*>(&ll);
 }

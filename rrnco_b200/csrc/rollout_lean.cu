@@ -621,7 +621,6 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       const uint32_t t_s = tb + (uint32_t)grp * 128u + lane_b, t_o = t_s + 112u;
       // s = q . k / 4; the operands carry kAScale kKvScale.  exp(s - m) = ex2(c1 v - c1 vmax); + 4 = log2(kAScale)
       const float c1 = 0.25f * 1.4426950408889634f / (kAScale * kKvScale);
-      const int nblk = (R16 + 31) >> 5;  // 32-column blocks; columns past R16 hold stale data that the mask zeroes
       uint32_t mrow[4];
       *reinterpret_cast<uint4*>(mrow) = *reinterpret_cast<const uint4*>(sm.mask[row]);
 #pragma unroll 1
@@ -629,45 +628,60 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         const int h = 4 * grp + j;
         tc05::mbar_wait(&sm.bar_s[h], step_par, 20);
         tc05::fence_after_sync();
+        // Both passes walk the row in 16-column blocks with the TMEM load of block k + 1 in flight while block k is
+        // processed (a TMEM round trip is a few hundred cycles; two resident tiles do not hide it by themselves).
+        const int nb16 = R16 >> 4;
+        uint32_t va[16], vb[16];
         // pass 1: row maximum over the feasible keys
         float vm0 = -INFINITY, vm1 = -INFINITY;
-#pragma unroll 1
-        for (int gb = 0; gb < nblk; ++gb) {
-          uint32_t v[2][16];
-          tc05::tmem_ld16(t_s + gb * 32, v[0]);
-          tc05::tmem_ld16(t_s + gb * 32 + 16, v[1]);
-          const uint32_t mw = mrow[gb];
-          tc05::tmem_wait_ld();
+        auto max_block = [&](const uint32_t (&v)[16], int kb) {
+          const uint32_t mw = mrow[kb >> 1] >> (16 * (kb & 1));
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            vm0 = fmaxf(vm0, ((mw >> i) & 1u) ? __uint_as_float(v[0][i]) : -INFINITY);
-            vm1 = fmaxf(vm1, ((mw >> (16 + i)) & 1u) ? __uint_as_float(v[1][i]) : -INFINITY);
+          for (int i = 0; i < 16; i += 2) {
+            vm0 = fmaxf(vm0, ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+            vm1 = fmaxf(vm1, ((mw >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : -INFINITY);
+          }
+        };
+        tc05::tmem_ld16(t_s, va);
+#pragma unroll 1
+        for (int kb = 0; kb < nb16; kb += 2) {
+          tc05::tmem_wait_ld();
+          if (kb + 1 < nb16) tc05::tmem_ld16(t_s + (kb + 1) * 16, vb);
+          max_block(va, kb);
+          if (kb + 1 < nb16) {
+            tc05::tmem_wait_ld();
+            if (kb + 2 < nb16) tc05::tmem_ld16(t_s + (kb + 2) * 16, va);
+            max_block(vb, kb + 1);
           }
         }
         const float off = fmaf(-c1, fmaxf(vm0, vm1), 4.0f);
         // pass 2: p = exp(s - max) (x kAScale), row sum, fp16 hi | lo split written back in place
         float sum0 = 0.f, sum1 = 0.f;
+        auto exp_block = [&](const uint32_t (&v)[16], int kb) {
+          const uint32_t mw = mrow[kb >> 1] >> (16 * (kb & 1));
+          uint32_t w[16];  // [hi (8 words) | lo (8 words)] of key block kb
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float e0 = ex2a(fmaf(c1, __uint_as_float(v[i]), off));
+            const float e1 = ex2a(fmaf(c1, __uint_as_float(v[i + 1]), off));
+            const float p0 = ((mw >> i) & 1u) ? e0 : 0.f;
+            const float p1 = ((mw >> (i + 1)) & 1u) ? e1 : 0.f;
+            sum0 += p0;
+            sum1 += p1;
+            f16s_split2(p0, p1, 1.0f, w[i >> 1], w[8 + (i >> 1)]);
+          }
+          tc05::tmem_st16(t_s + kb * 16, w);
+        };
+        tc05::tmem_ld16(t_s, va);
 #pragma unroll 1
-        for (int gb = 0; gb < nblk; ++gb) {
-          uint32_t v[2][16];
-          tc05::tmem_ld16(t_s + gb * 32, v[0]);
-          tc05::tmem_ld16(t_s + gb * 32 + 16, v[1]);
-          const uint32_t mw = mrow[gb];
+        for (int kb = 0; kb < nb16; kb += 2) {
           tc05::tmem_wait_ld();
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            uint32_t w[16];  // [hi (8 words) | lo (8 words)] of key block 2 gb + u
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              const float e0 = ex2a(fmaf(c1, __uint_as_float(v[u][i]), off));
-              const float e1 = ex2a(fmaf(c1, __uint_as_float(v[u][i + 1]), off));
-              const float p0 = ((mw >> (16 * u + i)) & 1u) ? e0 : 0.f;
-              const float p1 = ((mw >> (16 * u + i + 1)) & 1u) ? e1 : 0.f;
-              sum0 += p0;
-              sum1 += p1;
-              f16s_split2(p0, p1, 1.0f, w[i >> 1], w[8 + (i >> 1)]);
-            }
-            if (gb * 32 + u * 16 < R16) tc05::tmem_st16(t_s + gb * 32 + u * 16, w);  // (never past the O slot)
+          if (kb + 1 < nb16) tc05::tmem_ld16(t_s + (kb + 1) * 16, vb);
+          exp_block(va, kb);
+          if (kb + 1 < nb16) {
+            tc05::tmem_wait_ld();
+            if (kb + 2 < nb16) tc05::tmem_ld16(t_s + (kb + 2) * 16, va);
+            exp_block(vb, kb + 1);
           }
         }
         tc05::tmem_wait_st();
@@ -713,16 +727,14 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       for (int c = 0; c < 4; ++c) {
         tc05::mbar_wait(&sm.bar_h, c & 1, 32);
         tc05::fence_after_sync();
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
+        uint32_t va[16], vb[16];
+        auto epi_block = [&](const uint32_t (&v)[16], int q) {
           const int col0 = grp * 64 + q * 16;
-          uint32_t v[16], w[16];
-          tc05::tmem_ld16(t_h + col0, v);
+          uint32_t w[16];
           float bb[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
             *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.w.ffn_b1 + c * kRows + col0 + i));
-          tc05::tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             const float h0 = fmaxf(fmaf(__uint_as_float(v[i]), kUnscaleW, bb[i]), 0.f);
@@ -732,7 +744,19 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
             f16s_split2(h0, h1, kAScale, w[i >> 1], w[8 + (i >> 1)]);
           }
           tc05::tmem_st16(t_h + col0, w);
-        }
+        };
+        tc05::tmem_ld16(t_h + grp * 64, va);
+        tc05::tmem_wait_ld();
+        tc05::tmem_ld16(t_h + grp * 64 + 16, vb);
+        epi_block(va, 0);
+        tc05::tmem_wait_ld();
+        tc05::tmem_ld16(t_h + grp * 64 + 32, va);
+        epi_block(vb, 1);
+        tc05::tmem_wait_ld();
+        tc05::tmem_ld16(t_h + grp * 64 + 48, vb);
+        epi_block(va, 2);
+        tc05::tmem_wait_ld();
+        epi_block(vb, 3);
         tc05::tmem_wait_st();
         tc05::fence_before_sync();
         tc05::mbar_arrive(&sm.bar_epi);

@@ -34,7 +34,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // until the phase completes (wake-up ~60 cycles after the arrival) or the hint elapses, so a waiting warp does not
 // compete for issue slots with the warps that do the work (a polling loop with __nanosleep was 43 % of all executed
 // instructions of the fused rollout kernel, profiles/r2_ncu_lean_v1.txt).  `backoff_ns` is kept for call-site
-// compatibility and unused.  A lost arrival must fail loudly, never hang the GPU: after ~4 s of waiting the kernel traps.
+// compatibility and unused.  A lost arrival must fail loudly, never hang the GPU: after 2^24 failed waits (seconds) the kernel traps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t backoff_ns = 0) {
   (void)backoff_ns;
   const uint32_t addr = smem_u32(bar);
@@ -47,8 +47,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
       : "r"(addr), "r"(parity), "r"(1000000u)
       : "memory");
   if (ok) return;
-  unsigned long long t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t polls = 0;  // a failed try_wait has parked the thread for >= ~400 cycles: 2^24 of them are seconds
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -58,9 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
         : "r"(addr), "r"(parity), "r"(1000000u)
         : "memory");
     if (ok) break;
-    unsigned long long t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 4000000000ull) __trap();
+    if (++polls > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t tx_bytes) {
