@@ -49,6 +49,7 @@ struct LeanSmem {
   uint32_t mask[kRows][4];
   unsigned char cur[kRows], first[kRows], active[kRows], done[kRows];
   uint32_t lhmask[4];
+  uint32_t kmax2[kH];                      // max over the keys of |K_h row|^2 (fp32 bits; non-negative floats order as integers)
   uint64_t bar_full[kLStages], bar_empty[kLStages];
   uint64_t bar_step;     // compute -> producer: another decode step follows (or exit)
   uint64_t bar_q;        // compute -> issuer: query tiles written (256 arrivals; also the exit signal)
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
     tc05::mbar_init(&sm.bar_acc, 1);
     tc05::fence_mbar_init();
     sm.exit_flag = 0;
+    for (int i = 0; i < kH; ++i) sm.kmax2[i] = 0u;
   }
   if (tid < kE) {
 #pragma unroll
@@ -271,6 +273,11 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         if (r < N) {
           v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * kE) + c8 * 2);
           v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * kE) + c8 * 2 + 1);
+        }
+        if (which == 0) {  // |K_h row|^2 (lanes 2i, 2i+1 hold the two halves of a head) -> per-head maximum over the keys
+          float n2 = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+          n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+          if ((c8 & 1) == 0) atomicMax(&sm.kmax2[c8 >> 1], __float_as_uint(n2));
         }
         uint32_t h[4], l[4];
         f16s_split2(v0.x, v0.y, scale, h[0], l[0]); f16s_split2(v0.z, v0.w, scale, h[1], l[1]);
@@ -632,30 +639,47 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         // processed (a TMEM round trip is a few hundred cycles; two resident tiles do not hide it by themselves).
         const int nb16 = R16 >> 4;
         uint32_t va[16], vb[16];
-        // pass 1: row maximum over the feasible keys
-        float vm0 = -INFINITY, vm1 = -INFINITY;
-        auto max_block = [&](const uint32_t (&v)[16], int kb) {
-          const uint32_t mw = mrow[kb >> 1] >> (16 * (kb & 1));
+        // Softmax shift.  Any shift m' >= max gives the same probabilities; the exact row maximum costs a pass over the
+        // scores (a quarter of the softmax instructions), the Cauchy-Schwarz bound |q_h| max_k |k_h| costs ~30.  The fp16
+        // hi | lo operands of P V resolve 2^-24 absolute, so the largest p must stay >= 1 after scaling: with p scaled by
+        // 2^14 the bound may exceed the true maximum by 14 (log2 units), which holds whenever c1 vB <= 7 (scores within
+        // +-4.8: every random-init and moderately peaked head).  Otherwise: the exact maximum, p scaled by 2^4 as before.
+        float off;
+        {
+          const uint4 q0 = *reinterpret_cast<const uint4*>(&a_hi[(2 * h) * (kRows * 8) + row * 8]);
+          const uint4 q1 = *reinterpret_cast<const uint4*>(&a_hi[(2 * h + 1) * (kRows * 8) + row * 8]);
+          const uint32_t qw[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+          float qn2 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            vm0 = fmaxf(vm0, ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
-            vm1 = fmaxf(vm1, ((mw >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : -INFINITY);
+          for (int e = 0; e < 8; ++e) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&qw[e]));
+            qn2 = fmaf(f.x, f.x, fmaf(f.y, f.y, qn2));
           }
-        };
-        tc05::tmem_ld16(t_s, va);
+          // v = sum (kAScale q)(kKvScale k) <= |Q_hi| (1 + 2^-10) kKvScale max|k_h|
+          const float vB = sqrtf(qn2 * __uint_as_float(sm.kmax2[h])) * (kKvScale * 1.004f);
+          off = fmaf(-c1, vB, 14.0f);
+          // (warp-uniform decision: the TMEM loads below are warp-collective)
+          if (__any_sync(0xffffffffu, !(c1 * vB <= 7.0f))) {
+            // exact row maximum over the feasible keys
+            float vm0 = -INFINITY, vm1 = -INFINITY;
+            auto max_block = [&](const uint32_t (&v)[16], int kb) {
+              const uint32_t mw = mrow[kb >> 1] >> (16 * (kb & 1));
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                vm0 = fmaxf(vm0, ((mw >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY);
+                vm1 = fmaxf(vm1, ((mw >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : -INFINITY);
+              }
+            };
 #pragma unroll 1
-        for (int kb = 0; kb < nb16; kb += 2) {
-          tc05::tmem_wait_ld();
-          if (kb + 1 < nb16) tc05::tmem_ld16(t_s + (kb + 1) * 16, vb);
-          max_block(va, kb);
-          if (kb + 1 < nb16) {
-            tc05::tmem_wait_ld();
-            if (kb + 2 < nb16) tc05::tmem_ld16(t_s + (kb + 2) * 16, va);
-            max_block(vb, kb + 1);
+            for (int kb = 0; kb < nb16; ++kb) {
+              tc05::tmem_ld16(t_s + kb * 16, va);
+              tc05::tmem_wait_ld();
+              max_block(va, kb);
+            }
+            off = fmaf(-c1, fmaxf(vm0, vm1), 4.0f);
           }
         }
-        const float off = fmaf(-c1, fmaxf(vm0, vm1), 4.0f);
-        // pass 2: p = exp(s - max) (x kAScale), row sum, fp16 hi | lo split written back in place
+        // p = exp(s - m') (x 2^14 or 2^4), row sum, fp16 hi | lo split written back in place
         float sum0 = 0.f, sum1 = 0.f;
         auto exp_block = [&](const uint32_t (&v)[16], int kb) {
           const uint32_t mw = mrow[kb >> 1] >> (16 * (kb & 1));
