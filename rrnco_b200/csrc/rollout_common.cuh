@@ -30,6 +30,7 @@ struct RolloutParams {
   int32_t* max_steps_out;
   uint32_t* status;
   const unsigned char* ffn_packed;  // tcgen05 variant: W1 / W2 packed fp16 hi | lo slices (ffn_pack.cuh)
+  const float* ffn_bias_scaled;     // lean engine: kAScale * b1 [512] | kAScale * b2 [128] (written by its weight-pack kernel)
   unsigned char* kv_pack;           // tcgen05 variant: kKvSlots per-SM slots of packed fp16 K | V tiles (kKvSlotBytes each)
 };
 

@@ -1811,8 +1811,11 @@ int dispatch_env_tc(const RolloutParams& p, int env, int passes, cudaStream_t st
 #else
 int dispatch_env_tc(const RolloutParams& p, int env, int passes, cudaStream_t st);  // rollout_kernel_tc.cu
 int dispatch_env_lean(const RolloutParams& p, int env, int passes, cudaStream_t st);  // rollout_lean.cu
-int pack_ffn_lean(const float* w1, const float* w2, void* packed, cudaStream_t st);
+int pack_ffn_lean(const float* w1, const float* w2, const float* b1, const float* b2, void* packed, uint32_t* status,
+                  cudaStream_t st);
+constexpr int64_t kLeanBiasBytes = 4096;  // scaled biases behind the packed weight slices
 int64_t lean_kv_bytes(int32_t n_nodes, int64_t n_tiles_total);
+int phase_cycles_lean(long long* h_out, int reset);
 constexpr int kLeanMaxNodes = 112;  // two score buffers + two P V slots in 256 TMEM columns
 int phase_cycles_tc(long long* h_out, int reset);
 int timeline_tc(long long* h_out, int* n_out);
@@ -1859,7 +1862,8 @@ extern "C" {
 
 // debug: per-phase cycle totals of CTA 0 since the last reset (host buffer of 16 int64); reset != 0 clears them
 int rrnco_debug_phase_cycles(long long* h_out, int reset) {
-  return g_engine >= 1 ? phase_cycles_tc(h_out, reset) : phase_cycles_local(h_out, reset);
+  if (g_engine == 2) return phase_cycles_lean(h_out, reset);  // 32 counters
+  return g_engine == 1 ? phase_cycles_tc(h_out, reset) : phase_cycles_local(h_out, reset);
 }
 
 // debug: event timeline of the tcgen05 variant (512 int64 = 256 (tag, clock) pairs); development builds only
@@ -1887,7 +1891,7 @@ int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_in
   // packed K / V / logit-key tiles: one region per CTA (lean engine) or one slot per SM (one-CTA engine)
   int64_t kv = (int64_t)kKvSlots * kKvSlotBytes;
   if (n_nodes <= kLeanMaxNodes && lean_kv_bytes(n_nodes, tiles) > kv) kv = lean_kv_bytes(n_nodes, tiles);
-  return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL) + kFfnPackedBytes + kv;
+  return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL) + kFfnPackedBytes + kLeanBiasBytes + kv;
 }
 
 int rrnco_decoder_logits(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts,
@@ -1943,11 +1947,12 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
   const int64_t tiles = n_inst * p.n_tiles;
   unsigned char* packed = reinterpret_cast<unsigned char*>(p.ws_tile_steps) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL);
   p.ffn_packed = packed;
-  p.kv_pack = packed + kFfnPackedBytes;  // 16-byte aligned: every part above is a multiple of 16 bytes
+  p.ffn_bias_scaled = reinterpret_cast<const float*>(packed + kFfnPackedBytes);
+  p.kv_pack = packed + kFfnPackedBytes + kLeanBiasBytes;  // 16-byte aligned: every part above is a multiple of 16 bytes
   p.max_steps_out = max_steps_out; p.status = status;
   if (cudaMemsetAsync(max_steps_out, 0, sizeof(int32_t), st) != cudaSuccess) return RRNCO_ERR_CUDA;
   if (g_engine == 2 && n_nodes <= kLeanMaxNodes) {
-    rc = pack_ffn_lean(w->ffn_w1, w->ffn_w2, packed, st);
+    rc = pack_ffn_lean(w->ffn_w1, w->ffn_w2, w->ffn_b1, w->ffn_b2, packed, status, st);
     if (rc != RRNCO_OK) return rc;
     rc = dispatch_env_lean(p, env, g_passes, st);
   } else if (g_engine >= 1) {

@@ -36,6 +36,21 @@ constexpr int kLJobs = 8;                 // G1(0) G2(0) G1(1) G2(1) G1(2) G2(2)
 constexpr int kLWSlices = kLJobs * 8;     // one 8 KB slice per K step (16 k values) of a 128 x 128 x 128 job
 constexpr int64_t kLeanFfnPackedBytes = (int64_t)kLWSlices * kLStageBytes;  // 512 KB
 
+// per-phase cycle accumulator of thread 0 of CTA 0 (development builds: RRNCO_PHASE_STAMPS), read with rrnco_debug_phase_cycles
+__device__ long long g_lean_cycles[32];
+#ifdef RRNCO_PHASE_STAMPS
+#define LSTAMP(i)                                   \
+  do {                                              \
+    if (blockIdx.x == 0 && tid == 0) {              \
+      const long long now_ = clock64();             \
+      g_lean_cycles[i] += now_ - stamp_t0;          \
+      stamp_t0 = now_;                              \
+    }                                               \
+  } while (0)
+#else
+#define LSTAMP(i) do { } while (0)
+#endif
+
 template <int kEnv>
 struct LeanSmem {
   static constexpr int kNodeArrays = kEnv == RRNCO_ENV_RCVRPTW ? 7 : 1;
@@ -83,8 +98,15 @@ __device__ __forceinline__ int lean_sync_and(int pred) {
 // Pack W1 / W2 into 64 slices of 8 KB in tensor-pipe order: slice (job j, K step ks), job j = chunk j >> 1, half j & 1
 // (0: W1 rows of the chunk, k = input dims; 1: W2 rows = output dims, k = hidden units of the chunk);
 // layout [hi | lo][16-byte K chunk (2)][row (128)][8 halves].  One thread per (slice, row, k pair).
-__global__ void pack_ffn_lean_kernel(const float* __restrict__ w1, const float* __restrict__ w2, uint32_t* __restrict__ packed) {
+// Also writes the biases pre-scaled by kAScale behind the slices (b1 [512] | b2 [128]): the epilogues then produce the
+// scaled fp16 operands directly.  A weight outside the fp16 range of its scaled hi part is reported, never silent.
+__global__ void pack_ffn_lean_kernel(const float* __restrict__ w1, const float* __restrict__ w2, const float* __restrict__ b1,
+                                     const float* __restrict__ b2, uint32_t* __restrict__ packed, uint32_t* status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kF + kE) {
+    float* bs = reinterpret_cast<float*>(packed + kLWSlices * (kLStageBytes / 4));
+    bs[i] = kAScale * (i < kF ? b1[i] : b2[i - kF]);
+  }
   if (i >= kLWSlices * kRows * 8) return;
   const int kp = i & 7, row = (i >> 3) & 127, s = i >> 10;
   const int j = s >> 3, ks = s & 7, c = j >> 1, half = j & 1;
@@ -97,6 +119,7 @@ __global__ void pack_ffn_lean_kernel(const float* __restrict__ w1, const float* 
     v0 = w2[(size_t)row * kF + c * kRows + k];
     v1 = w2[(size_t)row * kF + c * kRows + k + 1];
   }
+  if (!(fabsf(v0) * kWScale < 65504.f) || !(fabsf(v1) * kWScale < 65504.f)) atomicOr(status, RRNCO_DEV_NAN_LOGITS);
   uint32_t hi, lo;
   f16s_split2(v0, v1, kWScale, hi, lo);
   uint32_t* dst = packed + (size_t)s * (kLStageBytes / 4) + (kp >> 2) * (kRows * 4) + row * 4 + (kp & 3);
@@ -474,11 +497,15 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
   uint32_t step_par = 0;
   int step = 0;
   int t_out = p.multistart ? 1 : 0;
+#ifdef RRNCO_PHASE_STAMPS
+  long long stamp_t0 = clock64();
+#endif
   uint16_t* a_hi = reinterpret_cast<uint16_t*>(sm.A);     // [16-byte K chunk (16)][row (128)][8 halves]
   uint16_t* a_lo = a_hi + kRows * kE;
   constexpr float kUnscaleW = 1.0f / (kAScale * kWScale), kUnscaleL = 1.0f / (kAScale * kLkScale);
 
   while (true) {
+    LSTAMP(24);
     const int all_done = lean_sync_and(tid < kRows ? (sm.done[tid] || !sm.active[tid]) : 1);  // own rows only: no race
     if (all_done) break;
     if (step >= p.max_steps) {  // policy.py:222-226: cut, but never silently
@@ -486,6 +513,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       break;
     }
     if (tid == 0) tc05::mbar_arrive(&sm.bar_step);
+    LSTAMP(0);
 
     // ---- A: lane = (rollout of the warp's 16, 64-wide half of the columns): action-mask words of that half, then the
     // query rows q = ctx_proj[cur] + sum_k state_k w_k -> fp16 hi | lo core-matrix tiles (A operand of Q K^T) ----
@@ -618,7 +646,9 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
     tc05::fence_proxy_async();
     tc05::fence_before_sync();
     tc05::mbar_arrive(&sm.bar_q);
+    LSTAMP(1);
     lean_sync();  // action-mask bitsets visible to the row-owner threads
+    LSTAMP(2);
 
     // ---- C: attention.  Group g (warps 4g .. 4g+3) owns score buffer g and heads 4g .. 4g+3: masked softmax of the
     // thread's row, probabilities written back IN PLACE as the fp16 hi | lo A operand of P V; then, once P V(h) has
@@ -630,11 +660,13 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       const float c1 = 0.25f * 1.4426950408889634f / (kAScale * kKvScale);
       uint32_t mrow[4];
       *reinterpret_cast<uint4*>(mrow) = *reinterpret_cast<const uint4*>(sm.mask[row]);
+      bool bad_operand = false;
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         const int h = 4 * grp + j;
         tc05::mbar_wait(&sm.bar_s[h], step_par, 20);
         tc05::fence_after_sync();
+        LSTAMP(3);
         // Both passes walk the row in 16-column blocks with the TMEM load of block k + 1 in flight while block k is
         // processed (a TMEM round trip is a few hundred cycles; two resident tiles do not hide it by themselves).
         const int nb16 = R16 >> 4;
@@ -679,6 +711,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
             off = fmaf(-c1, fmaxf(vm0, vm1), 4.0f);
           }
         }
+        LSTAMP(4);
         // p = exp(s - m') (x 2^14 or 2^4), row sum, fp16 hi | lo split written back in place
         float sum0 = 0.f, sum1 = 0.f;
         auto exp_block = [&](const uint32_t (&v)[16], int kb) {
@@ -711,10 +744,12 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         tc05::tmem_wait_st();
         tc05::fence_before_sync();
         tc05::mbar_arrive(&sm.bar_p[h]);
+        LSTAMP(5);
         // glimpse of head h (decoder.py:292-293)
-        const float inv = __fdividef(1.0f, kKvScale * (sum0 + sum1));
+        const float inv = __fdividef(kAScale, kKvScale * (sum0 + sum1));  // glimpse scaled by kAScale, like the query tiles
         tc05::mbar_wait(&sm.bar_o[h], step_par, 20);
         tc05::fence_after_sync();
+        LSTAMP(6);
         uint32_t o[16];
         tc05::tmem_ld16(t_o, o);
         tc05::tmem_wait_ld();
@@ -729,14 +764,18 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           for (int e = 0; e < 4; ++e) {
             const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&qhw[e]));
             const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&qlw[e]));
-            const float g0 = fmaf(__uint_as_float(o[cc * 8 + 2 * e]), inv, (fh.x + fl.x) * (1.0f / kAScale));
-            const float g1 = fmaf(__uint_as_float(o[cc * 8 + 2 * e + 1]), inv, (fh.y + fl.y) * (1.0f / kAScale));
-            f16s_split2(g0, g1, kAScale, hi[e], lo[e]);
+            const float g0 = fmaf(__uint_as_float(o[cc * 8 + 2 * e]), inv, fh.x + fl.x);
+            const float g1 = fmaf(__uint_as_float(o[cc * 8 + 2 * e + 1]), inv, fh.y + fl.y);
+            // every operand overflow / NaN upstream of the FFN ends up here (a ReLU would swallow it later): keep it loud
+            bad_operand |= !(fabsf(g0) < 65504.f) | !(fabsf(g1) < 65504.f);
+            f16s_split2(g0, g1, 1.0f, hi[e], lo[e]);
           }
           *reinterpret_cast<uint4*>(&a_hi[offq]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(&a_lo[offq]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
+      if (bad_operand) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
+      LSTAMP(7);
     }
     tc05::fence_proxy_async();
     tc05::fence_before_sync();
@@ -746,11 +785,11 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
     // (16 fp32 columns of K step ks -> hi at 16 ks .. +7, lo at 16 ks + 8 .. +15) = the A operand of GEMM2(c) ----
     {
       const uint32_t t_h = tb + lane_b;
-      float nonfinite = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         tc05::mbar_wait(&sm.bar_h, c & 1, 32);
         tc05::fence_after_sync();
+        LSTAMP(9);
         uint32_t va[16], vb[16];
         auto epi_block = [&](const uint32_t (&v)[16], int q) {
           const int col0 = grp * 64 + q * 16;
@@ -758,14 +797,14 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           float bb[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.w.ffn_b1 + c * kRows + col0 + i));
+            *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.ffn_bias_scaled + c * kRows + col0 + i));
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const float h0 = fmaxf(fmaf(__uint_as_float(v[i]), kUnscaleW, bb[i]), 0.f);
-            const float h1 = fmaxf(fmaf(__uint_as_float(v[i + 1]), kUnscaleW, bb[i + 1]), 0.f);
-            // the ReLU would swallow a NaN (fp16 operand overflow upstream of here, ffn_pack.cuh): x * 0 keeps it
-            nonfinite = fmaf(__uint_as_float(v[i]), 0.0f, fmaf(__uint_as_float(v[i + 1]), 0.0f, nonfinite));
-            f16s_split2(h0, h1, kAScale, w[i >> 1], w[8 + (i >> 1)]);
+            // kAScale relu(acc / (kAScale kWScale) + b1): the scaled operand directly (b1 pre-scaled; powers of two: exact).
+            // Non-finite accumulators cannot arise here: the operands of GEMM1 were checked where they were written.
+            const float h0 = fmaxf(fmaf(__uint_as_float(v[i]), kAScale * kUnscaleW, bb[i]), 0.f);
+            const float h1 = fmaxf(fmaf(__uint_as_float(v[i + 1]), kAScale * kUnscaleW, bb[i + 1]), 0.f);
+            f16s_split2(h0, h1, 1.0f, w[i >> 1], w[8 + (i >> 1)]);
           }
           tc05::tmem_st16(t_h + col0, w);
         };
@@ -784,10 +823,11 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         tc05::tmem_wait_st();
         tc05::fence_before_sync();
         tc05::mbar_arrive(&sm.bar_epi);
+        LSTAMP(10);
       }
-      if (nonfinite != 0.f) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);  // NaN != 0
       tc05::mbar_wait(&sm.bar_g2, step_par, 32);
       tc05::fence_after_sync();
+      LSTAMP(11);
       // output epilogue: g' = acc + b2 + g -> fp16 hi | lo in place over the output accumulator (A operand of the logits)
       const uint32_t t_oa = tb + 128u + lane_b;
       const int row = trow;
@@ -799,11 +839,11 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         float bb[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.w.ffn_b2 + col0 + i));
+          *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.ffn_bias_scaled + kF + col0 + i));
         tc05::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; i += 8) {
-          const int off = ((col0 + i) >> 3) * (kRows * 8) + row * 8;  // residual g = (hi + lo) / kAScale, exact to 2^-24
+          const int off = ((col0 + i) >> 3) * (kRows * 8) + row * 8;  // residual kAScale g = hi + lo, exact to 2^-24
           const uint4 gh = *reinterpret_cast<const uint4*>(&a_hi[off]);
           const uint4 gl = *reinterpret_cast<const uint4*>(&a_lo[off]);
           const uint32_t ghw[4] = {gh.x, gh.y, gh.z, gh.w}, glw[4] = {gl.x, gl.y, gl.z, gl.w};
@@ -811,9 +851,9 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           for (int e = 0; e < 4; ++e) {
             const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&ghw[e]));
             const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&glw[e]));
-            const float o0 = fmaf(__uint_as_float(v[i + 2 * e]), kUnscaleW, bb[i + 2 * e]) + (fh.x + fl.x) * (1.0f / kAScale);
-            const float o1 = fmaf(__uint_as_float(v[i + 2 * e + 1]), kUnscaleW, bb[i + 2 * e + 1]) + (fh.y + fl.y) * (1.0f / kAScale);
-            f16s_split2(o0, o1, kAScale, w[(i >> 1) + e], w[8 + (i >> 1) + e]);
+            const float o0 = fmaf(__uint_as_float(v[i + 2 * e]), kAScale * kUnscaleW, bb[i + 2 * e]) + (fh.x + fl.x);
+            const float o1 = fmaf(__uint_as_float(v[i + 2 * e + 1]), kAScale * kUnscaleW, bb[i + 2 * e + 1]) + (fh.y + fl.y);
+            f16s_split2(o0, o1, 1.0f, w[(i >> 1) + e], w[8 + (i >> 1) + e]);
           }
         }
         tc05::tmem_st16(t_oa + col0, w);
@@ -821,8 +861,10 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       tc05::tmem_wait_st();
       tc05::fence_before_sync();
       tc05::mbar_arrive(&sm.bar_lk);
+      LSTAMP(12);
     }
-    lean_sync();  // every thread has read its residual: the activation region may be overwritten by the bias tile
+    lean_sync();
+    LSTAMP(13);  // every thread has read its residual: the activation region may be overwritten by the bias tile
 
     // bias rows of the rollouts (alpha . D[cur,:] + beta . Dur[cur,:]) -> fp32 tile in the (dead) activation region while
     // the logits MMAs run: coalesced, one warp per 16 rollouts
@@ -855,9 +897,12 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           }
       }
     }
+    LSTAMP(14);
     lean_sync();
+    LSTAMP(15);
     tc05::mbar_wait(&sm.bar_acc, step_par, 32);
     tc05::fence_after_sync();
+    LSTAMP(16);
 
     // ---- S: select, thread per row: two threads own one rollout, 16-column groups dealt round-robin; three rolled
     // passes over the logits, which stay in TMEM (pass A rewrites them in place) ----
@@ -917,7 +962,9 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       tc05::tmem_wait_st();
       if (nan_seen) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
       xf[0][colhalf][row] = mxl;
+      LSTAMP(17);
       lean_sync();
+      LSTAMP(18);
       const float mx = fmaxf(xf[0][0][row], xf[0][1][row]);
       // pass B: softmax denominator
       float sel = 0.f;
@@ -930,7 +977,9 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         for (int i = 0; i < 16; ++i) sel += fexp(__uint_as_float(v[i]) - mx);
       }
       xf[1][colhalf][row] = sel;
+      LSTAMP(19);
       lean_sync();
+      LSTAMP(20);
       const float se = flog(xf[1][0][row] + xf[1][1][row]);
       // pass C: log-softmax in the reference's order; argmax of log p (greedy) or of log p + Gumbel noise (sampling);
       // evaluate: log p of the forced action
@@ -979,7 +1028,9 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       xf[2][colhalf][row] = best;
       xf[0][colhalf][row] = bestlp;  // xf[0] (row maxima) was last read before the previous barrier
       xi[colhalf][row] = (unsigned char)besti;
+      LSTAMP(21);
       lean_sync();
+      LSTAMP(22);
       int act = xi[0][row];  // larger key wins, ties -> lower index
       int win = 0;
       if (xf[2][1][row] > xf[2][0][row] || (xf[2][1][row] == xf[2][0][row] && xi[1][row] < act)) win = 1;
@@ -1003,6 +1054,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         }
       }
     }
+    LSTAMP(23);
     ++step;
     ++t_out;
     step_par ^= 1u;
@@ -1057,10 +1109,19 @@ int64_t lean_kv_bytes(int32_t n_nodes, int64_t n_tiles_total) {
   const int64_t R16 = ((n_nodes + 15) >> 4) << 4;
   return n_tiles_total * 24 * R16 * 64;
 }
-int pack_ffn_lean(const float* w1, const float* w2, void* packed, cudaStream_t st) {
+int pack_ffn_lean(const float* w1, const float* w2, const float* b1, const float* b2, void* packed, uint32_t* status,
+                  cudaStream_t st) {
   const int n = kLWSlices * kRows * 8;
-  pack_ffn_lean_kernel<<<(n + 255) / 256, 256, 0, st>>>(w1, w2, reinterpret_cast<uint32_t*>(packed));
+  pack_ffn_lean_kernel<<<(n + 255) / 256, 256, 0, st>>>(w1, w2, b1, b2, reinterpret_cast<uint32_t*>(packed), status);
   return rrnco_launch_status();
+}
+int phase_cycles_lean(long long* h_out, int reset) {
+  if (h_out && cudaMemcpyFromSymbol(h_out, g_lean_cycles, sizeof(long long) * 32) != cudaSuccess) return RRNCO_ERR_CUDA;
+  if (reset) {
+    long long z[32] = {0};
+    if (cudaMemcpyToSymbol(g_lean_cycles, z, sizeof(z)) != cudaSuccess) return RRNCO_ERR_CUDA;
+  }
+  return RRNCO_OK;
 }
 int dispatch_env_lean(const RolloutParams& p, int env, int passes, cudaStream_t st) {
   static_assert(sizeof(LeanSmem<RRNCO_ENV_RCVRPTW>) <= 115712, "two CTAs per SM need <= 113 KB of shared memory each");
