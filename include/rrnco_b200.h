@@ -99,8 +99,10 @@ int rrnco_minmax_normalize(int64_t n_mat, int32_t n_nodes, const float* dist_in,
  *   replaces Real_World_Sampler.sample rrnco/envs/rcvrp/sampler.py:84-90 (+ the fp32 cast of
  *   rrnco/envs/rcvrp/generator_lazy.py:300).  M is the float64 city matrix [L,L]
  *   (data_generation/utilities/create_dataset.py:169-174); idx is int32 [batch, n].
- *   If normalize != 0 the min-max normalisation of env.reset is fused (min_out / max_out filled);
- *   min_out / max_out may be NULL when normalize == 0.
+ *   normalize == 1 fuses the min-max normalisation of env.reset, (d - min) / (max - min + 1e-6);
+ *   normalize == 2 fuses the generators' duration law, (d - min) / (max - min) with a zero range replaced by 1
+ *   (rrnco/envs/rmtvrp/generator_lazy.py:365-369); min_out / max_out are filled in both cases and may be NULL
+ *   when normalize == 0.
  * ---------------------------------------------------------------------------------------------- */
 int rrnco_gather_submatrix(const double* city_matrix, int32_t city_len, const int32_t* idx, int64_t batch,
                            int32_t n, float* out, int32_t normalize, float* min_out, float* max_out,

@@ -15,7 +15,9 @@ from .models import (PrecomputedCache, RRNetDecoder, RRNetPolicy, fused_rollout,
                      stepwise_rollout)
 from .dataio import iter_batches, load_city_npz, load_npz_to_tensordict, prepare_test_td  # noqa: F401
 from .hostio import HostPrefetcher  # noqa: F401
-from .sampler import Real_World_Sampler  # noqa: F401
+from .sampler import CityOnDevice, Real_World_Sampler, remove_outlier_points  # noqa: F401
+from .generator import LazyATSPGenerator, LazyRCVRPGenerator, LazyRMTVRPGenerator  # noqa: F401
+from .transforms import StateAugmentation, dihedral_8_augmentation  # noqa: F401
 from .tdlite import TensorDictLite, batchify, unbatchify  # noqa: F401
 from .training import (batched_logprobs, collect_decode_inputs, pomo_shared_baseline_loss,  # noqa: F401
                        replay_log_likelihood)
@@ -23,4 +25,5 @@ from .training import (batched_logprobs, collect_decode_inputs, pomo_shared_base
 __all__ = ["ATSPEnv", "RCVRPEnv", "RMTVRPEnv", "get_env", "RRNetDecoder", "RRNetPolicy", "PrecomputedCache",
            "fused_rollout", "stepwise_rollout", "select_action", "Real_World_Sampler", "TensorDictLite", "batchify", "unbatchify", "set_precision", "set_ffn_engine", "set_step_tiling",
            "RRNCOError", "HostPrefetcher", "load_city_npz", "load_npz_to_tensordict", "prepare_test_td", "iter_batches", "replay_log_likelihood", "batched_logprobs", "collect_decode_inputs",
-           "pomo_shared_baseline_loss"]
+           "pomo_shared_baseline_loss", "CityOnDevice", "remove_outlier_points", "LazyATSPGenerator", "LazyRCVRPGenerator",
+           "LazyRMTVRPGenerator", "StateAugmentation", "dihedral_8_augmentation"]

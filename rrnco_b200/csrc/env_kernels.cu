@@ -67,6 +67,15 @@ __global__ void __launch_bounds__(256) minmax_normalize_kernel(int n2, const flo
 // kPer == 0: chunks of 4 loads issued before their 4 stores (the first version had one load in flight per thread:
 // long_scoreboard 18.9 per issue at 90 % occupancy, profiles/r1_ncu_env_kernels_v3.txt).  (i, j) advance incrementally:
 // one integer division per thread instead of one per element.
+// normalize == 1: env._reset's law for the distance matrix, (d - min) / (max - min + 1e-6)   (rcvrp/env.py:138-145)
+// normalize == 2: the generators' law for the duration matrix, (d - min) / (max - min), range 0 -> 1
+//                 (rmtvrp/generator_lazy.py:365-369: np.where(max - min == 0, 1, max - min))
+__device__ __forceinline__ float minmax_denom(float lo, float hi, int normalize) {
+  const float range = __fsub_rn(hi, lo);
+  if (normalize == 2) return range == 0.f ? 1.0f : range;
+  return __fadd_rn(range, 1e-6f);
+}
+
 template <typename T, int kPer>
 __global__ void __launch_bounds__(256) gather_submatrix_kernel(const T* __restrict__ M, int L,
                                                                const int32_t* __restrict__ idx, int n,
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(256) gather_submatrix_kernel(const T* __restri
         hi = fmaxf(hi, v[u]);
       }
     block_minmax(lo, hi, red);
-    const float denom = __fadd_rn(__fsub_rn(hi, lo), 1e-6f);
+    const float denom = minmax_denom(lo, hi, normalize);
 #pragma unroll
     for (int u = 0; u < kPer; ++u)
       if (threadIdx.x + u * 256 < n2) dst[threadIdx.x + u * 256] = __fdiv_rn(__fsub_rn(v[u], lo), denom);
@@ -133,7 +142,7 @@ __global__ void __launch_bounds__(256) gather_submatrix_kernel(const T* __restri
   }
   if (!normalize) return;
   block_minmax(lo, hi, red);  // contains __syncthreads: dst writes of this CTA are visible below
-  const float denom = __fadd_rn(__fsub_rn(hi, lo), 1e-6f);
+  const float denom = minmax_denom(lo, hi, normalize);
   for (int e = threadIdx.x; e < n2; e += 256) dst[e] = __fdiv_rn(__fsub_rn(dst[e], lo), denom);
   if (threadIdx.x == 0) {
     mn[b] = lo;
@@ -633,6 +642,7 @@ static int gather_launch(const T* city_matrix, int32_t city_len, const int32_t* 
                          int32_t normalize, float* min_out, float* max_out, void* stream) {
   if (batch == 0) return RRNCO_OK;
   RRNCO_CHECK_ARG(batch > 0 && n > 0 && city_len >= n && city_matrix && idx && out);
+  RRNCO_CHECK_ARG(normalize >= 0 && normalize <= 2);
   RRNCO_CHECK_ARG(!normalize || (min_out && max_out));
   if ((size_t)n * sizeof(int32_t) > 48 * 1024) return RRNCO_ERR_UNSUPPORTED;
   constexpr int kPer = 40;  // values per thread kept in registers: n <= 101

@@ -15,6 +15,9 @@ It puts `oracle/shims` (stand-ins for rl4co / tensordict / torchrl, see oracle/s
                       embeddings): actions, reward, log-likelihood -> rrnco/models/policy.py, decoding.py
   sampler.npz         Real_World_Sampler.sample on a small synthetic city -> rrnco/envs/*/sampler.py
   augment.npz         StateAugmentation(dihedral8)              -> rrnco/models/utils/transforms.py
+  generator_*.npz     Lazy{RCVRP,ATSP,RMTVRP}Generator._process_real_world_data / subsample_problems with the
+                      uniform draws they consumed               -> rrnco/envs/*/generator_lazy.py, rmtvrp/generator.py
+  sampler_outliers.npz Real_World_Sampler.sample on a city with > 1e5 entries -> rrnco/envs/rmtvrp/sampler.py:41-60
 
 Inputs are produced with oracle.synth (only as an input generator, nothing of the oracle's
 arithmetic is recorded).
@@ -201,7 +204,80 @@ def gen_augment():
     print("augment ok")
 
 
+def gen_generators():
+    """Lazy*Generator._process_real_world_data (+ subsample_problems) of the UNMODIFIED reference on sub-matrices drawn by
+    the reference's own sampler.  The uniform draws the laws consume are recorded by replaying the same torch RNG calls
+    after the same seed (rand / uniform_ share one stream), so that a re-implementation can be checked bit for bit."""
+    from rrnco.envs.rcvrp.generator_lazy import LazyRCVRPGenerator
+    from rrnco.envs.rmtvrp.generator_lazy import LazyRMTVRPGenerator
+    from rrnco.envs.atsp.generator_lazy import LazyATSPGenerator
+    city = synth.make_city(11, length=80)
+    city["duration"][3] = city["duration"][3, 0]  # (rows with a constant duration exist in OSRM tables)
+    B, n = 6, 12
+
+    def save(name, rec):
+        np.savez_compressed(os.path.join(HERE, name), **rec)
+        print(name, "ok")
+
+    # rcvrp
+    np.random.seed(77)
+    chunk = SamplerC().sample(city, batch=B, num_sample=n + 1)
+    gen = LazyRCVRPGenerator(num_loc=n)
+    torch.manual_seed(123)
+    td = gen._process_real_world_data(dict(chunk), [B])
+    torch.manual_seed(123)
+    rec = {"in.points": chunk["points"], "in.distance_matrix": chunk["distance_matrix"], "draw.demand": torch.rand(B, n).numpy(),
+           "capacity_value": np.float32(gen.capacity)}
+    rec.update({f"out.{k}": td[k].numpy() for k in td.keys()})
+    save("generator_rcvrp.npz", rec)
+
+    # atsp
+    np.random.seed(78)
+    chunk = SamplerC().sample(city, batch=B, num_sample=n)
+    td = LazyATSPGenerator(num_loc=n)._process_real_world_data(dict(chunk), [B])
+    rec = {"in.points": chunk["points"], "in.distance_matrix": chunk["distance_matrix"]}
+    rec.update({f"out.{k}": td[k].numpy() for k in td.keys()})
+    save("generator_atsp.npz", rec)
+
+    # rcvrptw (config preset "vrptw") and the all-features preset; one instance gets a constant duration matrix
+    for preset in ("vrptw", "ovrpbltw"):
+        np.random.seed(79)
+        chunk = SamplerTW().sample(city, batch=B, num_sample=n + 1)
+        chunk["duration_matrix"][2] = 7.5  # zero range -> the np.where guard
+        gen = LazyRMTVRPGenerator(num_loc=n, variant_preset=preset)
+        torch.manual_seed(321)
+        td = gen._process_real_world_data({k: v.copy() for k, v in chunk.items()}, [B])
+        torch.manual_seed(321)
+        rec = {"in.points": chunk["points"], "in.distance_matrix": chunk["distance_matrix"],
+               "in.duration_matrix": chunk["duration_matrix"], "capacity_value": np.float32(gen.capacity)}
+        for key, shape in (("linehaul", (B, n)), ("backhaul", (B, n)), ("is_linehaul", (B, n)), ("service_time", (B, n)),
+                           ("tw_length", (B, n)), ("tw_start", (B, n)), ("distance_limit", (B,))):
+            rec["draw." + key] = torch.rand(*shape).numpy()
+        rec.update({f"out.{k}": td[k].numpy() for k in td.keys()})
+        sub = gen.subsample_problems(TensorDict({k: v.clone() for k, v in td.items()}, batch_size=[B]))
+        rec.update({f"sub.{k}": sub[k].numpy() for k in sub.keys()})
+        save(f"generator_rcvrptw_{preset}.npz", rec)
+
+
+def gen_outliers():
+    """Real_World_Sampler.sample on a city with unreachable pairs (> 1e5): the row / column removal of sampler.py:41-60."""
+    city = synth.make_city(12, length=40)
+    for r, c in ((5, 9), (5, 17), (5, 30), (22, 9)):
+        city["distance"][r, c] = 2.0e5
+        city["duration"][r, c] = 2.0e5
+    rec = {f"city.{k}": v for k, v in city.items()}
+    np.random.seed(99)
+    s = SamplerTW().sample(city, batch=4, num_sample=9)
+    rec["points"], rec["distance_matrix"], rec["duration_matrix"] = s["points"], s["distance_matrix"], s["duration_matrix"]
+    np.savez_compressed(os.path.join(HERE, "sampler_outliers.npz"), **rec)
+    print("sampler outliers ok", s["distance_matrix"].max())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "new":  # fixtures added in round 2 (the others regenerate bit-identically)
+        gen_generators()
+        gen_outliers()
+        sys.exit(0)
     gen_env("atsp", 9, 6, 10)
     gen_env("rcvrp", 12, 6, 11)   # continuous demand law
     gen_env("rcvrp", 12, 6, 12, variant="int")  # integer demand law (seed even)
@@ -212,3 +288,5 @@ if __name__ == "__main__":
         gen_decoder_and_policy(name, 10, 3, 20)
     gen_sampler()
     gen_augment()
+    gen_generators()
+    gen_outliers()

@@ -862,6 +862,90 @@ def test_truncated_rollout_is_reported_and_open_route_reward_does_not_mutate(rb,
 
 
 # ----------------------------------------------------------------------------------------------------
+# on-device instance generation, un-materialised x8 augmentation
+# ----------------------------------------------------------------------------------------------------
+def test_gather_duration_law_and_outlier_city(rb):
+    """rrnco_gather_submatrix normalize == 2 = the generators' duration law (rmtvrp/generator_lazy.py:365-369), incl. a
+    constant matrix; a city with > 1e5 entries is cleaned at upload like sampler.py:41-60 (reference golden)."""
+    from rrnco_b200.sampler import CityOnDevice, gather_submatrix
+    city = synth.make_city(5, length=300)
+    city["duration"][:40, :40] = 3.25  # instances drawn from here have a zero range
+    dev_city = CityOnDevice(city, dev)
+    rng = np.random.RandomState(3)
+    idx = np.array([rng.choice(300, 31, replace=False) for _ in range(64)])
+    idx[7] = np.arange(31)  # constant sub-matrix
+    got, mn, mx = gather_submatrix(dev_city.duration_f32, torch.from_numpy(idx), normalize=2)
+    raw = torch.from_numpy(city["duration"][idx[:, :, None], idx[:, None, :]].astype(np.float32))
+    lo, hi = raw.amin(dim=(1, 2), keepdim=True), raw.amax(dim=(1, 2), keepdim=True)
+    want = (raw - lo) / torch.where(hi - lo == 0, torch.ones_like(hi), hi - lo)
+    assert torch.equal(got.cpu(), want) and (got[7] == 0).all()
+    assert torch.equal(mn.cpu(), lo.reshape(-1)) and torch.equal(mx.cpu(), hi.reshape(-1))
+    z = np.load(os.path.join(GOLDEN, "sampler_outliers.npz"))
+    bad_city = {k[5:]: z[k] for k in z.files if k.startswith("city.")}
+    np.random.seed(99)
+    s = rb.Real_World_Sampler(with_duration=True).sample(bad_city, 4, 9)
+    assert torch.equal(s["distance_matrix"].cpu(), torch.from_numpy(z["distance_matrix"].astype(np.float32)))
+    assert torch.equal(s["duration_matrix"].cpu(), torch.from_numpy(z["duration_matrix"].astype(np.float32)))
+    assert torch.equal(s["points"].cpu(), torch.from_numpy(z["points"].astype(np.float32)))
+
+
+@pytest.mark.parametrize("name", ["rcvrp", "rcvrptw", "atsp"])
+def test_on_device_generator_feeds_the_rollout(rb, name):
+    """Lazy*Generator on the device (10 synthetic cities -> gather -> laws) -> env.reset -> fused rollout: the instances
+    obey the reference's laws and every tour is feasible; the generator's own arithmetic is pinned bit-exactly to the
+    reference in tests/test_generator.py."""
+    n, B = 50, 200
+    cities = [synth.make_city(c, length=400) for c in range(12)]
+    cls = {"rcvrp": rb.LazyRCVRPGenerator, "rcvrptw": rb.LazyRMTVRPGenerator, "atsp": rb.LazyATSPGenerator}[name]
+    gen = cls(num_loc=n, cities=cities, device=dev, seed=11, chunk_size=100)
+    td = gen(B)
+    assert td.batch_size[0] == B and td["distance_matrix"].shape == (B, n + (name != "atsp"), n + (name != "atsp"))
+    if name == "rcvrp":
+        d = td["demand"] * 40.0  # CAPACITIES[50]
+        assert (d >= 1).all() and (d < 10).all()
+    if name == "rcvrptw":
+        assert td["duration_matrix"].amin() == 0 and td["duration_matrix"].amax() == 1
+        assert (td["time_windows"][:, 0, 1] == 4.6).all() and not td["open_route"].any()
+        d = td["demand_linehaul"] * 40  # get_vehicle_capacity(50) = 40
+        assert torch.equal(d.round(), d.round().clamp(1, 9)) and (td["demand_backhaul"] == 0).all()
+    gen2 = cls(num_loc=n, cities=cities, device=dev, seed=11, chunk_size=100)
+    assert torch.equal(gen2(B)["distance_matrix"], td["distance_matrix"])  # seeded: reproducible
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    tdr = env.reset(td)
+    S = env.get_num_starts(tdr)
+    N = n if name == "atsp" else n + 1
+    row, col = synth.random_embeddings(B, N, seed=1)
+    pol = make_policy(rb, name, omodel.init_decoder_params(name, seed=2), row.to(dev), col.to(dev))
+    out = pol(tdr, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    srt = out["actions"].sort(1)[0]
+    if name == "atsp":
+        assert (srt == torch.arange(n, device=dev)).all()
+    else:
+        assert (srt[:, -n:] == torch.arange(1, n + 1, device=dev)).all() and (srt[:, :-n] == 0).all()
+    if name == "rcvrp":
+        env.check_solution_validity(rb.batchify(tdr, S), out["actions"])
+
+
+def test_shared_instance_augmentation_equals_materialised(rb):
+    """StateAugmentation(dihedral8, share_instance_data=True) -> reset -> RRNetPolicy.forward gives the same tours and
+    rewards as upstream's materialised batchify x8 (transforms.py:142-154, test.py:188-212)."""
+    n, B, A = 30, 5, 8
+    raw = synth.make_instances("rcvrp", B, n, seed=21)
+    env = rb.get_env("rcvrp", generator_params={"num_loc": n}, check_solution=False)
+    row, col = synth.random_embeddings(A * B, n + 1, seed=22)
+    pol = make_policy(rb, "rcvrp", omodel.init_decoder_params("rcvrp", seed=23), row.to(dev), col.to(dev))
+    outs = []
+    for share in (False, True):
+        aug = rb.StateAugmentation(num_augment=A, augment_fn="dihedral8", no_aug_coords=False, share_instance_data=share)
+        td = env.reset(aug(lite(rb, raw)))
+        assert td.batch_size[0] == A * B and td["distance_matrix"].shape[0] == (B if share else A * B)
+        S = 31
+        out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+        outs.append((out["actions"].cpu(), out["reward"].cpu(), td["locs"].cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+# ----------------------------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties
 # ----------------------------------------------------------------------------------------------------
 def test_full_size_rcvrp_rollout_properties(rb):
