@@ -10,10 +10,17 @@ Instances are independent, so each rank owns its own 1024 instances (weak scalin
 the only collective is one all-gather of the best costs per step.
 
 Printed JSON line (rank 0): see the contract in the task statement; extra keys
-  roofline      dominant kernel (rollout_kernel) vs the measured HBM peak, algorithmic bytes per SURVEY.md 8(d)
+  roofline      dominant kernel (rollout_lean_kernel): bound "tensor" -- algorithmic FLOP/s (373 kFLOP per
+                rollout-step x the rollout-steps the tiles actually ran) against the measured bf16 peak, the issued-MMA
+                figure (three-term split, padded rows / keys) beside it, and the HBM-algorithmic figure of the north star
+                (3.2 KB per rollout-step) as `hbm_algorithmic`; `traffic` = measured DRAM bytes of this build (ncu)
   cpu_baseline  the CPU oracle (= line-faithful restatement of the reference's eager rollout) on this box's cores
   e2e           same metric through RRNetPolicy.forward with HOST (pinned) inputs, H2D/D2H inside the timing
+  configs       one short measured line per other BASELINE config: C1 ATSP n=100 batch 32 x8 aug, C3 RCVRPTW n=100
+                sampling batch 1024, C4 ATSP n=1000 batch 64, C5 RCVRP training rollouts (global batch 4096 sharded over
+                the ranks = strong scaling, instances generated on the device from 1000-node city matrices)
 `--impl reference` times the reference's own CPU path (oracle port; rl4co cannot be installed offline).
+`--workload c5` makes config C5 the headline line (strong scaling of the fixed global batch).
 """
 from __future__ import annotations
 
@@ -37,6 +44,38 @@ BYTES_PER_ROLLOUT_STEP = 737 + 404 + 512 + 12 + 1536   # env ste
 FLOPS_PER_ROLLOUT_STEP = 373_000
 
 
+def algorithmic_per_rollout_step(env_name, N, S):
+    """(bytes, flops) per rollout-step, SURVEY.md 8(d): env-step bytes + bias row(s) + context gather + 12 B out +
+    K/V/Lk amortised over the S starts that share them; context proj + QK + PV + FFN + logits."""
+    E = 128
+    env_b = {"atsp": 2 * N + 50, "rcvrp": 7 * N + 30, "rcvrptw": 39 * N + 100}[env_name]
+    bias_b = (8 if env_name == "rcvrptw" else 4) * N
+    ctx_b = (8 if env_name == "atsp" else 4) * E
+    k = {"atsp": E, "rcvrp": 1, "rcvrptw": 4}[env_name]
+    flops = 2 * (E + k) * E + 3 * 2 * N * E + 2 * 2 * E * 4 * E
+    return env_b + bias_b + ctx_b + 12 + 12 * N * E / S, flops
+
+
+def issued_mma_flops_per_tile_step(N, passes=3):
+    """Tensor-pipe FLOPs one 128-row tile issues per decode step in the fused kernel: operand terms of the fp16 split x
+    padded shapes (128 rows, keys rounded up to 16): QK 8 heads, PV 8 heads x R16/16 K steps (N=16), FFN 64 K steps of
+    128x128x16, logits 8 K steps."""
+    R16 = (N + 15) // 16 * 16
+    mma = lambda n: 2 * 128 * n * 16
+    return passes * (8 * mma(R16) + 8 * (R16 // 16) * mma(16) + 64 * mma(128) + 8 * mma(R16))
+
+
+def profile_stamp():
+    """Measured DRAM bytes per launch from the ncu captures of THIS build (profiles/r2_traffic.json, stamped with the
+    digest of the CUDA sources): a number taken from another build is not reported."""
+    try:
+        from rrnco_b200.build import build_digest
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        return d if d.get("build_digest") == build_digest() else {}
+    except Exception:
+        return {}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -47,6 +86,9 @@ def parse():
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3], help="3 = three-term fp16-split contractions, fp32-faithful (headline); 1 = single fp16 pass")
     ap.add_argument("--cpu-sample", type=int, default=16, help="instances in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (C1, C3, C4, C5)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="headline workload: BASELINE config[1] (default) or config[4]")
+    ap.add_argument("--c5-global-batch", type=int, default=4096)
     return ap.parse_args()
 
 
@@ -67,7 +109,8 @@ def make_city(city_id=0, length=1000):
     eu = np.linalg.norm(pts[:, None, :] - pts[None, :, :], axis=-1)
     dist = eu * (1.2 + 0.4 * rng.uniform(size=(length, length)))
     np.fill_diagonal(dist, 0.0)
-    return {"points": pts, "distance": dist}
+    speed = rng.uniform(20.0, 50.0, size=(length, length))  # km/h
+    return {"points": pts, "distance": dist, "duration": dist / speed * 60.0}
 
 
 def host_instances(batch, seed):
@@ -261,6 +304,10 @@ def run_ours(args, rank, world, local_rank):
     enc = HostEncoder()
     policy = rb.RRNetPolicy(encoder=enc, decoder=decoder, env_name="rcvrp").to(dev)
 
+    # StateAugmentation(dihedral8) of test.py:28,188 with the [N,N] matrices / demand rows left un-replicated (the kernels
+    # read row r % data_rows): no 8-fold device copy of the instance data
+    augment = rb.StateAugmentation(num_augment=N_AUG, augment_fn="dihedral8", no_aug_coords=False, share_instance_data=True)
+
     # two alternating batches so that consecutive steps never see the same inputs (and > L2: 1.7 GB of cache each)
     n_sets = 2
     host_sets, dev_sets = [], []
@@ -269,8 +316,7 @@ def run_ours(args, rank, world, local_rank):
         row, col = stand_in_embeddings(Bp, seed=200 * (rank + 1) + i)
         raw = {k: v.pin_memory() for k, v in raw.items()}
         host_sets.append((raw, row.pin_memory(), col.pin_memory()))
-        td = env.reset(rb.TensorDictLite({k: v.to(dev) for k, v in raw.items()}, batch_size=[B]))
-        td_aug = rb.batchify(td, N_AUG)
+        td_aug = env.reset(augment(rb.TensorDictLite({k: v.to(dev) for k, v in raw.items()}, batch_size=[B])))
         cache = decoder._precompute_cache((row.to(dev), col.to(dev)))
         dev_sets.append((td_aug, cache))
     torch.cuda.synchronize()
@@ -299,8 +345,7 @@ def run_ours(args, rank, world, local_rank):
         ticket = tickets.pop(i)
         d = prefetch.acquire(ticket)
         enc.row, enc.col = d["__row_emb"], d["__col_emb"]
-        td = env.reset(rb.TensorDictLite({k: v for k, v in d.items() if not k.startswith("__")}, batch_size=[B]))
-        td_aug = rb.batchify(td, N_AUG)                              # StateAugmentation (transforms.py:143)
+        td_aug = env.reset(augment(rb.TensorDictLite({k: v for k, v in d.items() if not k.startswith("__")}, batch_size=[B])))
         out = policy(td_aug, env, phase="val", decode_type="multistart_greedy", num_starts=N_START)
         best = rb.unbatchify(out["reward"], (N_AUG, N_START)).amax(-1).amax(-1)
         prefetch.release(ticket)
@@ -347,6 +392,35 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item() / steps, last
 
+    if args.workload == "c5":
+        # BASELINE config[4] as the headline: fixed GLOBAL batch sharded over the ranks (strong scaling)
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        launches0 = _lib.kernel_count
+        entry = measure_configs(args, rb, dev, rank, world, dist_on, timed, only=("C5",), steps=args.steps)["C5"]
+        launches = (_lib.kernel_count - launches0) // (args.steps + 3) * args.steps
+        clocks = sampler.stop() if sampler else None
+        if rank == 0:
+            hbm_peak, tf_peak, peak_src = peaks()
+            r = entry["roofline"]
+            line = {"metric": "RCVRP n100 POMO training-rollout instances/s (global batch %d)" % args.c5_global_batch,
+                    "value": entry["value"], "unit": "instances/s", "n_gpus": world, "steps": args.steps, "warmup": 3,
+                    "ms_per_step": entry["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "f32 (fp32-faithful: three-term fp16-split tcgen05 contractions, fp32 accumulate)",
+                    "data": "synthetic (8 city-like asymmetric 1000-node matrices in HBM, instances sub-sampled on the device; "
+                            "random-init decoder seed 1234; encoder output = stand-in embeddings)",
+                    "config": {"workload": entry["workload"], "global_batch": args.c5_global_batch,
+                               "instances_per_gpu": entry["instances_per_gpu"], "num_starts": entry["num_starts"],
+                               "decode": entry["decode"], "l2_policy": "a fresh batch is generated every step (key cache 4 x 212 MB per 4096 instances >> L2)"},
+                    "clocks": clocks, "gpu_launches": int(launches), "e2e": entry["e2e"],
+                    "roofline": {"bound": "tensor", "achieved": r["tensor_algorithmic"]["achieved"], "peak": tf_peak,
+                                 "unit": "TFLOP/s", "frac": r["tensor_algorithmic"]["frac"], "traffic": None,
+                                 "peak_source": peak_src, "hbm_algorithmic": r["hbm_algorithmic"]},
+                    "cpu_baseline": entry.get("cpu_baseline")}
+            print(json.dumps(line), flush=True)
+        if dist_on:
+            dist.destroy_process_group()
+        return
+
     # ---- value: inputs resident in HBM -------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.kernel_count
@@ -354,6 +428,7 @@ def run_ours(args, rank, world, local_rank):
     launches = (_lib.kernel_count - launches0) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop() if sampler else None
     T = int(out["actions"].shape[1])
+    tile_steps = out["tile_steps"].clone()
     value = world * B / (ms_step * 1e-3)
 
     # ---- dominant kernel alone (rollout + finalize), CUDA events on the launching stream -------------
@@ -371,7 +446,7 @@ def run_ours(args, rank, world, local_rank):
         R_probe = Bp * N_START
         N = N_LOC + 1
         g = torch.Generator(device=dev).manual_seed(0)
-        demand = rb.batchify(td_aug["demand"], N_START).contiguous()           # [R, N-1] as upstream's batchify
+        demand = rb.batchify(rb.batchify(td_aug["demand"], N_AUG), N_START).contiguous()  # [R, N-1] as upstream's batchify
         cap = torch.ones(R_probe, device=dev)
         used = torch.rand(R_probe, device=dev, generator=g) * 0.5
         visited = (torch.rand(R_probe, N, device=dev, generator=g) < 0.3).to(torch.uint8)
@@ -484,11 +559,17 @@ def run_ours(args, rank, world, local_rank):
         idx = torch.from_numpy(np.array([rng.choice(1000, N_LOC + 1, replace=False) for _ in range(4096)])).to(dev)
         ms = time_launch(lambda: gather_submatrix(city.distance_f32, idx, normalize=True), reps=20)
         ms64 = time_launch(lambda: gather_submatrix(city.distance, idx, normalize=True), reps=20)
-        nbytes = 4096 * 12 * (N_LOC + 1) ** 2  # 8 B fp64 gathered + 4 B fp32 written per element
-        return {"kernel": "rrnco::gather_submatrix_kernel<float> (+ fused reset normalisation; source = the fp32 copy of "
-                          "the fp64 city matrix that Real_World_Sampler keeps; bytes counted as SURVEY 8(d): 12 n^2)",
-                "instances": 4096, "ms_per_launch": ms, "algorithmic_bytes_per_launch": nbytes,
-                "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_launch_fp64_source": ms64}
+        n2 = 4096 * (N_LOC + 1) ** 2
+        # time and bytes of the SAME variant: fp32 source = 4 B gathered + 4 B written per element; the fp64 source (SURVEY
+        # 8(d)'s 12 n^2) is reported beside it with its own time
+        return {"kernel": "rrnco::gather_submatrix_kernel<float> (+ fused reset normalisation; source = the fp32 copy of the "
+                          "fp64 city matrix that Real_World_Sampler keeps: 8 n^2 B per instance)",
+                "instances": 4096, "ms_per_launch": ms, "algorithmic_bytes_per_launch": 8 * n2,
+                "achieved": 8 * n2 / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                "fp64_source": {"ms_per_launch": ms64, "algorithmic_bytes_per_launch": 12 * n2,
+                                "achieved": 12 * n2 / (ms64 * 1e-3) / 1e9, "unit": "GB/s"},
+                "note": "the city matrix (4 / 8 MB) is L2-resident and n of 1000 columns per row are wanted: bound by L2 "
+                        "sector requests, not HBM (ncu: profiles/r1_ncu_env_kernels_v4.txt)"}
 
     env_probe = env_step_probe() if rank == 0 else None
     gat_probe = gather_probe() if rank == 0 else None
@@ -501,12 +582,23 @@ def run_ours(args, rank, world, local_rank):
     h2d = sum(v.numel() * v.element_size() for v in raw.values()) + 2 * row.numel() * row.element_size()
     d2h = B * 4
 
+    # ---- the other BASELINE configs, one short measured line each ------------------------------------
+    cfg_block = None
+    if not args.no_configs:
+        del dev_sets, host_sets, out, best
+        torch.cuda.empty_cache()
+        cfg_block = measure_configs(args, rb, dev, rank, world, dist_on, timed)
+
     if rank == 0:
         hbm_peak, tf_peak, peak_src = peaks()
-        rollout_steps = Bp * N_START * T
+        stamp = profile_stamp()
+        # rollout-steps the kernel actually ran: every (instance, tile) CTA stops when ITS rollouts are done
+        rollout_steps = int((tile_steps.long() - 1).clamp_min(0).sum().item()) * N_START
+        tile_steps_total = int((tile_steps.long() - 1).clamp_min(0).sum().item())
         alg_bytes = rollout_steps * BYTES_PER_ROLLOUT_STEP
-        achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
-        tflops = rollout_steps * FLOPS_PER_ROLLOUT_STEP / (ms_kernel * 1e-3) / 1e12
+        alg_flops = rollout_steps * FLOPS_PER_ROLLOUT_STEP
+        issued_flops = tile_steps_total * issued_mma_flops_per_tile_step(N_LOC + 1, args.precision)
+        sec = ms_kernel * 1e-3
         line = {
             "metric": "RCVRP n100 POMO rollout instances/s", "value": value, "unit": "instances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -516,8 +608,10 @@ def run_ours(args, rank, world, local_rank):
                     "decoder seed 1234; encoder output = unit-variance stand-in embeddings)",
             "config": {"workload": "RCVRP n=100 POMO multi-start x8 aug greedy rollout, batch 1024 per GPU "
                                    "(BASELINE config[1])",
-                       "instances_per_gpu": B, "n_aug": N_AUG, "num_starts": N_START, "decode_steps": T,
+                       "instances_per_gpu": B, "n_aug": N_AUG, "num_starts": N_START, "decode_steps_max": T,
+                       "decode_steps_mean_per_tile": tile_steps_total / max(1, tile_steps.numel()),
                        "rollouts_per_gpu": Bp * N_START,
+                       "augmentation": "dihedral8 on locs; distance matrices / demands shared by the 8 copies (not replicated)",
                        "l2_policy": "two alternating input sets, 1.7 GB of key cache per set (>> 126 MB L2)"},
             "clocks": clocks,
             "gpu_launches": int(launches),
@@ -525,26 +619,42 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
                     "what": "RRNetPolicy.forward on pinned HOST inputs (instance td + encoder output): H2D "
                             "(every step, on the copy stream, double-buffered: the copy of batch i+1 overlaps the rollout "
-                            "of batch i), env.reset normalisation, x8 augmentation, cache GEMM, fused rollout, best-of "
-                            "reduction, D2H"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch, ncu --set full
-                         # (profiles/r1_ncu_rollout_full_size.csv); only valid for the default 1024-instance batch
-                         "traffic": 3.26e9 if B == 1024 else None, "peak_source": peak_src,
-                         "kernel": "rrnco::rollout_kernel<RCVRP>", "ms_per_launch": ms_kernel,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "tensor": {"achieved_tflops_algorithmic": tflops, "peak_bf16_tflops": tf_peak,
-                                    "frac": tflops / tf_peak,
-                                    "note": "fp32-faithful mode issues 3 fp16 tensor passes (hi*hi, lo*hi, hi*lo) per algorithmic FLOP"}},
+                            "of batch i), x8 augmentation, env.reset normalisation, cache GEMM, fused rollout, best-of "
+                            "reduction, D2H of the [B] best costs.  The ENCODER is outside both arms (it stays the "
+                            "reference's PyTorch module; its output is the host input here), and policy() returns "
+                            "actions [R,T] / reward [R] on the device as upstream does."},
+            "roofline": {"bound": "tensor", "achieved": alg_flops / sec / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": alg_flops / sec / 1e12 / tf_peak,
+                         "traffic": stamp.get("rollout_c2_dram_bytes") if B == 1024 else None,
+                         "traffic_source": stamp.get("rollout_c2_source") if B == 1024 else None,
+                         "peak_source": peak_src + ", sustained cuBLAS bf16",
+                         "kernel": "rrnco::rollout_lean_kernel<RCVRP, 3>", "ms_per_launch": ms_kernel,
+                         "algorithmic_flops_per_launch": alg_flops, "rollout_steps_per_launch": rollout_steps,
+                         "what": "algorithmic = 373 kFLOP per rollout-step (SURVEY 8(d)) x rollout-steps summed over the tiles "
+                                 "(each CTA stops at its own tour length)",
+                         "issued": {"tflops": issued_flops / sec / 1e12, "frac": issued_flops / sec / 1e12 / tf_peak,
+                                    "what": "tcgen05 FLOPs actually issued: 3 fp16 operand terms per product (fp32-faithful), "
+                                            "128-row tiles for 101 starts, keys padded 101 -> 112",
+                                    "tensor_pipe_active_pct_ncu": stamp.get("rollout_tensor_pipe_active_pct")},
+                         "hbm_algorithmic": {"achieved": alg_bytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                             "frac": alg_bytes / sec / 1e9 / hbm_peak,
+                                             "algorithmic_bytes_per_launch": alg_bytes,
+                                             "what": "north-star figure: 3.2 KB per rollout-step (SURVEY 8(d)) over the "
+                                                     "measured HBM peak; the fused kernel's real DRAM traffic is `traffic`"}},
         }
-        for probe in (env_probe, gat_probe, atsp_probe, tw_probe):
+        for probe, key in ((env_probe, "rcvrp_step_dram_bytes"), (gat_probe, "gather_dram_bytes"),
+                           (atsp_probe, "atsp_step_dram_bytes"), (tw_probe, "rcvrptw_step_dram_bytes")):
             probe["peak"] = hbm_peak
             probe["frac"] = probe["achieved"] / hbm_peak
+            probe["dram_bytes_measured"] = stamp.get(key)  # ncu dram__bytes_read + write of this build (None: not captured)
+            if stamp.get(key):
+                probe["dram_frac"] = stamp[key] / (probe["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak
         line["env_step"] = env_probe
         line["env_step_atsp"] = atsp_probe
         line["env_step_rcvrptw"] = tw_probe
         line["gather"] = gat_probe
+        if cfg_block is not None:
+            line["configs"] = cfg_block
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rate, dt, cost, Tc = cpu_rollout_rate(args.cpu_sample, threads)
@@ -554,6 +664,189 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if dist_on:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# the other BASELINE configs (C1, C3, C4, C5): value / e2e / cpu sample / roofline fractions each
+# --------------------------------------------------------------------------------------------------
+CONFIG_SPECS = {
+    "C1": dict(env="atsp", n=100, batch=32, aug=8, starts=100, decode="greedy", scaling="weak", steps=5,
+               what="ATSP n=100 greedy rollout x8 aug, batch 32 (BASELINE config[0]; the reference runs it on the CPU)"),
+    "C3": dict(env="rcvrptw", n=100, batch=1024, aug=1, starts=100, decode="sampling", scaling="weak", steps=5,
+               what="RCVRPTW n=100 with duration matrix and time windows, sampling decode, batch 1024 (BASELINE config[2])"),
+    "C4": dict(env="atsp", n=1000, batch=64, aug=1, starts=100, decode="greedy", scaling="weak", steps=2,
+               what="ATSP n=1000 generalisation rollout, batch 64, 100 starts as test.py:129-130 (BASELINE config[3])"),
+    "C5": dict(env="rcvrp", n=100, batch=None, aug=1, starts=101, decode="sampling", scaling="strong", steps=5,
+               what="RCVRP n=100 REINFORCE training rollouts, GLOBAL batch 4096 x 101 starts sharded over the ranks, instances "
+                    "sub-sampled on the device from synthetic 1000-node city matrices (BASELINE config[4])"),
+}
+
+
+def cpu_config_rate(spec, n_inst, threads, seed=777):
+    """CPU arm of one config: the oracle port on a bounded sample (host cores of this box)."""
+    from oracle import envs as oenvs, model as omodel, synth
+    from oracle.td import batchify
+    torch.set_num_threads(threads)
+    name, n = spec["env"], spec["n"]
+    N = n if name == "atsp" else n + 1
+    t0 = time.perf_counter()
+    raw = synth.make_instances(name, n_inst, n, seed=seed, city=synth.make_city(0, length=max(1000, N)))  # incl. the NumPy gather
+    t_gen = time.perf_counter() - t0
+    env = oenvs.make_env(name, n, check_solution=False)
+    p = omodel.init_decoder_params(name, seed=1234)
+    row, col = synth.random_embeddings(n_inst * spec["aug"], N, seed=seed)
+    with torch.inference_mode():
+        t0 = time.perf_counter()
+        td = env.reset(raw)
+        if spec["aug"] > 1:
+            td = batchify(td, spec["aug"])
+        out = omodel.policy_forward(p, env, td, row, col, decode_type="multistart_" + spec["decode"], num_starts=spec["starts"],
+                                    generator=torch.Generator().manual_seed(seed))
+        dt = time.perf_counter() - t0
+    if spec["scaling"] == "strong":
+        dt += t_gen  # C5 generates its instances inside the step
+    return n_inst / dt, dt, int(out["actions"].shape[1])
+
+
+def measure_configs(args, rb, dev, rank, world, dist_on, timed, only=None, steps=None):
+    from rrnco_b200.sharding import gather_costs
+    hbm_peak, tf_peak, _ = peaks()
+    block = {}
+    # 8 synthetic cities: every per-rank batch (32 ... 4096) splits evenly over them (upstream's `target // n_cities`
+    # integer division would otherwise hand back slightly fewer instances than asked, generator_lazy.py:203)
+    cities = [rb.CityOnDevice(make_city(c), dev) for c in range(8)]
+    cpu_samples = {"C1": 4, "C3": 16, "C4": 1, "C5": 16}
+    for cname, spec in CONFIG_SPECS.items():
+        if only is not None and cname not in only:
+            continue
+        if steps is not None:
+            spec = dict(spec, steps=steps)
+        name, n, A, S = spec["env"], spec["n"], spec["aug"], spec["starts"]
+        N = n if name == "atsp" else n + 1
+        Bc = spec["batch"] if spec["batch"] is not None else max(1, args.c5_global_batch // world)
+        env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False, device=dev)
+        torch.manual_seed(1234)
+        decoder = rb.RRNetDecoder(env_name=name).to(dev)
+        gen_cls = {"atsp": rb.LazyATSPGenerator, "rcvrp": rb.LazyRCVRPGenerator, "rcvrptw": rb.LazyRMTVRPGenerator}[name]
+        big = [rb.CityOnDevice(make_city(20 + c, length=1200), dev) for c in range(2)] if n >= 1000 else cities
+        gen = gen_cls(num_loc=n, cities=big, device=dev, seed=1000 * (rank + 1) + 7, chunk_size=max(1000, Bc))
+        augment = rb.StateAugmentation(num_augment=A, augment_fn="dihedral8", no_aug_coords=False, share_instance_data=True) if A > 1 else None
+        kind = spec["decode"]
+        g = torch.Generator(device=dev).manual_seed(5 + rank)
+        embeds = [(torch.randn(Bc * A, N, 128, device=dev, generator=g), torch.randn(Bc * A, N, 128, device=dev, generator=g))
+                  for _ in range(2)]
+
+        def make_td():
+            td = gen(Bc)
+            assert td.batch_size[0] == Bc, (td.batch_size, Bc)
+            return env.reset(augment(td) if augment is not None else td)
+
+        rollout = rb.fused_rollout if N <= 112 else rb.stepwise_rollout
+        state = {}
+
+        if spec["scaling"] == "strong":
+            # C5: generate batch i+1 (index sampling + gather + laws + reset) on a side stream under the rollout of batch i
+            side = torch.cuda.Stream(device=dev)
+            pending = {}
+
+            def prefetch(i):
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    td = make_td()
+                    cache = decoder._precompute_cache(embeds[i % 2])
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                pending[i] = (td, cache, ev)
+
+            def step(i):
+                if i not in pending:
+                    prefetch(i)
+                prefetch(i + 1)
+                td, cache, ev = pending.pop(i)
+                torch.cuda.current_stream(dev).wait_event(ev)
+                out = rollout(decoder, cache, env, td, S, True, kind, seed=1234 + i, check=False)
+                best = out["reward"].view(S, Bc).amax(0)
+                if dist_on:
+                    gather_costs(best, world * Bc)
+                state["out"] = out
+                return best.cpu()  # D2H of the costs: the step's host-visible result
+            ms_val, _ = timed(step, spec["steps"], 3)
+            ms_e2e, h2d, d2h = ms_val, 0, Bc * 4
+            e2e_what = ("same pipeline (this config has no host inputs: instances are generated on the device from the "
+                        "HBM-resident city matrices, the encoder output is a resident stand-in); D2H of the [B] best costs")
+            n_units = Bc * world if dist_on else Bc
+        else:
+            sets = [(make_td(), decoder._precompute_cache(embeds[i])) for i in range(2)]
+            torch.cuda.synchronize()
+
+            def step(i):
+                td, cache = sets[i % 2]
+                out = rollout(decoder, cache, env, td, S, True, kind, seed=1234 + i, check=False)
+                best = rb.unbatchify(out["reward"], (A, S)).amax(-1).amax(-1) if A > 1 else out["reward"].view(S, Bc).amax(0)
+                if dist_on:
+                    gather_costs(best, world * Bc)
+                state["out"] = out
+                return out
+            ms_val, _ = timed(step, spec["steps"], 3)
+            # e2e through the public API: pinned host instance td + encoder output -> H2D -> (aug) -> reset -> policy -> D2H
+            host_td = {k: v.cpu().pin_memory() for k, v in gen(Bc).items()}
+            host_emb = (embeds[0][0].cpu().pin_memory(), embeds[0][1].cpu().pin_memory())
+
+            class Enc(torch.nn.Module):
+                def forward(self, td, phase=None):
+                    return host_emb[0].to(dev, non_blocking=True), host_emb[1].to(dev, non_blocking=True)
+            policy = rb.RRNetPolicy(encoder=Enc(), decoder=decoder, env_name=name).to(dev)
+
+            def step_e2e_cfg(i):
+                td = rb.TensorDictLite({k: v.to(dev, non_blocking=True) for k, v in host_td.items()}, batch_size=[Bc])
+                td = env.reset(augment(td) if augment is not None else td)
+                with torch.no_grad():
+                    out = policy(td, env, phase="train" if kind == "sampling" else "val", decode_type="multistart_" + kind,
+                                 num_starts=S, seed=99 + i)
+                best = rb.unbatchify(out["reward"], (A, S)).amax(-1).amax(-1) if A > 1 else out["reward"].view(S, Bc).amax(0)
+                return best.cpu()
+            ms_e2e, _ = timed(step_e2e_cfg, spec["steps"], 2)
+            h2d = sum(v.numel() * v.element_size() for v in host_td.values()) + 2 * host_emb[0].numel() * 4
+            d2h = Bc * 4
+            e2e_what = "RRNetPolicy.forward on pinned HOST inputs (instance td + encoder output), H2D and D2H of the [B] costs inside"
+            n_units = Bc * world
+        out = state["out"]
+        if "tile_steps" in out:
+            ts = (out["tile_steps"].long() - 1).clamp_min(0)
+            n_tiles = (S + 127) // 128
+            rows = torch.tensor([min(128, S - t * 128) for t in range(n_tiles)], device=ts.device).repeat(ts.numel() // n_tiles)
+            rollout_steps = int((ts * rows).sum().item())
+        else:
+            rollout_steps = Bc * A * S * (out["actions"].shape[1] - 1)
+        b_alg, f_alg = algorithmic_per_rollout_step(name, N, S)
+        sec = ms_val * 1e-3
+        entry = {"workload": spec["what"], "value": n_units / sec, "unit": "instances/s", "scaling": spec["scaling"],
+                 "ms_per_step": ms_val, "steps": spec["steps"], "instances_per_gpu": Bc, "n_aug": A, "num_starts": S,
+                 "decode": kind, "decode_steps_max": int(out["actions"].shape[1]),
+                 "path": "fused persistent kernel (rrnco_rollout, lean engine)" if N <= 112 else
+                         "per-step pipeline (rrnco_decoder_logits_large + rrnco_select_action + env step)",
+                 "e2e": {"value": n_units / (ms_e2e * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": int(h2d),
+                         "d2h_bytes_per_step": int(d2h), "what": e2e_what},
+                 "roofline": {"hbm_algorithmic": {"achieved": rollout_steps * b_alg / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                                  "frac": rollout_steps * b_alg / sec / 1e9 / hbm_peak,
+                                                  "bytes_per_rollout_step": b_alg},
+                              "tensor_algorithmic": {"achieved": rollout_steps * f_alg / sec / 1e12, "peak": tf_peak,
+                                                     "unit": "TFLOP/s", "frac": rollout_steps * f_alg / sec / 1e12 / tf_peak,
+                                                     "flops_per_rollout_step": f_alg},
+                              "rollout_steps_per_step": rollout_steps}}
+        if rank == 0 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            k = cpu_samples[cname]
+            rate, dt, Tc = cpu_config_rate(spec, k, threads)
+            entry["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": threads, "kind": "port",
+                                     "sample": f"{k} instance(s) x {A} aug x {S} starts, {Tc} decode steps, {dt:.1f} s on {threads} threads"}
+        block[cname] = entry
+        del gen, decoder, embeds, out
+        state.clear()
+        if spec["scaling"] != "strong":
+            del sets
+        torch.cuda.empty_cache()
+    return block
 
 
 def main():

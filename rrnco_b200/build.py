@@ -67,5 +67,11 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_digest() -> str:
+    """Digest of the CUDA sources + flags the library on disk was built from (profiles stamp their numbers with it)."""
+    stamp = os.path.join(HERE, "build", "stamp")
+    return open(stamp).read().strip() if os.path.exists(stamp) else ""
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))

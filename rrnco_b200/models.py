@@ -381,6 +381,10 @@ def fused_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_s
     if check:
         _lib.raise_device_status(status)
     out = {"actions": acts[:, :T], "log_likelihood": ll}
+    # decode steps each (instance, 128-start tile) CTA actually ran (it stops when ITS rollouts are done): what the
+    # roofline accounting of bench.py counts, instead of the global maximum T
+    n_tiles = n_inst * ((S + 127) // 128)
+    out["tile_steps"] = ws[2 * R * 8: 2 * R * 8 + 4 * n_tiles].view(torch.int32)
     if per_step_logprobs:
         out["logprobs"] = logp[:, :T]
     if calc_reward:
