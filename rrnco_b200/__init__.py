@@ -19,6 +19,7 @@ from .sampler import CityOnDevice, Real_World_Sampler, remove_outlier_points  # 
 from .generator import LazyATSPGenerator, LazyRCVRPGenerator, LazyRMTVRPGenerator  # noqa: F401
 from .transforms import StateAugmentation, dihedral_8_augmentation  # noqa: F401
 from .tdlite import TensorDictLite, batchify, unbatchify  # noqa: F401
+from .torch_ops import use_torch_ops  # noqa: F401
 from .training import (batched_logprobs, collect_decode_inputs, pomo_shared_baseline_loss,  # noqa: F401
                        replay_log_likelihood)
 

@@ -139,6 +139,13 @@ def call(name, *args):
     check(getattr(lib(), name)(*args))
 
 
+def count_call(name: str):
+    """Launch accounting for calls that do not go through `call` (the torch-op binding)."""
+    global launch_count, kernel_count
+    launch_count += 1
+    kernel_count += _KERNELS_PER_CALL.get(name, 1)
+
+
 def set_precision(passes: int):
     check(lib().rrnco_set_precision(passes))
 

@@ -67,6 +67,34 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+TORCH_LIB = os.path.join(HERE, "librrnco_b200_torch.so")
+
+
+def build_torch_ops(force: bool = False) -> str:
+    """g++ csrc/torch_ops.cpp -> rrnco_b200/librrnco_b200_torch.so: the TORCH_LIBRARY registration of the C-ABI entry points
+    (no device code: it links against librrnco_b200.so, which is found next to it through $ORIGIN)."""
+    import torch
+    from torch.utils import cpp_extension as ce
+    build_library()
+    src = os.path.join(CSRC, "torch_ops.cpp")
+    stamp = os.path.join(HERE, "build", "stamp_torch")
+    digest = _digest([src, os.path.join(os.path.dirname(HERE), "include", "rrnco_b200.h")]) + torch.__version__
+    if not force and os.path.exists(TORCH_LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return TORCH_LIB
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           *[f"-I{p}" for p in ce.include_paths()], f"-I{cuda_home}/include", src, "-o", TORCH_LIB,
+           f"-L{tlib}", f"-L{HERE}", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-l:librrnco_b200.so",
+           f"-L{cuda_home}/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"torch_ops build failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return TORCH_LIB
+
+
 def build_digest() -> str:
     """Digest of the CUDA sources + flags the library on disk was built from (profiles stamp their numbers with it)."""
     stamp = os.path.join(HERE, "build", "stamp")
@@ -75,3 +103,4 @@ def build_digest() -> str:
 
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_torch_ops(force="--force" in sys.argv))

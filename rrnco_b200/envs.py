@@ -31,9 +31,18 @@ def _u8(t):
     return t.view(torch.uint8) if t.dtype == torch.bool else t.to(torch.uint8)
 
 
+def _lib_count(name):
+    from . import _lib
+    _lib.count_call(name)
+
+
 def minmax_normalize(distance):
     """(d - min) / (max - min + 1e-6) per instance -> (normalised fp32, min [B], max [B])."""
     d = _f32(distance)
+    from . import torch_ops
+    if torch_ops.enabled():
+        _lib_count("rrnco_minmax_normalize")
+        return torch_ops.ops().minmax_normalize(d)
     B, N = d.shape[0], d.shape[-1]
     out = torch.empty_like(d)
     mn = torch.empty(B, dtype=torch.float32, device=d.device)
@@ -43,6 +52,11 @@ def minmax_normalize(distance):
 
 
 def tour_reward(actions, distance, prepend_depot, open_route=None, min_d=None, max_d=None):
+    from . import torch_ops
+    if torch_ops.enabled():
+        _lib_count("rrnco_tour_reward")
+        real, norm = torch_ops.ops().tour_reward(actions, distance, bool(prepend_depot), open_route, min_d, max_d)
+        return (real if min_d is not None else None), norm
     actions = actions.contiguous()
     R, T = actions.shape
     dm = _f32(distance)
@@ -124,6 +138,13 @@ class ATSPEnv(_EnvBase):
 
     @staticmethod
     def _step(td):
+        from . import torch_ops
+        if torch_ops.enabled():
+            _lib_count("rrnco_atsp_step")
+            mask_out, first_out, cur_out, done = torch_ops.ops().atsp_step(td["action"], td["i"], td["action_mask"], td["first_node"])
+            td.update({"first_node": first_out, "current_node": cur_out, "i": td["i"] + 1, "action_mask": mask_out,
+                       "reward": torch.zeros_like(done), "done": done})
+            return td
         action = td["action"].contiguous()
         mask_in = td["action_mask"].contiguous()
         R, N = mask_in.shape
@@ -173,6 +194,13 @@ class RCVRPEnv(_EnvBase):
 
     @staticmethod
     def _kernel(td, action):
+        from . import torch_ops
+        if torch_ops.enabled():
+            _lib_count("rrnco_rcvrp_step")
+            cur, used, visited, done, mask = torch_ops.ops().rcvrp_step(
+                action, td["demand"], td["vehicle_capacity"], td["used_capacity"], td["visited"],
+                td["current_node"] if action is None else None)
+            return mask if action is None else (cur, used, visited, done, mask)
         visited_in = td["visited"].contiguous()
         R, N = visited_in.shape
         dev = visited_in.device

@@ -70,6 +70,23 @@ class _Pointer(nn.Module):
         self.ffn = _FFN(embed_dim)
 
 
+def instance_tensors_from_td(env_name: str, td) -> list:
+    """The members of rrnco_instance_data_t as a list of (optional) tensors, in order (torch-op binding)."""
+    f = lambda t: t.to(torch.float32).contiguous()
+    k = td.keys()
+    d = [None] * 12
+    d[0] = f(td["distance_matrix"])
+    if "min_distance" in k:
+        d[10], d[11] = f(td["min_distance"]), f(td["max_distance"])
+    if env_name == "rcvrp":
+        d[2], d[6] = f(td["demand"]), f(td["vehicle_capacity"].reshape(-1))
+    elif env_name == "rcvrptw":
+        d[1], d[2], d[3] = f(td["duration_matrix"]), f(td["demand_linehaul"]), f(td["demand_backhaul"])
+        d[4], d[5], d[6] = f(td["time_windows"]), f(td["service_time"]), f(td["vehicle_capacity"].reshape(-1))
+        d[7], d[8], d[9] = f(td["distance_limit"].reshape(-1)), _u8(td["open_route"].reshape(-1)), f(td["backhaul_class"].reshape(-1))
+    return d
+
+
 def instance_data_from_td(env_name: str, td, keep: list) -> InstanceData:
     """InstanceData over a reset td; rows are indexed by instance (b % data_rows)."""
     def put(t, dtype=torch.float32):
@@ -123,6 +140,17 @@ class RRNetDecoder(nn.Module):
         self._wcache = None
 
     # -- weights handed to the kernels ---------------------------------------------------------------
+    def kernel_weight_tensors(self):
+        """The members of rrnco_decoder_weights_t as tensors, in order (torch-op binding); (alpha, beta) as floats."""
+        E = self.embed_dim
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        lins = self.pointer.ffn.lins
+        wc = self.context_embedding.project_context.weight.detach().float()
+        state_w = f(wc[:, E:].t()) if self.env_name != "atsp" else None
+        placeholder = f(wc @ self.context_embedding.W_placeholder.detach().float()) if self.env_name == "atsp" else None
+        w, _ = self.kernel_weights()
+        return [f(lins[0].weight), f(lins[0].bias), f(lins[1].weight), f(lins[1].bias), state_w, placeholder], w.alpha, w.beta
+
     def kernel_weights(self, temperature: float = 1.0, tanh_clipping: float = 10.0):
         """(DecoderWeights struct, keep-alive list)."""
         E = self.embed_dim
@@ -352,31 +380,41 @@ def fused_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_s
         # select_start_nodes is `arange(S) % generator.num_loc` upstream; the kernel derives it from the instance size
         raise ValueError(f"env.generator.num_loc = {num_loc} does not match the instance size ({N} nodes): the fused "
                          "kernel's start-node rule would differ from env.select_start_nodes")
-    keep = []
-    w, keep_w = decoder.kernel_weights(temperature, tanh_clipping)
-    data = instance_data_from_td(name, td, keep)
     if t_cap is None:
         t_cap = N if name == "atsp" else 2 * N
     forced, forced_T = None, 0
     if kind == "evaluate":
         fa = forced_actions.to(dev).contiguous()
-        if multistart:
-            pass  # the given decisions follow the forced start (policy.py:214-218)
-        forced, forced_T = fa, fa.shape[1]
+        forced, forced_T = fa, fa.shape[1]  # the given decisions follow the forced start (policy.py:214-218)
         t_cap = max(t_cap, forced_T + (1 if multistart else 0))
-    acts = torch.empty((R, t_cap), dtype=torch.int64, device=dev)
-    logp = torch.empty((R, t_cap), dtype=torch.float32, device=dev) if per_step_logprobs else None
-    ll = torch.empty(R, dtype=torch.float32, device=dev)
-    norm = torch.empty(R, dtype=torch.float32, device=dev)
     has_minmax = "min_distance" in td.keys()
-    real = torch.empty(R, dtype=torch.float32, device=dev) if has_minmax else None
-    info = torch.zeros(2, dtype=torch.int32, device=dev)  # [max_steps, status]
     ws_bytes = _lib.lib().rrnco_rollout_workspace_bytes(ENV_ID[name], N, n_inst, S)
     ws = _workspace(dev, ws_bytes)
-    cs = cache.struct()
-    call("rrnco_rollout", ENV_ID[name], N, n_inst, S, int(multistart), DECODE_ID[kind], int(seed) & (2**64 - 1),
-         C.byref(w), C.byref(cs), C.byref(data), ptr(forced), forced_T, t_cap, ptr(acts), ptr(logp), ptr(ll),
-         ptr(norm), ptr(real), ptr(info[0:1]), ptr(info[1:2]), ptr(ws), stream_ptr(dev))
+    seed = int(seed) & (2**63 - 1)
+    from . import torch_ops
+    if torch_ops.enabled():
+        # dispatcher op over the same C entry point (csrc/torch_ops.cpp); outputs come from the caching allocator
+        wt, alpha, beta = decoder.kernel_weight_tensors()
+        acts, logp, ll, norm, real, info, _ = torch_ops.ops().rollout(
+            ENV_ID[name], S, bool(multistart), DECODE_ID[kind], seed, wt, alpha, beta, float(tanh_clipping), float(temperature),
+            [cache.glimpse_key, cache.glimpse_val, cache.logit_key, cache.ctx_node_proj, cache.ctx_node_proj2],
+            instance_tensors_from_td(name, td), forced, t_cap, bool(per_step_logprobs), ws)
+        _lib.count_call("rrnco_rollout")
+        real = real if has_minmax else None
+    else:
+        keep = []
+        w, keep_w = decoder.kernel_weights(temperature, tanh_clipping)
+        data = instance_data_from_td(name, td, keep)
+        acts = torch.empty((R, t_cap), dtype=torch.int64, device=dev)
+        logp = torch.empty((R, t_cap), dtype=torch.float32, device=dev) if per_step_logprobs else None
+        ll = torch.empty(R, dtype=torch.float32, device=dev)
+        norm = torch.empty(R, dtype=torch.float32, device=dev)
+        real = torch.empty(R, dtype=torch.float32, device=dev) if has_minmax else None
+        info = torch.zeros(2, dtype=torch.int32, device=dev)  # [max_steps, status]
+        cs = cache.struct()
+        call("rrnco_rollout", ENV_ID[name], N, n_inst, S, int(multistart), DECODE_ID[kind], seed,
+             C.byref(w), C.byref(cs), C.byref(data), ptr(forced), forced_T, t_cap, ptr(acts), ptr(logp), ptr(ll),
+             ptr(norm), ptr(real), ptr(info[0:1]), ptr(info[1:2]), ptr(ws), stream_ptr(dev))
     T, status = info.tolist()  # the ONE host sync of the rollout (upstream: 3-5 per decode step)
     if check:
         _lib.raise_device_status(status)
@@ -400,6 +438,14 @@ def fused_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_s
 def select_action(logits, mask, kind: str = "greedy", tanh_clipping: float = 10.0, temperature: float = 1.0,
                   seed: int = 0, step: int = 0, forced_action=None, status=None):
     """DecodingStrategy.step (decoding.py:219-298): (action int64 [R], log-prob fp32 [R]) in one kernel."""
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=logits.device)
+    from . import torch_ops
+    if torch_ops.enabled():
+        _lib.count_call("rrnco_select_action")
+        action, logp = torch_ops.ops().select_action(logits, mask, DECODE_ID[kind], float(tanh_clipping), float(temperature),
+                                                     int(seed) & (2**63 - 1), int(step), forced_action, status)
+        return action, logp, status
     logits, mask = logits.contiguous(), mask.contiguous()
     R, N = logits.shape
     action = torch.empty(R, dtype=torch.int64, device=logits.device)
@@ -408,7 +454,7 @@ def select_action(logits, mask, kind: str = "greedy", tanh_clipping: float = 10.
         status = torch.zeros(1, dtype=torch.int32, device=logits.device)
     forced = None if forced_action is None else forced_action.contiguous()
     call("rrnco_select_action", R, N, ptr(logits), ptr(_u8(mask)), DECODE_ID[kind], float(tanh_clipping),
-         float(temperature), int(seed) & (2**64 - 1), int(step), ptr(forced), ptr(action), ptr(logp), ptr(status),
+         float(temperature), int(seed) & (2**63 - 1), int(step), ptr(forced), ptr(action), ptr(logp), ptr(status),
          stream_ptr(logits.device))
     return action, logp, status
 

@@ -71,10 +71,15 @@ def gather_submatrix(matrix: torch.Tensor, idx: torch.Tensor, normalize: bool = 
     `matrix` is the fp64 city matrix or its fp32 copy (CityOnDevice.distance_f32): identical results."""
     if matrix.dtype not in (torch.float64, torch.float32) or not matrix.is_contiguous():
         raise TypeError("gather_submatrix: contiguous float64 / float32 city matrix expected")
+    normalize = int(normalize)
+    from . import torch_ops, _lib
+    if torch_ops.enabled():
+        _lib.count_call("rrnco_gather_submatrix")
+        out, mn, mx = torch_ops.ops().gather_submatrix(matrix, idx, normalize)
+        return (out, mn, mx) if normalize else out
     idx = idx.to(device=matrix.device, dtype=torch.int32).contiguous()
     B, n = idx.shape
-    out = torch.empty((B, n, n), dtype=torch.float32, device=matrix.device)
-    normalize = int(normalize)  # 0 none | 1 env.reset's distance law (eps 1e-6) | 2 generators' duration law (zero-range guard)
+    out = torch.empty((B, n, n), dtype=torch.float32, device=matrix.device)  # 0 none | 1 env.reset's distance law (eps 1e-6) | 2 generators' duration law (zero-range guard)
     mn = mx = None
     if normalize:
         mn = torch.empty(B, dtype=torch.float32, device=matrix.device)

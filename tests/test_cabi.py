@@ -55,6 +55,24 @@ def test_gumbel_uniform_is_in_the_open_interval(lib_path):
     assert np.float32(h.rrnco_u01(0)) == np.float32(2.0 ** -24)
 
 
+def test_torch_library_ops_registered(lib_path):
+    """csrc/torch_ops.cpp: the C-ABI entry points as dispatcher ops `torch.ops.rrnco_b200.*` (TORCH_LIBRARY over the same
+    shared library); loading and schema lookup need no GPU."""
+    from rrnco_b200.build import build_torch_ops
+    from rrnco_b200 import torch_ops
+    assert os.path.exists(build_torch_ops())
+    assert torch_ops.load()
+    ops = torch_ops.ops()
+    for name in ("minmax_normalize", "gather_submatrix", "atsp_step", "rcvrp_step", "tour_reward", "select_action", "rollout"):
+        schema = str(getattr(ops, name).default._schema)
+        assert schema.startswith(f"rrnco_b200::{name}("), schema
+    from rrnco_b200 import _lib
+    assert ops.rollout_workspace_bytes(1, 101, 4, 101) == _lib.lib().rrnco_rollout_workspace_bytes(1, 101, 4, 101)
+    if not torch.cuda.is_available():  # CUDA-only kernels: the dispatcher refuses host tensors, no silent fallback
+        with pytest.raises((NotImplementedError, RuntimeError)):
+            ops.minmax_normalize(torch.rand(2, 4, 4))
+
+
 def test_bad_arguments_rejected_without_gpu(lib_path):
     from rrnco_b200 import _lib
     h = _lib.lib()

@@ -946,6 +946,68 @@ def test_shared_instance_augmentation_equals_materialised(rb):
 
 
 # ----------------------------------------------------------------------------------------------------
+# bindings: TORCH_LIBRARY ops vs ctypes over the same C ABI; real-TensorDict duck typing
+# ----------------------------------------------------------------------------------------------------
+def test_torch_ops_and_ctypes_bindings_agree(rb):
+    """Every hot call goes through `torch.ops.rrnco_b200.*` by default; the ctypes fallback must give bitwise the same."""
+    from rrnco_b200 import torch_ops
+    assert torch_ops.enabled(), "librrnco_b200_torch.so missing: the torch-op binding is the default"
+    res = {}
+    for binding in (True, False):
+        assert rb.use_torch_ops(binding) == binding
+        for name, n, B in (("rcvrp", 20, 3), ("atsp", 12, 2), ("rcvrptw", 15, 2)):
+            raw = synth.make_instances(name, B, n, seed=3)
+            env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+            td = env.reset(lite(rb, raw))
+            S = env.get_num_starts(td)
+            N = td["action_mask"].shape[-1]
+            row, col = synth.random_embeddings(B, N, seed=4)
+            pol = make_policy(rb, name, omodel.init_decoder_params(name, seed=5), row.to(dev), col.to(dev))
+            out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+            with torch.no_grad():
+                smp = pol(td, env, phase="train", decode_type="multistart_sampling", num_starts=S, seed=7)
+            # per-step API: one env.step + get_reward on the batchified td
+            tdb = rb.batchify(td, S)
+            tdb.set("action", env.select_start_nodes(td, S))
+            tdb = env.step(tdb)["next"]
+            real, norm = env.get_reward(rb.batchify(td, S), out["actions"])
+            res.setdefault(name, []).append([out["actions"], out["reward"], out["log_likelihood"], smp["actions"],
+                                             smp["log_likelihood"], tdb["action_mask"], tdb["current_node"], real, norm])
+        city = rb.CityOnDevice(synth.make_city(2, length=120), dev)
+        idx = torch.from_numpy(np.array([np.random.RandomState(1).choice(120, 21, replace=False) for _ in range(9)]))
+        from rrnco_b200.sampler import gather_submatrix
+        res.setdefault("gather", []).append(list(gather_submatrix(city.distance_f32, idx, normalize=1)) +
+                                            [gather_submatrix(city.distance, idx)])
+    rb.use_torch_ops(True)
+    for name, (a, b) in res.items():
+        for x, y in zip(a, b):
+            assert x.shape == y.shape and torch.equal(x, y), name
+
+
+def test_reference_tensordict_duck_typing(rb):
+    """The envs / policy accept a TensorDict-like container that is NOT rrnco_b200's own (here the stand-in that the golden
+    generator runs the unmodified reference on): td[...], td.set, td.update, td.keys, td.batch_size, td.device."""
+    import sys
+    shims = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "shims")
+    sys.path.insert(0, shims)
+    try:
+        from tensordict import TensorDict
+    finally:
+        sys.path.remove(shims)
+    name, n, B = "rcvrp", 20, 3
+    raw = synth.make_instances(name, B, n, seed=8)
+    td_ref = TensorDict({k: v.to(dev) for k, v in raw.items()}, batch_size=[B])
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=True)
+    td = env.reset(td_ref)
+    assert type(td).__name__ == "TensorDict" and td["action_mask"].shape == (B, n + 1)
+    row, col = synth.random_embeddings(B, n + 1, seed=9)
+    pol = make_policy(rb, name, omodel.init_decoder_params(name, seed=10), row.to(dev), col.to(dev))
+    out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=n + 1)
+    want = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=n + 1)
+    assert torch.equal(out["actions"], want["actions"]) and torch.equal(out["reward"], want["reward"])
+
+
+# ----------------------------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties
 # ----------------------------------------------------------------------------------------------------
 def test_full_size_rcvrp_rollout_properties(rb):
