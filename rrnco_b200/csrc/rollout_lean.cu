@@ -6,7 +6,7 @@
 // tensor pipe / the weight stream with the CUDA cores idle.  With two independent tiles resident on an SM the hardware
 // interleaves them: one tile's FFN runs under the other tile's softmax.  That needs half the footprint per tile:
 //   * <= 113 KB of shared memory: the 64 KB activation tiles (Q -> glimpse, fp16 hi | lo, A operands of the SS MMAs) plus a
-//     4 x 8 KB ring through which EVERY B operand streams by TMA (cp.async.bulk) in the fixed order the tensor pipe
+//     4-5 x 8 KB ring through which EVERY B operand streams by TMA (cp.async.bulk) in the fixed order the tensor pipe
 //     consumes it: per step 16 K_h / V_h head tiles, 64 FFN weight K-step slices, 8 logit-key K-step slices, all
 //     <= 8 KB, all pre-packed fp16 hi | lo core-matrix tiles that stay L2-resident.  Nothing is resident but the
 //     activations; the fp32 bias tile alpha.D[cur,:] (+ beta.Dur[cur,:]) borrows the activation region while it is dead
@@ -28,7 +28,6 @@ namespace rrnco {
 
 constexpr int kLThreads = 320;            // warps 0-7 compute, 8 TMA producer, 9 MMA issue
 constexpr int kLCompute = 256;
-constexpr int kLStages = 4;
 constexpr uint32_t kLStageBytes = 8192;
 constexpr int kLBiasLd = 116;             // fp32 row stride of the bias tile (conflict-free float4 rows, 16-byte aligned)
 constexpr int kLBiasBytes = kRows * kLBiasLd * 4;  // 59 392: the select exchange arrays live behind it in the A region
@@ -53,10 +52,13 @@ __device__ long long g_lean_cycles[32];
 
 template <int kEnv>
 struct LeanSmem {
+  // ring depth: as many 8 KB stages as fit beside the activation tiles in 113 KB (the time-window env needs 7 per-node
+  // arrays and 4 state words per rollout: one stage less)
+  static constexpr int kStages = kEnv == RRNCO_ENV_RCVRPTW ? 4 : 5;
   static constexpr int kNodeArrays = kEnv == RRNCO_ENV_RCVRPTW ? 7 : 1;
   static constexpr int kStateArrays = kEnv == RRNCO_ENV_RCVRPTW ? 4 : 1;
   unsigned char A[kRows * kE * 4];         // Q -> glimpse (fp16 hi | lo tiles) | fp32 bias tile during logits + select
-  unsigned char ring[kLStages][kLStageBytes];
+  unsigned char ring[kStages][kLStageBytes];
   float wstate[kStateArrays][kE];          // context state weights; ATSP: row 0 = placeholder query
   float node[kNodeArrays][kRows];          // dem | demb tw0 tw1 svc dj0 uj0 (rcvrptw)
   float f[kStateArrays][kRows];            // rcvrp: used | rcvrptw: time, route, used_l, used_b
@@ -65,7 +67,7 @@ struct LeanSmem {
   unsigned char cur[kRows], first[kRows], active[kRows], done[kRows];
   uint32_t lhmask[4];
   uint32_t kmax2[kH];                      // max over the keys of |K_h row|^2 (fp32 bits; non-negative floats order as integers)
-  uint64_t bar_full[kLStages], bar_empty[kLStages];
+  uint64_t bar_full[kStages], bar_empty[kStages];
   uint64_t bar_step;     // compute -> producer: another decode step follows (or exit)
   uint64_t bar_q;        // compute -> issuer: query tiles written (256 arrivals; also the exit signal)
   uint64_t bar_s[kH];    // issuer -> compute: scores of head h in TMEM
@@ -82,6 +84,17 @@ struct LeanSmem {
 };
 
 __device__ __forceinline__ void lean_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+// Waits of many warps for one mbarrier: a single warp watches the mbarrier, the others sleep in a hardware barrier that
+// costs no issue slots (eight warps polling one mbarrier through the FFN were ~20 % of the executed instructions).
+__device__ __forceinline__ void lean_wait_all(uint64_t* bar, uint32_t parity, int warp) {
+  if (warp == 0) tc05::mbar_wait(bar, parity);
+  asm volatile("bar.sync 4, 256;\n" ::: "memory");
+}
+__device__ __forceinline__ void lean_wait_group(uint64_t* bar, uint32_t parity, int warp) {  // the 4 warps of a head group
+  if ((warp & 3) == 0) tc05::mbar_wait(bar, parity);
+  if (warp < 4) asm volatile("bar.sync 2, 128;\n" ::: "memory");
+  else asm volatile("bar.sync 3, 128;\n" ::: "memory");
+}
 __device__ __forceinline__ int lean_sync_and(int pred) {
   uint32_t r;
   asm volatile(
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
   // ---------------- one-time staging ----------------
   if (warp == 0) tc05::tmem_alloc(&sm.tmem_base, 256);
   if (tid == 32) {
-    for (int i = 0; i < kLStages; ++i) {
+    for (int i = 0; i < SmemT::kStages; ++i) {
       tc05::mbar_init(&sm.bar_full[i], 1);
       tc05::mbar_init(&sm.bar_empty[i], 1);
     }
@@ -337,13 +350,12 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
   if (uwarp == 8) {
     // ===== TMA producer: per decode step 88 slices through the ring, in the order the issuer consumes them =====
     if (tc05::elect_one()) {
-      uint32_t sl = 0, step_par = 0;
+      uint32_t st = 0, round = 0, step_par = 0;  // ring stage, number of completed passes over the ring
       auto push = [&](const unsigned char* src, uint32_t bytes) {
-        const int st = sl & (kLStages - 1);
-        if (sl >= (uint32_t)kLStages) tc05::mbar_wait(&sm.bar_empty[st], ((sl / kLStages) - 1) & 1, 32);
+        if (round > 0) tc05::mbar_wait(&sm.bar_empty[st], (round - 1) & 1, 32);
         tc05::mbar_arrive_expect_tx(&sm.bar_full[st], bytes);
         tc05::bulk_g2s(sm.ring[st], src, bytes, &sm.bar_full[st]);
-        ++sl;
+        if (++st == (uint32_t)SmemT::kStages) { st = 0; ++round; }
       };
       while (true) {
         tc05::mbar_wait(&sm.bar_step, step_par, 64);
@@ -382,16 +394,15 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       const uint32_t ring_addr = tc05::smem_u32(sm.ring[0]);
       const uint32_t lbo_l = (uint32_t)R16 * 16u;   // bytes between the two K chunks of a K_h / Lk slice
       const uint32_t var_l = (uint32_t)R16 * 32u;   // hi -> lo variant of a K_h / V_h / Lk slice
-      uint32_t sl = 0, step_par = 0;
+      uint32_t st = 0, round = 0, step_par = 0;  // ring stage, number of completed passes over the ring
       auto stage_wait = [&]() -> uint32_t {
-        const int st = sl & (kLStages - 1);
-        tc05::mbar_wait(&sm.bar_full[st], (sl / kLStages) & 1);
+        tc05::mbar_wait(&sm.bar_full[st], round & 1);
         tc05::fence_after_sync();
-        return ring_addr + (uint32_t)st * kLStageBytes;
+        return ring_addr + st * kLStageBytes;
       };
       auto stage_release = [&]() {
-        tc05::commit(&sm.bar_empty[sl & (kLStages - 1)]);
-        ++sl;
+        tc05::commit(&sm.bar_empty[st]);
+        if (++st == (uint32_t)SmemT::kStages) { st = 0; ++round; }
       };
       auto issue_qk = [&](int k) {
         const int h = (k & 1) * 4 + (k >> 1);
@@ -664,7 +675,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         const int h = 4 * grp + j;
-        tc05::mbar_wait(&sm.bar_s[h], step_par, 20);
+        lean_wait_group(&sm.bar_s[h], step_par, warp);
         tc05::fence_after_sync();
         LSTAMP(3);
         // Both passes walk the row in 16-column blocks with the TMEM load of block k + 1 in flight while block k is
@@ -747,7 +758,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         LSTAMP(5);
         // glimpse of head h (decoder.py:292-293)
         const float inv = __fdividef(kAScale, kKvScale * (sum0 + sum1));  // glimpse scaled by kAScale, like the query tiles
-        tc05::mbar_wait(&sm.bar_o[h], step_par, 20);
+        lean_wait_group(&sm.bar_o[h], step_par, warp);
         tc05::fence_after_sync();
         LSTAMP(6);
         uint32_t o[16];
@@ -787,7 +798,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       const uint32_t t_h = tb + lane_b;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        tc05::mbar_wait(&sm.bar_h, c & 1, 32);
+        lean_wait_all(&sm.bar_h, c & 1, warp);
         tc05::fence_after_sync();
         LSTAMP(9);
         uint32_t va[16], vb[16];
@@ -825,7 +836,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         tc05::mbar_arrive(&sm.bar_epi);
         LSTAMP(10);
       }
-      tc05::mbar_wait(&sm.bar_g2, step_par, 32);
+      lean_wait_all(&sm.bar_g2, step_par, warp);
       tc05::fence_after_sync();
       LSTAMP(11);
       // output epilogue: g' = acc + b2 + g -> fp16 hi | lo in place over the output accumulator (A operand of the logits)
@@ -900,7 +911,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
     LSTAMP(14);
     lean_sync();
     LSTAMP(15);
-    tc05::mbar_wait(&sm.bar_acc, step_par, 32);
+    lean_wait_all(&sm.bar_acc, step_par, warp);
     tc05::fence_after_sync();
     LSTAMP(16);
 
