@@ -11,7 +11,7 @@
  * Conventions
  *  - extern "C", C99 types only; every pointer is a DEVICE pointer unless its name starts with `h_`.
  *  - The library never allocates or frees caller-visible memory.  Its only process-wide state are the three
- *    development knobs below (rrnco_set_precision / rrnco_set_ffn_engine / rrnco_set_step_tiling: defaults are the
+ *    development knobs below (rrnco_set_precision / rrnco_set_ffn_engine / rrnco_set_step_tiling / rrnco_set_start_split: defaults are the
  *    product configuration, set them before the first launch and never concurrently with one) and per-device
  *    launch-configuration caches (shared-memory attributes, SM count), which are idempotent.
  *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises.
@@ -47,6 +47,9 @@ extern "C" {
 #define RRNCO_DEV_NO_FEASIBLE 4u      /* fully-masked row (never happens upstream: depot always feasible) */
 #define RRNCO_DEV_TRUNCATED 8u        /* rollout cut at t_cap with unfinished tours ("Exceeded maximum number of steps",
                                          rrnco/models/policy.py:222-226: upstream logs an error and breaks) */
+#define RRNCO_DEV_SOFTMAX_RANGE 16u   /* key-tiled fused kernel (N > RRNCO_MAX_NODES_TILE) only: an attention head's scores
+                                         exceed the range its fixed softmax shift covers (|q_h| max|k_h| / 4 > 4.85); the
+                                         rollout's outputs must be discarded and the per-step entry points used instead */
 
 #define RRNCO_ENV_ATSP 0
 #define RRNCO_ENV_RCVRP 1
@@ -58,7 +61,9 @@ extern "C" {
 
 #define RRNCO_EMBED_DIM 128           /* experiment/rrnet.yaml: embed_dim 128, 8 heads */
 #define RRNCO_NUM_HEADS 8
-#define RRNCO_MAX_NODES_FUSED 128     /* fused decode kernel: one key tile; larger N -> RRNCO_ERR_UNSUPPORTED */
+#define RRNCO_MAX_NODES_TILE 128      /* one key tile: rrnco_decoder_logits and the single-tile fused kernels */
+#define RRNCO_MAX_NODES_FUSED 1024    /* rrnco_rollout: up to 8 key tiles of 128 (key-tiled kernel above RRNCO_MAX_NODES_TILE);
+                                         larger N -> RRNCO_ERR_UNSUPPORTED (use the per-step entry points) */
 
 int rrnco_abi_version(void);
 const char* rrnco_strerror(int code);
@@ -288,6 +293,15 @@ int rrnco_select_action(int64_t n_rollouts, int32_t n_nodes, const float* logits
  *                    survives the call, but two concurrent rollouts (different streams) need two workspaces.
  * ---------------------------------------------------------------------------------------------- */
 int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts);
+
+/* POMO starts per CTA tile of rrnco_rollout for this shape on the current device: 128, unless rrnco_set_start_split(1)
+ * (process-wide development knob, default 0) lets the key-tiled kernel (n_nodes > RRNCO_MAX_NODES_TILE, one CTA per SM)
+ * split the starts of an instance over several CTAs, in whole warps of 32 rows, when the instances alone would not fill
+ * the SMs (config C4: 64 instances x 100 starts -> 2 tiles of 64 / 36; measured gain 5 %: the passes are bound per SM
+ * sub-partition, so it is off).  The workspace holds one int32 step count per (instance, tile):
+ * n_inst * ceil(n_starts / tile_rows) of them, instance-major, at byte offset 16 * n_inst * n_starts. */
+int32_t rrnco_rollout_tile_rows(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts);
+int rrnco_set_start_split(int32_t on);
 
 int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts, int32_t multistart,
                   int32_t decode_mode, uint64_t seed, const rrnco_decoder_weights_t* w,

@@ -15,8 +15,9 @@ LIB_PATH = os.path.join(_HERE, "librrnco_b200.so")
 
 ENV_ID = {"atsp": 0, "rcvrp": 1, "rcvrptw": 2}
 DECODE_ID = {"greedy": 0, "sampling": 1, "evaluate": 2}
-DEV_NAN_LOGITS, DEV_INFEASIBLE, DEV_NO_FEASIBLE, DEV_TRUNCATED = 1, 2, 4, 8
-MAX_NODES_FUSED = 128
+DEV_NAN_LOGITS, DEV_INFEASIBLE, DEV_NO_FEASIBLE, DEV_TRUNCATED, DEV_SOFTMAX_RANGE = 1, 2, 4, 8, 16
+MAX_NODES_TILE = 128     # one key tile: rrnco_decoder_logits, single-tile fused kernels
+MAX_NODES_FUSED = 1024   # rrnco_rollout (key-tiled kernel above MAX_NODES_TILE)
 MIN_STARTS_TILED = 8   # RRNetDecoder.forward: starts per instance from which the any-N tile kernels serve every N
 
 _f = C.c_void_p  # every device pointer travels as void*
@@ -52,6 +53,8 @@ _SIGNATURES = {
     "rrnco_set_precision": (C.c_int, [C.c_int32]),
     "rrnco_set_ffn_engine": (C.c_int, [C.c_int32]),
     "rrnco_set_step_tiling": (C.c_int, [C.c_int32]),
+    "rrnco_set_start_split": (C.c_int, [C.c_int32]),
+    "rrnco_rollout_tile_rows": (C.c_int32, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     "rrnco_minmax_normalize": (C.c_int, [C.c_int64, C.c_int32, _f, _f, _f, _f, _f]),
     "rrnco_gather_submatrix": (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, _f, C.c_int32, _f, _f, _f]),
     "rrnco_gather_submatrix_f32": (C.c_int, [_f, C.c_int32, _f, C.c_int64, C.c_int32, _f, C.c_int32, _f, _f, _f]),

@@ -10,6 +10,7 @@ constexpr int kMaxState = 4;
 
 struct RolloutParams {
   int N, NT, S, n_tiles, n_state;
+  int tile_rows;                    // POMO starts per CTA tile (<= kRows); tile t holds starts [t tile_rows, (t + 1) tile_rows)
   int64_t n_inst;
   int multistart, mode, logits_only, use_placeholder, t_cap, forced_T, max_steps;
   uint64_t seed;

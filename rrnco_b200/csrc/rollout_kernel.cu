@@ -1728,7 +1728,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(RolloutParams p, float* l
     const int64_t b = r % p.n_inst;
     const int s = (int)(r / p.n_inst);
     const int64_t drow = b % p.d.data_rows;
-    const int t_own = p.ws_tile_steps[b * p.n_tiles + s / kRows];
+    const int t_own = p.ws_tile_steps[b * p.n_tiles + s / p.tile_rows];
     double len = p.ws_len[r];
     if (kEnv != RRNCO_ENV_ATSP && t_glob > t_own) {
       float d00 = p.d.distance[drow * (int64_t)p.N * p.N];
@@ -1817,6 +1817,10 @@ constexpr int64_t kLeanBiasBytes = 4096;  // scaled biases behind the packed wei
 int64_t lean_kv_bytes(int32_t n_nodes, int64_t n_tiles_total);
 int phase_cycles_lean(long long* h_out, int reset);
 constexpr int kLeanMaxNodes = 112;  // two score buffers + two P V slots in 256 TMEM columns
+int dispatch_env_tiled(const RolloutParams& p, int env, int passes, cudaStream_t st);  // rollout_tiled.cu (N > 128)
+int pack_kv_tiled(const RolloutParams& p, cudaStream_t st);
+int64_t tiled_kv_bytes(int32_t n_nodes, int64_t n_inst);
+int phase_cycles_tiled(long long* h_out, int reset);
 int phase_cycles_tc(long long* h_out, int reset);
 int timeline_tc(long long* h_out, int* n_out);
 
@@ -1853,6 +1857,25 @@ int check_common(int32_t env, int32_t N, int64_t n_inst, int32_t S, const rrnco_
 }
 
 int g_passes = 3;  // set through rrnco_set_precision (process-wide default, read-only on the hot path)
+int g_start_split = 0;  // key-tiled kernel: split the starts of an instance over several CTAs when the SMs would idle.  Off: the
+                        // per-element passes are bound per SM SUB-PARTITION (rows <-> TMEM lane quarter <-> warp % 4), so a
+                        // tile of 32 or 64 rows takes as long as one of 128 (measured: 132.9 vs 139.8 ms at config C4)
+// POMO starts per CTA tile and tiles per instance (see rrnco_rollout_tile_rows in the header)
+void rollout_tiling(int32_t n_nodes, int64_t n_inst, int32_t n_starts, int* tile_rows, int* n_tiles) {
+  int tr = kRows;
+  if (n_nodes > RRNCO_MAX_NODES_TILE && g_start_split) {
+    const int sms = device_sm_count();
+    int64_t k = sms > 0 ? sms / n_inst : 1;
+    const int64_t kmax = (n_starts + 31) / 32;
+    k = k > kmax ? kmax : k;
+    k = k < 1 ? 1 : k;
+    tr = (int)(((n_starts + k - 1) / k + 31) / 32 * 32);
+    tr = tr > kRows ? kRows : tr;
+  }
+  *tile_rows = tr;
+  *n_tiles = (n_starts + tr - 1) / tr;
+}
+bool g_last_tiled = false;  // the last rrnco_rollout call ran the key-tiled kernel (which counters rrnco_debug_phase_cycles reads)
 int g_engine = 2;  // engine of the fused rollout: 2 = tcgen05, two lean CTAs per SM (N <= 112; else 1), 1 = tcgen05, one CTA
                    // per SM, 0 = mma.sync
 
@@ -1862,6 +1885,7 @@ extern "C" {
 
 // debug: per-phase cycle totals of CTA 0 since the last reset (host buffer of 16 int64); reset != 0 clears them
 int rrnco_debug_phase_cycles(long long* h_out, int reset) {
+  if (g_last_tiled) return phase_cycles_tiled(h_out, reset);  // 32 counters
   if (g_engine == 2) return phase_cycles_lean(h_out, reset);  // 32 counters
   return g_engine == 1 ? phase_cycles_tc(h_out, reset) : phase_cycles_local(h_out, reset);
 }
@@ -1883,14 +1907,30 @@ int rrnco_set_ffn_engine(int32_t engine) {
   return RRNCO_OK;
 }
 
+int32_t rrnco_rollout_tile_rows(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts) {
+  (void)env;
+  if (n_inst <= 0 || n_starts <= 0) return kRows;
+  int tr, nt;
+  rollout_tiling(n_nodes, n_inst, n_starts, &tr, &nt);
+  return tr;
+}
+
+int rrnco_set_start_split(int32_t on) {
+  g_start_split = on ? 1 : 0;
+  return RRNCO_OK;
+}
+
 int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts) {
   (void)env;
   if (n_inst <= 0 || n_starts <= 0) return 0;
   const int64_t R = n_inst * n_starts;
-  const int64_t tiles = n_inst * ((n_starts + kRows - 1) / kRows);
+  int tile_rows, n_tiles;
+  rollout_tiling(n_nodes, n_inst, n_starts, &tile_rows, &n_tiles);
+  const int64_t tiles = n_inst * n_tiles;
   // packed K / V / logit-key tiles: one region per CTA (lean engine) or one slot per SM (one-CTA engine)
   int64_t kv = (int64_t)kKvSlots * kKvSlotBytes;
   if (n_nodes <= kLeanMaxNodes && lean_kv_bytes(n_nodes, tiles) > kv) kv = lean_kv_bytes(n_nodes, tiles);
+  if (n_nodes > RRNCO_MAX_NODES_TILE) kv = tiled_kv_bytes(n_nodes, n_inst);  // one pack per instance, shared by its start tiles
   return 2 * R * (int64_t)sizeof(double) + ((tiles * (int64_t)sizeof(int32_t) + 15) & ~15LL) + kFfnPackedBytes + kLeanBiasBytes + kv;
 }
 
@@ -1901,12 +1941,14 @@ int rrnco_decoder_logits(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n
                          uint32_t* status, void* stream) {
   int rc = check_common(env, n_nodes, n_inst, n_starts, w, cache, data);
   if (rc != RRNCO_OK) return rc;
+  if (n_nodes > RRNCO_MAX_NODES_TILE) return RRNCO_ERR_UNSUPPORTED;  // rrnco_decoder_logits_large serves any N
   RRNCO_CHECK_ARG(current && mask && logits_out && status);
   RRNCO_CHECK_ARG(env == RRNCO_ENV_ATSP ? first != nullptr : ctx_state != nullptr);
   RRNCO_CHECK_ARG(!use_placeholder || w->ctx_placeholder_q);
   RolloutParams p{};
   p.N = n_nodes; p.NT = (n_nodes + 7) / 8; p.S = n_starts; p.n_tiles = (n_starts + kRows - 1) / kRows;
   p.n_state = env == RRNCO_ENV_ATSP ? 0 : env == RRNCO_ENV_RCVRP ? 1 : 4;
+  p.tile_rows = kRows;
   p.n_inst = n_inst; p.logits_only = 1; p.use_placeholder = use_placeholder; p.max_steps = 1;
   p.w = *w; p.c = *cache; p.d = *data;
   p.in_cur = current; p.in_first = first; p.in_mask = mask; p.in_state = ctx_state; p.logits_out = logits_out;
@@ -1934,7 +1976,8 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
   if (env == RRNCO_ENV_ATSP && !multistart) RRNCO_CHECK_ARG(w->ctx_placeholder_q != nullptr);
   cudaStream_t st = (cudaStream_t)stream;
   RolloutParams p{};
-  p.N = n_nodes; p.NT = (n_nodes + 7) / 8; p.S = n_starts; p.n_tiles = (n_starts + kRows - 1) / kRows;
+  p.N = n_nodes; p.NT = (n_nodes + 7) / 8; p.S = n_starts;
+  rollout_tiling(n_nodes, n_inst, n_starts, &p.tile_rows, &p.n_tiles);
   p.n_state = env == RRNCO_ENV_ATSP ? 0 : env == RRNCO_ENV_RCVRP ? 1 : 4;
   p.n_inst = n_inst; p.multistart = multistart; p.mode = decode_mode; p.use_placeholder = !multistart;
   p.t_cap = t_cap; p.forced_T = forced_T; p.max_steps = t_cap - (multistart ? 1 : 0); p.seed = seed;
@@ -1951,7 +1994,14 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
   p.kv_pack = packed + kFfnPackedBytes + kLeanBiasBytes;  // 16-byte aligned: every part above is a multiple of 16 bytes
   p.max_steps_out = max_steps_out; p.status = status;
   if (cudaMemsetAsync(max_steps_out, 0, sizeof(int32_t), st) != cudaSuccess) return RRNCO_ERR_CUDA;
-  if (g_engine == 2 && n_nodes <= kLeanMaxNodes) {
+  g_last_tiled = n_nodes > RRNCO_MAX_NODES_TILE;
+  if (n_nodes > RRNCO_MAX_NODES_TILE) {  // key-tiled tcgen05 kernel (the only fused engine for more than one key tile)
+    rc = pack_ffn_lean(w->ffn_w1, w->ffn_w2, w->ffn_b1, w->ffn_b2, packed, status, st);
+    if (rc != RRNCO_OK) return rc;
+    rc = pack_kv_tiled(p, st);
+    if (rc != RRNCO_OK) return rc;
+    rc = dispatch_env_tiled(p, env, g_passes, st);
+  } else if (g_engine == 2 && n_nodes <= kLeanMaxNodes) {
     rc = pack_ffn_lean(w->ffn_w1, w->ffn_w2, w->ffn_b1, w->ffn_b2, packed, status, st);
     if (rc != RRNCO_OK) return rc;
     rc = dispatch_env_lean(p, env, g_passes, st);

@@ -155,7 +155,7 @@ std::tuple<Tensor, Tensor> select_action(const Tensor& logits, const Tensor& mas
 // data   : [distance, duration?, demand?, demand_backhaul?, time_windows?, service_time?, vehicle_capacity?, distance_limit?,
 //           open_route?, backhaul_class?, min_distance?, max_distance?]   (the members of rrnco_instance_data_t, in order)
 // -> (actions [R, t_cap], logprob [R, t_cap] | empty, log_likelihood [R], normalised reward [R], real reward [R] | empty,
-//     info int32 [2] = (longest rollout T, device status word), tile_steps int32 [n_inst * ceil(S / 128)])
+//     info int32 [2] = (longest rollout T, device status word), tile_steps int32 [n_inst * ceil(S / rrnco_rollout_tile_rows)])
 std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> rollout(
     int64_t env, int64_t n_starts, bool multistart, int64_t decode_mode, int64_t seed, const c10::List<OptTensor>& weights,
     double alpha, double beta, double tanh_clipping, double temperature, const c10::List<OptTensor>& cache,
@@ -203,7 +203,8 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> rollout(
                          ll.data_ptr<float>(), norm.data_ptr<float>(), has_mm ? real.data_ptr<float>() : nullptr,
                          info.data_ptr<int32_t>(), reinterpret_cast<uint32_t*>(info.data_ptr<int32_t>() + 1),
                          workspace.data_ptr<uint8_t>(), stream_of(key)), "rollout");
-  const int64_t n_tiles = n_inst * ((n_starts + 127) / 128);
+  const int64_t tile_rows = rrnco_rollout_tile_rows((int32_t)env, (int32_t)N, n_inst, (int32_t)n_starts);
+  const int64_t n_tiles = n_inst * ((n_starts + tile_rows - 1) / tile_rows);
   Tensor tile_steps = workspace.narrow(0, 2 * R * 8, 4 * n_tiles).view(at::kInt);
   return {actions, logprob, ll, norm, real, info, tile_steps};
 }

@@ -234,7 +234,7 @@ class RRNetDecoder(nn.Module):
         cs = cached.struct()
         # per-step kernels: with >= 8 starts per instance the key-sharing tile kernels (any N) are also the faster ones at
         # N <= 128 (RCVRP n=100 x8 aug x101 starts, per-step loop: 904 vs 661 instances/s, tools/per_step_probe.py)
-        if N <= _lib.MAX_NODES_FUSED and S < _lib.MIN_STARTS_TILED:
+        if N <= _lib.MAX_NODES_TILE and S < _lib.MIN_STARTS_TILED:
             call("rrnco_decoder_logits", ENV_ID[self.env_name], N, n_inst, S, C.byref(w), C.byref(cs), C.byref(data),
                  ptr(cur), ptr(first), ptr(_u8(mask)), ptr(state), placeholder, ptr(logits), ptr(status),
                  stream_ptr(mask.device))
@@ -270,6 +270,7 @@ class RRNetPolicy(nn.Module):
         self.seed = None  # sampling seed base; None = derived from torch.initial_seed() and the distributed rank
         self._calls = 0
         self.train_replay_autocast = None  # e.g. torch.bfloat16: autocast of the differentiable replay in phase "train"
+        self.large_n_path = "fused"  # 128 < N <= 1024: "fused" = key-tiled rollout kernel, "stepwise" = per-step kernel pipeline
 
     def _seed_base(self) -> int:
         """Philox key of the Gumbel-max sampler when the caller passes no `seed=`: follows torch / Lightning seeding
@@ -319,11 +320,22 @@ class RRNetPolicy(nn.Module):
 
         cache = self.decoder._precompute_cache((row_emb, col_emb), num_starts=S)
         self._calls += 1
-        rollout_fn = fused_rollout if cache.glimpse_key.shape[1] <= _lib.MAX_NODES_FUSED else stepwise_rollout
-        out = rollout_fn(self.decoder, cache, env, td, S, multistart, decode_type.replace("multistart_", ""),
-                            forced_actions=actions, seed=decoding_kwargs.pop("seed", self._seed_base() + self._calls),
+        n_nodes = cache.glimpse_key.shape[1]
+        # N <= 128: single-tile fused kernels; N <= 1024: key-tiled fused kernel; beyond (or large_n_path = "stepwise"): the
+        # per-step kernel pipeline
+        use_fused = n_nodes <= _lib.MAX_NODES_TILE or (n_nodes <= _lib.MAX_NODES_FUSED and self.large_n_path == "fused")
+        rollout_fn = fused_rollout if use_fused else stepwise_rollout
+        rollout_args = dict(forced_actions=actions, seed=decoding_kwargs.pop("seed", self._seed_base() + self._calls),
                             temperature=temperature, tanh_clipping=tanh_clipping, calc_reward=calc_reward,
                             per_step_logprobs=not return_sum_log_likelihood, check=self.decoder.check_nan)
+        try:
+            out = rollout_fn(self.decoder, cache, env, td, S, multistart, decode_type.replace("multistart_", ""), **rollout_args)
+        except SoftmaxRangeError:
+            FALLBACKS["softmax_range"] += 1
+            # key-tiled fused kernel only (N > 128): a head's scores left the range of its fixed softmax shift; the per-step
+            # kernels (exact running maximum) serve such checkpoints -- still the CUDA path, never a CPU fallback
+            out = stepwise_rollout(self.decoder, cache, env, td, S, multistart, decode_type.replace("multistart_", ""),
+                                   **rollout_args)
         outdict = {"reward": out["reward"],
                    "log_likelihood": out["log_likelihood"] if return_sum_log_likelihood else out["logprobs"]}
         if phase == "train" and torch.is_grad_enabled() and multistart and actions is None:
@@ -347,6 +359,14 @@ class RRNetPolicy(nn.Module):
         if return_hidden:
             outdict["hidden"] = cache
         return outdict
+
+
+FALLBACKS = {"softmax_range": 0}  # rollouts re-run through the per-step pipeline (diagnostics)
+
+
+class SoftmaxRangeError(RuntimeError):
+    """RRNCO_DEV_SOFTMAX_RANGE: the key-tiled fused kernel cannot represent this model's attention scores; its outputs
+    were discarded (use stepwise_rollout)."""
 
 
 _WS_CACHE = {}
@@ -416,12 +436,15 @@ def fused_rollout(decoder: RRNetDecoder, cache: PrecomputedCache, env, td, num_s
              C.byref(w), C.byref(cs), C.byref(data), ptr(forced), forced_T, t_cap, ptr(acts), ptr(logp), ptr(ll),
              ptr(norm), ptr(real), ptr(info[0:1]), ptr(info[1:2]), ptr(ws), stream_ptr(dev))
     T, status = info.tolist()  # the ONE host sync of the rollout (upstream: 3-5 per decode step)
+    if status & _lib.DEV_SOFTMAX_RANGE:  # never silently inaccurate, whatever `check` says
+        raise SoftmaxRangeError("attention scores outside the range of the key-tiled kernel's fixed softmax shift")
     if check:
         _lib.raise_device_status(status)
     out = {"actions": acts[:, :T], "log_likelihood": ll}
-    # decode steps each (instance, 128-start tile) CTA actually ran (it stops when ITS rollouts are done): what the
+    # decode steps each (instance, start tile) CTA actually ran (it stops when ITS rollouts are done): what the
     # roofline accounting of bench.py counts, instead of the global maximum T
-    n_tiles = n_inst * ((S + 127) // 128)
+    tile_rows = _lib.lib().rrnco_rollout_tile_rows(ENV_ID[name], N, n_inst, S)
+    n_tiles = n_inst * ((S + tile_rows - 1) // tile_rows)
     out["tile_steps"] = ws[2 * R * 8: 2 * R * 8 + 4 * n_tiles].view(torch.int32)
     if per_step_logprobs:
         out["logprobs"] = logp[:, :T]

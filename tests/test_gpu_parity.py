@@ -457,11 +457,16 @@ def test_pointer_ffn_tcgen05(rb):
         assert (out.double() - ref).abs().max() < 2e-5
 
 
+_LARGE_N_ORACLE = {}
+
+
+@pytest.mark.parametrize("path", ["fused", "stepwise"])
 @pytest.mark.parametrize("name,n,B,S", [("atsp", 150, 2, None), ("rcvrp", 140, 2, None), ("rcvrptw", 130, 2, 40),
-                                         ("atsp", 1000, 1, 100)])
-def test_large_n_stepwise_rollout_vs_oracle(rb, name, n, B, S):
-    """N > 128 (incl. BASELINE's ATSP n=1000 generalisation case, 100 starts like test.py:129-130): key-streaming
-    decoder + select + env-step kernels, matrices never replicated over the starts."""
+                                         ("atsp", 1000, 1, 100), ("atsp", 257, 3, 130), ("rcvrp", 300, 2, 70)])
+def test_large_n_rollout_vs_oracle(rb, name, n, B, S, path):
+    """N > 128 (incl. BASELINE's ATSP n=1000 generalisation case, 100 starts like test.py:129-130) through both CUDA paths:
+    "fused" = the key-tiled persistent tcgen05 kernel (rollout_tiled.cu: one launch per rollout), "stepwise" = decoder +
+    select + env-step kernels per decode step.  Matrices are never replicated over the starts."""
     raw = synth.make_instances(name, B, n, seed=n)
     oenv = oenvs.make_env(name, n, check_solution=False)
     otd = oenv.reset(raw)
@@ -469,11 +474,17 @@ def test_large_n_stepwise_rollout_vs_oracle(rb, name, n, B, S):
     S = oenv.get_num_starts(otd) if S is None else S
     row, col = synth.random_embeddings(B, N, seed=n + 1)
     p = omodel.init_decoder_params(name, seed=n + 2)
-    with torch.inference_mode():
-        oout = omodel.policy_forward(p, oenv, otd, row, col, decode_type="multistart_greedy", num_starts=S)
+    if (name, n, B, S) not in _LARGE_N_ORACLE:  # the CPU oracle run is shared by the two paths
+        with torch.inference_mode():
+            _LARGE_N_ORACLE[(name, n, B, S)] = omodel.policy_forward(p, oenv, otd, row, col, decode_type="multistart_greedy",
+                                                                      num_starts=S)
+    oout = _LARGE_N_ORACLE[(name, n, B, S)]
     env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
     pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    pol.large_n_path = path
     out = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    if path == "fused":
+        assert rb.models.FALLBACKS["softmax_range"] == 0  # the fused kernel served it
     acts, want = out["actions"].cpu(), oout["actions"]
     T = max(acts.shape[1], want.shape[1])
     acts = torch.nn.functional.pad(acts, (0, T - acts.shape[1]))
@@ -481,10 +492,94 @@ def test_large_n_stepwise_rollout_vs_oracle(rb, name, n, B, S):
     same = (acts == want).all(1)
     assert same.float().mean() >= 0.97, same.float().mean()
     assert rel(out["reward"].cpu()[same], oout["reward"][same]) < 1e-6
+    ll, oll = out["log_likelihood"].cpu()[same], oout["log_likelihood"][same]
+    assert ((ll - oll).abs() <= 2e-5 * oll.abs() + 2e-3).all(), (ll - oll).abs().max()
     best, obest = out["reward"].cpu().view(S, B).max(0)[0], oout["reward"].view(S, B).max(0)[0]
     assert ((best - obest).abs() / obest.abs() < 1e-4).all()
     if name == "atsp":  # every tour is a permutation
         assert (out["actions"].sort(1)[0] == torch.arange(N, device=dev)).all()
+
+
+def test_key_tiled_kernel_exact_softmax_shift_on_peaked_heads(rb):
+    """rollout_tiled.cu picks the softmax shift per decode step: the Cauchy-Schwarz bound when every head's scores stay
+    within +-4.8, else a first sweep of single-term scores for the masked row maxima.  Embeddings scaled x3 give scores of
+    +-30 (peaked heads, every step in the second mode): tours / costs / log-likelihoods must still match the fp32 oracle,
+    and the per-step pipeline (running maximum).  Scaled x14 the scores leave even that sweep's range: the policy must then
+    serve the call through the per-step pipeline (loud status bit, counted), never return the fused kernel's numbers."""
+    name, n, B, S = "atsp", 300, 2, 64
+    raw = synth.make_instances(name, B, n, seed=5)
+    oenv = oenvs.make_env(name, n, check_solution=False)
+    row, col = synth.random_embeddings(B, n, seed=6)
+    row, col = 3.0 * row, 3.0 * col
+    p = omodel.init_decoder_params(name, seed=7)
+    with torch.inference_mode():
+        oout = omodel.policy_forward(p, oenv, oenv.reset(raw), row, col, decode_type="multistart_greedy", num_starts=S)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    before = rb.models.FALLBACKS["softmax_range"]
+    out = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    assert rb.models.FALLBACKS["softmax_range"] == before
+    same = _same_tours(out["actions"].cpu(), oout["actions"])
+    assert same.float().mean() >= 0.97, same.float().mean()
+    assert rel(out["reward"].cpu()[same], oout["reward"][same]) < 1e-6
+    ll, oll = out["log_likelihood"].cpu()[same], oout["log_likelihood"][same]
+    assert ((ll - oll).abs() <= 2e-5 * oll.abs() + 2e-3).all(), (ll - oll).abs().max()
+    pol.large_n_path = "stepwise"
+    out2 = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    assert _same_tours(out["actions"], out2["actions"]).float().mean() >= 0.97
+    # beyond the single-term sweep's range: fused kernel refuses loudly, the policy falls back to the per-step kernels
+    pol14 = make_policy(rb, name, p, (14.0 / 3.0 * row).to(dev), (14.0 / 3.0 * col).to(dev))
+    cache = pol14.decoder._precompute_cache(((14.0 / 3.0 * row).to(dev), (14.0 / 3.0 * col).to(dev)))
+    td = env.reset(lite(rb, raw))
+    with pytest.raises(rb.models.SoftmaxRangeError):
+        rb.fused_rollout(pol14.decoder, cache, env, td, S, True, "greedy", check=False)
+    out3 = pol14(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    assert rb.models.FALLBACKS["softmax_range"] == before + 1
+    assert (out3["actions"].sort(1)[0] == torch.arange(n, device=dev)).all()
+
+
+def test_key_tiled_kernel_sampling_evaluate_and_determinism(rb):
+    """rollout_tiled.cu, the other decode modes at N > 128: sampling draws arg-max(v + Gumbel) with the same Philox
+    counters as rrnco_select_action (so the per-step pipeline with the same seed samples the same tours), evaluate mode
+    reproduces the per-step log-probs of those tours, and two runs are bitwise identical."""
+    name, n, B, S = "rcvrp", 200, 3, 64
+    raw = synth.make_instances(name, B, n, seed=21)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    row, col = synth.random_embeddings(B, n + 1, seed=22)
+    pol = make_policy(rb, name, omodel.init_decoder_params(name, seed=23), row.to(dev), col.to(dev))
+    td = env.reset(lite(rb, raw))
+    kw = dict(phase="val", decode_type="multistart_sampling", num_starts=S, seed=99, return_sum_log_likelihood=False)
+    out = pol(td, env, **kw)
+    again = pol(td, env, **kw)
+    assert torch.equal(out["actions"], again["actions"]) and torch.equal(out["log_likelihood"], again["log_likelihood"])
+    assert torch.equal(out["reward"], again["reward"])
+    srt = out["actions"].sort(1)[0]
+    assert (srt[:, -n:] == torch.arange(1, n + 1, device=dev)).all() and (srt[:, :-n] == 0).all()
+    pol.large_n_path = "stepwise"
+    ref = pol(td, env, **kw)
+    pol.large_n_path = "fused"
+    same = _same_tours(out["actions"], ref["actions"])
+    assert same.float().mean() >= 0.97, same.float().mean()
+    T = min(out["log_likelihood"].shape[1], ref["log_likelihood"].shape[1])
+    assert (out["log_likelihood"][same][:, :T] - ref["log_likelihood"][same][:, :T]).abs().max() < 1e-4
+    assert rel(out["reward"][same], ref["reward"][same]) < 1e-6
+    # evaluate: the sampled decisions forced back in give the same per-step log-probs
+    ev = pol(td, env, phase="train", num_starts=S, actions=out["actions"][:, 1:], return_sum_log_likelihood=False)
+    assert torch.equal(ev["actions"], out["actions"])
+    assert (ev["log_likelihood"] - out["log_likelihood"]).abs().max() < 1e-5
+    assert rel(ev["reward"], out["reward"]) < 1e-6
+    # not a multiple of four nodes (bias rows not 16-byte aligned: 4-byte cp.async pieces) and more starts than one tile
+    name, n, S = "atsp", 203, 203
+    raw = synth.make_instances(name, 2, n, seed=31)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    row, col = synth.random_embeddings(2, n, seed=32)
+    pol = make_policy(rb, name, omodel.init_decoder_params(name, seed=33), row.to(dev), col.to(dev))
+    td = env.reset(lite(rb, raw))
+    a = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    pol.large_n_path = "stepwise"
+    b = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    same = _same_tours(a["actions"], b["actions"])
+    assert same.float().mean() >= 0.97 and rel(a["reward"][same], b["reward"][same]) < 1e-6
 
 
 @pytest.mark.parametrize("name,n,S", [("atsp", 200, 37), ("rcvrptw", 150, 20), ("rcvrp", 133, 5)])
@@ -807,7 +902,8 @@ def test_sampling_twin_rcvrptw_n100(rb):
 
 
 def test_c4_shape_atsp_n1000_batch4_vs_oracle(rb):
-    """Config C4's shape with more than one instance: ATSP n=1000, 4 instances x 100 starts (test.py:129-130)."""
+    """Config C4's shape with more than one instance: ATSP n=1000, 4 instances x 100 starts (test.py:129-130), through the
+    key-tiled fused kernel (8 key tiles)."""
     name, n, B, S = "atsp", 1000, 4, 100
     raw = synth.make_instances(name, B, n, seed=1000)
     oenv = oenvs.make_env(name, n, check_solution=False)
