@@ -741,7 +741,7 @@ def measure_configs(args, rb, dev, rank, world, dist_on, timed, only=None, steps
             assert td.batch_size[0] == Bc, (td.batch_size, Bc)
             return env.reset(augment(td) if augment is not None else td)
 
-        rollout = rb.fused_rollout if N <= 112 else rb.stepwise_rollout
+        rollout = rb.fused_rollout if N <= 1024 else rb.stepwise_rollout
         state = {}
 
         if spec["scaling"] == "strong":
@@ -813,8 +813,9 @@ def measure_configs(args, rb, dev, rank, world, dist_on, timed, only=None, steps
         out = state["out"]
         if "tile_steps" in out:
             ts = (out["tile_steps"].long() - 1).clamp_min(0)
-            n_tiles = (S + 127) // 128
-            rows = torch.tensor([min(128, S - t * 128) for t in range(n_tiles)], device=ts.device).repeat(ts.numel() // n_tiles)
+            tr = rb._lib.lib().rrnco_rollout_tile_rows(rb._lib.ENV_ID[name], N, Bc * A, S)  # POMO starts per CTA tile
+            n_tiles = (S + tr - 1) // tr
+            rows = torch.tensor([min(tr, S - t * tr) for t in range(n_tiles)], device=ts.device).repeat(ts.numel() // n_tiles)
             rollout_steps = int((ts * rows).sum().item())
         else:
             rollout_steps = Bc * A * S * (out["actions"].shape[1] - 1)
@@ -824,7 +825,8 @@ def measure_configs(args, rb, dev, rank, world, dist_on, timed, only=None, steps
                  "ms_per_step": ms_val, "steps": spec["steps"], "instances_per_gpu": Bc, "n_aug": A, "num_starts": S,
                  "decode": kind, "decode_steps_max": int(out["actions"].shape[1]),
                  "path": "fused persistent kernel (rrnco_rollout, lean engine)" if N <= 112 else
-                         "per-step pipeline (rrnco_decoder_logits_large + rrnco_select_action + env step)",
+                         "fused persistent key-tiled kernel (rrnco_rollout, rollout_tiled.cu: 128-key tiles, CTA pairs)" if N <= 1024
+                         else "per-step pipeline (rrnco_decoder_logits_large + rrnco_select_action + env step)",
                  "e2e": {"value": n_units / (ms_e2e * 1e-3), "unit": "instances/s", "h2d_bytes_per_step": int(h2d),
                          "d2h_bytes_per_step": int(d2h), "what": e2e_what},
                  "roofline": {"hbm_algorithmic": {"achieved": rollout_steps * b_alg / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",

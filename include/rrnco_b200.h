@@ -295,13 +295,14 @@ int rrnco_select_action(int64_t n_rollouts, int32_t n_nodes, const float* logits
 int64_t rrnco_rollout_workspace_bytes(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts);
 
 /* POMO starts per CTA tile of rrnco_rollout for this shape on the current device: 128, unless rrnco_set_start_split(1)
- * (process-wide development knob, default 0) lets the key-tiled kernel (n_nodes > RRNCO_MAX_NODES_TILE, one CTA per SM)
+ * (process-wide development knob, default 0; 2 = default tiling but without the key-tiled kernel's CTA pairs, i.e. one
+ * CTA per tile even when that leaves most SMs idle) lets the key-tiled kernel (n_nodes > RRNCO_MAX_NODES_TILE, one CTA per SM)
  * split the starts of an instance over several CTAs, in whole warps of 32 rows, when the instances alone would not fill
  * the SMs (config C4: 64 instances x 100 starts -> 2 tiles of 64 / 36; measured gain 5 %: the passes are bound per SM
  * sub-partition, so it is off).  The workspace holds one int32 step count per (instance, tile):
  * n_inst * ceil(n_starts / tile_rows) of them, instance-major, at byte offset 16 * n_inst * n_starts. */
 int32_t rrnco_rollout_tile_rows(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts);
-int rrnco_set_start_split(int32_t on);
+int rrnco_set_start_split(int32_t mode);
 
 int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts, int32_t multistart,
                   int32_t decode_mode, uint64_t seed, const rrnco_decoder_weights_t* w,

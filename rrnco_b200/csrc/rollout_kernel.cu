@@ -1821,6 +1821,7 @@ int dispatch_env_tiled(const RolloutParams& p, int env, int passes, cudaStream_t
 int pack_kv_tiled(const RolloutParams& p, cudaStream_t st);
 int64_t tiled_kv_bytes(int32_t n_nodes, int64_t n_inst);
 int phase_cycles_tiled(long long* h_out, int reset);
+extern int g_tiled_pairs;
 int phase_cycles_tc(long long* h_out, int reset);
 int timeline_tc(long long* h_out, int* n_out);
 
@@ -1915,8 +1916,10 @@ int32_t rrnco_rollout_tile_rows(int32_t env, int32_t n_nodes, int64_t n_inst, in
   return tr;
 }
 
-int rrnco_set_start_split(int32_t on) {
-  g_start_split = on ? 1 : 0;
+int rrnco_set_start_split(int32_t mode) {  // 0 = product configuration; 1 = split the starts over CTAs; 2 = no CTA pairs
+  if (mode < 0 || mode > 2) return RRNCO_ERR_BAD_ARG;
+  g_start_split = mode == 1 ? 1 : 0;
+  g_tiled_pairs = mode == 2 ? 0 : 1;
   return RRNCO_OK;
 }
 

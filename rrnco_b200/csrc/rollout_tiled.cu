@@ -25,6 +25,12 @@
 // columns: a thread-per-row read straight from global memory costs one L1 wavefront per element and bounded the select.
 // A tile holds p.tile_rows <= 128 POMO starts (the launcher splits the starts of an instance over several CTAs when the
 // grid would not fill the SMs); warps whose 32 rows are all padding skip every per-element pass.
+// CTA PAIRS (kPair, a thread-block cluster of 2): when the tiles alone leave more than half of the SMs idle (config C4: 64
+// tiles on 148 SMs) two CTAs share a tile.  Both hold the full rollout state and run the FFN redundantly; rank r computes
+// the attention of heads 4 r .. 4 r + 3 only and writes its half of the glimpse tile into BOTH CTAs' activation tiles
+// (st.shared::cluster), and it computes the logits / select pass of half of the key tiles only; the per-row partial
+// results (maximum, sum, best key) are exchanged the same way and merged in rank order, so both CTAs take the same
+// transition.  Cross-CTA ordering: remote mbarrier arrivals with release / acquire at cluster scope.
 // Scores beyond the single-term sweep's reach (|q_h| max|k_h| / 4 > 350) raise RRNCO_DEV_SOFTMAX_RANGE:
 // the host then runs the per-step pipeline (step_kernels.cu) instead -- loud, never silently inaccurate.
 #include <cstdio>
@@ -43,6 +49,7 @@ constexpr int kGWords = kGMaxNodes / 32;   // 32 mask words per rollout
 constexpr int kGWordLd = kGWords + 1;      // padded row stride: thread-per-row accesses are conflict-free
 constexpr int kGSlicesPerTile = 24;        // K heads 0-7 | V heads 8-15 | logit-key K steps 16-23
 constexpr int kGJobs = 8, kGWSlices = kGJobs * 8;
+int g_tiled_pairs = 1;  // rrnco_set_start_split(2) turns the CTA pairs off (development knob)
 
 // per-phase cycle accumulator of thread 0 of CTA 0 (development builds: RRNCO_PHASE_STAMPS), read with rrnco_debug_phase_cycles
 __device__ long long g_tiled_cycles[32];
@@ -77,6 +84,8 @@ struct TiledSmem {
   float bias[kEnv == RRNCO_ENV_RCVRPTW ? 1 : 2][2][kEnv == RRNCO_ENV_RCVRPTW ? 4 : kRows * 16];  // [group][buffer][row][16 columns]
   float xf[4][2][kRows];                   // select exchange: running max, sum, best key, value at the best / forced column
   int xi[2][kRows];
+  float xpf[4][kRows];                     // CTA pair: the peer's per-row partial of the select pass (written remotely)
+  int xpi[kRows];
   uint16_t cur[kRows], first[kRows], cnt[kRows];
   unsigned char active[kRows], done[kRows];
   uint32_t lhmask[kGWords];
@@ -92,10 +101,55 @@ struct TiledSmem {
   uint64_t bar_h, bar_epi, bar_g2, bar_lk;  // FFN chain, as in rollout_lean.cu
   uint64_t bar_l[2];      // issuer -> group b: logits of a key tile in buffer b
   uint64_t bar_lfree[2];  // group b -> issuer: logits buffer b consumed (128 arrivals)
+  uint64_t bar_xg;        // CTA pair: the peer's half of the glimpse tile has been written into this CTA's A (256 remote arrivals)
+  uint64_t bar_xs;        // CTA pair: the peer's select partials have been written into xpf / xpi (128 remote arrivals)
   uint32_t tmem_base;
   volatile int exit_flag;
   volatile int need_max;  // this step runs the exact-shift sweep first (CTA-uniform)
 };
+
+// ---- thread-block cluster helpers (CTA pair) ----
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of both CTAs (used once, before any thread exits)
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(const void* local_smem, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(tc05::smem_u32(local_smem)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_b32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.b32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
+}
+// arrive on an mbarrier of the peer CTA; release at cluster scope: this thread's earlier (remote) stores are visible to
+// whoever observes the phase completion with an acquire at cluster scope
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = tc05::smem_u32(bar);
+  uint32_t ok = 0, polls = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (ok) break;
+    if (++polls > (1u << 24)) __trap();
+  }
+}
 
 __device__ __forceinline__ void tiled_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 __device__ __forceinline__ void tiled_wait_all(uint64_t* bar, uint32_t parity, int warp) {
@@ -229,7 +283,7 @@ __device__ __forceinline__ float tiled_transition(TiledSmem<kEnv>& sm, int N, in
   return leg;
 }
 
-template <int kEnv, int kPasses>
+template <int kEnv, int kPasses, bool kPair>
 __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const RolloutParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using SmemT = TiledSmem<kEnv>;
@@ -244,8 +298,14 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
   const int nT = (N + kRows - 1) / kRows;              // key tiles
   const int W = (N + 31) >> 5;                         // mask words in use
   const int nb_last = ((N - (nT - 1) * kRows) + 15) >> 4;  // 16-key blocks of the last key tile
-  const int tile = blockIdx.x % p.n_tiles;
-  const int64_t b = blockIdx.x / p.n_tiles;
+  const uint32_t rank = kPair ? cluster_rank() : 0u;           // CTA pair: which half of the heads / key tiles is mine
+  const int tile_id = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile = tile_id % p.n_tiles;
+  const int64_t b = tile_id / p.n_tiles;
+  const int h_lo = kPair ? 4 * (int)rank : 0;                  // my attention heads [h_lo, h_lo + n_heads)
+  constexpr int n_heads = kPair ? kH / 2 : kH;
+  const int t_lo = kPair && rank ? (nT + 1) / 2 : 0;           // my logits key tiles [t_lo, t_hi)
+  const int t_hi = kPair && !rank ? (nT + 1) / 2 : nT;
   const int rows_here = min(p.tile_rows, p.S - tile * p.tile_rows);  // real rollouts of this tile (rows beyond are padding)
   const int rows_on = min(kRows, (rows_here + 31) & ~31);            // rows of the warps that compute (padding rows among
                                                                      // them shadow the tile's first rollout)
@@ -288,6 +348,8 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
     tc05::mbar_init(&sm.bar_epi, kGCompute);
     tc05::mbar_init(&sm.bar_g2, 1);
     tc05::mbar_init(&sm.bar_lk, kGCompute);
+    tc05::mbar_init(&sm.bar_xg, kGCompute);
+    tc05::mbar_init(&sm.bar_xs, kGCompute / 2);
     tc05::fence_mbar_init();
     sm.exit_flag = 0;
     sm.need_max = 0;
@@ -355,7 +417,7 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
       const int a0 = s % num_loc + (kEnv == RRNCO_ENV_ATSP ? 0 : 1);  // select_start_nodes
       len_acc += (double)tiled_transition<kEnv>(sm, N, row, a0, D, U, closed, /*count_leg=*/false);  // depot -> a0 (VRPs)
       sm.first[row] = (uint16_t)a0;
-      if (active) {
+      if (active && rank == 0u) {
         p.actions[r * p.t_cap] = a0;
         if (p.logprob) p.logprob[r * p.t_cap] = 0.f;
       }
@@ -364,9 +426,10 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
   tc05::fence_before_sync();
   __syncthreads();
   tc05::fence_after_sync();
+  if (kPair) cluster_sync_all();  // the peer CTA has started and initialised its barriers: its shared memory may be written
 
   const int uwarp = __shfl_sync(0xffffffffu, warp, 0);  // warp index as a value the compiler knows to be warp-uniform
-  const int n_pairs = kH * nT;
+  const int n_pairs = n_heads * nT;
   if (uwarp == 8) {
     // ===== TMA producer: the slices of a decode step in the order the issuer consumes them =====
     if (tc05::elect_one()) {
@@ -386,18 +449,18 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
         // rest of the exact-shift sweep (K of every pair, then K(0..2) again), then V(i), K(i + 3);
         // pair i = (head i / nT, key tile i % nT)
         const int npre = min(3, n_pairs);
-        for (int i = 0; i < npre; ++i) push(slice(i % nT, i / nT));
+        for (int i = 0; i < npre; ++i) push(slice(i % nT, h_lo + i / nT));
         tc05::mbar_wait(&sm.bar_mode, step_par ^ 1u, 32);  // (step_par was flipped above: this step's phase)
         if (sm.need_max) {
-          int h = npre / nT, t = npre % nT;
+          int h = h_lo + npre / nT, t = npre % nT;
 #pragma unroll 1
           for (int i = npre; i < n_pairs; ++i) {
             push(slice(t, h));
             if (++t == nT) { t = 0; ++h; }
           }
-          for (int i = 0; i < npre; ++i) push(slice(i % nT, i / nT));
+          for (int i = 0; i < npre; ++i) push(slice(i % nT, h_lo + i / nT));
         }
-        int h = 0, t = 0, h2 = 3 / nT, t2 = 3 % nT;
+        int h = h_lo, t = 0, h2 = h_lo + 3 / nT, t2 = 3 % nT;
 #pragma unroll 1
         for (int i = 0; i < n_pairs; ++i) {
           push(slice(t, 8 + h));
@@ -408,7 +471,7 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
 #pragma unroll 1
         for (int s = 0; s < kGWSlices; ++s) push(p.ffn_packed + (size_t)s * kGStage);
 #pragma unroll 1
-        for (int tt = 0; tt < nT; ++tt)
+        for (int tt = t_lo; tt < t_hi; ++tt)
 #pragma unroll 1
           for (int ks = 0; ks < 8; ++ks) push(slice(tt, 16 + ks));
       }
@@ -466,8 +529,8 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
         tc05::fence_after_sync();
         if (sm.need_max) {
           // sweep 1: single-term scores of every pair, consumed by the row-maximum pass
-          for (int i = 0; i < npre; ++i) issue_qk(i, i / nT, 1);
-          int h2 = 3 / nT, t2 = 3 % nT;
+          for (int i = 0; i < npre; ++i) issue_qk(i, h_lo + i / nT, 1);
+          int h2 = h_lo + 3 / nT, t2 = 3 % nT;
 #pragma unroll 1
           for (int i = 0; i < n_pairs; ++i) {
             wait_consumed(i);
@@ -476,8 +539,8 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
           }
           u0 += (uint32_t)n_pairs;
         }
-        for (int i = 0; i < npre; ++i) issue_qk(i, i / nT, kPasses);
-        int h = 0, t = 0, h2 = 3 / nT, t2 = 3 % nT;
+        for (int i = 0; i < npre; ++i) issue_qk(i, h_lo + i / nT, kPasses);
+        int h = h_lo, t = 0, h2 = h_lo + 3 / nT, t2 = 3 % nT;
 #pragma unroll 1
         for (int i = 0; i < n_pairs; ++i) {
           const uint32_t t_s = tb + wait_consumed(i) * 128u;
@@ -538,8 +601,8 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
         tc05::mbar_wait(&sm.bar_lk, step_par, 32);
         tc05::fence_after_sync();
 #pragma unroll 1
-        for (int tt = 0; tt < nT; ++tt) {
-          const int bsel = tt & 1;
+        for (int tt = t_lo; tt < t_hi; ++tt) {
+          const int bsel = (tt - t_lo) & 1;
           if (n_l[bsel] > 0u) {  // the previous tile in this buffer has been consumed
             tc05::mbar_wait(&sm.bar_lfree[bsel], (n_l[bsel] - 1u) & 1u, 32);
             tc05::fence_after_sync();
@@ -685,22 +748,24 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
           sm.mask[row][0] = word0;
         }
       }
-      // query rows, 4 chunks of 8 dims at a time (8 float4 loads in flight)
+      // query rows, 4 chunks of 8 dims at a time (8 float4 loads in flight).  A CTA of a pair needs the columns of its own
+      // heads only (the peer writes the other half of the glimpse tile): 32 columns per lane instead of 64
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < (kPair ? 1 : 2); ++half) {
+        const int colb = kPair ? 64 * (int)rank + 32 * dh : 64 * dh + 32 * half;
         float4 pq[8];
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
-          pq[cc] = *reinterpret_cast<const float4*>(src1 + dh * 64 + half * 32 + cc * 4);
+          pq[cc] = *reinterpret_cast<const float4*>(src1 + colb + cc * 4);
           if (kEnv == RRNCO_ENV_ATSP && src2) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(src2 + dh * 64 + half * 32 + cc * 4));
+            const float4 w = __ldg(reinterpret_cast<const float4*>(src2 + colb + cc * 4));
             pq[cc] = make_float4(pq[cc].x + w.x, pq[cc].y + w.y, pq[cc].z + w.z, pq[cc].w + w.w);
           }
         }
         float qn2 = 0.f;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const int c8 = dh * 8 + half * 4 + cc;
+          const int c8 = (colb >> 3) + cc;
           float4 v0 = pq[2 * cc], v1 = pq[2 * cc + 1];
           if (kEnv != RRNCO_ENV_ATSP) {
 #pragma unroll
@@ -753,7 +818,7 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
       // sweep 1: masked row maxima of the single-term scores, per head
       const int row = trow;
       float mx0 = -INFINITY, mx1 = -INFINITY;
-      int h = grp / nT, t = grp - h * nT, hprev = h;
+      int h = h_lo + grp / nT, t = grp % nT, hprev = h;
 #pragma unroll 1
       for (int i = grp; i < n_pairs; i += 2) {
         if (h != hprev) {
@@ -809,7 +874,7 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
       const int row = trow;
       float off = 0.f, sum0 = 0.f, sum1 = 0.f;
       bool range_bad = false;
-      int h = grp / nT, t = grp - h * nT, hprev = -1;
+      int h = h_lo + grp / nT, t = grp % nT, hprev = -1;
 #pragma unroll 1
       for (int i = grp; i < n_pairs; i += 2) {
         if (h != hprev) {
@@ -894,12 +959,14 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
     tc05::fence_after_sync();
     GSTAMP(6);
     // glimpse of heads 4 grp .. 4 grp + 3 (decoder.py:292-293): O_h / sum + q_h -> fp16 hi | lo tiles in place over the query
+    // (CTA pair: heads h_lo + 2 grp, + 1, written into the peer's tile as well)
+    const uint32_t peer_a_hi = kPair ? map_to_rank(sm.A, rank ^ 1u) : 0u;
     if (warp_on) {
       const int row = trow;
       bool bad_operand = false;
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int h = 4 * grp + j;
+      for (int j = 0; j < (kPair ? 2 : 4); ++j) {
+        const int h = kPair ? h_lo + 2 * grp + j : 4 * grp + j;
         const float inv = __fdividef(kAScale, kKvScale * (sm.psum[0][h][row] + sm.psum[1][h][row]));
         uint32_t o[16];
         tc05::tmem_ld16(tb + 384u + 16u * h + lane_b, o);
@@ -920,11 +987,22 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
             bad_operand |= !(fabsf(g0) < 65504.f) | !(fabsf(g1) < 65504.f);
             f16s_split2(g0, g1, 1.0f, hi[e], lo[e]);
           }
-          *reinterpret_cast<uint4*>(&a_hi[offq]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(&a_lo[offq]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          const uint4 whi = make_uint4(hi[0], hi[1], hi[2], hi[3]), wlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(&a_hi[offq]) = whi;
+          *reinterpret_cast<uint4*>(&a_lo[offq]) = wlo;
+          if (kPair) {
+            st_cluster_v4(peer_a_hi + 2u * offq, whi);
+            st_cluster_v4(peer_a_hi + 2u * (offq + kRows * kE), wlo);
+          }
         }
       }
       if (bad_operand) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
+    }
+    if (kPair) {
+      // my half of the glimpse tile is in the peer's A; wait for the peer's half in mine
+      mbar_arrive_remote(map_to_rank(&sm.bar_xg, rank ^ 1u));
+      if ((warp & 3) == 0) mbar_wait_cluster(&sm.bar_xg, step_par);
+      tiled_group_sync(warp);
     }
     tc05::fence_proxy_async();
     tc05::fence_before_sync();
@@ -1068,9 +1146,9 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
         cp_async_commit();
       };
       int kblock = 0;
-      if (kStage && grp < nT) stage_block(grp * kRows, 0);
+      if (kStage && t_lo + grp < t_hi) stage_block((t_lo + grp) * kRows, 0);
 #pragma unroll 1
-      for (int t = grp; t < nT; t += 2) {
+      for (int t = t_lo + grp; t < t_hi; t += 2) {
         const int nb16 = t == nT - 1 ? nb_last : 8;
         uint32_t mrow[4];
 #pragma unroll 1
@@ -1079,7 +1157,7 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
             cp_async_wait<0>();
             tiled_group_sync(warp);  // block `kblock` landed for every thread; everyone is done reading the other buffer
             if (kb + 1 < nb16) stage_block(t * kRows + (kb + 1) * 16, (kblock + 1) & 1);
-            else if (t + 2 < nT) stage_block((t + 2) * kRows, (kblock + 1) & 1);
+            else if (t + 2 < t_hi) stage_block((t + 2) * kRows, (kblock + 1) & 1);
           }
           if (kb == 0) {
             GSTAMP(14);
@@ -1197,29 +1275,56 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
       GSTAMP(14);
       tiled_sync();
       GSTAMP(16);
-      if (grp == 0 && warp_on) {
-        const float m0 = sm.xf[0][0][row], m1 = sm.xf[0][1][row];
-        const float mx = fmaxf(m0, m1);
-        const float tot = sm.xf[1][0][row] * fexp(m0 - mx) + sm.xf[1][1][row] * fexp(m1 - mx);
-        const float se = flog(tot);
-        int win = 0;  // larger key wins, ties -> lower index
+      if (grp == 0) {
+        // this CTA's partial over its key tiles: the two groups merged (larger key wins, ties -> lower index)
+        float m0 = sm.xf[0][0][row], m1 = sm.xf[0][1][row];
+        float mx = fmaxf(m0, m1);
+        float tot = sm.xf[1][0][row] * fexp(m0 - mx) + sm.xf[1][1][row] * fexp(m1 - mx);
+        int win = 0;
         if (sm.xf[2][1][row] > sm.xf[2][0][row] || (sm.xf[2][1][row] == sm.xf[2][0][row] && sm.xi[1][row] < sm.xi[0][row])) win = 1;
+        float bkey = sm.xf[2][win][row], bval = sm.xf[3][win][row];
         int act = sm.xi[win][row];
-        if (act == 0x7fffffff) act = 0;
-        if (p.mode == RRNCO_DECODE_EVALUATE) {
-          act = forced;
-          win = (act >> 7) & 1;  // the group that owns the forced column recorded its value
+        // evaluate: only the group that owns the forced column recorded its value (-inf elsewhere)
+        if (p.mode == RRNCO_DECODE_EVALUATE) bval = fmaxf(sm.xf[3][0][row], sm.xf[3][1][row]);
+        if (kPair) {
+          // exchange the partial with the peer CTA and merge in RANK order: both CTAs compute bit-identical results
+          const uint32_t peer = rank ^ 1u;
+          st_cluster_b32(map_to_rank(&sm.xpf[0][row], peer), __float_as_uint(mx));
+          st_cluster_b32(map_to_rank(&sm.xpf[1][row], peer), __float_as_uint(tot));
+          st_cluster_b32(map_to_rank(&sm.xpf[2][row], peer), __float_as_uint(bkey));
+          st_cluster_b32(map_to_rank(&sm.xpf[3][row], peer), __float_as_uint(bval));
+          st_cluster_b32(map_to_rank(&sm.xpi[row], peer), (uint32_t)act);
+          mbar_arrive_remote(map_to_rank(&sm.bar_xs, peer));
+          mbar_wait_cluster(&sm.bar_xs, step_par);
+          const float mp = sm.xpf[0][row], sp = sm.xpf[1][row], kp = sm.xpf[2][row], vp = sm.xpf[3][row];
+          const int ip = sm.xpi[row];
+          const float ma = rank ? mp : mx, mb = rank ? mx : mp;      // a = rank 0 (lower key tiles), b = rank 1
+          const float sa = rank ? sp : tot, sb = rank ? tot : sp;
+          const float ka = rank ? kp : bkey, kb2 = rank ? bkey : kp;
+          const float va = rank ? vp : bval, vb2 = rank ? bval : vp;
+          const int ia = rank ? ip : act, ib = rank ? act : ip;
+          mx = fmaxf(ma, mb);
+          tot = sa * fexp(ma - mx) + sb * fexp(mb - mx);
+          const bool second = kb2 > ka || (kb2 == ka && ib < ia);
+          bkey = second ? kb2 : ka;
+          bval = p.mode == RRNCO_DECODE_EVALUATE ? fmaxf(va, vb2) : (second ? vb2 : va);
+          act = second ? ib : ia;
         }
-        const float chosen = __fsub_rn(__fsub_rn(sm.xf[3][win][row], mx), se);
-        const bool feasible = (sm.mask[row][act >> 5] >> (act & 31)) & 1u;
-        if (!feasible && sm.active[row]) atomicOr(p.status, RRNCO_DEV_INFEASIBLE);
-        const bool count_leg = kEnv != RRNCO_ENV_ATSP || t_out > 0;
-        len_acc += (double)tiled_transition<kEnv>(sm, N, row, act, D, U, closed, count_leg);
-        if (kEnv == RRNCO_ENV_ATSP && t_out == 0) sm.first[row] = (uint16_t)act;
-        lp_acc += (double)chosen;
-        if (sm.active[row] && t_out < p.t_cap) {
-          p.actions[rg * p.t_cap + t_out] = act;
-          if (p.logprob) p.logprob[rg * p.t_cap + t_out] = chosen;
+        if (warp_on) {
+          const float se = flog(tot);
+          if (act == 0x7fffffff) act = 0;
+          if (p.mode == RRNCO_DECODE_EVALUATE) act = forced;
+          const float chosen = __fsub_rn(__fsub_rn(bval, mx), se);
+          const bool feasible = (sm.mask[row][act >> 5] >> (act & 31)) & 1u;
+          if (!feasible && sm.active[row]) atomicOr(p.status, RRNCO_DEV_INFEASIBLE);
+          const bool count_leg = kEnv != RRNCO_ENV_ATSP || t_out > 0;
+          len_acc += (double)tiled_transition<kEnv>(sm, N, row, act, D, U, closed, count_leg);
+          if (kEnv == RRNCO_ENV_ATSP && t_out == 0) sm.first[row] = (uint16_t)act;
+          lp_acc += (double)chosen;
+          if (sm.active[row] && t_out < p.t_cap && rank == 0u) {
+            p.actions[rg * p.t_cap + t_out] = act;
+            if (p.logprob) p.logprob[rg * p.t_cap + t_out] = chosen;
+          }
         }
       }
     }
@@ -1230,7 +1335,7 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
   }
 
   // ---------------- exit: close the tours, publish per-rollout sums ----------------
-  if (tid < kRows && sm.active[tid]) {  // tid < 128 = group 0: the threads that own len_acc / lp_acc
+  if (tid < kRows && sm.active[tid] && rank == 0u) {  // tid < 128 = group 0: the threads that own len_acc / lp_acc
     const int row = tid;
     const int64_t r = (int64_t)(tile * p.tile_rows + row) * p.n_inst + b;
     const int last = sm.cur[row];
@@ -1245,8 +1350,10 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
     p.ws_lp[r] = lp_acc;
   }
   if (tid == 0) {
-    p.ws_tile_steps[blockIdx.x] = t_out;
-    atomicMax(p.max_steps_out, t_out);
+    if (rank == 0u) {
+      p.ws_tile_steps[tile_id] = t_out;
+      atomicMax(p.max_steps_out, t_out);
+    }
     sm.exit_flag = 1;
   }
   tc05::fence_before_sync();
@@ -1256,9 +1363,9 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
   if (warp == 0) tc05::tmem_dealloc(sm.tmem_base, 512);
 }
 
-template <int kEnv, int kPasses>
+template <int kEnv, int kPasses, bool kPair>
 static int launch_tiled(const RolloutParams& p, cudaStream_t st) {
-  auto kern = rollout_tiled_kernel<kEnv, kPasses>;
+  auto kern = rollout_tiled_kernel<kEnv, kPasses, kPair>;
   static PerDeviceOnce once;
   if (once.first()) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TiledSmem<kEnv>)) != cudaSuccess) {
@@ -1266,9 +1373,21 @@ static int launch_tiled(const RolloutParams& p, cudaStream_t st) {
       return RRNCO_ERR_CUDA;
     }
   }
-  const int64_t grid = p.n_inst * p.n_tiles;
+  const int64_t grid = p.n_inst * p.n_tiles * (kPair ? 2 : 1);
   if (grid <= 0 || grid > 0x7fffffffLL) return RRNCO_ERR_UNSUPPORTED;
-  kern<<<(unsigned)grid, kGThreads, sizeof(TiledSmem<kEnv>), st>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kGThreads);
+  cfg.dynamicSmemBytes = sizeof(TiledSmem<kEnv>);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess) return RRNCO_ERR_CUDA;
   return rrnco_launch_status();
 }
 
@@ -1294,13 +1413,20 @@ int phase_cycles_tiled(long long* h_out, int reset) {
   }
   return RRNCO_OK;
 }
+// CTA pairs when the tiles leave more than half of the SMs idle
+bool tiled_use_pairs(int64_t n_tiles_total) {
+  const int sms = device_sm_count();
+  return g_tiled_pairs && sms > 0 && 2 * n_tiles_total <= sms;
+}
 int dispatch_env_tiled(const RolloutParams& p, int env, int passes, cudaStream_t st) {
   static_assert(sizeof(TiledSmem<RRNCO_ENV_RCVRPTW>) <= 232448, "one CTA per SM: at most 227 KB of shared memory");
   static_assert(sizeof(TiledSmem<RRNCO_ENV_ATSP>) <= 232448 && sizeof(TiledSmem<RRNCO_ENV_RCVRP>) <= 232448, "shared memory");
+  const bool pairs = tiled_use_pairs(p.n_inst * p.n_tiles);
+  (void)passes;  // the key-tiled kernel is built fp32-faithful only (three-term products)
   switch (env) {
-    case RRNCO_ENV_ATSP: return passes == 1 ? launch_tiled<RRNCO_ENV_ATSP, 1>(p, st) : launch_tiled<RRNCO_ENV_ATSP, 3>(p, st);
-    case RRNCO_ENV_RCVRP: return passes == 1 ? launch_tiled<RRNCO_ENV_RCVRP, 1>(p, st) : launch_tiled<RRNCO_ENV_RCVRP, 3>(p, st);
-    case RRNCO_ENV_RCVRPTW: return passes == 1 ? launch_tiled<RRNCO_ENV_RCVRPTW, 1>(p, st) : launch_tiled<RRNCO_ENV_RCVRPTW, 3>(p, st);
+    case RRNCO_ENV_ATSP: return pairs ? launch_tiled<RRNCO_ENV_ATSP, 3, true>(p, st) : launch_tiled<RRNCO_ENV_ATSP, 3, false>(p, st);
+    case RRNCO_ENV_RCVRP: return pairs ? launch_tiled<RRNCO_ENV_RCVRP, 3, true>(p, st) : launch_tiled<RRNCO_ENV_RCVRP, 3, false>(p, st);
+    case RRNCO_ENV_RCVRPTW: return pairs ? launch_tiled<RRNCO_ENV_RCVRPTW, 3, true>(p, st) : launch_tiled<RRNCO_ENV_RCVRPTW, 3, false>(p, st);
     default: return RRNCO_ERR_BAD_ARG;
   }
 }
