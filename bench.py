@@ -571,7 +571,49 @@ def run_ours(args, rank, world, local_rank):
                 "note": "the city matrix (4 / 8 MB) is L2-resident and n of 1000 columns per row are wanted: bound by L2 "
                         "sector requests, not HBM (ncu: profiles/r1_ncu_env_kernels_v4.txt)"}
 
+    def nab_probe():
+        """Encoder hot spot: one DistAngleFusion module (gating neural adaptive bias, ATSP / RCVRP
+        variant) over the augmented batch of the headline config -- the encoder evaluates 12 of them per encode."""
+        torch.manual_seed(1234)
+        mod = rb.DistAngleFusion(128).to(dev)
+        Bn = B * N_AUG
+        g = torch.Generator(device=dev).manual_seed(11)
+        coords = torch.rand(Bn, N_LOC + 1, 2, device=dev, generator=g)
+        cost = torch.rand(Bn, N_LOC + 1, N_LOC + 1, device=dev, generator=g)
+        with torch.no_grad():
+            ms = time_launch(lambda: mod(coords, cost), reps=10)
+            ms_t = time_launch(lambda: mod(coords, cost.transpose(1, 2)), reps=10)
+        pairs = Bn * (N_LOC + 1) ** 2
+        entry = {"kernel": "rrnco::nab_gating_kernel (DistAngleFusion.forward, attn_freenet.py:242-289, collapsed to four "
+                           "E-vectors per module; CUDA cores, nothing materialised)",
+                 "instances": Bn, "pairs": pairs, "ms_per_launch": ms, "ms_per_launch_transposed_cost": ms_t,
+                 "algorithmic_bytes_per_launch": 8 * pairs, "achieved": 8 * pairs / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                 "fp32_lane_ops_per_pair": 1024, "fp32_lane_ops_per_s": 1024 * pairs / (ms * 1e-3),
+                 "fp32_peak_lane_ops_per_s": 148 * 128 * 1.965e9,
+                 "reference_flops_per_pair": 4 * 128 * 128 + 8 * 128,
+                 "reference_activation_bytes_per_pair": 2 * 128 * 4 * 2,
+                 "note": "compute-bound on the fp32 pipes (2 x 128 relu-FMAs + 4 x 128 FMAs per pair), not HBM-bound: "
+                         "`frac` is the HBM figure for 4 B read + 4 B written per pair, `fp32_frac` the binding one"}
+        entry["fp32_frac"] = entry["fp32_lane_ops_per_s"] / entry["fp32_peak_lane_ops_per_s"]
+        if not args.no_cpu_baseline:
+            from oracle import encoder as oenc
+            torch.set_num_threads(os.cpu_count() or 1)
+            k = 8
+            pc = {kk: v.detach().cpu() for kk, v in mod.state_dict().items()}
+            cc, cm = coords[:k].cpu(), cost[:k].cpu()
+            with torch.inference_mode():
+                oenc.dist_angle_fusion(pc, cc[:1], cm[:1])
+                t0 = time.perf_counter()
+                oenc.dist_angle_fusion(pc, cc, cm)
+                dt = time.perf_counter() - t0
+            entry["cpu_baseline"] = {"value": k / dt, "unit": "instances/s per module", "cores": os.cpu_count() or 1, "kind": "port",
+                                     "sample": f"{k} instances, {dt:.2f} s"}
+            entry["value"] = Bn / (ms * 1e-3)
+            entry["value_unit"] = "instances/s per module"
+        return entry
+
     env_probe = env_step_probe() if rank == 0 else None
+    nab_entry = nab_probe() if rank == 0 else None
     gat_probe = gather_probe() if rank == 0 else None
     atsp_probe = atsp_step_probe() if rank == 0 else None
     tw_probe = rcvrptw_step_probe() if rank == 0 else None
@@ -643,7 +685,8 @@ def run_ours(args, rank, world, local_rank):
                                                      "measured HBM peak; the fused kernel's real DRAM traffic is `traffic`"}},
         }
         for probe, key in ((env_probe, "rcvrp_step_dram_bytes"), (gat_probe, "gather_dram_bytes"),
-                           (atsp_probe, "atsp_step_dram_bytes"), (tw_probe, "rcvrptw_step_dram_bytes")):
+                           (atsp_probe, "atsp_step_dram_bytes"), (tw_probe, "rcvrptw_step_dram_bytes"),
+                           (nab_entry, "nab_dram_bytes")):
             probe["peak"] = hbm_peak
             probe["frac"] = probe["achieved"] / hbm_peak
             probe["dram_bytes_measured"] = stamp.get(key)  # ncu dram__bytes_read + write of this build (None: not captured)
@@ -653,6 +696,7 @@ def run_ours(args, rank, world, local_rank):
         line["env_step_atsp"] = atsp_probe
         line["env_step_rcvrptw"] = tw_probe
         line["gather"] = gat_probe
+        line["encoder_nab"] = nab_entry
         if cfg_block is not None:
             line["configs"] = cfg_block
         if not args.no_cpu_baseline:

@@ -311,6 +311,29 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
                   float* logprob_out, float* loglik_out, float* norm_reward_out, float* real_reward_out,
                   int32_t* max_steps_out, uint32_t* status, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Encoder hot spot: gating neural adaptive bias of an attention-free block, variant without the
+ * duration channel -- DistAngleFusion.forward, rrnco/models/nn/attn_freenet.py:242-289 (ATSP / RCVRP encoders,
+ * rrnco/models/encoder.py:63-66), times the block's `alpha` (attn_freenet.py:424-430).
+ *   adapt_bias[b,i,j] = scale * out_lin( g * dist_emb(c) + (1 - g) * angle_emb(theta) ),  g = sigmoid(gate([dist_emb, angle_emb]))
+ *   c = cost[b,i,j] (cost[b,j,i] when transpose_cost != 0: the col-encoding block sees the transposed matrix with the
+ *   same coords, attn_freenet.py:480-486), theta = atan2(y_i - y_j, x_i - x_j).
+ * Upstream materialises the two [B,N,N,E] embeddings; here the module is collapsed once per call into four E-vectors
+ * (rrnco_nab_pack, fp64 accumulation: the second Linear of each MLP, the gate and out_lin are linear in the hidden
+ * vectors) and evaluated per pair on the CUDA cores: 4 B read + 4 B written per pair, nothing materialised.
+ *   rrnco_nab_pack: the module's parameters in nn.Linear layout (dist_emb.0 / .2, angle_emb.0 / .2: weight [E,1] / [E,E],
+ *                   bias [E]; gate.0: weight [1,2E], bias [1]; out_lin: weight [1,E], bias [1]) -> packed fp32
+ *                   [rrnco_nab_packed_floats()], 16-byte aligned.
+ *   rrnco_nab_gating: coords fp32 [B,N,2] (8-byte aligned), cost fp32 [B,N,N], out fp32 [B,N,N].
+ * Forward only (test.py / validation path). ---------------------------------------------------- */
+int64_t rrnco_nab_packed_floats(void);
+int rrnco_nab_pack(const float* dist_w1, const float* dist_b1, const float* dist_w2, const float* dist_b2,
+                   const float* angle_w1, const float* angle_b1, const float* angle_w2, const float* angle_b2,
+                   const float* gate_w, const float* gate_b, const float* out_w, const float* out_b, float* packed,
+                   void* stream);
+int rrnco_nab_gating(int64_t n_inst, int32_t n_nodes, const float* coords, const float* cost, int32_t transpose_cost,
+                     const float* packed, float scale, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

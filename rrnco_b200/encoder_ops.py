@@ -1,0 +1,84 @@
+"""Encoder hot spot on the B200: the gating neural adaptive bias of an attention-free block.
+
+`DistAngleFusion` mirrors `rrnco/models/nn/attn_freenet.py:201-289` (same constructor, same parameter names, so the
+reference module's state_dict loads unchanged); its forward is ONE kernel (`rrnco_nab_gating`) that never materialises the
+[B, N, N, E] embeddings upstream builds twice per block.  `patch_encoder` swaps it into an upstream `RRNetEncoder`
+(`encoder.net.layers[i].{row,col}_encoding_block.angle_distance_fusion`) for the inference path (test.py / validation).
+The duration-channel variant (rcvrptw: Linear(3E, E) -> SiLU -> Linear(E, 3) gate, softmax with a temperature) keeps
+upstream's module: its gate is not linear in the embeddings, so it does not collapse to scalar functions.
+No CPU fallback: a host tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+
+class DistAngleFusion(nn.Module):
+    def __init__(self, embed_dim: int = 128, use_duration_matrix: bool = False):
+        super().__init__()
+        if embed_dim != 128:
+            raise NotImplementedError("the kernels are built for embed_dim = 128 (experiment/rrnet.yaml)")
+        if use_duration_matrix:
+            raise NotImplementedError("duration-channel gate (rcvrptw): use the reference module; only the ATSP / RCVRP "
+                                      "variant (attn_freenet.py:239, encoder.py:63-66) collapses to the fused kernel")
+        self.embed_dim = embed_dim
+        self.dist_emb = nn.Sequential(nn.Linear(1, embed_dim), nn.ReLU(), nn.Linear(embed_dim, embed_dim))
+        self.angle_emb = nn.Sequential(nn.Linear(1, embed_dim), nn.ReLU(), nn.Linear(embed_dim, embed_dim))
+        self.gate = nn.Sequential(nn.Linear(embed_dim * 2, 1), nn.Sigmoid())
+        self.out_lin = nn.Linear(embed_dim, 1)
+        self._packed = None
+        self._packed_key = None
+
+    def packed_parameters(self) -> torch.Tensor:
+        """The module collapsed into four E-vectors + constants (rrnco_nab_pack); cached until a parameter changes."""
+        ps = [self.dist_emb[0].weight, self.dist_emb[0].bias, self.dist_emb[2].weight, self.dist_emb[2].bias,
+              self.angle_emb[0].weight, self.angle_emb[0].bias, self.angle_emb[2].weight, self.angle_emb[2].bias,
+              self.gate[0].weight, self.gate[0].bias, self.out_lin.weight, self.out_lin.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._packed is None or self._packed_key != key:
+            dev = ps[0].device
+            packed = torch.empty(_lib.lib().rrnco_nab_packed_floats(), dtype=torch.float32, device=dev)
+            cont = [p.detach().float().contiguous() for p in ps]
+            call("rrnco_nab_pack", *[ptr(p) for p in cont], ptr(packed), stream_ptr(dev))
+            self._packed, self._packed_key = packed, key
+        return self._packed
+
+    def forward(self, coords: torch.Tensor, cost_mat: torch.Tensor, duration_mat=None, scale: float = 1.0) -> torch.Tensor:
+        """adapt_bias [B, N, N] (times `scale`, e.g. the block's alpha).  `cost_mat` may be the transposed VIEW the
+        col-encoding block passes (attn_freenet.py:480-486): it is read through its base, never copied."""
+        if duration_mat is not None:
+            raise NotImplementedError("duration-channel gate: use the reference module")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("forward-only kernel: call under torch.no_grad() / inference_mode (test.py path)")
+        B, N, _ = cost_mat.shape
+        coords = coords.float().contiguous()
+        transposed = 0
+        if not cost_mat.is_contiguous() and cost_mat.transpose(1, 2).is_contiguous():
+            cost_mat, transposed = cost_mat.transpose(1, 2), 1
+        cost_mat = cost_mat.float().contiguous()
+        out = torch.empty((B, N, N), dtype=torch.float32, device=cost_mat.device)
+        call("rrnco_nab_gating", B, N, ptr(coords), ptr(cost_mat), transposed, ptr(self.packed_parameters()), float(scale),
+             ptr(out), stream_ptr(cost_mat.device))
+        return out
+
+
+def patch_encoder(encoder: nn.Module) -> int:
+    """Replaces every gating `DistAngleFusion` without duration channel inside an upstream encoder (attribute
+    `angle_distance_fusion` of the attention-free blocks, attn_freenet.py:386-389) by the kernel-backed module with the
+    same parameters.  Returns the number of modules replaced."""
+    n = 0
+    for block in encoder.modules():
+        ref = getattr(block, "angle_distance_fusion", None)
+        if ref is None or isinstance(ref, DistAngleFusion) or hasattr(ref, "dur_emb"):
+            continue
+        mine = DistAngleFusion(ref.embed_dim).to(next(ref.parameters()).device)
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        block.angle_distance_fusion = mine
+        n += 1
+    return n

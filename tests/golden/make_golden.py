@@ -18,6 +18,8 @@ It puts `oracle/shims` (stand-ins for rl4co / tensordict / torchrl, see oracle/s
   generator_*.npz     Lazy{RCVRP,ATSP,RMTVRP}Generator._process_real_world_data / subsample_problems with the
                       uniform draws they consumed               -> rrnco/envs/*/generator_lazy.py, rmtvrp/generator.py
   sampler_outliers.npz Real_World_Sampler.sample on a city with > 1e5 entries -> rrnco/envs/rmtvrp/sampler.py:41-60
+  encoder_nab.npz     DistAngleFusion (both gate variants) + AFTFull of the encoder's attention-free block
+                                                                -> rrnco/models/nn/attn_freenet.py:201-327
 
 Inputs are produced with oracle.synth (only as an input generator, nothing of the oracle's
 arithmetic is recorded).
@@ -273,7 +275,42 @@ def gen_outliers():
     print("sampler outliers ok", s["distance_matrix"].max())
 
 
+def gen_encoder_nab():
+    """DistAngleFusion (gating neural adaptive bias, both gate variants), the block's `alpha` scaling and AFTFull of the
+    UNMODIFIED reference (rrnco/models/nn/attn_freenet.py:201-327, 417-432) on a small instance batch: parameters
+    (state_dict), inputs and outputs.  The col-encoding block sees the TRANSPOSED cost matrix with the same coords
+    (attn_freenet.py:480-486): recorded too."""
+    from rrnco.models.nn.attn_freenet import AFTFull, DistAngleFusion
+    torch.manual_seed(77)
+    B, N, E = 3, 13, 128
+    g = torch.Generator().manual_seed(78)
+    coords = torch.rand(B, N, 2, generator=g)
+    cost = torch.rand(B, N, N, generator=g) * (1 - torch.eye(N))
+    dur = torch.rand(B, N, N, generator=g) * (1 - torch.eye(N))
+    rec = {"coords": coords.numpy(), "cost": cost.numpy(), "dur": dur.numpy()}
+    with torch.no_grad():
+        for tag, use_dur in (("nodur", False), ("dur", True)):
+            m = DistAngleFusion(E, use_duration_matrix=use_dur)
+            for q in m.parameters():  # default init gives a nearly constant bias: widen it so that every term matters
+                q.mul_(3.0)
+            for k, v in m.state_dict().items():
+                rec[f"{tag}.param.{k}"] = v.numpy()
+            rec[f"{tag}.bias"] = m(coords, cost, dur if use_dur else None).numpy()
+            rec[f"{tag}.bias_T"] = m(coords, cost.transpose(1, 2), dur.transpose(1, 2) if use_dur else None).numpy()
+        aft = AFTFull(dim=E, hidden_dim=E)
+        for k, v in aft.state_dict().items():
+            rec[f"aft.param.{k}"] = v.numpy()
+        x, y = torch.randn(B, N, E, generator=g), torch.randn(B, N, E, generator=g)
+        rec["aft.x"], rec["aft.y"] = x.numpy(), y.numpy()
+        rec["aft.out"] = aft(x, y=y, adapt_bias=torch.from_numpy(rec["nodur.bias"]) * 1.7).numpy()
+    np.savez_compressed(os.path.join(HERE, "encoder_nab.npz"), **rec)
+    print("encoder_nab", {k: v.shape for k, v in rec.items() if not k.startswith(("nodur.param", "dur.param", "aft.param"))})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder":  # fixture of the encoder hot spot (round 2, second half)
+        gen_encoder_nab()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "new":  # fixtures added in round 2 (the others regenerate bit-identically)
         gen_generators()
         gen_outliers()
@@ -290,3 +327,4 @@ if __name__ == "__main__":
     gen_augment()
     gen_generators()
     gen_outliers()
+    gen_encoder_nab()
