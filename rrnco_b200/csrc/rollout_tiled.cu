@@ -1360,6 +1360,10 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
   tiled_sync();
   if (tid == 0) tc05::mbar_arrive(&sm.bar_step);  // releases the producer ...
   tc05::mbar_arrive(&sm.bar_q);                   // ... and the issuer (both see exit_flag)
+  // CTA pair: neither CTA leaves while the other could still touch its shared memory.  (The step protocol already implies
+  // it -- the last remote accesses precede the partner's last wait -- this makes it explicit; exited threads of the
+  // producer / issuer warps count as arrived.)
+  if (kPair) cluster_sync_all();
   if (warp == 0) tc05::tmem_dealloc(sm.tmem_base, 512);
 }
 

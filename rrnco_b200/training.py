@@ -26,6 +26,9 @@ import torch.nn.functional as F
 from .tdlite import TensorDictLite, batchify
 
 
+ATTENTION_IMPL = "sdpa"  # "sdpa" | "matmul": how batched_logprobs evaluates the masked 8-head attention
+
+
 def collect_decode_inputs(decoder, env, td, actions: torch.Tensor, num_starts: int) -> dict:
     """Replays `actions` [R, T] (R = num_starts * n_inst, multistart order) through the env's CUDA step kernels and
     records, for every decoder call (steps 1..T-1; step 0 is the forced POMO start, decoding.py:186-192), what the
@@ -102,7 +105,12 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
         else:               # context.py:18-31: [current-node embedding, state scalars]
             ctx = torch.cat([emb_cur, per_inst(inputs["ctx_state"][t0:t1]).to(emb_cur.dtype)], -1)
         q = F.linear(ctx, W)                                               # [n_inst, L, E]
-        h = F.scaled_dot_product_attention(heads(q), kh, vh, attn_mask=mask.unsqueeze(1))  # decoder.py:281-293
+        if ATTENTION_IMPL == "sdpa":
+            h = F.scaled_dot_product_attention(heads(q), kh, vh, attn_mask=mask.unsqueeze(1))  # decoder.py:281-293
+        else:  # explicit: head dim 16 and 101 keys are far from the tile shapes of the fused SDPA kernels
+            sc = torch.matmul(heads(q), kh.transpose(-1, -2)) * (1.0 / math.sqrt(E // H))
+            sc = sc.masked_fill(~mask.unsqueeze(1), float("-inf"))
+            h = torch.matmul(torch.softmax(sc, dim=-1), vh)
         g = h.transpose(1, 2).flatten(-2) + q
         g = F.linear(F.relu(F.linear(g, w1, b1)), w2, b2) + g              # decoder.py:296
         logits = torch.bmm(g, lk.transpose(1, 2)).float() / math.sqrt(E)   # [n_inst, L, N]

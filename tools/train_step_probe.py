@@ -32,8 +32,11 @@ def sync_time():
     return time.perf_counter()
 
 
-for it in range(5):
-    ac = torch.bfloat16 if it >= 3 else None
+from rrnco_b200 import training as _tr  # noqa: E402
+for it in range(int(os.environ.get("ITERS", 5))):
+    ac = torch.bfloat16 if it >= 3 and not os.environ.get("FP32_ONLY") else None
+    _tr.ATTENTION_IMPL = os.environ.get("ATTN", "sdpa")
+    torch.backends.cuda.matmul.allow_tf32 = bool(int(os.environ.get("TF32", 0)))
     torch.cuda.reset_peak_memory_stats()
     t0 = sync_time()
     with torch.no_grad():
