@@ -325,6 +325,9 @@ int rrnco_rollout(int32_t env, int32_t n_nodes, int64_t n_inst, int32_t n_starts
  *                   bias [E]; gate.0: weight [1,2E], bias [1]; out_lin: weight [1,E], bias [1]) -> packed fp32
  *                   [rrnco_nab_packed_floats()], 16-byte aligned.
  *   rrnco_nab_gating: coords fp32 [B,N,2] (8-byte aligned), cost fp32 [B,N,N], out fp32 [B,N,N].
+ *                   variant 0 (default): each collapsed function is piecewise linear in its scalar with <= E breakpoints;
+ *                   the pack holds them sorted with per-segment slope / intercept (fp64 sums), the kernel does two
+ *                   8-probe segment searches + 4 FMAs per pair.  variant 1: the sum over the E hidden units (cross-check).
  * Forward only (test.py / validation path). ---------------------------------------------------- */
 int64_t rrnco_nab_packed_floats(void);
 int rrnco_nab_pack(const float* dist_w1, const float* dist_b1, const float* dist_w2, const float* dist_b2,
@@ -332,7 +335,7 @@ int rrnco_nab_pack(const float* dist_w1, const float* dist_b1, const float* dist
                    const float* gate_w, const float* gate_b, const float* out_w, const float* out_b, float* packed,
                    void* stream);
 int rrnco_nab_gating(int64_t n_inst, int32_t n_nodes, const float* coords, const float* cost, int32_t transpose_cost,
-                     const float* packed, float scale, float* out, void* stream);
+                     const float* packed, float scale, int32_t variant, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,15 +12,25 @@
 // materialised, the kernel reads the cost entry (4 B) and writes the bias (4 B).  This is NOT GEMM-shaped work (four output
 // columns per pair, an A operand that would have to be generated element by element): no tensor cores.
 //
-// Layout of `packed` (fp32): [E][8] = (w1d, b1d, ug_d, uo_d, w1a, b1a, ug_a, uo_a) per hidden unit k, then 4 constants
-// (gate constant, wo . b2d, wo . b2a, bo).
+// Each of the four collapsed functions  f(x) = sum_k u_k relu(w_k x + b_k)  is PIECEWISE LINEAR in its scalar argument with
+// at most E breakpoints t_k = -b_k / w_k.  rrnco_nab_pack therefore also sorts the breakpoints of the two MLPs and tabulates
+// slope and intercept of the gate and output functions on each of the E + 1 segments (fp64 prefix sums): the default
+// variant of the kernel finds the segment of the cost entry and of the angle by binary search in shared memory and
+// evaluates four FMAs -- ~100 instructions per pair instead of ~1000, which moves the kernel from the fp32 pipes toward
+// the HBM bound (4 B read + 4 B written per pair).  The brute-force sum over the hidden units (variant 1) is the cross-check.
+//
+// Layout of `packed` (fp32): [E][8] = (w1d, b1d, ug_d, uo_d, w1a, b1a, ug_a, uo_a) per hidden unit k, 4 constants
+// (gate constant, wo . b2d, wo . b2a, bo); then per MLP (dist, angle): E sorted breakpoints, (E + 1) x 4 segment
+// coefficients (gate slope, gate intercept, out slope, out intercept).
 #include "common.cuh"
 
 namespace rrnco {
 
 constexpr int kNabThreads = 256;
 constexpr int kNabPairs = 4;                                  // pairs per thread: every parameter load serves four pairs
-constexpr int kNabPacked = kE * 8 + 4;
+constexpr int kNabBrute = kE * 8 + 4;
+constexpr int kNabTable = kE + (kE + 1) * 4;                  // sorted breakpoints + segment coefficients of one MLP
+constexpr int kNabPacked = kNabBrute + 2 * kNabTable;
 
 // one block of kE threads: thread k collapses hidden unit k
 __global__ void __launch_bounds__(kE) nab_pack_kernel(const float* __restrict__ w1d, const float* __restrict__ b1d,
@@ -52,6 +62,37 @@ __global__ void __launch_bounds__(kE) nab_pack_kernel(const float* __restrict__ 
     float* c = packed + kE * 8;
     c[0] = (float)cg; c[1] = (float)cod; c[2] = (float)coa; c[3] = bo[0];
   }
+  // ---- piecewise-linear tables of the two MLPs ----
+  __shared__ double s_t[kE], s_w[kE], s_b[kE], s_ug[kE], s_uo[kE];
+  __shared__ int s_rank[kE];
+#pragma unroll 1
+  for (int mlp = 0; mlp < 2; ++mlp) {
+    const double w = mlp ? (double)w1a[k] : (double)w1d[k], bb = mlp ? (double)b1a[k] : (double)b1d[k];
+    __syncthreads();
+    s_w[k] = w; s_b[k] = bb; s_ug[k] = mlp ? uga : ugd; s_uo[k] = mlp ? uoa : uod;
+    s_t[k] = w != 0.0 ? -bb / w : INFINITY;  // a unit with zero slope never switches: no breakpoint
+    __syncthreads();
+    int r = 0;
+    for (int j = 0; j < kE; ++j) r += (s_t[j] < s_t[k] || (s_t[j] == s_t[k] && j < k)) ? 1 : 0;
+    s_rank[k] = r;
+    float* tab = packed + kNabBrute + mlp * kNabTable;
+    tab[r] = (float)s_t[k];
+    __syncthreads();
+    // segment s = arguments with exactly s breakpoints strictly below them; unit j is active there iff
+    // (w_j > 0 and rank_j < s) or (w_j < 0 and rank_j >= s) or (w_j == 0 and b_j > 0)
+    for (int sgm = k; sgm <= kE; sgm += kE) {
+      double sg = 0.0, tg = 0.0, so = 0.0, to = 0.0;
+      for (int j = 0; j < kE; ++j) {
+        const bool on = s_w[j] > 0.0 ? s_rank[j] < sgm : (s_w[j] < 0.0 ? s_rank[j] >= sgm : s_b[j] > 0.0);
+        if (on) {
+          sg += s_ug[j] * s_w[j]; tg += s_ug[j] * s_b[j];
+          so += s_uo[j] * s_w[j]; to += s_uo[j] * s_b[j];
+        }
+      }
+      float* q4 = tab + kE + sgm * 4;
+      q4[0] = (float)sg; q4[1] = (float)tg; q4[2] = (float)so; q4[3] = (float)to;
+    }
+  }
 }
 
 // grid (instances, chunks of kNabThreads * kNabPairs pairs); thread t of a chunk owns pairs t, t + 256, t + 512, t + 768 of
@@ -60,9 +101,9 @@ __global__ void __launch_bounds__(kNabThreads) nab_gating_kernel(int N, const fl
                                                                  const float* __restrict__ cost, int transpose_cost,
                                                                  const float* __restrict__ packed, float scale,
                                                                  float* __restrict__ out) {
-  __shared__ __align__(16) float sp[kNabPacked];
+  __shared__ __align__(16) float sp[kNabBrute];
   const int tid = threadIdx.x;
-  for (int i = tid; i < kNabPacked; i += kNabThreads) sp[i] = packed[i];
+  for (int i = tid; i < kNabBrute; i += kNabThreads) sp[i] = packed[i];
   __syncthreads();
   const int64_t b = blockIdx.x;
   const int NN = N * N;
@@ -111,6 +152,49 @@ __global__ void __launch_bounds__(kNabThreads) nab_gating_kernel(int N, const fl
   }
 }
 
+// number of sorted breakpoints strictly below x (lower bound over kE = 128 entries, 8 shared-memory probes)
+__device__ __forceinline__ int nab_segment(const float* __restrict__ t, float x) {
+  int pos = 0;
+#pragma unroll
+  for (int step = kE / 2; step >= 1; step >>= 1) pos += t[pos + step - 1] < x ? step : 0;
+  return pos + (t[pos] < x ? 1 : 0);
+}
+
+// Table variant: thread t of a chunk owns pairs t, t + 256, ... (coalesced loads / stores), one segment search per scalar.
+__global__ void __launch_bounds__(kNabThreads) nab_gating_table_kernel(int N, const float* __restrict__ coords,
+                                                                       const float* __restrict__ cost, int transpose_cost,
+                                                                       const float* __restrict__ packed, float scale,
+                                                                       float* __restrict__ out) {
+  __shared__ __align__(16) float st[2 * kNabTable + 4];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * kNabTable; i += kNabThreads) st[i] = packed[kNabBrute + i];
+  if (tid < 4) st[2 * kNabTable + tid] = packed[kE * 8 + tid];
+  __syncthreads();
+  const float* td = st;                      // dist: breakpoints, then coefficients
+  const float* ta = st + kNabTable;          // angle
+  const float cg = st[2 * kNabTable], cod = st[2 * kNabTable + 1], coa = st[2 * kNabTable + 2], bo = st[2 * kNabTable + 3];
+  const int64_t b = blockIdx.x;
+  const int NN = N * N;
+  const float* cb = cost + b * (int64_t)NN;
+  const float2* xy = reinterpret_cast<const float2*>(coords + b * (int64_t)N * 2);
+#pragma unroll
+  for (int m = 0; m < kNabPairs; ++m) {
+    const int p = blockIdx.y * (kNabThreads * kNabPairs) + m * kNabThreads + tid;
+    if (p < NN) {
+      const int i = p / N, j = p - i * N;
+      const float c = transpose_cost ? __ldg(cb + (size_t)j * N + i) : __ldg(cb + p);
+      const float2 pi = __ldg(xy + i), pj = __ldg(xy + j);
+      const float th = atan2f(pi.y - pj.y, pi.x - pj.x);  // attn_freenet.py:254-262
+      const float4 qd = *reinterpret_cast<const float4*>(td + kE + 4 * nab_segment(td, c));
+      const float4 qa = *reinterpret_cast<const float4*>(ta + kE + 4 * nab_segment(ta, th));
+      const float z = fmaf(qd.x, c, qd.y) + fmaf(qa.x, th, qa.y) + cg;
+      const float g = 1.0f / (1.0f + expf(-z));
+      const float y = g * (fmaf(qd.z, c, qd.w) + cod) + (1.0f - g) * (fmaf(qa.z, th, qa.w) + coa) + bo;
+      out[b * (int64_t)NN + p] = y * scale;
+    }
+  }
+}
+
 }  // namespace rrnco
 
 using namespace rrnco;
@@ -131,14 +215,18 @@ int rrnco_nab_pack(const float* dist_w1, const float* dist_b1, const float* dist
 }
 
 int rrnco_nab_gating(int64_t n_inst, int32_t n_nodes, const float* coords, const float* cost, int32_t transpose_cost,
-                     const float* packed, float scale, float* out, void* stream) {
+                     const float* packed, float scale, int32_t variant, float* out, void* stream) {
   RRNCO_CHECK_ARG(n_inst > 0 && n_nodes > 0 && coords && cost && packed && out);
   RRNCO_CHECK_ARG((reinterpret_cast<uintptr_t>(coords) & 7u) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15u) == 0);
   const int per_cta = kNabThreads * kNabPairs;
   const int64_t chunks = ((int64_t)n_nodes * n_nodes + per_cta - 1) / per_cta;
   if (n_inst > 0x7fffffffLL || chunks > 65535) return RRNCO_ERR_UNSUPPORTED;
   const dim3 grid((unsigned)n_inst, (unsigned)chunks);
-  nab_gating_kernel<<<grid, kNabThreads, 0, (cudaStream_t)stream>>>(n_nodes, coords, cost, transpose_cost, packed, scale, out);
+  RRNCO_CHECK_ARG(variant == 0 || variant == 1);
+  if (variant == 0)
+    nab_gating_table_kernel<<<grid, kNabThreads, 0, (cudaStream_t)stream>>>(n_nodes, coords, cost, transpose_cost, packed, scale, out);
+  else
+    nab_gating_kernel<<<grid, kNabThreads, 0, (cudaStream_t)stream>>>(n_nodes, coords, cost, transpose_cost, packed, scale, out);
   return rrnco_launch_status();
 }
 

@@ -49,9 +49,11 @@ class DistAngleFusion(nn.Module):
             self._packed, self._packed_key = packed, key
         return self._packed
 
-    def forward(self, coords: torch.Tensor, cost_mat: torch.Tensor, duration_mat=None, scale: float = 1.0) -> torch.Tensor:
+    def forward(self, coords: torch.Tensor, cost_mat: torch.Tensor, duration_mat=None, scale: float = 1.0,
+                variant: int = 0) -> torch.Tensor:
         """adapt_bias [B, N, N] (times `scale`, e.g. the block's alpha).  `cost_mat` may be the transposed VIEW the
-        col-encoding block passes (attn_freenet.py:480-486): it is read through its base, never copied."""
+        col-encoding block passes (attn_freenet.py:480-486): it is read through its base, never copied.
+        `variant` 0 = piecewise-linear segment tables (default), 1 = brute-force sum over the hidden units (cross-check)."""
         if duration_mat is not None:
             raise NotImplementedError("duration-channel gate: use the reference module")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -64,7 +66,7 @@ class DistAngleFusion(nn.Module):
         cost_mat = cost_mat.float().contiguous()
         out = torch.empty((B, N, N), dtype=torch.float32, device=cost_mat.device)
         call("rrnco_nab_gating", B, N, ptr(coords), ptr(cost_mat), transposed, ptr(self.packed_parameters()), float(scale),
-             ptr(out), stream_ptr(cost_mat.device))
+             int(variant), ptr(out), stream_ptr(cost_mat.device))
         return out
 
 

@@ -74,12 +74,13 @@ def test_nab_kernel_matches_reference_fixture_and_oracle():
     m.load_state_dict(params["nodur"], strict=True)
     coords, cost = t["coords"].to(dev), t["cost"].to(dev)
     with torch.no_grad():
-        out = m(coords, cost)
-        outT = m(coords, cost.transpose(1, 2))  # the transposed view of the col-encoding block: read through its base
-        out2 = m(coords, cost, scale=0.37)
-    assert (out.cpu() - t["nodur.bias"]).abs().max() < 2e-5
-    assert (outT.cpu() - t["nodur.bias_T"]).abs().max() < 2e-5
-    assert torch.allclose(out2, out * 0.37, rtol=1e-6, atol=1e-7)
+        for variant in (0, 1):  # 0 = piecewise-linear segment tables (default), 1 = sum over the hidden units
+            out = m(coords, cost, variant=variant)
+            outT = m(coords, cost.transpose(1, 2), variant=variant)  # the col-encoding block's transposed view: read through its base
+            out2 = m(coords, cost, scale=0.37, variant=variant)
+            assert (out.cpu() - t["nodur.bias"]).abs().max() < 2e-5, variant
+            assert (outT.cpu() - t["nodur.bias_T"]).abs().max() < 2e-5, variant
+            assert torch.allclose(out2, out * 0.37, rtol=1e-6, atol=1e-7)
     with pytest.raises(NotImplementedError):  # forward-only
         m(coords, cost)
     # n = 100 customers + depot, default initialisation (what a freshly built encoder holds), ragged tail of the pair chunks
@@ -92,7 +93,15 @@ def test_nab_kernel_matches_reference_fixture_and_oracle():
     want = oenc.dist_angle_fusion(p2, coords, cost)
     with torch.no_grad():
         got = m2(coords.to(dev), cost.to(dev))
+        got1 = m2(coords.to(dev), cost.to(dev), variant=1)
+        # arguments exactly ON breakpoints and far outside their range (every segment incl. the two unbounded ones)
+        w, bb = m2.dist_emb[0].weight[:, 0], m2.dist_emb[0].bias
+        edge = torch.cat([-bb / w, torch.tensor([-1e6, -50.0, 0.0, 50.0, 1e6], device=dev)])
+        ce = edge[torch.randint(0, edge.numel(), (2, 101, 101), device=dev, generator=torch.Generator(device=dev).manual_seed(5))]
+        e0, e1 = m2(coords[:2].to(dev), ce, variant=0), m2(coords[:2].to(dev), ce, variant=1)
     assert (got.cpu() - want).abs().max() < 2e-6 * max(1.0, want.abs().max().item())
+    assert (got1.cpu() - want).abs().max() < 2e-6 * max(1.0, want.abs().max().item())
+    assert torch.isfinite(e0).all() and ((e0 - e1).abs() <= 1e-5 * e1.abs() + 1e-5).all()
     # a parameter update invalidates the packed cache
     with torch.no_grad():
         m2.out_lin.bias.add_(1.0)
