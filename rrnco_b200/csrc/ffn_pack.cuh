@@ -50,6 +50,37 @@ __host__ __device__ constexpr int ffn_job_chunk(int j) { return j == 0 ? 0 : j =
 __host__ __device__ constexpr int ffn_job_half(int j) { return j == 0 ? 0 : j == 1 ? 0 : j == 2 ? 1 : j == 3 ? 0 : j == 4 ? 1 : j == 5 ? 0 : j == 6 ? 1 : 1; }
 
 #ifdef __CUDACC__
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2, two IEEE operations per issue slot; bit-identical to the scalar forms).  The
+// element-wise passes of the rollout kernels are bound by instruction issue, so halving their FMA / ADD count is a direct gain.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// pair (x0, x1) (already scaled) -> packed hi / lo fp16 words: F2FP, unpack, one FADD2, F2FP
+__device__ __forceinline__ void f16s_split_pair(float2 x, uint32_t& hi, uint32_t& lo) {
+  const __half2 hh = __floats2half2_rn(x.x, x.y);
+  const float2 hf = __half22float2(hh);
+  const float2 r = fadd2(x, make_float2(-hf.x, -hf.y));
+  const __half2 ll = __floats2half2_rn(r.x, r.y);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
 // pair (x0, x1), pre-scaled by `scale` -> packed hi / lo fp16 words (low half = x0): hi = fp16(x) (round to nearest, 11
 // significant bits; one F2FP per pair), lo = fp16(x - hi) with the subtraction exact in fp32.  6 instructions per pair.
 __device__ __forceinline__ void f16s_split2(float x0, float x1, float scale, uint32_t& hi, uint32_t& lo) {

@@ -724,19 +724,18 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         }
         LSTAMP(4);
         // p = exp(s - m') (x 2^14 or 2^4), row sum, fp16 hi | lo split written back in place
-        float sum0 = 0.f, sum1 = 0.f;
+        float2 sum01 = make_float2(0.f, 0.f);
+        const float2 c1c1 = make_float2(c1, c1), offoff = make_float2(off, off);
         auto exp_block = [&](const uint32_t (&v)[16], int kb) {
           const uint32_t mw = mrow[kb >> 1] >> (16 * (kb & 1));
           uint32_t w[16];  // [hi (8 words) | lo (8 words)] of key block kb
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const float e0 = ex2a(fmaf(c1, __uint_as_float(v[i]), off));
-            const float e1 = ex2a(fmaf(c1, __uint_as_float(v[i + 1]), off));
-            const float p0 = ((mw >> i) & 1u) ? e0 : 0.f;
-            const float p1 = ((mw >> (i + 1)) & 1u) ? e1 : 0.f;
-            sum0 += p0;
-            sum1 += p1;
-            f16s_split2(p0, p1, 1.0f, w[i >> 1], w[8 + (i >> 1)]);
+            const float2 a = ffma2(c1c1, make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), offoff);
+            const float e0 = ex2a(a.x), e1 = ex2a(a.y);
+            const float2 pp = make_float2(((mw >> i) & 1u) ? e0 : 0.f, ((mw >> (i + 1)) & 1u) ? e1 : 0.f);
+            sum01 = fadd2(sum01, pp);
+            f16s_split_pair(pp, w[i >> 1], w[8 + (i >> 1)]);
           }
           tc05::tmem_st16(t_s + kb * 16, w);
         };
@@ -757,7 +756,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         tc05::mbar_arrive(&sm.bar_p[h]);
         LSTAMP(5);
         // glimpse of head h (decoder.py:292-293)
-        const float inv = __fdividef(kAScale, kKvScale * (sum0 + sum1));  // glimpse scaled by kAScale, like the query tiles
+        const float inv = __fdividef(kAScale, kKvScale * (sum01.x + sum01.y));  // glimpse scaled by kAScale, like the query tiles
         lean_wait_group(&sm.bar_o[h], step_par, warp);
         tc05::fence_after_sync();
         LSTAMP(6);
@@ -775,11 +774,12 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           for (int e = 0; e < 4; ++e) {
             const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&qhw[e]));
             const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&qlw[e]));
-            const float g0 = fmaf(__uint_as_float(o[cc * 8 + 2 * e]), inv, fh.x + fl.x);
-            const float g1 = fmaf(__uint_as_float(o[cc * 8 + 2 * e + 1]), inv, fh.y + fl.y);
+            const float2 gg = ffma2(make_float2(__uint_as_float(o[cc * 8 + 2 * e]), __uint_as_float(o[cc * 8 + 2 * e + 1])),
+                                    make_float2(inv, inv), fadd2(fh, fl));
+            const float g0 = gg.x, g1 = gg.y;
             // every operand overflow / NaN upstream of the FFN ends up here (a ReLU would swallow it later): keep it loud
             bad_operand |= !(fabsf(g0) < 65504.f) | !(fabsf(g1) < 65504.f);
-            f16s_split2(g0, g1, 1.0f, hi[e], lo[e]);
+            f16s_split_pair(gg, hi[e], lo[e]);
           }
           *reinterpret_cast<uint4*>(&a_hi[offq]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(&a_lo[offq]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -813,9 +813,9 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           for (int i = 0; i < 16; i += 2) {
             // kAScale relu(acc / (kAScale kWScale) + b1): the scaled operand directly (b1 pre-scaled; powers of two: exact).
             // Non-finite accumulators cannot arise here: the operands of GEMM1 were checked where they were written.
-            const float h0 = fmaxf(fmaf(__uint_as_float(v[i]), kAScale * kUnscaleW, bb[i]), 0.f);
-            const float h1 = fmaxf(fmaf(__uint_as_float(v[i + 1]), kAScale * kUnscaleW, bb[i + 1]), 0.f);
-            f16s_split2(h0, h1, 1.0f, w[i >> 1], w[8 + (i >> 1)]);
+            const float2 a = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                                   make_float2(kAScale * kUnscaleW, kAScale * kUnscaleW), make_float2(bb[i], bb[i + 1]));
+            f16s_split_pair(make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), w[i >> 1], w[8 + (i >> 1)]);
           }
           tc05::tmem_st16(t_h + col0, w);
         };
@@ -862,9 +862,9 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           for (int e = 0; e < 4; ++e) {
             const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&ghw[e]));
             const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&glw[e]));
-            const float o0 = fmaf(__uint_as_float(v[i + 2 * e]), kAScale * kUnscaleW, bb[i + 2 * e]) + (fh.x + fl.x);
-            const float o1 = fmaf(__uint_as_float(v[i + 2 * e + 1]), kAScale * kUnscaleW, bb[i + 2 * e + 1]) + (fh.y + fl.y);
-            f16s_split2(o0, o1, 1.0f, w[(i >> 1) + e], w[8 + (i >> 1) + e]);
+            const float2 acc = ffma2(make_float2(__uint_as_float(v[i + 2 * e]), __uint_as_float(v[i + 2 * e + 1])),
+                                     make_float2(kAScale * kUnscaleW, kAScale * kUnscaleW), make_float2(bb[i + 2 * e], bb[i + 2 * e + 1]));
+            f16s_split_pair(fadd2(acc, fadd2(fh, fl)), w[(i >> 1) + e], w[8 + (i >> 1) + e]);
           }
         }
         tc05::tmem_st16(t_oa + col0, w);

@@ -914,18 +914,18 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
 #pragma unroll
           for (int k = 0; k < 4; ++k) mrow[k] = sm.mask[row][min(4 * t + k, kGWords - 1)];
           uint32_t va[16], vb[16];
+          const float2 c1c1 = make_float2(c1, c1), offoff = make_float2(off, off);
+          float2 sum01 = make_float2(sum0, sum1);
           auto exp_block = [&](const uint32_t (&v)[16], int kb) {
             const uint32_t mw = mrow[kb >> 1] >> (16 * (kb & 1));
             uint32_t w[16];  // [hi (8 words) | lo (8 words)] of key block kb
 #pragma unroll
             for (int e = 0; e < 16; e += 2) {
-              const float e0 = ex2a(fmaf(c1, __uint_as_float(v[e]), off));
-              const float e1 = ex2a(fmaf(c1, __uint_as_float(v[e + 1]), off));
-              const float p0 = ((mw >> e) & 1u) ? e0 : 0.f;
-              const float p1 = ((mw >> (e + 1)) & 1u) ? e1 : 0.f;
-              sum0 += p0;
-              sum1 += p1;
-              f16s_split2(p0, p1, 1.0f, w[e >> 1], w[8 + (e >> 1)]);
+              const float2 a = ffma2(c1c1, make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), offoff);
+              const float e0 = ex2a(a.x), e1 = ex2a(a.y);
+              const float2 pp = make_float2(((mw >> e) & 1u) ? e0 : 0.f, ((mw >> (e + 1)) & 1u) ? e1 : 0.f);
+              sum01 = fadd2(sum01, pp);
+              f16s_split_pair(pp, w[e >> 1], w[8 + (e >> 1)]);
             }
             tc05::tmem_st16(t_s + kb * 16, w);
           };
@@ -941,6 +941,8 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
               exp_block(vb, kb + 1);
             }
           }
+          sum0 = sum01.x;
+          sum1 = sum01.y;
           sm.psum[grp][h][row] = sum0 + sum1;  // running sum of this group's tiles of head h
           tc05::tmem_wait_st();
         }
@@ -982,10 +984,11 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
           for (int e = 0; e < 4; ++e) {
             const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&qhw[e]));
             const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&qlw[e]));
-            const float g0 = fmaf(__uint_as_float(o[cc * 8 + 2 * e]), inv, fh.x + fl.x);
-            const float g1 = fmaf(__uint_as_float(o[cc * 8 + 2 * e + 1]), inv, fh.y + fl.y);
+            const float2 gg = ffma2(make_float2(__uint_as_float(o[cc * 8 + 2 * e]), __uint_as_float(o[cc * 8 + 2 * e + 1])),
+                                    make_float2(inv, inv), fadd2(fh, fl));
+            const float g0 = gg.x, g1 = gg.y;
             bad_operand |= !(fabsf(g0) < 65504.f) | !(fabsf(g1) < 65504.f);
-            f16s_split2(g0, g1, 1.0f, hi[e], lo[e]);
+            f16s_split_pair(gg, hi[e], lo[e]);
           }
           const uint4 whi = make_uint4(hi[0], hi[1], hi[2], hi[3]), wlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           *reinterpret_cast<uint4*>(&a_hi[offq]) = whi;
@@ -1028,9 +1031,9 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
             *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.ffn_bias_scaled + c * kRows + col0 + i));
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
-            const float h0 = fmaxf(fmaf(__uint_as_float(v[i]), kAScale * kUnscaleW, bb[i]), 0.f);
-            const float h1 = fmaxf(fmaf(__uint_as_float(v[i + 1]), kAScale * kUnscaleW, bb[i + 1]), 0.f);
-            f16s_split2(h0, h1, 1.0f, w[i >> 1], w[8 + (i >> 1)]);
+            const float2 a = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                                   make_float2(kAScale * kUnscaleW, kAScale * kUnscaleW), make_float2(bb[i], bb[i + 1]));
+            f16s_split_pair(make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), w[i >> 1], w[8 + (i >> 1)]);
           }
           tc05::tmem_st16(t_h + col0, w);
         };
@@ -1078,9 +1081,9 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
           for (int e = 0; e < 4; ++e) {
             const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&ghw[e]));
             const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&glw[e]));
-            const float o0 = fmaf(__uint_as_float(v[i + 2 * e]), kAScale * kUnscaleW, bb[i + 2 * e]) + (fh.x + fl.x);
-            const float o1 = fmaf(__uint_as_float(v[i + 2 * e + 1]), kAScale * kUnscaleW, bb[i + 2 * e + 1]) + (fh.y + fl.y);
-            f16s_split2(o0, o1, 1.0f, w[(i >> 1) + e], w[8 + (i >> 1) + e]);
+            const float2 acc = ffma2(make_float2(__uint_as_float(v[i + 2 * e]), __uint_as_float(v[i + 2 * e + 1])),
+                                     make_float2(kAScale * kUnscaleW, kAScale * kUnscaleW), make_float2(bb[i + 2 * e], bb[i + 2 * e + 1]));
+            f16s_split_pair(fadd2(acc, fadd2(fh, fl)), w[(i >> 1) + e], w[8 + (i >> 1) + e]);
           }
         }
         tc05::tmem_st16(t_oa + col0, w);
