@@ -20,9 +20,9 @@
 //     other kernels); evaluate = the forced column.
 // K / V / logit keys are packed once per INSTANCE (pack_kv_tiled_kernel) into 24 slices per key tile; all start tiles of an
 // instance stream the same L2-resident pack.  TMEM (512 columns): scores 0 / 128 / 256, O of the 8 heads at 384 + 16 h;
-// FFN hidden 0, output 128; logits 256 / 384.  One CTA per SM (~215 KB of shared memory).
-// The bias rows are staged by cp.async (coalesced 16-byte pieces, XOR-swizzled) into per-group double buffers of 16
-// columns: a thread-per-row read straight from global memory costs one L1 wavefront per element and bounded the select.
+// FFN hidden 0, output 128; logits 256 / 384.  One CTA per SM (~185 KB of shared memory).
+// The bias rows are staged by cp.async (coalesced 16-byte pieces, XOR-swizzled) into per-group double buffers of 32
+// columns inside the activation region (dead between the output epilogue and the next step): a thread-per-row read straight from global memory costs one L1 wavefront per element and bounded the select.
 // A tile holds p.tile_rows <= 128 POMO starts (the launcher splits the starts of an instance over several CTAs when the
 // grid would not fill the SMs); warps whose 32 rows are all padding skip every per-element pass.
 // CTA PAIRS (kPair, a thread-block cluster of 2): when the tiles alone leave more than half of the SMs idle (config C4: 64
@@ -81,7 +81,6 @@ struct TiledSmem {
   uint32_t mask[kRows][kGWordLd];
   float psum[2][kH][kRows];                // softmax row sums of the two groups
   float pmax[2][kH][kRows];                // masked row maxima of the single-term scores (exact-shift sweep)
-  float bias[kEnv == RRNCO_ENV_RCVRPTW ? 1 : 2][2][kEnv == RRNCO_ENV_RCVRPTW ? 4 : kRows * 16];  // [group][buffer][row][16 columns]
   float xf[4][2][kRows];                   // select exchange: running max, sum, best key, value at the best / forced column
   int xi[2][kRows];
   float xpf[4][kRows];                     // CTA pair: the peer's per-row partial of the select pass (written remotely)
@@ -284,7 +283,7 @@ __device__ __forceinline__ float tiled_transition(TiledSmem<kEnv>& sm, int N, in
 }
 
 template <int kEnv, int kPasses, bool kPair>
-__global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const RolloutParams p) {
+__global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const RolloutParams p) {  // (168 registers: 3 of the 10 warps share one 16 K-register sub-partition)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using SmemT = TiledSmem<kEnv>;
   SmemT& sm = *reinterpret_cast<SmemT*>(smem_raw);
@@ -1118,22 +1117,25 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
       float ssum = 0.f, best = -INFINITY, bestv = -INFINITY, chk = 0.f;
       int besti = 0x7fffffff;
       // Bias rows alpha . D[cur, :]: a thread-per-row read from global memory is one L1 wavefront per ELEMENT (32 lanes, 32
-      // rows), which bounded this pass.  Instead the group's 128 threads copy the 16 columns of a block for every row with
-      // cp.async: 16-byte pieces, four consecutive lanes per row (whole sectors), into a double buffer whose pieces are
-      // XOR-swizzled by the row so that the thread-per-row float4 reads are conflict-free.  (The time-window env would
-      // need two matrices staged: it keeps the direct loads.)
+      // rows), which bounded this pass.  Instead the group's 128 threads copy 32 columns of every row at a time with
+      // cp.async: 16-byte pieces, eight consecutive lanes per row (coalesced), XOR-swizzled by the row so that the
+      // thread-per-row float4 reads are conflict-free, into a double buffer in the (dead) activation region: group g owns
+      // the bytes of chunks 8g .. 8g + 7 of the hi and of the lo tile, which only ITS threads read in the output epilogue --
+      // so one group barrier after that epilogue frees them.  (The time-window env would need two matrices staged: it
+      // keeps the direct loads.)
       constexpr bool kStage = kEnv != RRNCO_ENV_RCVRPTW;
       const int gt = tid & 127;
       const bool vec16 = (N & 3) == 0 && (reinterpret_cast<uintptr_t>(D) & 15u) == 0;
-      auto stage_block = [&](int c_lo, int buf) {
-        float* dstb = sm.bias[kStage ? grp : 0][buf];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int q = gt + 128 * k, r = q >> 2, piece = q & 3;
+      auto bias_buf = [&](int buf) { return reinterpret_cast<float*>(sm.A + buf * (kRows * kE * 2) + grp * (kRows * 32 * 4)); };
+      auto stage_chunk = [&](int c_lo, int buf) {  // columns [c_lo, c_lo + 32) of the rows that compute
+        float* dstb = bias_buf(buf);
+#pragma unroll 2
+        for (int k = 0; k < 8; ++k) {
+          const int q = gt + 128 * k, r = q >> 3, piece = q & 7;
           if (r < rows_on) {
             const int col = c_lo + piece * 4;
             const float* src = D + (size_t)sm.cur[r] * N + col;
-            const uint32_t dst = tc05::smem_u32(dstb + r * 16 + ((piece ^ ((r >> 1) & 3)) << 2));
+            const uint32_t dst = tc05::smem_u32(dstb + r * 32 + ((piece ^ (r & 7)) << 2));
             if (vec16) {
               const int nbytes = max(0, min(16, (N - col) * 4));
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(nbytes > 0 ? src : D), "r"(nbytes));
@@ -1148,21 +1150,25 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
         }
         cp_async_commit();
       };
-      int kblock = 0;
-      if (kStage && t_lo + grp < t_hi) stage_block((t_lo + grp) * kRows, 0);
+      int kchunk = 0;
+      if (kStage) {
+        tiled_group_sync(warp);  // every thread of the group has read its residual: the group's share of A is free
+        if (t_lo + grp < t_hi) stage_chunk((t_lo + grp) * kRows, 0);
+      }
 #pragma unroll 1
       for (int t = t_lo + grp; t < t_hi; t += 2) {
         const int nb16 = t == nT - 1 ? nb_last : 8;
+        const int nch = (nb16 + 1) >> 1;
         uint32_t mrow[4];
 #pragma unroll 1
-        for (int kb = 0; kb < nb16; ++kb) {
+        for (int c = 0; c < nch; ++c) {
           if (kStage) {
             cp_async_wait<0>();
-            tiled_group_sync(warp);  // block `kblock` landed for every thread; everyone is done reading the other buffer
-            if (kb + 1 < nb16) stage_block(t * kRows + (kb + 1) * 16, (kblock + 1) & 1);
-            else if (t + 2 < t_hi) stage_block((t + 2) * kRows, (kblock + 1) & 1);
+            tiled_group_sync(warp);  // chunk `kchunk` landed for every thread; everyone is done reading the other buffer
+            if (c + 1 < nch) stage_chunk(t * kRows + (c + 1) * 32, (kchunk + 1) & 1);
+            else if (t + 2 < t_hi) stage_chunk((t + 2) * kRows, (kchunk + 1) & 1);
           }
-          if (kb == 0) {
+          if (c == 0) {
             GSTAMP(14);
             tiled_wait_group(&sm.bar_l[grp], n_lt & 1u, warp);
             ++n_lt;
@@ -1171,16 +1177,19 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
 #pragma unroll
             for (int k = 0; k < 4; ++k) mrow[k] = sm.mask[row][min(4 * t + k, kGWords - 1)];
           }
-          if (warp_on) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int kb = 2 * c + half;
+            if (kb < nb16 && warp_on) {
             const int c0 = t * kRows + kb * 16;
             uint32_t v[16];
             tc05::tmem_ld16(t_l + kb * 16, v);
             float bv[16];
             if (kStage) {
-              const float* srcb = sm.bias[kStage ? grp : 0][kblock & 1] + row * 16;
+              const float* srcb = bias_buf(kchunk & 1) + row * 32;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float4 x = *reinterpret_cast<const float4*>(srcb + ((j ^ ((row >> 1) & 3)) << 2));
+                const float4 x = *reinterpret_cast<const float4*>(srcb + (((4 * half + j) ^ (row & 7)) << 2));
                 bv[4 * j] = alpha2 * x.x; bv[4 * j + 1] = alpha2 * x.y;
                 bv[4 * j + 2] = alpha2 * x.z; bv[4 * j + 3] = alpha2 * x.w;
               }
@@ -1261,8 +1270,9 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
                 for (int i = 0; i < 16; ++i) bestv = c0 + i == forced ? val[i] : bestv;
               }
             }
+            }
           }
-          ++kblock;
+          ++kchunk;
         }
         tc05::fence_before_sync();
         tc05::mbar_arrive(&sm.bar_lfree[grp]);

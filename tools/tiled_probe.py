@@ -50,12 +50,12 @@ def compare(name, n, B, S, kind="greedy"):
           flush=True)
 
 
-def c4(B, reps=2):
+def c4(B, reps=5, warm=3):
     env, td, pol = setup("atsp", 1000, B, seed=1)
     for path in ("fused",) if os.environ.get("FUSED_ONLY") else ("fused", "stepwise"):
         pol.large_n_path = path
-        for i in range(reps + 1):
-            if i == 1:
+        for i in range(reps + warm):
+            if i == warm:
                 torch.cuda.synchronize(); t0 = time.perf_counter()
             out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=100)
         torch.cuda.synchronize()
