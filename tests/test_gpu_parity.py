@@ -538,6 +538,52 @@ def test_key_tiled_kernel_exact_softmax_shift_on_peaked_heads(rb):
     assert (out3["actions"].sort(1)[0] == torch.arange(n, device=dev)).all()
 
 
+def test_key_tiled_kernel_tilings_and_single_start(rb):
+    """rollout_tiled.cu: (a) one CTA per tile, CTA pairs and start-split tilings (rrnco_set_start_split 2 / 0 / 1) decode the
+    same tours; (b) the non-multistart path (one rollout per instance, learned placeholder query at step 0 for ATSP,
+    depot start for the VRPs) matches the per-step pipeline and the oracle."""
+    L = rb._lib.lib()
+    name, n, B, S = "atsp", 180, 3, 90
+    raw = synth.make_instances(name, B, n, seed=41)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    row, col = synth.random_embeddings(B, n, seed=42)
+    p = omodel.init_decoder_params(name, seed=43)
+    pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+    td = env.reset(lite(rb, raw))
+    outs = {}
+    try:
+        for mode in (0, 1, 2):
+            assert L.rrnco_set_start_split(mode) == 0
+            outs[mode] = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+        assert L.rrnco_rollout_tile_rows(0, n, B, S) == 128
+        L.rrnco_set_start_split(1)
+        assert L.rrnco_rollout_tile_rows(0, n, B, S) == 32  # 148 SMs / 3 instances: whole warps of 32 starts
+    finally:
+        L.rrnco_set_start_split(0)
+    for mode in (1, 2):
+        assert torch.equal(outs[mode]["actions"], outs[0]["actions"]), mode
+        assert torch.equal(outs[mode]["reward"], outs[0]["reward"])
+        assert (outs[mode]["log_likelihood"] - outs[0]["log_likelihood"]).abs().max() < 1e-3
+    for name, n, B in (("atsp", 150, 5), ("rcvrp", 139, 4)):
+        raw = synth.make_instances(name, B, n, seed=n)
+        oenv = oenvs.make_env(name, n, check_solution=False)
+        otd = oenv.reset(raw)
+        N = otd["action_mask"].shape[-1]
+        row, col = synth.random_embeddings(B, N, seed=n + 1)
+        p = omodel.init_decoder_params(name, seed=n + 2)
+        with torch.inference_mode():
+            oout = omodel.policy_forward(p, oenv, otd, row, col, decode_type="greedy")
+        env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+        pol = make_policy(rb, name, p, row.to(dev), col.to(dev))
+        out = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="greedy")
+        same = _same_tours(out["actions"].cpu(), oout["actions"])
+        assert same.float().mean() >= 0.75, (name, same)  # B rollouts only: at most one may differ
+        assert rel(out["reward"].cpu()[same], oout["reward"][same]) < 1e-6
+        pol.large_n_path = "stepwise"
+        out2 = pol(env.reset(lite(rb, raw)), env, phase="val", decode_type="greedy")
+        assert _same_tours(out["actions"], out2["actions"]).float().mean() >= 0.75
+
+
 def test_key_tiled_kernel_sampling_evaluate_and_determinism(rb):
     """rollout_tiled.cu, the other decode modes at N > 128: sampling draws arg-max(v + Gumbel) with the same Philox
     counters as rrnco_select_action (so the per-step pipeline with the same seed samples the same tours), evaluate mode
