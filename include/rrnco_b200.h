@@ -76,7 +76,8 @@ float rrnco_u01(uint32_t x);
 /* Precision of the in-kernel contractions of the fused decoder kernels (process-wide, set before use):
  *   3 = error-compensated tensor-core contractions, fp32-faithful (default; the reference's CPU / fp32 path):
  *       three-term fp16 operand split on tcgen05 (engine 1) / 3xTF32 on mma.sync (engine 0)
- *   1 = one reduced-precision pass (analogue of the reference's `torch.autocast("cuda")` inference path, test.py:182-185) */
+ *   1 = one reduced-precision pass (analogue of the reference's `torch.autocast("cuda")` inference path, test.py:182-185)
+ * The key-tiled kernel (n_nodes > RRNCO_MAX_NODES_TILE) is built fp32-faithful only and ignores the setting. */
 int rrnco_set_precision(int32_t passes);
 
 /* FFN engine of the fused rollout kernel (process-wide, set before use):

@@ -1438,14 +1438,21 @@ bool tiled_use_pairs(int64_t n_tiles_total) {
 int dispatch_env_tiled(const RolloutParams& p, int env, int passes, cudaStream_t st) {
   static_assert(sizeof(TiledSmem<RRNCO_ENV_RCVRPTW>) <= 232448, "one CTA per SM: at most 227 KB of shared memory");
   static_assert(sizeof(TiledSmem<RRNCO_ENV_ATSP>) <= 232448 && sizeof(TiledSmem<RRNCO_ENV_RCVRP>) <= 232448, "shared memory");
-  const bool pairs = tiled_use_pairs(p.n_inst * p.n_tiles);
   (void)passes;  // the key-tiled kernel is built fp32-faithful only (three-term products)
-  switch (env) {
-    case RRNCO_ENV_ATSP: return pairs ? launch_tiled<RRNCO_ENV_ATSP, 3, true>(p, st) : launch_tiled<RRNCO_ENV_ATSP, 3, false>(p, st);
-    case RRNCO_ENV_RCVRP: return pairs ? launch_tiled<RRNCO_ENV_RCVRP, 3, true>(p, st) : launch_tiled<RRNCO_ENV_RCVRP, 3, false>(p, st);
-    case RRNCO_ENV_RCVRPTW: return pairs ? launch_tiled<RRNCO_ENV_RCVRPTW, 3, true>(p, st) : launch_tiled<RRNCO_ENV_RCVRPTW, 3, false>(p, st);
-    default: return RRNCO_ERR_BAD_ARG;
+  auto launch = [&](bool pairs) -> int {
+    switch (env) {
+      case RRNCO_ENV_ATSP: return pairs ? launch_tiled<RRNCO_ENV_ATSP, 3, true>(p, st) : launch_tiled<RRNCO_ENV_ATSP, 3, false>(p, st);
+      case RRNCO_ENV_RCVRP: return pairs ? launch_tiled<RRNCO_ENV_RCVRP, 3, true>(p, st) : launch_tiled<RRNCO_ENV_RCVRP, 3, false>(p, st);
+      case RRNCO_ENV_RCVRPTW: return pairs ? launch_tiled<RRNCO_ENV_RCVRPTW, 3, true>(p, st) : launch_tiled<RRNCO_ENV_RCVRPTW, 3, false>(p, st);
+      default: return RRNCO_ERR_BAD_ARG;
+    }
+  };
+  if (tiled_use_pairs(p.n_inst * p.n_tiles)) {
+    // a device partition that cannot co-schedule a 2-CTA cluster of this footprint refuses the launch: one CTA per tile then
+    if (launch(true) == RRNCO_OK) return RRNCO_OK;
+    (void)cudaGetLastError();
   }
+  return launch(false);
 }
 
 }  // namespace rrnco
