@@ -597,6 +597,29 @@ def run_ours(args, rank, world, local_rank):
                  "reference_flops_per_pair": 4 * 128 * 128 + 8 * 128,
                  "reference_activation_bytes_per_pair": 2 * 128 * 4 * 2,
                  "note": "`frac` = 4 B read + 4 B written per pair over the measured HBM peak"}
+        # the whole O(N^2) part of a block fused (bias -> row softmax -> exp -> two [N,N] x [N,E] products -> sigmoid gate)
+        q, k, v = (torch.randn(Bn, N_LOC + 1, 128, device=dev, generator=g) for _ in range(3))
+
+        def unfused():  # the same math with the bias kernel + torch ops, as AFTFull.forward writes it (attn_freenet.py:319-324)
+            a = torch.exp(torch.softmax(mod(coords, cost, scale=0.9), dim=-1))
+            e1 = torch.exp(torch.softmax(k, dim=1))
+            return torch.sigmoid(q) * (a @ (e1 * v)) / (a @ e1)
+        with torch.no_grad():
+            ms_f = time_launch(lambda: rb.aft_nab(q, k, v, coords, cost, mod, scale=0.9), reps=10)
+            ms_u = time_launch(unfused, reps=5)
+            err = (rb.aft_nab(q[:64], k[:64], v[:64], coords[:64], cost[:64], mod, scale=0.9) -
+                   (lambda a, e1: torch.sigmoid(q[:64]) * (a @ (e1 * v[:64])) / (a @ e1))(
+                       torch.exp(torch.softmax(mod(coords[:64], cost[:64], scale=0.9), dim=-1)), torch.exp(torch.softmax(k[:64], dim=1)))
+                   ).abs().max().item()
+        aft_bytes = Bn * (4 * (N_LOC + 1) * 128 * 4 + (N_LOC + 1) ** 2 * 4)
+        entry["fused_aft_block"] = {
+            "kernel": "rrnco::aft_nab_kernel (neural adaptive bias + AFTFull.forward :309-327 without its Linear layers; "
+                      "adapt_bias, its softmax / exp and E1 / E2 never reach HBM)",
+            "ms_per_launch": ms_f, "ms_unfused_bias_kernel_plus_torch": ms_u, "max_abs_diff_vs_unfused": err,
+            "algorithmic_bytes_per_launch": aft_bytes, "achieved": aft_bytes / (ms_f * 1e-3) / 1e9, "unit": "GB/s",
+            "frac": aft_bytes / (ms_f * 1e-3) / 1e9 / peaks()[0],
+            "fp32_fma_per_launch": Bn * 2 * (N_LOC + 1) ** 2 * 128,
+            "what": "q, k, v read + y written ([B,N,128] fp32 each) + the cost matrix once = algorithmic bytes"}
         if not args.no_cpu_baseline:
             from oracle import encoder as oenc
             torch.set_num_threads(os.cpu_count() or 1)

@@ -338,6 +338,14 @@ int rrnco_nab_pack(const float* dist_w1, const float* dist_b1, const float* dist
 int rrnco_nab_gating(int64_t n_inst, int32_t n_nodes, const float* coords, const float* cost, int32_t transpose_cost,
                      const float* packed, float scale, int32_t variant, float* out, void* stream);
 
+/* The O(N^2) part of one attention-free block fused (attn_freenet.py:424-432 + AFTFull.forward :309-327, n_nodes <= 128):
+ *   out[b,i,:] = sigmoid(q[b,i,:]) * (sum_j a_ij E2[j,:]) / (sum_j a_ij E1[j,:]),   a_ij = exp(softmax_j(scale * adapt_bias[b,i,j])),
+ *   E1 = exp(softmax over the tokens of k[b]), E2 = E1 * v[b]   -- i.e. AFTFull without its four Linear layers (q / k / v are
+ *   to_q(x) / to_k(y) / to_v(y), the caller applies `project`).  adapt_bias comes from the segment tables of rrnco_nab_pack
+ *   and never reaches memory; E1 / E2 of the instance stay in shared memory.  q, k, v, out fp32 [B,N,128] (16-byte aligned). */
+int rrnco_aft_nab(int64_t n_inst, int32_t n_nodes, const float* q, const float* k, const float* v, const float* coords,
+                  const float* cost, int32_t transpose_cost, const float* packed, float scale, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ from .generator import LazyATSPGenerator, LazyRCVRPGenerator, LazyRMTVRPGenerato
 from .transforms import StateAugmentation, dihedral_8_augmentation  # noqa: F401
 from .tdlite import TensorDictLite, batchify, unbatchify  # noqa: F401
 from .torch_ops import use_torch_ops  # noqa: F401
-from .encoder_ops import DistAngleFusion, patch_encoder  # noqa: F401
+from .encoder_ops import DistAngleFusion, aft_nab, patch_encoder  # noqa: F401
 from .training import (batched_logprobs, collect_decode_inputs, pomo_shared_baseline_loss,  # noqa: F401
                        replay_log_likelihood)
 

@@ -23,6 +23,7 @@
 // (gate constant, wo . b2d, wo . b2a, bo); then per MLP (dist, angle): E sorted breakpoints, (E + 1) x 4 segment
 // coefficients (gate slope, gate intercept, out slope, out intercept).
 #include "common.cuh"
+#include "ffn_pack.cuh"  // ffma2: packed fp32 pairs
 
 namespace rrnco {
 
@@ -195,6 +196,145 @@ __global__ void __launch_bounds__(kNabThreads) nab_gating_table_kernel(int N, co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused neural-adaptive-bias + AFT-full of one attention-free block (attn_freenet.py:424-432 + AFTFull.forward :309-327):
+//     Y[i,:] = sigmoid(Q[i,:]) * (sum_j a_ij E2[j,:]) / (sum_j a_ij E1[j,:]),
+//     a_ij = exp(softmax_j(alpha * adapt_bias[i,j])),  E1 = exp(softmax over the tokens of K),  E2 = E1 * V
+// One CTA per instance.  Upstream writes adapt_bias [B,N,N], its softmax, its exp and two [B,N,N] x [B,N,E] products
+// through HBM; here the bias row of a node is produced in registers by the segment tables (above), normalised with
+// warp shuffles and consumed at once, and E1 / E2 of the instance stay in shared memory: HBM sees Q, K, V, the cost
+// matrix once and Y.  Four rows per warp at a time, so that every shared-memory read of an E1 / E2 row serves four rows
+// (the products are bound by shared-memory wavefronts otherwise); a_ij travels by shuffle.  fp32 FMAs: the two products are
+// 2 x N x N x E = 2.6 MFLOP per instance, far too small and too oddly shaped (N = 101) for a tcgen05 tile.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kAftThreads = 256;
+constexpr int kAftRows = 4;            // rows per warp per pass
+constexpr int kAftMaxNodes = 128;      // four key slots per lane
+
+__global__ void __launch_bounds__(kAftThreads, 2) aft_nab_kernel(int N, const float* __restrict__ Q, const float* __restrict__ K,
+                                                                 const float* __restrict__ V, const float* __restrict__ coords,
+                                                                 const float* __restrict__ cost, int transpose_cost,
+                                                                 const float* __restrict__ packed, float scale,
+                                                                 float* __restrict__ Y) {
+  extern __shared__ __align__(16) float smem_aft[];
+  float* E1 = smem_aft;                        // [N][kE]
+  float* E2 = E1 + (size_t)N * kE;             // [N][kE]
+  float* st = E2 + (size_t)N * kE;             // segment tables (2 * kNabTable + 4)
+  float2* xy = reinterpret_cast<float2*>(st + 2 * kNabTable + 4);  // [N]
+  float* red = reinterpret_cast<float*>(xy + kAftMaxNodes);        // [2][kE] column-softmax exchange
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b = blockIdx.x;
+  const float* Kb = K + b * (int64_t)N * kE;
+  const float* Vb = V + b * (int64_t)N * kE;
+  const float* Qb = Q + b * (int64_t)N * kE;
+  for (int i = tid; i < 2 * kNabTable; i += kAftThreads) st[i] = packed[kNabBrute + i];
+  if (tid < 4) st[2 * kNabTable + tid] = packed[kE * 8 + tid];
+  if (tid < N) xy[tid] = __ldg(reinterpret_cast<const float2*>(coords + b * (int64_t)N * 2) + tid);
+  // ---- E1 = exp(softmax over the tokens (dim = 1) of K), E2 = E1 * V (attn_freenet.py:320-322): thread = (column, row half) ----
+  {
+    const int d = tid & (kE - 1), half = tid >> 7;
+    const int j0 = half ? N / 2 : 0, j1 = half ? N : N / 2;
+    float mx = -INFINITY;
+#pragma unroll 8
+    for (int j = j0; j < j1; ++j) mx = fmaxf(mx, __ldg(Kb + (size_t)j * kE + d));
+    red[half * kE + d] = mx;
+    __syncthreads();
+    mx = fmaxf(red[d], red[kE + d]);
+    float sum = 0.f;
+#pragma unroll 8
+    for (int j = j0; j < j1; ++j) sum += expf(__ldg(Kb + (size_t)j * kE + d) - mx);
+    __syncthreads();
+    red[half * kE + d] = sum;
+    __syncthreads();
+    sum = red[d] + red[kE + d];
+    const float inv_sum = 1.0f / sum;
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
+      const float e = expf(expf(__ldg(Kb + (size_t)j * kE + d) - mx) * inv_sum);
+      E1[(size_t)j * kE + d] = e;
+      E2[(size_t)j * kE + d] = e * __ldg(Vb + (size_t)j * kE + d);
+    }
+  }
+  __syncthreads();
+  const float* td = st;
+  const float* ta = st + kNabTable;
+  const float cg = st[2 * kNabTable], cod = st[2 * kNabTable + 1], coa = st[2 * kNabTable + 2], bo = st[2 * kNabTable + 3];
+  const float* cb = cost + b * (int64_t)N * N;
+  // ---- rows: warp w owns rows 4 (w + 8 t) .. + 3 ----
+  for (int i0 = warp * kAftRows; i0 < N; i0 += (kAftThreads / 32) * kAftRows) {
+    float a[kAftRows][4];  // a_ij of row i0 + r, key j = lane + 32 m
+#pragma unroll
+    for (int r = 0; r < kAftRows; ++r) {
+      const int i = min(i0 + r, N - 1);  // (rows beyond N repeat the last one; they are not stored)
+      const float2 pi = xy[i];
+      float bias[4];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int j = lane + 32 * m;
+        bias[m] = -INFINITY;
+        if (j < N) {
+          const float c = transpose_cost ? __ldg(cb + (size_t)j * N + i) : __ldg(cb + (size_t)i * N + j);
+          const float2 pj = xy[j];
+          const float th = atan2f(pi.y - pj.y, pi.x - pj.x);
+          const float4 qd = *reinterpret_cast<const float4*>(td + kE + 4 * nab_segment(td, c));
+          const float4 qa = *reinterpret_cast<const float4*>(ta + kE + 4 * nab_segment(ta, th));
+          const float z = fmaf(qd.x, c, qd.y) + fmaf(qa.x, th, qa.y) + cg;
+          const float g = 1.0f / (1.0f + expf(-z));
+          bias[m] = (g * (fmaf(qd.z, c, qd.w) + cod) + (1.0f - g) * (fmaf(qa.z, th, qa.w) + coa) + bo) * scale;
+        }
+        mx = fmaxf(mx, bias[m]);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        bias[m] = expf(bias[m] - mx);  // exp(-inf) = 0 for the slots beyond N
+        sum += bias[m];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) a[r][m] = lane + 32 * m < N ? expf(bias[m] / sum) : 0.f;  // exp(softmax) (attn_freenet.py:319-321)
+    }
+    // num / den over the keys; lane owns output dims 4 lane .. 4 lane + 3 (packed fp32 pairs: two FMAs per issue slot)
+    float2 num[kAftRows][2], den[kAftRows][2];
+#pragma unroll
+    for (int r = 0; r < kAftRows; ++r) num[r][0] = num[r][1] = den[r][0] = den[r][1] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int jn = min(32, N - 32 * m);
+#pragma unroll 4
+      for (int jj = 0; jj < jn; ++jj) {
+        const int j = 32 * m + jj;
+        const float4 e2 = *reinterpret_cast<const float4*>(E2 + (size_t)j * kE + 4 * lane);
+        const float4 e1 = *reinterpret_cast<const float4*>(E1 + (size_t)j * kE + 4 * lane);
+#pragma unroll
+        for (int r = 0; r < kAftRows; ++r) {
+          const float w = __shfl_sync(0xffffffffu, a[r][m], jj);
+          const float2 ww = make_float2(w, w);
+          num[r][0] = ffma2(ww, make_float2(e2.x, e2.y), num[r][0]);
+          num[r][1] = ffma2(ww, make_float2(e2.z, e2.w), num[r][1]);
+          den[r][0] = ffma2(ww, make_float2(e1.x, e1.y), den[r][0]);
+          den[r][1] = ffma2(ww, make_float2(e1.z, e1.w), den[r][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kAftRows; ++r) {
+      const int i = i0 + r;
+      if (i < N) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(Qb + (size_t)i * kE) + lane);
+        float4 y;
+        y.x = num[r][0].x / den[r][0].x / (1.0f + expf(-q.x)); y.y = num[r][0].y / den[r][0].y / (1.0f + expf(-q.y));
+        y.z = num[r][1].x / den[r][1].x / (1.0f + expf(-q.z)); y.w = num[r][1].y / den[r][1].y / (1.0f + expf(-q.w));
+        reinterpret_cast<float4*>(Y + (b * (int64_t)N + i) * kE)[lane] = y;
+      }
+    }
+  }
+}
+
 }  // namespace rrnco
 
 using namespace rrnco;
@@ -227,6 +367,27 @@ int rrnco_nab_gating(int64_t n_inst, int32_t n_nodes, const float* coords, const
     nab_gating_table_kernel<<<grid, kNabThreads, 0, (cudaStream_t)stream>>>(n_nodes, coords, cost, transpose_cost, packed, scale, out);
   else
     nab_gating_kernel<<<grid, kNabThreads, 0, (cudaStream_t)stream>>>(n_nodes, coords, cost, transpose_cost, packed, scale, out);
+  return rrnco_launch_status();
+}
+
+
+int rrnco_aft_nab(int64_t n_inst, int32_t n_nodes, const float* q, const float* k, const float* v, const float* coords,
+                  const float* cost, int32_t transpose_cost, const float* packed, float scale, float* out, void* stream) {
+  RRNCO_CHECK_ARG(n_inst > 0 && n_nodes > 0 && q && k && v && coords && cost && packed && out);
+  RRNCO_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(coords) & 7u) == 0);
+  if (n_nodes > kAftMaxNodes || n_inst > 0x7fffffffLL) return RRNCO_ERR_UNSUPPORTED;
+  const size_t smem = ((size_t)2 * n_nodes * kE + 2 * kNabTable + 4 + 2 * kAftMaxNodes + 2 * kE) * sizeof(float);
+  static PerDeviceOnce once;
+  if (once.first()) {
+    if (cudaFuncSetAttribute(aft_nab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(aft_nab_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
+      once.undo();
+      return RRNCO_ERR_CUDA;
+    }
+  }
+  aft_nab_kernel<<<(unsigned)n_inst, kAftThreads, smem, (cudaStream_t)stream>>>(n_nodes, q, k, v, coords, cost, transpose_cost,
+                                                                                 packed, scale, out);
   return rrnco_launch_status();
 }
 

@@ -70,10 +70,49 @@ class DistAngleFusion(nn.Module):
         return out
 
 
-def patch_encoder(encoder: nn.Module) -> int:
+def aft_nab(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, coords: torch.Tensor, cost_mat: torch.Tensor,
+            fusion: DistAngleFusion, scale: float = 1.0) -> torch.Tensor:
+    """The O(N^2) part of an attention-free block in one kernel (`rrnco_aft_nab`): the neural adaptive bias
+    (`fusion`, times `scale` = the block's alpha), its row softmax and exp, exp(softmax over the tokens of k), the two
+    [N,N] x [N,E] products and the sigmoid(q) gate -- `AFTFull.forward` (attn_freenet.py:309-327) without its Linear layers:
+    q / k / v are to_q(x) / to_k(y) / to_v(y) and the caller applies `project`.  N <= 128; nothing of size [B,N,N] is written."""
+    B, N, E = q.shape
+    if N > 128:
+        raise NotImplementedError("rrnco_aft_nab holds the instance's key tiles in shared memory: N <= 128 "
+                                  "(use DistAngleFusion + torch for larger instances)")
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        raise NotImplementedError("forward-only kernel: call under torch.no_grad() / inference_mode (test.py path)")
+    q, k, v = q.float().contiguous(), k.float().contiguous(), v.float().contiguous()
+    coords = coords.float().contiguous()
+    transposed = 0
+    if not cost_mat.is_contiguous() and cost_mat.transpose(1, 2).is_contiguous():
+        cost_mat, transposed = cost_mat.transpose(1, 2), 1
+    cost_mat = cost_mat.float().contiguous()
+    out = torch.empty_like(q)
+    call("rrnco_aft_nab", B, N, ptr(q), ptr(k), ptr(v), ptr(coords), ptr(cost_mat), transposed, ptr(fusion.packed_parameters()),
+         float(scale), ptr(out), stream_ptr(q.device))
+    return out
+
+
+def _fused_block_forward(self, row_emb, col_emb, cost_mat, coords, duration_mat=None):
+    """AttnFree_Block.forward (attn_freenet.py:417-442) with the bias + AFT-full part as one kernel; everything else
+    (norms, Linear layers, feed-forward) is the block's own modules, unchanged."""
+    row_emb = self.norm1(row_emb)
+    col_emb = self.norm2(col_emb)
+    aft = self.attn_free
+    y = aft_nab(aft.to_q(row_emb), aft.to_k(col_emb), aft.to_v(col_emb), coords, cost_mat, self.angle_distance_fusion,
+                float(self.alpha))
+    out_concat = aft.project(y)
+    multi_head_out = self.norm3(self.multi_head_combine(out_concat))
+    return self.feed_forward(multi_head_out, row_emb)
+
+
+def patch_encoder(encoder: nn.Module, fuse_aft: bool = True) -> int:
     """Replaces every gating `DistAngleFusion` without duration channel inside an upstream encoder (attribute
     `angle_distance_fusion` of the attention-free blocks, attn_freenet.py:386-389) by the kernel-backed module with the
-    same parameters.  Returns the number of modules replaced."""
+    same parameters, and (fuse_aft, instances of <= 128 nodes) routes the block's bias -> AFT-full chain through the fused
+    kernel.  Inference path only.  Returns the number of blocks patched."""
+    import types
     n = 0
     for block in encoder.modules():
         ref = getattr(block, "angle_distance_fusion", None)
@@ -82,5 +121,14 @@ def patch_encoder(encoder: nn.Module) -> int:
         mine = DistAngleFusion(ref.embed_dim).to(next(ref.parameters()).device)
         mine.load_state_dict(ref.state_dict(), strict=True)
         block.angle_distance_fusion = mine
+        if fuse_aft and all(hasattr(block, a) for a in ("attn_free", "norm1", "norm2", "norm3", "multi_head_combine",
+                                                        "feed_forward", "alpha")):
+            unfused = block.forward
+
+            def forward(self, row_emb, col_emb, cost_mat, coords, duration_mat=None, _unfused=unfused):
+                if cost_mat.shape[-1] > 128 or duration_mat is not None or torch.is_grad_enabled():
+                    return _unfused(row_emb, col_emb, cost_mat, coords, duration_mat)
+                return _fused_block_forward(self, row_emb, col_emb, cost_mat, coords, duration_mat)
+            block.forward = types.MethodType(forward, block)
         n += 1
     return n

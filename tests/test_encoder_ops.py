@@ -140,3 +140,103 @@ def test_patch_encoder_swaps_the_gating_modules():
         got = [b.angle_distance_fusion(coords, cost.transpose(1, 2)) for b in enc]
     for a, b in zip(got, want):
         assert (a - b).abs().max() < 5e-6
+
+
+def aft_core(q, k, v, bias):
+    """AFTFull.forward (attn_freenet.py:309-327) between its Linear layers, fp64."""
+    a = torch.exp(torch.softmax(bias.double(), dim=-1))
+    e1 = torch.exp(torch.softmax(k.double(), dim=1))
+    return torch.sigmoid(q.double()) * (a @ (e1 * v.double())) / (a @ e1)
+
+
+@pytest.mark.gpu
+def test_fused_aft_nab_kernel_matches_reference_fixture_and_oracle():
+    import rrnco_b200 as rb
+    import torch.nn.functional as F
+    dev = "cuda"
+    t, params = _fixture()
+    m = rb.DistAngleFusion(128).to(dev)
+    m.load_state_dict(params["nodur"], strict=True)
+    pa = {k: v.to(dev) for k, v in params["aft"].items()}
+    x, y = t["aft.x"].to(dev), t["aft.y"].to(dev)
+    coords, cost = t["coords"].to(dev), t["cost"].to(dev)
+    with torch.no_grad():
+        q = F.linear(x, pa["to_q.weight"], pa["to_q.bias"])
+        k = F.linear(y, pa["to_k.weight"], pa["to_k.bias"])
+        v = F.linear(y, pa["to_v.weight"], pa["to_v.bias"])
+        core = rb.aft_nab(q, k, v, coords, cost, m, scale=1.7)  # the fixture's AFT call used adapt_bias * 1.7
+        out = F.linear(core, pa["project.weight"], pa["project.bias"])
+    assert (out.cpu() - t["aft.out"]).abs().max() < 2e-5
+    # n = 100 + depot, default-initialised modules, transposed cost view (col-encoding block), ragged row groups
+    torch.manual_seed(9)
+    m2 = rb.DistAngleFusion(128).to(dev)
+    p2 = {kk: vv.detach().cpu() for kk, vv in m2.state_dict().items()}
+    g = torch.Generator().manual_seed(10)
+    B, N = 6, 101
+    coords = torch.rand(B, N, 2, generator=g)
+    cost = torch.rand(B, N, N, generator=g) * 1.4
+    q, k, v = (torch.randn(B, N, 128, generator=g) for _ in range(3))
+    for transposed in (False, True):
+        cm = cost.transpose(1, 2) if transposed else cost
+        want = aft_core(q, k, v, oenc.dist_angle_fusion(p2, coords, cm) * 0.8)
+        with torch.no_grad():
+            got = rb.aft_nab(q.to(dev), k.to(dev), v.to(dev), coords.to(dev), cm.to(dev), m2, scale=0.8)
+        assert (got.cpu().double() - want).abs().max() < 2e-6 * max(1.0, want.abs().max().item()), transposed
+    with pytest.raises(NotImplementedError):
+        rb.aft_nab(torch.zeros(1, 130, 128, device=dev), torch.zeros(1, 130, 128, device=dev), torch.zeros(1, 130, 128, device=dev),
+                   torch.zeros(1, 130, 2, device=dev), torch.zeros(1, 130, 130, device=dev), m2)
+
+
+@pytest.mark.gpu
+def test_patch_encoder_fuses_the_block():
+    """patch_encoder on a block with upstream's attribute names (attn_freenet.py:360-442): the fused forward equals the
+    unfused one (bias module -> AFTFull with torch ops)."""
+    import rrnco_b200 as rb
+    from torch import nn
+    import torch.nn.functional as F
+
+    class AFT(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.to_q, self.to_k, self.to_v, self.project = (nn.Linear(128, 128) for _ in range(4))
+
+        def forward(self, x, y=None, adapt_bias=None):
+            p = {k: v for k, v in self.state_dict().items()}
+            return oenc.aft_full(p, x, y, adapt_bias)
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.alpha = nn.Parameter(torch.full((1,), 1.3))
+            self.attn_free = AFT()
+            self.multi_head_combine = nn.Linear(128, 128)
+            self.angle_distance_fusion = rb.DistAngleFusion(128)  # (stands for upstream's module: same parameters)
+            self.norm1, self.norm2, self.norm3 = nn.LayerNorm(128), nn.LayerNorm(128), nn.LayerNorm(128)
+            self.feed_forward = lambda a, b: a + b
+
+        def forward(self, row_emb, col_emb, cost_mat, coords, duration_mat=None):  # attn_freenet.py:417-442
+            row_emb, col_emb = self.norm1(row_emb), self.norm2(col_emb)
+            bias = self.angle_distance_fusion(coords, cost_mat, duration_mat) * self.alpha
+            out = self.attn_free(row_emb, y=col_emb, adapt_bias=bias)
+            return self.feed_forward(self.norm3(self.multi_head_combine(out)), row_emb)
+
+    torch.manual_seed(12)
+    blk = Block().to("cuda")
+    ref_fusion = blk.angle_distance_fusion
+
+    class Ref(nn.Module):  # what upstream's module looks like to patch_encoder: not a DistAngleFusion instance
+        def __init__(self, m):
+            super().__init__()
+            self.embed_dim, self.dist_emb, self.angle_emb, self.gate, self.out_lin = 128, m.dist_emb, m.angle_emb, m.gate, m.out_lin
+
+        def forward(self, coords, cost_mat, duration_mat=None):
+            return ref_fusion(coords, cost_mat)
+    blk.angle_distance_fusion = Ref(ref_fusion)
+    g = torch.Generator().manual_seed(13)
+    row, col = torch.randn(3, 40, 128, generator=g).cuda(), torch.randn(3, 40, 128, generator=g).cuda()
+    coords, cost = torch.rand(3, 40, 2, generator=g).cuda(), torch.rand(3, 40, 40, generator=g).cuda()
+    with torch.no_grad():
+        want = blk(row, col, cost.transpose(1, 2), coords)
+        assert rb.patch_encoder(blk) == 1
+        got = blk(row, col, cost.transpose(1, 2), coords)
+    assert (got - want).abs().max() < 2e-5
