@@ -895,6 +895,9 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
             if (c < N) {
               bv = __fmul_rn(p.w.alpha, D[cur_s * N + c]);
               if (kEnv == RRNCO_ENV_RCVRPTW) bv = __fadd_rn(bv, __fmul_rn(p.w.beta, U[cur_s * N + c]));
+#ifndef RRNCO_LEAN_SELECT3
+              bv *= 1.4426950408889634f;  // the single-pass select works in log2 units
+#endif
             }
             bias[i][cq] = bv;
           }
@@ -915,6 +918,142 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
     tc05::fence_after_sync();
     LSTAMP(16);
 
+#ifndef RRNCO_LEAN_SELECT3
+    // ---- S: select, thread per row, SINGLE pass: two threads own one rollout, 16-column groups dealt round-robin.  Per
+    // element: u = 2^(acc k1 - bias log2 e) + 1e-6 (decoder.py:198-201), v = clip (1 - 2 / (u^2 + 1)) (= clip tanh(log u)),
+    // mask; sum of exp(v - shift) with the fixed shift clip / temperature (clipped values are bounded: no maximum pass);
+    // arg-max by a tree maximum per block + an index search only when the block improves it.  log p(chosen) =
+    // (v - max) - log sum.  Greedy = arg-max v (lowest index on ties), sampling = arg-max v + Gumbel, evaluate = the forced
+    // column.  (The three-pass form -- values rewritten to TMEM, sum pass, log-softmax pass -- is kept behind
+    // RRNCO_LEAN_SELECT3: two TMEM round trips and two CTA barriers more per step.) ----
+    {
+      const int row = trow, colhalf = grp;
+      const int64_t rg = (int64_t)(tile * kRows + (sm.active[row] ? row : 0)) * p.n_inst + b;
+      const float k1 = 0.08838834764831845f * kUnscaleL * 1.4426950408889634f;  // raw accumulator -> logit in log2 units
+      const float clip = p.w.tanh_clipping, temperature = p.w.temperature;
+      const int hsh = 16 * colhalf;  // this thread's columns: 32 q + hsh + i
+      const uint32_t t_l = tb + lane_b + hsh;
+      const int nq = (R16 - hsh + 31) >> 5;  // 16-column groups of this thread (warp-uniform)
+      const float* brow = reinterpret_cast<const float*>(sm.A) + row * kLBiasLd + hsh;  // bias in log2 units (gather above)
+      // exchange between the two column halves of a row: behind the bias tile in the (dead) activation region
+      float (*xf)[2][kRows] = reinterpret_cast<float (*)[2][kRows]>(sm.A + kLBiasBytes);            // [4][2][kRows]
+      unsigned char (*xi)[kRows] = reinterpret_cast<unsigned char (*)[kRows]>(sm.A + kLBiasBytes + 4 * 2 * kRows * 4);
+      uint32_t mrow[4];
+      *reinterpret_cast<uint4*>(mrow) = *reinterpret_cast<const uint4*>(sm.mask[row]);
+      int forced = -1;
+      if (p.mode == RRNCO_DECODE_EVALUATE) {
+        forced = step < p.forced_T ? (int)p.forced[rg * p.forced_T + step] : 0;
+        forced = min(max(forced, 0), N - 1);
+      }
+      const uint2 key2 = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+      float m = clip > 0.f ? __fdiv_rn(clip, temperature) : -INFINITY;
+      float ssum = 0.f, best = -INFINITY, bestv = -INFINITY, chk = 0.f;
+      int besti = 255;
+#pragma unroll 1
+      for (int q = 0; q < nq; ++q) {
+        uint32_t v[16];
+        tc05::tmem_ld16(t_l + 32 * q, v);
+        float bv[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bv[i]) = *reinterpret_cast<const float4*>(brow + 32 * q + i);
+        const uint32_t mq = mrow[q] >> hsh;  // mask bits of columns >= N are never set
+        const int cbase = 32 * q + hsh;
+        tc05::tmem_wait_ld();
+        float val[16];
+        if (clip > 0.f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            chk = fmaf(__uint_as_float(v[i]), 0.f, chk);  // NaN / Inf accumulators (fp16 operand overflow) -> NaN, masked columns too
+            const float u = __fadd_rn(ex2a(fmaf(__uint_as_float(v[i]), k1, -bv[i])), 1e-6f);
+            const float th = fmaf(-2.0f, rcpa(fmaf(u, u, 1.0f)), 1.0f);
+            val[i] = ((mq >> i) & 1u) ? __fmul_rn(th, clip) : -INFINITY;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            chk = fmaf(__uint_as_float(v[i]), 0.f, chk);
+            const float l = flog(__fadd_rn(ex2a(fmaf(__uint_as_float(v[i]), k1, -bv[i])), 1e-6f));
+            val[i] = ((mq >> i) & 1u) ? l : -INFINITY;
+          }
+        }
+        if (temperature != 1.0f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) val[i] = __fdiv_rn(val[i], temperature);
+        }
+        float bm = fmaxf(fmaxf(fmaxf(val[0], val[1]), fmaxf(val[2], val[3])), fmaxf(fmaxf(val[4], val[5]), fmaxf(val[6], val[7])));
+        bm = fmaxf(bm, fmaxf(fmaxf(fmaxf(val[8], val[9]), fmaxf(val[10], val[11])), fmaxf(fmaxf(val[12], val[13]), fmaxf(val[14], val[15]))));
+        if (clip <= 0.f && bm > m) {  // unclipped logits: running maximum
+          ssum *= fexp(m - bm);
+          m = bm;
+        }
+        const float ms2 = (m == -INFINITY ? 0.f : m) * 1.4426950408889634f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ssum += ex2a(fmaf(val[i], 1.4426950408889634f, -ms2));
+        if (p.mode == RRNCO_DECODE_SAMPLING) {
+#pragma unroll 1
+          for (int i4 = 0; i4 < 16; i4 += 4) {
+            const float4 gn = gumbel4(make_uint4((uint32_t)rg, (uint32_t)(rg >> 32), (uint32_t)step, (uint32_t)((cbase + i4) >> 2)), key2);
+            const float gv[4] = {gn.x, gn.y, gn.z, gn.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x = i4 == 0 ? val[e] : i4 == 4 ? val[4 + e] : i4 == 8 ? val[8 + e] : val[12 + e];
+              const float key = x + gv[e];
+              const bool better = key > best;
+              best = better ? key : best;
+              bestv = better ? x : bestv;
+              besti = better ? cbase + i4 + e : besti;
+            }
+          }
+        } else {
+          if (bm > best) {  // a new maximum: its first column (the groups come in increasing column order)
+            best = bm;
+            int idx = 15;
+#pragma unroll
+            for (int i = 14; i >= 0; --i) idx = val[i] == bm ? i : idx;
+            besti = cbase + idx;
+          }
+          if (p.mode == RRNCO_DECODE_EVALUATE && (unsigned)(forced - cbase) < 16u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bestv = cbase + i == forced ? val[i] : bestv;
+          }
+        }
+      }
+      if (!(chk == 0.f)) atomicOr(p.status, RRNCO_DEV_NAN_LOGITS);
+      if (p.mode == RRNCO_DECODE_GREEDY) bestv = best;
+      xf[0][colhalf][row] = m;
+      xf[1][colhalf][row] = ssum;
+      xf[2][colhalf][row] = best;
+      xf[3][colhalf][row] = bestv;
+      xi[colhalf][row] = (unsigned char)besti;
+      LSTAMP(17);
+      lean_sync();
+      LSTAMP(18);
+      if (colhalf == 0) {
+        const float m0 = xf[0][0][row], m1 = xf[0][1][row];
+        const float mx = fmaxf(m0, m1);
+        const float se = flog(xf[1][0][row] * fexp(m0 - mx) + xf[1][1][row] * fexp(m1 - mx));
+        int win = 0;  // larger key wins, ties -> lower index
+        if (xf[2][1][row] > xf[2][0][row] || (xf[2][1][row] == xf[2][0][row] && xi[1][row] < xi[0][row])) win = 1;
+        int act = xi[win][row];
+        if (act == 255) act = 0;
+        if (p.mode == RRNCO_DECODE_EVALUATE) {
+          act = forced;
+          win = (act >> 4) & 1;  // the half that owns the forced column recorded its value
+        }
+        const float chosen = __fsub_rn(__fsub_rn(xf[3][win][row], mx), se);
+        const bool feasible = (mrow[act >> 5] >> (act & 31)) & 1u;
+        if (!feasible && sm.active[row]) atomicOr(p.status, RRNCO_DEV_INFEASIBLE);
+        const bool count_leg = kEnv != RRNCO_ENV_ATSP || t_out > 0;
+        len_acc += (double)lean_transition<kEnv>(sm, N, row, act, D, U, closed, count_leg);
+        if (kEnv == RRNCO_ENV_ATSP && t_out == 0) sm.first[row] = (unsigned char)act;
+        lp_acc += (double)chosen;
+        if (sm.active[row] && t_out < p.t_cap) {
+          p.actions[rg * p.t_cap + t_out] = act;
+          if (p.logprob) p.logprob[rg * p.t_cap + t_out] = chosen;
+        }
+      }
+    }
+#else
     // ---- S: select, thread per row: two threads own one rollout, 16-column groups dealt round-robin; three rolled
     // passes over the logits, which stay in TMEM (pass A rewrites them in place) ----
     {
@@ -1065,6 +1204,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         }
       }
     }
+#endif
     LSTAMP(23);
     ++step;
     ++t_out;
@@ -1136,7 +1276,7 @@ int phase_cycles_lean(long long* h_out, int reset) {
 }
 int dispatch_env_lean(const RolloutParams& p, int env, int passes, cudaStream_t st) {
   static_assert(sizeof(LeanSmem<RRNCO_ENV_RCVRPTW>) <= 115712, "two CTAs per SM need <= 113 KB of shared memory each");
-  static_assert(kLBiasBytes + 3 * 2 * kRows * 4 + 2 * kRows <= kRows * kE * 4, "bias tile + exchange arrays fit the A region");
+  static_assert(kLBiasBytes + 4 * 2 * kRows * 4 + 2 * kRows <= kRows * kE * 4, "bias tile + exchange arrays fit the A region");
   switch (env) {
     case RRNCO_ENV_ATSP: return passes == 1 ? launch_lean<RRNCO_ENV_ATSP, 1>(p, st) : launch_lean<RRNCO_ENV_ATSP, 3>(p, st);
     case RRNCO_ENV_RCVRP: return passes == 1 ? launch_lean<RRNCO_ENV_RCVRP, 1>(p, st) : launch_lean<RRNCO_ENV_RCVRP, 3>(p, st);
