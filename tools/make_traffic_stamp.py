@@ -30,7 +30,7 @@ for r in rows:  # one row per (launch id, metric)
     d = per.setdefault(r["ID"], {"name": r["Kernel Name"]})
     v = float(r["Metric Value"].replace(",", ""))
     unit = r["Metric Unit"].lower()
-    scale = {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "byte": 1.0, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6, "second": 1e3}.get(unit, 1.0)
+    scale = {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "byte": 1.0, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6, "second": 1e3, "us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}.get(unit, 1.0)
     d[r["Metric Name"]] = v * scale
 launches = [per[k] for k in sorted(per, key=int)]
 
