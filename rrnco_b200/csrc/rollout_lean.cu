@@ -67,6 +67,12 @@ struct LeanSmem {
   unsigned char cur[kRows], first[kRows], active[kRows], done[kRows];
   uint32_t lhmask[4];
   uint32_t kmax2[kH];                      // max over the keys of |K_h row|^2 (fp32 bits; non-negative floats order as integers)
+  // rcvrp: the capacity mask {c : fl(demand_c + used) > cap} is an upper set in demand order (fl(x + u) is monotone in x), so a
+  // rollout finds it with a 8-probe search over the instance's sorted demands and one precomputed 128-bit suffix mask
+  // instead of 112 add-compare-shift steps per decode step -- bit-exact, the predicate is evaluated as upstream writes it
+  static constexpr int kSorted = kEnv == RRNCO_ENV_RCVRP ? kRows : 1;
+  float sdem[kSorted];                     // demands ascending (ties by node index)
+  uint32_t sufmask[kSorted + 1][4];        // sufmask[K] = nodes of rank >= K
   uint64_t bar_full[kStages], bar_empty[kStages];
   uint64_t bar_step;     // compute -> producer: another decode step follows (or exit)
   uint64_t bar_q;        // compute -> issuer: query tiles written (256 arrivals; also the exit signal)
@@ -262,6 +268,29 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
     if (lane == 0) sm.lhmask[warp] = lh;
   }
   __syncthreads();
+
+  if (kEnv == RRNCO_ENV_RCVRP) {
+    unsigned char* s_rank = sm.A;  // (scratch: the activation region is not in use yet)
+    if (tid < kRows) {
+      const float dk = sm.node[iDem][tid];
+      int r = 0;
+      for (int j = 0; j < kRows; ++j) {
+        const float dj = sm.node[iDem][j];
+        r += (dj < dk || (dj == dk && j < tid)) ? 1 : 0;
+      }
+      s_rank[tid] = (unsigned char)r;
+      sm.sdem[r % SmemT::kSorted] = dk;
+    }
+    __syncthreads();
+    if (tid <= kRows) {  // suffix masks: nodes of rank >= tid
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      for (int c = 0; c < kRows; ++c)
+        if ((int)s_rank[c] >= tid) w[c >> 5] |= 1u << (c & 31);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sm.sufmask[tid % (SmemT::kSorted + 1)][k] = w[k];
+    }
+    __syncthreads();
+  }
 
   // ---------------- rollout state init ----------------
   const int num_loc = kEnv == RRNCO_ENV_ATSP ? N : N - 1;
@@ -561,6 +590,17 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         uint32_t bits2[2];
         const uint2 visw = *reinterpret_cast<const uint2*>(&sm.vis[row][2 * dh]);
         bool missing = false, carrying_b = false;
+        uint32_t over2[2] = {0u, 0u};  // rcvrp: capacity-mask words 2 dh, 2 dh + 1
+        if (kEnv == RRNCO_ENV_RCVRP) {
+          int pos = 0;  // number of nodes, in demand order, that still fit: lower bound of the (monotone) predicate
+#pragma unroll
+          for (int stp = kRows / 2; stp >= 1; stp >>= 1)
+            pos += __fadd_rn(sm.sdem[(pos + stp - 1) % SmemT::kSorted], f0) > cap ? 0 : stp;
+          pos += __fadd_rn(sm.sdem[pos % SmemT::kSorted], f0) > cap ? 0 : 1;
+          const uint2 sw = *reinterpret_cast<const uint2*>(&sm.sufmask[pos % (SmemT::kSorted + 1)][2 * dh]);
+          over2[0] = sw.x;
+          over2[1] = sw.y;
+        }
         if (kEnv == RRNCO_ENV_RCVRPTW) {
           uint32_t m = (sm.lhmask[2 * dh] & ~visw.x) | (sm.lhmask[2 * dh + 1] & ~visw.y);
           m |= __shfl_xor_sync(0xffffffffu, m, 16);
@@ -573,10 +613,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           const uint32_t valid = N >= c0 + 32 ? 0xffffffffu : (N > c0 ? (1u << (N - c0)) - 1u : 0u);
           uint32_t ok = ~(k ? visw.y : visw.x) & valid;
           if (kEnv == RRNCO_ENV_RCVRP) {
-            uint32_t bad = 0u;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) bad |= (__fadd_rn(sm.node[iDem][c0 + i], f0) > cap ? 1u : 0u) << i;
-            ok &= ~bad;
+            ok &= ~over2[k];
           } else if (kEnv == RRNCO_ENV_RCVRPTW) {
             uint32_t good = 0u;
 #pragma unroll 2
@@ -1275,7 +1312,8 @@ int phase_cycles_lean(long long* h_out, int reset) {
   return RRNCO_OK;
 }
 int dispatch_env_lean(const RolloutParams& p, int env, int passes, cudaStream_t st) {
-  static_assert(sizeof(LeanSmem<RRNCO_ENV_RCVRPTW>) <= 115712, "two CTAs per SM need <= 113 KB of shared memory each");
+  static_assert(sizeof(LeanSmem<RRNCO_ENV_RCVRPTW>) <= 115712 && sizeof(LeanSmem<RRNCO_ENV_RCVRP>) <= 115712 &&
+                    sizeof(LeanSmem<RRNCO_ENV_ATSP>) <= 115712, "two CTAs per SM need <= 113 KB of shared memory each");
   static_assert(kLBiasBytes + 4 * 2 * kRows * 4 + 2 * kRows <= kRows * kE * 4, "bias tile + exchange arrays fit the A region");
   switch (env) {
     case RRNCO_ENV_ATSP: return passes == 1 ? launch_lean<RRNCO_ENV_ATSP, 1>(p, st) : launch_lean<RRNCO_ENV_ATSP, 3>(p, st);
