@@ -585,6 +585,15 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           st[3] = rem;
         }
       }
+      float4 pq0[8];  // first half of the query row: in flight while the mask words are computed
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        pq0[cc] = *reinterpret_cast<const float4*>(src1 + dh * 64 + cc * 4);
+        if (kEnv == RRNCO_ENV_ATSP && src2) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(src2 + dh * 64 + cc * 4));
+          pq0[cc] = make_float4(pq0[cc].x + w.x, pq0[cc].y + w.y, pq0[cc].z + w.z, pq0[cc].w + w.w);
+        }
+      }
       // action mask (rcvrp/env.py:183-195, rmtvrp/env.py:343-428, atsp/env.py:107-111): words 2 dh, 2 dh + 1
       {
         uint32_t bits2[2];
@@ -655,10 +664,9 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         }
         *reinterpret_cast<uint2*>(&sm.mask[row][2 * dh]) = make_uint2(bits2[0], bits2[1]);
       }
-      // query rows, 4 chunks of 8 dims at a time (8 float4 loads in flight)
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        float4 pq[8];
+      // query rows, 4 chunks of 8 dims at a time.  The 8 float4 loads of the first half were issued BEFORE the mask words were
+      // computed (pq0: their L2 latency hides under the mask code), those of the second half before the first is processed.
+      auto load_q = [&](int half, float4 (&pq)[8]) {
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
           pq[cc] = *reinterpret_cast<const float4*>(src1 + dh * 64 + half * 32 + cc * 4);
@@ -667,6 +675,8 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
             pq[cc] = make_float4(pq[cc].x + w.x, pq[cc].y + w.y, pq[cc].z + w.z, pq[cc].w + w.w);
           }
         }
+      };
+      auto write_q = [&](int half, const float4 (&pq)[8]) {
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const int c8 = dh * 8 + half * 4 + cc;
@@ -689,6 +699,12 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           *reinterpret_cast<uint4*>(&a_hi[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(&a_lo[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
         }
+      };
+      {
+        float4 pq1[8];
+        load_q(1, pq1);
+        write_q(0, pq0);
+        write_q(1, pq1);
       }
     }
     tc05::fence_proxy_async();
