@@ -927,17 +927,14 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
       tc05::mbar_arrive(&sm.bar_lk);
       LSTAMP(12);
     }
-    lean_sync();
-    LSTAMP(13);  // every thread has read its residual: the activation region may be overwritten by the bias tile
-
     // bias rows of the rollouts (alpha . D[cur,:] + beta . Dur[cur,:]) -> fp32 tile in the (dead) activation region while
-    // the logits MMAs run: coalesced, one warp per 16 rollouts
+    // the logits MMAs run: coalesced, one warp per 16 rollouts, 8 rollouts at a time (up to 32 / 64 independent L2 loads in
+    // flight per lane before the first store).  The loads of the first 8 are issued BEFORE the barrier that frees the
+    // activation region (only the stores need it).
     {
       float* btile = reinterpret_cast<float*>(sm.A);
-      // 8 rollouts at a time: up to 32 (64 with durations) independent L2 loads in flight per lane before the first store
-#pragma unroll 1
-      for (int i0 = 0; i0 < 16; i0 += 8) {
-        float bias[8][4];
+      float bias[8][4];
+      auto load_rows = [&](int i0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int cur_s = sm.cur[warp * 16 + i0 + i];
@@ -955,6 +952,8 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
             bias[i][cq] = bv;
           }
         }
+      };
+      auto store_rows = [&](int i0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -962,7 +961,13 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
             const int c = cq * 32 + lane;
             if (c < R16) btile[(warp * 16 + i0 + i) * kLBiasLd + c] = bias[i][cq];
           }
-      }
+      };
+      load_rows(0);
+      lean_sync();
+      LSTAMP(13);  // every thread has read its residual: the activation region may be overwritten by the bias tile
+      store_rows(0);
+      load_rows(8);
+      store_rows(8);
     }
     LSTAMP(14);
     lean_sync();
