@@ -685,6 +685,18 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
           st[3] = rem;
         }
       }
+      float4 pq0[8];  // first half of the query row: in flight while the mask words are computed
+      {
+        const int colb = kPair ? 64 * (int)rank + 32 * dh : 64 * dh;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          pq0[cc] = *reinterpret_cast<const float4*>(src1 + colb + cc * 4);
+          if (kEnv == RRNCO_ENV_ATSP && src2) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(src2 + colb + cc * 4));
+            pq0[cc] = make_float4(pq0[cc].x + w.x, pq0[cc].y + w.y, pq0[cc].z + w.z, pq0[cc].w + w.w);
+          }
+        }
+      }
       // action mask (rcvrp/env.py:183-195, rmtvrp/env.py:343-428, atsp/env.py:107-111): words [16 dh, 16 dh + 16)
       {
         const int w_lo = dh * (kGWords / 2), w_hi = min(W, w_lo + kGWords / 2);
@@ -747,12 +759,11 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
           sm.mask[row][0] = word0;
         }
       }
-      // query rows, 4 chunks of 8 dims at a time (8 float4 loads in flight).  A CTA of a pair needs the columns of its own
-      // heads only (the peer writes the other half of the glimpse tile): 32 columns per lane instead of 64
-#pragma unroll 1
-      for (int half = 0; half < (kPair ? 1 : 2); ++half) {
+      // query rows, 4 chunks of 8 dims at a time.  A CTA of a pair needs the columns of its own heads only (the peer writes
+      // the other half of the glimpse tile): 32 columns per lane instead of 64.  The 8 float4 loads of the first (only)
+      // half were issued before the mask words were computed (pq0): their L2 latency hides under the mask code.
+      auto load_q = [&](int half, float4 (&pq)[8]) {
         const int colb = kPair ? 64 * (int)rank + 32 * dh : 64 * dh + 32 * half;
-        float4 pq[8];
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
           pq[cc] = *reinterpret_cast<const float4*>(src1 + colb + cc * 4);
@@ -761,6 +772,9 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
             pq[cc] = make_float4(pq[cc].x + w.x, pq[cc].y + w.y, pq[cc].z + w.z, pq[cc].w + w.w);
           }
         }
+      };
+      auto write_q = [&](int half, const float4 (&pq)[8]) {
+        const int colb = kPair ? 64 * (int)rank + 32 * dh : 64 * dh + 32 * half;
         float qn2 = 0.f;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -790,6 +804,14 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
           *reinterpret_cast<uint4*>(&a_hi[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(&a_lo[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
         }
+      };
+      if (kPair) {
+        write_q(0, pq0);
+      } else {
+        float4 pq1[8];
+        load_q(1, pq1);
+        write_q(0, pq0);
+        write_q(1, pq1);
       }
     }
     {  // row sums of the softmax start from zero
