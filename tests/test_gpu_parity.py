@@ -1189,3 +1189,41 @@ def test_full_size_rcvrp_rollout_properties(rb):
     # augmentation copies share matrices and (here) differ only by embeddings: best-of reduction shape
     best = rb.unbatchify(out["reward"], (A, S)).max(-1)[0].max(-1)[0]
     assert best.shape == (B,)
+
+
+def test_full_size_c4_rollout_properties(rb):
+    """BASELINE config C4 at its full size (ATSP n = 1000, 64 instances x 100 starts, 999 decode steps) through the
+    key-tiled fused kernel with CTA pairs: every tour a permutation, in-kernel reward == the independent tour-reward kernel,
+    log-likelihoods finite and negative, the evaluate replay of the greedy tours reproduces them, two runs are bitwise
+    identical, and a sample of rollouts is re-decoded by the per-step pipeline."""
+    name, n, B, S = "atsp", 1000, 64, 100
+    raw = synth.make_instances(name, B, n, seed=31)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    td = env.reset(lite(rb, raw))
+    row, col = synth.random_embeddings(B, n, seed=32)
+    pol = make_policy(rb, name, omodel.init_decoder_params(name, seed=33), row.to(dev), col.to(dev))
+    before = rb.models.FALLBACKS["softmax_range"]
+    out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    assert rb.models.FALLBACKS["softmax_range"] == before  # served by the fused kernel (some CTAs in exact-shift mode)
+    acts = out["actions"]
+    assert acts.shape == (B * S, n)
+    assert (acts.sort(1)[0] == torch.arange(n, device=dev)).all()
+    assert (acts[:, 0].view(S, B) == (torch.arange(S, device=dev) % n)[:, None]).all()  # select_start_nodes
+    from rrnco_b200.envs import tour_reward
+    real, norm = tour_reward(acts, td["distance_matrix"], False, None, td["min_distance"], td["max_distance"])
+    assert rel(norm, out["normalized_reward"]) < 1e-6 and rel(real, out["reward"]) < 1e-6
+    ll = out["log_likelihood"]
+    assert torch.isfinite(ll).all() and (ll < 0).all()
+    again = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    assert torch.equal(again["actions"], acts) and torch.equal(again["log_likelihood"], ll)
+    ev = pol(td, env, phase="val", num_starts=S, actions=acts[:, 1:])
+    assert torch.equal(ev["actions"], acts)
+    assert (ev["log_likelihood"] - ll).abs().max() < 1e-4
+    # two instances again through the per-step kernels (running-maximum softmax, three-pass select)
+    sub = rb.TensorDictLite({k: v[:2] for k, v in raw.items()}, batch_size=[2])
+    pol2 = make_policy(rb, name, omodel.init_decoder_params(name, seed=33), row[:2].to(dev), col[:2].to(dev))
+    pol2.large_n_path = "stepwise"
+    ref = pol2(env.reset(lite(rb, sub)), env, phase="val", decode_type="multistart_greedy", num_starts=S)
+    mine = acts.view(S, B, n)[:, :2].reshape(2 * S, n)
+    same = (mine == ref["actions"]).all(1)
+    assert same.float().mean() >= 0.97, same.float().mean()
