@@ -338,6 +338,22 @@ int rrnco_nab_pack(const float* dist_w1, const float* dist_b1, const float* dist
 int rrnco_nab_gating(int64_t n_inst, int32_t n_nodes, const float* coords, const float* cost, int32_t transpose_cost,
                      const float* packed, float scale, int32_t variant, float* out, void* stream);
 
+/* Duration-channel variant (rcvrptw encoder, use_duration_matrix = True): three MLPs (cost, angle, duration) and the gate
+ * Linear(3E,E) - SiLU - Linear(E,3) - softmax(. / exp(temperature)); attn_freenet.py:226-238,268-281.  The layers that are
+ * linear in the hidden vectors are collapsed at pack time (fp64); the remaining [pairs x 3E] . [3E x E] contraction runs on
+ * tcgen05 (three-term fp16 split, fp32-faithful) over tiles of 128 pairs, the A operand generated on the fly from the
+ * pair's scalars, the weight slices streamed by TMA; SiLU / E -> 3 / softmax / blend in the epilogue.
+ *   d_params: DEVICE array of 19 device pointers, nn.Linear layouts: dist_emb.0.weight, .0.bias, .2.weight, .2.bias, the same
+ *             four of angle_emb and of dur_emb, gate.0.weight [E,3E], gate.0.bias, gate.2.weight [3,E], gate.2.bias,
+ *             gate_temperature [1], out_lin.weight [1,E], out_lin.bias [1]
+ *   packed:   rrnco_nab_dur_packed_bytes() bytes, 16-byte aligned; status: sticky device word (RRNCO_DEV_NAN_LOGITS on an
+ *             fp16 operand overflow: |weights| >= 255 or hidden activations >= 4094)
+ *   transpose != 0: cost AND duration are read transposed (col-encoding block, attn_freenet.py:476-486). */
+int64_t rrnco_nab_dur_packed_bytes(void);
+int rrnco_nab_dur_pack(const float* const* d_params, void* packed, uint32_t* status, void* stream);
+int rrnco_nab_dur_gating(int64_t n_inst, int32_t n_nodes, const float* coords, const float* cost, const float* duration,
+                         int32_t transpose, const void* packed, float scale, float* out, uint32_t* status, void* stream);
+
 /* The O(N^2) part of one attention-free block fused (attn_freenet.py:424-432 + AFTFull.forward :309-327, n_nodes <= 128):
  *   out[b,i,:] = sigmoid(q[b,i,:]) * (sum_j a_ij E2[j,:]) / (sum_j a_ij E1[j,:]),   a_ij = exp(softmax_j(scale * adapt_bias[b,i,j])),
  *   E1 = exp(softmax over the tokens of k[b]), E2 = E1 * v[b]   -- i.e. AFTFull without its four Linear layers (q / k / v are

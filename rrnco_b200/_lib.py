@@ -56,6 +56,9 @@ _SIGNATURES = {
     "rrnco_set_start_split": (C.c_int, [C.c_int32]),
     "rrnco_nab_packed_floats": (C.c_int64, []),
     "rrnco_nab_pack": (C.c_int, [_f] * 14),
+    "rrnco_nab_dur_packed_bytes": (C.c_int64, []),
+    "rrnco_nab_dur_pack": (C.c_int, [_f, _f, _f, _f]),
+    "rrnco_nab_dur_gating": (C.c_int, [C.c_int64, C.c_int32, _f, _f, _f, C.c_int32, _f, C.c_float, _f, _f, _f]),
     "rrnco_aft_nab": (C.c_int, [C.c_int64, C.c_int32, _f, _f, _f, _f, _f, C.c_int32, _f, C.c_float, _f, _f]),
     "rrnco_nab_gating": (C.c_int, [C.c_int64, C.c_int32, _f, _f, C.c_int32, _f, C.c_float, C.c_int32, _f, _f]),
     "rrnco_rollout_tile_rows": (C.c_int32, [C.c_int32, C.c_int32, C.c_int64, C.c_int32]),

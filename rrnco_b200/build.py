@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librrnco_b200.so")
-SOURCES = ["env_kernels.cu", "rollout_kernel.cu", "rollout_kernel_tc.cu", "rollout_lean.cu", "rollout_tiled.cu", "cache_kernel.cu", "ffn_tc_kernel.cu", "step_kernels.cu", "encoder_kernels.cu"]
+SOURCES = ["env_kernels.cu", "rollout_kernel.cu", "rollout_kernel_tc.cu", "rollout_lean.cu", "rollout_tiled.cu", "cache_kernel.cu", "ffn_tc_kernel.cu", "step_kernels.cu", "encoder_kernels.cu", "encoder_dur_kernel.cu"]
 # development switches (never set for the product build): per-phase cycle stamps, device printf, raw lo split
 NVCC_FLAGS = [f"-D{k}" for k in ("RRNCO_PHASE_STAMPS", "RRNCO_DEBUG_PRINT", "RRNCO_SPLIT_LO_RAW", "RRNCO_LEAN_SELECT3") if os.environ.get(k)] + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

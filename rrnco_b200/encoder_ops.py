@@ -4,8 +4,9 @@
 reference module's state_dict loads unchanged); its forward is ONE kernel (`rrnco_nab_gating`) that never materialises the
 [B, N, N, E] embeddings upstream builds twice per block.  `patch_encoder` swaps it into an upstream `RRNetEncoder`
 (`encoder.net.layers[i].{row,col}_encoding_block.angle_distance_fusion`) for the inference path (test.py / validation).
-The duration-channel variant (rcvrptw: Linear(3E, E) -> SiLU -> Linear(E, 3) gate, softmax with a temperature) keeps
-upstream's module: its gate is not linear in the embeddings, so it does not collapse to scalar functions.
+The duration-channel variant (rcvrptw: Linear(3E, E) -> SiLU -> Linear(E, 3) gate, softmax with a temperature) does not
+collapse to scalar functions (its gate is not linear in the embeddings): what remains after collapsing the linear layers is a
+[pairs x 3E] x [3E x E] contraction, which runs on tcgen05 (`rrnco_nab_dur_gating`, csrc/encoder_dur_kernel.cu).
 No CPU fallback: a host tensor or a missing library raises.
 """
 from __future__ import annotations
@@ -24,16 +25,38 @@ class DistAngleFusion(nn.Module):
         super().__init__()
         if embed_dim != 128:
             raise NotImplementedError("the kernels are built for embed_dim = 128 (experiment/rrnet.yaml)")
-        if use_duration_matrix:
-            raise NotImplementedError("duration-channel gate (rcvrptw): use the reference module; only the ATSP / RCVRP "
-                                      "variant (attn_freenet.py:239, encoder.py:63-66) collapses to the fused kernel")
-        self.embed_dim = embed_dim
+        self.use_duration_matrix = bool(use_duration_matrix)
+        self.embed_dim = embed_dim // 2 if use_duration_matrix else embed_dim  # (upstream's attribute, attn_freenet.py:210-214)
         self.dist_emb = nn.Sequential(nn.Linear(1, embed_dim), nn.ReLU(), nn.Linear(embed_dim, embed_dim))
         self.angle_emb = nn.Sequential(nn.Linear(1, embed_dim), nn.ReLU(), nn.Linear(embed_dim, embed_dim))
-        self.gate = nn.Sequential(nn.Linear(embed_dim * 2, 1), nn.Sigmoid())
+        if use_duration_matrix:  # attn_freenet.py:226-238
+            self.dur_emb = nn.Sequential(nn.Linear(1, embed_dim), nn.ReLU(), nn.Linear(embed_dim, embed_dim))
+            self.gate = nn.Sequential(nn.Linear(3 * embed_dim, embed_dim), nn.SiLU(), nn.Linear(embed_dim, 3))
+            self.gate_temperature = nn.Parameter(torch.tensor(5.0))
+        else:
+            self.gate = nn.Sequential(nn.Linear(embed_dim * 2, 1), nn.Sigmoid())
         self.out_lin = nn.Linear(embed_dim, 1)
         self._packed = None
         self._packed_key = None
+        self._keep = None
+        self.check_overflow = True  # read the kernel's status word back after each duration-gate call (one host sync)
+
+    def _packed_duration(self) -> torch.Tensor:
+        ps = [*(m for seq in (self.dist_emb, self.angle_emb, self.dur_emb) for m in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)),
+              self.gate[0].weight, self.gate[0].bias, self.gate[2].weight, self.gate[2].bias, self.gate_temperature,
+              self.out_lin.weight, self.out_lin.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._packed is None or self._packed_key != key:
+            dev = ps[0].device
+            cont = [p.detach().float().contiguous().reshape(-1) for p in ps]
+            ptrs = torch.tensor([c.data_ptr() for c in cont], dtype=torch.int64, device=dev)
+            packed = torch.empty(_lib.lib().rrnco_nab_dur_packed_bytes(), dtype=torch.uint8, device=dev)
+            status = torch.zeros(1, dtype=torch.int32, device=dev)
+            call("rrnco_nab_dur_pack", ptr(ptrs), ptr(packed), ptr(status), stream_ptr(dev))
+            if int(status.item()):
+                raise AssertionError("DistAngleFusion: collapsed gate weights outside the fp16 operand range (|w| >= 255)")
+            self._packed, self._packed_key, self._keep = packed, key, cont
+        return self._packed
 
     def packed_parameters(self) -> torch.Tensor:
         """The module collapsed into four E-vectors + constants (rrnco_nab_pack); cached until a parameter changes."""
@@ -54,10 +77,10 @@ class DistAngleFusion(nn.Module):
         """adapt_bias [B, N, N] (times `scale`, e.g. the block's alpha).  `cost_mat` may be the transposed VIEW the
         col-encoding block passes (attn_freenet.py:480-486): it is read through its base, never copied.
         `variant` 0 = piecewise-linear segment tables (default), 1 = brute-force sum over the hidden units (cross-check)."""
-        if duration_mat is not None:
-            raise NotImplementedError("duration-channel gate: use the reference module")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("forward-only kernel: call under torch.no_grad() / inference_mode (test.py path)")
+        if (duration_mat is not None) != self.use_duration_matrix:
+            raise ValueError("duration_mat must be given exactly when the module was built with use_duration_matrix=True")
         B, N, _ = cost_mat.shape
         coords = coords.float().contiguous()
         transposed = 0
@@ -65,6 +88,17 @@ class DistAngleFusion(nn.Module):
             cost_mat, transposed = cost_mat.transpose(1, 2), 1
         cost_mat = cost_mat.float().contiguous()
         out = torch.empty((B, N, N), dtype=torch.float32, device=cost_mat.device)
+        if self.use_duration_matrix:  # three-way gate: tcgen05 kernel (encoder_dur_kernel.cu)
+            dur = duration_mat
+            if transposed:  # the col-encoding block transposes both matrices (attn_freenet.py:476-486)
+                dur = dur.transpose(1, 2)
+            dur = dur.float().contiguous()
+            status = torch.zeros(1, dtype=torch.int32, device=out.device)
+            call("rrnco_nab_dur_gating", B, N, ptr(coords), ptr(cost_mat), ptr(dur), transposed, ptr(self._packed_duration()),
+                 float(scale), ptr(out), ptr(status), stream_ptr(out.device))
+            if self.check_overflow and int(status.item()):
+                raise AssertionError("DistAngleFusion: hidden activations outside the fp16 operand range (>= 4094)")
+            return out
         call("rrnco_nab_gating", B, N, ptr(coords), ptr(cost_mat), transposed, ptr(self.packed_parameters()), float(scale),
              int(variant), ptr(out), stream_ptr(cost_mat.device))
         return out
@@ -115,6 +149,14 @@ def patch_encoder(encoder: nn.Module, fuse_aft: bool = True) -> int:
     import types
     n = 0
     for block in encoder.modules():
+        # rcvrptw blocks: attribute `neural_adaptive_bias` holding a DistAngleFusion with the duration channel (:380-384)
+        refd = getattr(block, "neural_adaptive_bias", None)
+        if refd is not None and not isinstance(refd, DistAngleFusion) and hasattr(refd, "dur_emb") and hasattr(refd, "gate_temperature"):
+            mine = DistAngleFusion(128, use_duration_matrix=True).to(next(refd.parameters()).device)
+            mine.load_state_dict(refd.state_dict(), strict=True)
+            block.neural_adaptive_bias = mine
+            n += 1
+            continue
         ref = getattr(block, "angle_distance_fusion", None)
         if ref is None or isinstance(ref, DistAngleFusion) or hasattr(ref, "dur_emb"):
             continue

@@ -61,8 +61,9 @@ def test_mirror_module_has_the_reference_parameter_names():
     m = rb.DistAngleFusion(128)
     assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in params["nodur"].items()}
     m.load_state_dict(params["nodur"], strict=True)
-    with pytest.raises(NotImplementedError):
-        rb.DistAngleFusion(128, use_duration_matrix=True)
+    md = rb.DistAngleFusion(128, use_duration_matrix=True)  # rcvrptw variant (attn_freenet.py:226-238)
+    assert {k: tuple(v.shape) for k, v in md.state_dict().items()} == {k: tuple(v.shape) for k, v in params["dur"].items()}
+    md.load_state_dict(params["dur"], strict=True)
 
 
 @pytest.mark.gpu
@@ -240,3 +241,40 @@ def test_patch_encoder_fuses_the_block():
         assert rb.patch_encoder(blk) == 1
         got = blk(row, col, cost.transpose(1, 2), coords)
     assert (got - want).abs().max() < 2e-5
+
+
+@pytest.mark.gpu
+def test_duration_gate_kernel_matches_reference_fixture_and_oracle():
+    """rcvrptw variant on tcgen05 (encoder_dur_kernel.cu): the fixture recorded from the reference module (parameters x3),
+    both matrix orientations; then default initialisation at n = 50 (2601 pairs per instance: ragged last tile) vs the
+    CPU restatement; the col-encoding block's transposed views; the status word on an operand overflow."""
+    import rrnco_b200 as rb
+    dev = "cuda"
+    t, params = _fixture()
+    m = rb.DistAngleFusion(128, use_duration_matrix=True).to(dev)
+    m.load_state_dict(params["dur"], strict=True)
+    coords, cost, dur = t["coords"].to(dev), t["cost"].to(dev), t["dur"].to(dev)
+    with torch.no_grad():
+        out = m(coords, cost, dur)
+        outT = m(coords, cost.transpose(1, 2), dur.transpose(1, 2))
+        out2 = m(coords, cost, dur, scale=1.9)
+    assert (out.cpu() - t["dur.bias"]).abs().max() < 3e-5, (out.cpu() - t["dur.bias"]).abs().max()
+    assert (outT.cpu() - t["dur.bias_T"]).abs().max() < 3e-5
+    assert torch.allclose(out2, out * 1.9, rtol=1e-6, atol=1e-6)
+    torch.manual_seed(21)
+    m2 = rb.DistAngleFusion(128, use_duration_matrix=True).to(dev)
+    p2 = {k: v.detach().cpu() for k, v in m2.state_dict().items()}
+    g = torch.Generator().manual_seed(22)
+    B, N = 7, 51
+    coords = torch.rand(B, N, 2, generator=g)
+    cost, dur = torch.rand(B, N, N, generator=g) * 1.4, torch.rand(B, N, N, generator=g)
+    want = oenc.dist_angle_fusion(p2, coords, cost, dur)
+    with torch.no_grad():
+        got = m2(coords.to(dev), cost.to(dev), dur.to(dev))
+        again = m2(coords.to(dev), cost.to(dev), dur.to(dev))
+    assert (got.cpu() - want).abs().max() < 3e-6 * max(1.0, want.abs().max().item()), (got.cpu() - want).abs().max()
+    assert torch.equal(got, again)  # one issuing thread, fixed order: bitwise reproducible
+    with torch.no_grad(), pytest.raises(ValueError):
+        m2(coords.to(dev), cost.to(dev))
+    with torch.no_grad(), pytest.raises(AssertionError, match="fp16 operand range"):
+        m2(coords.to(dev), cost.to(dev) * 1e6, dur.to(dev))
