@@ -620,6 +620,37 @@ def run_ours(args, rank, world, local_rank):
             "frac": aft_bytes / (ms_f * 1e-3) / 1e9 / peaks()[0],
             "fp32_fma_per_launch": Bn * 2 * (N_LOC + 1) ** 2 * 128,
             "what": "q, k, v read + y written ([B,N,128] fp32 each) + the cost matrix once = algorithmic bytes"}
+        # rcvrptw variant (duration channel, three-way gate) on tcgen05, at config C3's batch (1024 instances)
+        torch.manual_seed(1235)
+        modd = rb.DistAngleFusion(128, use_duration_matrix=True).to(dev)
+        modd.check_overflow = False
+        Bd = B
+        durm = torch.rand(Bd, N_LOC + 1, N_LOC + 1, device=dev, generator=g)
+
+        def torch_materialised(nb):  # upstream's op sequence on the GPU (materialises three [B,N,N,E] embeddings), small batch
+            import torch.nn.functional as F
+            c, u = cost[:nb].unsqueeze(-1), durm[:nb].unsqueeze(-1)
+            diff = coords[:nb].unsqueeze(2) - coords[:nb].unsqueeze(1)
+            a = torch.atan2(diff[..., 1], diff[..., 0]).unsqueeze(-1)
+            d, an, du = modd.dist_emb(c), modd.angle_emb(a), modd.dur_emb(u)
+            gt = F.softmax(modd.gate(torch.cat([d, an, du], -1)) / modd.gate_temperature.exp(), -1)
+            return modd.out_lin(gt[..., [0]] * d + gt[..., [1]] * an + gt[..., [2]] * du).squeeze(-1)
+        with torch.no_grad():
+            ms_d = time_launch(lambda: modd(coords[:Bd], cost[:Bd], durm), reps=10)
+            nb = 64
+            ms_t = time_launch(lambda: torch_materialised(nb), reps=3, warm=1)
+            errd = (modd(coords[:nb], cost[:nb], durm[:nb]) - torch_materialised(nb)).abs().max().item()
+        pairs_d = Bd * (N_LOC + 1) ** 2
+        flops_issued = pairs_d * 3 * 2 * 384 * 128  # three split terms
+        entry["duration_gate"] = {
+            "kernel": "rrnco::nab_dur_kernel (DistAngleFusion.forward with the duration channel, attn_freenet.py:242-289: "
+                      "[pairs x 3E] x [3E x E] on tcgen05, three-term fp16 split, A operand generated on the fly)",
+            "instances": Bd, "pairs": pairs_d, "ms_per_launch": ms_d,
+            "issued_tflops": flops_issued / (ms_d * 1e-3) / 1e12, "tensor_peak_tflops": peaks()[1],
+            "tensor_frac_issued": flops_issued / (ms_d * 1e-3) / 1e12 / peaks()[1],
+            "algorithmic_bytes_per_launch": 12 * pairs_d, "achieved": 12 * pairs_d / (ms_d * 1e-3) / 1e9, "unit": "GB/s",
+            "ms_torch_materialised_same_batch_extrapolated": ms_t * Bd / nb, "torch_sample_instances": nb,
+            "max_abs_diff_vs_torch_fp32": errd}
         if not args.no_cpu_baseline:
             from oracle import encoder as oenc
             torch.set_num_threads(os.cpu_count() or 1)
