@@ -41,3 +41,10 @@ with torch.no_grad():
     o = m(torch.rand(2, 37, 2, device=dev), torch.rand(2, 37, 37, device=dev).transpose(1, 2))
 torch.cuda.synchronize()
 print("nab ok", float(o.mean()))
+with torch.no_grad():
+    y = rb.aft_nab(torch.randn(2, 37, 128, device=dev), torch.randn(2, 37, 128, device=dev), torch.randn(2, 37, 128, device=dev),
+                   torch.rand(2, 37, 2, device=dev), torch.rand(2, 37, 37, device=dev), m, scale=0.7)
+    md = rb.DistAngleFusion(128, use_duration_matrix=True).to(dev)
+    od = md(torch.rand(3, 29, 2, device=dev), torch.rand(3, 29, 29, device=dev), torch.rand(3, 29, 29, device=dev).transpose(1, 2).contiguous().transpose(1, 2))
+torch.cuda.synchronize()
+print("aft_nab ok", float(y.mean()), "| duration gate ok", float(od.mean()))
