@@ -358,7 +358,8 @@ int rrnco_nab_dur_gating(int64_t n_inst, int32_t n_nodes, const float* coords, c
  *   out[b,i,:] = sigmoid(q[b,i,:]) * (sum_j a_ij E2[j,:]) / (sum_j a_ij E1[j,:]),   a_ij = exp(softmax_j(scale * adapt_bias[b,i,j])),
  *   E1 = exp(softmax over the tokens of k[b]), E2 = E1 * v[b]   -- i.e. AFTFull without its four Linear layers (q / k / v are
  *   to_q(x) / to_k(y) / to_v(y), the caller applies `project`).  adapt_bias comes from the segment tables of rrnco_nab_pack
- *   and never reaches memory; E1 / E2 of the instance stay in shared memory.  q, k, v, out fp32 [B,N,128] (16-byte aligned). */
+ *   and never reaches memory; E1 / E2 of the instance stay in shared memory.  q, k, v, out fp32 [B,N,128] (16-byte aligned).
+ *   packed == NULL: `cost` holds adapt_bias [B,N,N] itself (e.g. the output of rrnco_nab_dur_gating), coords is unused. */
 int rrnco_aft_nab(int64_t n_inst, int32_t n_nodes, const float* q, const float* k, const float* v, const float* coords,
                   const float* cost, int32_t transpose_cost, const float* packed, float scale, float* out, void* stream);
 

@@ -212,6 +212,7 @@ constexpr int kAftThreads = 256;
 constexpr int kAftRows = 4;            // rows per warp per pass
 constexpr int kAftMaxNodes = 128;      // four key slots per lane
 
+template <bool kGiven>  // kGiven: `cost` holds the adapt_bias itself (any gate variant, e.g. from rrnco_nab_dur_gating)
 __global__ void __launch_bounds__(kAftThreads, 2) aft_nab_kernel(int N, const float* __restrict__ Q, const float* __restrict__ K,
                                                                  const float* __restrict__ V, const float* __restrict__ coords,
                                                                  const float* __restrict__ cost, int transpose_cost,
@@ -228,9 +229,11 @@ __global__ void __launch_bounds__(kAftThreads, 2) aft_nab_kernel(int N, const fl
   const float* Kb = K + b * (int64_t)N * kE;
   const float* Vb = V + b * (int64_t)N * kE;
   const float* Qb = Q + b * (int64_t)N * kE;
-  for (int i = tid; i < 2 * kNabTable; i += kAftThreads) st[i] = packed[kNabBrute + i];
-  if (tid < 4) st[2 * kNabTable + tid] = packed[kE * 8 + tid];
-  if (tid < N) xy[tid] = __ldg(reinterpret_cast<const float2*>(coords + b * (int64_t)N * 2) + tid);
+  if (!kGiven) {
+    for (int i = tid; i < 2 * kNabTable; i += kAftThreads) st[i] = packed[kNabBrute + i];
+    if (tid < 4) st[2 * kNabTable + tid] = packed[kE * 8 + tid];
+    if (tid < N) xy[tid] = __ldg(reinterpret_cast<const float2*>(coords + b * (int64_t)N * 2) + tid);
+  }
   // ---- E1 = exp(softmax over the tokens (dim = 1) of K), E2 = E1 * V (attn_freenet.py:320-322): thread = (column, row half) ----
   {
     const int d = tid & (kE - 1), half = tid >> 7;
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(kAftThreads, 2) aft_nab_kernel(int N, const fl
 #pragma unroll
     for (int r = 0; r < kAftRows; ++r) {
       const int i = min(i0 + r, N - 1);  // (rows beyond N repeat the last one; they are not stored)
-      const float2 pi = xy[i];
+      const float2 pi = kGiven ? make_float2(0.f, 0.f) : xy[i];
       float bias[4];
       float mx = -INFINITY;
 #pragma unroll
@@ -276,13 +279,17 @@ __global__ void __launch_bounds__(kAftThreads, 2) aft_nab_kernel(int N, const fl
         bias[m] = -INFINITY;
         if (j < N) {
           const float c = transpose_cost ? __ldg(cb + (size_t)j * N + i) : __ldg(cb + (size_t)i * N + j);
-          const float2 pj = xy[j];
-          const float th = atan2f(pi.y - pj.y, pi.x - pj.x);
-          const float4 qd = *reinterpret_cast<const float4*>(td + kE + 4 * nab_segment(td, c));
-          const float4 qa = *reinterpret_cast<const float4*>(ta + kE + 4 * nab_segment(ta, th));
-          const float z = fmaf(qd.x, c, qd.y) + fmaf(qa.x, th, qa.y) + cg;
-          const float g = 1.0f / (1.0f + expf(-z));
-          bias[m] = (g * (fmaf(qd.z, c, qd.w) + cod) + (1.0f - g) * (fmaf(qa.z, th, qa.w) + coa) + bo) * scale;
+          if (kGiven) {
+            bias[m] = c * scale;
+          } else {
+            const float2 pj = xy[j];
+            const float th = atan2f(pi.y - pj.y, pi.x - pj.x);
+            const float4 qd = *reinterpret_cast<const float4*>(td + kE + 4 * nab_segment(td, c));
+            const float4 qa = *reinterpret_cast<const float4*>(ta + kE + 4 * nab_segment(ta, th));
+            const float z = fmaf(qd.x, c, qd.y) + fmaf(qa.x, th, qa.y) + cg;
+            const float g = 1.0f / (1.0f + expf(-z));
+            bias[m] = (g * (fmaf(qd.z, c, qd.w) + cod) + (1.0f - g) * (fmaf(qa.z, th, qa.w) + coa) + bo) * scale;
+          }
         }
         mx = fmaxf(mx, bias[m]);
       }
@@ -373,21 +380,28 @@ int rrnco_nab_gating(int64_t n_inst, int32_t n_nodes, const float* coords, const
 
 int rrnco_aft_nab(int64_t n_inst, int32_t n_nodes, const float* q, const float* k, const float* v, const float* coords,
                   const float* cost, int32_t transpose_cost, const float* packed, float scale, float* out, void* stream) {
-  RRNCO_CHECK_ARG(n_inst > 0 && n_nodes > 0 && q && k && v && coords && cost && packed && out);
+  // packed == NULL: `cost` is the adapt_bias [B,N,N] itself (times `scale`), coords unused
+  RRNCO_CHECK_ARG(n_inst > 0 && n_nodes > 0 && q && k && v && cost && out && (packed == nullptr || coords != nullptr));
   RRNCO_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0 &&
                   (reinterpret_cast<uintptr_t>(coords) & 7u) == 0);
   if (n_nodes > kAftMaxNodes || n_inst > 0x7fffffffLL) return RRNCO_ERR_UNSUPPORTED;
   const size_t smem = ((size_t)2 * n_nodes * kE + 2 * kNabTable + 4 + 2 * kAftMaxNodes + 2 * kE) * sizeof(float);
   static PerDeviceOnce once;
   if (once.first()) {
-    if (cudaFuncSetAttribute(aft_nab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(aft_nab_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
+    if (cudaFuncSetAttribute(aft_nab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(aft_nab_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+        cudaFuncSetAttribute(aft_nab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(aft_nab_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
       once.undo();
       return RRNCO_ERR_CUDA;
     }
   }
-  aft_nab_kernel<<<(unsigned)n_inst, kAftThreads, smem, (cudaStream_t)stream>>>(n_nodes, q, k, v, coords, cost, transpose_cost,
-                                                                                 packed, scale, out);
+  if (packed)
+    aft_nab_kernel<false><<<(unsigned)n_inst, kAftThreads, smem, (cudaStream_t)stream>>>(n_nodes, q, k, v, coords, cost, transpose_cost,
+                                                                                        packed, scale, out);
+  else
+    aft_nab_kernel<true><<<(unsigned)n_inst, kAftThreads, smem, (cudaStream_t)stream>>>(n_nodes, q, k, v, coords, cost, transpose_cost,
+                                                                                       packed, scale, out);
   return rrnco_launch_status();
 }
 

@@ -12,6 +12,7 @@ No CPU fallback: a host tensor or a missing library raises.
 from __future__ import annotations
 
 import ctypes as C
+from typing import Optional
 
 import torch
 from torch import nn
@@ -104,12 +105,13 @@ class DistAngleFusion(nn.Module):
         return out
 
 
-def aft_nab(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, coords: torch.Tensor, cost_mat: torch.Tensor,
-            fusion: DistAngleFusion, scale: float = 1.0) -> torch.Tensor:
+def aft_nab(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, coords, cost_mat: torch.Tensor,
+            fusion: Optional[DistAngleFusion], scale: float = 1.0) -> torch.Tensor:
     """The O(N^2) part of an attention-free block in one kernel (`rrnco_aft_nab`): the neural adaptive bias
     (`fusion`, times `scale` = the block's alpha), its row softmax and exp, exp(softmax over the tokens of k), the two
     [N,N] x [N,E] products and the sigmoid(q) gate -- `AFTFull.forward` (attn_freenet.py:309-327) without its Linear layers:
-    q / k / v are to_q(x) / to_k(y) / to_v(y) and the caller applies `project`.  N <= 128; nothing of size [B,N,N] is written."""
+    q / k / v are to_q(x) / to_k(y) / to_v(y) and the caller applies `project`.  N <= 128; nothing of size [B,N,N] is written.
+    `fusion=None`: `cost_mat` IS the adapt_bias [B,N,N] (any gate variant, e.g. the duration gate's output), `coords` unused."""
     B, N, E = q.shape
     if N > 128:
         raise NotImplementedError("rrnco_aft_nab holds the instance's key tiles in shared memory: N <= 128 "
@@ -117,14 +119,14 @@ def aft_nab(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, coords: torch.Ten
     if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
         raise NotImplementedError("forward-only kernel: call under torch.no_grad() / inference_mode (test.py path)")
     q, k, v = q.float().contiguous(), k.float().contiguous(), v.float().contiguous()
-    coords = coords.float().contiguous()
+    coords = None if fusion is None else coords.float().contiguous()
     transposed = 0
     if not cost_mat.is_contiguous() and cost_mat.transpose(1, 2).is_contiguous():
         cost_mat, transposed = cost_mat.transpose(1, 2), 1
     cost_mat = cost_mat.float().contiguous()
     out = torch.empty_like(q)
-    call("rrnco_aft_nab", B, N, ptr(q), ptr(k), ptr(v), ptr(coords), ptr(cost_mat), transposed, ptr(fusion.packed_parameters()),
-         float(scale), ptr(out), stream_ptr(q.device))
+    call("rrnco_aft_nab", B, N, ptr(q), ptr(k), ptr(v), ptr(coords), ptr(cost_mat), transposed,
+         ptr(None if fusion is None else fusion.packed_parameters()), float(scale), ptr(out), stream_ptr(q.device))
     return out
 
 
@@ -134,8 +136,12 @@ def _fused_block_forward(self, row_emb, col_emb, cost_mat, coords, duration_mat=
     row_emb = self.norm1(row_emb)
     col_emb = self.norm2(col_emb)
     aft = self.attn_free
-    y = aft_nab(aft.to_q(row_emb), aft.to_k(col_emb), aft.to_v(col_emb), coords, cost_mat, self.angle_distance_fusion,
-                float(self.alpha))
+    if duration_mat is not None:  # rcvrptw: bias from the tcgen05 gate kernel, then the fused AFT-full over it
+        bias = self.neural_adaptive_bias(coords, cost_mat, duration_mat, scale=float(self.alpha))
+        y = aft_nab(aft.to_q(row_emb), aft.to_k(col_emb), aft.to_v(col_emb), None, bias, None, 1.0)
+    else:
+        y = aft_nab(aft.to_q(row_emb), aft.to_k(col_emb), aft.to_v(col_emb), coords, cost_mat, self.angle_distance_fusion,
+                    float(self.alpha))
     out_concat = aft.project(y)
     multi_head_out = self.norm3(self.multi_head_combine(out_concat))
     return self.feed_forward(multi_head_out, row_emb)
@@ -155,6 +161,15 @@ def patch_encoder(encoder: nn.Module, fuse_aft: bool = True) -> int:
             mine = DistAngleFusion(128, use_duration_matrix=True).to(next(refd.parameters()).device)
             mine.load_state_dict(refd.state_dict(), strict=True)
             block.neural_adaptive_bias = mine
+            if fuse_aft and all(hasattr(block, a) for a in ("attn_free", "norm1", "norm2", "norm3", "multi_head_combine",
+                                                            "feed_forward", "alpha")):
+                unfused_d = block.forward
+
+                def forward_d(self, row_emb, col_emb, cost_mat, coords, duration_mat=None, _unfused=unfused_d):
+                    if cost_mat.shape[-1] > 128 or duration_mat is None or torch.is_grad_enabled():
+                        return _unfused(row_emb, col_emb, cost_mat, coords, duration_mat)
+                    return _fused_block_forward(self, row_emb, col_emb, cost_mat, coords, duration_mat)
+                block.forward = types.MethodType(forward_d, block)
             n += 1
             continue
         ref = getattr(block, "angle_distance_fusion", None)

@@ -183,6 +183,13 @@ def test_fused_aft_nab_kernel_matches_reference_fixture_and_oracle():
         with torch.no_grad():
             got = rb.aft_nab(q.to(dev), k.to(dev), v.to(dev), coords.to(dev), cm.to(dev), m2, scale=0.8)
         assert (got.cpu().double() - want).abs().max() < 2e-6 * max(1.0, want.abs().max().item()), transposed
+    # given-bias form (any gate variant upstream of it): same result as torch on an arbitrary bias
+    bias = torch.randn(B, N, N, generator=g)
+    with torch.no_grad():
+        got = rb.aft_nab(q.to(dev), k.to(dev), v.to(dev), None, bias.to(dev), None, scale=1.3)
+        gotT = rb.aft_nab(q.to(dev), k.to(dev), v.to(dev), None, bias.to(dev).transpose(1, 2), None, scale=1.3)
+    assert (got.cpu().double() - aft_core(q, k, v, bias * 1.3)).abs().max() < 2e-6 * 4
+    assert (gotT.cpu().double() - aft_core(q, k, v, bias.transpose(1, 2) * 1.3)).abs().max() < 2e-6 * 4
     with pytest.raises(NotImplementedError):
         rb.aft_nab(torch.zeros(1, 130, 128, device=dev), torch.zeros(1, 130, 128, device=dev), torch.zeros(1, 130, 128, device=dev),
                    torch.zeros(1, 130, 2, device=dev), torch.zeros(1, 130, 130, device=dev), m2)
