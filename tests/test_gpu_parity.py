@@ -1071,20 +1071,19 @@ def test_on_device_generator_feeds_the_rollout(rb, name):
 def test_shared_instance_augmentation_equals_materialised(rb):
     """StateAugmentation(dihedral8, share_instance_data=True) -> reset -> RRNetPolicy.forward gives the same tours and
     rewards as upstream's materialised batchify x8 (transforms.py:142-154, test.py:188-212)."""
-    n, B, A = 30, 5, 8
-    raw = synth.make_instances("rcvrp", B, n, seed=21)
-    env = rb.get_env("rcvrp", generator_params={"num_loc": n}, check_solution=False)
-    row, col = synth.random_embeddings(A * B, n + 1, seed=22)
-    pol = make_policy(rb, "rcvrp", omodel.init_decoder_params("rcvrp", seed=23), row.to(dev), col.to(dev))
-    outs = []
-    for share in (False, True):
-        aug = rb.StateAugmentation(num_augment=A, augment_fn="dihedral8", no_aug_coords=False, share_instance_data=share)
-        td = env.reset(aug(lite(rb, raw)))
-        assert td.batch_size[0] == A * B and td["distance_matrix"].shape[0] == (B if share else A * B)
-        S = 31
-        out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
-        outs.append((out["actions"].cpu(), out["reward"].cpu(), td["locs"].cpu()))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    for n, B, A, S in ((30, 5, 8, 31), (135, 2, 8, 20)):  # the lean kernel; the key-tiled kernel (136 nodes, CTA pairs)
+        raw = synth.make_instances("rcvrp", B, n, seed=21)
+        env = rb.get_env("rcvrp", generator_params={"num_loc": n}, check_solution=False)
+        row, col = synth.random_embeddings(A * B, n + 1, seed=22)
+        pol = make_policy(rb, "rcvrp", omodel.init_decoder_params("rcvrp", seed=23), row.to(dev), col.to(dev))
+        outs = []
+        for share in (False, True):
+            aug = rb.StateAugmentation(num_augment=A, augment_fn="dihedral8", no_aug_coords=False, share_instance_data=share)
+            td = env.reset(aug(lite(rb, raw)))
+            assert td.batch_size[0] == A * B and td["distance_matrix"].shape[0] == (B if share else A * B)
+            out = pol(td, env, phase="val", decode_type="multistart_greedy", num_starts=S)
+            outs.append((out["actions"].cpu(), out["reward"].cpu(), td["locs"].cpu()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
 
 
 # ----------------------------------------------------------------------------------------------------
