@@ -728,19 +728,13 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         const int h = 4 * grp + j;
-        lean_wait_group(&sm.bar_s[h], step_par, warp);
-        tc05::fence_after_sync();
-        LSTAMP(3);
-        // Both passes walk the row in 16-column blocks with the TMEM load of block k + 1 in flight while block k is
-        // processed (a TMEM round trip is a few hundred cycles; two resident tiles do not hide it by themselves).
-        const int nb16 = R16 >> 4;
-        uint32_t va[16], vb[16];
         // Softmax shift.  Any shift m' >= max gives the same probabilities; the exact row maximum costs a pass over the
         // scores (a quarter of the softmax instructions), the Cauchy-Schwarz bound |q_h| max_k |k_h| costs ~30.  The fp16
         // hi | lo operands of P V resolve 2^-24 absolute, so the largest p must stay >= 1 after scaling: with p scaled by
         // 2^14 the bound may exceed the true maximum by 14 (log2 units), which holds whenever c1 vB <= 7 (scores within
         // +-4.8: every random-init and moderately peaked head).  Otherwise: the exact maximum, p scaled by 2^4 as before.
-        float off;
+        // The bound needs the query tile only: it is computed BEFORE waiting for the scores of the head.
+        float off, vB;
         {
           const uint4 q0 = *reinterpret_cast<const uint4*>(&a_hi[(2 * h) * (kRows * 8) + row * 8]);
           const uint4 q1 = *reinterpret_cast<const uint4*>(&a_hi[(2 * h + 1) * (kRows * 8) + row * 8]);
@@ -752,8 +746,17 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
             qn2 = fmaf(f.x, f.x, fmaf(f.y, f.y, qn2));
           }
           // v = sum (kAScale q)(kKvScale k) <= |Q_hi| (1 + 2^-10) kKvScale max|k_h|
-          const float vB = sqrtf(qn2 * __uint_as_float(sm.kmax2[h])) * (kKvScale * 1.004f);
+          vB = sqrtf(qn2 * __uint_as_float(sm.kmax2[h])) * (kKvScale * 1.004f);
           off = fmaf(-c1, vB, 14.0f);
+        }
+        lean_wait_group(&sm.bar_s[h], step_par, warp);
+        tc05::fence_after_sync();
+        LSTAMP(3);
+        // Both passes walk the row in 16-column blocks with the TMEM load of block k + 1 in flight while block k is
+        // processed (a TMEM round trip is a few hundred cycles; two resident tiles do not hide it by themselves).
+        const int nb16 = R16 >> 4;
+        uint32_t va[16], vb[16];
+        {
           // (warp-uniform decision: the TMEM loads below are warp-collective)
           if (__any_sync(0xffffffffu, !(c1 * vB <= 7.0f))) {
             // exact row maximum over the feasible keys
