@@ -20,7 +20,7 @@ OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 log = os.path.join(OUT, "r2_launches_bench.csv")
 metrics = "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
-cmd = ["ncu", "--metrics", metrics, "--clock-control", "none", "-c", "600", "--csv", "--log-file", log,
+cmd = ["ncu", "--metrics", metrics, "--clock-control", "none", "-c", "4000", "--csv", "--log-file", log,
        sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--no-configs", "--no-cpu-baseline"]
 subprocess.run(cmd, check=True, cwd=ROOT, stdout=subprocess.DEVNULL)
 
