@@ -54,11 +54,13 @@ template <int kEnv>
 struct LeanSmem {
   // ring depth: as many 8 KB stages as fit beside the activation tiles in 113 KB (the time-window env needs 7 per-node
   // arrays and 4 state words per rollout: one stage less)
-  static constexpr int kStages = kEnv == RRNCO_ENV_RCVRPTW ? 4 : 5;
+  static constexpr int kStages = 4;  // (a fifth stage where it fits was measured neutral; the space holds the FFN biases)
   static constexpr int kNodeArrays = kEnv == RRNCO_ENV_RCVRPTW ? 7 : 1;
   static constexpr int kStateArrays = kEnv == RRNCO_ENV_RCVRPTW ? 4 : 1;
   unsigned char A[kRows * kE * 4];         // Q -> glimpse (fp16 hi | lo tiles) | fp32 bias tile during logits + select
   unsigned char ring[kStages][kLStageBytes];
+  float ffn_bias[kF + kE];                 // kAScale b1 | kAScale b2: read by every epilogue block (from L1 / L2 they were the
+                                           // top stall of the FFN epilogues: 17.8 % of the kernel's stall samples)
   float wstate[kStateArrays][kE];          // context state weights; ATSP: row 0 = placeholder query
   float node[kNodeArrays][kRows];          // dem | demb tw0 tw1 svc dj0 uj0 (rcvrptw)
   float f[kStateArrays][kRows];            // rcvrp: used | rcvrptw: time, route, used_l, used_b
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
     sm.exit_flag = 0;
     for (int i = 0; i < kH; ++i) sm.kmax2[i] = 0u;
   }
+  for (int i = tid; i < kF + kE; i += kLThreads) sm.ffn_bias[i] = p.ffn_bias_scaled[i];
   if (tid < kE) {
 #pragma unroll
     for (int k = 0; k < SmemT::kStateArrays; ++k) {
@@ -864,7 +867,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
           float bb[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.ffn_bias_scaled + c * kRows + col0 + i));
+            *reinterpret_cast<float4*>(&bb[i]) = *reinterpret_cast<const float4*>(&sm.ffn_bias[c * kRows + col0 + i]);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             // kAScale relu(acc / (kAScale kWScale) + b1): the scaled operand directly (b1 pre-scaled; powers of two: exact).
@@ -906,7 +909,7 @@ __global__ void __launch_bounds__(kLThreads, 2) rollout_lean_kernel(const Rollou
         float bb[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.ffn_bias_scaled + kF + col0 + i));
+          *reinterpret_cast<float4*>(&bb[i]) = *reinterpret_cast<const float4*>(&sm.ffn_bias[kF + col0 + i]);
         tc05::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; i += 8) {

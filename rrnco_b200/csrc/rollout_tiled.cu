@@ -74,6 +74,7 @@ struct TiledSmem {
   static constexpr int kNodeLen = kEnv == RRNCO_ENV_ATSP ? 4 : kGMaxNodes;
   unsigned char A[kRows * kE * 4];         // Q -> glimpse (fp16 hi | lo tiles)
   unsigned char ring[kStages][kGStage];
+  float ffn_bias[kF + kE];                 // kAScale b1 | kAScale b2 (shared-memory broadcast reads in the FFN epilogues)
   float wstate[kStateArrays][kE];          // context state weights; ATSP: row 0 = placeholder query
   float node[kNodeArrays][kNodeLen];       // dem | demb tw0 tw1 svc dj0 uj0 (rcvrptw)
   float f[kStateArrays][kRows];            // rcvrp: used | rcvrptw: time, route, used_l, used_b
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
     const uint32_t* km = reinterpret_cast<const uint32_t*>(p.kv_pack + (size_t)p.n_inst * ((size_t)nT * kGSlicesPerTile * kGStage));
     for (int i = 0; i < kH; ++i) sm.kmax2[i] = km[b * kH + i];
   }
+  for (int i = tid; i < kF + kE; i += kGThreads) sm.ffn_bias[i] = p.ffn_bias_scaled[i];
   if (tid < kE) {
 #pragma unroll
     for (int k = 0; k < SmemT::kStateArrays; ++k) {
@@ -1049,7 +1051,7 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
           float bb[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.ffn_bias_scaled + c * kRows + col0 + i));
+            *reinterpret_cast<float4*>(&bb[i]) = *reinterpret_cast<const float4*>(&sm.ffn_bias[c * kRows + col0 + i]);
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             const float2 a = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
@@ -1090,7 +1092,7 @@ __global__ void __launch_bounds__(kGThreads, 1) rollout_tiled_kernel(const Rollo
         float bb[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(p.ffn_bias_scaled + kF + col0 + i));
+          *reinterpret_cast<float4*>(&bb[i]) = *reinterpret_cast<const float4*>(&sm.ffn_bias[kF + col0 + i]);
         tc05::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; i += 8) {
