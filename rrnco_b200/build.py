@@ -95,6 +95,43 @@ def build_torch_ops(force: bool = False) -> str:
     return TORCH_LIB
 
 
+TRAIN_LIB = os.path.join(HERE, "librrnco_b200_train.so")
+TRAIN_SOURCES = ["ffn_train.cu", "attention_train.cu", "logits_train.cu"]
+
+
+def build_train_library(force: bool = False) -> str:
+    """nvcc csrc_train/*.cu -> rrnco_b200/librrnco_b200_train.so (include/rrnco_b200_train.h): the kernels of the training
+    hand-off.  A library of its own: the rollout library's build digest (profiles are stamped with it) covers csrc/ only."""
+    tdir = os.path.join(HERE, "csrc_train")
+    srcs = [os.path.join(tdir, f) for f in TRAIN_SOURCES if os.path.exists(os.path.join(tdir, f))]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("common.cuh", "tc05.cuh", "ffn_pack.cuh")]
+    deps += [os.path.join(os.path.dirname(HERE), "include", f) for f in ("rrnco_b200.h", "rrnco_b200_train.h")]
+    stamp = os.path.join(HERE, "build", "stamp_train")
+    digest = _digest(deps)
+    if not force and os.path.exists(TRAIN_LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return TRAIN_LIB
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(HERE, "build", "train_" + os.path.basename(src).replace(".cu", ".o"))
+        r = subprocess.run([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        with open(obj + ".ptxas.txt", "w") as f:
+            f.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    r = subprocess.run([nvcc, "-shared", "-o", TRAIN_LIB, *objs], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return TRAIN_LIB
+
+
 def build_digest() -> str:
     """Digest of the CUDA sources + flags the library on disk was built from (profiles stamp their numbers with it)."""
     stamp = os.path.join(HERE, "build", "stamp")
@@ -104,3 +141,4 @@ def build_digest() -> str:
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
     print(build_torch_ops(force="--force" in sys.argv))
+    print(build_train_library(force="--force" in sys.argv))

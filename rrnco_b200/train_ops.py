@@ -1,0 +1,228 @@
+"""ctypes binding of librrnco_b200_train.so (include/rrnco_b200_train.h) and the autograd Functions built on it: the heavy
+parts of the training hand-off (`training.batched_logprobs`) as hand-written sm_100a kernels, forward AND backward.
+
+    fused_ffn(x, w1, b1, w2, b2)             residual FFN of the pointer (decoder.py:272-277, 296) on tcgen05, fp32-faithful
+    fused_attention(q, k, v, mask)           masked 8-head attention + residual (decoder.py:281-293)
+    fused_logits_tail(z, decoder, ...)       edge bias / log(exp + 1e-6) / tanh clip / mask / log-softmax / gather
+                                             (decoder.py:183-198, decoding.py:311-399)
+
+No CPU fallback: a missing library or a CPU tensor raises.  Torch is used for device memory, streams and the autograd graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librrnco_b200_train.so")
+MAX_NODES_ATTENTION = 108   # K, V, dK, dV tiles of one instance in shared memory (rrnco_train_attention_bwd)
+DEV_NAN_LOGITS = 1
+
+_f = C.c_void_p
+_SIGNATURES = {
+    "rrnco_train_ffn_packed_bytes": (C.c_int64, []),
+    "rrnco_train_ffn_pack": (C.c_int, [_f, _f, _f, _f, _f]),
+    "rrnco_train_ffn": (C.c_int, [C.c_int32, C.c_int64, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
+    "rrnco_train_xty": (C.c_int, [C.c_int64, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
+    "rrnco_train_attention_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, C.c_int32, _f, _f, _f]),
+    "rrnco_train_attention_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, C.c_int32, _f, _f, _f, _f, _f, _f]),
+    "rrnco_train_logits_tail": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, _f, _f, _f, C.c_float, C.c_float,
+                                          C.c_float, _f, _f, _f, _f]),
+}
+_lib = None
+_status: dict = {}
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python rrnco_b200/build.py` (there is no CPU fallback)")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = h
+    return _lib
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("rrnco_b200.train_ops: CUDA tensors only (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed with code {rc}")
+
+
+def status_word(dev) -> torch.Tensor:
+    """Sticky device word of this device: RRNCO_DEV_NAN_LOGITS when an fp16 operand overflowed in any call so far."""
+    dev = torch.device(dev)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _status:
+        _status[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return _status[key]
+
+
+def check_status(dev) -> None:
+    """One device -> host read: raises if a kernel flagged an fp16 operand overflow since the last check."""
+    w = status_word(dev)
+    v = int(w.item())
+    if v:
+        w.zero_()
+        raise FloatingPointError(f"rrnco_b200.train_ops: fp16 hi|lo operand overflow (status {v}): result not to be trusted")
+
+
+def pow2_scale(t: torch.Tensor, bound_factor=None, target: float = 512.0) -> torch.Tensor:
+    """Device scalar 2^k with max|t| * bound_factor * 2^k in (target / 2, target]: the pre-split scale of a gradient operand."""
+    amax = t.detach().abs().amax().float()
+    if bound_factor is not None:
+        amax = amax * bound_factor
+    amax = amax.clamp(1e-30, 1e30)
+    return torch.exp2(torch.floor(torch.log2(target / amax))).reshape(1).contiguous()
+
+
+def _pack(wa, wb, dev):
+    h = lib()
+    packed = torch.empty(h.rrnco_train_ffn_packed_bytes(), dtype=torch.uint8, device=dev)
+    _check(h.rrnco_train_ffn_pack(_p(wa), _p(wb), _p(packed), _p(status_word(dev)), _stream(dev)), "rrnco_train_ffn_pack")
+    return packed
+
+
+class _FusedFFN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        h, dev = lib(), x.device
+        x = x.detach().contiguous().float()
+        w1, b1, w2, b2 = (t.detach().contiguous().float() for t in (w1, b1, w2, b2))
+        rows = x.shape[0]
+        mask = torch.empty(rows, 16, dtype=torch.int32, device=dev)
+        y = torch.empty_like(x)
+        _check(h.rrnco_train_ffn(0, rows, _p(x), _p(_pack(w1, w2, dev)), _p(b1), _p(b2), None, _p(mask), None, _p(y),
+                                 _p(status_word(dev)), _stream(dev)), "rrnco_train_ffn")
+        ctx.save_for_backward(x, mask, w1, b1, w2, b2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mask, w1, b1, w2, b2 = ctx.saved_tensors
+        h, dev, st = lib(), x.device, status_word(x.device)
+        rows = x.shape[0]
+        dy = dy.contiguous().float()
+        s_dy = pow2_scale(dy)
+        # |dhidden_j| <= max|dy| * sum_e |W2[e, j]|: a rigorous bound without a pass over the [rows, 512] tensor
+        s_dh = pow2_scale(dy, bound_factor=w2.abs().sum(0).amax().clamp_min(1.0))
+        hidden = torch.empty(rows, 512, dtype=torch.float32, device=dev)
+        _check(h.rrnco_train_ffn(0, rows, _p(x), _p(_pack(w1, w2, dev)), _p(b1), _p(b2), None, None, _p(hidden), None, _p(st),
+                                 _stream(dev)), "rrnco_train_ffn (recompute)")
+        dhid = torch.empty(rows, 512, dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x)
+        packed_t = _pack(w2.t().contiguous(), w1.t().contiguous(), dev)
+        _check(h.rrnco_train_ffn(1, rows, _p(dy), _p(packed_t), None, None, _p(s_dy), _p(mask), _p(dhid), _p(dx), _p(st),
+                                 _stream(dev)), "rrnco_train_ffn (backward)")
+        dw1 = torch.zeros(512, 128, dtype=torch.float32, device=dev)
+        db1 = torch.zeros(512, dtype=torch.float32, device=dev)
+        dw2t = torch.zeros(512, 128, dtype=torch.float32, device=dev)
+        db2 = torch.zeros(128, dtype=torch.float32, device=dev)
+        _check(h.rrnco_train_xty(rows, _p(dhid), _p(x), _p(s_dh), None, _p(dw1), _p(db1), None, _p(st), _stream(dev)),
+               "rrnco_train_xty (dW1)")
+        _check(h.rrnco_train_xty(rows, _p(hidden), _p(dy), None, _p(s_dy), _p(dw2t), None, _p(db2), _p(st), _stream(dev)),
+               "rrnco_train_xty (dW2)")
+        return dx, dw1, db1, dw2t.t(), db2
+
+
+def fused_ffn(x, w1, b1, w2, b2):
+    """y = relu(x w1^T + b1) w2^T + b2 + x for x [..., 128]; forward, data and weight gradients on tcgen05 (fp32-faithful)."""
+    return _FusedFFN.apply(x.reshape(-1, 128), w1, b1, w2, b2).view(x.shape)
+
+
+class _FusedAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, mask, add_residual):
+        h, dev = lib(), q.device
+        q, k, v = (t.detach().contiguous().float() for t in (q, k, v))
+        m8 = mask.contiguous().view(torch.uint8)
+        n_inst, L, _ = q.shape
+        N = k.shape[1]
+        out = torch.empty_like(q)
+        lse = torch.empty(n_inst, L, 8, dtype=torch.float32, device=dev)
+        _check(h.rrnco_train_attention_fwd(n_inst, L, N, _p(q), _p(k), _p(v), _p(m8), int(add_residual), _p(out), _p(lse),
+                                           _stream(dev)), "rrnco_train_attention_fwd")
+        ctx.save_for_backward(q, k, v, m8, out, lse)
+        ctx.add_residual = int(add_residual)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v, m8, out, lse = ctx.saved_tensors
+        h, dev = lib(), q.device
+        n_inst, L, _ = q.shape
+        N = k.shape[1]
+        d_out = d_out.contiguous().float()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _check(h.rrnco_train_attention_bwd(n_inst, L, N, _p(q), _p(k), _p(v), _p(m8), _p(out), ctx.add_residual, _p(lse),
+                                           _p(d_out), _p(dq), _p(dk), _p(dv), _stream(dev)), "rrnco_train_attention_bwd")
+        return dq, dk, dv, None, None
+
+
+def fused_attention(q, k, v, mask, add_residual: bool = True):
+    """softmax(q_h k_h^T / 4 + mask) v_h (+ q): q [n_inst, L, 128], k / v [n_inst, N, 128], mask [n_inst, L, N] bool."""
+    return _FusedAttention.apply(q, k, v, mask, add_residual)
+
+
+class _LogitsTail(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature):
+        h, dev = lib(), z.device
+        n_inst, L, N = z.shape
+        jac = z.detach()
+        if not jac.is_contiguous() or jac.dtype != torch.float32:
+            jac = jac.contiguous().float()
+        rows = n_inst * L
+        logp = torch.empty(n_inst, L, dtype=torch.float32, device=dev)
+        da = torch.empty(n_inst, L, dtype=torch.float32, device=dev)
+        db = torch.empty(n_inst, L, dtype=torch.float32, device=dev) if duration is not None else None
+        alpha_d = alpha.detach().reshape(-1).float().contiguous()
+        beta_d = beta.detach().reshape(-1).float().contiguous() if duration is not None else None
+        _check(h.rrnco_train_logits_tail(rows, L, N, _p(jac), _p(distance.contiguous()),
+                                         _p(duration.contiguous()) if duration is not None else None, _p(cur.contiguous()),
+                                         _p(mask.contiguous().view(torch.uint8)), _p(act.contiguous()), _p(alpha_d), _p(beta_d),
+                                         1.0 / math.sqrt(128.0), float(tanh_clipping), float(temperature), _p(logp), _p(da), _p(db),
+                                         _stream(dev)), "rrnco_train_logits_tail")
+        ctx.save_for_backward(jac, da, db)
+        ctx.shapes = (alpha.shape, beta.shape if beta is not None else None)
+        return logp
+
+    @staticmethod
+    def backward(ctx, g):
+        jac, da, db = ctx.saved_tensors
+        g = g.float()
+        dz = jac.mul_(g.unsqueeze(-1))  # the Jacobian is this node's own buffer (the raw scores were overwritten in place)
+        dalpha = (g * da).sum().reshape(ctx.shapes[0])
+        dbeta = (g * db).sum().reshape(ctx.shapes[1]) if db is not None else None
+        return dz, dalpha, dbeta, None, None, None, None, None, None, None
+
+
+def fused_logits_tail(z, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature):
+    """log pi(act | state) [n_inst, L] from the raw pointer scores z = g . Lk^T [n_inst, L, N] (consumed: overwritten in place by
+    the Jacobian); distance / duration [n_inst, N, N], cur / act [n_inst, L] int64, mask [n_inst, L, N] bool."""
+    return _LogitsTail.apply(z, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature)

@@ -26,7 +26,11 @@ import torch.nn.functional as F
 from .tdlite import TensorDictLite, batchify
 
 
-ATTENTION_IMPL = "sdpa"  # "sdpa" | "matmul": how batched_logprobs evaluates the masked 8-head attention
+ATTENTION_IMPL = "sdpa"  # "sdpa" | "matmul": how the ATen form of batched_logprobs evaluates the masked 8-head attention
+# CUDA tensors: attention, residual FFN and the pointer tail (forward AND backward) run on the hand-written kernels of
+# librrnco_b200_train.so (rrnco_b200/train_ops.py; a missing library raises).  "aten" keeps the plain-torch form on the GPU:
+# the comparison arm of tests/test_gpu_parity.py and tools/train_step_probe.py, and the bf16-autocast option.
+REPLAY_IMPL = "fused"   # "fused" | "aten"
 
 
 def collect_decode_inputs(decoder, env, td, actions: torch.Tensor, num_starts: int) -> dict:
@@ -77,6 +81,10 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
     S = int(num_starts)
     R = S * n_inst
     Tm = inputs["current_node"].shape[0]
+    fused = col_emb.is_cuda and REPLAY_IMPL == "fused" and not torch.is_autocast_enabled()
+    if fused:
+        from . import train_ops
+        fused = N <= train_ops.MAX_NODES_ATTENTION and E == 128 and H == 8  # larger instances: the ATen form below
     k, v, lk = F.linear(col_emb, decoder.project_node_embeddings.weight).chunk(3, dim=-1)  # decoder.py:214-232
     W = decoder.context_embedding.project_context.weight
 
@@ -105,6 +113,16 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
         else:               # context.py:18-31: [current-node embedding, state scalars]
             ctx = torch.cat([emb_cur, per_inst(inputs["ctx_state"][t0:t1]).to(emb_cur.dtype)], -1)
         q = F.linear(ctx, W)                                               # [n_inst, L, E]
+        if fused:
+            from . import train_ops
+            g = train_ops.fused_attention(q, k, v, mask, add_residual=True)             # decoder.py:281-293 (+ q)
+            g = train_ops.fused_ffn(g, w1, b1, w2, b2)                                  # decoder.py:296
+            z = torch.bmm(g, lk.transpose(1, 2))                                        # raw pointer scores [n_inst, L, N]
+            logp = train_ops.fused_logits_tail(z, decoder.alpha, decoder.beta if name == "rcvrptw" else None, distance,
+                                               duration if name == "rcvrptw" else None, cur, mask, act, tanh_clipping,
+                                               temperature)                             # decoder.py:183-198, decoding.py:311-399
+            out.append(logp.unflatten(1, (t1 - t0, S)).permute(2, 0, 1).reshape(R, t1 - t0))
+            continue
         if ATTENTION_IMPL == "sdpa":
             h = F.scaled_dot_product_attention(heads(q), kh, vh, attn_mask=mask.unsqueeze(1))  # decoder.py:281-293
         else:  # explicit: head dim 16 and 101 keys are far from the tile shapes of the fused SDPA kernels

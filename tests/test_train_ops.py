@@ -1,0 +1,199 @@
+"""Training hand-off kernels (librrnco_b200_train.so, include/rrnco_b200_train.h): each autograd Function of
+rrnco_b200/train_ops.py against the same op in fp64 torch (values and every gradient), and the fused form of
+`training.batched_logprobs` against its plain-torch form (rl.py:99-130, decoder.py:151-206,281-326).
+Tolerances: the kernels are fp32-faithful (fp32 FMA, or three-term fp16-split tcgen05 products with fp32 accumulation);
+relative errors are taken against the largest magnitude of the tensor."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_train_header_symbols_exported():
+    from rrnco_b200.build import build_train_library
+    from rrnco_b200 import train_ops
+    path = build_train_library()
+    header = open(os.path.join(ROOT, "include", "rrnco_b200_train.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rrnco_[a-z_0-9]+)\s*\(", header))
+    assert {"rrnco_train_ffn", "rrnco_train_xty", "rrnco_train_attention_bwd", "rrnco_train_logits_tail"} <= declared
+    handle = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/rrnco_b200_train.h but not exported"
+    assert declared == set(train_ops.exported_symbols())
+    assert train_ops.lib().rrnco_train_ffn_packed_bytes() == 512 * 1024
+
+
+def test_train_ops_reject_cpu_tensors():
+    from rrnco_b200 import train_ops
+    x = torch.zeros(4, 128)
+    with pytest.raises(RuntimeError):
+        train_ops.fused_ffn(x, torch.zeros(512, 128), torch.zeros(512), torch.zeros(128, 512), torch.zeros(128))
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-300)).item()
+
+
+def _ffn_params(seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    w1 = (torch.rand(512, 128, generator=g) * 2 - 1) / 128 ** 0.5
+    b1 = (torch.rand(512, generator=g) * 2 - 1) / 128 ** 0.5
+    w2 = (torch.rand(128, 512, generator=g) * 2 - 1) / 512 ** 0.5
+    b2 = (torch.rand(128, generator=g) * 2 - 1) / 512 ** 0.5
+    return [t.to(dev).requires_grad_(True) for t in (w1, b1, w2, b2)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,gscale", [(1000, 1.0), (128 * 150 + 77, 3e-7), (5, 1e-9)])
+def test_fused_ffn_forward_backward(rows, gscale):
+    from rrnco_b200 import train_ops
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, 128, generator=g) * 2).to(dev).requires_grad_(True)
+    r = (torch.randn(rows, 128, generator=g) * gscale).to(dev)
+    # rows of a rollout have very different gradient magnitudes (advantage x probability): mimic it
+    r = r * torch.logspace(0, -4, rows, device=dev)[torch.randperm(rows, device=dev)].unsqueeze(1)
+    params = _ffn_params(1, dev)
+    y = train_ops.fused_ffn(x, *params)
+    (y * r).sum().backward()
+    got = [y.detach(), x.grad] + [p.grad for p in params]
+    xd = x.detach().double().requires_grad_(True)
+    pd = [p.detach().double().requires_grad_(True) for p in params]
+    yd = F.linear(F.relu(F.linear(xd, pd[0], pd[1])), pd[2], pd[3]) + xd
+    (yd * r.double()).sum().backward()
+    want = [yd.detach(), xd.grad] + [p.grad for p in pd]
+    train_ops.check_status(dev)
+    for name, a, b in zip(("y", "dx", "dw1", "db1", "dw2", "db2"), got, want):
+        assert a.shape == b.shape, name
+        assert _rel(a, b) < 2e-6, (name, _rel(a, b))
+
+
+def _attention_ref(q, k, v, mask):
+    n_inst, L, _ = q.shape
+    qh = q.unflatten(-1, (8, 16)).transpose(1, 2)
+    kh = k.unflatten(-1, (8, 16)).transpose(1, 2)
+    vh = v.unflatten(-1, (8, 16)).transpose(1, 2)
+    sc = torch.matmul(qh, kh.transpose(-1, -2)) / 4.0
+    sc = sc.masked_fill(~mask.unsqueeze(1), float("-inf"))
+    return torch.matmul(torch.softmax(sc, -1), vh).transpose(1, 2).flatten(-2) + q
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_inst,L,N,qscale", [(3, 70, 101, 1.0), (2, 2500, 100, 3.0), (5, 33, 21, 1.0), (1, 64, 108, 8.0)])
+def test_fused_attention_forward_backward(n_inst, L, N, qscale):
+    from rrnco_b200 import train_ops
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(L)
+    q = (torch.randn(n_inst, L, 128, generator=g) * qscale).to(dev).requires_grad_(True)
+    k = torch.randn(n_inst, N, 128, generator=g).to(dev).requires_grad_(True)
+    v = torch.randn(n_inst, N, 128, generator=g).to(dev).requires_grad_(True)
+    mask = (torch.rand(n_inst, L, N, generator=g) < 0.4).to(dev)
+    mask[..., 0] |= ~mask.any(-1)          # at least one feasible node per row
+    mask[0, 0] = False
+    mask[0, 0, N - 1] = True                # a single feasible node
+    r = (torch.randn(n_inst, L, 128, generator=g) * 1e-6).to(dev)
+    out = train_ops.fused_attention(q, k, v, mask)
+    (out * r).sum().backward()
+    got = [out.detach(), q.grad, k.grad, v.grad]
+    qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    od = _attention_ref(qd, kd, vd, mask)
+    (od * r.double()).sum().backward()
+    want = [od.detach(), qd.grad, kd.grad, vd.grad]
+    for name, a, b in zip(("out", "dq", "dk", "dv"), got, want):
+        assert _rel(a, b) < 5e-6, (name, _rel(a, b))
+
+
+def _tail_ref(z, alpha, beta, dist, dur, cur, mask, act, clip, temp):
+    n_inst = z.shape[0]
+    inst = torch.arange(n_inst, device=z.device)
+    logits = z / 128 ** 0.5
+    bias = alpha * dist[inst[:, None], cur]
+    if dur is not None:
+        bias = bias + beta * dur[inst[:, None], cur]
+    logits = torch.log(torch.exp(logits - bias) + 1e-6)
+    if clip > 0:
+        logits = torch.tanh(logits) * clip
+    logits = logits.masked_fill(~mask, float("-inf")) / temp
+    return F.log_softmax(logits, -1).gather(-1, act.unsqueeze(-1)).squeeze(-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_dur,clip,temp,N", [(False, 10.0, 1.0, 101), (True, 10.0, 0.7, 101), (False, 0.0, 1.0, 37), (True, 10.0, 1.0, 128)])
+def test_fused_logits_tail_forward_backward(with_dur, clip, temp, N):
+    from rrnco_b200 import train_ops
+    dev = torch.device("cuda", 0)
+    n_inst, L = 3, 257
+    g = torch.Generator().manual_seed(N)
+    z = (torch.randn(n_inst, L, N, generator=g) * 30).to(dev).requires_grad_(True)
+    dist = torch.rand(n_inst, N, N, generator=g).to(dev)
+    dur = torch.rand(n_inst, N, N, generator=g).to(dev) if with_dur else None
+    alpha = torch.tensor([1.3], device=dev, requires_grad=True)
+    beta = torch.tensor([0.6], device=dev, requires_grad=True) if with_dur else None
+    cur = torch.randint(0, N, (n_inst, L), generator=g).to(dev)
+    mask = (torch.rand(n_inst, L, N, generator=g) < 0.5).to(dev)
+    act = torch.randint(0, N, (n_inst, L), generator=g).to(dev)
+    mask.scatter_(-1, act.unsqueeze(-1), True)
+    r = torch.randn(n_inst, L, generator=g).to(dev)
+    zd = z.detach().double().requires_grad_(True)
+    ad = alpha.detach().double().requires_grad_(True)
+    bd = beta.detach().double().requires_grad_(True) if with_dur else None
+    want = _tail_ref(zd, ad, bd, dist.double(), dur.double() if with_dur else None, cur, mask, act, clip, temp)
+    (want * r.double()).sum().backward()
+    logp = train_ops.fused_logits_tail(z * 1.0, alpha, beta, dist, dur, cur, mask, act, clip, temp)  # z * 1.0: consumed in place
+    (logp * r).sum().backward()
+    assert (logp.detach().double() - want.detach()).abs().max().item() < 2e-5
+    assert _rel(z.grad, zd.grad) < 2e-5
+    assert abs(alpha.grad.item() - ad.grad.item()) < 2e-4 * max(1.0, abs(ad.grad.item()))
+    if with_dur:
+        assert abs(beta.grad.item() - bd.grad.item()) < 2e-4 * max(1.0, abs(bd.grad.item()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rcvrp", "atsp", "rcvrptw"])
+def test_fused_replay_matches_aten_replay(name):
+    """training.batched_logprobs: fused kernels vs the plain-torch form on the same sampled rollouts - log-likelihood and the
+    gradients of the REINFORCE loss w.r.t. every decoder parameter and both encoder outputs."""
+    import rrnco_b200 as rb
+    from rrnco_b200 import training, train_ops
+    from oracle import synth, model as omodel
+    dev = torch.device("cuda", 0)
+    n, B, S = 20, 6, 12
+    raw = synth.make_instances(name, B, n, seed=3)
+    env = rb.get_env(name, generator_params={"num_loc": n}, check_solution=False)
+    td = env.reset(rb.TensorDictLite({k: v.to(dev) for k, v in raw.items()}, batch_size=[B]))
+    N = td["action_mask"].shape[-1]
+    row, col = synth.random_embeddings(B, N, seed=4)
+
+    class Enc(torch.nn.Module):
+        def forward(self, td, phase=None):
+            return row.to(dev), col.to(dev)
+
+    pol = rb.RRNetPolicy(encoder=Enc(), env_name=name).to(dev)
+    pol.decoder.load_state_dict(omodel.init_decoder_params(name, seed=5))
+    with torch.no_grad():
+        out = pol(td, env, phase="train", decode_type="multistart_sampling", num_starts=S)
+        inputs = rb.collect_decode_inputs(pol.decoder, env, td, out["actions"], S)
+    dur = td["duration_matrix"].float() if name == "rcvrptw" else None
+    res = {}
+    for impl in ("aten", "fused"):
+        training.REPLAY_IMPL = impl
+        r_, c_ = row.to(dev).requires_grad_(True), col.to(dev).requires_grad_(True)
+        pol.zero_grad(set_to_none=True)
+        logp = rb.batched_logprobs(pol.decoder, r_, c_, td["distance_matrix"].float(), dur, inputs, out["actions"], S, step_chunk=7)
+        ll = logp.sum(1)
+        rb.pomo_shared_baseline_loss(out["reward"], ll, S).backward()
+        res[impl] = (ll.detach(), {"row": r_.grad, "col": c_.grad,
+                                   **{k: p.grad.clone() for k, p in pol.decoder.named_parameters() if p.grad is not None}})
+    training.REPLAY_IMPL = "fused"
+    train_ops.check_status(dev)
+    assert (res["fused"][0] - res["aten"][0]).abs().max().item() < 2e-4
+    assert (res["fused"][0] - out["log_likelihood"]).abs().max().item() < 2e-4   # and the sampling kernel's own log-likelihood
+    assert set(res["fused"][1]) == set(res["aten"][1])
+    for k, gref in res["aten"][1].items():
+        assert _rel(res["fused"][1][k], gref) < 1e-4, (k, _rel(res["fused"][1][k], gref))

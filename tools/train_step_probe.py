@@ -34,8 +34,9 @@ def sync_time():
 
 from rrnco_b200 import training as _tr  # noqa: E402
 for it in range(int(os.environ.get("ITERS", 5))):
-    ac = torch.bfloat16 if it >= 3 and not os.environ.get("FP32_ONLY") else None
+    ac = torch.bfloat16 if it >= 3 and os.environ.get("BF16") else None
     _tr.ATTENTION_IMPL = os.environ.get("ATTN", "sdpa")
+    _tr.REPLAY_IMPL = os.environ.get("IMPL", "fused")
     torch.backends.cuda.matmul.allow_tf32 = bool(int(os.environ.get("TF32", 0)))
     torch.cuda.reset_peak_memory_stats()
     t0 = sync_time()
@@ -53,7 +54,7 @@ for it in range(int(os.environ.get("ITERS", 5))):
     loss.backward()
     t4 = sync_time()
     err = (ll - out["log_likelihood"]).abs().max().item()
-    print(f"iter {it} ({'bf16 autocast' if ac else 'fp32'}): B={B} S={S} T={out['actions'].shape[1]}  sample (fused kernel) {1e3*(t1-t0):7.1f} ms | env replay "
+    print(f"iter {it} ({'bf16 autocast' if ac else 'fp32'}, {_tr.REPLAY_IMPL if not ac else 'aten'} replay): B={B} S={S} T={out['actions'].shape[1]}  sample (fused kernel) {1e3*(t1-t0):7.1f} ms | env replay "
           f"{1e3*(t2-t1):7.1f} | batched logprobs fwd {1e3*(t3-t2):7.1f} | bwd {1e3*(t4-t3):7.1f} | total {1e3*(t4-t0):7.1f} ms "
           f"= {B/(t4-t0):7.1f} instances/s | max |ll - kernel ll| {err:.1e} | peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB")
     pol.zero_grad(set_to_none=True)
