@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) logits_tail_kernel(int64_t rows, int64_t 
         const float x = zrow[j] * inv_sqrt_e - bias;
         const float ex = expf(x);
         const float u = logf(ex + 1e-6f);               // decoder.py:198
-        const float sig = ex / (ex + 1e-6f);            // d u / d x
+        const float sig = 1.0f / (1.0f + 1e-6f / ex);   // d u / d x = ex / (ex + 1e-6), finite for ex = 0 and ex = inf
         if (clip > 0.f) {                               // decoding.py:332-333
           const float th = tanhf(u);
           lj[i] = th * clip * inv_temp;

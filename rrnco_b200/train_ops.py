@@ -117,7 +117,8 @@ class _FusedFFN(torch.autograd.Function):
         rows = x.shape[0]
         mask = torch.empty(rows, 16, dtype=torch.int32, device=dev)
         y = torch.empty_like(x)
-        _check(h.rrnco_train_ffn(0, rows, _p(x), _p(_pack(w1, w2, dev)), _p(b1), _p(b2), None, _p(mask), None, _p(y),
+        packed = _pack(w1, w2, dev)
+        _check(h.rrnco_train_ffn(0, rows, _p(x), _p(packed), _p(b1), _p(b2), None, _p(mask), None, _p(y),
                                  _p(status_word(dev)), _stream(dev)), "rrnco_train_ffn")
         ctx.save_for_backward(x, mask, w1, b1, w2, b2)
         return y
@@ -132,7 +133,8 @@ class _FusedFFN(torch.autograd.Function):
         # |dhidden_j| <= max|dy| * sum_e |W2[e, j]|: a rigorous bound without a pass over the [rows, 512] tensor
         s_dh = pow2_scale(dy, bound_factor=w2.abs().sum(0).amax().clamp_min(1.0))
         hidden = torch.empty(rows, 512, dtype=torch.float32, device=dev)
-        _check(h.rrnco_train_ffn(0, rows, _p(x), _p(_pack(w1, w2, dev)), _p(b1), _p(b2), None, None, _p(hidden), None, _p(st),
+        packed = _pack(w1, w2, dev)
+        _check(h.rrnco_train_ffn(0, rows, _p(x), _p(packed), _p(b1), _p(b2), None, None, _p(hidden), None, _p(st),
                                  _stream(dev)), "rrnco_train_ffn (recompute)")
         dhid = torch.empty(rows, 512, dtype=torch.float32, device=dev)
         dx = torch.empty_like(x)
@@ -203,9 +205,11 @@ class _LogitsTail(torch.autograd.Function):
         db = torch.empty(n_inst, L, dtype=torch.float32, device=dev) if duration is not None else None
         alpha_d = alpha.detach().reshape(-1).float().contiguous()
         beta_d = beta.detach().reshape(-1).float().contiguous() if duration is not None else None
-        _check(h.rrnco_train_logits_tail(rows, L, N, _p(jac), _p(distance.contiguous()),
-                                         _p(duration.contiguous()) if duration is not None else None, _p(cur.contiguous()),
-                                         _p(mask.contiguous().view(torch.uint8)), _p(act.contiguous()), _p(alpha_d), _p(beta_d),
+        # every argument stays referenced until the launch is enqueued (a temporary's block could be handed to the next one)
+        distance, cur, act = distance.contiguous(), cur.contiguous(), act.contiguous()
+        duration = duration.contiguous() if duration is not None else None
+        m8 = mask.contiguous().view(torch.uint8)
+        _check(h.rrnco_train_logits_tail(rows, L, N, _p(jac), _p(distance), _p(duration), _p(cur), _p(m8), _p(act), _p(alpha_d), _p(beta_d),
                                          1.0 / math.sqrt(128.0), float(tanh_clipping), float(temperature), _p(logp), _p(da), _p(db),
                                          _stream(dev)), "rrnco_train_logits_tail")
         ctx.save_for_backward(jac, da, db)

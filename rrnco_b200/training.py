@@ -115,6 +115,7 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
         q = F.linear(ctx, W)                                               # [n_inst, L, E]
         if fused:
             from . import train_ops
+            cur, mask, act = cur.contiguous(), mask.contiguous(), act.contiguous()    # per_inst returns strided views
             g = train_ops.fused_attention(q, k, v, mask, add_residual=True)             # decoder.py:281-293 (+ q)
             g = train_ops.fused_ffn(g, w1, b1, w2, b2)                                  # decoder.py:296
             z = torch.bmm(g, lk.transpose(1, 2))                                        # raw pointer scores [n_inst, L, N]
