@@ -13,6 +13,7 @@
  *                           column sums of X and Y (bias gradients) from the same pass
  *   rrnco_train_attention   masked 8-head attention of one query row per (rollout, step) over the instance's keys
  *                           (decoder.py:281-293), forward and backward
+ *   rrnco_train_context_query  the context projection as a table gather + rank-k update (context.py:18-70), forward / backward
  *   rrnco_train_logits_tail edge bias, log(exp(.) + 1e-6), tanh clip, mask, temperature, log-softmax and the log-prob of
  *                           the given action with its Jacobian, in one pass (decoder.py:183-198, decoding.py:311-399)
  *
@@ -77,6 +78,18 @@ int rrnco_train_logits_tail(int64_t rows, int64_t rows_per_inst, int32_t n_nodes
                             const float* duration, const int64_t* current_node, const uint8_t* mask, const int64_t* action,
                             const float* alpha, const float* beta, float inv_sqrt_e, float tanh_clipping, float temperature,
                             float* logp, float* dlogp_dalpha, float* dlogp_dbeta, void* stream);
+
+/* Context query of the pointer (rrnco/models/env_embeddings/context.py:18-70, decoder.py:151-170) for the batched replay:
+ *     q[row] = table_a[b, index_a[row]] (+ table_b[b, index_b[row]]) + sum_s state[row, s] state_w[s]        b = row / rows_per_inst
+ *   table_a / table_b [n_inst, n_nodes, 128] = row_emb W_t^T (the node part of project_context; table_b / index_b NULL except
+ *   atsp: [first node, current node]); state [rows, n_state] (n_state <= 8), state_w [n_state, 128] = the state columns of W.
+ * backward: d_table_a / d_table_b / d_state_w are ACCUMULATED (fp32 vector atomics): the caller zeroes them. */
+int rrnco_train_context_query_fwd(int64_t rows, int64_t rows_per_inst, int32_t n_nodes, const float* table_a, const int64_t* index_a,
+                                  const float* table_b, const int64_t* index_b, const float* state, int32_t n_state,
+                                  const float* state_w, float* q, void* stream);
+int rrnco_train_context_query_bwd(int64_t rows, int64_t rows_per_inst, int32_t n_nodes, const float* dq, const int64_t* index_a,
+                                  const int64_t* index_b, const float* state, int32_t n_state, float* d_table_a, float* d_table_b,
+                                  float* d_state_w, void* stream);
 
 #ifdef __cplusplus
 }

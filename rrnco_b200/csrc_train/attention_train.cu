@@ -83,32 +83,38 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_fwd_kernel(int64_t L, int 
       const uint32_t word = mb[lane * kMbStride + wi];
       const int jn = min(32, N - wi * 32);
 #pragma unroll 1
-      for (int jj = 0; jj < jn; ++jj) {
-        const bool bit = (word >> jj) & 1u;
-        if (!__any_sync(0xffffffffu, bit)) continue;
-        const int j = wi * 32 + jj;
-        const float4* kp = reinterpret_cast<const float4*>(Ks + j * kE + h * 16);
-        float s = 0.f;
+      for (int jj = 0; jj < jn; jj += 2) {  // two keys per iteration (two independent chains)
+        const bool bit0 = (word >> jj) & 1u, bit1 = jj + 1 < jn && ((word >> (jj + 1)) & 1u);
+        if (!__any_sync(0xffffffffu, bit0 || bit1)) continue;
+        const int j0 = wi * 32 + jj, j1 = min(j0 + 1, N - 1);
+        const float4* kp0 = reinterpret_cast<const float4*>(Ks + j0 * kE + h * 16);
+        const float4* kp1 = reinterpret_cast<const float4*>(Ks + j1 * kE + h * 16);
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = kp[i];
-          s = fmaf(qs[4 * i], t.x, s); s = fmaf(qs[4 * i + 1], t.y, s); s = fmaf(qs[4 * i + 2], t.z, s); s = fmaf(qs[4 * i + 3], t.w, s);
+          const float4 t = kp0[i], t1 = kp1[i];
+          s0 = fmaf(qs[4 * i], t.x, s0); s0 = fmaf(qs[4 * i + 1], t.y, s0); s0 = fmaf(qs[4 * i + 2], t.z, s0); s0 = fmaf(qs[4 * i + 3], t.w, s0);
+          s1 = fmaf(qs[4 * i], t1.x, s1); s1 = fmaf(qs[4 * i + 1], t1.y, s1); s1 = fmaf(qs[4 * i + 2], t1.z, s1); s1 = fmaf(qs[4 * i + 3], t1.w, s1);
         }
-        if (bit && s > m + 8.f) {  // lazy rescale: rare after the first feasible key
-          const float corr = exp2f(m - s);
+        const float smax = fmaxf(bit0 ? s0 : -INFINITY, bit1 ? s1 : -INFINITY);
+        if (smax > m + 8.f) {  // lazy rescale: rare after the first feasible key
+          const float corr = exp2f(m - smax);
           l *= corr;
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] *= corr;
-          m = s;
+          m = smax;
         }
-        const float p = bit ? exp2f(s - m) : 0.f;
-        l += p;
-        const float4* vp = reinterpret_cast<const float4*>(Vs + j * kE + h * 16);
+        const float p0 = bit0 ? exp2f(s0 - m) : 0.f, p1 = bit1 ? exp2f(s1 - m) : 0.f;
+        l += p0 + p1;
+        const float4* vp0 = reinterpret_cast<const float4*>(Vs + j0 * kE + h * 16);
+        const float4* vp1 = reinterpret_cast<const float4*>(Vs + j1 * kE + h * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = vp[i];
-          o[4 * i] = fmaf(p, t.x, o[4 * i]); o[4 * i + 1] = fmaf(p, t.y, o[4 * i + 1]);
-          o[4 * i + 2] = fmaf(p, t.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(p, t.w, o[4 * i + 3]);
+          const float4 t = vp0[i], t1 = vp1[i];
+          o[4 * i] = fmaf(p0, t.x, o[4 * i]); o[4 * i + 1] = fmaf(p0, t.y, o[4 * i + 1]);
+          o[4 * i + 2] = fmaf(p0, t.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(p0, t.w, o[4 * i + 3]);
+          o[4 * i] = fmaf(p1, t1.x, o[4 * i]); o[4 * i + 1] = fmaf(p1, t1.y, o[4 * i + 1]);
+          o[4 * i + 2] = fmaf(p1, t1.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(p1, t1.w, o[4 * i + 3]);
         }
       }
     }
@@ -137,9 +143,9 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int 
   float* Vs = Ks + N * kE;
   float* dKs = Vs + N * kE;
   float* dVs = dKs + N * kE;
-  float* ps = dVs + N * kE;            // [8 warps][2 buffers][32 rows]
-  float* dss = ps + 8 * 2 * 32;
-  uint32_t* mb = reinterpret_cast<uint32_t*>(dss + 8 * 2 * 32);
+  float* ps = dVs + N * kE;            // [8 warps][2 buffers][2 keys][32 rows]
+  float* dss = ps + 8 * 2 * 64;
+  uint32_t* mb = reinterpret_cast<uint32_t*>(dss + 8 * 2 * 64);
   const int tid = threadIdx.x, h = tid >> 5, lane = tid & 31;
   const int64_t b = blockIdx.y;
   {
@@ -152,8 +158,8 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int 
       reinterpret_cast<float4*>(dVs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  float* pw = ps + h * 64;
-  float* dw = dss + h * 64;
+  float* pw = ps + h * 128;
+  float* dw = dss + h * 128;
   const int d = lane & 15, half = lane >> 4;
   const int64_t row_lo = b * L + (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row_hi = min(row_lo + rows_per_cta, (b + 1) * L);
@@ -198,44 +204,58 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int 
     for (int wi = 0; wi < 4; ++wi) {
       const uint32_t word = mb[lane * kMbStride + wi];
       const int jn = min(32, N - wi * 32);
+      // two keys per iteration: two independent dependency chains per warp (the kernel runs two warps per scheduler)
 #pragma unroll 1
-      for (int jj = 0; jj < jn; ++jj) {
-        const bool bit = (word >> jj) & 1u;
-        if (!__any_sync(0xffffffffu, bit)) continue;
-        const int j = wi * 32 + jj;
-        const float4* kp = reinterpret_cast<const float4*>(Ks + j * kE + h * 16);
-        const float4* vp = reinterpret_cast<const float4*>(Vs + j * kE + h * 16);
-        float kr[16];
-        float s = 0.f, dp = 0.f;
+      for (int jj = 0; jj < jn; jj += 2) {
+        const bool bit0 = (word >> jj) & 1u, bit1 = jj + 1 < jn && ((word >> (jj + 1)) & 1u);
+        if (!__any_sync(0xffffffffu, bit0 || bit1)) continue;
+        const int j0 = wi * 32 + jj, j1 = min(j0 + 1, N - 1);  // j1 clamped: its p / ds are zero when jj + 1 == jn
+        const float4* kp0 = reinterpret_cast<const float4*>(Ks + j0 * kE + h * 16);
+        const float4* vp0 = reinterpret_cast<const float4*>(Vs + j0 * kE + h * 16);
+        const float4* kp1 = reinterpret_cast<const float4*>(Ks + j1 * kE + h * 16);
+        const float4* vp1 = reinterpret_cast<const float4*>(Vs + j1 * kE + h * 16);
+        float s0 = 0.f, dp0 = 0.f, s1 = 0.f, dp1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = kp[i];
-          kr[4 * i] = t.x; kr[4 * i + 1] = t.y; kr[4 * i + 2] = t.z; kr[4 * i + 3] = t.w;
-          s = fmaf(qs[4 * i], t.x, s); s = fmaf(qs[4 * i + 1], t.y, s); s = fmaf(qs[4 * i + 2], t.z, s); s = fmaf(qs[4 * i + 3], t.w, s);
-          const float4 u = vp[i];
-          dp = fmaf(go[4 * i], u.x, dp); dp = fmaf(go[4 * i + 1], u.y, dp); dp = fmaf(go[4 * i + 2], u.z, dp); dp = fmaf(go[4 * i + 3], u.w, dp);
+          const float4 t = kp0[i], u = vp0[i], t1 = kp1[i], u1 = vp1[i];
+          s0 = fmaf(qs[4 * i], t.x, s0); s0 = fmaf(qs[4 * i + 1], t.y, s0); s0 = fmaf(qs[4 * i + 2], t.z, s0); s0 = fmaf(qs[4 * i + 3], t.w, s0);
+          dp0 = fmaf(go[4 * i], u.x, dp0); dp0 = fmaf(go[4 * i + 1], u.y, dp0); dp0 = fmaf(go[4 * i + 2], u.z, dp0); dp0 = fmaf(go[4 * i + 3], u.w, dp0);
+          s1 = fmaf(qs[4 * i], t1.x, s1); s1 = fmaf(qs[4 * i + 1], t1.y, s1); s1 = fmaf(qs[4 * i + 2], t1.z, s1); s1 = fmaf(qs[4 * i + 3], t1.w, s1);
+          dp1 = fmaf(go[4 * i], u1.x, dp1); dp1 = fmaf(go[4 * i + 1], u1.y, dp1); dp1 = fmaf(go[4 * i + 2], u1.z, dp1); dp1 = fmaf(go[4 * i + 3], u1.w, dp1);
         }
-        const float p = bit ? exp2f(s - lse) : 0.f;
-        const float ds = p * (dp - D);  // gradient of the natural-log-domain score q . k / 4
+        const float p0 = bit0 ? exp2f(s0 - lse) : 0.f, p1 = bit1 ? exp2f(s1 - lse) : 0.f;
+        const float ds0 = p0 * (dp0 - D), ds1 = p1 * (dp1 - D);  // gradients of the natural-log-domain scores q . k / 4
 #pragma unroll
-        for (int i = 0; i < 16; ++i) gq[i] = fmaf(ds, kr[i], gq[i]);
-        pw[buf * 32 + lane] = p;
-        dw[buf * 32 + lane] = ds;
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = kp0[i], t1 = kp1[i];
+          gq[4 * i] = fmaf(ds0, t.x, gq[4 * i]); gq[4 * i + 1] = fmaf(ds0, t.y, gq[4 * i + 1]);
+          gq[4 * i + 2] = fmaf(ds0, t.z, gq[4 * i + 2]); gq[4 * i + 3] = fmaf(ds0, t.w, gq[4 * i + 3]);
+          gq[4 * i] = fmaf(ds1, t1.x, gq[4 * i]); gq[4 * i + 1] = fmaf(ds1, t1.y, gq[4 * i + 1]);
+          gq[4 * i + 2] = fmaf(ds1, t1.z, gq[4 * i + 2]); gq[4 * i + 3] = fmaf(ds1, t1.w, gq[4 * i + 3]);
+        }
+        float* pb = pw + buf * 64;
+        float* db = dw + buf * 64;
+        pb[lane] = p0; pb[32 + lane] = p1;
+        db[lane] = ds0; db[32 + lane] = ds1;
         __syncwarp();
         // sums over the 32 rows: lanes 0-15 finish dV[j][d], lanes 16-31 dK[j][d]
-        const float4* pp = reinterpret_cast<const float4*>(pw + buf * 32 + half * 16);
-        const float4* dd = reinterpret_cast<const float4*>(dw + buf * 32 + half * 16);
-        float av = 0.f, ak = 0.f;
+        float av0 = 0.f, ak0 = 0.f, av1 = 0.f, ak1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = pp[i], u = dd[i];
-          av = fmaf(t.x, cdo[4 * i], av); av = fmaf(t.y, cdo[4 * i + 1], av); av = fmaf(t.z, cdo[4 * i + 2], av); av = fmaf(t.w, cdo[4 * i + 3], av);
-          ak = fmaf(u.x, cq[4 * i], ak); ak = fmaf(u.y, cq[4 * i + 1], ak); ak = fmaf(u.z, cq[4 * i + 2], ak); ak = fmaf(u.w, cq[4 * i + 3], ak);
+          const float4 t = reinterpret_cast<const float4*>(pb + half * 16)[i], u = reinterpret_cast<const float4*>(db + half * 16)[i];
+          const float4 t1 = reinterpret_cast<const float4*>(pb + 32 + half * 16)[i], u1 = reinterpret_cast<const float4*>(db + 32 + half * 16)[i];
+          av0 = fmaf(t.x, cdo[4 * i], av0); av0 = fmaf(t.y, cdo[4 * i + 1], av0); av0 = fmaf(t.z, cdo[4 * i + 2], av0); av0 = fmaf(t.w, cdo[4 * i + 3], av0);
+          ak0 = fmaf(u.x, cq[4 * i], ak0); ak0 = fmaf(u.y, cq[4 * i + 1], ak0); ak0 = fmaf(u.z, cq[4 * i + 2], ak0); ak0 = fmaf(u.w, cq[4 * i + 3], ak0);
+          av1 = fmaf(t1.x, cdo[4 * i], av1); av1 = fmaf(t1.y, cdo[4 * i + 1], av1); av1 = fmaf(t1.z, cdo[4 * i + 2], av1); av1 = fmaf(t1.w, cdo[4 * i + 3], av1);
+          ak1 = fmaf(u1.x, cq[4 * i], ak1); ak1 = fmaf(u1.y, cq[4 * i + 1], ak1); ak1 = fmaf(u1.z, cq[4 * i + 2], ak1); ak1 = fmaf(u1.w, cq[4 * i + 3], ak1);
         }
-        av += __shfl_xor_sync(0xffffffffu, av, 16);
-        ak += __shfl_xor_sync(0xffffffffu, ak, 16);
-        float* acc = (half == 0 ? dVs : dKs) + j * kE + h * 16 + d;
-        *acc += half == 0 ? av : ak;
+        av0 += __shfl_xor_sync(0xffffffffu, av0, 16);
+        ak0 += __shfl_xor_sync(0xffffffffu, ak0, 16);
+        av1 += __shfl_xor_sync(0xffffffffu, av1, 16);
+        ak1 += __shfl_xor_sync(0xffffffffu, ak1, 16);
+        float* acc = (half == 0 ? dVs : dKs) + h * 16 + d;
+        acc[j0 * kE] += half == 0 ? av0 : ak0;
+        if (jj + 1 < jn) acc[j1 * kE] += half == 0 ? av1 : ak1;
         buf ^= 1;
       }
     }
@@ -304,7 +324,7 @@ int rrnco_train_attention_bwd(int64_t n_inst, int64_t rows_per_inst, int32_t n_n
   RRNCO_CHECK_ARG(n_inst > 0 && rows_per_inst > 0 && n_nodes > 0 && q && k && v && mask && out && lse && d_out && dq && dk && dv);
   RRNCO_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                     reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(dq)) & 15u) == 0);
-  const size_t smem = (size_t)4 * n_nodes * kE * sizeof(float) + 2 * 8 * 2 * 32 * sizeof(float) + kAtGroup * kMbStride * sizeof(uint32_t);
+  const size_t smem = (size_t)4 * n_nodes * kE * sizeof(float) + 2 * 8 * 2 * 64 * sizeof(float) + kAtGroup * kMbStride * sizeof(uint32_t);
   if (smem > 227 * 1024 || n_inst > 65535) return RRNCO_ERR_UNSUPPORTED;  // n_nodes <= 108
   static PerDeviceOnce once;
   if (once.first()) {

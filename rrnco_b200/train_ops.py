@@ -29,6 +29,8 @@ _SIGNATURES = {
     "rrnco_train_xty": (C.c_int, [C.c_int64, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
     "rrnco_train_attention_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, C.c_int32, _f, _f, _f]),
     "rrnco_train_attention_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, C.c_int32, _f, _f, _f, _f, _f, _f]),
+    "rrnco_train_context_query_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, C.c_int32, _f, _f, _f]),
+    "rrnco_train_context_query_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, C.c_int32, _f, _f, _f, _f]),
     "rrnco_train_logits_tail": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, _f, _f, _f, C.c_float, C.c_float,
                                           C.c_float, _f, _f, _f, _f]),
 }
@@ -108,6 +110,9 @@ def _pack(wa, wb, dev):
     return packed
 
 
+SAVE_HIDDEN = True   # keep the [rows, 512] hidden activations of the forward call for dW2 (2 KB per row) instead of recomputing them
+
+
 class _FusedFFN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
@@ -117,25 +122,29 @@ class _FusedFFN(torch.autograd.Function):
         rows = x.shape[0]
         mask = torch.empty(rows, 16, dtype=torch.int32, device=dev)
         y = torch.empty_like(x)
+        keep = SAVE_HIDDEN and any(ctx.needs_input_grad)
+        hidden = torch.empty(rows, 512, dtype=torch.float32, device=dev) if keep else None
         packed = _pack(w1, w2, dev)
-        _check(h.rrnco_train_ffn(0, rows, _p(x), _p(packed), _p(b1), _p(b2), None, _p(mask), None, _p(y),
+        _check(h.rrnco_train_ffn(0, rows, _p(x), _p(packed), _p(b1), _p(b2), None, _p(mask), _p(hidden), _p(y),
                                  _p(status_word(dev)), _stream(dev)), "rrnco_train_ffn")
-        ctx.save_for_backward(x, mask, w1, b1, w2, b2)
+        ctx.save_for_backward(x, mask, w1, b1, w2, b2, hidden)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, mask, w1, b1, w2, b2 = ctx.saved_tensors
+        x, mask, w1, b1, w2, b2, hidden = ctx.saved_tensors
         h, dev, st = lib(), x.device, status_word(x.device)
         rows = x.shape[0]
         dy = dy.contiguous().float()
-        s_dy = pow2_scale(dy)
+        amax = dy.abs().amax()
+        s_dy = pow2_scale(amax)
         # |dhidden_j| <= max|dy| * sum_e |W2[e, j]|: a rigorous bound without a pass over the [rows, 512] tensor
-        s_dh = pow2_scale(dy, bound_factor=w2.abs().sum(0).amax().clamp_min(1.0))
-        hidden = torch.empty(rows, 512, dtype=torch.float32, device=dev)
-        packed = _pack(w1, w2, dev)
-        _check(h.rrnco_train_ffn(0, rows, _p(x), _p(packed), _p(b1), _p(b2), None, None, _p(hidden), None, _p(st),
-                                 _stream(dev)), "rrnco_train_ffn (recompute)")
+        s_dh = pow2_scale(amax, bound_factor=w2.abs().sum(0).amax().clamp_min(1.0))
+        if hidden is None:
+            hidden = torch.empty(rows, 512, dtype=torch.float32, device=dev)
+            packed = _pack(w1, w2, dev)
+            _check(h.rrnco_train_ffn(0, rows, _p(x), _p(packed), _p(b1), _p(b2), None, None, _p(hidden), None, _p(st),
+                                     _stream(dev)), "rrnco_train_ffn (recompute)")
         dhid = torch.empty(rows, 512, dtype=torch.float32, device=dev)
         dx = torch.empty_like(x)
         packed_t = _pack(w2.t().contiguous(), w1.t().contiguous(), dev)
@@ -189,6 +198,46 @@ class _FusedAttention(torch.autograd.Function):
 def fused_attention(q, k, v, mask, add_residual: bool = True):
     """softmax(q_h k_h^T / 4 + mask) v_h (+ q): q [n_inst, L, 128], k / v [n_inst, N, 128], mask [n_inst, L, N] bool."""
     return _FusedAttention.apply(q, k, v, mask, add_residual)
+
+
+class _ContextQuery(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table_a, index_a, table_b, index_b, state, state_w):
+        h, dev = lib(), table_a.device
+        n_inst, N, _ = table_a.shape
+        L = index_a.shape[1]
+        table_a = table_a.detach().contiguous().float()
+        table_b = table_b.detach().contiguous().float() if table_b is not None else None
+        index_a = index_a.contiguous()
+        index_b = index_b.contiguous() if index_b is not None else None
+        n_state = 0 if state is None else state.shape[-1]
+        state = state.detach().contiguous().float() if state is not None else None
+        state_w = state_w.detach().contiguous().float() if state_w is not None else None
+        q = torch.empty(n_inst, L, 128, dtype=torch.float32, device=dev)
+        _check(h.rrnco_train_context_query_fwd(n_inst * L, L, N, _p(table_a), _p(index_a), _p(table_b), _p(index_b), _p(state), n_state,
+                                               _p(state_w), _p(q), _stream(dev)), "rrnco_train_context_query_fwd")
+        ctx.save_for_backward(index_a, index_b, state)
+        ctx.dims = (n_inst, N, L, n_state)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        index_a, index_b, state = ctx.saved_tensors
+        h, dev = lib(), dq.device
+        n_inst, N, L, n_state = ctx.dims
+        dq = dq.contiguous().float()
+        da = torch.zeros(n_inst, N, 128, dtype=torch.float32, device=dev)
+        db = torch.zeros(n_inst, N, 128, dtype=torch.float32, device=dev) if index_b is not None else None
+        dw = torch.zeros(n_state, 128, dtype=torch.float32, device=dev) if n_state else None
+        _check(h.rrnco_train_context_query_bwd(n_inst * L, L, N, _p(dq), _p(index_a), _p(index_b), _p(state), n_state, _p(da), _p(db),
+                                               _p(dw), _stream(dev)), "rrnco_train_context_query_bwd")
+        return da, None, db, None, None, dw
+
+
+def context_query(table_a, index_a, table_b=None, index_b=None, state=None, state_w=None):
+    """q [n_inst, L, 128] = table_a[b, index_a] (+ table_b[b, index_b]) + state @ state_w; tables [n_inst, N, 128] = row_emb W_t^T,
+    indices [n_inst, L] int64, state [n_inst, L, k], state_w [k, 128] (context.py:18-70 with the linear projection pulled through the gather)."""
+    return _ContextQuery.apply(table_a, index_a, table_b, index_b, state, state_w)
 
 
 class _LogitsTail(torch.autograd.Function):

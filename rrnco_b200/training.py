@@ -95,6 +95,9 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
     inst = torch.arange(n_inst, device=col_emb.device)
     w1, b1 = decoder.pointer.ffn.lins[0].weight, decoder.pointer.ffn.lins[0].bias
     w2, b2 = decoder.pointer.ffn.lins[1].weight, decoder.pointer.ffn.lins[1].bias
+    if fused:  # node part of project_context as per-instance tables (tiny GEMMs, torch autograd)
+        tab_a = F.linear(row_emb, W[:, :E])
+        tab_b = F.linear(row_emb, W[:, E:2 * E]) if name == "atsp" else None
     out = []
     for t0 in range(0, Tm, step_chunk):
         t1 = min(Tm, t0 + step_chunk)
@@ -106,16 +109,13 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
         cur = per_inst(inputs["current_node"][t0:t1])                      # [n_inst, L]
         mask = per_inst(inputs["action_mask"][t0:t1]).bool()               # [n_inst, L, N]
         act = per_inst(actions[:, 1 + t0:1 + t1].t().contiguous())         # [n_inst, L]
-        emb_cur = row_emb[inst[:, None], cur]                              # [n_inst, L, E]
-        if name == "atsp":  # rl4co TSPContext: [first, current] (multistart: never the placeholder)
-            first = per_inst(inputs["first_node"][t0:t1])
-            ctx = torch.cat([row_emb[inst[:, None], first], emb_cur], -1)
-        else:               # context.py:18-31: [current-node embedding, state scalars]
-            ctx = torch.cat([emb_cur, per_inst(inputs["ctx_state"][t0:t1]).to(emb_cur.dtype)], -1)
-        q = F.linear(ctx, W)                                               # [n_inst, L, E]
-        if fused:
+        if fused:   # context.py:18-70 with the projection pulled through the gather: q = P[b, cur] (+ P2[b, ..]) + state W_s^T
             from . import train_ops
             cur, mask, act = cur.contiguous(), mask.contiguous(), act.contiguous()    # per_inst returns strided views
+            if name == "atsp":
+                q = train_ops.context_query(tab_a, per_inst(inputs["first_node"][t0:t1]), tab_b, cur)
+            else:
+                q = train_ops.context_query(tab_a, cur, None, None, per_inst(inputs["ctx_state"][t0:t1]), W[:, E:].t())
             g = train_ops.fused_attention(q, k, v, mask, add_residual=True)             # decoder.py:281-293 (+ q)
             g = train_ops.fused_ffn(g, w1, b1, w2, b2)                                  # decoder.py:296
             z = torch.bmm(g, lk.transpose(1, 2))                                        # raw pointer scores [n_inst, L, N]
@@ -124,6 +124,13 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
                                                temperature)                             # decoder.py:183-198, decoding.py:311-399
             out.append(logp.unflatten(1, (t1 - t0, S)).permute(2, 0, 1).reshape(R, t1 - t0))
             continue
+        emb_cur = row_emb[inst[:, None], cur]                              # [n_inst, L, E]
+        if name == "atsp":  # rl4co TSPContext: [first, current] (multistart: never the placeholder)
+            first = per_inst(inputs["first_node"][t0:t1])
+            ctx = torch.cat([row_emb[inst[:, None], first], emb_cur], -1)
+        else:               # context.py:18-31: [current-node embedding, state scalars]
+            ctx = torch.cat([emb_cur, per_inst(inputs["ctx_state"][t0:t1]).to(emb_cur.dtype)], -1)
+        q = F.linear(ctx, W)                                               # [n_inst, L, E]
         if ATTENTION_IMPL == "sdpa":
             h = F.scaled_dot_product_attention(heads(q), kh, vh, attn_mask=mask.unsqueeze(1))  # decoder.py:281-293
         else:  # explicit: head dim 16 and 101 keys are far from the tile shapes of the fused SDPA kernels

@@ -21,7 +21,7 @@ def test_train_header_symbols_exported():
     header = open(os.path.join(ROOT, "include", "rrnco_b200_train.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     declared = set(re.findall(r"\b(rrnco_[a-z_0-9]+)\s*\(", header))
-    assert {"rrnco_train_ffn", "rrnco_train_xty", "rrnco_train_attention_bwd", "rrnco_train_logits_tail"} <= declared
+    assert {"rrnco_train_ffn", "rrnco_train_xty", "rrnco_train_attention_bwd", "rrnco_train_logits_tail", "rrnco_train_context_query_bwd"} <= declared
     handle = ctypes.CDLL(path)
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in include/rrnco_b200_train.h but not exported"
@@ -54,6 +54,7 @@ def _ffn_params(seed, dev):
 def test_fused_ffn_forward_backward(rows, gscale):
     from rrnco_b200 import train_ops
     dev = torch.device("cuda", 0)
+    torch.manual_seed(rows)
     g = torch.Generator().manual_seed(rows)
     x = (torch.randn(rows, 128, generator=g) * 2).to(dev).requires_grad_(True)
     r = (torch.randn(rows, 128, generator=g) * gscale).to(dev)
@@ -71,7 +72,7 @@ def test_fused_ffn_forward_backward(rows, gscale):
     train_ops.check_status(dev)
     for name, a, b in zip(("y", "dx", "dw1", "db1", "dw2", "db2"), got, want):
         assert a.shape == b.shape, name
-        assert _rel(a, b) < 2e-6, (name, _rel(a, b))
+        assert _rel(a, b) < 5e-6, (name, _rel(a, b))   # fp32 level: an fp32 FMA chain over K = 512 is no closer to fp64
 
 
 def _attention_ref(q, k, v, mask):
@@ -155,6 +156,41 @@ def test_fused_logits_tail_forward_backward(with_dur, clip, temp, N):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("two_tables,n_state", [(False, 1), (True, 0), (False, 4)])
+def test_context_query_forward_backward(two_tables, n_state):
+    from rrnco_b200 import train_ops
+    dev = torch.device("cuda", 0)
+    n_inst, L, N = 4, 333, 101
+    g = torch.Generator().manual_seed(7 + n_state)
+    ta = torch.randn(n_inst, N, 128, generator=g).to(dev).requires_grad_(True)
+    tb = torch.randn(n_inst, N, 128, generator=g).to(dev).requires_grad_(True) if two_tables else None
+    ia = torch.randint(0, N, (n_inst, L), generator=g).to(dev)
+    ib = torch.randint(0, N, (n_inst, L), generator=g).to(dev) if two_tables else None
+    st = torch.rand(n_inst, L, n_state, generator=g).to(dev) if n_state else None
+    sw = torch.randn(128, n_state, generator=g).to(dev).requires_grad_(True) if n_state else None   # W[:, E:]
+    r = torch.randn(n_inst, L, 128, generator=g).to(dev)
+    q = train_ops.context_query(ta, ia, tb, ib, st, sw.t() if n_state else None)
+    (q * r).sum().backward()
+    inst = torch.arange(n_inst, device=dev)[:, None]
+    tad = ta.detach().double().requires_grad_(True)
+    want = tad[inst, ia]
+    tbd = swd = None
+    if two_tables:
+        tbd = tb.detach().double().requires_grad_(True)
+        want = want + tbd[inst, ib]
+    if n_state:
+        swd = sw.detach().double().requires_grad_(True)
+        want = want + st.double() @ swd.t()
+    (want * r.double()).sum().backward()
+    assert _rel(q.detach(), want.detach()) < 1e-6
+    assert _rel(ta.grad, tad.grad) < 1e-5
+    if two_tables:
+        assert _rel(tb.grad, tbd.grad) < 1e-5
+    if n_state:
+        assert _rel(sw.grad, swd.grad) < 1e-5
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["rcvrp", "atsp", "rcvrptw"])
 def test_fused_replay_matches_aten_replay(name):
     """training.batched_logprobs: fused kernels vs the plain-torch form on the same sampled rollouts - log-likelihood and the
@@ -195,5 +231,5 @@ def test_fused_replay_matches_aten_replay(name):
     assert (res["fused"][0] - res["aten"][0]).abs().max().item() < 2e-4
     assert (res["fused"][0] - out["log_likelihood"]).abs().max().item() < 2e-4   # and the sampling kernel's own log-likelihood
     assert set(res["fused"][1]) == set(res["aten"][1])
-    for k, gref in res["aten"][1].items():
-        assert _rel(res["fused"][1][k], gref) < 1e-4, (k, _rel(res["fused"][1][k], gref))
+    errs = {k: _rel(res["fused"][1][k], gref) for k, gref in res["aten"][1].items()}
+    assert max(errs.values()) < 1e-4, errs

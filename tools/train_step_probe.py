@@ -33,7 +33,12 @@ def sync_time():
 
 
 from rrnco_b200 import training as _tr  # noqa: E402
+_prof = None
 for it in range(int(os.environ.get("ITERS", 5))):
+    if os.environ.get("PROFILE") and it == int(os.environ.get("ITERS", 5)) - 1:
+        from torch.profiler import profile, ProfilerActivity
+        _prof = profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU])
+        _prof.__enter__()
     ac = torch.bfloat16 if it >= 3 and os.environ.get("BF16") else None
     _tr.ATTENTION_IMPL = os.environ.get("ATTN", "sdpa")
     _tr.REPLAY_IMPL = os.environ.get("IMPL", "fused")
@@ -59,3 +64,6 @@ for it in range(int(os.environ.get("ITERS", 5))):
           f"= {B/(t4-t0):7.1f} instances/s | max |ll - kernel ll| {err:.1e} | peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB")
     pol.zero_grad(set_to_none=True)
     row.grad = col.grad = None
+if _prof is not None:
+    _prof.__exit__(None, None, None)
+    print(_prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
