@@ -61,7 +61,7 @@ int rrnco_train_xty(int64_t rows, const float* x, const float* y, const float* s
  *            masked scores (opaque: saved for the backward pass)
  * backward:  given d_out (gradient of `out`) and the forward call's `out` / `lse` / `add_residual`: dq [n_inst L, 128] (the residual
  *            path d_out included when add_residual != 0), dk / dv [n_inst, n_nodes, 128]
- *            (zeroed, then accumulated with fp32 atomics); n_nodes <= 108 (K, V, dK, dV tiles in shared memory) */
+ *            (zeroed, then accumulated with fp32 atomics); n_nodes <= 102 (K, V, dK, dV tiles in shared memory) */
 int rrnco_train_attention_fwd(int64_t n_inst, int64_t rows_per_inst, int32_t n_nodes, const float* q, const float* k, const float* v,
                               const uint8_t* mask, int32_t add_residual, float* out, float* lse, void* stream);
 int rrnco_train_attention_bwd(int64_t n_inst, int64_t rows_per_inst, int32_t n_nodes, const float* q, const float* k, const float* v,

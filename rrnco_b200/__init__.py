@@ -21,11 +21,11 @@ from .transforms import StateAugmentation, dihedral_8_augmentation  # noqa: F401
 from .tdlite import TensorDictLite, batchify, unbatchify  # noqa: F401
 from .torch_ops import use_torch_ops  # noqa: F401
 from .encoder_ops import DistAngleFusion, aft_nab, patch_encoder  # noqa: F401
-from .training import (batched_logprobs, collect_decode_inputs, pomo_shared_baseline_loss,  # noqa: F401
+from .training import (batched_logprobs, collect_decode_inputs, iter_decode_inputs, pomo_shared_baseline_loss,  # noqa: F401
                        replay_log_likelihood)
 
 __all__ = ["ATSPEnv", "RCVRPEnv", "RMTVRPEnv", "get_env", "RRNetDecoder", "RRNetPolicy", "PrecomputedCache",
            "fused_rollout", "stepwise_rollout", "select_action", "Real_World_Sampler", "TensorDictLite", "batchify", "unbatchify", "set_precision", "set_ffn_engine", "set_step_tiling",
-           "RRNCOError", "HostPrefetcher", "load_city_npz", "load_npz_to_tensordict", "prepare_test_td", "iter_batches", "replay_log_likelihood", "batched_logprobs", "collect_decode_inputs",
+           "RRNCOError", "HostPrefetcher", "load_city_npz", "load_npz_to_tensordict", "prepare_test_td", "iter_batches", "replay_log_likelihood", "batched_logprobs", "collect_decode_inputs", "iter_decode_inputs",
            "pomo_shared_baseline_loss", "CityOnDevice", "remove_outlier_points", "LazyATSPGenerator", "LazyRCVRPGenerator",
            "LazyRMTVRPGenerator", "StateAugmentation", "dihedral_8_augmentation"]

@@ -21,6 +21,8 @@ constexpr int kAtGroup = 32;      // rows per group (lane = row)
 constexpr int kMbStride = 5;      // mask words per row in shared memory (4 + 1 pad)
 constexpr float kQScale = 0.25f * 1.4426950408889634f;  // 1 / sqrt(16) and log2(e): scores in the log2 domain
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
 // mask bytes of the 32 rows [g0, g0 + 32) -> 4 bit words per row in shared memory (thread = (row, 16-key segment))
 __device__ __forceinline__ void stage_mask_bits(uint32_t* mb, const uint8_t* __restrict__ mask, int64_t g0, int64_t row_hi, int N,
                                                 int tid) {
@@ -63,6 +65,10 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_fwd_kernel(int64_t L, int 
     __syncthreads();
     const int64_t row = g0 + lane;
     const bool valid = row < row_hi;
+    if (row + kAtGroup < row_hi) {  // the next group's rows stream from HBM: start them now (one CTA per SM leaves nothing else to hide the latency)
+      prefetch_l2(q + (row + kAtGroup) * kE + h * 16);
+      if (tid * 16 < kAtGroup * N) prefetch_l2(mask + (g0 + kAtGroup) * N + tid * 16);
+    }
     float qr[16], qs[16], o[16];
     {
       const float4* src = reinterpret_cast<const float4*>(q + row * kE + h * 16);
@@ -89,13 +95,14 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_fwd_kernel(int64_t L, int 
         const int j0 = wi * 32 + jj, j1 = min(j0 + 1, N - 1);
         const float4* kp0 = reinterpret_cast<const float4*>(Ks + j0 * kE + h * 16);
         const float4* kp1 = reinterpret_cast<const float4*>(Ks + j1 * kE + h * 16);
-        float s0 = 0.f, s1 = 0.f;
+        float sa[4], sb[4];   // independent partial sums (short dependency chains)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 t = kp0[i], t1 = kp1[i];
-          s0 = fmaf(qs[4 * i], t.x, s0); s0 = fmaf(qs[4 * i + 1], t.y, s0); s0 = fmaf(qs[4 * i + 2], t.z, s0); s0 = fmaf(qs[4 * i + 3], t.w, s0);
-          s1 = fmaf(qs[4 * i], t1.x, s1); s1 = fmaf(qs[4 * i + 1], t1.y, s1); s1 = fmaf(qs[4 * i + 2], t1.z, s1); s1 = fmaf(qs[4 * i + 3], t1.w, s1);
+          sa[i] = fmaf(qs[4 * i + 3], t.w, fmaf(qs[4 * i + 2], t.z, fmaf(qs[4 * i + 1], t.y, qs[4 * i] * t.x)));
+          sb[i] = fmaf(qs[4 * i + 3], t1.w, fmaf(qs[4 * i + 2], t1.z, fmaf(qs[4 * i + 1], t1.y, qs[4 * i] * t1.x)));
         }
+        const float s0 = (sa[0] + sa[1]) + (sa[2] + sa[3]), s1 = (sb[0] + sb[1]) + (sb[2] + sb[3]);
         const float smax = fmaxf(bit0 ? s0 : -INFINITY, bit1 ? s1 : -INFINITY);
         if (smax > m + 8.f) {  // lazy rescale: rare after the first feasible key
           const float corr = exp2f(m - smax);
@@ -132,6 +139,13 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_fwd_kernel(int64_t L, int 
   }
 }
 
+// Backward.  Shared memory -> register bandwidth (128 B per clock per SM, broadcast or not) is what bounds these kernels: a
+// K / V row costs 32 crossbar cycles per (32 rows, key, head).  The sums over rows (dV = P^T dO, dK = dS^T q) therefore do NOT
+// go through per-lane broadcast reads of p / ds (another 32 cycles): they are 16 x 8 x 32 products on the legacy tensor path
+// (mma.sync m16n8k8, 3xTF32 = fp32-faithful): A = the head's dO^T / q^T columns of the 32 rows (raw fp32 in registers, split on
+// the fly), B = the p / ds values of 8 keys as each lane wrote them ([key][row], conflict-free fragment loads: 2 cycles per key).
+constexpr int kPsStride = 36;   // floats per key row of the p / ds hand-over tiles: (36 g + t) % 32 distinct over a fragment load
+constexpr int kAccStride = 132; // floats per key row of the dK / dV tiles: (2 t * 132 + g) % 32 distinct over a fragment update
 __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int rows_per_cta, int N, const float* __restrict__ q,
                                                                 const float* __restrict__ k, const float* __restrict__ v,
                                                                 const uint8_t* __restrict__ mask, const float* __restrict__ out,
@@ -141,12 +155,13 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int 
   extern __shared__ __align__(16) float at_smem[];
   float* Ks = at_smem;
   float* Vs = Ks + N * kE;
-  float* dKs = Vs + N * kE;
-  float* dVs = dKs + N * kE;
-  float* ps = dVs + N * kE;            // [8 warps][2 buffers][2 keys][32 rows]
-  float* dss = ps + 8 * 2 * 64;
-  uint32_t* mb = reinterpret_cast<uint32_t*>(dss + 8 * 2 * 64);
+  float* dKs = Vs + N * kE;                 // [N][kAccStride]
+  float* dVs = dKs + N * kAccStride;
+  float* ps = dVs + N * kAccStride;         // [8 warps][8 keys][kPsStride]
+  float* dss = ps + 8 * 8 * kPsStride;
+  uint32_t* mb = reinterpret_cast<uint32_t*>(dss + 8 * 8 * kPsStride);
   const int tid = threadIdx.x, h = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int64_t b = blockIdx.y;
   {
     const float4* k4 = reinterpret_cast<const float4*>(k + b * N * kE);
@@ -154,13 +169,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int 
     for (int i = tid; i < N * (kE / 4); i += kAtThreads) {
       reinterpret_cast<float4*>(Ks)[i] = __ldg(k4 + i);
       reinterpret_cast<float4*>(Vs)[i] = __ldg(v4 + i);
-      reinterpret_cast<float4*>(dKs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      reinterpret_cast<float4*>(dVs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    for (int i = tid; i < 2 * N * kAccStride; i += kAtThreads) dKs[i] = 0.f;   // dKs and dVs are adjacent
   }
-  float* pw = ps + h * 128;
-  float* dw = dss + h * 128;
-  const int d = lane & 15, half = lane >> 4;
+  float* pw = ps + h * 8 * kPsStride;
+  float* dw = dss + h * 8 * kPsStride;
   const int64_t row_lo = b * L + (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row_hi = min(row_lo + rows_per_cta, (b + 1) * L);
   for (int64_t g0 = row_lo; g0 < row_hi; g0 += kAtGroup) {
@@ -169,6 +182,12 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int 
     __syncthreads();
     const int64_t row = g0 + lane;
     const bool valid = row < row_hi;
+    if (row + kAtGroup < row_hi) {  // the next group's rows stream from HBM: start them now (one CTA per SM leaves nothing else to hide the latency)
+      prefetch_l2(q + (row + kAtGroup) * kE + h * 16);
+      prefetch_l2(d_out + (row + kAtGroup) * kE + h * 16);
+      prefetch_l2(out + (row + kAtGroup) * kE + h * 16);
+      if (tid * 16 < kAtGroup * N) prefetch_l2(mask + (g0 + kAtGroup) * N + tid * 16);
+    }
     // ---- this lane's row: scaled q, dO, D = dO . attn, log-sum-exp ----
     float qs[16], go[16], gq[16];
     float D = 0.f;
@@ -190,74 +209,86 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int 
     const float lse = valid ? __ldg(lse2 + row * kH + h) : 1e30f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) gq[i] = 0.f;
-    // ---- the 16 rows of this lane's half, column d: dO and q (for the sums over rows) ----
-    float cdo[16], cq[16];
+    // ---- A fragments of the row sums: dO^T and (q / 4)^T of this head, [16 columns x 32 rows], raw fp32 ----
+    float ado[4][4], aq[4][4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int64_t r = g0 + half * 16 + i;
-      const bool ok = r < row_hi;
-      cdo[i] = ok ? __ldg(d_out + r * kE + h * 16 + d) : 0.f;
-      cq[i] = ok ? __ldg(q + r * kE + h * 16 + d) * 0.25f : 0.f;
-    }
-    int buf = 0;
-#pragma unroll 1
-    for (int wi = 0; wi < 4; ++wi) {
-      const uint32_t word = mb[lane * kMbStride + wi];
-      const int jn = min(32, N - wi * 32);
-      // two keys per iteration: two independent dependency chains per warp (the kernel runs two warps per scheduler)
-#pragma unroll 1
-      for (int jj = 0; jj < jn; jj += 2) {
-        const bool bit0 = (word >> jj) & 1u, bit1 = jj + 1 < jn && ((word >> (jj + 1)) & 1u);
-        if (!__any_sync(0xffffffffu, bit0 || bit1)) continue;
-        const int j0 = wi * 32 + jj, j1 = min(j0 + 1, N - 1);  // j1 clamped: its p / ds are zero when jj + 1 == jn
-        const float4* kp0 = reinterpret_cast<const float4*>(Ks + j0 * kE + h * 16);
-        const float4* vp0 = reinterpret_cast<const float4*>(Vs + j0 * kE + h * 16);
-        const float4* kp1 = reinterpret_cast<const float4*>(Ks + j1 * kE + h * 16);
-        const float4* vp1 = reinterpret_cast<const float4*>(Vs + j1 * kE + h * 16);
-        float s0 = 0.f, dp0 = 0.f, s1 = 0.f, dp1 = 0.f;
+    for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 t = kp0[i], u = vp0[i], t1 = kp1[i], u1 = vp1[i];
-          s0 = fmaf(qs[4 * i], t.x, s0); s0 = fmaf(qs[4 * i + 1], t.y, s0); s0 = fmaf(qs[4 * i + 2], t.z, s0); s0 = fmaf(qs[4 * i + 3], t.w, s0);
-          dp0 = fmaf(go[4 * i], u.x, dp0); dp0 = fmaf(go[4 * i + 1], u.y, dp0); dp0 = fmaf(go[4 * i + 2], u.z, dp0); dp0 = fmaf(go[4 * i + 3], u.w, dp0);
-          s1 = fmaf(qs[4 * i], t1.x, s1); s1 = fmaf(qs[4 * i + 1], t1.y, s1); s1 = fmaf(qs[4 * i + 2], t1.z, s1); s1 = fmaf(qs[4 * i + 3], t1.w, s1);
-          dp1 = fmaf(go[4 * i], u1.x, dp1); dp1 = fmaf(go[4 * i + 1], u1.y, dp1); dp1 = fmaf(go[4 * i + 2], u1.z, dp1); dp1 = fmaf(go[4 * i + 3], u1.w, dp1);
-        }
-        const float p0 = bit0 ? exp2f(s0 - lse) : 0.f, p1 = bit1 ? exp2f(s1 - lse) : 0.f;
-        const float ds0 = p0 * (dp0 - D), ds1 = p1 * (dp1 - D);  // gradients of the natural-log-domain scores q . k / 4
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 t = kp0[i], t1 = kp1[i];
-          gq[4 * i] = fmaf(ds0, t.x, gq[4 * i]); gq[4 * i + 1] = fmaf(ds0, t.y, gq[4 * i + 1]);
-          gq[4 * i + 2] = fmaf(ds0, t.z, gq[4 * i + 2]); gq[4 * i + 3] = fmaf(ds0, t.w, gq[4 * i + 3]);
-          gq[4 * i] = fmaf(ds1, t1.x, gq[4 * i]); gq[4 * i + 1] = fmaf(ds1, t1.y, gq[4 * i + 1]);
-          gq[4 * i + 2] = fmaf(ds1, t1.z, gq[4 * i + 2]); gq[4 * i + 3] = fmaf(ds1, t1.w, gq[4 * i + 3]);
-        }
-        float* pb = pw + buf * 64;
-        float* db = dw + buf * 64;
-        pb[lane] = p0; pb[32 + lane] = p1;
-        db[lane] = ds0; db[32 + lane] = ds1;
-        __syncwarp();
-        // sums over the 32 rows: lanes 0-15 finish dV[j][d], lanes 16-31 dK[j][d]
-        float av0 = 0.f, ak0 = 0.f, av1 = 0.f, ak1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 t = reinterpret_cast<const float4*>(pb + half * 16)[i], u = reinterpret_cast<const float4*>(db + half * 16)[i];
-          const float4 t1 = reinterpret_cast<const float4*>(pb + 32 + half * 16)[i], u1 = reinterpret_cast<const float4*>(db + 32 + half * 16)[i];
-          av0 = fmaf(t.x, cdo[4 * i], av0); av0 = fmaf(t.y, cdo[4 * i + 1], av0); av0 = fmaf(t.z, cdo[4 * i + 2], av0); av0 = fmaf(t.w, cdo[4 * i + 3], av0);
-          ak0 = fmaf(u.x, cq[4 * i], ak0); ak0 = fmaf(u.y, cq[4 * i + 1], ak0); ak0 = fmaf(u.z, cq[4 * i + 2], ak0); ak0 = fmaf(u.w, cq[4 * i + 3], ak0);
-          av1 = fmaf(t1.x, cdo[4 * i], av1); av1 = fmaf(t1.y, cdo[4 * i + 1], av1); av1 = fmaf(t1.z, cdo[4 * i + 2], av1); av1 = fmaf(t1.w, cdo[4 * i + 3], av1);
-          ak1 = fmaf(u1.x, cq[4 * i], ak1); ak1 = fmaf(u1.y, cq[4 * i + 1], ak1); ak1 = fmaf(u1.z, cq[4 * i + 2], ak1); ak1 = fmaf(u1.w, cq[4 * i + 3], ak1);
-        }
-        av0 += __shfl_xor_sync(0xffffffffu, av0, 16);
-        ak0 += __shfl_xor_sync(0xffffffffu, ak0, 16);
-        av1 += __shfl_xor_sync(0xffffffffu, av1, 16);
-        ak1 += __shfl_xor_sync(0xffffffffu, ak1, 16);
-        float* acc = (half == 0 ? dVs : dKs) + h * 16 + d;
-        acc[j0 * kE] += half == 0 ? av0 : ak0;
-        if (jj + 1 < jn) acc[j1 * kE] += half == 0 ? av1 : ak1;
-        buf ^= 1;
+      for (int i = 0; i < 4; ++i) {
+        const int64_t r = g0 + ks * 8 + t + (i >> 1) * 4;       // a0: (g, t)  a1: (g + 8, t)  a2: (g, t + 4)  a3: (g + 8, t + 4)
+        const int col = h * 16 + g + (i & 1) * 8;
+        const bool ok = r < row_hi;
+        ado[ks][i] = ok ? __ldg(d_out + r * kE + col) : 0.f;
+        aq[ks][i] = ok ? __ldg(q + r * kE + col) * 0.25f : 0.f;
       }
+    const uint32_t w0 = mb[lane * kMbStride], w1 = mb[lane * kMbStride + 1], w2 = mb[lane * kMbStride + 2], w3 = mb[lane * kMbStride + 3];
+#pragma unroll 1
+    for (int j0 = 0; j0 < N; j0 += 8) {
+      const uint32_t word = (j0 >> 5) == 0 ? w0 : (j0 >> 5) == 1 ? w1 : (j0 >> 5) == 2 ? w2 : w3;
+      const uint32_t bits8 = (word >> (j0 & 31)) & 0xffu;   // keys beyond N have no bits
+      if (!__any_sync(0xffffffffu, bits8 != 0u)) continue;
+      // ---- phase 1: p and ds of 8 keys for this lane's row; dq in registers ----
+#pragma unroll 2
+      for (int kk = 0; kk < 8; ++kk) {
+        const int j = min(j0 + kk, N - 1);
+        const bool bit = (bits8 >> kk) & 1u;
+        const float4* kp = reinterpret_cast<const float4*>(Ks + j * kE + h * 16);
+        const float4* vp = reinterpret_cast<const float4*>(Vs + j * kE + h * 16);
+        float kr[16];
+        float sp[4], dpp[4];   // four independent partial sums each: the kernel runs two warps per scheduler, a 16-long FMA chain stalls it
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = kp[i], u = vp[i];
+          kr[4 * i] = a.x; kr[4 * i + 1] = a.y; kr[4 * i + 2] = a.z; kr[4 * i + 3] = a.w;
+          sp[i] = fmaf(qs[4 * i + 3], a.w, fmaf(qs[4 * i + 2], a.z, fmaf(qs[4 * i + 1], a.y, qs[4 * i] * a.x)));
+          dpp[i] = fmaf(go[4 * i + 3], u.w, fmaf(go[4 * i + 2], u.z, fmaf(go[4 * i + 1], u.y, go[4 * i] * u.x)));
+        }
+        const float s = (sp[0] + sp[1]) + (sp[2] + sp[3]), dp = (dpp[0] + dpp[1]) + (dpp[2] + dpp[3]);
+        const float p = bit ? exp2f(s - lse) : 0.f;
+        const float ds = p * (dp - D);  // gradient of the natural-log-domain score q . k / 4
+#pragma unroll
+        for (int i = 0; i < 16; ++i) gq[i] = fmaf(ds, kr[i], gq[i]);
+        pw[kk * kPsStride + lane] = p;
+        dw[kk * kPsStride + lane] = ds;
+      }
+      __syncwarp();
+      // ---- phase 2: C[column d][key] += A[d][row] B[row][key] over the 32 rows, for dV (A = dO^T, B = p) and dK (A = q^T / 4, B = ds) ----
+      float cvp[4][4], ckp[4][4];   // one accumulator per K step: four independent MMA chains of three instead of one of twelve
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cvp[ks][i] = ckp[ks][i] = 0.f;
+        uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(ado[ks][i], ah[i], al[i]);
+        split_tf32(pw[g * kPsStride + ks * 8 + t], bh[0], bl[0]);
+        split_tf32(pw[g * kPsStride + ks * 8 + t + 4], bh[1], bl[1]);
+        mma_x<3>(cvp[ks], ah, al, bh, bl);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(aq[ks][i], ah[i], al[i]);
+        split_tf32(dw[g * kPsStride + ks * 8 + t], bh[0], bl[0]);
+        split_tf32(dw[g * kPsStride + ks * 8 + t + 4], bh[1], bl[1]);
+        mma_x<3>(ckp[ks], ah, al, bh, bl);
+      }
+      float cv[4], ck[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cv[i] = (cvp[0][i] + cvp[1][i]) + (cvp[2][i] + cvp[3][i]);
+        ck[i] = (ckp[0][i] + ckp[1][i]) + (ckp[2][i] + ckp[3][i]);
+      }
+      // c0: (d = g, key 2t)  c1: (g, 2t + 1)  c2: (g + 8, 2t)  c3: (g + 8, 2t + 1); this warp owns the head's 16 columns
+      {
+        const int ja = j0 + 2 * t, col = h * 16 + g;
+        if (ja < N) {
+          dVs[ja * kAccStride + col] += cv[0]; dVs[ja * kAccStride + col + 8] += cv[2];
+          dKs[ja * kAccStride + col] += ck[0]; dKs[ja * kAccStride + col + 8] += ck[2];
+        }
+        if (ja + 1 < N) {
+          dVs[(ja + 1) * kAccStride + col] += cv[1]; dVs[(ja + 1) * kAccStride + col + 8] += cv[3];
+          dKs[(ja + 1) * kAccStride + col] += ck[1]; dKs[(ja + 1) * kAccStride + col + 8] += ck[3];
+        }
+      }
+      __syncwarp();   // the next block of keys overwrites the hand-over tiles
     }
     if (valid) {
       float4* dst = reinterpret_cast<float4*>(dq + row * kE + h * 16);
@@ -272,8 +303,9 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int 
   float* gk = dk + b * N * kE;
   float* gv = dv + b * N * kE;
   for (int i = tid; i < N * kE; i += kAtThreads) {
-    atomicAdd(gk + i, dKs[i]);
-    atomicAdd(gv + i, dVs[i]);
+    const int j = i >> 7, c = i & 127;
+    atomicAdd(gk + i, dKs[j * kAccStride + c]);
+    atomicAdd(gv + i, dVs[j * kAccStride + c]);
   }
 }
 
@@ -324,8 +356,9 @@ int rrnco_train_attention_bwd(int64_t n_inst, int64_t rows_per_inst, int32_t n_n
   RRNCO_CHECK_ARG(n_inst > 0 && rows_per_inst > 0 && n_nodes > 0 && q && k && v && mask && out && lse && d_out && dq && dk && dv);
   RRNCO_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                     reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(dq)) & 15u) == 0);
-  const size_t smem = (size_t)4 * n_nodes * kE * sizeof(float) + 2 * 8 * 2 * 64 * sizeof(float) + kAtGroup * kMbStride * sizeof(uint32_t);
-  if (smem > 227 * 1024 || n_inst > 65535) return RRNCO_ERR_UNSUPPORTED;  // n_nodes <= 108
+  const size_t smem = ((size_t)2 * n_nodes * kE + (size_t)2 * n_nodes * kAccStride + 2 * 8 * 8 * kPsStride) * sizeof(float) +
+                      kAtGroup * kMbStride * sizeof(uint32_t);
+  if (smem > 227 * 1024 || n_inst > 65535) return RRNCO_ERR_UNSUPPORTED;  // n_nodes <= 102
   static PerDeviceOnce once;
   if (once.first()) {
     if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {

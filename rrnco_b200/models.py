@@ -341,9 +341,8 @@ class RRNetPolicy(nn.Module):
         if phase == "train" and torch.is_grad_enabled() and multistart and actions is None:
             # rl.py:119-128 differentiates out["log_likelihood"]: the kernel's value carries no graph, so the sampled
             # actions are re-evaluated by the differentiable batched replay (training.py), same encoder output
-            from .training import batched_logprobs, collect_decode_inputs
-            with torch.no_grad():
-                inputs = collect_decode_inputs(self.decoder, env, td, out["actions"], S)
+            from .training import batched_logprobs, iter_decode_inputs
+            inputs = iter_decode_inputs(self.decoder, env, td, out["actions"], S)   # generator: replay overlaps the kernels
             logp = batched_logprobs(self.decoder, row_emb.float(), col_emb.float(), td["distance_matrix"].float(),
                                     td["duration_matrix"].float() if self.env_name == "rcvrptw" else None, inputs,
                                     out["actions"], S, temperature, tanh_clipping,

@@ -18,7 +18,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librrnco_b200_train.so")
-MAX_NODES_ATTENTION = 108   # K, V, dK, dV tiles of one instance in shared memory (rrnco_train_attention_bwd)
+MAX_NODES_ATTENTION = 102   # K, V, dK, dV tiles of one instance in shared memory (rrnco_train_attention_bwd)
 DEV_NAN_LOGITS = 1
 
 _f = C.c_void_p

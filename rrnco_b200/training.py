@@ -33,36 +33,49 @@ ATTENTION_IMPL = "sdpa"  # "sdpa" | "matmul": how the ATen form of batched_logpr
 REPLAY_IMPL = "fused"   # "fused" | "aten"
 
 
-def collect_decode_inputs(decoder, env, td, actions: torch.Tensor, num_starts: int) -> dict:
-    """Replays `actions` [R, T] (R = num_starts * n_inst, multistart order) through the env's CUDA step kernels and
-    records, for every decoder call (steps 1..T-1; step 0 is the forced POMO start, decoding.py:186-192), what the
-    decoder saw: current_node [T-1, R], first_node (atsp), ctx_state [T-1, R, k], action_mask [T-1, R, N]."""
+def iter_decode_inputs(decoder, env, td, actions: torch.Tensor, num_starts: int, step_chunk: int = 32):
+    """Replays `actions` [R, T] (R = num_starts * n_inst, multistart order) through the env's CUDA step kernels and yields, per
+    chunk of `step_chunk` decoder calls, `(t0, t1, inputs)` with what the decoder saw at steps t0+1 .. t1 (step 0 is the forced
+    POMO start, decoding.py:186-192): current_node [t1-t0, R], first_node (atsp), ctx_state [t1-t0, R, k], action_mask
+    [t1-t0, R, N].  A generator: the replay is launch-bound (one small kernel per step), so `batched_logprobs` consumes the chunks
+    as they appear and its kernels run on the GPU while the host issues the next steps."""
     from .models import _ROLLOUT_STATE_KEYS
     name = decoder.env_name
     S = int(num_starts)
     if S < 2:
         raise NotImplementedError("training replay is multistart (POMO) only, as rl.py:119 asserts")
     R, T = actions.shape
-    roll = TensorDictLite({k: (batchify(td[k], S) if k in _ROLLOUT_STATE_KEYS[name] else td[k])
-                           for k in td.keys() if k != "done"}, batch_size=[R])
-    roll.set("action", actions[:, 0].contiguous())
-    roll = env.step(roll)["next"]
-    cur, first, state, mask = [], [], [], []
-    for t in range(1, T):
-        cur.append(roll["current_node"].reshape(-1).clone())
-        mask.append(roll["action_mask"].clone())
-        if name == "atsp":
-            first.append(roll["first_node"].reshape(-1).clone())
-        else:
-            state.append(decoder._ctx_state(roll).clone())
-        roll.set("action", actions[:, t].contiguous())
+    with torch.no_grad():
+        roll = TensorDictLite({k: (batchify(td[k], S) if k in _ROLLOUT_STATE_KEYS[name] else td[k])
+                               for k in td.keys() if k != "done"}, batch_size=[R])
+        roll.set("action", actions[:, 0].contiguous())
         roll = env.step(roll)["next"]
-    out = {"current_node": torch.stack(cur), "action_mask": torch.stack(mask)}
-    if name == "atsp":
-        out["first_node"] = torch.stack(first)
-    else:
-        out["ctx_state"] = torch.stack(state)
-    return out
+    for t0 in range(0, T - 1, step_chunk):
+        t1 = min(T - 1, t0 + step_chunk)
+        cur, first, state, mask = [], [], [], []
+        with torch.no_grad():   # not held across the yield: the consumer builds its graph in between
+            for t in range(t0 + 1, t1 + 1):
+                cur.append(roll["current_node"].reshape(-1).clone())
+                mask.append(roll["action_mask"].clone())
+                if name == "atsp":
+                    first.append(roll["first_node"].reshape(-1).clone())
+                else:
+                    state.append(decoder._ctx_state(roll).clone())
+                roll.set("action", actions[:, t].contiguous())
+                roll = env.step(roll)["next"]
+            out = {"current_node": torch.stack(cur), "action_mask": torch.stack(mask)}
+            if name == "atsp":
+                out["first_node"] = torch.stack(first)
+            else:
+                out["ctx_state"] = torch.stack(state)
+        yield t0, t1, out
+
+
+def collect_decode_inputs(decoder, env, td, actions: torch.Tensor, num_starts: int) -> dict:
+    """All chunks of `iter_decode_inputs` at once: current_node [T-1, R], first_node (atsp), ctx_state [T-1, R, k],
+    action_mask [T-1, R, N]."""
+    chunks = [c for _, _, c in iter_decode_inputs(decoder, env, td, actions, num_starts)]
+    return {k: torch.cat([c[k] for c in chunks]) for k in chunks[0]}
 
 
 def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict, actions: torch.Tensor,
@@ -80,7 +93,16 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
     n_inst, N, _ = col_emb.shape
     S = int(num_starts)
     R = S * n_inst
-    Tm = inputs["current_node"].shape[0]
+    Tm = actions.shape[1] - 1
+
+    def chunks():  # `inputs`: the dict of collect_decode_inputs, or the generator iter_decode_inputs (consumed as it is produced)
+        if isinstance(inputs, dict):
+            for a in range(0, Tm, step_chunk):
+                b = min(Tm, a + step_chunk)
+                yield a, b, {key: val[a:b] for key, val in inputs.items()}
+        else:
+            yield from inputs
+
     fused = col_emb.is_cuda and REPLAY_IMPL == "fused" and not torch.is_autocast_enabled()
     if fused:
         from . import train_ops
@@ -99,23 +121,22 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
         tab_a = F.linear(row_emb, W[:, :E])
         tab_b = F.linear(row_emb, W[:, E:2 * E]) if name == "atsp" else None
     out = []
-    for t0 in range(0, Tm, step_chunk):
-        t1 = min(Tm, t0 + step_chunk)
+    for t0, t1, chunk in chunks():
         L = (t1 - t0) * S
 
         def per_inst(x):  # [Tc, R, ...] with r = s * n_inst + b  ->  [n_inst, Tc * S, ...]
             return x.unflatten(1, (S, n_inst)).movedim(2, 0).flatten(1, 2)
 
-        cur = per_inst(inputs["current_node"][t0:t1])                      # [n_inst, L]
-        mask = per_inst(inputs["action_mask"][t0:t1]).bool()               # [n_inst, L, N]
+        cur = per_inst(chunk["current_node"])                      # [n_inst, L]
+        mask = per_inst(chunk["action_mask"]).bool()               # [n_inst, L, N]
         act = per_inst(actions[:, 1 + t0:1 + t1].t().contiguous())         # [n_inst, L]
         if fused:   # context.py:18-70 with the projection pulled through the gather: q = P[b, cur] (+ P2[b, ..]) + state W_s^T
             from . import train_ops
             cur, mask, act = cur.contiguous(), mask.contiguous(), act.contiguous()    # per_inst returns strided views
             if name == "atsp":
-                q = train_ops.context_query(tab_a, per_inst(inputs["first_node"][t0:t1]), tab_b, cur)
+                q = train_ops.context_query(tab_a, per_inst(chunk["first_node"]), tab_b, cur)
             else:
-                q = train_ops.context_query(tab_a, cur, None, None, per_inst(inputs["ctx_state"][t0:t1]), W[:, E:].t())
+                q = train_ops.context_query(tab_a, cur, None, None, per_inst(chunk["ctx_state"]), W[:, E:].t())
             g = train_ops.fused_attention(q, k, v, mask, add_residual=True)             # decoder.py:281-293 (+ q)
             g = train_ops.fused_ffn(g, w1, b1, w2, b2)                                  # decoder.py:296
             z = torch.bmm(g, lk.transpose(1, 2))                                        # raw pointer scores [n_inst, L, N]
@@ -126,10 +147,10 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
             continue
         emb_cur = row_emb[inst[:, None], cur]                              # [n_inst, L, E]
         if name == "atsp":  # rl4co TSPContext: [first, current] (multistart: never the placeholder)
-            first = per_inst(inputs["first_node"][t0:t1])
+            first = per_inst(chunk["first_node"])
             ctx = torch.cat([row_emb[inst[:, None], first], emb_cur], -1)
         else:               # context.py:18-31: [current-node embedding, state scalars]
-            ctx = torch.cat([emb_cur, per_inst(inputs["ctx_state"][t0:t1]).to(emb_cur.dtype)], -1)
+            ctx = torch.cat([emb_cur, per_inst(chunk["ctx_state"]).to(emb_cur.dtype)], -1)
         q = F.linear(ctx, W)                                               # [n_inst, L, E]
         if ATTENTION_IMPL == "sdpa":
             h = F.scaled_dot_product_attention(heads(q), kh, vh, attn_mask=mask.unsqueeze(1))  # decoder.py:281-293
@@ -158,8 +179,7 @@ def replay_log_likelihood(policy, td, env, actions: torch.Tensor, num_starts: in
     """log_likelihood [R] of `actions` with a graph to the decoder parameters and the encoder (policy.py:240-243 for the
     Evaluate strategy, decoding.py:386-399).  `td` is the reset td of the batch the actions were sampled on."""
     row_emb, col_emb = embeddings if embeddings is not None else policy.encoder(td, phase=phase)
-    with torch.no_grad():
-        inputs = collect_decode_inputs(policy.decoder, env, td, actions, num_starts)
+    inputs = iter_decode_inputs(policy.decoder, env, td, actions, num_starts, step_chunk)   # consumed chunk by chunk below
     dur = td["duration_matrix"].float() if policy.decoder.env_name == "rcvrptw" else None
     logp = batched_logprobs(policy.decoder, row_emb.float(), col_emb.float(), td["distance_matrix"].float(), dur, inputs,
                             actions, num_starts, policy.temperature if temperature is None else temperature,

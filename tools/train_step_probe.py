@@ -48,8 +48,11 @@ for it in range(int(os.environ.get("ITERS", 5))):
     with torch.no_grad():
         out = pol(td, env, phase="train", decode_type="multistart_sampling", num_starts=S)
     t1 = sync_time()
-    with torch.no_grad():
-        inputs = rb.collect_decode_inputs(pol.decoder, env, td, out["actions"], S)
+    if os.environ.get("SPLIT"):   # separate timings of the env replay and the forward pass (a host sync in between)
+        with torch.no_grad():
+            inputs = rb.collect_decode_inputs(pol.decoder, env, td, out["actions"], S)
+    else:                         # product form: the replay generator is consumed chunk by chunk, kernels overlap the host loop
+        inputs = rb.iter_decode_inputs(pol.decoder, env, td, out["actions"], S)
     t2 = sync_time()
     logp = rb.batched_logprobs(pol.decoder, row, col, td["distance_matrix"].float(), None, inputs, out["actions"], S,
                               autocast_dtype=ac)
