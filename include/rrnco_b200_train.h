@@ -14,6 +14,7 @@
  *   rrnco_train_attention   masked 8-head attention of one query row per (rollout, step) over the instance's keys
  *                           (decoder.py:281-293), forward and backward
  *   rrnco_train_context_query  the context projection as a table gather + rank-k update (context.py:18-70), forward / backward
+ *   rrnco_train_inst_gemm / _xty  the pointer scores g . Lk^T and their gradients, one weight tile per instance (decoder.py:298-301)
  *   rrnco_train_logits_tail edge bias, log(exp(.) + 1e-6), tanh clip, mask, temperature, log-softmax and the log-prob of
  *                           the given action with its Jacobian, in one pass (decoder.py:183-198, decoding.py:311-399)
  *
@@ -70,11 +71,12 @@ int rrnco_train_attention_bwd(int64_t n_inst, int64_t rows_per_inst, int32_t n_n
 
 /* Tail of the pointer for the batched replay (decoder.py:183-198 edge bias + log(exp(.) + 1e-6); decoding.py:311-361 tanh clip,
  * mask, temperature; :386-399 log-prob of the given action), one pass:
- *   z [rows, n_nodes] (in / out): raw pointer scores g . Lk^T on entry, J = d logp / d z on return (backward: dz = g_row J)
+ *   z [rows, ldz] (in / out; row stride ldz >= n_nodes, <= 128): raw pointer scores g . Lk^T on entry, J = d logp / d z on return
+ *   (backward: dz = g_row J; padding columns are zeroed)
  *   distance / duration [n_inst, n_nodes, n_nodes] (duration NULL except rcvrptw), instance of a row = row / rows_per_inst
  *   current_node / action [rows] int64, mask [rows, n_nodes] bytes, alpha / beta device scalars (decoder.alpha / .beta)
  *   logp [rows] = log pi(action | state);  dlogp_dalpha / dlogp_dbeta [rows] (beta: NULL without duration);  n_nodes <= 128 */
-int rrnco_train_logits_tail(int64_t rows, int64_t rows_per_inst, int32_t n_nodes, float* z, const float* distance,
+int rrnco_train_logits_tail(int64_t rows, int64_t rows_per_inst, int32_t n_nodes, int32_t ldz, float* z, const float* distance,
                             const float* duration, const int64_t* current_node, const uint8_t* mask, const int64_t* action,
                             const float* alpha, const float* beta, float inv_sqrt_e, float tanh_clipping, float temperature,
                             float* logp, float* dlogp_dalpha, float* dlogp_dbeta, void* stream);
@@ -90,6 +92,19 @@ int rrnco_train_context_query_fwd(int64_t rows, int64_t rows_per_inst, int32_t n
 int rrnco_train_context_query_bwd(int64_t rows, int64_t rows_per_inst, int32_t n_nodes, const float* dq, const int64_t* index_a,
                                   const int64_t* index_b, const float* state, int32_t n_state, float* d_table_a, float* d_table_b,
                                   float* d_state_w, void* stream);
+
+/* Pointer scores (decoder.py:298-301) on tcgen05, one zero-padded 128 x 128 weight tile per instance:
+ *   rrnco_train_inst_pack   w [n_inst, n_nodes, 128] -> packed (rrnco_train_inst_packed_bytes(n_inst) bytes); transpose == 0 packs
+ *                           B[node][e] (z = g w^T), transpose == 1 packs B[e][node] (dg = dz w); |w| < 4094
+ *   rrnco_train_inst_gemm   y [n_inst L, 128] = x [n_inst L, 128] B_b   (a_scale: optional device power of two for gradient operands)
+ *   rrnco_train_inst_xty    c [n_inst, n_nodes, 128] += x_b^T y_b over the rows of instance b (x, y [n_inst L, 128]; fp32 atomics) */
+int64_t rrnco_train_inst_packed_bytes(int64_t n_inst);
+int rrnco_train_inst_pack(int64_t n_inst, int32_t n_nodes, const float* w, int32_t transpose, void* packed, uint32_t* status,
+                          void* stream);
+int rrnco_train_inst_gemm(int64_t n_inst, int64_t rows_per_inst, const float* x, const void* packed, const float* a_scale, float* y,
+                          uint32_t* status, void* stream);
+int rrnco_train_inst_xty(int64_t n_inst, int64_t rows_per_inst, int32_t n_nodes, const float* x, const float* y, const float* sx,
+                         const float* sy, float* c, uint32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) logits_tail_kernel(int64_t rows, int64_t L, int N, float* __restrict__ z,
+__global__ void __launch_bounds__(256) logits_tail_kernel(int64_t rows, int64_t L, int N, int ldz, float* __restrict__ z,
                                                          const float* __restrict__ dist, const float* __restrict__ dur,
                                                          const int64_t* __restrict__ cur, const uint8_t* __restrict__ mask,
                                                          const int64_t* __restrict__ act, const float* __restrict__ alpha_p,
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) logits_tail_kernel(int64_t rows, int64_t 
     const int a = (int)__ldg(act + row);
     const float* drow = dist + (b * N + c) * N;
     const float* urow = dur != nullptr ? dur + (b * N + c) * N : nullptr;
-    float* zrow = z + row * N;
+    float* zrow = z + row * ldz;
     const uint8_t* mrow = mask + row * N;
     float lj[4], dj[4], uj[4], fac[4];  // clipped logit / T, distance, duration, d l / d x
     float mx = -INFINITY;
@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(256) logits_tail_kernel(int64_t rows, int64_t 
         zrow[j] = dx * inv_sqrt_e;
         sa = fmaf(-dx, dj[i], sa);
         sb = fmaf(-dx, uj[i], sb);
+      } else if (j < ldz) {
+        zrow[j] = 0.f;   // padding columns of a 128-wide score row
       }
     }
     sa = warp_sum(sa);
@@ -99,7 +101,7 @@ using namespace rrnco;
 
 extern "C" {
 
-int rrnco_train_logits_tail(int64_t rows, int64_t rows_per_inst, int32_t n_nodes, float* z, const float* distance,
+int rrnco_train_logits_tail(int64_t rows, int64_t rows_per_inst, int32_t n_nodes, int32_t ldz, float* z, const float* distance,
                             const float* duration, const int64_t* current_node, const uint8_t* mask, const int64_t* action,
                             const float* alpha, const float* beta, float inv_sqrt_e, float tanh_clipping, float temperature,
                             float* logp, float* dlogp_dalpha, float* dlogp_dbeta, void* stream) {
@@ -107,11 +109,12 @@ int rrnco_train_logits_tail(int64_t rows, int64_t rows_per_inst, int32_t n_nodes
   RRNCO_CHECK_ARG(rows > 0 && rows_per_inst > 0 && n_nodes > 0 && z && distance && current_node && mask && action && alpha && logp &&
                   dlogp_dalpha && temperature > 0.f);
   RRNCO_CHECK_ARG(duration == nullptr || (beta != nullptr && dlogp_dbeta != nullptr));
-  if (n_nodes > 128) return RRNCO_ERR_UNSUPPORTED;
+  RRNCO_CHECK_ARG(ldz >= n_nodes);
+  if (n_nodes > 128 || ldz > 128) return RRNCO_ERR_UNSUPPORTED;
   const int sms = device_sm_count();
   int64_t grid = (rows + 7) / 8;
   if (grid > 16LL * sms) grid = 16LL * sms;
-  logits_tail_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(rows, rows_per_inst, n_nodes, z, distance, duration, current_node,
+  logits_tail_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(rows, rows_per_inst, n_nodes, ldz, z, distance, duration, current_node,
                                                                     mask, action, alpha, beta, inv_sqrt_e, tanh_clipping,
                                                                     1.0f / temperature, logp, dlogp_dalpha, dlogp_dbeta);
   return rrnco_launch_status();

@@ -31,8 +31,12 @@ _SIGNATURES = {
     "rrnco_train_attention_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, C.c_int32, _f, _f, _f, _f, _f, _f]),
     "rrnco_train_context_query_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, C.c_int32, _f, _f, _f]),
     "rrnco_train_context_query_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, C.c_int32, _f, _f, _f, _f]),
-    "rrnco_train_logits_tail": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, _f, _f, _f, C.c_float, C.c_float,
+    "rrnco_train_logits_tail": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _f, _f, _f, _f, _f, _f, _f, _f, C.c_float, C.c_float,
                                           C.c_float, _f, _f, _f, _f]),
+    "rrnco_train_inst_packed_bytes": (C.c_int64, [C.c_int64]),
+    "rrnco_train_inst_pack": (C.c_int, [C.c_int64, C.c_int32, _f, C.c_int32, _f, _f, _f]),
+    "rrnco_train_inst_gemm": (C.c_int, [C.c_int64, C.c_int64, _f, _f, _f, _f, _f, _f]),
+    "rrnco_train_inst_xty": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, _f, _f]),
 }
 _lib = None
 _status: dict = {}
@@ -96,7 +100,8 @@ def check_status(dev) -> None:
 
 def pow2_scale(t: torch.Tensor, bound_factor=None, target: float = 512.0) -> torch.Tensor:
     """Device scalar 2^k with max|t| * bound_factor * 2^k in (target / 2, target]: the pre-split scale of a gradient operand."""
-    amax = t.detach().abs().amax().float()
+    lo, hi = torch.aminmax(t.detach())          # one pass, nothing materialised (|t| would be a full copy)
+    amax = torch.maximum(-lo, hi).float()
     if bound_factor is not None:
         amax = amax * bound_factor
     amax = amax.clamp(1e-30, 1e30)
@@ -136,7 +141,8 @@ class _FusedFFN(torch.autograd.Function):
         h, dev, st = lib(), x.device, status_word(x.device)
         rows = x.shape[0]
         dy = dy.contiguous().float()
-        amax = dy.abs().amax()
+        lo, hi = torch.aminmax(dy)
+        amax = torch.maximum(-lo, hi)
         s_dy = pow2_scale(amax)
         # |dhidden_j| <= max|dy| * sum_e |W2[e, j]|: a rigorous bound without a pass over the [rows, 512] tensor
         s_dh = pow2_scale(amax, bound_factor=w2.abs().sum(0).amax().clamp_min(1.0))
@@ -240,11 +246,49 @@ def context_query(table_a, index_a, table_b=None, index_b=None, state=None, stat
     return _ContextQuery.apply(table_a, index_a, table_b, index_b, state, state_w)
 
 
+class _PointerScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, lk):
+        h, dev, st = lib(), g.device, status_word(g.device)
+        g, lk = g.detach().contiguous().float(), lk.detach().contiguous().float()
+        n_inst, L, _ = g.shape
+        N = lk.shape[1]
+        packed = torch.empty(h.rrnco_train_inst_packed_bytes(n_inst), dtype=torch.uint8, device=dev)
+        _check(h.rrnco_train_inst_pack(n_inst, N, _p(lk), 0, _p(packed), _p(st), _stream(dev)), "rrnco_train_inst_pack")
+        z = torch.empty(n_inst, L, 128, dtype=torch.float32, device=dev)
+        _check(h.rrnco_train_inst_gemm(n_inst, L, _p(g), _p(packed), None, _p(z), _p(st), _stream(dev)), "rrnco_train_inst_gemm")
+        ctx.save_for_backward(g, lk)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        g, lk = ctx.saved_tensors
+        h, dev, st = lib(), g.device, status_word(g.device)
+        n_inst, L, _ = g.shape
+        N = lk.shape[1]
+        dz = dz.contiguous().float()
+        s_dz = pow2_scale(dz)
+        packed = torch.empty(h.rrnco_train_inst_packed_bytes(n_inst), dtype=torch.uint8, device=dev)
+        _check(h.rrnco_train_inst_pack(n_inst, N, _p(lk), 1, _p(packed), _p(st), _stream(dev)), "rrnco_train_inst_pack")
+        dg = torch.empty_like(g)
+        _check(h.rrnco_train_inst_gemm(n_inst, L, _p(dz), _p(packed), _p(s_dz), _p(dg), _p(st), _stream(dev)), "rrnco_train_inst_gemm (dg)")
+        dlk = torch.zeros_like(lk)
+        _check(h.rrnco_train_inst_xty(n_inst, L, N, _p(dz), _p(g), _p(s_dz), None, _p(dlk), _p(st), _stream(dev)), "rrnco_train_inst_xty")
+        return dg, dlk
+
+
+def pointer_scores(g, lk):
+    """z [n_inst, L, 128] = g lk^T (columns >= N are zero): g [n_inst, L, 128], lk [n_inst, N <= 128, 128]; forward, dg and dlk on
+    tcgen05 in the fp32-faithful fp16 hi|lo split (decoder.py:298-301 without the 1 / sqrt(E), which the tail applies)."""
+    return _PointerScores.apply(g, lk)
+
+
 class _LogitsTail(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature):
         h, dev = lib(), z.device
-        n_inst, L, N = z.shape
+        n_inst, L, ldz = z.shape      # ldz >= N: the 128-wide rows of pointer_scores, or exactly N
+        N = distance.shape[-1]
         jac = z.detach()
         if not jac.is_contiguous() or jac.dtype != torch.float32:
             jac = jac.contiguous().float()
@@ -258,7 +302,7 @@ class _LogitsTail(torch.autograd.Function):
         distance, cur, act = distance.contiguous(), cur.contiguous(), act.contiguous()
         duration = duration.contiguous() if duration is not None else None
         m8 = mask.contiguous().view(torch.uint8)
-        _check(h.rrnco_train_logits_tail(rows, L, N, _p(jac), _p(distance), _p(duration), _p(cur), _p(m8), _p(act), _p(alpha_d), _p(beta_d),
+        _check(h.rrnco_train_logits_tail(rows, L, N, ldz, _p(jac), _p(distance), _p(duration), _p(cur), _p(m8), _p(act), _p(alpha_d), _p(beta_d),
                                          1.0 / math.sqrt(128.0), float(tanh_clipping), float(temperature), _p(logp), _p(da), _p(db),
                                          _stream(dev)), "rrnco_train_logits_tail")
         ctx.save_for_backward(jac, da, db)

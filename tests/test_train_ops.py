@@ -21,7 +21,7 @@ def test_train_header_symbols_exported():
     header = open(os.path.join(ROOT, "include", "rrnco_b200_train.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     declared = set(re.findall(r"\b(rrnco_[a-z_0-9]+)\s*\(", header))
-    assert {"rrnco_train_ffn", "rrnco_train_xty", "rrnco_train_attention_bwd", "rrnco_train_logits_tail", "rrnco_train_context_query_bwd"} <= declared
+    assert {"rrnco_train_ffn", "rrnco_train_xty", "rrnco_train_attention_bwd", "rrnco_train_logits_tail", "rrnco_train_context_query_bwd", "rrnco_train_inst_gemm"} <= declared
     handle = ctypes.CDLL(path)
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in include/rrnco_b200_train.h but not exported"
@@ -153,6 +153,28 @@ def test_fused_logits_tail_forward_backward(with_dur, clip, temp, N):
     assert abs(alpha.grad.item() - ad.grad.item()) < 2e-4 * max(1.0, abs(ad.grad.item()))
     if with_dur:
         assert abs(beta.grad.item() - bd.grad.item()) < 2e-4 * max(1.0, abs(bd.grad.item()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_inst,L,N,gscale", [(3, 300, 101, 1.0), (2, 2000, 100, 1e-7), (4, 50, 21, 1e-3), (1, 128, 128, 1.0)])
+def test_pointer_scores_forward_backward(n_inst, L, N, gscale):
+    from rrnco_b200 import train_ops
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator().manual_seed(L + N)
+    g = (torch.randn(n_inst, L, 128, generator=gen) * 3).to(dev).requires_grad_(True)
+    lk = torch.randn(n_inst, N, 128, generator=gen).to(dev).requires_grad_(True)
+    r = (torch.randn(n_inst, L, N, generator=gen) * gscale).to(dev)
+    r = r * torch.logspace(0, -3, L, device=dev)[None, :, None]
+    z = train_ops.pointer_scores(g, lk)
+    assert z.shape == (n_inst, L, 128) and (z[..., N:] == 0).all()
+    (z[..., :N] * r).sum().backward()
+    gd, ld = g.detach().double().requires_grad_(True), lk.detach().double().requires_grad_(True)
+    zd = torch.bmm(gd, ld.transpose(1, 2))
+    (zd * r.double()).sum().backward()
+    train_ops.check_status(dev)
+    assert _rel(z[..., :N].detach(), zd.detach()) < 2e-6
+    assert _rel(g.grad, gd.grad) < 5e-6
+    assert _rel(lk.grad, ld.grad) < 5e-6
 
 
 @pytest.mark.gpu
