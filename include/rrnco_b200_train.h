@@ -97,14 +97,16 @@ int rrnco_train_context_query_bwd(int64_t rows, int64_t rows_per_inst, int32_t n
  *   rrnco_train_inst_pack   w [n_inst, n_nodes, 128] -> packed (rrnco_train_inst_packed_bytes(n_inst) bytes); transpose == 0 packs
  *                           B[node][e] (z = g w^T), transpose == 1 packs B[e][node] (dg = dz w); |w| < 4094
  *   rrnco_train_inst_gemm   y [n_inst L, 128] = x [n_inst L, 128] B_b   (a_scale: optional device power of two for gradient operands)
- *   rrnco_train_inst_xty    c [n_inst, n_nodes, 128] += x_b^T y_b over the rows of instance b (x, y [n_inst L, 128]; fp32 atomics) */
+ *   rrnco_train_inst_xty    c [n_inst, n_nodes, 128] += x_b^T y_b over the rows of instance b (x, y [n_inst L, 128]; fp32 atomics)
+ *   row_scale (optional, [n_inst L]): x is used as diag(row_scale) x -- the upstream gradient of a row times the Jacobian that
+ *   rrnco_train_logits_tail left in z, without materialising the product */
 int64_t rrnco_train_inst_packed_bytes(int64_t n_inst);
 int rrnco_train_inst_pack(int64_t n_inst, int32_t n_nodes, const float* w, int32_t transpose, void* packed, uint32_t* status,
                           void* stream);
-int rrnco_train_inst_gemm(int64_t n_inst, int64_t rows_per_inst, const float* x, const void* packed, const float* a_scale, float* y,
-                          uint32_t* status, void* stream);
+int rrnco_train_inst_gemm(int64_t n_inst, int64_t rows_per_inst, const float* x, const void* packed, const float* a_scale,
+                          const float* row_scale, float* y, uint32_t* status, void* stream);
 int rrnco_train_inst_xty(int64_t n_inst, int64_t rows_per_inst, int32_t n_nodes, const float* x, const float* y, const float* sx,
-                         const float* sy, float* c, uint32_t* status, void* stream);
+                         const float* sy, const float* row_scale, float* c, uint32_t* status, void* stream);
 
 #ifdef __cplusplus
 }

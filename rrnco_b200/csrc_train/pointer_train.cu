@@ -51,7 +51,8 @@ struct InstGemmSmem {
 
 __global__ void __launch_bounds__(kPtThreads, 1) inst_gemm_kernel(int64_t L, int rows_per_cta, const float* __restrict__ X,
                                                                  const unsigned char* __restrict__ packed,
-                                                                 const float* __restrict__ a_scale_ptr, float* __restrict__ Y,
+                                                                 const float* __restrict__ a_scale_ptr,
+                                                                 const float* __restrict__ row_scale, float* __restrict__ Y,
                                                                  uint32_t* __restrict__ status) {
   extern __shared__ __align__(128) unsigned char pt_smem_raw[];
   InstGemmSmem& sm = *reinterpret_cast<InstGemmSmem*>(pt_smem_raw);
@@ -117,6 +118,11 @@ __global__ void __launch_bounds__(kPtThreads, 1) inst_gemm_kernel(int64_t L, int
         const float4* src = reinterpret_cast<const float4*>(X + (m0 + r) * kE) + c8 * 2;
         v0 = __ldg(src);
         v1 = __ldg(src + 1);
+        if (row_scale != nullptr) {  // x = diag(row_scale) X: the upstream gradient of a row times its saved Jacobian
+          const float rs = __ldg(row_scale + m0 + r);
+          v0.x *= rs; v0.y *= rs; v0.z *= rs; v0.w *= rs;
+          v1.x *= rs; v1.y *= rs; v1.z *= rs; v1.w *= rs;
+        }
       }
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))) * a_scale);
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))) * a_scale);
@@ -171,7 +177,8 @@ struct XtyInstSmem {
 
 __global__ void __launch_bounds__(kPtThreads, 2) xty_inst_kernel(int64_t L, int rows_per_cta, int N, const float* __restrict__ X,
                                                                 const float* __restrict__ Y, const float* __restrict__ sx_ptr,
-                                                                const float* __restrict__ sy_ptr, float* __restrict__ C,
+                                                                const float* __restrict__ sy_ptr,
+                                                                const float* __restrict__ row_scale, float* __restrict__ C,
                                                                 uint32_t* __restrict__ status) {
   extern __shared__ __align__(128) unsigned char pt_smem_raw[];
   XtyInstSmem& sm = *reinterpret_cast<XtyInstSmem*>(pt_smem_raw);
@@ -232,6 +239,10 @@ __global__ void __launch_bounds__(kPtThreads, 2) xty_inst_kernel(int64_t L, int 
     float xv[kXiRows];
 #pragma unroll
     for (int r = 0; r < kXiRows; ++r) xv[r] = (r0 + r < row_hi) ? __ldg(src + (r0 + r) * kE) : 0.f;
+    if (is_x && row_scale != nullptr) {
+#pragma unroll
+      for (int r = 0; r < kXiRows; ++r) xv[r] *= (r0 + r < row_hi) ? __ldg(row_scale + r0 + r) : 0.f;
+    }
     if (it >= 2) tc05::mbar_wait(&sm.bar_free[st], ((it >> 1) - 1) & 1);
     uint16_t* dh = is_x ? sm.x_hi[st] : sm.y_hi[st];
     uint16_t* dl = is_x ? sm.x_lo[st] : sm.y_lo[st];
@@ -303,8 +314,8 @@ int rrnco_train_inst_pack(int64_t n_inst, int32_t n_nodes, const float* w, int32
   return rrnco_launch_status();
 }
 
-int rrnco_train_inst_gemm(int64_t n_inst, int64_t rows_per_inst, const float* x, const void* packed, const float* a_scale, float* y,
-                          uint32_t* status, void* stream) {
+int rrnco_train_inst_gemm(int64_t n_inst, int64_t rows_per_inst, const float* x, const void* packed, const float* a_scale,
+                          const float* row_scale, float* y, uint32_t* status, void* stream) {
   if (n_inst == 0 || rows_per_inst == 0) return RRNCO_OK;
   RRNCO_CHECK_ARG(n_inst > 0 && rows_per_inst > 0 && x && packed && y && status);
   RRNCO_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0);
@@ -319,12 +330,12 @@ int rrnco_train_inst_gemm(int64_t n_inst, int64_t rows_per_inst, const float* x,
   int per = 1;
   const int rows = pt_rows_per_cta(rows_per_inst, n_inst, &per);
   inst_gemm_kernel<<<dim3((unsigned)per, (unsigned)n_inst), kPtThreads, sizeof(InstGemmSmem), (cudaStream_t)stream>>>(
-      rows_per_inst, rows, x, reinterpret_cast<const unsigned char*>(packed), a_scale, y, status);
+      rows_per_inst, rows, x, reinterpret_cast<const unsigned char*>(packed), a_scale, row_scale, y, status);
   return rrnco_launch_status();
 }
 
 int rrnco_train_inst_xty(int64_t n_inst, int64_t rows_per_inst, int32_t n_nodes, const float* x, const float* y, const float* sx,
-                         const float* sy, float* c, uint32_t* status, void* stream) {
+                         const float* sy, const float* row_scale, float* c, uint32_t* status, void* stream) {
   if (n_inst == 0 || rows_per_inst == 0) return RRNCO_OK;
   RRNCO_CHECK_ARG(n_inst > 0 && rows_per_inst > 0 && n_nodes > 0 && x && y && c && status);
   if (n_nodes > 128 || n_inst > 65535) return RRNCO_ERR_UNSUPPORTED;
@@ -339,7 +350,7 @@ int rrnco_train_inst_xty(int64_t n_inst, int64_t rows_per_inst, int32_t n_nodes,
   int per = 1;
   const int rows = pt_rows_per_cta(rows_per_inst, n_inst, &per);
   xty_inst_kernel<<<dim3((unsigned)per, (unsigned)n_inst), kPtThreads, sizeof(XtyInstSmem), (cudaStream_t)stream>>>(
-      rows_per_inst, rows, n_nodes, x, y, sx, sy, c, status);
+      rows_per_inst, rows, n_nodes, x, y, sx, sy, row_scale, c, status);
   return rrnco_launch_status();
 }
 

@@ -35,8 +35,8 @@ _SIGNATURES = {
                                           C.c_float, _f, _f, _f, _f]),
     "rrnco_train_inst_packed_bytes": (C.c_int64, [C.c_int64]),
     "rrnco_train_inst_pack": (C.c_int, [C.c_int64, C.c_int32, _f, C.c_int32, _f, _f, _f]),
-    "rrnco_train_inst_gemm": (C.c_int, [C.c_int64, C.c_int64, _f, _f, _f, _f, _f, _f]),
-    "rrnco_train_inst_xty": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, _f, _f]),
+    "rrnco_train_inst_gemm": (C.c_int, [C.c_int64, C.c_int64, _f, _f, _f, _f, _f, _f, _f]),
+    "rrnco_train_inst_xty": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, _f, _f, _f]),
 }
 _lib = None
 _status: dict = {}
@@ -256,7 +256,7 @@ class _PointerScores(torch.autograd.Function):
         packed = torch.empty(h.rrnco_train_inst_packed_bytes(n_inst), dtype=torch.uint8, device=dev)
         _check(h.rrnco_train_inst_pack(n_inst, N, _p(lk), 0, _p(packed), _p(st), _stream(dev)), "rrnco_train_inst_pack")
         z = torch.empty(n_inst, L, 128, dtype=torch.float32, device=dev)
-        _check(h.rrnco_train_inst_gemm(n_inst, L, _p(g), _p(packed), None, _p(z), _p(st), _stream(dev)), "rrnco_train_inst_gemm")
+        _check(h.rrnco_train_inst_gemm(n_inst, L, _p(g), _p(packed), None, None, _p(z), _p(st), _stream(dev)), "rrnco_train_inst_gemm")
         ctx.save_for_backward(g, lk)
         return z
 
@@ -271,9 +271,9 @@ class _PointerScores(torch.autograd.Function):
         packed = torch.empty(h.rrnco_train_inst_packed_bytes(n_inst), dtype=torch.uint8, device=dev)
         _check(h.rrnco_train_inst_pack(n_inst, N, _p(lk), 1, _p(packed), _p(st), _stream(dev)), "rrnco_train_inst_pack")
         dg = torch.empty_like(g)
-        _check(h.rrnco_train_inst_gemm(n_inst, L, _p(dz), _p(packed), _p(s_dz), _p(dg), _p(st), _stream(dev)), "rrnco_train_inst_gemm (dg)")
+        _check(h.rrnco_train_inst_gemm(n_inst, L, _p(dz), _p(packed), _p(s_dz), None, _p(dg), _p(st), _stream(dev)), "rrnco_train_inst_gemm (dg)")
         dlk = torch.zeros_like(lk)
-        _check(h.rrnco_train_inst_xty(n_inst, L, N, _p(dz), _p(g), _p(s_dz), None, _p(dlk), _p(st), _stream(dev)), "rrnco_train_inst_xty")
+        _check(h.rrnco_train_inst_xty(n_inst, L, N, _p(dz), _p(g), _p(s_dz), None, None, _p(dlk), _p(st), _stream(dev)), "rrnco_train_inst_xty")
         return dg, dlk
 
 
@@ -323,3 +323,61 @@ def fused_logits_tail(z, alpha, beta, distance, duration, cur, mask, act, tanh_c
     """log pi(act | state) [n_inst, L] from the raw pointer scores z = g . Lk^T [n_inst, L, N] (consumed: overwritten in place by
     the Jacobian); distance / duration [n_inst, N, N], cur / act [n_inst, L] int64, mask [n_inst, L, N] bool."""
     return _LogitsTail.apply(z, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature)
+
+
+class _PointerLogProb(torch.autograd.Function):
+    """pointer_scores + fused_logits_tail as ONE node: the backward pass feeds the saved Jacobian and the upstream gradient of
+    each row straight into the dg / dlk kernels (`row_scale`), so dz = g_row J is never written."""
+
+    @staticmethod
+    def forward(ctx, g, lk, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature):
+        h, dev, st = lib(), g.device, status_word(g.device)
+        g, lk = g.detach().contiguous().float(), lk.detach().contiguous().float()
+        n_inst, L, _ = g.shape
+        N = lk.shape[1]
+        packed = torch.empty(h.rrnco_train_inst_packed_bytes(n_inst), dtype=torch.uint8, device=dev)
+        _check(h.rrnco_train_inst_pack(n_inst, N, _p(lk), 0, _p(packed), _p(st), _stream(dev)), "rrnco_train_inst_pack")
+        jac = torch.empty(n_inst, L, 128, dtype=torch.float32, device=dev)
+        _check(h.rrnco_train_inst_gemm(n_inst, L, _p(g), _p(packed), None, None, _p(jac), _p(st), _stream(dev)), "rrnco_train_inst_gemm")
+        logp = torch.empty(n_inst, L, dtype=torch.float32, device=dev)
+        da = torch.empty(n_inst, L, dtype=torch.float32, device=dev)
+        db = torch.empty(n_inst, L, dtype=torch.float32, device=dev) if duration is not None else None
+        alpha_d = alpha.detach().reshape(-1).float().contiguous()
+        beta_d = beta.detach().reshape(-1).float().contiguous() if duration is not None else None
+        distance, cur, act = distance.contiguous(), cur.contiguous(), act.contiguous()
+        duration = duration.contiguous() if duration is not None else None
+        m8 = mask.contiguous().view(torch.uint8)
+        _check(h.rrnco_train_logits_tail(n_inst * L, L, N, 128, _p(jac), _p(distance), _p(duration), _p(cur), _p(m8), _p(act),
+                                         _p(alpha_d), _p(beta_d), 1.0 / math.sqrt(128.0), float(tanh_clipping), float(temperature),
+                                         _p(logp), _p(da), _p(db), _stream(dev)), "rrnco_train_logits_tail")
+        ctx.save_for_backward(g, lk, jac, da, db)
+        ctx.shapes = (alpha.shape, beta.shape if beta is not None else None)
+        # |J| <= clip / (T sqrt(E)) (tanh' <= 1, exp / (exp + 1e-6) <= 1, |delta - softmax| <= 1): bound of the scaled operand
+        ctx.jmax = (float(tanh_clipping) if tanh_clipping > 0 else 1.0) / (float(temperature) * math.sqrt(128.0))
+        return logp
+
+    @staticmethod
+    def backward(ctx, gl):
+        g, lk, jac, da, db = ctx.saved_tensors
+        h, dev, st = lib(), g.device, status_word(g.device)
+        n_inst, L, _ = g.shape
+        N = lk.shape[1]
+        gl = gl.contiguous().float()
+        s_dz = pow2_scale(gl, bound_factor=ctx.jmax)
+        packed = torch.empty(h.rrnco_train_inst_packed_bytes(n_inst), dtype=torch.uint8, device=dev)
+        _check(h.rrnco_train_inst_pack(n_inst, N, _p(lk), 1, _p(packed), _p(st), _stream(dev)), "rrnco_train_inst_pack")
+        dg = torch.empty_like(g)
+        _check(h.rrnco_train_inst_gemm(n_inst, L, _p(jac), _p(packed), _p(s_dz), _p(gl), _p(dg), _p(st), _stream(dev)),
+               "rrnco_train_inst_gemm (dg)")
+        dlk = torch.zeros_like(lk)
+        _check(h.rrnco_train_inst_xty(n_inst, L, N, _p(jac), _p(g), _p(s_dz), None, _p(gl), _p(dlk), _p(st), _stream(dev)),
+               "rrnco_train_inst_xty")
+        dalpha = (gl * da).sum().reshape(ctx.shapes[0])
+        dbeta = (gl * db).sum().reshape(ctx.shapes[1]) if db is not None else None
+        return dg, dlk, dalpha, dbeta, None, None, None, None, None, None, None
+
+
+def pointer_logprob(g, lk, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature):
+    """log pi(act | state) [n_inst, L] from the pointer input g [n_inst, L, 128] and the logit keys lk [n_inst, N, 128]
+    (decoder.py:183-198, 298-301; decoding.py:311-399): pointer_scores and fused_logits_tail as one autograd node."""
+    return _PointerLogProb.apply(g, lk, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature)

@@ -139,10 +139,9 @@ def batched_logprobs(decoder, row_emb, col_emb, distance, duration, inputs: dict
                 q = train_ops.context_query(tab_a, cur, None, None, per_inst(chunk["ctx_state"]), W[:, E:].t())
             g = train_ops.fused_attention(q, k, v, mask, add_residual=True)             # decoder.py:281-293 (+ q)
             g = train_ops.fused_ffn(g, w1, b1, w2, b2)                                  # decoder.py:296
-            z = train_ops.pointer_scores(g, lk)                                         # raw pointer scores, 128 wide (decoder.py:298-301)
-            logp = train_ops.fused_logits_tail(z, decoder.alpha, decoder.beta if name == "rcvrptw" else None, distance,
-                                               duration if name == "rcvrptw" else None, cur, mask, act, tanh_clipping,
-                                               temperature)                             # decoder.py:183-198, decoding.py:311-399
+            logp = train_ops.pointer_logprob(g, lk, decoder.alpha, decoder.beta if name == "rcvrptw" else None, distance,
+                                             duration if name == "rcvrptw" else None, cur, mask, act, tanh_clipping,
+                                             temperature)           # decoder.py:183-198, 298-301; decoding.py:311-399
             out.append(logp.unflatten(1, (t1 - t0, S)).permute(2, 0, 1).reshape(R, t1 - t0))
             continue
         emb_cur = row_emb[inst[:, None], cur]                              # [n_inst, L, E]

@@ -178,6 +178,40 @@ def test_pointer_scores_forward_backward(n_inst, L, N, gscale):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("with_dur,N", [(False, 101), (True, 100), (False, 30)])
+def test_pointer_logprob_forward_backward(with_dur, N):
+    """pointer_scores + logits tail as one node (the Jacobian and the row gradient go straight into the dg / dlk kernels)."""
+    from rrnco_b200 import train_ops
+    dev = torch.device("cuda", 0)
+    n_inst, L = 3, 391
+    gen = torch.Generator().manual_seed(N)
+    g = (torch.randn(n_inst, L, 128, generator=gen) * 2).to(dev).requires_grad_(True)
+    lk = (torch.randn(n_inst, N, 128, generator=gen) * 1.5).to(dev).requires_grad_(True)
+    dist = torch.rand(n_inst, N, N, generator=gen).to(dev)
+    dur = torch.rand(n_inst, N, N, generator=gen).to(dev) if with_dur else None
+    alpha = torch.tensor([0.9], device=dev, requires_grad=True)
+    beta = torch.tensor([1.2], device=dev, requires_grad=True) if with_dur else None
+    cur = torch.randint(0, N, (n_inst, L), generator=gen).to(dev)
+    mask = (torch.rand(n_inst, L, N, generator=gen) < 0.5).to(dev)
+    act = torch.randint(0, N, (n_inst, L), generator=gen).to(dev)
+    mask.scatter_(-1, act.unsqueeze(-1), True)
+    r = (torch.randn(n_inst, L, generator=gen) * 1e-5).to(dev) * torch.logspace(0, -3, L, device=dev)[None]
+    logp = train_ops.pointer_logprob(g, lk, alpha, beta, dist, dur, cur, mask, act, 10.0, 1.0)
+    (logp * r).sum().backward()
+    gd, ld = g.detach().double().requires_grad_(True), lk.detach().double().requires_grad_(True)
+    ad = alpha.detach().double().requires_grad_(True)
+    bd = beta.detach().double().requires_grad_(True) if with_dur else None
+    want = _tail_ref(torch.bmm(gd, ld.transpose(1, 2)), ad, bd, dist.double(), dur.double() if with_dur else None, cur, mask, act, 10.0, 1.0)
+    (want * r.double()).sum().backward()
+    train_ops.check_status(dev)
+    assert (logp.detach().double() - want.detach()).abs().max().item() < 5e-5
+    assert _rel(g.grad, gd.grad) < 2e-5 and _rel(lk.grad, ld.grad) < 2e-5
+    assert abs(alpha.grad.item() - ad.grad.item()) < 2e-4 * max(1e-6, abs(ad.grad.item())) + 1e-12
+    if with_dur:
+        assert abs(beta.grad.item() - bd.grad.item()) < 2e-4 * max(1e-6, abs(bd.grad.item())) + 1e-12
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("two_tables,n_state", [(False, 1), (True, 0), (False, 4)])
 def test_context_query_forward_backward(two_tables, n_state):
     from rrnco_b200 import train_ops
