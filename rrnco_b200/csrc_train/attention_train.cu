@@ -39,6 +39,9 @@ __device__ __forceinline__ void stage_mask_bits(uint32_t* mb, const uint8_t* __r
   if ((p & 1) == 0) mb[r * kMbStride + (p >> 1)] = bits | (other << 16);
 }
 
+// Forward: two rows per lane (rows g0 + lane and g0 + 32 + lane of a 64-row group), so that one broadcast K / V read serves two
+// rows: the kernel is bound by shared memory -> register bandwidth (32 crossbar cycles per K + V row of a head, whatever the
+// number of lanes that read it), not by the FMAs.
 __global__ void __launch_bounds__(kAtThreads, 2) attn_fwd_kernel(int64_t L, int rows_per_cta, int N, const float* __restrict__ q,
                                                                 const float* __restrict__ k, const float* __restrict__ v,
                                                                 const uint8_t* __restrict__ mask, int add_res,
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_fwd_kernel(int64_t L, int 
   extern __shared__ __align__(16) float at_smem[];
   float* Ks = at_smem;
   float* Vs = Ks + N * kE;
-  uint32_t* mb = reinterpret_cast<uint32_t*>(Vs + N * kE);
+  uint32_t* mb = reinterpret_cast<uint32_t*>(Vs + N * kE);   // [64 rows][kMbStride]
   const int tid = threadIdx.x, h = tid >> 5, lane = tid & 31;
   const int64_t b = blockIdx.y;
   {
@@ -59,82 +62,99 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_fwd_kernel(int64_t L, int 
   }
   const int64_t row_lo = b * L + (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row_hi = min(row_lo + rows_per_cta, (b + 1) * L);
-  for (int64_t g0 = row_lo; g0 < row_hi; g0 += kAtGroup) {
+  for (int64_t g0 = row_lo; g0 < row_hi; g0 += 2 * kAtGroup) {
     __syncthreads();
     stage_mask_bits(mb, mask, g0, row_hi, N, tid);
+    stage_mask_bits(mb + kAtGroup * kMbStride, mask, g0 + kAtGroup, row_hi, N, tid);
     __syncthreads();
-    const int64_t row = g0 + lane;
-    const bool valid = row < row_hi;
-    if (row + kAtGroup < row_hi) {  // the next group's rows stream from HBM: start them now (one CTA per SM leaves nothing else to hide the latency)
-      prefetch_l2(q + (row + kAtGroup) * kE + h * 16);
-      if (tid * 16 < kAtGroup * N) prefetch_l2(mask + (g0 + kAtGroup) * N + tid * 16);
+    const int64_t rowa = g0 + lane, rowb = g0 + kAtGroup + lane;
+    const bool va = rowa < row_hi, vb = rowb < row_hi;
+    if (rowa + 2 * kAtGroup < row_hi) {  // the next group's rows stream from HBM: start them now
+      prefetch_l2(q + (rowa + 2 * kAtGroup) * kE + h * 16);
+      prefetch_l2(q + (rowb + 2 * kAtGroup) * kE + h * 16);
+      if (tid * 32 < 2 * kAtGroup * N) prefetch_l2(mask + (g0 + 2 * kAtGroup) * N + tid * 32);
     }
-    float qr[16], qs[16], o[16];
+    float qa[16], qb[16], oa[16], ob[16];
     {
-      const float4* src = reinterpret_cast<const float4*>(q + row * kE + h * 16);
+      const float4* sa = reinterpret_cast<const float4*>(q + rowa * kE + h * 16);
+      const float4* sb = reinterpret_cast<const float4*>(q + rowb * kE + h * 16);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 t = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        qr[4 * i] = t.x; qr[4 * i + 1] = t.y; qr[4 * i + 2] = t.z; qr[4 * i + 3] = t.w;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 ta = va ? __ldg(sa + i) : z, tb = vb ? __ldg(sb + i) : z;
+        qa[4 * i] = ta.x * kQScale; qa[4 * i + 1] = ta.y * kQScale; qa[4 * i + 2] = ta.z * kQScale; qa[4 * i + 3] = ta.w * kQScale;
+        qb[4 * i] = tb.x * kQScale; qb[4 * i + 1] = tb.y * kQScale; qb[4 * i + 2] = tb.z * kQScale; qb[4 * i + 3] = tb.w * kQScale;
       }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      qs[i] = qr[i] * kQScale;
-      o[i] = 0.f;
-    }
-    float m = -1e30f, l = 0.f;
+    for (int i = 0; i < 16; ++i) oa[i] = ob[i] = 0.f;
+    float ma = -1e30f, la = 0.f, mbx = -1e30f, lb = 0.f;
 #pragma unroll 1
     for (int wi = 0; wi < 4; ++wi) {
-      const uint32_t word = mb[lane * kMbStride + wi];
+      const uint32_t worda = mb[lane * kMbStride + wi], wordb = mb[(kAtGroup + lane) * kMbStride + wi];
       const int jn = min(32, N - wi * 32);
 #pragma unroll 1
-      for (int jj = 0; jj < jn; jj += 2) {  // two keys per iteration (two independent chains)
-        const bool bit0 = (word >> jj) & 1u, bit1 = jj + 1 < jn && ((word >> (jj + 1)) & 1u);
-        if (!__any_sync(0xffffffffu, bit0 || bit1)) continue;
-        const int j0 = wi * 32 + jj, j1 = min(j0 + 1, N - 1);
-        const float4* kp0 = reinterpret_cast<const float4*>(Ks + j0 * kE + h * 16);
-        const float4* kp1 = reinterpret_cast<const float4*>(Ks + j1 * kE + h * 16);
-        float sa[4], sb[4];   // independent partial sums (short dependency chains)
+      for (int jj = 0; jj < jn; ++jj) {
+        const bool bita = (worda >> jj) & 1u, bitb = (wordb >> jj) & 1u;
+        if (!__any_sync(0xffffffffu, bita || bitb)) continue;
+        const int j = wi * 32 + jj;
+        const float4* kp = reinterpret_cast<const float4*>(Ks + j * kE + h * 16);
+        float pa[4], pb[4];   // independent partial sums (short dependency chains)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = kp0[i], t1 = kp1[i];
-          sa[i] = fmaf(qs[4 * i + 3], t.w, fmaf(qs[4 * i + 2], t.z, fmaf(qs[4 * i + 1], t.y, qs[4 * i] * t.x)));
-          sb[i] = fmaf(qs[4 * i + 3], t1.w, fmaf(qs[4 * i + 2], t1.z, fmaf(qs[4 * i + 1], t1.y, qs[4 * i] * t1.x)));
+          const float4 t = kp[i];
+          pa[i] = fmaf(qa[4 * i + 3], t.w, fmaf(qa[4 * i + 2], t.z, fmaf(qa[4 * i + 1], t.y, qa[4 * i] * t.x)));
+          pb[i] = fmaf(qb[4 * i + 3], t.w, fmaf(qb[4 * i + 2], t.z, fmaf(qb[4 * i + 1], t.y, qb[4 * i] * t.x)));
         }
-        const float s0 = (sa[0] + sa[1]) + (sa[2] + sa[3]), s1 = (sb[0] + sb[1]) + (sb[2] + sb[3]);
-        const float smax = fmaxf(bit0 ? s0 : -INFINITY, bit1 ? s1 : -INFINITY);
-        if (smax > m + 8.f) {  // lazy rescale: rare after the first feasible key
-          const float corr = exp2f(m - smax);
-          l *= corr;
+        const float sa = (pa[0] + pa[1]) + (pa[2] + pa[3]), sb = (pb[0] + pb[1]) + (pb[2] + pb[3]);
+        if (bita && sa > ma + 8.f) {  // lazy rescale: rare after the first feasible key
+          const float corr = exp2f(ma - sa);
+          la *= corr;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] *= corr;
-          m = smax;
+          for (int i = 0; i < 16; ++i) oa[i] *= corr;
+          ma = sa;
         }
-        const float p0 = bit0 ? exp2f(s0 - m) : 0.f, p1 = bit1 ? exp2f(s1 - m) : 0.f;
-        l += p0 + p1;
-        const float4* vp0 = reinterpret_cast<const float4*>(Vs + j0 * kE + h * 16);
-        const float4* vp1 = reinterpret_cast<const float4*>(Vs + j1 * kE + h * 16);
+        if (bitb && sb > mbx + 8.f) {
+          const float corr = exp2f(mbx - sb);
+          lb *= corr;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ob[i] *= corr;
+          mbx = sb;
+        }
+        const float wa = bita ? exp2f(sa - ma) : 0.f, wb = bitb ? exp2f(sb - mbx) : 0.f;
+        la += wa;
+        lb += wb;
+        const float4* vp = reinterpret_cast<const float4*>(Vs + j * kE + h * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = vp0[i], t1 = vp1[i];
-          o[4 * i] = fmaf(p0, t.x, o[4 * i]); o[4 * i + 1] = fmaf(p0, t.y, o[4 * i + 1]);
-          o[4 * i + 2] = fmaf(p0, t.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(p0, t.w, o[4 * i + 3]);
-          o[4 * i] = fmaf(p1, t1.x, o[4 * i]); o[4 * i + 1] = fmaf(p1, t1.y, o[4 * i + 1]);
-          o[4 * i + 2] = fmaf(p1, t1.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(p1, t1.w, o[4 * i + 3]);
+          const float4 t = vp[i];
+          oa[4 * i] = fmaf(wa, t.x, oa[4 * i]); oa[4 * i + 1] = fmaf(wa, t.y, oa[4 * i + 1]);
+          oa[4 * i + 2] = fmaf(wa, t.z, oa[4 * i + 2]); oa[4 * i + 3] = fmaf(wa, t.w, oa[4 * i + 3]);
+          ob[4 * i] = fmaf(wb, t.x, ob[4 * i]); ob[4 * i + 1] = fmaf(wb, t.y, ob[4 * i + 1]);
+          ob[4 * i + 2] = fmaf(wb, t.z, ob[4 * i + 2]); ob[4 * i + 3] = fmaf(wb, t.w, ob[4 * i + 3]);
         }
       }
     }
-    if (valid) {
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
-      float4* dst = reinterpret_cast<float4*>(out + row * kE + h * 16);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 t = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
-        if (add_res) { t.x += qr[4 * i]; t.y += qr[4 * i + 1]; t.z += qr[4 * i + 2]; t.w += qr[4 * i + 3]; }
-        dst[i] = t;
+    for (int r = 0; r < 2; ++r) {
+      const int64_t row = r == 0 ? rowa : rowb;
+      if (row < row_hi) {
+        const float l = r == 0 ? la : lb, m = r == 0 ? ma : mbx;
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        float4* dst = reinterpret_cast<float4*>(out + row * kE + h * 16);
+        const float4* src = reinterpret_cast<const float4*>(q + row * kE + h * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* o = r == 0 ? oa : ob;
+          float4 t = make_float4(o[4 * i] * inv, o[4 * i + 1] * inv, o[4 * i + 2] * inv, o[4 * i + 3] * inv);
+          if (add_res) {
+            const float4 u = __ldg(src + i);
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+          }
+          dst[i] = t;
+        }
+        lse2[row * kH + h] = l > 0.f ? m + log2f(l) : 1e30f;
       }
-      lse2[row * kH + h] = l > 0.f ? m + log2f(l) : 1e30f;
     }
   }
 }
@@ -333,10 +353,10 @@ int rrnco_train_attention_fwd(int64_t n_inst, int64_t rows_per_inst, int32_t n_n
   RRNCO_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                     reinterpret_cast<uintptr_t>(out)) & 15u) == 0);
   if (n_nodes > 128 || n_inst > 65535) return RRNCO_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)2 * n_nodes * kE * sizeof(float) + kAtGroup * kMbStride * sizeof(uint32_t);
+  const size_t smem = (size_t)2 * n_nodes * kE * sizeof(float) + 2 * kAtGroup * kMbStride * sizeof(uint32_t);
   static PerDeviceOnce once;
   if (once.first()) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * kE * 4 + 1024) != cudaSuccess ||
+    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * kE * 4 + 2048) != cudaSuccess ||
         cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
       once.undo();
       return RRNCO_ERR_CUDA;
