@@ -180,15 +180,26 @@ __global__ void __launch_bounds__(kTThreads, 1) ffn_train_kernel(int64_t M, cons
   const float unscale1 = 1.0f / (a_scale * kWScale), unscale2 = 1.0f / (h_scale * kWScale);
   float amax = 0.f;  // largest scaled operand magnitude seen by this thread (fp16 overflow check)
 
-  auto convert_tile = [&](int64_t m0) {
-    for (int idx = tid; idx < kFRows * 16; idx += 256) {
-      const int r = idx & 127, c8 = idx >> 7;
+  float4 buf[16];   // this thread's 8 (row, 8-column chunk) items of the NEXT tile, loaded while the current tile is in its epilogues
+  auto load_tile = [&](int64_t m0) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + it * 256, r = idx & 127, c8 = idx >> 7;
       float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
       if (m0 + r < M) {
         const float4* src = reinterpret_cast<const float4*>(x + (m0 + r) * kE) + c8 * 2;
         v0 = __ldg(src);
         v1 = __ldg(src + 1);
       }
+      buf[2 * it] = v0;
+      buf[2 * it + 1] = v1;
+    }
+  };
+  auto convert_tile = [&]() {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + it * 256, r = idx & 127, c8 = idx >> 7;
+      const float4 v0 = buf[2 * it], v1 = buf[2 * it + 1];
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))) * a_scale);
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))) * a_scale);
       uint32_t h[4], l[4];
@@ -206,10 +217,14 @@ __global__ void __launch_bounds__(kTThreads, 1) ffn_train_kernel(int64_t M, cons
 
   uint32_t n_h[2] = {0u, 0u}, n_g2 = 0u;
   int64_t t = blockIdx.x;
-  if (t < n_tiles) convert_tile(t * kFRows);
+  if (t < n_tiles) {
+    load_tile(t * kFRows);
+    convert_tile();
+  }
   for (; t < n_tiles; t += gridDim.x) {
     const int64_t m0 = t * kFRows;
     const bool valid = m0 + row < M;
+    if (t + gridDim.x < n_tiles) load_tile((t + gridDim.x) * kFRows);
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       tc05::mbar_wait(&sm.bar_h[c & 1], n_h[c & 1] & 1u);
@@ -258,7 +273,7 @@ __global__ void __launch_bounds__(kTThreads, 1) ffn_train_kernel(int64_t M, cons
       tc05::mbar_arrive(&sm.bar_epi);
     }
     // every GEMM1 of this tile has completed (bar_h of chunk 3): the x tile may be replaced while GEMM2(3) runs
-    if (t + gridDim.x < n_tiles) convert_tile((t + gridDim.x) * kFRows);
+    if (t + gridDim.x < n_tiles) convert_tile();
     tc05::mbar_wait(&sm.bar_g2, n_g2 & 1u);  // GEMM2(3): output accumulator complete
     ++n_g2;
     tc05::fence_after_sync();

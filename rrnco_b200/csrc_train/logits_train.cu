@@ -50,25 +50,29 @@ __global__ void __launch_bounds__(256) logits_tail_kernel(int64_t rows, int64_t 
         }
         const float x = zrow[j] * inv_sqrt_e - bias;
         const float ex = expf(x);
-        const float u = logf(ex + 1e-6f);               // decoder.py:198
-        const float sig = 1.0f / (1.0f + 1e-6f / ex);   // d u / d x = ex / (ex + 1e-6), finite for ex = 0 and ex = inf
+        const float y = ex + 1e-6f;                     // decoder.py:198: u = log(y)
+        const float sig = 1.0f - 1e-6f / y;             // d u / d x = ex / (ex + 1e-6), finite for ex = 0 and ex = inf
         if (clip > 0.f) {                               // decoding.py:332-333
-          const float th = tanhf(u);
-          lj[i] = th * clip * inv_temp;
-          fac[i] = clip * (1.0f - th * th) * sig * inv_temp;
+          // tanh(log y) = (y^2 - 1) / (y^2 + 1) = 1 - w,  1 - tanh^2 = w (2 - w),  w = 2 / (y^2 + 1): no log, no tanh, finite for y = inf
+          const float w = 2.0f / fmaf(y, y, 1.0f);
+          lj[i] = (1.0f - w) * clip * inv_temp;
+          fac[i] = clip * w * (2.0f - w) * sig * inv_temp;
         } else {
-          lj[i] = u * inv_temp;
+          lj[i] = logf(y) * inv_temp;
           fac[i] = sig * inv_temp;
         }
         mx = fmaxf(mx, lj[i]);
       }
     }
     mx = warp_max(mx);
-    float se = 0.f;
+    float se = 0.f, ej[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) se += lj[i] > -INFINITY ? expf(lj[i] - mx) : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      ej[i] = lj[i] > -INFINITY ? expf(lj[i] - mx) : 0.f;
+      se += ej[i];
+    }
     se = warp_sum(se);
-    const float lse = mx + logf(se);
+    const float lse = mx + logf(se), inv_se = 1.0f / se;
     float la = (a >> 5) == 0 ? lj[0] : (a >> 5) == 1 ? lj[1] : (a >> 5) == 2 ? lj[2] : lj[3];
     la = __shfl_sync(0xffffffffu, la, a & 31);
     float sa = 0.f, sb = 0.f;
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(256) logits_tail_kernel(int64_t rows, int64_t 
       const int j = lane + 32 * i;
       if (j < N) {
         float dx = 0.f;  // d logp / d x_j
-        if (lj[i] > -INFINITY) dx = ((j == a ? 1.0f : 0.f) - expf(lj[i] - lse)) * fac[i];
+        if (lj[i] > -INFINITY) dx = ((j == a ? 1.0f : 0.f) - ej[i] * inv_se) * fac[i];
         zrow[j] = dx * inv_sqrt_e;
         sa = fmaf(-dx, dj[i], sa);
         sb = fmaf(-dx, uj[i], sb);

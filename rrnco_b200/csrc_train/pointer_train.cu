@@ -108,11 +108,11 @@ __global__ void __launch_bounds__(kPtThreads, 1) inst_gemm_kernel(int64_t L, int
   const float a_scale = a_scale_ptr ? __ldg(a_scale_ptr) : kAScale;
   const float unscale = 1.0f / (a_scale * kLkScale);
   float amax = 0.f;
-  for (int i = 0; i < n_tiles; ++i) {
-    const int64_t m0 = row_lo + (int64_t)i * kFRows;
-    // x tile -> fp16 hi | lo core-matrix tiles (the previous tile's MMAs have completed: its epilogue waited for them)
-    for (int idx = tid; idx < kFRows * 16; idx += 256) {
-      const int r = idx & 127, c8 = idx >> 7;
+  float4 buf[16];   // this thread's 8 (row, 8-column chunk) items of a tile, raw: the next tile is in flight while the current one is consumed
+  auto load_tile = [&](int64_t m0) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + it * 256, r = idx & 127, c8 = idx >> 7;
       float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
       if (m0 + r < row_hi) {
         const float4* src = reinterpret_cast<const float4*>(X + (m0 + r) * kE) + c8 * 2;
@@ -124,6 +124,18 @@ __global__ void __launch_bounds__(kPtThreads, 1) inst_gemm_kernel(int64_t L, int
           v1.x *= rs; v1.y *= rs; v1.z *= rs; v1.w *= rs;
         }
       }
+      buf[2 * it] = v0;
+      buf[2 * it + 1] = v1;
+    }
+  };
+  if (n_tiles > 0) load_tile(row_lo);
+  for (int i = 0; i < n_tiles; ++i) {
+    const int64_t m0 = row_lo + (int64_t)i * kFRows;
+    // x tile -> fp16 hi | lo core-matrix tiles (the previous tile's MMAs have completed: its epilogue waited for them)
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + it * 256, r = idx & 127, c8 = idx >> 7;
+      const float4 v0 = buf[2 * it], v1 = buf[2 * it + 1];
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))) * a_scale);
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))) * a_scale);
       uint32_t h[4], l[4];
@@ -135,6 +147,7 @@ __global__ void __launch_bounds__(kPtThreads, 1) inst_gemm_kernel(int64_t L, int
       *reinterpret_cast<uint4*>(&sm.a_hi[dst]) = make_uint4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<uint4*>(&sm.a_lo[dst]) = make_uint4(l[0], l[1], l[2], l[3]);
     }
+    if (i + 1 < n_tiles) load_tile(m0 + kFRows);
     tc05::fence_proxy_async();
     tc05::mbar_arrive(&sm.bar_a);
     tc05::mbar_wait(&sm.bar_mma, i & 1);

@@ -13,6 +13,10 @@ g = torch.Generator(device=dev).manual_seed(0)
 
 
 def timed(fn, reps=3):
+    if os.environ.get("ONCE"):   # one launch of each kernel (for an ncu capture)
+        fn()
+        torch.cuda.synchronize()
+        return float("nan")
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -70,12 +74,21 @@ print(f"attention forward               {t:7.2f} ms")
 dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
 t = timed(lambda: h.rrnco_train_attention_bwd(n_inst, L, N, P(q), P(k), P(v), P(m8), P(out), 1, P(lse), P(dy.view_as(q)), P(dq), P(dk), P(dv), S(dev)))
 print(f"attention backward              {t:7.2f} ms")
+lk = torch.randn(n_inst, N, 128, device=dev, generator=g)
+pk = torch.empty(h.rrnco_train_inst_packed_bytes(n_inst), dtype=torch.uint8, device=dev)
+h.rrnco_train_inst_pack(n_inst, N, P(lk), 0, P(pk), P(st), S(dev))
+zz = torch.empty(n_inst, L, 128, device=dev)
+t = timed(lambda: h.rrnco_train_inst_gemm(n_inst, L, P(q), P(pk), None, None, P(zz), P(st), S(dev)))
+print(f"pointer scores (inst_gemm)      {t:7.2f} ms  {2 * rows * 128 * 128 / t / 1e9:7.1f} TFLOP/s on the padded tile")
+dlk = torch.zeros(n_inst, N, 128, device=dev)
+t = timed(lambda: h.rrnco_train_inst_xty(n_inst, L, N, P(zz), P(q), None, None, None, P(dlk), P(st), S(dev)))
+print(f"pointer dLk (xty_inst)          {t:7.2f} ms")
 z = torch.randn(n_inst, L, N, device=dev, generator=g) * 20
 dist = torch.rand(n_inst, N, N, device=dev, generator=g)
 cur = torch.randint(0, N, (n_inst, L), device=dev, generator=g)
 act = torch.zeros(n_inst, L, dtype=torch.int64, device=dev)
 alpha = torch.ones(1, device=dev)
 lp, da = torch.empty(n_inst, L, device=dev), torch.empty(n_inst, L, device=dev)
-t = timed(lambda: h.rrnco_train_logits_tail(rows, L, N, P(z), P(dist), None, P(cur), P(m8), P(act), P(alpha), None, 128 ** -0.5, 10.0, 1.0, P(lp), P(da), None, S(dev)))
+t = timed(lambda: h.rrnco_train_logits_tail(rows, L, N, N, P(z), P(dist), None, P(cur), P(m8), P(act), P(alpha), None, 128 ** -0.5, 10.0, 1.0, P(lp), P(da), None, S(dev)))
 print(f"logits tail                     {t:7.2f} ms  {rows * N * 9 / t / 1e6:7.1f} GB/s (z in/out + mask)")
 train_ops.check_status(dev)
