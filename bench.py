@@ -687,6 +687,12 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         cfg_block = measure_configs(args, rb, dev, rank, world, dist_on, timed)
 
+    # ---- training hand-off: one REINFORCE step at the C5 per-GPU shape, rank 0 only ----------------
+    train_entry = None
+    if rank == 0 and not args.no_configs:
+        torch.cuda.empty_cache()
+        train_entry = training_probe(rb, dev)
+
     if rank == 0:
         hbm_peak, tf_peak, peak_src = peaks()
         stamp = profile_stamp()
@@ -755,6 +761,8 @@ def run_ours(args, rank, world, local_rank):
         line["encoder_nab"] = nab_entry
         if cfg_block is not None:
             line["configs"] = cfg_block
+        if train_entry is not None:
+            line["training_step"] = train_entry
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rate, dt, cost, Tc = cpu_rollout_rate(args.cpu_sample, threads)
@@ -764,6 +772,65 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if dist_on:
         dist.destroy_process_group()
+
+
+def training_probe(rb, dev, n_inst=512, steps=3):
+    """One training step as upstream's `shared_step` runs it (rl.py:99-130) at the per-GPU shape of config C5: sampling
+    rollout on the fused kernel (no graph) -> differentiable replay of the sampled actions -> POMO shared-baseline loss ->
+    backward to the decoder parameters and the encoder output.  Timed on the device (CUDA events, median of `steps` after one
+    warm-up) for the hand-written replay kernels (librrnco_b200_train.so) and, once, for the plain-torch (ATen) replay."""
+    from rrnco_b200 import training as tr, train_ops
+    S = N_LOC + 1
+    env = rb.RCVRPEnv(generator_params={"num_loc": N_LOC}, check_solution=False, device=dev)
+    raw = host_instances(n_inst, seed=31337)
+    td = env.reset(rb.TensorDictLite({k: v.to(dev) for k, v in raw.items()}, batch_size=[n_inst]))
+    row, col = stand_in_embeddings(n_inst, seed=31338)
+    row, col = row.to(dev).requires_grad_(True), col.to(dev).requires_grad_(True)
+    torch.manual_seed(1234)
+    decoder = rb.RRNetDecoder(env_name="rcvrp").to(dev)
+
+    class Enc(torch.nn.Module):
+        def forward(self, td, phase=None):
+            return row, col
+
+    pol = rb.RRNetPolicy(encoder=Enc(), decoder=decoder, env_name="rcvrp").to(dev)
+
+    def one(impl):
+        tr.REPLAY_IMPL = impl
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        with torch.no_grad():
+            out = pol(td, env, phase="train", decode_type="multistart_sampling", num_starts=S)
+        ll = rb.replay_log_likelihood(pol, td, env, out["actions"], S, embeddings=(row, col))
+        rb.pomo_shared_baseline_loss(out["reward"], ll, S).backward()
+        e1.record()
+        torch.cuda.synchronize()
+        err = (ll.detach() - out["log_likelihood"]).abs().max().item()
+        gn = float(sum(p.grad.double().pow(2).sum() for p in decoder.parameters() if p.grad is not None).sqrt())
+        pol.zero_grad(set_to_none=True)
+        row.grad = col.grad = None
+        return e0.elapsed_time(e1), int(out["actions"].shape[1]), err, gn
+
+    try:
+        one("fused")
+        runs = sorted(one("fused") for _ in range(steps))
+        train_ops.check_status(dev)
+        ms, T, err, gn = runs[len(runs) // 2]
+        one("aten")
+        ms_aten, T_aten, err_aten, _ = one("aten")
+    finally:
+        tr.REPLAY_IMPL = "fused"
+    return {"workload": f"one REINFORCE step, RCVRP n={N_LOC}: {n_inst} instances x {S} starts sampled by the fused rollout kernel, "
+                        "differentiable replay of the sampled actions, POMO shared-baseline loss, backward (rl.py:99-130; per-GPU "
+                        "share of config C5)",
+            "ms_per_step": ms, "instances_per_s": n_inst / (ms * 1e-3), "decode_steps": T,
+            "replay": "hand-written kernels, forward and backward (librrnco_b200_train.so: tcgen05 FFN / pointer GEMMs in the "
+                      "three-term fp16 split, CUDA-core + mma.sync 3xTF32 attention), fp32-faithful",
+            "max_abs_loglik_diff_vs_sampling_kernel": err, "decoder_grad_norm": gn,
+            "aten_replay": {"ms_per_step": ms_aten, "decode_steps": T_aten, "max_abs_loglik_diff_vs_sampling_kernel": err_aten,
+                            "what": "the same step with the plain-torch replay (fp32 SDPA / cuBLAS SIMT GEMMs / element-wise ATen)"},
+            "timing": f"CUDA events around the whole step, median of {steps} after one warm-up; ATen arm: second of two steps"}
 
 
 # --------------------------------------------------------------------------------------------------
