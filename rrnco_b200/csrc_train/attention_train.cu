@@ -12,6 +12,7 @@
 //             shuffle joins the halves, and the result is added to the CTA's dK / dV tile in shared memory (the head's
 //             16 columns belong to this warp alone: no atomics); one atomic pass per CTA adds the tile to global memory.
 #include "../csrc/common.cuh"
+#include "../csrc/ffn_pack.cuh"   // ffma2 / fadd2: packed fp32 pairs (two IEEE FMAs per issue slot, same bits as the scalar forms)
 #include "../../include/rrnco_b200_train.h"
 
 namespace rrnco {
@@ -99,14 +100,17 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_fwd_kernel(int64_t L, int 
         if (!__any_sync(0xffffffffu, bita || bitb)) continue;
         const int j = wi * 32 + jj;
         const float4* kp = reinterpret_cast<const float4*>(Ks + j * kE + h * 16);
-        float pa[4], pb[4];   // independent partial sums (short dependency chains)
+        // packed fp32 pairs (FFMA2), two independent chains per dot product
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 t = kp[i];
-          pa[i] = fmaf(qa[4 * i + 3], t.w, fmaf(qa[4 * i + 2], t.z, fmaf(qa[4 * i + 1], t.y, qa[4 * i] * t.x)));
-          pb[i] = fmaf(qb[4 * i + 3], t.w, fmaf(qb[4 * i + 2], t.z, fmaf(qb[4 * i + 1], t.y, qb[4 * i] * t.x)));
+          a0 = ffma2(make_float2(qa[4 * i], qa[4 * i + 1]), make_float2(t.x, t.y), a0);
+          a1 = ffma2(make_float2(qa[4 * i + 2], qa[4 * i + 3]), make_float2(t.z, t.w), a1);
+          b0 = ffma2(make_float2(qb[4 * i], qb[4 * i + 1]), make_float2(t.x, t.y), b0);
+          b1 = ffma2(make_float2(qb[4 * i + 2], qb[4 * i + 3]), make_float2(t.z, t.w), b1);
         }
-        const float sa = (pa[0] + pa[1]) + (pa[2] + pa[3]), sb = (pb[0] + pb[1]) + (pb[2] + pb[3]);
+        const float sa = (a0.x + a0.y) + (a1.x + a1.y), sb = (b0.x + b0.y) + (b1.x + b1.y);
         if (bita && sa > ma + 8.f) {  // lazy rescale: rare after the first feasible key
           const float corr = exp2f(ma - sa);
           la *= corr;
@@ -125,13 +129,16 @@ __global__ void __launch_bounds__(kAtThreads, 2) attn_fwd_kernel(int64_t L, int 
         la += wa;
         lb += wb;
         const float4* vp = reinterpret_cast<const float4*>(Vs + j * kE + h * 16);
+        const float2 wa2 = make_float2(wa, wa), wb2 = make_float2(wb, wb);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 t = vp[i];
-          oa[4 * i] = fmaf(wa, t.x, oa[4 * i]); oa[4 * i + 1] = fmaf(wa, t.y, oa[4 * i + 1]);
-          oa[4 * i + 2] = fmaf(wa, t.z, oa[4 * i + 2]); oa[4 * i + 3] = fmaf(wa, t.w, oa[4 * i + 3]);
-          ob[4 * i] = fmaf(wb, t.x, ob[4 * i]); ob[4 * i + 1] = fmaf(wb, t.y, ob[4 * i + 1]);
-          ob[4 * i + 2] = fmaf(wb, t.z, ob[4 * i + 2]); ob[4 * i + 3] = fmaf(wb, t.w, ob[4 * i + 3]);
+          const float2 x0 = ffma2(wa2, make_float2(t.x, t.y), make_float2(oa[4 * i], oa[4 * i + 1]));
+          const float2 x1 = ffma2(wa2, make_float2(t.z, t.w), make_float2(oa[4 * i + 2], oa[4 * i + 3]));
+          const float2 y0 = ffma2(wb2, make_float2(t.x, t.y), make_float2(ob[4 * i], ob[4 * i + 1]));
+          const float2 y1 = ffma2(wb2, make_float2(t.z, t.w), make_float2(ob[4 * i + 2], ob[4 * i + 3]));
+          oa[4 * i] = x0.x; oa[4 * i + 1] = x0.y; oa[4 * i + 2] = x1.x; oa[4 * i + 3] = x1.y;
+          ob[4 * i] = y0.x; ob[4 * i + 1] = y0.y; ob[4 * i + 2] = y1.x; ob[4 * i + 3] = y1.y;
         }
       }
     }
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_bwd_kernel(int64_t L, int 
         const float p = bit ? exp2f(s - lse) : 0.f;
         const float ds = p * (dp - D);  // gradient of the natural-log-domain score q . k / 4
 #pragma unroll
-        for (int i = 0; i < 16; ++i) gq[i] = fmaf(ds, kr[i], gq[i]);
+        for (int i = 0; i < 16; ++i) gq[i] = fmaf(ds, kr[i], gq[i]);   // (packed FFMA2 pairs were measured here: 4 % slower)
         pw[kk * kPsStride + lane] = p;
         dw[kk * kPsStride + lane] = ds;
       }
