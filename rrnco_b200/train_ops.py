@@ -71,6 +71,21 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
+def _on_device(fn):
+    """Kernel launches go to the CURRENT device: run the wrapped forward / backward on the device of its first tensor argument
+    (a process may hold tensors on several GPUs)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                with torch.cuda.device(a.device):
+                    return fn(ctx, *args)
+        return fn(ctx, *args)
+    return wrapped
+
+
 def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
@@ -120,6 +135,7 @@ SAVE_HIDDEN = True   # keep the [rows, 512] hidden activations of the forward ca
 
 class _FusedFFN(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, w1, b1, w2, b2):
         h, dev = lib(), x.device
         x = x.detach().contiguous().float()
@@ -136,6 +152,7 @@ class _FusedFFN(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         x, mask, w1, b1, w2, b2, hidden = ctx.saved_tensors
         h, dev, st = lib(), x.device, status_word(x.device)
@@ -174,6 +191,7 @@ def fused_ffn(x, w1, b1, w2, b2):
 
 class _FusedAttention(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, q, k, v, mask, add_residual):
         h, dev = lib(), q.device
         q, k, v = (t.detach().contiguous().float() for t in (q, k, v))
@@ -189,6 +207,7 @@ class _FusedAttention(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, d_out):
         q, k, v, m8, out, lse = ctx.saved_tensors
         h, dev = lib(), q.device
@@ -208,6 +227,7 @@ def fused_attention(q, k, v, mask, add_residual: bool = True):
 
 class _ContextQuery(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, table_a, index_a, table_b, index_b, state, state_w):
         h, dev = lib(), table_a.device
         n_inst, N, _ = table_a.shape
@@ -227,6 +247,7 @@ class _ContextQuery(torch.autograd.Function):
         return q
 
     @staticmethod
+    @_on_device
     def backward(ctx, dq):
         index_a, index_b, state = ctx.saved_tensors
         h, dev = lib(), dq.device
@@ -248,6 +269,7 @@ def context_query(table_a, index_a, table_b=None, index_b=None, state=None, stat
 
 class _PointerScores(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, g, lk):
         h, dev, st = lib(), g.device, status_word(g.device)
         g, lk = g.detach().contiguous().float(), lk.detach().contiguous().float()
@@ -261,6 +283,7 @@ class _PointerScores(torch.autograd.Function):
         return z
 
     @staticmethod
+    @_on_device
     def backward(ctx, dz):
         g, lk = ctx.saved_tensors
         h, dev, st = lib(), g.device, status_word(g.device)
@@ -285,6 +308,7 @@ def pointer_scores(g, lk):
 
 class _LogitsTail(torch.autograd.Function):
     @staticmethod
+    @_on_device
     def forward(ctx, z, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature):
         h, dev = lib(), z.device
         n_inst, L, ldz = z.shape      # ldz >= N: the 128-wide rows of pointer_scores, or exactly N
@@ -310,6 +334,7 @@ class _LogitsTail(torch.autograd.Function):
         return logp
 
     @staticmethod
+    @_on_device
     def backward(ctx, g):
         jac, da, db = ctx.saved_tensors
         g = g.float()
@@ -330,6 +355,7 @@ class _PointerLogProb(torch.autograd.Function):
     each row straight into the dg / dlk kernels (`row_scale`), so dz = g_row J is never written."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, g, lk, alpha, beta, distance, duration, cur, mask, act, tanh_clipping, temperature):
         h, dev, st = lib(), g.device, status_word(g.device)
         g, lk = g.detach().contiguous().float(), lk.detach().contiguous().float()
@@ -357,6 +383,7 @@ class _PointerLogProb(torch.autograd.Function):
         return logp
 
     @staticmethod
+    @_on_device
     def backward(ctx, gl):
         g, lk, jac, da, db = ctx.saved_tensors
         h, dev, st = lib(), g.device, status_word(g.device)
