@@ -44,16 +44,19 @@ int rrnco_train_ffn_pack(const float* wa, const float* wb, void* packed, uint32_
  *   a_scale:    optional device scalar (power of two): x and hidden are multiplied by it before the fp16 hi|lo split
  *               (gradients are tiny: pick 2^k with max|x| a_scale ~ 512); NULL = 16, the rollout kernels' activation scale
  *   mask:       [rows, 16] uint32: bit (j & 31) of word j >> 5 = hidden unit j active
- *   hidden_out: optional [rows, 512] fp32 copy of `hidden` (the X operand of rrnco_train_xty)
+ *   hidden_out: optional fp32 copy of `hidden`, the X operand of rrnco_train_xty, TILE-BLOCKED AND TRANSPOSED:
+ *               [ceil(rows / 128)][512][128], element (row r, unit j) at (r / 128) * 65536 + j * 128 + r % 128 (coalesced for the
+ *               thread-per-row epilogue that writes it; rows beyond `rows` are not written)
  *   y:          optional [rows, 128] */
 int rrnco_train_ffn(int32_t mode, int64_t rows, const float* x, const void* packed, const float* b1, const float* b2,
                     const float* a_scale, uint32_t* mask, float* hidden_out, float* y, uint32_t* status, void* stream);
 
 /* C[512, 128] += X^T Y,  xsum[512] += column sums of X,  ysum[128] += column sums of Y  (xsum / ysum optional).
- *   x: [rows, 512], y: [rows, 128]; sx / sy: optional device scalars (powers of two) applied before the split, NULL = 16.
+ *   x: [rows, 512] row-major (x_tiled == 0) or the tile-blocked layout of rrnco_train_ffn's hidden_out (x_tiled != 0), y: [rows, 128];
+ *   sx / sy: optional device scalars (powers of two) applied before the split, NULL = 16.
  * C / xsum / ysum are accumulated with fp32 atomics (the order of the partial sums is not fixed run to run). */
-int rrnco_train_xty(int64_t rows, const float* x, const float* y, const float* sx, const float* sy, float* c, float* xsum,
-                    float* ysum, uint32_t* status, void* stream);
+int rrnco_train_xty(int64_t rows, const float* x, int32_t x_tiled, const float* y, const float* sx, const float* sy, float* c,
+                    float* xsum, float* ysum, uint32_t* status, void* stream);
 
 /* Masked multi-head attention of decoder.py:281-293 for the batched replay: instance b owns rows [b L, (b + 1) L) of q.
  *   q [n_inst L, 128], k / v [n_inst, n_nodes, 128] (head h = columns 16 h .. 16 h + 15), mask [n_inst L, n_nodes] bytes

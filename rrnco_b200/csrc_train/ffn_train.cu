@@ -255,9 +255,11 @@ __global__ void __launch_bounds__(kTThreads, 1) ffn_train_kernel(int64_t M, cons
           amax = fmaxf(amax, fabsf(h[i]) * h_scale);
         }
         if (hid_out != nullptr && valid) {
-          float4* dst = reinterpret_cast<float4*>(hid_out + (m0 + row) * kF + c * kFRows + col0);
+          // tile-blocked, transposed: [tile][hidden unit (512)][row (128)] - the 32 lanes of a store are 32 consecutive rows of one
+          // unit (one 128-byte wavefront) instead of 32 half-filled sectors 2 KB apart; xty_kernel is the only reader
+          float* dst = hid_out + t * (int64_t)(kF * kFRows) + (int64_t)(c * kFRows + col0) * kFRows + row;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+          for (int i = 0; i < 16; ++i) dst[i * kFRows] = h[i];
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) f16s_split2(h[2 * i], h[2 * i + 1], h_scale, hi[i], lo[i]);
@@ -333,7 +335,7 @@ static_assert(sizeof(XtySmem) <= 113 * 1024, "two CTAs per SM");
 __global__ void __launch_bounds__(kXThreads, 2) xty_kernel(int64_t M, const float* __restrict__ X, const float* __restrict__ Y,
                                                           const float* __restrict__ sx_ptr, const float* __restrict__ sy_ptr,
                                                           float* __restrict__ C, float* __restrict__ xsum, float* __restrict__ ysum,
-                                                          uint32_t* __restrict__ status) {
+                                                          uint32_t* __restrict__ status, int x_tiled) {
   extern __shared__ __align__(128) unsigned char xty_smem_raw[];
   XtySmem& sm = *reinterpret_cast<XtySmem*>(xty_smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -388,13 +390,34 @@ __global__ void __launch_bounds__(kXThreads, 2) xty_kernel(int64_t M, const floa
   const int fy = tid & 127, ry = tid >> 7;   // Y column, first 8-row group (second: ry + 2)
   const float* xcol = X + half * kXFeat + f;
   float csum = 0.f, ysm = 0.f, amax = 0.f;
+  float csum4[4] = {0.f, 0.f, 0.f, 0.f};   // x_tiled: the four features of this thread's items
   uint32_t it = 0;
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
     const uint32_t st = it & 1u;
     const int64_t r0 = t * kXRows;
     float xv[kXRows], yv[16];
+    if (x_tiled) {
+      // X = [tile of 128 rows][feature (512)][row (128)] (ffn_train_kernel's hidden_out): item = (feature, 8-row group), 32 contiguous
+      // bytes; lane & 3 = group, so four lanes read one 128-byte line; item u of this thread: feature u * 64 + tid / 4
+      const float* xt = X + (r0 >> 7) * (int64_t)(kF * kFRows) + (int64_t)(half * kXFeat) * kFRows + (r0 & 127);
+      const int kc = tid & 3;
 #pragma unroll
-    for (int r = 0; r < kXRows; ++r) xv[r] = (r0 + r < M) ? __ldg(xcol + (r0 + r) * kF) : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const int fu = u * 64 + (tid >> 2);
+        const float4* src = reinterpret_cast<const float4*>(xt + (int64_t)fu * kFRows + kc * 8);
+        const int64_t rr = r0 + kc * 8;
+        float4 a = __ldg(src), c4 = __ldg(src + 1);
+        if (rr + 7 >= M) {  // ragged tail: rows beyond M hold nothing
+          if (rr + 0 >= M) a.x = 0.f; if (rr + 1 >= M) a.y = 0.f; if (rr + 2 >= M) a.z = 0.f; if (rr + 3 >= M) a.w = 0.f;
+          if (rr + 4 >= M) c4.x = 0.f; if (rr + 5 >= M) c4.y = 0.f; if (rr + 6 >= M) c4.z = 0.f; if (rr + 7 >= M) c4.w = 0.f;
+        }
+        xv[u * 8] = a.x; xv[u * 8 + 1] = a.y; xv[u * 8 + 2] = a.z; xv[u * 8 + 3] = a.w;
+        xv[u * 8 + 4] = c4.x; xv[u * 8 + 5] = c4.y; xv[u * 8 + 6] = c4.z; xv[u * 8 + 7] = c4.w;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < kXRows; ++r) xv[r] = (r0 + r < M) ? __ldg(xcol + (r0 + r) * kF) : 0.f;
+    }
 #pragma unroll
     for (int g = 0; g < 2; ++g)
 #pragma unroll
@@ -404,16 +427,20 @@ __global__ void __launch_bounds__(kXThreads, 2) xty_kernel(int64_t M, const floa
       }
     if (it >= 2) tc05::mbar_wait(&sm.bar_free[st], ((it >> 1) - 1) & 1u);  // the MMAs that read this stage have completed
 #pragma unroll
-    for (int kc = 0; kc < 4; ++kc) {
+    for (int u = 0; u < 4; ++u) {   // row-major X: u = 8-row group of feature f; tiled X: u = item (feature u * 64 + tid / 4, group tid & 3)
       uint32_t h[4], l[4];
+      float part = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float a = xv[kc * 8 + 2 * i], b = xv[kc * 8 + 2 * i + 1];
-        csum += a + b;
+        const float a = xv[u * 8 + 2 * i], b = xv[u * 8 + 2 * i + 1];
+        part += a + b;
         amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)) * sx);
         f16s_split2(a, b, sx, h[i], l[i]);
       }
-      const int dst = (f >> 7) * (4 * kFRows * 8) + kc * (kFRows * 8) + (f & 127) * 8;
+      csum += part;
+      csum4[u] += part;
+      const int fe = x_tiled ? u * 64 + (tid >> 2) : f, kc = x_tiled ? (tid & 3) : u;
+      const int dst = (fe >> 7) * (4 * kFRows * 8) + kc * (kFRows * 8) + (fe & 127) * 8;
       *reinterpret_cast<uint4*>(&sm.x_hi[st][dst]) = make_uint4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<uint4*>(&sm.x_lo[st][dst]) = make_uint4(l[0], l[1], l[2], l[3]);
     }
@@ -451,7 +478,14 @@ __global__ void __launch_bounds__(kXThreads, 2) xty_kernel(int64_t M, const floa
       for (int i = 0; i < 16; ++i) atomicAdd(crow + q * 16 + i, __uint_as_float(v[i]) * unscale);
     }
   }
-  if (xsum != nullptr) atomicAdd(xsum + half * kXFeat + f, csum);
+  if (xsum != nullptr) {
+    if (x_tiled) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) atomicAdd(xsum + half * kXFeat + u * 64 + (tid >> 2), csum4[u]);
+    } else {
+      atomicAdd(xsum + half * kXFeat + f, csum);
+    }
+  }
   if (ysum != nullptr && half == 0) atomicAdd(ysum + fy, ysm);
   if (!(amax < kF16Max)) atomicOr(status, RRNCO_DEV_NAN_LOGITS);
   tc05::fence_before_sync();
@@ -502,10 +536,10 @@ int rrnco_train_ffn(int32_t mode, int64_t rows, const float* x, const void* pack
   return rrnco_launch_status();
 }
 
-int rrnco_train_xty(int64_t rows, const float* x, const float* y, const float* sx, const float* sy, float* c, float* xsum,
-                    float* ysum, uint32_t* status, void* stream) {
+int rrnco_train_xty(int64_t rows, const float* x, int32_t x_tiled, const float* y, const float* sx, const float* sy, float* c,
+                    float* xsum, float* ysum, uint32_t* status, void* stream) {
   if (rows == 0) return RRNCO_OK;
-  RRNCO_CHECK_ARG(rows > 0 && x && y && c && status);
+  RRNCO_CHECK_ARG(rows > 0 && x && y && c && status && (reinterpret_cast<uintptr_t>(x) & 15u) == 0);
   static PerDeviceOnce once;
   if (once.first()) {
     if (cudaFuncSetAttribute(xty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XtySmem)) != cudaSuccess ||
@@ -517,7 +551,7 @@ int rrnco_train_xty(int64_t rows, const float* x, const float* y, const float* s
   const int64_t n_tiles = (rows + kXRows - 1) / kXRows;
   const int sms = device_sm_count();
   dim3 grid((unsigned)(n_tiles < sms ? n_tiles : sms), 2);
-  xty_kernel<<<grid, kXThreads, sizeof(XtySmem), (cudaStream_t)stream>>>(rows, x, y, sx, sy, c, xsum, ysum, status);
+  xty_kernel<<<grid, kXThreads, sizeof(XtySmem), (cudaStream_t)stream>>>(rows, x, y, sx, sy, c, xsum, ysum, status, x_tiled);
   return rrnco_launch_status();
 }
 

@@ -26,7 +26,7 @@ _SIGNATURES = {
     "rrnco_train_ffn_packed_bytes": (C.c_int64, []),
     "rrnco_train_ffn_pack": (C.c_int, [_f, _f, _f, _f, _f]),
     "rrnco_train_ffn": (C.c_int, [C.c_int32, C.c_int64, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
-    "rrnco_train_xty": (C.c_int, [C.c_int64, _f, _f, _f, _f, _f, _f, _f, _f, _f]),
+    "rrnco_train_xty": (C.c_int, [C.c_int64, _f, C.c_int32, _f, _f, _f, _f, _f, _f, _f, _f]),
     "rrnco_train_attention_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, C.c_int32, _f, _f, _f]),
     "rrnco_train_attention_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, C.c_int32, _f, _f, _f, _f, _f, _f]),
     "rrnco_train_context_query_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, _f, _f, _f, _f, _f, C.c_int32, _f, _f, _f]),
@@ -144,7 +144,7 @@ class _FusedFFN(torch.autograd.Function):
         mask = torch.empty(rows, 16, dtype=torch.int32, device=dev)
         y = torch.empty_like(x)
         keep = SAVE_HIDDEN and any(ctx.needs_input_grad)
-        hidden = torch.empty(rows, 512, dtype=torch.float32, device=dev) if keep else None
+        hidden = torch.empty((rows + 127) // 128 * 128 * 512, dtype=torch.float32, device=dev) if keep else None   # tile-blocked
         packed = _pack(w1, w2, dev)
         _check(h.rrnco_train_ffn(0, rows, _p(x), _p(packed), _p(b1), _p(b2), None, _p(mask), _p(hidden), _p(y),
                                  _p(status_word(dev)), _stream(dev)), "rrnco_train_ffn")
@@ -164,11 +164,11 @@ class _FusedFFN(torch.autograd.Function):
         # |dhidden_j| <= max|dy| * sum_e |W2[e, j]|: a rigorous bound without a pass over the [rows, 512] tensor
         s_dh = pow2_scale(amax, bound_factor=w2.abs().sum(0).amax().clamp_min(1.0))
         if hidden is None:
-            hidden = torch.empty(rows, 512, dtype=torch.float32, device=dev)
+            hidden = torch.empty((rows + 127) // 128 * 128 * 512, dtype=torch.float32, device=dev)
             packed = _pack(w1, w2, dev)
             _check(h.rrnco_train_ffn(0, rows, _p(x), _p(packed), _p(b1), _p(b2), None, None, _p(hidden), None, _p(st),
                                      _stream(dev)), "rrnco_train_ffn (recompute)")
-        dhid = torch.empty(rows, 512, dtype=torch.float32, device=dev)
+        dhid = torch.empty((rows + 127) // 128 * 128 * 512, dtype=torch.float32, device=dev)   # tile-blocked, as hidden
         dx = torch.empty_like(x)
         packed_t = _pack(w2.t().contiguous(), w1.t().contiguous(), dev)
         _check(h.rrnco_train_ffn(1, rows, _p(dy), _p(packed_t), None, None, _p(s_dy), _p(mask), _p(dhid), _p(dx), _p(st),
@@ -177,9 +177,9 @@ class _FusedFFN(torch.autograd.Function):
         db1 = torch.zeros(512, dtype=torch.float32, device=dev)
         dw2t = torch.zeros(512, 128, dtype=torch.float32, device=dev)
         db2 = torch.zeros(128, dtype=torch.float32, device=dev)
-        _check(h.rrnco_train_xty(rows, _p(dhid), _p(x), _p(s_dh), None, _p(dw1), _p(db1), None, _p(st), _stream(dev)),
+        _check(h.rrnco_train_xty(rows, _p(dhid), 1, _p(x), _p(s_dh), None, _p(dw1), _p(db1), None, _p(st), _stream(dev)),
                "rrnco_train_xty (dW1)")
-        _check(h.rrnco_train_xty(rows, _p(hidden), _p(dy), None, _p(s_dy), _p(dw2t), None, _p(db2), _p(st), _stream(dev)),
+        _check(h.rrnco_train_xty(rows, _p(hidden), 1, _p(dy), None, _p(s_dy), _p(dw2t), None, _p(db2), _p(st), _stream(dev)),
                "rrnco_train_xty (dW2)")
         return dx, dw1, db1, dw2t.t(), db2
 

@@ -52,7 +52,7 @@ t = timed(lambda: h.rrnco_train_ffn(0, rows, P(x), P(packed), P(b1), P(b2), None
 print(f"ffn forward (hidden out)        {t:7.2f} ms")
 t = timed(lambda: h.rrnco_train_ffn(1, rows, P(dy), P(packed_t), None, None, P(sdy), P(mask), P(dhid), P(y), P(st), S(dev)))
 print(f"ffn backward-data (dhidden out) {t:7.2f} ms")
-t = timed(lambda: h.rrnco_train_xty(rows, P(hid), P(x), None, None, P(c), P(cs), None, P(st), S(dev)))
+t = timed(lambda: h.rrnco_train_xty(rows, P(hid), 1, P(x), None, None, P(c), P(cs), None, P(st), S(dev)))
 print(f"xty [rows,512]^T [rows,128]     {t:7.2f} ms  {2 * rows * 512 * 128 / t / 1e9:7.1f} TFLOP/s algorithmic, {rows * 640 * 4 / t / 1e6:7.1f} GB/s read")
 ffn = lambda: train_ops.fused_ffn(x.requires_grad_(True), w1.requires_grad_(True), b1.requires_grad_(True), w2.requires_grad_(True), b2.requires_grad_(True))
 def fb():
