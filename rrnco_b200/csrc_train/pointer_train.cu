@@ -45,6 +45,7 @@ struct InstGemmSmem {
   uint16_t a_lo[kFRows * kE];
   uint16_t b_hi[kFRows * kE];
   uint16_t b_lo[kFRows * kE];
+  float stage[kFRows * 132];   // output tile, row stride 132 floats: thread-per-row float4 writes and row-contiguous reads are conflict-free
   uint64_t bar_b, bar_a, bar_mma;
   uint32_t tmem_base;
 };
@@ -152,23 +153,29 @@ __global__ void __launch_bounds__(kPtThreads, 1) inst_gemm_kernel(int64_t L, int
     tc05::mbar_arrive(&sm.bar_a);
     tc05::mbar_wait(&sm.bar_mma, i & 1);
     tc05::fence_after_sync();
-    const bool valid = m0 + row < row_hi;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int col0 = colhalf * 64 + q * 16;
       uint32_t v[16];
       tc05::tmem_ld16(tb + lane_base + col0, v);
       tc05::tmem_wait_ld();
-      if (valid) {
-        float4* dst = reinterpret_cast<float4*>(Y + (m0 + row) * kE + col0);
+      // through shared memory: a thread-per-row store to global memory is 32 half-filled sectors per instruction, a staged warp
+      // writes one whole 512-byte row per instruction
+      float4* dst = reinterpret_cast<float4*>(&sm.stage[row * 132 + col0]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_float4(__uint_as_float(v[4 * j]) * unscale, __uint_as_float(v[4 * j + 1]) * unscale,
-                               __uint_as_float(v[4 * j + 2]) * unscale, __uint_as_float(v[4 * j + 3]) * unscale);
-      }
+      for (int j = 0; j < 4; ++j)
+        dst[j] = make_float4(__uint_as_float(v[4 * j]) * unscale, __uint_as_float(v[4 * j + 1]) * unscale,
+                             __uint_as_float(v[4 * j + 2]) * unscale, __uint_as_float(v[4 * j + 3]) * unscale);
     }
     tc05::fence_before_sync();
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");  // every accumulator read has completed before the next tile's first MMA is triggered
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");  // tile staged (and every accumulator read has completed)
+#pragma unroll 4
+    for (int k = tid; k < kFRows * (kE / 4); k += 256) {
+      const int r = k >> 5, c4 = k & 31;
+      if (m0 + r < row_hi)
+        reinterpret_cast<float4*>(Y + (m0 + r) * kE)[c4] = *reinterpret_cast<const float4*>(&sm.stage[r * 132 + c4 * 4]);
+    }
+    // (the next tile's epilogue writes `stage` only after bar_mma, i.e. after every thread has arrived on bar_a behind this loop)
   }
   if (!(amax < kPtMax)) atomicOr(status, RRNCO_DEV_NAN_LOGITS);
   tc05::fence_before_sync();
