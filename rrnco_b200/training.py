@@ -55,12 +55,13 @@ def iter_decode_inputs(decoder, env, td, actions: torch.Tensor, num_starts: int,
         cur, first, state, mask = [], [], [], []
         with torch.no_grad():   # not held across the yield: the consumer builds its graph in between
             for t in range(t0 + 1, t1 + 1):
-                cur.append(roll["current_node"].reshape(-1).clone())
-                mask.append(roll["action_mask"].clone())
+                # no copies: every env step hands out freshly allocated state tensors (envs.py `_step`), nothing is updated in place
+                cur.append(roll["current_node"].reshape(-1))
+                mask.append(roll["action_mask"])
                 if name == "atsp":
-                    first.append(roll["first_node"].reshape(-1).clone())
+                    first.append(roll["first_node"].reshape(-1))
                 else:
-                    state.append(decoder._ctx_state(roll).clone())
+                    state.append(decoder._ctx_state(roll))
                 roll.set("action", actions[:, t].contiguous())
                 roll = env.step(roll)["next"]
             out = {"current_node": torch.stack(cur), "action_mask": torch.stack(mask)}
