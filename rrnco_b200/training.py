@@ -6,15 +6,21 @@ The fused rollout kernel is forward-only.  Upstream's training step (`rrnco/mode
   1. actions are sampled by `RRNetPolicy.forward(..., phase="train")` on the fused kernel (no graph);
   2. `replay_log_likelihood` re-evaluates log pi(a_t | s_t) for those actions with autograd:
      a) the env is replayed on the CUDA step kernels (no graph) to collect the decoder inputs of every step - current /
-        first node, state scalars, action mask (`collect_decode_inputs`);
-     b) because the actions are known, ALL decode steps are evaluated at once as dense batched torch ops
+        first node, state scalars, action mask (`iter_decode_inputs`, a generator consumed chunk by chunk);
+     b) because the actions are known, ALL decode steps are evaluated at once, one row per (rollout, step)
         (`batched_logprobs`: context projection, 8-head masked attention, FFN + residual, pointer logits, scale-adaptive
         bias, tanh clip, mask, log-softmax; decoder.py:151-206,281-326, decoding.py:311-361) instead of upstream's T
-        sequential small-kernel steps; autograd gives the gradients (cuBLAS / ATen: library code, like the encoder).
+        sequential small-kernel steps.  On CUDA tensors those rows go through the hand-written kernels of
+        librrnco_b200_train.so, forward AND backward (`train_ops.py`: context query as a table gather, attention on the CUDA
+        cores with mma.sync row sums, tcgen05 FFN with a relu bit mask and an X^T Y weight-gradient kernel, tcgen05 pointer
+        scores + a one-pass tail that leaves the Jacobian); torch keeps the autograd graph and the two tiny per-instance
+        projections.  `REPLAY_IMPL = "aten"` (and any CPU tensor, bf16 autocast, N > 102) selects the same math as plain
+        torch ops.
   3. `pomo_shared_baseline_loss` = rl4co REINFORCE with the shared (POMO) baseline [rl4co-recalled], rl.py:119-128.
 
-`batched_logprobs` is device-agnostic torch and is checked against the oracle's per-step decoder on the CPU; the
-replay-vs-kernel agreement (log-likelihood of the fused kernel's evaluate mode) is checked on the GPU.
+The plain-torch form is checked against the oracle's per-step decoder on the CPU (tests/test_training_handoff.py); the kernels
+against fp64 torch op by op and against the plain-torch form on sampled rollouts, and the replay against the log-likelihood of
+the sampling kernel itself, on the GPU (tests/test_train_ops.py, tests/test_gpu_parity.py).
 """
 from __future__ import annotations
 
