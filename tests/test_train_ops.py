@@ -36,6 +36,21 @@ def test_train_ops_reject_cpu_tensors():
         train_ops.fused_ffn(x, torch.zeros(512, 128), torch.zeros(512), torch.zeros(128, 512), torch.zeros(128))
 
 
+def test_pow2_scale_is_an_exact_power_of_two_in_range():
+    """The pre-split scale of a gradient operand: 2^k with max|t| * factor * 2^k in (target / 2, target] - exactly undone in the
+    kernels' epilogues, whatever the magnitude (gradients of a REINFORCE step are 1e-6 .. 1e-9)."""
+    from rrnco_b200 import train_ops
+    for mag in (3e-9, 1e-6, 0.37, 1.0, 512.0, 7e4):
+        t = torch.tensor([[-0.2 * mag, mag], [0.5 * mag, -0.9 * mag]])
+        for factor in (None, 5.6):
+            s = float(train_ops.pow2_scale(t, bound_factor=factor))
+            m, e = torch.frexp(torch.tensor(s))
+            assert float(m) == 0.5, s                                   # a power of two
+            top = mag * (factor or 1.0) * s
+            assert 256.0 < top <= 512.0 * (1 + 1e-6), (mag, factor, s, top)
+    assert float(train_ops.pow2_scale(torch.zeros(4))) > 0              # an all-zero gradient does not divide by zero
+
+
 def _rel(a, b):
     return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-300)).item()
 
