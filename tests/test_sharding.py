@@ -53,3 +53,40 @@ def test_gloo_two_ranks_shard_and_gather(tmp_path, n_items):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), n_items, str(tmp_path)), nprocs=world, join=True)
     assert all(torch.load(os.path.join(tmp_path, f"ok{r}.pt")) for r in range(world))
+
+
+def _grad_worker(rank, world, port, n_items, out_dir):
+    """Two ranks, shards of different sizes: REINFORCE gradients of the shards, all-reduced, equal the single-process gradient."""
+    from rrnco_b200.sharding import allreduce_gradients, shard_range
+    from rrnco_b200.training import pomo_shared_baseline_loss
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    S = 5
+    g = torch.Generator().manual_seed(0)
+    feats = torch.randn(S, n_items, 7, generator=g)          # [starts, instances, features] (r = s * n_inst + b order)
+    reward = torch.randn(S, n_items, generator=g)
+
+    def model():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(7, 4), torch.nn.Tanh(), torch.nn.Linear(4, 1))
+
+    def backward(net, lo, hi):
+        ll = net(feats[:, lo:hi]).squeeze(-1)                  # stand-in log-likelihoods with a graph to the parameters
+        pomo_shared_baseline_loss(reward[:, lo:hi].reshape(-1), ll.reshape(-1), S).backward()
+
+    ref = model()
+    backward(ref, 0, n_items)
+    net = model()
+    lo, hi = shard_range(n_items, rank, world)
+    backward(net, lo, hi)
+    allreduce_gradients(net.parameters(), hi - lo, n_items)
+    ok = all(torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-7) for p, q in zip(net.parameters(), ref.parameters()))
+    torch.save(ok, os.path.join(out_dir, f"gok{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [8, 9])
+def test_gloo_two_ranks_gradient_allreduce(tmp_path, n_items):
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), n_items, str(tmp_path)), nprocs=world, join=True)
+    assert all(torch.load(os.path.join(tmp_path, f"gok{r}.pt")) for r in range(world))
